@@ -1,0 +1,288 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE'S OWN PYTHON CODE (build container only).
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py
+
+The reference (/root/reference, read-only) has no tests or golden vectors, so
+parity is pinned by executing its unmodified `layers` / `utils.calc_performance` code on seeded
+synthetic inputs (fdt_b200.synth) under torch CPU, and storing inputs-by-seed (+ sha256 digest),
+or small inputs verbatim, together with the reference outputs.
+
+Harness-side shims only (the reference is never edited):
+  * torch.Tensor.cuda = identity   (match_* call .cuda() on CPU tensors, box_utils.py:139-143,198-200)
+  * the tracker loop lives under `if __name__ == '__main__'` behind weights + a video, so
+    iouTracke_cal.py:126-155,174-176 is restated verbatim around the reference's importable
+    utils.calc_performance.calculate_iou.
+"""
+import os
+import sys
+import warnings
+
+sys.dont_write_bytecode = True
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+warnings.filterwarnings("ignore")
+
+import numpy as np
+import torch
+
+torch.Tensor.cuda = lambda self, *a, **k: self      # shim (1)
+torch.set_num_threads(8)
+
+from layers import Detect, PriorBoxLayer, MultiBoxLoss                    # noqa: E402  (reference)
+from layers import box_utils as ref_bu                                    # noqa: E402  (reference)
+from utils.calc_performance import calculate_iou as ref_iou_np            # noqa: E402  (reference)
+
+from fdt_b200 import synth                                                # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+VAR = [0.1, 0.2]
+
+
+def save(name, **kw):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **kw)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KB")
+
+
+def ref_priors(width, height, strides=synth.STRIDES6, boxes=synth.BOXES6, **kw):
+    layer = PriorBoxLayer(width, height, stride=strides, box=boxes, **kw)
+    return torch.cat([layer(i, fw, fh) for i, (fw, fh) in enumerate(synth.feature_maps(width, height, strides))], 0)
+
+
+# ------------------------------------------------------------------ 1. PriorBoxLayer
+def gen_priorbox():
+    d = {}
+    for tag, (w, h, st, bx) in {
+        "640x640": (640, 640, synth.STRIDES6, synth.BOXES6),
+        "1024x1024": (1024, 1024, synth.STRIDES6, synth.BOXES6),
+        "640x480": (640, 480, synth.STRIDES6, synth.BOXES6),
+        "640x640_5lvl": (640, 640, (4, 8, 16, 32, 64), (16, 32, 64, 128, 256)),      # pyramid_mb2_try3.py:144
+        "640x640_head": (640, 640, (8, 16, 32, 64, 128, 128), (16, 32, 64, 128, 256, 512)),
+    }.items():
+        p = ref_priors(w, h, st, bx).numpy()
+        d[tag + "_sha"] = np.array(synth.digest(p)); d[tag + "_n"] = np.array(p.shape[0])
+        d[tag + "_head"] = p[:64].copy(); d[tag + "_tail"] = p[-64:].copy()
+    # small config with scales and aspect ratios, stored in full
+    layer = PriorBoxLayer(96, 64, stride=(8, 16), box=(16, 40), scale=(3, 2), aspect_ratios=([2, 0.5], [3]))
+    d["ar_l0"] = layer(0, 12, 8).numpy(); d["ar_l1"] = layer(1, 6, 4).numpy()
+    save("priorbox", **d)
+
+
+# ------------------------------------------------------------------ 2. elementwise box utils
+def gen_boxutils():
+    rng = np.random.Generator(np.random.PCG64(101))
+    pri = synth.priors_numpy(160, 160)                                   # 2138 priors
+    n = pri.shape[0]
+    loc = (rng.standard_normal((n, 4)) * 0.7).astype(np.float32)
+    dec = ref_bu.decode(torch.from_numpy(loc), torch.from_numpy(pri), VAR).numpy()
+    gt = synth.gt_boxes(n, rng)[:, :4]
+    enc = ref_bu.encode(torch.from_numpy(gt), torch.from_numpy(pri), VAR).numpy()
+    pf = ref_bu.point_form(torch.from_numpy(pri)).numpy()
+    cs = ref_bu.center_size(torch.from_numpy(pf)).numpy()
+    a = synth.gt_boxes(37, rng)[:, :4]
+    inter = ref_bu.intersect(torch.from_numpy(a), torch.from_numpy(pf)).numpy()
+    iou = ref_bu.calculate_iou(torch.from_numpy(a), torch.from_numpy(pf)).numpy()
+    x = (rng.standard_normal((500, 2)) * 3).astype(np.float32)
+    lse = ref_bu.log_sum_exp(torch.from_numpy(x)).numpy()
+    a64 = rng.uniform(0, 600, (50, 2)); a64 = np.concatenate([a64, a64 + rng.uniform(5, 80, (50, 2))], 1)
+    b64 = rng.uniform(0, 600, (40, 2)); b64 = np.concatenate([b64, b64 + rng.uniform(5, 80, (40, 2))], 1)
+    iou64 = ref_iou_np(a64, b64)
+    save("boxutils", priors=pri, loc=loc, decode=dec, gt=gt, encode=enc, point_form=pf, center_size=cs,
+         a=a, intersect=inter, iou=iou, x=x, lse=lse, a64=a64, b64=b64, iou64=iou64)
+
+
+# ------------------------------------------------------------------ 3. nms
+def gen_nms():
+    d = {}
+    pri = synth.priors_numpy(640, 640)
+    for tag, seed, n, thr, topk in (("a", 7, 3000, 0.3, 5000), ("b", 8, 6000, 0.5, 5000), ("c", 9, 300, 0.35, 200)):
+        rng = np.random.Generator(np.random.PCG64(seed))
+        sel = np.sort(rng.permutation(25600 + 6400)[:n])
+        loc = (rng.standard_normal((n, 4)) * 0.5).astype(np.float32)
+        boxes = ref_bu.decode(torch.from_numpy(loc), torch.from_numpy(pri[sel]), VAR).numpy()
+        scores = np.unique(rng.uniform(0.05, 1, 2 * n).astype(np.float32))
+        scores = rng.permutation(scores)[:n].copy()
+        keep, count = ref_bu.nms(torch.from_numpy(boxes), torch.from_numpy(scores), thr, topk)
+        d.update({f"{tag}_boxes": boxes, f"{tag}_scores": scores, f"{tag}_thr": np.float32(thr), f"{tag}_topk": np.int64(topk),
+                  f"{tag}_keep": keep.numpy()[:count].astype(np.int32), f"{tag}_count": np.int64(count)})
+        print("  nms", tag, "kept", count, "of", n)
+    save("nms", **d)
+
+
+# ------------------------------------------------------------------ 4. Detect
+def ref_detect_aux(det, loc, conf, pri):
+    """Reference Detect output + kept prior indices (recomputed with the reference's own pieces)."""
+    out = det(loc, conf, pri)
+    B = loc.shape[0]
+    kept = -np.ones((B, det.num_classes, det.top_k), np.int64)
+    counts = np.zeros((B, det.num_classes), np.int32)
+    for i in range(B):
+        boxes = ref_bu.decode(loc[i], pri, det.variance)
+        for cl in range(1, det.num_classes):
+            m = conf[i, :, cl].gt(det.conf_thresh)
+            nz = m.nonzero().squeeze()
+            sc = conf[i, :, cl][nz]
+            if sc.dim() == 0:
+                continue
+            bx = boxes[m.unsqueeze(1).expand_as(boxes)].view(-1, 4)
+            ids, c = ref_bu.nms(bx, sc, det.nms_thresh, min(bx.shape[0], det.nms_top_k))
+            c = min(c, det.top_k)
+            kept[i, cl, :c] = nz[ids[:c]].numpy(); counts[i, cl] = c
+            assert torch.equal(out[i, cl, :c, 0], sc[ids[:c]])
+    return out.numpy(), counts, kept
+
+
+def gen_detect():
+    d = {}
+    # (a) config 1: one 640x640 image, N = 34,125, Detect(2,0,750,0.05,0.3)   [inputs by seed]
+    pri = ref_priors(640, 640)
+    assert np.array_equal(pri.numpy(), synth.priors_numpy(640, 640))
+    for tag, mode, seed, B in (("cfg1", "random", 20261, 1), ("clustered", "clustered", 20262, 2)):
+        loc, conf = synth.detect_inputs(B, pri.numpy(), seed, 0.05, mode)
+        det = Detect(2, 0, 750, 0.05, 0.3)
+        out, counts, kept = ref_detect_aux(det, torch.from_numpy(loc), torch.from_numpy(conf), pri)
+        print("  detect", tag, "counts", counts[:, 1], "candidates", (conf[..., 1] > 0.05).sum(1))
+        d.update({f"{tag}_seed": np.int64(seed), f"{tag}_B": np.int64(B), f"{tag}_mode": np.array(mode),
+                  f"{tag}_in_sha": np.array(synth.digest(loc, conf)), f"{tag}_out": out, f"{tag}_counts": counts,
+                  f"{tag}_kept": kept.astype(np.int32)})
+    # (b) small: head-branch-sized prior set, production thresholds, quirk images   [inputs stored]
+    pri_s = ref_priors(160, 160)
+    loc, conf = synth.detect_inputs(4, pri_s.numpy(), 5, 0.3, "random")
+    conf[1, :, 1] = 0.01; conf[1, 777, 1] = 0.9            # Q2: exactly one candidate -> no detection
+    conf[2, :, 1] = 0.2                                     # zero candidates
+    conf[..., 0] = 1 - conf[..., 1]
+    det = Detect(2, 0, 750, 0.3, 0.5)                       # pyramid.py:198
+    out, counts, kept = ref_detect_aux(det, torch.from_numpy(loc), torch.from_numpy(conf), pri_s)
+    print("  detect small counts", counts[:, 1])
+    d.update(small_loc=loc, small_conf=conf, small_priors=pri_s.numpy(), small_out=out, small_counts=counts,
+             small_kept=kept.astype(np.int32))
+    save("detect", **d)
+
+
+# ------------------------------------------------------------------ 5. match / MultiBoxLoss
+def ref_match(bipartite, thr, truth, pri, labels):
+    N = pri.shape[0]
+    loc_t = torch.zeros(1, N, 4); conf_t = torch.zeros(1, N, dtype=torch.long)
+    fn = ref_bu.match_ensure_max_prior if bipartite else ref_bu.match_default
+    fn(thr, truth, pri, VAR, labels, loc_t, conf_t, 0)
+    bti = ref_bu.calculate_iou(truth, ref_bu.point_form(pri)).max(0)[1]
+    return loc_t[0].numpy(), conf_t[0].numpy(), bti.numpy()
+
+
+def ref_mining(crit, loc, conf, pri, targets):
+    """multibox_loss.py:65-116 restated around the reference's match_* and log_sum_exp to expose
+    conf_t / loss_c / neg (forward() only returns two scalars)."""
+    B, N, _ = loc.shape
+    loc_t = torch.Tensor(B, N, 4); conf_t = torch.LongTensor(B, N)
+    fn = ref_bu.match_ensure_max_prior if crit.bipartite else ref_bu.match_default
+    for i in range(B):
+        fn(crit.threshold, targets[i][:, :-1], pri, crit.variance, targets[i][:, -1], loc_t, conf_t, i)
+    pos = conf_t > 0
+    bc = conf.view(-1, crit.num_classes)
+    loss_c = ref_bu.log_sum_exp(bc) - bc.gather(1, conf_t.view(-1, 1))
+    loss_c = loss_c.view(B, -1); loss_c[pos] = 0
+    _, li = loss_c.sort(1, descending=True); _, rank = li.sort(1)
+    num_neg = torch.clamp(crit.negpos_ratio * pos.long().sum(1, keepdim=True), max=pos.size(1) - 1)
+    neg = rank < num_neg.expand_as(rank)
+    # tie audit: the selected set is order-independent iff the boundary value is not duplicated
+    for i in range(B):
+        k = int(num_neg[i])
+        if 0 < k < N:
+            srt = loss_c[i].sort(descending=True)[0]
+            assert srt[k - 1] != srt[k], "mining boundary tie in golden input; change the seed"
+    return loc_t.numpy(), conf_t.numpy(), loss_c.numpy(), neg.numpy()
+
+
+def gen_multibox():
+    d = {}
+    pri_s = ref_priors(160, 160)
+    rng = np.random.Generator(np.random.PCG64(303))
+    for tag, G in (("g1", 1), ("g7", 7), ("g60", 60)):
+        gt = synth.gt_boxes(G, rng)
+        for bip in (0, 1):
+            lt, ct, bti = ref_match(bip, 0.35, torch.from_numpy(gt[:, :4]), pri_s, torch.from_numpy(gt[:, 4]))
+            d.update({f"{tag}_gt": gt, f"{tag}_b{bip}_loc_t": lt, f"{tag}_b{bip}_conf_t": ct.astype(np.int8),
+                      f"{tag}_b{bip}_bti": bti.astype(np.int16)})
+    d["small_priors"] = pri_s.numpy()
+    # full forward, small
+    loc, conf, targets = synth.multibox_inputs(4, pri_s.numpy(), 404, 1, 20)
+    for bip in (0, 1):
+        crit = MultiBoxLoss(2, 0.35, True, 0, True, 3, 0.35, False, bipartite=bool(bip), use_gpu=False)
+        tl = [torch.from_numpy(t) for t in targets]
+        ll, lc = crit((torch.from_numpy(loc), torch.from_numpy(conf), pri_s), tl)
+        lt, ct, lca, neg = ref_mining(crit, torch.from_numpy(loc), torch.from_numpy(conf), pri_s, tl)
+        d.update({f"fwd_b{bip}_loss": np.array([float(ll), float(lc)], np.float64), f"fwd_b{bip}_conf_t": ct.astype(np.int8),
+                  f"fwd_b{bip}_neg": np.packbits(neg), f"fwd_b{bip}_loss_c_all": lca, f"fwd_b{bip}_loc_t": lt})
+        print("  multibox small bip", bip, float(ll), float(lc), "pos", int((ct > 0).sum()), "neg", int(neg.sum()))
+    d["fwd_seed"] = np.int64(404); d["fwd_in_sha"] = np.array(synth.digest(loc, conf, *targets))
+    # production size: B=2, N=34,125, G in [1,200]   [inputs by seed]
+    pri = ref_priors(640, 640)
+    loc, conf, targets = synth.multibox_inputs(2, pri.numpy(), 505, 1, 200)
+    crit = MultiBoxLoss(2, 0.35, True, 0, True, 3, 0.35, False, bipartite=False, use_gpu=False)   # MyTrain_repo.py:105-114
+    tl = [torch.from_numpy(t) for t in targets]
+    ll, lc = crit((torch.from_numpy(loc), torch.from_numpy(conf), pri), tl)
+    lt, ct, lca, neg = ref_mining(crit, torch.from_numpy(loc), torch.from_numpy(conf), pri, tl)
+    bti = np.stack([ref_bu.calculate_iou(t[:, :4], ref_bu.point_form(pri)).max(0)[1].numpy() for t in tl])
+    d.update(big_seed=np.int64(505), big_in_sha=np.array(synth.digest(loc, conf, *targets)),
+             big_loss=np.array([float(ll), float(lc)], np.float64), big_conf_t=ct.astype(np.int8),
+             big_bti=bti.astype(np.int16), big_neg=np.packbits(neg), big_G=np.array([t.shape[0] for t in targets]))
+    print("  multibox big", float(ll), float(lc), "pos", int((ct > 0).sum()), "neg", int(neg.sum()))
+    save("multibox", **d)
+
+
+# ------------------------------------------------------------------ 6. tracker
+def ref_tracker(frames, sigma_iou=0.4, sigma_h=0.6, t_min=5):
+    """VERBATIM restatement of iouTracke_cal.py:126-155 (loop body, use_iou=True) and :174-176 (flush)
+    around the reference's utils.calc_performance.calculate_iou."""
+    frame_num = 0
+    tracks_active = []
+    tracks_finished = []
+    for det0 in frames:
+        frame_num += 1
+        dets = det0.tolist()
+        updated_tracks = []
+        for track in tracks_active:
+            if len(dets) > 0:
+                iou = ref_iou_np(np.array(dets)[:, :4], np.array([track['bboxes'][-1]]))
+                best_match = iou.argmax()
+                matched = iou[best_match] > sigma_iou
+                if matched:
+                    track['bboxes'].append(dets[best_match][:4])
+                    track['max_score'] = max(track['max_score'], dets[best_match][4])
+                    updated_tracks.append(track)
+                    del dets[best_match]
+                else:
+                    if track['max_score'] > sigma_h and len(track['bboxes']) > t_min:
+                        tracks_finished.append(track)
+        new_tracks = [{'bboxes': [det[:4], ], 'max_score': det[4], 'start_frame': frame_num} for det in dets]
+        tracks_active = updated_tracks + new_tracks
+    tracks_finished += [track for track in tracks_active
+                        if track['max_score'] > sigma_h and len(track['bboxes']) >= t_min]
+    return tracks_finished
+
+
+def gen_tracker():
+    d = {}
+    for tag, kw in (("a", dict(F=400, seed=11, d_lo=1, d_hi=40, n_objects=40, empty_every=57)),
+                    ("b", dict(F=120, seed=12, d_lo=1, d_hi=300, n_objects=300, empty_every=50, sigma=4.0))):
+        frames = synth.tracker_frames(**kw)
+        if tag == "a":                      # two consecutive empty frames: dummy-vs-dummy IoU is 0/0 = NaN
+            frames[200] = np.array([[0, 0, 0, 0, 0.4]]); frames[201] = np.array([[0, 0, 0, 0, 0.4]])
+        tr = ref_tracker(frames)
+        bb = np.array([b for t in tr for b in t['bboxes']], np.float64).reshape(-1, 4)
+        d.update({f"{tag}_kw": np.array(repr(kw)), f"{tag}_in_sha": np.array(synth.digest(*frames)),
+                  f"{tag}_len": np.array([len(t['bboxes']) for t in tr], np.int64),
+                  f"{tag}_start": np.array([t['start_frame'] for t in tr], np.int64),
+                  f"{tag}_max": np.array([t['max_score'] for t in tr], np.float64), f"{tag}_bboxes": bb})
+        print("  tracker", tag, "tracks", len(tr), "boxes", bb.shape[0])
+    save("tracker", **d)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["priorbox", "boxutils", "nms", "detect", "multibox", "tracker"]
+    for w in which:
+        print("==", w)
+        globals()["gen_" + w]()
