@@ -1,0 +1,140 @@
+"""ctypes binding of csrc/libfdt_b200.so (include/fdt_b200.h).  No CPU fallback: if the library or a
+CUDA device is missing the product path raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(CSRC, "libfdt_b200.so")
+
+FDT_OK, FDT_E_INVALID, FDT_E_CUDA, FDT_E_WORKSPACE, FDT_E_UNSUPPORTED, FDT_E_DEVICE = 0, -1, -2, -3, -4, -5
+MAX_NMS_TOP_K = 8192
+
+_vp, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
+
+# symbol -> (restype, argtypes); one entry per declaration in include/fdt_b200.h
+SIGNATURES = {
+    "fdt_version": (_i, []),
+    "fdt_last_error": (C.c_char_p, []),
+    "fdt_device_check": (_i, [_i]),
+    "fdt_priorbox": (_i, [_d, _d, _d, _d, _i, _vp, _i, _vp, _i, _i, _vp, _vp]),
+    "fdt_point_form": (_i, [_vp, _i64, _vp, _vp]),
+    "fdt_center_size": (_i, [_vp, _i64, _vp, _vp]),
+    "fdt_intersect": (_i, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "fdt_calculate_iou": (_i, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "fdt_calculate_iou_f64": (_i, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "fdt_encode": (_i, [_vp, _vp, _i64, _f, _f, _vp, _vp]),
+    "fdt_decode": (_i, [_vp, _vp, _i64, _f, _f, _vp, _vp]),
+    "fdt_log_sum_exp": (_i, [_vp, _i64, _i, _vp, _vp, _sz, _vp]),
+    "fdt_nms_workspace_bytes": (_sz, [_i64]),
+    "fdt_nms": (_i, [_vp, _vp, _i64, _f, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "fdt_detect_workspace_bytes": (_sz, [_i, _i64, _i]),
+    "fdt_detect": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "fdt_detect_threshold_compact": (_i, [_vp, _i, _i64, _i, _f, _vp, _sz, _vp]),
+    "fdt_detect_sort_nms": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "fdt_detect_candidate_counts": (_i, [_vp, _i, _i, _vp, _vp]),
+    "fdt_ctx_create": (_i, [_i, C.POINTER(_vp)]),
+    "fdt_ctx_destroy": (_i, [_vp]),
+    "fdt_detect_host": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp]),
+    "fdt_match_workspace_bytes": (_sz, [_i, _i64, _i64]),
+    "fdt_match_encode": (_i, [_vp, _vp, _vp, _i, _i64, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "fdt_mine_workspace_bytes": (_sz, [_i, _i64]),
+    "fdt_hard_negative_mine": (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp, _sz, _vp]),
+    "fdt_multibox_workspace_bytes": (_sz, [_i, _i64, _i, _i64]),
+    "fdt_multibox_loss_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _f, _i, _i, _f, _f,
+                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "fdt_multibox_loss_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i64, _i, _vp, _vp, _vp]),
+    "fdt_iou_track_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "fdt_iou_track": (_i, [_vp, _vp, _i64, _i64, _i64, _d, _d, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libfdt_b200.so for sm_100a (csrc/Makefile; nvcc cross-compiles without a GPU)."""
+    env = dict(os.environ)
+    r = subprocess.run(["make", "-C", CSRC, "-j8", "libfdt_b200.so"], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError("building libfdt_b200.so failed")
+    return SO_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(SO_PATH):
+                    raise RuntimeError(
+                        f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(fdt_b200 has no CPU fallback)")
+                l = C.CDLL(SO_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(l, name)          # AttributeError here = stale .so; rebuild
+                    fn.restype, fn.argtypes = res, args
+                _lib = l
+    return _lib
+
+
+def last_error() -> str:
+    return lib().fdt_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc == FDT_OK:
+        return
+    msg = last_error()
+    if rc == FDT_E_INVALID:
+        raise ValueError(msg)
+    if rc == FDT_E_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(f"libfdt_b200 error {rc}: {msg}")
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("fdt_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+_workspaces = {}
+
+
+def workspace(nbytes: int, device: torch.device, tag: str = "") -> torch.Tensor:
+    """Grow-only scratch buffer per (device, stream, tag); torch's caching allocator returns 512-byte
+    aligned blocks, which satisfies the library's 256-byte requirement."""
+    key = (device.index, stream_ptr(), tag)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def dev_f32(t: torch.Tensor, device: torch.device) -> torch.Tensor:
+    """fp32, contiguous, on `device`, 16-byte aligned."""
+    t = t.detach()
+    if t.dtype != torch.float32 or t.device != device or not t.is_contiguous():
+        t = t.to(device=device, dtype=torch.float32).contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t

@@ -1,0 +1,85 @@
+"""Detect -- drop-in for layers/functions/detection.py:9-84 on hand-written sm_100a kernels."""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import torch
+
+from ... import _lib
+from ...data import face as cfg
+
+_host_ctx = threading.local()
+
+
+def _ctx(device_index: int):
+    """One fdt_ctx (stream + device staging buffers) per host thread and device."""
+    d = getattr(_host_ctx, "ctx", None)
+    if d is None:
+        d = _host_ctx.ctx = {}
+    if device_index not in d:
+        h = C.c_void_p()
+        _lib.check(_lib.lib().fdt_ctx_create(device_index, C.byref(h)))
+        d[device_index] = h
+    return d[device_index]
+
+
+class Detect:
+    """At test time, Detect is the final layer of SSD: decode, threshold, top-k, NMS (detection.py:9-14).
+
+    Same constructor, attributes and call signature as the reference.  CUDA inputs are processed in
+    place on the current stream (asynchronous, CUDA-graph capturable) and the result is a CUDA tensor;
+    CPU inputs go through fdt_detect_host (H2D copy, kernels, D2H copy) and the result is a CPU tensor,
+    like the reference's torch.zeros(...) output on a CPU default device (detection.py:48).
+    """
+
+    def __init__(self, num_classes, bkg_label, top_k, conf_thresh, nms_thresh):
+        self.num_classes = num_classes
+        self.background_label = bkg_label
+        self.top_k = top_k
+        self.nms_thresh = nms_thresh
+        if nms_thresh <= 0:
+            raise ValueError('nms_threshold must be non negative.')      # detection.py:28-29
+        self.conf_thresh = conf_thresh
+        self.variance = cfg['variance']
+        self.nms_top_k = 5000                                            # detection.py:32
+
+    def __call__(self, loc_data, conf_data, prior_data, return_aux=False):
+        """loc_data [B,N,4] (or [B,N*4]), conf_data [B,N,C] (or [B*N,C]) post-softmax, prior_data [N,4]
+        -> output [B, num_classes, top_k, 5] rows [score, x1, y1, x2, y2].
+        return_aux=True additionally returns (counts[B,C] int32, kept_prior[B,C,top_k] int64)."""
+        _lib.require_cuda()
+        num = loc_data.size(0)
+        num_priors = prior_data.size(0)
+        C_ = self.num_classes
+        args = (num, num_priors, C_, int(self.top_k), int(self.nms_top_k), float(self.conf_thresh),
+                float(self.nms_thresh), float(self.variance[0]), float(self.variance[1]))
+        if not loc_data.is_cuda:
+            return self._call_host(loc_data, conf_data, prior_data, args, return_aux)
+        dev = loc_data.device
+        with torch.cuda.device(dev):
+            loc = _lib.dev_f32(loc_data, dev).view(num, num_priors, 4)
+            conf = _lib.dev_f32(conf_data, dev).view(num, num_priors, C_)
+            pri = _lib.dev_f32(prior_data, dev).view(num_priors, 4)
+            out = torch.empty((num, C_, self.top_k, 5), dtype=torch.float32, device=dev)
+            counts = torch.empty((num, C_), dtype=torch.int32, device=dev) if return_aux else None
+            kept = torch.empty((num, C_, self.top_k), dtype=torch.int64, device=dev) if return_aux else None
+            L = _lib.lib()
+            nbytes = L.fdt_detect_workspace_bytes(num, num_priors, C_)
+            ws = _lib.workspace(nbytes, dev, "detect")
+            _lib.check(L.fdt_detect(_lib.ptr(loc), _lib.ptr(conf), _lib.ptr(pri), *args, _lib.ptr(out),
+                                    _lib.ptr(counts), _lib.ptr(kept), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        return (out, counts, kept) if return_aux else out
+
+    def _call_host(self, loc_data, conf_data, prior_data, args, return_aux):
+        num, num_priors, C_ = args[0], args[1], args[2]
+        loc = loc_data.detach().to(torch.float32).contiguous()
+        conf = conf_data.detach().to(torch.float32).contiguous()
+        pri = prior_data.detach().to(torch.float32).contiguous().cpu()
+        out = torch.empty((num, C_, self.top_k, 5), dtype=torch.float32, pin_memory=True)
+        counts = torch.empty((num, C_), dtype=torch.int32) if return_aux else None
+        kept = torch.empty((num, C_, self.top_k), dtype=torch.int64) if return_aux else None
+        ctx = _ctx(torch.cuda.current_device())
+        _lib.check(_lib.lib().fdt_detect_host(ctx, _lib.ptr(loc), _lib.ptr(conf), _lib.ptr(pri), *args,
+                                              _lib.ptr(out), _lib.ptr(counts), _lib.ptr(kept)))
+        return (out, counts, kept) if return_aux else out

@@ -1,0 +1,165 @@
+/*
+ * fdt_b200.h -- C ABI of libfdt_b200.so: the B200 (sm_100a) SSD box pipeline.
+ *
+ * The reference (limacv/Face-detection-and-tracking) is pure Python and has NO FFI; its boundary
+ * for this path is the Python call signatures of `layers`.  Each entry point
+ * below names the reference function it replaces (file:line relative to the reference root); the
+ * Python modules in face-detection-and-tracking_b200/ keep those signatures and call these symbols
+ * through ctypes.  INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer owned by the caller unless the
+ *     parameter is documented as host (`_h` suffix or "host");
+ *   - the library allocates nothing on the device-pointer entry points: scratch comes from a caller
+ *     workspace sized by the matching *_workspace_bytes(); 256-byte alignment is required;
+ *   - every launch goes to `stream` (a cudaStream_t passed as void*), asynchronously; calls are
+ *     reentrant across streams with distinct workspaces and CUDA-graph capturable;
+ *   - returns FDT_OK or a negative FDT_E_* code; fdt_last_error() gives the thread-local message;
+ *     no exceptions, no exit(), no CPU fallback.
+ *   - fp32 arithmetic is IEEE in the reference's operand order with FMA contraction off
+ *     (-fmad=false); exp/log are evaluated in fp64 and rounded once to fp32.
+ */
+#ifndef FDT_B200_H
+#define FDT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDT_OK             0
+#define FDT_E_INVALID     -1   /* bad argument (null pointer, negative size, misaligned buffer) */
+#define FDT_E_CUDA        -2   /* CUDA runtime error; message carries cudaGetErrorString */
+#define FDT_E_WORKSPACE   -3   /* workspace smaller than *_workspace_bytes() */
+#define FDT_E_UNSUPPORTED -4   /* size outside the kernel limits (see each function) */
+#define FDT_E_DEVICE      -5   /* device is not sm_100 (B200) */
+
+#define FDT_MAX_NMS_TOP_K  8192   /* candidates sorted + held in shared memory per image/class */
+
+typedef void *fdt_stream_t;        /* cudaStream_t */
+typedef struct fdt_ctx fdt_ctx;    /* host-buffer context: owns a stream, device + pinned staging buffers */
+
+int         fdt_version(void);
+const char *fdt_last_error(void);
+/* FDT_OK iff `device` exists and is compute capability 10.0 (the only target this library is built for). */
+int         fdt_device_check(int device);
+
+/* ---- P1  PriorBoxLayer.__call__  (layers/functions/prior_box.py:28-44) --------------------------
+ * One pyramid level -> out[f_h*f_w*n_scales*(1+n_ar), 4] = [cx,cy,w,h], y outer / x inner.
+ * box_scale_h[n_scales] = (2**(1/3))**s and sqrt_ar_h[n_ar] = sqrt(ar) are HOST arrays evaluated by the
+ * caller in python-float arithmetic (prior_box.py:33,41); fp64 on device, one rounding to fp32. */
+int fdt_priorbox(double width, double height, double stride, double box,
+                 int n_scales, const double *box_scale_h, int n_ar, const double *sqrt_ar_h,
+                 int f_w, int f_h, float *out, fdt_stream_t stream);
+
+/* ---- M1  point_form / center_size  (layers/box_utils.py:7-16, 19-28) ---------------------------- */
+int fdt_point_form(const float *boxes, int64_t n, float *out, fdt_stream_t stream);
+int fdt_center_size(const float *boxes, int64_t n, float *out, fdt_stream_t stream);
+
+/* ---- M2/M3  intersect / calculate_iou  (layers/box_utils.py:31-67, 70-100) -> out[A,B] fp32 ------ */
+int fdt_intersect(const float *box_a, int64_t A, const float *box_b, int64_t B, float *out, fdt_stream_t stream);
+int fdt_calculate_iou(const float *box_a, int64_t A, const float *box_b, int64_t B, float *out, fdt_stream_t stream);
+/* ---- T1  utils.calc_performance.calculate_iou (utils/calc_performance.py:54-74), float64 -------- */
+int fdt_calculate_iou_f64(const double *box_a, int64_t A, const double *box_b, int64_t B, double *out, fdt_stream_t stream);
+
+/* ---- M6 / D1  encode / decode  (layers/box_utils.py:213-234, 238-258) --------------------------- */
+int fdt_encode(const float *matched, const float *priors, int64_t n, float var0, float var1, float *out, fdt_stream_t stream);
+int fdt_decode(const float *loc, const float *priors, int64_t n, float var0, float var1, float *out, fdt_stream_t stream);
+
+/* ---- L1  log_sum_exp  (layers/box_utils.py:261-269): x[R,C] -> out[R]; global max as the reference.
+ * workspace: 256 bytes. */
+int fdt_log_sum_exp(const float *x, int64_t R, int C, float *out, void *ws, size_t ws_bytes, fdt_stream_t stream);
+
+/* ---- N1  nms  (layers/box_utils.py:275-340) ------------------------------------------------------
+ * boxes[n,4], scores[n] -> keep[n] int64 zero-padded (indices into the input, descending score),
+ * *count (device int64).  Sort ties: higher index first.  Limits: min(n, top_k) <= FDT_MAX_NMS_TOP_K
+ * (top_k <= 0 means n, as idx[-0:] does) and min(n, top_k) <= 5000 when run to completion. */
+size_t fdt_nms_workspace_bytes(int64_t n);
+int fdt_nms(const float *boxes, const float *scores, int64_t n, float overlap, int64_t top_k,
+            int64_t *keep, int64_t *count, void *ws, size_t ws_bytes, fdt_stream_t stream);
+
+/* ---- D3  Detect.__call__  (layers/functions/detection.py:34-84) ---------------------------------
+ * loc[B,N,4], conf[B,N,C] (post-softmax), priors[N,4] -> out[B,C,top_k,5] rows [score,x1,y1,x2,y2]
+ * in keep order, zero padded; class-0 plane zero.  Optional: counts[B,C] int32 rows written;
+ * kept_prior[B,C,top_k] int64 prior index per row (-1 padding).  Candidates: score > conf_thresh
+ * (strict); exactly one candidate yields no detection (reference quirk, detection.py:66-72).
+ * Limits: 1 <= nms_top_k <= FDT_MAX_NMS_TOP_K, 1 <= top_k <= nms_top_k ... see DESIGN.md. */
+size_t fdt_detect_workspace_bytes(int B, int64_t N, int C);
+int fdt_detect(const float *loc, const float *conf, const float *priors,
+               int B, int64_t N, int C, int top_k, int nms_top_k,
+               float conf_thresh, float nms_thresh, float var0, float var1,
+               float *out, int32_t *counts, int64_t *kept_prior,
+               void *ws, size_t ws_bytes, fdt_stream_t stream);
+
+/* Stage entry points (same workspace, same semantics; fdt_detect == stage 1 then stage 2).  They let
+ * tests and bench.py check / time the two kernels separately:
+ *   stage 1  K2 threshold + compaction: conf -> per-(image,class) candidate keys + counts in `ws`
+ *   stage 2  K3 select/sort + decode + NMS + output rows, consuming `ws` */
+int fdt_detect_threshold_compact(const float *conf, int B, int64_t N, int C, float conf_thresh,
+                                 void *ws, size_t ws_bytes, fdt_stream_t stream);
+int fdt_detect_sort_nms(const float *loc, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
+                        float nms_thresh, float var0, float var1,
+                        float *out, int32_t *counts, int64_t *kept_prior,
+                        void *ws, size_t ws_bytes, fdt_stream_t stream);
+/* Number of candidates per (image, class>=1) list after stage 1: copies B*(C-1) int32 to counts_out (device). */
+int fdt_detect_candidate_counts(const void *ws, int B, int C, int32_t *counts_out, fdt_stream_t stream);
+
+/* ---- host-buffer variants (the reference-facing call when tensors live on the CPU) --------------
+ * All pointers are HOST pointers (pinned memory makes the copies asynchronous).  The context owns
+ * the stream and grows its device buffers on demand; one context per host thread. */
+int fdt_ctx_create(int device, fdt_ctx **ctx);
+int fdt_ctx_destroy(fdt_ctx *ctx);
+int fdt_detect_host(fdt_ctx *ctx, const float *loc_h, const float *conf_h, const float *priors_h,
+                    int B, int64_t N, int C, int top_k, int nms_top_k,
+                    float conf_thresh, float nms_thresh, float var0, float var1,
+                    float *out_h, int32_t *counts_h, int64_t *kept_prior_h);
+
+/* ---- M4/M5  match_default / match_ensure_max_prior (layers/box_utils.py:165-210, 103-162) -------
+ * Batched over images: gt[total,5] rows [x1,y1,x2,y2,label], gt_off[B+1] int64 (device).
+ * -> loc_t[B,N,4], conf_t[B,N] int64; optional best_truth_idx[B,N] int32, best_truth_overlap[B,N].
+ * Images with zero GT (the reference raises) are defined as all-background, loc_t = 0. */
+size_t fdt_match_workspace_bytes(int B, int64_t N, int64_t total_gt);
+int fdt_match_encode(const float *priors, const float *gt, const int64_t *gt_off, int B, int64_t N,
+                     float threshold, float var0, float var1, int bipartite,
+                     float *loc_t, int64_t *conf_t, int32_t *best_truth_idx, float *best_truth_overlap,
+                     void *ws, size_t ws_bytes, fdt_stream_t stream);
+
+/* ---- L2  hard-negative mining  (layers/modules/multibox_loss.py:112-116) -------------------------
+ * loss_c[B,N] (zero at positives), pos[B,N] uint8 -> neg[B,N] uint8 = rank < min(ratio*num_pos, N-1).
+ * Ties at the boundary: lower prior index first (stable descending). */
+size_t fdt_mine_workspace_bytes(int B, int64_t N);
+int fdt_hard_negative_mine(const float *loss_c, const uint8_t *pos, int B, int64_t N, int negpos_ratio,
+                           uint8_t *neg, void *ws, size_t ws_bytes, fdt_stream_t stream);
+
+/* ---- L2  MultiBoxLoss.forward / backward  (layers/modules/multibox_loss.py:48-136) ---------------
+ * forward: match+encode, smooth-L1 over positives, per-prior CE, mining, CE over pos U neg.
+ * losses[2] (device) = {loss_l/N, loss_c/N}; norm[1] (device) = N.  loc_t/conf_t/sel are outputs the
+ * backward pass reuses (sel[B,N] uint8 = pos | neg).
+ * backward: grad_loc[B,N,4], grad_conf[B,N,C] for upstream gradients g_l, g_c (host scalars). */
+size_t fdt_multibox_workspace_bytes(int B, int64_t N, int C, int64_t total_gt);
+int fdt_multibox_loss_forward(const float *loc, const float *conf, const float *priors,
+                              const float *gt, const int64_t *gt_off, int B, int64_t N, int C,
+                              float threshold, int negpos_ratio, int bipartite, float var0, float var1,
+                              float *losses, float *norm, float *loc_t, int64_t *conf_t, uint8_t *sel,
+                              float *loss_c_all, void *ws, size_t ws_bytes, fdt_stream_t stream);
+int fdt_multibox_loss_backward(const float *loc, const float *conf, const float *loc_t, const int64_t *conf_t,
+                               const uint8_t *sel, const float *norm, float g_l, float g_c,
+                               int B, int64_t N, int C, float *grad_loc, float *grad_conf, fdt_stream_t stream);
+
+/* ---- T2  IoU tracker association  (iouTracke_cal.py:126-155 loop, :174-176 flush) ----------------
+ * dets[total,5] float64 rows [x1,y1,x2,y2,score]; frame_off[F+1] int64 (device); frames are 1-based in
+ * the output.  Outputs (device): n_tracks[1] int64; track_off[total+1] int64 CSR offsets into
+ * track_dets[total] int64 (global det rows in append order); track_start[total] int64;
+ * track_max[total] float64 -- entries [0, n_tracks) are valid, in the reference's finishing order. */
+size_t fdt_iou_track_workspace_bytes(int64_t F, int64_t total, int64_t max_dets_per_frame);
+int fdt_iou_track(const double *dets, const int64_t *frame_off, int64_t F, int64_t total, int64_t max_dets_per_frame,
+                  double sigma_iou, double sigma_h, int64_t t_min,
+                  int64_t *n_tracks, int64_t *track_off, int64_t *track_dets, int64_t *track_start, double *track_max,
+                  void *ws, size_t ws_bytes, fdt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDT_B200_H */
