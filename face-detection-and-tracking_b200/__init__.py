@@ -5,3 +5,6 @@ limacv/Face-detection-and-tracking.  Compute runs in hand-written CUDA kernels b
 `csrc/libfdt_b200.so` (include/fdt_b200.h); there is no CPU fallback.
 """
 __version__ = "0.1.0"
+
+from . import data, layers, synth, tracker  # noqa: E402,F401
+from .layers import Detect, MultiBoxLoss, PriorBoxLayer  # noqa: E402,F401

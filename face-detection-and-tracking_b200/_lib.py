@@ -43,11 +43,11 @@ SIGNATURES = {
     "fdt_ctx_destroy": (_i, [_vp]),
     "fdt_detect_host": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp]),
     "fdt_match_workspace_bytes": (_sz, [_i, _i64, _i64]),
-    "fdt_match_encode": (_i, [_vp, _vp, _vp, _i, _i64, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "fdt_match_encode": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fdt_mine_workspace_bytes": (_sz, [_i, _i64]),
     "fdt_hard_negative_mine": (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp, _sz, _vp]),
     "fdt_multibox_workspace_bytes": (_sz, [_i, _i64, _i, _i64]),
-    "fdt_multibox_loss_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _f, _i, _i, _f, _f,
+    "fdt_multibox_loss_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i64, _i, _f, _i, _i, _f, _f,
                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fdt_multibox_loss_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i64, _i, _vp, _vp, _vp]),
     "fdt_iou_track_workspace_bytes": (_sz, [_i64, _i64, _i64]),

@@ -1,9 +1,555 @@
-// placeholder until the MultiBoxLoss kernels land (next commit): keeps the ABI complete and loud.
+// MultiBoxLoss (layers/modules/multibox_loss.py:48-136): fused jaccard/argmax match + encode
+// (layers/box_utils.py:103-210), per-prior confidence loss, hard-negative mining, loss reduction and
+// the backward pass, for sm_100a.
+//
+//   k_match        one thread per (image, prior); GT boxes of the image staged through shared memory in
+//                  tiles; IoU = inter / ((area_a + area_b) - inter) exactly as calculate_iou
+//                  (box_utils.py:94-100), argmax with first-index ties (torch.max(0)), then label +
+//                  encode written straight to loc_t / conf_t -- the [G,N] overlap matrix is never
+//                  materialised.  Bipartite mode also reduces the best prior per GT (warp REDUX ->
+//                  shared -> one 64-bit atomicMax per block and GT) and a second pass applies
+//                  box_utils.py:150-154.
+//   k_loss_prior   smooth-L1 over positives (:96-101) and the mining input loss_c (:104-110).
+//   k_mine         one CTA per image: radix select of the num_neg-th largest loss (keys cached in shared
+//                  memory when the row fits), neg = rank < num_neg (:112-116), then CE over pos U neg
+//                  (:119-128).
+//   k_loss_final / k_multibox_backward.
 #include "fdt_common.cuh"
-FDT_API size_t fdt_match_workspace_bytes(int, int64_t, int64_t) { return 256; }
-FDT_API int fdt_match_encode(const float *, const float *, const int64_t *, int, int64_t, float, float, float, int, float *, int64_t *, int32_t *, float *, void *, size_t, fdt_stream_t) { fdt_set_error("fdt_match_encode: not built yet"); return FDT_E_UNSUPPORTED; }
+
+namespace {
+
+constexpr int M_THREADS = 256;
+constexpr int M_WARPS = M_THREADS / 32;
+constexpr int GT_TILE = 256;
+constexpr int MINE_THREADS = 1024;
+constexpr int MINE_SMEM_KEYS = 53248;       // 208 KB of cached keys
+
+struct GtTile {
+    float4 box[GT_TILE];
+    float area[GT_TILE];
+};
+
+__device__ __forceinline__ float iou_match(const float4 a, const float area_a, const float4 pf, const float area_b)
+{
+    float w = fminf(a.z, pf.z) - fmaxf(a.x, pf.x);
+    float h = fminf(a.w, pf.w) - fmaxf(a.y, pf.y);
+    w = fmaxf(w, 0.0f); h = fmaxf(h, 0.0f);
+    float inter = w * h;
+    float uni = area_a + area_b - inter;               // box_utils.py:98
+    if (inter > 0.0f || !(uni > 0.0f)) return inter / uni;
+    return 0.0f;                                       // 0 / positive
+}
+
+__device__ __forceinline__ void finalize_prior(const float *__restrict__ gt, int64_t g0, int idx, float ov, float thr,
+                                               float4 pr, float v0, float v1, float4 *loc_t, int64_t *conf_t,
+                                               int32_t *bti, float *bto, int64_t t)
+{
+    const float *row = gt + 5 * (g0 + idx);
+    float4 m = make_float4(row[0], row[1], row[2], row[3]);
+    float c = row[4] + 1.0f;                           // box_utils.py:205
+    if (ov < thr) c = 0.0f;                            // :206
+    conf_t[t] = (int64_t)c;                            // :210 (float -> long)
+    loc_t[t] = fdt_encode1(m, pr, v0, v1);             // :208
+    if (bti) bti[t] = idx;
+    if (bto) bto[t] = ov;
+}
+
+template <bool BIP>
+__global__ void __launch_bounds__(M_THREADS)
+k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const int64_t *__restrict__ gt_off,
+        int64_t N, float thr, float v0, float v1,
+        float4 *__restrict__ loc_t, int64_t *__restrict__ conf_t, int32_t *__restrict__ bti, float *__restrict__ bto,
+        int32_t *__restrict__ tmp_idx, float *__restrict__ tmp_ov, unsigned long long *__restrict__ bestprior)
+{
+    __shared__ GtTile tile;
+    __shared__ unsigned long long s_best[BIP ? GT_TILE : 1][BIP ? M_WARPS : 1];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t p = (int64_t)blockIdx.x * M_THREADS + tid;
+    const bool valid = p < N;
+    const int64_t g0 = gt_off[b];
+    const int G = (int)(gt_off[b + 1] - g0);
+    const int64_t t = (int64_t)b * N + p;
+    const float4 pr = priors[valid ? p : 0];
+    if (G <= 0) {                                      // reference raises (Q3); defined: all background
+        if (valid) {
+            conf_t[t] = 0; loc_t[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bti) bti[t] = 0;
+            if (bto) bto[t] = 0.0f;
+        }
+        return;
+    }
+    const float hw = pr.z / 2.0f, hh = pr.w / 2.0f;    // point_form, box_utils.py:15-16
+    const float4 pf = make_float4(pr.x - hw, pr.y - hh, pr.x + hw, pr.y + hh);
+    const float area_b = (pf.z - pf.x) * (pf.w - pf.y);
+    float best = 0.0f;
+    int bi = 0;
+    for (int t0 = 0; t0 < G; t0 += GT_TILE) {
+        const int tn = min(GT_TILE, G - t0);
+        __syncthreads();
+        if (tid < tn) {
+            const float *row = gt + 5 * (g0 + t0 + tid);
+            float4 a = make_float4(row[0], row[1], row[2], row[3]);
+            tile.box[tid] = a;
+            tile.area[tid] = (a.z - a.x) * (a.w - a.y);
+        }
+        __syncthreads();
+        for (int g = 0; g < tn; ++g) {
+            const float v = iou_match(tile.box[g], tile.area[g], pf, area_b);
+            if (t0 + g == 0) { best = v; bi = 0; }
+            else if (v > best) { best = v; bi = t0 + g; }                      // first index wins ties (:197)
+            if (BIP) {
+                unsigned key = valid ? fdt_float_key(v) : 0u;
+                unsigned mx = __reduce_max_sync(0xffffffffu, key);
+                unsigned cand = (valid && key == mx) ? (unsigned)p : 0xffffffffu;
+                unsigned pm = __reduce_min_sync(0xffffffffu, cand);           // first prior wins ties (:136)
+                if (lane == 0) s_best[g][warp] = ((unsigned long long)mx << 32) | (0xffffffffu - pm);
+            }
+        }
+        if (BIP) {
+            __syncthreads();
+            if (tid < tn) {
+                unsigned long long m = s_best[tid][0];
+#pragma unroll
+                for (int w = 1; w < M_WARPS; ++w) m = max(m, s_best[tid][w]);
+                atomicMax(&bestprior[g0 + t0 + tid], m);
+            }
+        }
+    }
+    if (!valid) return;
+    if (BIP) { tmp_idx[t] = bi; tmp_ov[t] = best; }
+    else finalize_prior(gt, g0, bi, best, thr, pr, v0, v1, loc_t, conf_t, bti, bto, t);
+}
+
+// box_utils.py:150-154: best_truth_overlap[best_prior_idx[j]] = 2; best_truth_idx[best_prior_idx[j]] = j (last j wins)
+__global__ void __launch_bounds__(M_THREADS)
+k_match_bipartite_finalize(const float4 *__restrict__ priors, const float *__restrict__ gt, const int64_t *__restrict__ gt_off,
+                           int64_t N, float thr, float v0, float v1,
+                           float4 *__restrict__ loc_t, int64_t *__restrict__ conf_t, int32_t *__restrict__ bti, float *__restrict__ bto,
+                           const int32_t *__restrict__ tmp_idx, const float *__restrict__ tmp_ov,
+                           const unsigned long long *__restrict__ bestprior)
+{
+    __shared__ unsigned s_bp[GT_TILE];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int64_t p = (int64_t)blockIdx.x * M_THREADS + tid;
+    const bool valid = p < N;
+    const int64_t g0 = gt_off[b];
+    const int G = (int)(gt_off[b + 1] - g0);
+    if (G <= 0) return;                                 // k_match already wrote the all-background rows
+    const int64_t t = (int64_t)b * N + p;
+    int idx = valid ? tmp_idx[t] : 0;
+    float ov = valid ? tmp_ov[t] : 0.0f;
+    for (int t0 = 0; t0 < G; t0 += GT_TILE) {
+        const int tn = min(GT_TILE, G - t0);
+        __syncthreads();
+        if (tid < tn) s_bp[tid] = 0xffffffffu - (unsigned)(bestprior[g0 + t0 + tid] & 0xffffffffull);
+        __syncthreads();
+        for (int j = 0; j < tn; ++j)
+            if (s_bp[j] == (unsigned)p) { idx = t0 + j; ov = 2.0f; }
+    }
+    if (valid) finalize_prior(gt, g0, idx, ov, thr, priors[p], v0, v1, loc_t, conf_t, bti, bto, t);
+}
+
+// ---------------------------------------------------------------------------------------------- loss
+__global__ void k_conf_global_max(const float *__restrict__ x, int64_t n, unsigned *__restrict__ gmax_key)
+{
+    unsigned k = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        k = max(k, fdt_float_key(x[i]));
+    k = __reduce_max_sync(0xffffffffu, k);
+    if ((threadIdx.x & 31) == 0) atomicMax(gmax_key, k);
+}
+
+struct LossAcc {            // lives in the workspace, zeroed per call
+    double loss_l, loss_c;
+    unsigned gmax_key;
+    unsigned pad;
+};
+
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T *s_red)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    v = (threadIdx.x < nw) ? s_red[threadIdx.x] : (T)0;
+    if (warp == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    return v;     // valid in thread 0
+}
+
+// multibox_loss.py:90-110
+__global__ void __launch_bounds__(M_THREADS)
+k_loss_prior(const float4 *__restrict__ loc, const float *__restrict__ conf, const float4 *__restrict__ loc_t,
+             const int64_t *__restrict__ conf_t, int64_t N, int C, LossAcc *__restrict__ acc,
+             float *__restrict__ loss_c_all, int32_t *__restrict__ num_pos)
+{
+    __shared__ double s_red[M_WARPS];
+    __shared__ int s_cnt[M_WARPS];
+    const int b = blockIdx.y;
+    const int64_t p = (int64_t)blockIdx.x * M_THREADS + threadIdx.x;
+    const float xmax = fdt_key_float(acc->gmax_key);
+    double sl = 0.0;
+    int is_pos = 0;
+    if (p < N) {
+        const int64_t t = (int64_t)b * N + p;
+        const int64_t label = conf_t[t];
+        is_pos = label > 0;
+        if (is_pos) {                                              // :96-101 smooth L1, beta = 1, sum
+            const float4 a = loc[t], g = loc_t[t];
+            const float d[4] = {fabsf(a.x - g.x), fabsf(a.y - g.y), fabsf(a.z - g.z), fabsf(a.w - g.w)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sl += (double)(d[k] < 1.0f ? 0.5f * d[k] * d[k] : d[k] - 0.5f);
+        }
+        const float *row = conf + t * C;
+        float s = 0.0f;
+        for (int c = 0; c < C; ++c) s += fdt_expf_cr(row[c] - xmax);                // box_utils.py:269
+        const float v = (fdt_logf_cr(s) + xmax) - row[label];                      // :106
+        loss_c_all[t] = is_pos ? 0.0f : v;                                         // :110
+    }
+    const double tot = block_sum<double>(sl, s_red);
+    const int cnt = block_sum<int>(is_pos, s_cnt);
+    if (threadIdx.x == 0) {
+        if (tot != 0.0) atomicAdd(&acc->loss_l, tot);
+        if (cnt) atomicAdd(&num_pos[b], cnt);
+    }
+}
+
+// One CTA per image.  MODE 0: standalone mining (pos given as uint8, writes neg).  MODE 1: fused with the
+// final CE over pos U neg (writes sel = pos | neg and accumulates loss_c).
+template <int MODE>
+__global__ void __launch_bounds__(MINE_THREADS, 1)
+k_mine(const float *__restrict__ loss_c, const uint8_t *__restrict__ pos_in, const int64_t *__restrict__ conf_t,
+       const float *__restrict__ conf, const int32_t *__restrict__ num_pos_in, int64_t N, int C, int negpos_ratio,
+       uint8_t *__restrict__ out_mask, LossAcc *__restrict__ acc, int use_smem)
+{
+    extern __shared__ unsigned s_keys[];
+    __shared__ int s_hist[256];
+    __shared__ int s_sel[3];
+    __shared__ int s_red_i[32];
+    __shared__ double s_red_d[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *lrow = loss_c + (int64_t)b * N;
+
+    int64_t num_pos;
+    if (MODE == 0) {
+        int c = 0;
+        for (int64_t p = tid; p < N; p += MINE_THREADS) c += pos_in[(int64_t)b * N + p] != 0;
+        c = block_sum<int>(c, s_red_i);
+        if (tid == 0) s_sel[0] = c;
+        __syncthreads();
+        num_pos = s_sel[0];
+        __syncthreads();
+    } else {
+        num_pos = num_pos_in[b];
+    }
+    int64_t num_neg = (int64_t)negpos_ratio * num_pos;                         // multibox_loss.py:115
+    if (num_neg > N - 1) num_neg = N - 1;
+
+    if (use_smem)
+        for (int64_t p = tid; p < N; p += MINE_THREADS) s_keys[p] = fdt_float_key(lrow[p]);
+    __syncthreads();
+    auto key_at = [&](int64_t p) -> unsigned { return use_smem ? s_keys[p] : fdt_float_key(lrow[p]); };
+
+    unsigned T = 0xffffffffu;      // selected: key > T, plus the first r (index order) with key == T
+    int r = 0, n_eq = 0;
+    if (num_neg > 0) {
+        unsigned prefix = 0, pmask = 0;
+        int need = (int)num_neg;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (tid < 256) s_hist[tid] = 0;
+            __syncthreads();
+            for (int64_t base = 0; base < N; base += MINE_THREADS) {
+                int64_t p = base + tid;
+                int d = 256;
+                if (p < N) {
+                    unsigned k = key_at(p);
+                    if ((k & pmask) == prefix) d = (int)((k >> shift) & 0xff);
+                }
+                unsigned peers = __match_any_sync(0xffffffffu, d);
+                if (d < 256 && lane == __ffs(peers) - 1) atomicAdd(&s_hist[d], __popc(peers));
+            }
+            __syncthreads();
+            if (warp == 0) {
+                int c = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) c += s_hist[255 - 8 * lane - q];
+                int cum = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, cum, o); if (lane >= o) cum += v; }
+                unsigned hit = __ballot_sync(0xffffffffu, cum >= need);
+                int first = __ffs(hit) - 1;
+                if (lane == first) {
+                    int rem = need - (cum - c);
+                    for (int q = 0; q < 8; ++q) {
+                        int hc = s_hist[255 - 8 * lane - q];
+                        if (hc >= rem) { s_sel[0] = 255 - 8 * lane - q; s_sel[1] = rem; s_sel[2] = hc; break; }
+                        rem -= hc;
+                    }
+                }
+            }
+            __syncthreads();
+            prefix |= (unsigned)s_sel[0] << shift;
+            pmask |= 0xffu << shift;
+            need = s_sel[1];
+            n_eq = s_sel[2];
+            __syncthreads();
+        }
+        T = prefix; r = need;              // n_eq keys equal T; the first r of them (lowest index) are taken
+    }
+
+    // neg mask (+ CE over pos U neg)
+    unsigned char *mrow = out_mask + (int64_t)b * N;
+    double ce = 0.0;
+    const bool tie_slow = (num_neg > 0) && (r < n_eq);
+    for (int64_t p = tid; p < N; p += MINE_THREADS) {
+        const unsigned k = key_at(p);
+        bool neg = (num_neg > 0) && (k > T || (k == T && !tie_slow));
+        bool pos = (MODE == 0) ? false : (conf_t[(int64_t)b * N + p] > 0);
+        mrow[p] = (unsigned char)(neg || pos);
+    }
+    if (tie_slow) {                        // rare: duplicated boundary value -> ordered pick by one warp
+        __syncthreads();
+        if (warp == 0) {
+            int taken = 0;
+            for (int64_t base = 0; base < N && taken < r; base += 32) {
+                int64_t p = base + lane;
+                bool eq = p < N && key_at(p) == T;
+                unsigned bal = __ballot_sync(0xffffffffu, eq);
+                int rank = taken + __popc(bal & ((1u << lane) - 1u));
+                if (eq && rank < r) mrow[p] = 1;
+                taken += __popc(bal);
+            }
+        }
+        __syncthreads();
+    }
+    if (MODE == 1) {
+        __syncthreads();
+        for (int64_t p = tid; p < N; p += MINE_THREADS) {
+            if (!mrow[p]) continue;
+            const int64_t t = (int64_t)b * N + p;
+            const float *row = conf + t * C;
+            float m = row[0];
+            for (int c = 1; c < C; ++c) m = fmaxf(m, row[c]);
+            double s = 0.0;
+            for (int c = 0; c < C; ++c) s += exp((double)(row[c] - m));
+            ce += (log(s) + (double)m) - (double)row[conf_t[t]];                   // :128 F.cross_entropy, sum
+        }
+        ce = block_sum<double>(ce, s_red_d);
+        if (tid == 0 && ce != 0.0) atomicAdd(&acc->loss_c, ce);
+    }
+}
+
+__global__ void k_loss_final(const LossAcc *__restrict__ acc, const int32_t *__restrict__ num_pos, int B,
+                             float *__restrict__ losses, float *__restrict__ norm)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    long long n = 0;
+    for (int b = 0; b < B; ++b) n += num_pos[b];
+    double Nn = (double)n;                         // multibox_loss.py:130
+    if (n == 0) Nn = (double)B;                    // :132-133
+    losses[0] = (float)(acc->loss_l / Nn);
+    losses[1] = (float)(acc->loss_c / Nn);
+    norm[0] = (float)Nn;
+}
+
+// d loss_l / d loc = smooth-L1' at positives / N ; d loss_c / d conf = (softmax - onehot) at pos U neg / N
+__global__ void __launch_bounds__(M_THREADS)
+k_multibox_backward(const float4 *__restrict__ loc, const float *__restrict__ conf, const float4 *__restrict__ loc_t,
+                    const int64_t *__restrict__ conf_t, const uint8_t *__restrict__ sel, const float *__restrict__ norm,
+                    float g_l, float g_c, int64_t total, int C, float4 *__restrict__ grad_loc, float *__restrict__ grad_conf)
+{
+    const int64_t t = (int64_t)blockIdx.x * M_THREADS + threadIdx.x;
+    if (t >= total) return;
+    const float inv = 1.0f / norm[0];
+    const int64_t label = conf_t[t];
+    float4 gl = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (label > 0) {
+        const float4 a = loc[t], g = loc_t[t];
+        const float d[4] = {a.x - g.x, a.y - g.y, a.z - g.z, a.w - g.w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = (fabsf(d[k]) < 1.0f ? d[k] : (d[k] > 0.f ? 1.0f : -1.0f)) * g_l * inv;
+        gl = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    grad_loc[t] = gl;
+    const float *row = conf + t * C;
+    float *go = grad_conf + t * C;
+    if (sel[t]) {
+        float m = row[0];
+        for (int c = 1; c < C; ++c) m = fmaxf(m, row[c]);
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s += expf(row[c] - m);
+        for (int c = 0; c < C; ++c) go[c] = (expf(row[c] - m) / s - (c == label ? 1.0f : 0.0f)) * g_c * inv;
+    } else {
+        for (int c = 0; c < C; ++c) go[c] = 0.0f;
+    }
+}
+
+struct MatchWs { unsigned long long *bestprior; int32_t *tmp_idx; float *tmp_ov; size_t bytes; };
+MatchWs plan_match_ws(void *ws, int B, int64_t N, int64_t total_gt)
+{
+    MatchWs m;
+    char *p = (char *)ws;
+    size_t o = 0;
+    m.bestprior = (unsigned long long *)(p + o); o += fdt_align256((size_t)(total_gt > 0 ? total_gt : 1) * 8);
+    m.tmp_idx = (int32_t *)(p + o); o += fdt_align256((size_t)B * N * 4);
+    m.tmp_ov = (float *)(p + o); o += fdt_align256((size_t)B * N * 4);
+    m.bytes = o;
+    return m;
+}
+
+int launch_match(const float *priors, const float *gt, const int64_t *gt_off, int B, int64_t N, int64_t total_gt,
+                 float thr, float v0, float v1, int bipartite, float *loc_t, int64_t *conf_t, int32_t *bti, float *bto,
+                 void *ws, cudaStream_t st)
+{
+    dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
+    MatchWs m = plan_match_ws(ws, B, N, total_gt);
+    if (!bipartite) {
+        k_match<false><<<grid, M_THREADS, 0, st>>>((const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t, conf_t,
+                                                   bti, bto, nullptr, nullptr, nullptr);
+        FDT_LAUNCH_CHECK();
+    } else {
+        FDT_CUDA(cudaMemsetAsync(m.bestprior, 0, (size_t)(total_gt > 0 ? total_gt : 1) * 8, st));
+        k_match<true><<<grid, M_THREADS, 0, st>>>((const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t, conf_t,
+                                                  bti, bto, m.tmp_idx, m.tmp_ov, m.bestprior);
+        FDT_LAUNCH_CHECK();
+        k_match_bipartite_finalize<<<grid, M_THREADS, 0, st>>>((const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t,
+                                                               conf_t, bti, bto, m.tmp_idx, m.tmp_ov, m.bestprior);
+        FDT_LAUNCH_CHECK();
+    }
+    return FDT_OK;
+}
+
+template <int MODE>
+int launch_mine(const float *loss_c, const uint8_t *pos, const int64_t *conf_t, const float *conf, const int32_t *num_pos,
+                int B, int64_t N, int C, int ratio, uint8_t *mask, LossAcc *acc, cudaStream_t st)
+{
+    const int use_smem = N <= MINE_SMEM_KEYS;
+    const size_t smem = use_smem ? (size_t)N * 4 : 0;
+    FDT_CUDA(cudaFuncSetAttribute(k_mine<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, MINE_SMEM_KEYS * 4));
+    k_mine<MODE><<<B, MINE_THREADS, smem, st>>>(loss_c, pos, conf_t, conf, num_pos, N, C, ratio, mask, acc, use_smem);
+    FDT_LAUNCH_CHECK();
+    return FDT_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+FDT_API size_t fdt_match_workspace_bytes(int B, int64_t N, int64_t total_gt)
+{
+    if (B <= 0 || N <= 0) return 256;
+    return plan_match_ws(nullptr, B, N, total_gt).bytes;
+}
+
+static int match_args_ok(const char *who, const float *priors, const float *gt, const int64_t *gt_off, int B, int64_t N,
+                         const float *loc_t, const int64_t *conf_t, const void *ws)
+{
+    FDT_REQUIRE(B >= 0 && N >= 0 && N < (1ll << 31), FDT_E_INVALID, "%s: bad sizes B=%d N=%lld", who, B, (long long)N);
+    if (B == 0 || N == 0) return FDT_OK;
+    FDT_REQUIRE(priors && gt && gt_off && loc_t && conf_t && ws, FDT_E_INVALID, "%s: null pointer argument", who);
+    FDT_REQUIRE(fdt_aligned(priors, 16) && fdt_aligned(loc_t, 16) && fdt_aligned(ws, 256), FDT_E_INVALID,
+                "%s: priors/loc_t need 16-byte, workspace 256-byte alignment", who);
+    return FDT_OK;
+}
+
+FDT_API int fdt_match_encode(const float *priors, const float *gt, const int64_t *gt_off, int64_t total_gt, int B, int64_t N,
+                             float threshold, float var0, float var1, int bipartite,
+                             float *loc_t, int64_t *conf_t, int32_t *best_truth_idx, float *best_truth_overlap,
+                             void *ws, size_t ws_bytes, fdt_stream_t stream)
+{
+    int rc = match_args_ok("fdt_match_encode", priors, gt, gt_off, B, N, loc_t, conf_t, ws);
+    if (rc != FDT_OK || B == 0 || N == 0) return rc;
+    FDT_REQUIRE(total_gt >= 0, FDT_E_INVALID, "fdt_match_encode: negative total_gt");
+    FDT_REQUIRE(ws_bytes >= fdt_match_workspace_bytes(B, N, total_gt), FDT_E_WORKSPACE,
+                "fdt_match_encode: workspace %zu < %zu bytes", ws_bytes, fdt_match_workspace_bytes(B, N, total_gt));
+    return launch_match(priors, gt, gt_off, B, N, total_gt, threshold, var0, var1, bipartite, loc_t, conf_t,
+                        best_truth_idx, best_truth_overlap, ws, (cudaStream_t)stream);
+}
+
 FDT_API size_t fdt_mine_workspace_bytes(int, int64_t) { return 256; }
-FDT_API int fdt_hard_negative_mine(const float *, const uint8_t *, int, int64_t, int, uint8_t *, void *, size_t, fdt_stream_t) { fdt_set_error("fdt_hard_negative_mine: not built yet"); return FDT_E_UNSUPPORTED; }
-FDT_API size_t fdt_multibox_workspace_bytes(int, int64_t, int, int64_t) { return 256; }
-FDT_API int fdt_multibox_loss_forward(const float *, const float *, const float *, const float *, const int64_t *, int, int64_t, int, float, int, int, float, float, float *, float *, float *, int64_t *, uint8_t *, float *, void *, size_t, fdt_stream_t) { fdt_set_error("fdt_multibox_loss_forward: not built yet"); return FDT_E_UNSUPPORTED; }
-FDT_API int fdt_multibox_loss_backward(const float *, const float *, const float *, const int64_t *, const uint8_t *, const float *, float, float, int, int64_t, int, float *, float *, fdt_stream_t) { fdt_set_error("fdt_multibox_loss_backward: not built yet"); return FDT_E_UNSUPPORTED; }
+
+FDT_API int fdt_hard_negative_mine(const float *loss_c, const uint8_t *pos, int B, int64_t N, int negpos_ratio,
+                                   uint8_t *neg, void *, size_t, fdt_stream_t stream)
+{
+    FDT_REQUIRE(B >= 0 && N >= 0 && negpos_ratio >= 0, FDT_E_INVALID, "fdt_hard_negative_mine: bad sizes");
+    if (B == 0 || N == 0) return FDT_OK;
+    FDT_REQUIRE(loss_c && pos && neg, FDT_E_INVALID, "fdt_hard_negative_mine: null pointer argument");
+    return launch_mine<0>(loss_c, pos, nullptr, nullptr, nullptr, B, N, 2, negpos_ratio, neg, nullptr, (cudaStream_t)stream);
+}
+
+struct LossWs { LossAcc *acc; int32_t *num_pos; float *loss_c_all; void *match; size_t bytes; };
+static LossWs plan_loss_ws(void *ws, int B, int64_t N, int64_t total_gt)
+{
+    LossWs w;
+    char *p = (char *)ws;
+    size_t o = 0;
+    w.acc = (LossAcc *)(p + o); o += 256;
+    w.num_pos = (int32_t *)(p + o); o += fdt_align256((size_t)B * 4);
+    w.loss_c_all = (float *)(p + o); o += fdt_align256((size_t)B * N * 4);
+    w.match = (void *)(p + o); o += plan_match_ws(nullptr, B, N, total_gt).bytes;
+    w.bytes = o;
+    return w;
+}
+
+FDT_API size_t fdt_multibox_workspace_bytes(int B, int64_t N, int, int64_t total_gt)
+{
+    if (B <= 0 || N <= 0) return 256;
+    return plan_loss_ws(nullptr, B, N, total_gt).bytes;
+}
+
+FDT_API int fdt_multibox_loss_forward(const float *loc, const float *conf, const float *priors,
+                                      const float *gt, const int64_t *gt_off, int64_t total_gt, int B, int64_t N, int C,
+                                      float threshold, int negpos_ratio, int bipartite, float var0, float var1,
+                                      float *losses, float *norm, float *loc_t, int64_t *conf_t, uint8_t *sel,
+                                      float *loss_c_all, void *ws, size_t ws_bytes, fdt_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = match_args_ok("fdt_multibox_loss_forward", priors, gt, gt_off, B, N, loc_t, conf_t, ws);
+    if (rc != FDT_OK) return rc;
+    FDT_REQUIRE(B > 0 && N > 0 && C >= 2, FDT_E_INVALID, "fdt_multibox_loss_forward: needs B > 0, N > 0, C >= 2");
+    FDT_REQUIRE(loc && conf && losses && norm && sel, FDT_E_INVALID, "fdt_multibox_loss_forward: null pointer argument");
+    FDT_REQUIRE(fdt_aligned(loc, 16), FDT_E_INVALID, "fdt_multibox_loss_forward: loc needs 16-byte alignment");
+    FDT_REQUIRE(total_gt >= 0, FDT_E_INVALID, "fdt_multibox_loss_forward: negative total_gt");
+    LossWs w = plan_loss_ws(ws, B, N, total_gt);
+    FDT_REQUIRE(ws_bytes >= w.bytes, FDT_E_WORKSPACE, "fdt_multibox_loss_forward: workspace %zu < %zu bytes", ws_bytes, w.bytes);
+    float *lca = loss_c_all ? loss_c_all : w.loss_c_all;
+
+    FDT_CUDA(cudaMemsetAsync(w.acc, 0, 256 + fdt_align256((size_t)B * 4), st));
+    const int64_t n_conf = (int64_t)B * N * C;
+    unsigned blocks = (unsigned)((n_conf + 256 * 8 - 1) / (256 * 8));
+    if (blocks > FDT_NUM_SMS * 8) blocks = FDT_NUM_SMS * 8;
+    k_conf_global_max<<<blocks, 256, 0, st>>>(conf, n_conf, &w.acc->gmax_key);
+    FDT_LAUNCH_CHECK();
+    rc = launch_match(priors, gt, gt_off, B, N, total_gt, threshold, var0, var1, bipartite, loc_t, conf_t, nullptr, nullptr, w.match, st);
+    if (rc != FDT_OK) return rc;
+    dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
+    k_loss_prior<<<grid, M_THREADS, 0, st>>>((const float4 *)loc, conf, (const float4 *)loc_t, conf_t, N, C, w.acc, lca, w.num_pos);
+    FDT_LAUNCH_CHECK();
+    rc = launch_mine<1>(lca, nullptr, conf_t, conf, w.num_pos, B, N, C, negpos_ratio, sel, w.acc, st);
+    if (rc != FDT_OK) return rc;
+    k_loss_final<<<1, 32, 0, st>>>(w.acc, w.num_pos, B, losses, norm);
+    FDT_LAUNCH_CHECK();
+    return FDT_OK;
+}
+
+FDT_API int fdt_multibox_loss_backward(const float *loc, const float *conf, const float *loc_t, const int64_t *conf_t,
+                                       const uint8_t *sel, const float *norm, float g_l, float g_c,
+                                       int B, int64_t N, int C, float *grad_loc, float *grad_conf, fdt_stream_t stream)
+{
+    FDT_REQUIRE(B >= 0 && N >= 0 && C >= 2, FDT_E_INVALID, "fdt_multibox_loss_backward: bad sizes");
+    if (B == 0 || N == 0) return FDT_OK;
+    FDT_REQUIRE(loc && conf && loc_t && conf_t && sel && norm && grad_loc && grad_conf, FDT_E_INVALID,
+                "fdt_multibox_loss_backward: null pointer argument");
+    FDT_REQUIRE(fdt_aligned(loc, 16) && fdt_aligned(loc_t, 16) && fdt_aligned(grad_loc, 16), FDT_E_INVALID,
+                "fdt_multibox_loss_backward: loc/loc_t/grad_loc need 16-byte alignment");
+    const int64_t total = (int64_t)B * N;
+    k_multibox_backward<<<(unsigned)((total + M_THREADS - 1) / M_THREADS), M_THREADS, 0, (cudaStream_t)stream>>>(
+        (const float4 *)loc, conf, (const float4 *)loc_t, conf_t, sel, norm, g_l, g_c, total, C, (float4 *)grad_loc, grad_conf);
+    FDT_LAUNCH_CHECK();
+    return FDT_OK;
+}

@@ -1,4 +1,430 @@
-// placeholder until the tracker kernels land (next commit): keeps the ABI complete and loud.
+// IoU tracker association (iouTracke_cal.py:126-155 per-frame loop, :174-176 flush) for sm_100a, float64.
+//
+// Every active track's last box is a detection of the previous frame (a track that is not extended in a
+// frame is finished or dropped at once), so the active list after frame f is a permutation of frame f's
+// detections.  That splits the problem:
+//
+//   k_track_mask     all frame pairs in parallel, one warp per previous-frame detection: float64 IoU
+//                    (utils/calc_performance.py:54-74 operand order) against every detection of the next
+//                    frame -> bit rows "IoU > sigma_iou" (+ a per-row NaN flag).  This is the O(sum D^2)
+//                    part and it is embarrassingly parallel.
+//   k_track_resolve  one CTA walks the frames in order (the greedy chain is inherently serial across
+//                    frames).  Inside a frame the reference's "for track in tracks_active: take the best
+//                    remaining detection" is a serial dictatorship in track order; it is evaluated as a
+//                    parallel deferred-acceptance fixed point (each track proposes to its best not-yet-
+//                    refused candidate, a detection keeps the lowest-order proposer), which reaches exactly
+//                    the sequential result.  Frames that contain a NaN IoU (0/0: zero-area boxes such as the
+//                    reference's dummy detection [0,0,0,0,0.4], :73-74) take an exact warp-sequential path
+//                    that mirrors numpy's argmax-picks-first-NaN behaviour.
+//   k_track_scatter  detections -> CSR track_dets via (head, position) recorded during resolve.
+#include <cstdlib>
+#include <climits>
 #include "fdt_common.cuh"
-FDT_API size_t fdt_iou_track_workspace_bytes(int64_t, int64_t, int64_t) { return 256; }
-FDT_API int fdt_iou_track(const double *, const int64_t *, int64_t, int64_t, int64_t, double, double, int64_t, int64_t *, int64_t *, int64_t *, int64_t *, double *, void *, size_t, fdt_stream_t) { fdt_set_error("fdt_iou_track: not built yet"); return FDT_E_UNSUPPORTED; }
+
+namespace {
+
+constexpr int TR_THREADS = 1024;
+constexpr int TR_MAX_D = 1024;             // one thread per track / detection; shared memory caps this near 800
+                                           // (Detect emits at most top_k = 750 detections per frame)
+
+__device__ __forceinline__ double dmin_nan(double a, double b) { return (a != a || b != b) ? (double)NAN : (a < b ? a : b); }
+__device__ __forceinline__ double dmax_nan(double a, double b) { return (a != a || b != b) ? (double)NAN : (a > b ? a : b); }
+
+// calc_performance.py:20-31, 65-74 with box_a = detection, box_b = the track's last box
+__device__ __forceinline__ double iou_f64(const double *a, const double *b)
+{
+    double w = dmin_nan(a[2], b[2]) - dmax_nan(a[0], b[0]);
+    double h = dmin_nan(a[3], b[3]) - dmax_nan(a[1], b[1]);
+    w = dmax_nan(w, 0.0); h = dmax_nan(h, 0.0);
+    double inter = w * h;
+    double area_a = (a[2] - a[0]) * (a[3] - a[1]);
+    double area_b = (b[2] - b[0]) * (b[3] - b[1]);
+    double uni = area_a + area_b - inter;
+    return inter / uni;
+}
+
+__global__ void k_track_frame_of(const int64_t *__restrict__ frame_off, int64_t F, int32_t *__restrict__ frame_of)
+{
+    int64_t f = blockIdx.x;
+    for (int64_t g = frame_off[f] + threadIdx.x; g < frame_off[f + 1]; g += blockDim.x) frame_of[g] = (int32_t)f;
+}
+
+// one warp per detection g of frame f (f < F-1): bits over the detections of frame f+1
+__global__ void __launch_bounds__(256)
+k_track_mask(const double *__restrict__ dets, const int64_t *__restrict__ frame_off, const int32_t *__restrict__ frame_of,
+             int64_t F, int64_t total, int W, double sigma_iou, uint32_t *__restrict__ mask, uint8_t *__restrict__ row_nan)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= total) return;
+    const int64_t f = frame_of[g];
+    if (f + 1 >= F) return;
+    const int64_t n0 = frame_off[f + 1];
+    const int D = (int)(frame_off[f + 2] - n0);
+    double tb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tb[k] = dets[5 * g + k];
+    bool any_nan = false;
+    for (int c = 0; c * 32 < D && c < W; ++c) {
+        const int j = c * 32 + lane;
+        bool over = false, isn = false;
+        if (j < D) {
+            double db[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) db[k] = dets[5 * (n0 + j) + k];
+            const double v = iou_f64(db, tb);
+            over = v > sigma_iou;                                  // iouTracke_cal.py:134
+            isn = v != v;
+        }
+        const unsigned bits = __ballot_sync(0xffffffffu, over);
+        any_nan |= __any_sync(0xffffffffu, isn);
+        if (lane == 0) mask[g * W + c] = bits;
+    }
+    if (lane == 0) row_nan[g] = any_nan;
+}
+
+struct TrackState {            // per local detection index, double buffered across frames
+    int32_t *head, *len, *start;
+    double *maxs;
+    double *box;               // [TR_MAX_D][5]
+};
+
+// exclusive scan of one int per thread over the block; returns (exclusive prefix, total)
+__device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int n = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += n; }
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    return inc - v + s_warp[warp];
+}
+
+struct ResolveParams {
+    const double *dets; const int64_t *frame_off; int64_t F; int W; int cap;   // cap = W * 32 >= max detections per frame
+    const uint32_t *mask; const uint8_t *row_nan;
+    double sigma_iou, sigma_h; int64_t t_min;
+    int32_t *det_head, *det_pos, *fin_id;        // [total]
+    int64_t *n_tracks, *track_off, *track_start; double *track_max;
+    int force_slow;
+};
+
+__global__ void __launch_bounds__(TR_THREADS, 1)
+k_track_resolve(const ResolveParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    // layout: cand[cap * W] | boxes[2][CAP*5] f64 | maxs[2][CAP] f64 | int arrays
+    const int W = P.W, CAP = P.cap;
+    uint32_t *cand = reinterpret_cast<uint32_t *>(smem);
+    double *boxbuf = reinterpret_cast<double *>(smem + ((size_t)CAP * W * 4 + 15) / 16 * 16);
+    double *maxbuf = boxbuf + 2 * CAP * 5;
+    int32_t *ibase = reinterpret_cast<int32_t *>(maxbuf + 2 * CAP);
+    int32_t *headbuf = ibase, *lenbuf = ibase + 2 * CAP, *startbuf = ibase + 4 * CAP;
+    int32_t *order = ibase + 6 * CAP;        // [2][CAP] local det index of each active track, in order
+    int32_t *owner = ibase + 8 * CAP;        // [CAP]
+    int32_t *match = ibase + 9 * CAP;        // [CAP] det matched to track t (or -1)
+    __shared__ int s_warp[33];
+    __shared__ int s_flag;
+    __shared__ int s_slow[4];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int cur = 0;                       // buffer index of the frame being processed
+    int T = 0;                         // active tracks = |order[prev]|
+    int64_t n_fin = 0, fin_rows = 0;   // finished tracks so far, and their total length (uniform across threads)
+
+    for (int64_t f = 0; f < P.F; ++f, cur ^= 1) {
+        const int prv = cur ^ 1;
+        const int64_t g0 = P.frame_off[f];
+        const int D = min((int)(P.frame_off[f + 1] - g0), CAP);      // host guarantees D <= cap; clamp keeps memory safe
+        const int64_t gp0 = f > 0 ? P.frame_off[f - 1] : 0;
+        double *box = boxbuf + cur * CAP * 5, *pbox = boxbuf + prv * CAP * 5;
+        double *maxs = maxbuf + cur * CAP, *pmaxs = maxbuf + prv * CAP;
+        int32_t *head = headbuf + cur * CAP, *phead = headbuf + prv * CAP;
+        int32_t *len = lenbuf + cur * CAP, *plen = lenbuf + prv * CAP;
+        int32_t *start = startbuf + cur * CAP, *pstart = startbuf + prv * CAP;
+        int32_t *ord = order + cur * CAP, *pord = order + prv * CAP;
+
+        // ---- stage this frame: boxes, candidate rows of the active tracks, NaN flag
+        if (tid == 0) s_flag = 0;
+        __syncthreads();
+        for (int i = tid; i < D * 5; i += TR_THREADS) box[i] = P.dets[5 * g0 + i];
+        const int Wd = (D + 31) >> 5;
+        int has_nan = 0;
+        for (int i = tid; i < T * Wd; i += TR_THREADS) {
+            const int t = i / Wd, c = i - t * Wd;
+            cand[t * W + c] = P.mask[(gp0 + pord[t]) * W + c];
+        }
+        for (int t = tid; t < T; t += TR_THREADS) has_nan |= P.row_nan[gp0 + pord[t]];
+        if (tid < D) owner[tid] = INT_MAX;
+        if (tid < CAP) match[tid] = -1;
+        if (has_nan || (P.force_slow && T > 0)) s_flag = 1;
+        __syncthreads();
+        const bool slow = s_flag != 0;
+        __syncthreads();
+
+        int n_upd = 0;                 // tracks continued into this frame (uniform after the paths below)
+        if (!slow) {
+            // ---- deferred acceptance == serial dictatorship in track order (see header)
+            int prop = -1;
+            for (;;) {
+                if (tid == 0) s_flag = 0;
+                __syncthreads();
+                prop = -1;
+                if (tid < T && D > 0) {
+                    const double *tb = pbox + 5 * pord[tid];
+                    double bv = 0.0;
+                    for (int c = 0; c < Wd; ++c) {
+                        uint32_t bits = cand[tid * W + c];
+                        while (bits) {
+                            const int j = c * 32 + __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            const double v = iou_f64(box + 5 * j, tb);
+                            if (prop < 0 || v > bv) { bv = v; prop = j; }       // argmax: first max (:133)
+                        }
+                    }
+                    if (prop >= 0) atomicMin(&owner[prop], tid);
+                }
+                __syncthreads();
+                if (prop >= 0 && owner[prop] != tid) {                          // refused by a lower-order track
+                    cand[tid * W + (prop >> 5)] &= ~(1u << (prop & 31));
+                    s_flag = 1;
+                }
+                __syncthreads();
+                const bool again = s_flag != 0;
+                __syncthreads();
+                if (!again) break;
+            }
+            const int matched = (tid < T && prop >= 0) ? 1 : 0;
+            if (matched) match[tid] = prop;
+            int tot;
+            const int before = block_excl_scan(matched, s_warp, tot);
+            n_upd = tot;
+            // a track whose turn comes after all D detections are taken is dropped, not finished (:130, Q5)
+            const bool had_dets = D > 0 && before < D;
+            int fin = 0;
+            if (tid < T && !matched && had_dets) {
+                const int i = pord[tid];
+                fin = (pmaxs[i] > P.sigma_h && (int64_t)plen[i] > P.t_min) ? 1 : 0;        // :147 strict >
+            }
+            if (matched) ord[before] = prop;
+            int ftot;
+            const int fbefore = block_excl_scan(fin, s_warp, ftot);
+            int ltot;
+            const int lbefore = block_excl_scan(fin ? plen[pord[tid < T ? tid : 0]] : 0, s_warp, ltot);
+            if (fin) {
+                const int i = pord[tid];
+                const int64_t id = n_fin + fbefore;
+                P.fin_id[phead[i]] = (int32_t)id;
+                P.track_off[id] = fin_rows + lbefore;
+                P.track_start[id] = pstart[i];
+                P.track_max[id] = pmaxs[i];
+            }
+            n_fin += ftot; fin_rows += ltot;
+            __syncthreads();
+        } else {
+            // ---- exact sequential path (warp 0), mirrors the python loop including NaN argmax
+            if (warp == 0) {
+                int n_alive = D, nu = 0;
+                int64_t nf = n_fin, fr = fin_rows;
+                for (int t = 0; t < T; ++t) {
+                    const int i = pord[t];
+                    if (n_alive <= 0) continue;                                  // :130 silently dropped
+                    const double *tb = pbox + 5 * i;
+                    double bv = 0.0; int bj = INT_MAX; int bn = 0;               // lane-local: value, index, is-NaN
+                    for (int j = lane; j < D; j += 32) {
+                        if (owner[j] != INT_MAX) continue;                       // already deleted from dets (:145)
+                        const double v = iou_f64(box + 5 * j, tb);
+                        const int vn = v != v;
+                        if (bj == INT_MAX) { bv = v; bj = j; bn = vn; }
+                        else if (!bn && (vn || v > bv)) { bv = v; bj = j; bn = vn; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {                           // first NaN, else first max
+                        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                        const int on = __shfl_xor_sync(0xffffffffu, bn, o);
+                        if (oj == INT_MAX) continue;
+                        bool take;
+                        if (bj == INT_MAX) take = true;
+                        else if (bn != on) take = on != 0;
+                        else if (bn) take = oj < bj;
+                        else take = (ov > bv) || (ov == bv && oj < bj);
+                        if (take) { bv = ov; bj = oj; bn = on; }
+                    }
+                    const bool matched = !bn && bv > P.sigma_iou;                // :134
+                    if (matched) {
+                        if (lane == 0) { owner[bj] = t; match[t] = bj; ord[nu] = bj; }
+                        ++nu; --n_alive;
+                    } else if (pmaxs[i] > P.sigma_h && (int64_t)plen[i] > P.t_min) {
+                        if (lane == 0) {
+                            P.fin_id[phead[i]] = (int32_t)nf;
+                            P.track_off[nf] = fr; P.track_start[nf] = pstart[i]; P.track_max[nf] = pmaxs[i];
+                        }
+                        ++nf; fr += plen[i];
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) { s_slow[0] = nu; s_slow[1] = (int)(nf - n_fin); s_slow[2] = (int)(fr - fin_rows); }
+            }
+            __syncthreads();
+            n_upd = s_slow[0]; n_fin += s_slow[1]; fin_rows += s_slow[2];
+            __syncthreads();
+        }
+
+        // ---- state of the continued tracks (:141-143) ...
+        if (tid < T && match[tid] >= 0) {
+            const int i = pord[tid], j = match[tid];
+            const double sc = box[5 * j + 4];
+            head[j] = phead[i];
+            len[j] = plen[i] + 1;
+            start[j] = pstart[i];
+            maxs[j] = sc > pmaxs[i] ? sc : pmaxs[i];                            // python max(a, b)
+            P.det_head[g0 + j] = phead[i];
+            P.det_pos[g0 + j] = plen[i];
+        }
+        // ---- ... and new tracks from the detections left over, in detection order (:150-154)
+        {
+            const int is_new = (tid < D && owner[tid] == INT_MAX) ? 1 : 0;
+            int tot;
+            const int before = block_excl_scan(is_new, s_warp, tot);
+            if (is_new) {
+                const int j = tid;
+                ord[n_upd + before] = j;
+                head[j] = (int32_t)(g0 + j);
+                len[j] = 1;
+                start[j] = (int32_t)(f + 1);                                     // frame_num is 1-based (:118)
+                maxs[j] = box[5 * j + 4];
+                P.det_head[g0 + j] = (int32_t)(g0 + j);
+                P.det_pos[g0 + j] = 0;
+            }
+            T = n_upd + tot;                                                     // :155
+        }
+        __syncthreads();
+    }
+
+    // ---- flush (:174-175): active tracks with max_score > sigma_h and len >= t_min, in active order
+    {
+        const int prv = cur ^ 1;
+        const double *pmaxs = maxbuf + prv * CAP;
+        const int32_t *phead = headbuf + prv * CAP, *plen = lenbuf + prv * CAP, *pstart = startbuf + prv * CAP;
+        const int32_t *pord = order + prv * CAP;
+        int fin = 0, i = 0;
+        if (tid < T) { i = pord[tid]; fin = (pmaxs[i] > P.sigma_h && (int64_t)plen[i] >= P.t_min) ? 1 : 0; }
+        int ftot, ltot;
+        const int fbefore = block_excl_scan(fin, s_warp, ftot);
+        const int lbefore = block_excl_scan(fin ? plen[i] : 0, s_warp, ltot);
+        if (fin) {
+            const int64_t id = n_fin + fbefore;
+            P.fin_id[phead[i]] = (int32_t)id;
+            P.track_off[id] = fin_rows + lbefore;
+            P.track_start[id] = pstart[i];
+            P.track_max[id] = pmaxs[i];
+        }
+        n_fin += ftot; fin_rows += ltot;
+        if (tid == 0) { *P.n_tracks = n_fin; P.track_off[n_fin] = fin_rows; }
+    }
+}
+
+__global__ void k_track_scatter(const int32_t *__restrict__ det_head, const int32_t *__restrict__ det_pos,
+                                const int32_t *__restrict__ fin_id, const int64_t *__restrict__ track_off, int64_t total,
+                                int64_t *__restrict__ track_dets)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const int32_t id = fin_id[det_head[g]];
+    if (id >= 0) track_dets[track_off[id] + det_pos[g]] = g;
+}
+
+struct TrackWs { uint32_t *mask; uint8_t *row_nan; int32_t *frame_of, *det_head, *det_pos, *fin_id; size_t bytes; };
+TrackWs plan_track_ws(void *ws, int64_t total, int W)
+{
+    TrackWs t;
+    char *p = (char *)ws;
+    size_t o = 0;
+    const size_t n = (size_t)(total > 0 ? total : 1);
+    t.mask = (uint32_t *)(p + o); o += fdt_align256(n * W * 4);
+    t.row_nan = (uint8_t *)(p + o); o += fdt_align256(n);
+    t.frame_of = (int32_t *)(p + o); o += fdt_align256(n * 4);
+    t.det_head = (int32_t *)(p + o); o += fdt_align256(n * 4);
+    t.det_pos = (int32_t *)(p + o); o += fdt_align256(n * 4);
+    t.fin_id = (int32_t *)(p + o); o += fdt_align256(n * 4);
+    t.bytes = o;
+    return t;
+}
+
+size_t resolve_smem(int W)
+{
+    const size_t cap = (size_t)W * 32;
+    size_t s = (cap * W * 4 + 15) / 16 * 16;
+    s += sizeof(double) * (2 * cap * 5 + 2 * cap);
+    s += sizeof(int32_t) * 10 * cap;
+    return s;
+}
+
+}  // namespace
+
+FDT_API size_t fdt_iou_track_workspace_bytes(int64_t F, int64_t total, int64_t max_dets_per_frame)
+{
+    (void)F;
+    int W = (int)((max_dets_per_frame + 31) / 32);
+    if (W < 1) W = 1;
+    return plan_track_ws(nullptr, total, W).bytes;
+}
+
+FDT_API int fdt_iou_track(const double *dets, const int64_t *frame_off, int64_t F, int64_t total, int64_t max_dets_per_frame,
+                          double sigma_iou, double sigma_h, int64_t t_min,
+                          int64_t *n_tracks, int64_t *track_off, int64_t *track_dets, int64_t *track_start, double *track_max,
+                          void *ws, size_t ws_bytes, fdt_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    FDT_REQUIRE(F >= 0 && total >= 0 && max_dets_per_frame >= 0, FDT_E_INVALID, "fdt_iou_track: negative size");
+    FDT_REQUIRE(n_tracks && track_off, FDT_E_INVALID, "fdt_iou_track: null output pointer");
+    FDT_REQUIRE(total < (1ll << 31), FDT_E_UNSUPPORTED, "fdt_iou_track: total=%lld exceeds 2^31-1", (long long)total);
+    FDT_REQUIRE(max_dets_per_frame <= TR_MAX_D, FDT_E_UNSUPPORTED,
+                "fdt_iou_track: %lld detections in one frame exceeds the limit of %d", (long long)max_dets_per_frame, TR_MAX_D);
+    if (F == 0 || total == 0) {
+        FDT_CUDA(cudaMemsetAsync(n_tracks, 0, sizeof(int64_t), st));
+        FDT_CUDA(cudaMemsetAsync(track_off, 0, sizeof(int64_t), st));
+        return FDT_OK;
+    }
+    FDT_REQUIRE(dets && frame_off && track_dets && track_start && track_max && ws, FDT_E_INVALID, "fdt_iou_track: null pointer argument");
+    FDT_REQUIRE(fdt_aligned(ws, 256), FDT_E_INVALID, "fdt_iou_track: workspace needs 256-byte alignment");
+    int W = (int)((max_dets_per_frame + 31) / 32);
+    if (W < 1) W = 1;
+    TrackWs t = plan_track_ws(ws, total, W);
+    FDT_REQUIRE(ws_bytes >= t.bytes, FDT_E_WORKSPACE, "fdt_iou_track: workspace %zu < %zu bytes", ws_bytes, t.bytes);
+
+    FDT_CUDA(cudaMemsetAsync(t.fin_id, 0xff, (size_t)total * 4, st));
+    k_track_frame_of<<<(unsigned)F, 128, 0, st>>>(frame_off, F, t.frame_of);
+    FDT_LAUNCH_CHECK();
+    k_track_mask<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(dets, frame_off, t.frame_of, F, total, W, sigma_iou, t.mask, t.row_nan);
+    FDT_LAUNCH_CHECK();
+    ResolveParams P{};
+    P.dets = dets; P.frame_off = frame_off; P.F = F; P.W = W; P.cap = W * 32; P.mask = t.mask; P.row_nan = t.row_nan;
+    P.sigma_iou = sigma_iou; P.sigma_h = sigma_h; P.t_min = t_min;
+    P.det_head = t.det_head; P.det_pos = t.det_pos; P.fin_id = t.fin_id;
+    P.n_tracks = n_tracks; P.track_off = track_off; P.track_start = track_start; P.track_max = track_max;
+    const char *env = getenv("FDT_TRACK_FORCE_SLOW");
+    P.force_slow = (env && env[0] == '1') ? 1 : 0;
+    const size_t smem = resolve_smem(W);
+    FDT_REQUIRE(smem <= (size_t)FDT_SMEM_MAX - 1024, FDT_E_UNSUPPORTED,
+                "fdt_iou_track: %lld detections in one frame need %zu bytes of shared memory (limit %d; 768 per frame always fits)",
+                (long long)max_dets_per_frame, smem, FDT_SMEM_MAX - 1024);
+    FDT_CUDA(cudaFuncSetAttribute(k_track_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_track_resolve<<<1, TR_THREADS, smem, st>>>(P);
+    FDT_LAUNCH_CHECK();
+    k_track_scatter<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t.det_head, t.det_pos, t.fin_id, track_off, total, track_dets);
+    FDT_LAUNCH_CHECK();
+    return FDT_OK;
+}

@@ -109,7 +109,7 @@ def _match(bipartite, threshold, truth_loc, priors, variances, truth_conf, loc_t
     with torch.cuda.device(dev):
         L = _lib.lib()
         ws = _lib.workspace(L.fdt_match_workspace_bytes(1, N, t.shape[0]), dev, "match")
-        _lib.check(L.fdt_match_encode(_lib.ptr(p), _lib.ptr(gt), _lib.ptr(off), 1, N, float(threshold),
+        _lib.check(L.fdt_match_encode(_lib.ptr(p), _lib.ptr(gt), _lib.ptr(off), t.shape[0], 1, N, float(threshold),
                                       float(variances[0]), float(variances[1]), int(bool(bipartite)),
                                       _lib.ptr(lt), _lib.ptr(ct), None, None, _lib.ptr(ws), ws.numel(),
                                       _lib.stream_ptr()))

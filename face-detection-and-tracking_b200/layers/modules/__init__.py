@@ -1,1 +1,3 @@
-__all__ = []
+from .multibox_loss import MultiBoxLoss
+
+__all__ = ['MultiBoxLoss']

@@ -1,0 +1,81 @@
+"""IoU tracker -- drop-in for the association loop of iouTracke_cal.py (:126-155, flush :174-176, use_iou=True)
+and its `.npy` output (:177, consumed by iouTracke_display.py:29), computed by fdt_iou_track on the GPU."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+# module-level defaults of the reference script (iouTracke_cal.py:22-28)
+sigma_iou = 0.4
+sigma_h = 0.6
+t_min = 5
+
+
+def pack_frames(frames):
+    """list of per-frame [D_f, 5] arrays (what detect_face returns, iouTracke_cal.py:70-84; float32 rows or
+    the float64 dummy [[0,0,0,0,0.4]]) -> (dets[total,5] float64, frame_off[F+1] int64).
+    The reference widens to python floats with det0.tolist() (:127), i.e. float64, exactly like this."""
+    off = np.zeros(len(frames) + 1, np.int64)
+    for i, f in enumerate(frames):
+        off[i + 1] = off[i] + np.asarray(f).reshape(-1, 5).shape[0]
+    dets = np.zeros((max(int(off[-1]), 1), 5), np.float64)
+    for i, f in enumerate(frames):
+        if off[i + 1] > off[i]:
+            dets[off[i]:off[i + 1]] = np.asarray(f, dtype=np.float64).reshape(-1, 5)
+    return dets, off
+
+
+def iou_track_raw(dets, frame_off, sigma_iou=sigma_iou, sigma_h=sigma_h, t_min=t_min):
+    """dets[total,5] float64 + frame_off[F+1] (numpy or torch, host or device)
+    -> (track_off[T+1], track_dets[rows], track_start[T], track_max[T]) as CUDA tensors; tracks are in the
+    reference's finishing order, track_dets are global detection rows in append order."""
+    dev = _lib.require_cuda()
+    d = torch.as_tensor(dets, dtype=torch.float64).to(dev).contiguous()
+    off_h = torch.as_tensor(frame_off, dtype=torch.int64).cpu()
+    off = off_h.to(dev)
+    F = off_h.numel() - 1
+    total = int(off_h[-1])
+    max_d = int((off_h[1:] - off_h[:-1]).max()) if F > 0 else 0
+    n = torch.zeros(1, dtype=torch.int64, device=dev)
+    t_off = torch.zeros(total + 2, dtype=torch.int64, device=dev)
+    t_dets = torch.zeros(max(total, 1), dtype=torch.int64, device=dev)
+    t_start = torch.zeros(total + 1, dtype=torch.int64, device=dev)
+    t_max = torch.zeros(total + 1, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        L = _lib.lib()
+        ws = _lib.workspace(L.fdt_iou_track_workspace_bytes(F, total, max_d), dev, "track")
+        _lib.check(L.fdt_iou_track(_lib.ptr(d), _lib.ptr(off), F, total, max_d, float(sigma_iou), float(sigma_h),
+                                   int(t_min), _lib.ptr(n), _lib.ptr(t_off), _lib.ptr(t_dets), _lib.ptr(t_start),
+                                   _lib.ptr(t_max), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    T = int(n.item())
+    rows = int(t_off[T].item()) if T else 0
+    return t_off[:T + 1], t_dets[:rows], t_start[:T], t_max[:T]
+
+
+def iou_track(frames, sigma_iou=sigma_iou, sigma_h=sigma_h, t_min=t_min):
+    """Run the tracker over a whole video.  -> tracks_finished: list of
+    {'bboxes': [[x1,y1,x2,y2], ...], 'max_score': float, 'start_frame': int}, the structure
+    iouTracke_cal.py:150-154 builds and :177 saves ("track ID" = index in this list)."""
+    dets, off = pack_frames(frames)
+    t_off, t_dets, t_start, t_max = iou_track_raw(dets, off, sigma_iou, sigma_h, t_min)
+    t_off, t_dets = t_off.cpu().numpy(), t_dets.cpu().numpy()
+    t_start, t_max = t_start.cpu().numpy(), t_max.cpu().numpy()
+    boxes = dets[t_dets, :4]
+    return [{'bboxes': boxes[t_off[t]:t_off[t + 1]].tolist(), 'max_score': float(t_max[t]),
+             'start_frame': int(t_start[t])} for t in range(len(t_start))]
+
+
+def save_tracks(path, tracks_finished):
+    """np.save(video_file + ".npy", np.array(tracks_finished))   [iouTracke_cal.py:177] -- a pickled 1-D object
+    array of dicts; `path` gets the .npy suffix from numpy exactly as in the reference."""
+    arr = np.empty(len(tracks_finished), dtype=object)
+    for i, t in enumerate(tracks_finished):
+        arr[i] = t
+    np.save(path, arr, allow_pickle=True)
+
+
+def load_tracks(path):
+    """tracks = np.load(video_file + '.npy').tolist()   [iouTracke_display.py:29]; modern numpy needs allow_pickle."""
+    return np.load(path, allow_pickle=True).tolist()

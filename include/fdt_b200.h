@@ -117,11 +117,11 @@ int fdt_detect_host(fdt_ctx *ctx, const float *loc_h, const float *conf_h, const
                     float *out_h, int32_t *counts_h, int64_t *kept_prior_h);
 
 /* ---- M4/M5  match_default / match_ensure_max_prior (layers/box_utils.py:165-210, 103-162) -------
- * Batched over images: gt[total,5] rows [x1,y1,x2,y2,label], gt_off[B+1] int64 (device).
+ * Batched over images: gt[total_gt,5] rows [x1,y1,x2,y2,label], gt_off[B+1] int64 (device).
  * -> loc_t[B,N,4], conf_t[B,N] int64; optional best_truth_idx[B,N] int32, best_truth_overlap[B,N].
  * Images with zero GT (the reference raises) are defined as all-background, loc_t = 0. */
 size_t fdt_match_workspace_bytes(int B, int64_t N, int64_t total_gt);
-int fdt_match_encode(const float *priors, const float *gt, const int64_t *gt_off, int B, int64_t N,
+int fdt_match_encode(const float *priors, const float *gt, const int64_t *gt_off, int64_t total_gt, int B, int64_t N,
                      float threshold, float var0, float var1, int bipartite,
                      float *loc_t, int64_t *conf_t, int32_t *best_truth_idx, float *best_truth_overlap,
                      void *ws, size_t ws_bytes, fdt_stream_t stream);
@@ -140,7 +140,7 @@ int fdt_hard_negative_mine(const float *loss_c, const uint8_t *pos, int B, int64
  * backward: grad_loc[B,N,4], grad_conf[B,N,C] for upstream gradients g_l, g_c (host scalars). */
 size_t fdt_multibox_workspace_bytes(int B, int64_t N, int C, int64_t total_gt);
 int fdt_multibox_loss_forward(const float *loc, const float *conf, const float *priors,
-                              const float *gt, const int64_t *gt_off, int B, int64_t N, int C,
+                              const float *gt, const int64_t *gt_off, int64_t total_gt, int B, int64_t N, int C,
                               float threshold, int negpos_ratio, int bipartite, float var0, float var1,
                               float *losses, float *norm, float *loc_t, int64_t *conf_t, uint8_t *sel,
                               float *loss_c_all, void *ws, size_t ws_bytes, fdt_stream_t stream);

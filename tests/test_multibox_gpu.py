@@ -1,0 +1,218 @@
+"""GPU parity tests for match/encode, hard-negative mining and MultiBoxLoss (forward + backward)."""
+import numpy as np
+import pytest
+import torch
+
+from fdt_b200 import synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+VAR = (0.1, 0.2)
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def layers():
+    import fdt_b200.layers as L
+    return L
+
+
+def gpu_match(bip, thr, gt, pri, want_best=True):
+    """fdt_match_encode for one image -> loc_t, conf_t, best_truth_idx, best_truth_overlap (numpy)."""
+    from fdt_b200 import _lib
+    dev = torch.device("cuda", torch.cuda.current_device())
+    N = pri.shape[0]
+    g = cu(gt.astype(np.float32)); p = cu(pri)
+    off = torch.tensor([0, gt.shape[0]], dtype=torch.int64, device=dev)
+    lt = torch.empty((N, 4), dtype=torch.float32, device=dev); ct = torch.empty(N, dtype=torch.int64, device=dev)
+    bti = torch.empty(N, dtype=torch.int32, device=dev); bto = torch.empty(N, dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    ws = _lib.workspace(L.fdt_match_workspace_bytes(1, N, gt.shape[0]), dev, "t")
+    _lib.check(L.fdt_match_encode(p.data_ptr(), g.data_ptr(), off.data_ptr(), gt.shape[0], 1, N, thr, VAR[0], VAR[1], int(bip),
+                                  lt.data_ptr(), ct.data_ptr(), bti.data_ptr(), bto.data_ptr(), ws.data_ptr(), ws.numel(),
+                                  _lib.stream_ptr()))
+    return npy(lt), npy(ct), npy(bti), npy(bto)
+
+
+@pytest.mark.parametrize("tag", ["g1", "g7", "g60"])
+@pytest.mark.parametrize("bip", [0, 1])
+def test_match_golden(golden, tag, bip):
+    g = golden("multibox")
+    gt, pri = g[f"{tag}_gt"], g["small_priors"]
+    lt, ct, bti, bto = gpu_match(bip, 0.35, gt, pri)
+    assert np.array_equal(ct, g[f"{tag}_b{bip}_conf_t"])                      # labels bit-exact vs the reference
+    if not bip:
+        assert np.array_equal(bti, g[f"{tag}_b{bip}_bti"])                    # match indices bit-exact
+    np.testing.assert_allclose(lt, g[f"{tag}_b{bip}_loc_t"], rtol=1e-5, atol=1e-6)
+    o_lt, o_ct, o_bti, o_bto = orc.match(bip, 0.35, gt[:, :4], pri, VAR, gt[:, 4])
+    assert np.array_equal(ct, o_ct) and np.array_equal(bti, o_bti) and np.array_equal(bto, o_bto)
+    np.testing.assert_allclose(lt, o_lt, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("G,bip,seed", [(1, 0, 1), (200, 0, 2), (200, 1, 3), (257, 1, 4), (700, 0, 5), (1968, 1, 6)])
+def test_match_production_size_vs_oracle(G, bip, seed):
+    """N = 34,125; G up to the WIDER maximum (1,968 faces) -> several shared-memory GT tiles."""
+    pri = synth.priors_numpy(640, 640)
+    gt = synth.gt_boxes(G, np.random.Generator(np.random.PCG64(seed)))
+    lt, ct, bti, bto = gpu_match(bip, 0.35, gt, pri)
+    o_lt, o_ct, o_bti, o_bto = orc.match(bip, 0.35, gt[:, :4], pri, VAR, gt[:, 4])
+    assert np.array_equal(ct, o_ct) and np.array_equal(bti, o_bti) and np.array_equal(bto, o_bto)
+    np.testing.assert_allclose(lt, o_lt, rtol=1e-6, atol=1e-7)
+
+
+def test_match_duplicate_gt_ties(golden):
+    """identical GT boxes: per-prior argmax keeps the first GT; bipartite override keeps the last (box_utils.py:153-154)."""
+    pri = golden("multibox")["small_priors"]
+    gt = np.array([[0.2, 0.2, 0.4, 0.4, 0], [0.2, 0.2, 0.4, 0.4, 0], [0.6, 0.6, 0.7, 0.8, 0]], np.float32)
+    for bip in (0, 1):
+        lt, ct, bti, bto = gpu_match(bip, 0.35, gt, pri)
+        o_lt, o_ct, o_bti, o_bto = orc.match(bip, 0.35, gt[:, :4], pri, VAR, gt[:, 4])
+        assert np.array_equal(ct, o_ct) and np.array_equal(bti, o_bti) and np.array_equal(bto, o_bto)
+
+
+def test_box_utils_match_dropin_signature(layers, golden):
+    g = golden("multibox")
+    gt, pri = g["g7_gt"], g["small_priors"]
+    N = pri.shape[0]
+    for fn, bip in ((layers.box_utils.match_default, 0), (layers.box_utils.match_ensure_max_prior, 1)):
+        loc_t = torch.zeros(3, N, 4); conf_t = torch.zeros(3, N, dtype=torch.long)
+        fn(0.35, torch.from_numpy(gt[:, :4]), torch.from_numpy(pri), list(VAR), torch.from_numpy(gt[:, 4]), loc_t, conf_t, 1)
+        assert np.array_equal(conf_t[1].numpy(), g[f"g7_b{bip}_conf_t"])
+        assert not conf_t[0].any() and not conf_t[2].any()
+    with pytest.raises(IndexError):
+        layers.box_utils.match_default(0.35, torch.zeros(0, 4), torch.from_numpy(pri), list(VAR), torch.zeros(0),
+                                       torch.zeros(1, N, 4), torch.zeros(1, N, dtype=torch.long), 0)
+
+
+# ------------------------------------------------------------------------------- mining
+def gpu_mine(loss_c, pos, ratio):
+    from fdt_b200 import _lib
+    dev = torch.device("cuda", torch.cuda.current_device())
+    B, N = loss_c.shape
+    lc = cu(loss_c.astype(np.float32)); ps = cu(pos.astype(np.uint8))
+    neg = torch.empty((B, N), dtype=torch.uint8, device=dev)
+    _lib.check(_lib.lib().fdt_hard_negative_mine(lc.data_ptr(), ps.data_ptr(), B, N, ratio, neg.data_ptr(), None, 0, _lib.stream_ptr()))
+    return npy(neg).astype(bool)
+
+
+@pytest.mark.parametrize("bip", [0, 1])
+def test_mining_on_reference_loss_bit_exact(golden, bip):
+    g = golden("multibox")
+    lc = g[f"fwd_b{bip}_loss_c_all"]; pos = g[f"fwd_b{bip}_conf_t"] > 0
+    neg_ref = np.unpackbits(g[f"fwd_b{bip}_neg"])[:lc.size].reshape(lc.shape).astype(bool)
+    assert np.array_equal(gpu_mine(lc, pos, 3), neg_ref)
+
+
+@pytest.mark.parametrize("N,npos,ratio", [(34125, 50, 3), (34125, 0, 3), (34125, 20000, 3), (87360, 300, 3), (1000, 10, 7), (33, 4, 3)])
+def test_mining_vs_oracle_including_ties(N, npos, ratio):
+    rng = np.random.Generator(np.random.PCG64(N + npos))
+    B = 3
+    lc = rng.uniform(0, 5, (B, N)).astype(np.float32)
+    lc[1] = np.round(lc[1] * 4) / 4                         # heavy ties: boundary value duplicated
+    lc[2, ::2] = 0.0
+    pos = np.zeros((B, N), bool)
+    for b in range(B):
+        pos[b, rng.permutation(N)[:npos]] = True
+    lc[pos] = 0
+    assert np.array_equal(gpu_mine(lc, pos, ratio), orc.hard_negative_mine(lc, pos, ratio))
+
+
+# ------------------------------------------------------------------------------- MultiBoxLoss
+def run_loss(layers, loc, conf, pri, targets, bip, host=False):
+    crit = layers.MultiBoxLoss(2, 0.35, True, 0, True, 3, 0.35, False, bipartite=bool(bip))
+    f = (lambda a: torch.from_numpy(a)) if host else cu
+    l = f(loc).requires_grad_(True); c = f(conf).requires_grad_(True)
+    ll, lc = crit((l, c, f(pri)), [f(t) for t in targets])
+    return crit, l, c, ll, lc
+
+
+@pytest.mark.parametrize("bip", [0, 1])
+def test_multibox_forward_golden_small(layers, golden, bip):
+    g = golden("multibox")
+    pri = g["small_priors"]
+    loc, conf, targets = synth.multibox_inputs(4, pri, int(g["fwd_seed"]), 1, 20)
+    crit, l, c, ll, lc = run_loss(layers, loc, conf, pri, targets, bip)
+    np.testing.assert_allclose([float(ll), float(lc)], g[f"fwd_b{bip}_loss"], rtol=1e-5)
+    loc_t, conf_t, sel = (npy(t) for t in crit.last_aux)
+    assert np.array_equal(conf_t, g[f"fwd_b{bip}_conf_t"])
+    neg_ref = np.unpackbits(g[f"fwd_b{bip}_neg"])[:conf_t.size].reshape(conf_t.shape).astype(bool)
+    assert np.array_equal(sel.astype(bool), neg_ref | (conf_t > 0))            # mined negatives bit-exact
+    np.testing.assert_allclose(loc_t, g[f"fwd_b{bip}_loc_t"], rtol=1e-5, atol=1e-6)
+
+
+def test_multibox_forward_golden_production_size(layers, golden):
+    g = golden("multibox")
+    pri = synth.priors_numpy(640, 640)
+    loc, conf, targets = synth.multibox_inputs(2, pri, int(g["big_seed"]), 1, 200)
+    crit, l, c, ll, lc = run_loss(layers, loc, conf, pri, targets, 0)
+    np.testing.assert_allclose([float(ll), float(lc)], g["big_loss"], rtol=1e-5)
+    _, conf_t, sel = (npy(t) for t in crit.last_aux)
+    assert np.array_equal(conf_t, g["big_conf_t"])
+    neg_ref = np.unpackbits(g["big_neg"])[:conf_t.size].reshape(conf_t.shape).astype(bool)
+    assert np.array_equal(sel.astype(bool), neg_ref | (conf_t > 0))
+
+
+@pytest.mark.parametrize("bip", [0, 1])
+def test_multibox_batch32_config3_vs_oracle(layers, bip):
+    """BASELINE config 3: B=32, N=34,125, G_i in [0,200] (zero-GT images are defined as all-background)."""
+    pri = synth.priors_numpy(640, 640)
+    loc, conf, targets = synth.multibox_inputs(32, pri, 3030, 0, 200)
+    targets[5] = np.zeros((0, 5), np.float32)
+    crit, l, c, ll, lc = run_loss(layers, loc, conf, pri, targets, bip)
+    r = orc.multibox_loss(loc, conf, pri, targets, 0.35, 3, bool(bip), VAR)
+    loc_t, conf_t, sel = (npy(t) for t in crit.last_aux)
+    assert np.array_equal(conf_t, r["conf_t"])
+    assert np.array_equal(sel.astype(bool), r["neg"] | (r["conf_t"] > 0))
+    np.testing.assert_allclose(loc_t, r["loc_t"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose([float(ll), float(lc)], [r["loss_l"], r["loss_c"]], rtol=1e-5)
+
+
+def torch_reference_loss(loc, conf, loc_t, conf_t, sel):
+    """plain PyTorch fp32 statement of multibox_loss.py:90-135 given targets and the selection mask."""
+    pos = conf_t > 0
+    loss_l = torch.nn.functional.smooth_l1_loss(loc[pos], loc_t[pos], reduction="sum")
+    loss_c = torch.nn.functional.cross_entropy(conf[sel.bool()], conf_t[sel.bool()], reduction="sum")
+    n = pos.sum().float().clamp(min=1)
+    return loss_l / n, loss_c / n
+
+
+def test_multibox_backward_matches_autograd(layers, golden):
+    g = golden("multibox")
+    pri = g["small_priors"]
+    loc, conf, targets = synth.multibox_inputs(4, pri, 404, 1, 20)
+    crit, l, c, ll, lc = run_loss(layers, loc, conf, pri, targets, 0)
+    (ll + 0.5 * lc).backward()
+    loc_t, conf_t, sel = crit.last_aux
+    l2 = cu(loc).requires_grad_(True); c2 = cu(conf).requires_grad_(True)
+    rl, rc = torch_reference_loss(l2, c2, loc_t, conf_t, sel)
+    (rl + 0.5 * rc).backward()
+    np.testing.assert_allclose(npy(l.grad), npy(l2.grad), rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(npy(c.grad), npy(c2.grad), rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose([float(ll), float(lc)], [float(rl), float(rc)], rtol=1e-5)
+
+
+def test_multibox_cpu_tensor_inputs(layers, golden):
+    g = golden("multibox")
+    pri = g["small_priors"]
+    loc, conf, targets = synth.multibox_inputs(4, pri, 404, 1, 20)
+    crit, l, c, ll, lc = run_loss(layers, loc, conf, pri, targets, 0, host=True)
+    assert ll.device.type == "cpu"
+    np.testing.assert_allclose([float(ll), float(lc)], g["fwd_b0_loss"], rtol=1e-5)
+    (ll + lc).backward()
+    assert l.grad is not None and l.grad.device.type == "cpu" and float(l.grad.abs().sum()) > 0
+
+
+def test_multibox_no_positive_anywhere(layers, golden):
+    """num_pos == 0 -> N = batch size (multibox_loss.py:132-133), nothing mined -> both losses 0."""
+    pri = golden("multibox")["small_priors"]
+    loc, conf, _ = synth.multibox_inputs(2, pri, 9, 1, 2)
+    targets = [np.array([[0.9, 0.9, 0.9001, 0.9001, 0]], np.float32)] * 2
+    crit, l, c, ll, lc = run_loss(layers, loc, conf, pri, targets, 0)
+    assert float(ll) == 0.0 and float(lc) == 0.0
