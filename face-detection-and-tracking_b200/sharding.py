@@ -1,0 +1,103 @@
+"""Multi-GPU use of the box pipeline: images are independent (detection.py:52 and multibox_loss.py:69 loop
+over the batch with no cross-image state), so the batch dimension is split contiguously across ranks, one
+process per GPU, with NO collective on the data path.  The only exchanges are
+
+  * Detect: one all-gather of the detections -- either the fixed-shape [B_local, C, top_k, 5] block
+    (byte-identical to the single-GPU output once concatenated) or counts + packed variable-length rows;
+  * MultiBoxLoss: one all-reduce(sum) of (sum loss_l, sum loss_c, num_pos) before the division at
+    multibox_loss.py:134-135.
+
+The tracker is a serial chain per video: replicas only (one video per rank), no collective.
+Backends: NCCL over NVLink on GPUs; the same code runs under gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous balanced split: rank r owns [lo, hi); the first n_items % world ranks get one extra item."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _world(group):
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def all_gather_ragged(t: torch.Tensor, group=None):
+    """all-gather along dim 0 of tensors whose dim-0 length differs per rank (other dims equal)."""
+    rank, world = _world(group)
+    if world == 1:
+        return t
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(sizes)
+    if all(s == m for s in sizes):
+        out = torch.empty((world * m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+        return out
+    pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)], 0)
+
+
+class ShardedDetect:
+    """detect: a Detect-like callable (loc, conf, priors) -> [B_local, C, top_k, 5] run on this rank's images.
+
+    __call__ returns the detections of ALL ranks' images in rank order (== the single-process result on the
+    concatenated batch).  gather="block" exchanges the zero-padded block; gather="packed" exchanges
+    counts[B, C] + only the rows that hold detections and rebuilds the block locally."""
+
+    def __init__(self, detect, group=None, gather="block"):
+        assert gather in ("block", "packed")
+        self.detect, self.group, self.gather = detect, group, gather
+
+    def __call__(self, loc_local, conf_local, priors):
+        out = self.detect(loc_local, conf_local, priors)
+        rank, world = _world(self.group)
+        if world == 1:
+            return out
+        if self.gather == "block":
+            return all_gather_ragged(out, self.group)
+        B, C, K, _ = out.shape
+        valid = out[..., 0] > 0                      # rows are written in keep order, scores > conf_thresh >= 0
+        counts = valid.sum(-1).to(torch.int32)       # [B, C]
+        rows = out[valid]                            # [sum counts, 5] in (image, class, rank) order
+        counts_all = all_gather_ragged(counts, self.group)
+        rows_all = all_gather_ragged(rows, self.group)
+        full = torch.zeros((counts_all.shape[0], C, K, 5), dtype=out.dtype, device=out.device)
+        idx = torch.arange(K, device=out.device).expand(counts_all.shape[0], C, K) < counts_all.unsqueeze(-1)
+        full[idx] = rows_all
+        return full
+
+
+def sharded_multibox_loss(criterion, predictions_local, targets_local, group=None):
+    """criterion: a MultiBoxLoss-like module whose forward sets .last_aux = (loc_t, conf_t, sel) and returns
+    (loss_l, loss_c) normalised by the LOCAL number of positives.  Returns the losses normalised by the GLOBAL
+    number of positives, exactly what one process would return on the concatenated batch."""
+    loss_l, loss_c = criterion(predictions_local, targets_local)
+    rank, world = _world(group)
+    if world == 1:
+        return loss_l, loss_c
+    conf_t = criterion.last_aux[1]
+    num_pos = (conf_t > 0).sum().to(torch.float32)
+    b_local = torch.tensor(float(conf_t.shape[0]), device=num_pos.device)
+    n_local = torch.where(num_pos > 0, num_pos, b_local)                    # multibox_loss.py:130-133
+    dev = num_pos.device
+    sums = torch.stack([loss_l.detach().to(dev) * n_local, loss_c.detach().to(dev) * n_local, num_pos, b_local])
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    n_glob = torch.where(sums[2] > 0, sums[2], sums[3])
+    # keep the autograd graph of the local terms: d(global)/d(local inputs) = local grad * n_local / n_glob
+    scale = (n_local / n_glob).to(loss_l.device)
+    others_l = (sums[0] / n_glob).to(loss_l.device) - loss_l.detach() * scale
+    others_c = (sums[1] / n_glob).to(loss_c.device) - loss_c.detach() * scale
+    return loss_l * scale + others_l, loss_c * scale + others_c
