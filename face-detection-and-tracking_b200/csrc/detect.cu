@@ -15,6 +15,7 @@
 //
 // Tie rule (unspecified in the reference, torch.sort is unstable): keys are unique, descending key order =
 // descending score, higher prior index first among equal scores.
+#include <cstdlib>
 #include "fdt_common.cuh"
 
 namespace {
@@ -24,9 +25,15 @@ constexpr int K2_PER_THREAD = 8;
 constexpr int K2_TILE = K2_THREADS * K2_PER_THREAD;
 
 constexpr int K3_THREADS = 1024;
-constexpr int SORT_CAP = FDT_MAX_NMS_TOP_K;     // 8192 keys = 64 KB
-constexpr int CHUNK = 64;
-constexpr int GROUP = K3_THREADS / CHUNK;       // 16 threads cooperate on one candidate in phase A
+constexpr int NB = 4096;                        // score buckets of the shared-memory bucket sort
+constexpr int SORT_SLACK = 256;                 // room for the bucket that straddles rank nms_top_k
+constexpr int RANK_U = (FDT_MAX_NMS_TOP_K + SORT_SLACK + K3_THREADS - 1) / K3_THREADS;
+constexpr int ROUND = 256;                      // sorted candidates examined per NMS round
+constexpr int TPC = K3_THREADS / ROUND;         // threads cooperating on one candidate in phase A
+constexpr int NLEV = 5;                         // grid levels: 32, 16, 8, 4, 2 cells per side
+constexpr int NCELLS = 1024 + 256 + 64 + 16 + 4;
+constexpr int CELL_CAP = 12;
+constexpr int MAX_QUERY_CELLS = 64;
 
 enum { MODE_DETECT = 0, MODE_NMS = 1 };
 
@@ -110,7 +117,9 @@ struct SortNmsParams {
     int64_t *keep;              // [n] (MODE_NMS)
     int64_t *count_out;         // [1] (MODE_NMS)
     int64_t n;                  // MODE_NMS list length
-    int off_cbox, off_kbox, off_karea, off_kpos;   // byte offsets into dynamic shared memory
+    int key_cap;                // entries in the shared-memory key array (>= nms_top_k + SORT_SLACK)
+    long long *prof;            // diagnostics: per-phase clock64 of CTA 0 (null unless FDT_K3_PROFILE=1)
+    int off_cbox, off_scr, off_big, off_klist;   // byte offsets into dynamic shared memory
 };
 
 // "i (kept, higher score) suppresses j": box_utils.py:322-339, union = (area_j - inter) + area_i,
@@ -127,22 +136,66 @@ __device__ __forceinline__ bool fdt_suppresses(const float4 bi, const float area
     return !(uni > 0.0f) && !(uni < 0.0f);          // 0/uni is NaN iff uni is 0 or NaN
 }
 
-template <int MODE, bool KEPT_COPY>
+__device__ __forceinline__ float box_area(const float4 b) { return (b.z - b.x) * (b.w - b.y); }   // box_utils.py:296
+// Boxes the spatial grid may index: finite, not inverted, 0 < area < inf.  For two such boxes inter <= min(area_i,
+// area_j) holds exactly in fp32 (rounding is monotone), so union >= area_i > 0 and IoU is a finite number bounded by
+// the ratio of the longer sides; they can only suppress each other if they intersect.  Everything else (NaN/inf
+// coordinates, inverted or zero-area boxes -- 0/0 = NaN suppresses at ANY distance, box_utils.py:337-339) goes to the
+// always-tested list and is itself tested against every kept box.
+__device__ __forceinline__ bool box_regular(const float4 b)
+{
+    const float a = (b.z - b.x) * (b.w - b.y);
+    return (b.z >= b.x) && (b.w >= b.y) && fabsf(b.x) < INFINITY && fabsf(b.y) < INFINITY && fabsf(b.z) < INFINITY &&
+           fabsf(b.w) < INFINITY && a > 0.0f && a < INFINITY;
+}
+
+struct GridGeom {
+    float x0, y0;          // origin = min corner over all regular candidate boxes
+    float inv0;            // cells per unit length at level 0 (32 / extent)
+    float c0;              // cell size at level 0
+    int ok;                // 0: degenerate extent -> everything is "big"
+};
+__device__ __forceinline__ int grid_off(int lev) { return lev == 0 ? 0 : lev == 1 ? 1024 : lev == 2 ? 1280 : lev == 3 ? 1344 : 1360; }
+__device__ __forceinline__ int cell_of(float x, float origin, float inv, int G)
+{
+    int c = __float2int_rd((x - origin) * inv);
+    return max(0, min(G - 1, c));
+}
+// smallest level whose cell size is >= the box's longer side; NLEV if none (box is "big")
+__device__ __forceinline__ int level_of(float side, float c0)
+{
+    float c = c0;
+#pragma unroll
+    for (int l = 0; l < NLEV; ++l) { if (side <= c) return l; c *= 2.0f; }
+    return NLEV;
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(K3_THREADS, 1)
 k_sort_nms(const SortNmsParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    uint64_t *skeys = reinterpret_cast<uint64_t *>(smem);
-    float4 *cbox = reinterpret_cast<float4 *>(smem + P.off_cbox);
-    float4 *kbox = reinterpret_cast<float4 *>(smem + P.off_kbox);
-    float *karea = reinterpret_cast<float *>(smem + P.off_karea);
-    int32_t *kpos = reinterpret_cast<int32_t *>(smem + P.off_kpos);
-    __shared__ uint64_t s_mask[CHUNK];
-    __shared__ uint64_t s_keptbits;
-    __shared__ unsigned char s_flag[CHUNK];
-    __shared__ int s_hist[256];
+    uint64_t *skeys = reinterpret_cast<uint64_t *>(smem);                    // [key_cap]
+    float4 *cbox = reinterpret_cast<float4 *>(smem + P.off_cbox);             // [kcap] boxes in sorted order
+    int *s_hist = reinterpret_cast<int *>(smem + P.off_scr);                  // sort: fill[NB] | start[NB]
+    int *s_start = s_hist + NB;
+    int *cell_cnt = reinterpret_cast<int *>(smem + P.off_scr);                // nms:  cnt[NCELLS] | items[NCELLS*CELL_CAP]
+    uint16_t *cell_items = reinterpret_cast<uint16_t *>(cell_cnt + NCELLS);
+    uint16_t *big = reinterpret_cast<uint16_t *>(smem + P.off_big);           // [kcap] kept boxes every candidate tests
+    uint16_t *klist = reinterpret_cast<uint16_t *>(smem + P.off_klist);       // [max_keep] kept positions, in order
+
     __shared__ int s_sel[3];
-    __shared__ int s_cnt;
+    __shared__ int s_placed, s_nbig, s_unknown;
+    __shared__ unsigned s_kmin, s_kmax;
+    __shared__ int s_hist8[256];
+    __shared__ int s_warp[33];
+    __shared__ unsigned s_ext[4];          // extent of the regular boxes as order-preserving keys
+    __shared__ unsigned char s_flag[ROUND];
+    __shared__ float4 sv_box[ROUND];
+    __shared__ float sv_area[ROUND], sv_side[ROUND];
+    __shared__ uint16_t sv_pos[ROUND];
+    __shared__ unsigned sv_rows[ROUND][ROUND / 32];
+    __shared__ unsigned s_keptw[ROUND / 32], s_deadw[ROUND / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int list = blockIdx.x;
@@ -152,190 +205,351 @@ k_sort_nms(const SortNmsParams P)
 
     int n_c = (MODE == MODE_DETECT) ? P.counters[list] : (int)P.n;
     if (MODE == MODE_DETECT && n_c == 1) n_c = 0;            // detection.py:66-72: one candidate -> `continue`
-    int n_sorted;
+    const int k = min(n_c, P.nms_top_k);                     // box_utils.py:299 idx[-top_k:]
+    const bool prof = P.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    long long pt = prof ? clock64() : 0, pacc[6] = {0, 0, 0, 0, 0, 0};
+#define K3_STAMP(slot) do { if (prof) { long long now_ = clock64(); P.prof[slot] = now_ - pt; pt = now_; } } while (0)
+#define K3_ACC(slot) do { if (prof) { long long now_ = clock64(); pacc[slot] += now_ - pt; pt = now_; } } while (0)
 
-    // ---------------- select: top nms_top_k keys into shared memory
-    if (n_c <= SORT_CAP) {
-        for (int i = tid; i < n_c; i += K3_THREADS) skeys[i] = gkeys[i];
-        n_sorted = n_c;
-    } else {
-        // MSB-first radix select (8 bits per pass) of the nms_top_k-th largest key over the global list
-        uint64_t prefix = 0, pmask = 0;
-        int need = P.nms_top_k;
-        for (int shift = 56; shift >= 0; shift -= 8) {
-            if (tid < 256) s_hist[tid] = 0;
+    // =========================================================== stage 1: top-k selection + sort (bucket sort)
+    // Monotone score -> bucket map, counting sort by bucket (descending), exact in-bucket ranking with the full
+    // 64-bit key.  Keys stream from global/L2 three times; only buckets that can reach rank < k are materialised.
+    if (k > 0) {
+        if (tid == 0) { s_kmin = 0xffffffffu; s_kmax = 0u; }
+        for (int i = tid; i < 2 * NB; i += K3_THREADS) s_hist[i] = 0;
+        __syncthreads();
+        {
+            unsigned lo = 0xffffffffu, hi = 0u;
+            for (int i = tid; i < n_c; i += K3_THREADS) { unsigned k32 = (unsigned)(gkeys[i] >> 32); lo = min(lo, k32); hi = max(hi, k32); }
+            lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+            if (lane == 0) { atomicMin(&s_kmin, lo); atomicMax(&s_kmax, hi); }
+        }
+        __syncthreads();
+        K3_STAMP(0);
+        const unsigned kmin = s_kmin;
+        const float inv = (float)NB / ((float)(s_kmax - kmin) + 1.0f);
+        auto bucket = [&](uint64_t key) -> int { return min(NB - 1, (int)((float)((unsigned)(key >> 32) - kmin) * inv)); };
+        uint64_t tmin = 0;                                   // after the fallback select: only keys >= tmin take part
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            for (int i = tid; i < n_c; i += K3_THREADS) { uint64_t key = gkeys[i]; if (key >= tmin) atomicAdd(&s_hist[bucket(key)], 1); }
             __syncthreads();
-            for (int base = 0; base < n_c; base += K3_THREADS) {
-                int i = base + tid;
-                int d = 256;
-                if (i < n_c) {
-                    uint64_t key = gkeys[i];
-                    if ((key & pmask) == prefix) d = (int)((key >> shift) & 0xff);
-                }
-                unsigned peers = __match_any_sync(0xffffffffu, d);
-                if (d < 256 && lane == __ffs(peers) - 1) atomicAdd(&s_hist[d], __popc(peers));
-            }
+            // descending exclusive scan: start[b] = number of keys in higher buckets
+            int c[NB / K3_THREADS], sum = 0;
+#pragma unroll
+            for (int q = 0; q < NB / K3_THREADS; ++q) { c[q] = s_hist[NB - 1 - (tid * (NB / K3_THREADS) + q)]; sum += c[q]; }
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+            if (lane == 31) s_warp[warp] = inc;
+            if (tid == 0) s_placed = 0;
             __syncthreads();
             if (warp == 0) {
-                int c = 0;
+                int w = s_warp[lane], winc = w;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) c += s_hist[255 - 8 * lane - q];
-                int cum = c;
+                for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += v; }
+                s_warp[lane] = winc - w;
+            }
+            __syncthreads();
+            int run = inc - sum + s_warp[warp];
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, cum, o); if (lane >= o) cum += v; }
-                unsigned hit = __ballot_sync(0xffffffffu, cum >= need);
-                int first = __ffs(hit) - 1;
-                if (lane == first) {
-                    int rem = need - (cum - c);
-                    for (int q = 0; q < 8; ++q) {
-                        int hcount = s_hist[255 - 8 * lane - q];
-                        if (hcount >= rem) { s_sel[0] = 255 - 8 * lane - q; s_sel[1] = rem; s_sel[2] = hcount; break; }
-                        rem -= hcount;
+            for (int q = 0; q < NB / K3_THREADS; ++q) {
+                const int bq = NB - 1 - (tid * (NB / K3_THREADS) + q);
+                s_start[bq] = run;
+                s_hist[bq] = 0;                              // becomes the fill counter of the scatter pass
+                if (run < k && run + c[q] >= k) s_placed = run + c[q];      // exactly one bucket straddles rank k
+                run += c[q];
+            }
+            __syncthreads();
+            if (s_placed <= P.key_cap || attempt == 1) break;
+            // Degenerate score distribution (a single bucket larger than the slack): exact MSB radix select of the
+            // k-th largest key, then bucket only the k keys >= that threshold.
+            uint64_t prefix = 0, pmask = 0;
+            int need = k;
+            for (int shift = 56; shift >= 0; shift -= 8) {
+                if (tid < 256) s_hist8[tid] = 0;
+                __syncthreads();
+                for (int base = 0; base < n_c; base += K3_THREADS) {
+                    int i = base + tid;
+                    int d = 256;
+                    if (i < n_c) {
+                        uint64_t key = gkeys[i];
+                        if ((key & pmask) == prefix) d = (int)((key >> shift) & 0xff);
+                    }
+                    unsigned peers = __match_any_sync(0xffffffffu, d);
+                    if (d < 256 && lane == __ffs(peers) - 1) atomicAdd(&s_hist8[d], __popc(peers));
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    int cc = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) cc += s_hist8[255 - 8 * lane - q];
+                    int cum = cc;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, cum, o); if (lane >= o) cum += v; }
+                    unsigned hit = __ballot_sync(0xffffffffu, cum >= need);
+                    int first = __ffs(hit) - 1;
+                    if (lane == first) {
+                        int rem = need - (cum - cc);
+                        for (int q = 0; q < 8; ++q) {
+                            int hcount = s_hist8[255 - 8 * lane - q];
+                            if (hcount >= rem) { s_sel[0] = 255 - 8 * lane - q; s_sel[1] = rem; s_sel[2] = hcount; break; }
+                            rem -= hcount;
+                        }
+                    }
+                }
+                __syncthreads();
+                prefix |= (uint64_t)s_sel[0] << shift;
+                pmask |= (uint64_t)0xff << shift;
+                need = s_sel[1];
+                const bool done = (s_sel[2] == need);
+                __syncthreads();
+                if (done) break;
+            }
+            tmin = prefix;                                   // exactly k keys are >= prefix (keys are unique)
+        }
+        K3_STAMP(1);
+        // scatter into bucket-contiguous order (arbitrary order inside a bucket)
+        for (int i = tid; i < n_c; i += K3_THREADS) {
+            uint64_t key = gkeys[i];
+            if (key < tmin) continue;
+            const int bq = bucket(key);
+            const int st = s_start[bq];
+            if (st < k) skeys[st + atomicAdd(&s_hist[bq], 1)] = key;
+        }
+        __syncthreads();
+        K3_STAMP(2);
+        // exact rank = bucket start + number of larger keys in the same bucket; permute through registers
+        const int placed = min(s_placed, P.key_cap);
+        uint64_t rk[RANK_U];
+        int rr[RANK_U];
+#pragma unroll
+        for (int u = 0; u < RANK_U; ++u) {
+            const int i = tid + u * K3_THREADS;
+            rr[u] = -1;
+            if (i < placed) {
+                const uint64_t key = skeys[i];
+                const int bq = bucket(key);
+                const int lo = s_start[bq], hi = lo + s_hist[bq];
+                int g = 0;
+                for (int t = lo; t < hi; ++t) g += skeys[t] > key;
+                rk[u] = key; rr[u] = lo + g;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < RANK_U; ++u)
+            if (rr[u] >= 0 && rr[u] < k) skeys[rr[u]] = rk[u];
+        __syncthreads();
+        K3_STAMP(3);
+    }
+
+    // =========================================================== stage 2: boxes of the selected candidates + extent
+    {
+        float x0 = INFINITY, y0 = INFINITY, x1 = -INFINITY, y1 = -INFINITY;
+        for (int j = tid; j < k; j += K3_THREADS) {
+            const uint32_t p = (uint32_t)skeys[j];
+            float4 bx;
+            if (MODE == MODE_DETECT) {
+                const float4 l = __ldg(reinterpret_cast<const float4 *>(P.loc) + ((int64_t)b * P.N + p));
+                const float4 pr = __ldg(reinterpret_cast<const float4 *>(P.priors) + p);
+                bx = fdt_decode1(l, pr, P.v0, P.v1);              // detection.py:55, only for rows NMS can reach
+            } else {
+                bx = __ldg(reinterpret_cast<const float4 *>(P.boxes) + p);
+            }
+            cbox[j] = bx;
+            if (box_regular(bx)) { x0 = fminf(x0, bx.x); y0 = fminf(y0, bx.y); x1 = fmaxf(x1, bx.z); y1 = fmaxf(y1, bx.w); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+            x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        }
+        if (tid == 0) { s_ext[0] = 0xffffffffu; s_ext[1] = 0xffffffffu; s_ext[2] = 0u; s_ext[3] = 0u; s_nbig = 0; }
+        for (int i = tid; i < NCELLS; i += K3_THREADS) cell_cnt[i] = 0;      // the sort scratch is dead: it becomes the grid
+        __syncthreads();
+        if (lane == 0) {      // float min/max through the order-preserving integer map
+            atomicMin(&s_ext[0], fdt_float_key(x0)); atomicMin(&s_ext[1], fdt_float_key(y0));
+            atomicMax(&s_ext[2], fdt_float_key(x1)); atomicMax(&s_ext[3], fdt_float_key(y1));
+        }
+        __syncthreads();
+    }
+    K3_STAMP(4);
+    GridGeom gg;
+    {
+        const float ex0 = fdt_key_float(s_ext[0]), ey0 = fdt_key_float(s_ext[1]);
+        const float ex1 = fdt_key_float(s_ext[2]), ey1 = fdt_key_float(s_ext[3]);
+        const float ext = fmaxf(ex1 - ex0, ey1 - ey0);
+        gg.ok = (k > 0) && (ext > 0.0f) && (ext < INFINITY);
+        gg.x0 = ex0; gg.y0 = ey0;
+        gg.inv0 = gg.ok ? 32.0f / ext : 0.0f;
+        gg.c0 = gg.ok ? ext / 32.0f : 0.0f;
+        if (!(gg.inv0 > 0.0f && gg.inv0 < INFINITY && gg.c0 > 0.0f)) gg.ok = 0;
+    }
+
+    // =========================================================== stage 3: lazy greedy NMS in rounds of ROUND candidates
+    const float thr = P.nms_thresh;
+    const float prune = 0.99f * thr;        // IoU <= ratio of the longer sides; 1 % margin covers fp32 rounding of IoU
+    const int max_keep = P.max_keep;
+    int nkept = 0;
+
+    // tests candidate (bj, aj, sj) against every kept box that could suppress it; work split over TPC threads (q)
+    auto suppressed_by_kept = [&](const float4 bj, const float aj, const float sj, const bool regular, const int q) -> bool {
+        bool brute = !regular || !gg.ok;
+        if (!brute) {
+            float c = gg.c0, inv = gg.inv0, cprev = 0.0f;
+            int G = 32;
+#pragma unroll
+            for (int lev = 0; lev < NLEV; ++lev, cprev = c, c *= 2.0f, inv *= 0.5f, G >>= 1) {
+                if (c < prune * sj) continue;                    // every box of this level is too small to reach thr
+                if (cprev * prune > sj) break;                   // this and all coarser levels hold boxes too large
+                const int cx0 = cell_of(bj.x, gg.x0, inv, G), cx1 = cell_of(bj.z, gg.x0, inv, G);
+                const int cy0 = cell_of(bj.y, gg.y0, inv, G), cy1 = cell_of(bj.w, gg.y0, inv, G);
+                const int nx = cx1 - cx0 + 1, nc = nx * (cy1 - cy0 + 1);
+                if (nc > MAX_QUERY_CELLS) { brute = true; break; }
+                const int base = grid_off(lev);
+                for (int ci = q; ci < nc; ci += TPC) {
+                    const int cy = ci / nx, cx = ci - cy * nx;
+                    const int cell = base + (cy0 + cy) * G + cx0 + cx;
+                    const int n = min(cell_cnt[cell], CELL_CAP);
+                    for (int t = 0; t < n; ++t) {
+                        const float4 bi = cbox[cell_items[cell * CELL_CAP + t]];
+                        if (fdt_suppresses(bi, box_area(bi), bj, aj, thr)) return true;
                     }
                 }
             }
-            __syncthreads();
-            prefix |= (uint64_t)s_sel[0] << shift;
-            pmask |= (uint64_t)0xff << shift;
-            need = s_sel[1];
-            const bool done = (s_sel[2] == need);
-            __syncthreads();
-            if (done) break;
         }
-        if (tid == 0) s_cnt = 0;
-        __syncthreads();
-        for (int base = 0; base < n_c; base += K3_THREADS) {
-            int i = base + tid;
-            uint64_t key = 0;
-            bool take = false;
-            if (i < n_c) { key = gkeys[i]; take = key >= prefix; }
-            unsigned bal = __ballot_sync(0xffffffffu, take);
-            int wbase = 0;
-            if (lane == 0 && bal) wbase = atomicAdd(&s_cnt, __popc(bal));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (take) skeys[wbase + __popc(bal & ((1u << lane) - 1u))] = key;
+        if (!brute) {
+            const int nb = s_nbig;
+            for (int t = q; t < nb; t += TPC) {
+                const float4 bi = cbox[big[t]];
+                if (fdt_suppresses(bi, box_area(bi), bj, aj, thr)) return true;
+            }
+        } else {
+            const int nk = min(nkept, max_keep);
+            for (int t = q; t < nk; t += TPC) {
+                const float4 bi = cbox[klist[t]];
+                if (fdt_suppresses(bi, box_area(bi), bj, aj, thr)) return true;
+            }
         }
-        __syncthreads();
-        n_sorted = s_cnt;           // == nms_top_k (keys are unique)
-    }
+        return false;
+    };
 
-    // ---------------- bitonic sort, descending, padded with the minimum key
-    int P2 = 2;
-    while (P2 < n_sorted) P2 <<= 1;
-    for (int i = n_sorted + tid; i < P2; i += K3_THREADS) skeys[i] = 0;
-    __syncthreads();
-    if (n_sorted > 1) {
-        for (int size = 2; size <= P2; size <<= 1) {
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int t = tid; t < (P2 >> 1); t += K3_THREADS) {
-                    int i = 2 * t - (t & (stride - 1));
-                    int j = i + stride;
-                    uint64_t a = skeys[i], c = skeys[j];
-                    bool desc = (i & size) == 0;
-                    if ((a < c) == desc) { skeys[i] = c; skeys[j] = a; }
+    for (int pos = 0; pos < k && nkept < max_keep; pos += ROUND) {
+        // ---- phase A: the round's candidates against the kept boxes (spatial grid + always-tested list)
+        {
+            const int cidx = tid / TPC, q = tid % TPC;
+            const int j = pos + cidx;
+            bool alive = false;
+            if (j < k) {
+                const float4 bj = cbox[j];
+                const float sj = fmaxf(bj.z - bj.x, bj.w - bj.y);
+                alive = !suppressed_by_kept(bj, box_area(bj), sj, box_regular(bj), q);
+            }
+            // all TPC threads of a candidate sit in one warp: AND their verdicts
+            const unsigned bal = __ballot_sync(0xffffffffu, alive);
+            const unsigned grp = ((1u << TPC) - 1u) << ((lane / TPC) * TPC);
+            if (q == 0) s_flag[cidx] = (j < k) && ((bal & grp) == grp);
+        }
+        K3_ACC(0);
+        for (int i = tid; i < ROUND * (ROUND / 32); i += K3_THREADS) (&sv_rows[0][0])[i] = 0;
+        if (tid < ROUND / 32) { s_keptw[tid] = 0; s_deadw[tid] = 0; }
+        __syncthreads();
+        // ---- compact the survivors (order preserved) with their boxes
+        int S;
+        {
+            int f = (tid < ROUND) ? s_flag[tid] : 0;
+            unsigned bal = __ballot_sync(0xffffffffu, f);
+            if (tid < ROUND && lane == 0) s_warp[warp] = __popc(bal);
+            __syncthreads();
+            int before = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < ROUND / 32; ++w) { int c = s_warp[w]; if (w < warp) before += c; tot += c; }
+            S = tot;
+            if (f) {
+                const int r = before + __popc(bal & ((1u << lane) - 1u));
+                const float4 bx = cbox[pos + tid];
+                sv_box[r] = bx; sv_area[r] = box_area(bx); sv_side[r] = fmaxf(bx.z - bx.x, bx.w - bx.y);
+                sv_pos[r] = (uint16_t)(pos + tid);
+            }
+        }
+        __syncthreads();
+        K3_ACC(1);
+        // ---- phase B: suppression bits among the survivors (a earlier than b), then dependency resolution
+        for (int p = tid; p < S * S; p += K3_THREADS) {
+            const int a = p / S, bb = p - a * S;
+            if (a >= bb) continue;
+            const float sa = sv_side[a], sb = sv_side[bb];
+            if (sa < prune * sb || sb < prune * sa) continue;            // longer-side ratio bounds IoU (NaN -> test)
+            if (fdt_suppresses(sv_box[a], sv_area[a], sv_box[bb], sv_area[bb], thr)) atomicOr(&sv_rows[bb][a >> 5], 1u << (a & 31));
+        }
+        __syncthreads();
+        K3_ACC(2);
+        // survivor b is kept iff every earlier survivor that suppresses it is dead; dead iff one of them is kept.
+        // The earliest undecided survivor always resolves, so this terminates; statuses never change once set.
+        {
+            int status = (tid < S) ? 0 : 3;          // 0 undecided, 1 kept, 2 dead, 3 not a survivor
+            for (;;) {
+                if (tid == 0) s_unknown = 0;
+                __syncthreads();
+                if (status == 0) {
+                    bool any_kept = false, all_dead = true;
+#pragma unroll
+                    for (int w = 0; w < ROUND / 32; ++w) {
+                        const unsigned row = sv_rows[tid][w];
+                        any_kept |= (row & s_keptw[w]) != 0;
+                        all_dead &= (row & ~s_deadw[w]) == 0;
+                    }
+                    if (any_kept) { status = 2; atomicOr(&s_deadw[tid >> 5], 1u << (tid & 31)); }
+                    else if (all_dead) { status = 1; atomicOr(&s_keptw[tid >> 5], 1u << (tid & 31)); }
+                    else s_unknown = 1;
                 }
                 __syncthreads();
+                const bool again = s_unknown != 0;
+                __syncthreads();
+                if (!again) break;
             }
-        }
-    }
-    const int k = min(n_sorted, P.nms_top_k);                 // box_utils.py:299 idx[-top_k:]
-
-    // ---------------- boxes of the selected candidates (decode only what NMS will look at)
-    for (int j = tid; j < k; j += K3_THREADS) {
-        uint32_t p = (uint32_t)skeys[j];
-        float4 bx;
-        if (MODE == MODE_DETECT) {
-            float4 l = __ldg(reinterpret_cast<const float4 *>(P.loc) + ((int64_t)b * P.N + p));
-            float4 pr = __ldg(reinterpret_cast<const float4 *>(P.priors) + p);
-            bx = fdt_decode1(l, pr, P.v0, P.v1);              // detection.py:55
-        } else {
-            bx = __ldg(reinterpret_cast<const float4 *>(P.boxes) + p);
-        }
-        cbox[j] = bx;
-    }
-    __syncthreads();
-
-    // ---------------- lazy greedy NMS
-    const float thr = P.nms_thresh;
-    const int max_keep = P.max_keep;
-    int nkept = 0;
-    const int c = tid / GROUP, s = tid % GROUP;
-    const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << ((lane / GROUP) * GROUP));
-    for (int pos = 0; pos < k && nkept < max_keep; pos += CHUNK) {
-        // phase A: candidate j against every box kept so far
-        {
-            const int j = pos + c;
-            const bool valid = j < k;
-            const float4 bj = cbox[valid ? j : 0];
-            const float aj = (bj.z - bj.x) * (bj.w - bj.y);                  // box_utils.py:296
-            bool sup = false;
-            const int nk = min(nkept, max_keep);
-            for (int m0 = 0; m0 < nk; m0 += GROUP) {
-                int m = m0 + s;
-                if (valid && m < nk) {
-                    float4 bi; float ai;
-                    if (KEPT_COPY) { bi = kbox[m]; ai = karea[m]; }
-                    else { bi = cbox[kpos[m]]; ai = (bi.z - bi.x) * (bi.w - bi.y); }
-                    sup = fdt_suppresses(bi, ai, bj, aj, thr);
-                }
-                if (__any_sync(gmask, sup)) { sup = true; break; }
-            }
-            if (s == 0) s_flag[c] = valid && !sup;
-        }
-        __syncthreads();
-        // phase B: 64x64 intra-chunk mask; warp w owns rows 2w, 2w+1, lanes own columns lane, lane+32
-        {
-            const int j0 = pos + lane, j1 = pos + lane + 32;
-            const float4 b0 = cbox[j0 < k ? j0 : 0], b1 = cbox[j1 < k ? j1 : 0];
-            const float a0 = (b0.z - b0.x) * (b0.w - b0.y), a1 = (b1.z - b1.x) * (b1.w - b1.y);
-            const bool f0 = s_flag[lane], f1 = s_flag[lane + 32];
+            K3_ACC(3);
+            // ---- append the newly kept boxes (in order) and register them in the grid
+            int before = 0, tot = 0;
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int i = 2 * warp + r;
-                uint64_t word = 0;
-                if (s_flag[i]) {                                            // warp-uniform
-                    const float4 bi = cbox[pos + i];
-                    const float ai = (bi.z - bi.x) * (bi.w - bi.y);
-                    bool t0 = f0 && lane > i && fdt_suppresses(bi, ai, b0, a0, thr);
-                    bool t1 = f1 && lane + 32 > i && fdt_suppresses(bi, ai, b1, a1, thr);
-                    unsigned lo = __ballot_sync(0xffffffffu, t0), hi = __ballot_sync(0xffffffffu, t1);
-                    word = (uint64_t)lo | ((uint64_t)hi << 32);
+            for (int w = 0; w < ROUND / 32; ++w) { const int c = __popc(s_keptw[w]); if (w < (tid >> 5)) before += c; tot += c; }
+            if (status == 1) {
+                const int slot = nkept + before + __popc(s_keptw[tid >> 5] & ((1u << (tid & 31)) - 1u));
+                const int ps = sv_pos[tid];
+                if (slot < max_keep) klist[slot] = (uint16_t)ps;
+                const float4 bx = sv_box[tid];
+                bool to_big = true;
+                if (gg.ok && box_regular(bx)) {
+                    const int lev = level_of(sv_side[tid], gg.c0);
+                    if (lev < NLEV) {
+                        const int G = 32 >> lev;
+                        const float inv = gg.inv0 / (float)(1 << lev);
+                        const int cx0 = cell_of(bx.x, gg.x0, inv, G), cx1 = cell_of(bx.z, gg.x0, inv, G);
+                        const int cy0 = cell_of(bx.y, gg.y0, inv, G), cy1 = cell_of(bx.w, gg.y0, inv, G);
+                        if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) <= 9) {
+                            to_big = false;
+                            for (int cy = cy0; cy <= cy1; ++cy)
+                                for (int cx = cx0; cx <= cx1; ++cx) {
+                                    const int cell = grid_off(lev) + cy * G + cx;
+                                    const int sl = atomicAdd(&cell_cnt[cell], 1);
+                                    if (sl < CELL_CAP) cell_items[cell * CELL_CAP + sl] = (uint16_t)ps;
+                                    else to_big = true;          // full cell: also list it where everybody looks
+                                }
+                        }
+                    }
                 }
-                if (lane == 0) s_mask[i] = word;
+                if (to_big) big[atomicAdd(&s_nbig, 1)] = (uint16_t)ps;
             }
+            nkept += tot;
         }
         __syncthreads();
-        // warp-serial mask reduction
-        if (warp == 0) {
-            unsigned lo = __ballot_sync(0xffffffffu, s_flag[lane]), hi = __ballot_sync(0xffffffffu, s_flag[lane + 32]);
-            uint64_t remv = ~((uint64_t)lo | ((uint64_t)hi << 32));
-            uint64_t keptbits = 0;
-#pragma unroll
-            for (int i = 0; i < CHUNK; ++i) {
-                uint64_t mi = s_mask[i];
-                if (!((remv >> i) & 1ull)) { keptbits |= 1ull << i; remv |= mi; }
-            }
-            if (lane == 0) s_keptbits = keptbits;
-        }
-        __syncthreads();
-        const uint64_t kb = s_keptbits;
-        if (tid < CHUNK && ((kb >> tid) & 1ull)) {
-            int slot = nkept + __popcll(kb & ((1ull << tid) - 1ull));
-            if (slot < max_keep) {
-                kpos[slot] = pos + tid;
-                if (KEPT_COPY) {
-                    float4 bx = cbox[pos + tid];
-                    kbox[slot] = bx;
-                    karea[slot] = (bx.z - bx.x) * (bx.w - bx.y);
-                }
-            }
-        }
-        nkept += __popcll(kb);
-        __syncthreads();
+        K3_ACC(4);
+        if (prof) pacc[5] += 1;
     }
     nkept = min(nkept, max_keep);
+    if (prof) { for (int q = 0; q < 6; ++q) P.prof[5 + q] = pacc[q]; P.prof[12] = nkept; P.prof[13] = k; P.prof[14] = s_nbig; }
 
-    // ---------------- outputs
+    // =========================================================== stage 4: outputs
     if (MODE == MODE_DETECT) {
         const int top_k = P.top_k;
         const int cnt = min(nkept, top_k);                                   // detection.py:80
@@ -344,7 +558,7 @@ k_sort_nms(const SortNmsParams P)
             int r = t / 5, col = t - 5 * r;
             float v = 0.0f;
             if (r < cnt) {
-                int ps = kpos[r];
+                int ps = klist[r];
                 if (col == 0) v = fdt_key_float((uint32_t)(skeys[ps] >> 32));
                 else {
                     const float *bx = reinterpret_cast<const float *>(cbox + ps);
@@ -355,7 +569,7 @@ k_sort_nms(const SortNmsParams P)
         }
         if (P.kept_prior) {
             int64_t *kp = P.kept_prior + (int64_t)(b * P.C + cl) * top_k;
-            for (int r = tid; r < top_k; r += K3_THREADS) kp[r] = r < cnt ? (int64_t)(uint32_t)skeys[kpos[r]] : -1;
+            for (int r = tid; r < top_k; r += K3_THREADS) kp[r] = r < cnt ? (int64_t)(uint32_t)skeys[klist[r]] : -1;
         }
         if (P.counts && tid == 0) P.counts[b * P.C + cl] = cnt;
         if (cl == 1) {                                                       // class-0 plane stays zero (:48, :63)
@@ -369,42 +583,49 @@ k_sort_nms(const SortNmsParams P)
         }
     } else {
         for (int64_t t = tid; t < P.n; t += K3_THREADS)
-            P.keep[t] = t < nkept ? (int64_t)(uint32_t)skeys[kpos[t]] : 0;    // box_utils.py:289 zero-initialised
+            P.keep[t] = t < nkept ? (int64_t)(uint32_t)skeys[klist[t]] : 0;   // box_utils.py:289 zero-initialised
         if (tid == 0) *P.count_out = nkept;
     }
+    K3_STAMP(11);
+#undef K3_STAMP
+#undef K3_ACC
 }
 
-struct SmemPlan { int off_cbox, off_kbox, off_karea, off_kpos, total; };
+struct SmemPlan { int key_cap, off_cbox, off_scr, off_big, off_klist, total; };
 
-SmemPlan plan_smem(int kcap, int max_keep, bool kept_copy)
+SmemPlan plan_smem(int kcap, int max_keep)
 {
+    auto up16 = [](int x) { return (x + 15) / 16 * 16; };
     SmemPlan s;
-    int off = SORT_CAP * 8;
-    s.off_cbox = off; off += ((kcap * 16 + 15) / 16) * 16;
-    s.off_kbox = off; if (kept_copy) off += max_keep * 16;
-    s.off_karea = off; if (kept_copy) off += ((max_keep * 4 + 15) / 16) * 16;
-    s.off_kpos = off; off += ((max_keep * 4 + 15) / 16) * 16;
+    s.key_cap = kcap + SORT_SLACK;
+    int off = up16(s.key_cap * 8);
+    s.off_cbox = off; off += up16(kcap * 16);
+    const int scr_sort = 2 * NB * 4, scr_grid = NCELLS * 4 + NCELLS * CELL_CAP * 2;
+    s.off_scr = off; off += up16(scr_sort > scr_grid ? scr_sort : scr_grid);
+    s.off_big = off; off += up16(kcap * 2);
+    s.off_klist = off; off += up16(max_keep * 2);
     s.total = off;
     return s;
 }
 
+static long long *g_prof_dev = nullptr;
+
 template <int MODE>
 int launch_sort_nms(SortNmsParams &P, int lists, int kcap, cudaStream_t st)
 {
-    SmemPlan sp = plan_smem(kcap, P.max_keep, true);
-    const int limit = FDT_SMEM_MAX - 2048;      // static shared memory of k_sort_nms
-    bool kept_copy = sp.total <= limit;
-    if (!kept_copy) sp = plan_smem(kcap, P.max_keep, false);
+    const char *env = getenv("FDT_K3_PROFILE");
+    if (env && env[0] == '1') {
+        if (!g_prof_dev) { FDT_CUDA(cudaMalloc(&g_prof_dev, 32 * sizeof(long long))); }
+        FDT_CUDA(cudaMemsetAsync(g_prof_dev, 0, 32 * sizeof(long long), st));
+        P.prof = g_prof_dev;
+    }
+    SmemPlan sp = plan_smem(kcap, P.max_keep);
+    const int limit = FDT_SMEM_MAX - 20480;      // static shared memory of k_sort_nms (round buffers)
     FDT_REQUIRE(sp.total <= limit, FDT_E_UNSUPPORTED,
                 "nms_top_k=%d / max_keep=%d need %d bytes of shared memory (limit %d)", kcap, P.max_keep, sp.total, limit);
-    P.off_cbox = sp.off_cbox; P.off_kbox = sp.off_kbox; P.off_karea = sp.off_karea; P.off_kpos = sp.off_kpos;
-    if (kept_copy) {
-        FDT_CUDA(cudaFuncSetAttribute(k_sort_nms<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
-        k_sort_nms<MODE, true><<<lists, K3_THREADS, sp.total, st>>>(P);
-    } else {
-        FDT_CUDA(cudaFuncSetAttribute(k_sort_nms<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
-        k_sort_nms<MODE, false><<<lists, K3_THREADS, sp.total, st>>>(P);
-    }
+    P.key_cap = sp.key_cap; P.off_cbox = sp.off_cbox; P.off_scr = sp.off_scr; P.off_big = sp.off_big; P.off_klist = sp.off_klist;
+    FDT_CUDA(cudaFuncSetAttribute(k_sort_nms<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+    k_sort_nms<MODE><<<lists, K3_THREADS, sp.total, st>>>(P);
     FDT_LAUNCH_CHECK();
     return FDT_OK;
 }
@@ -502,6 +723,18 @@ FDT_API int fdt_detect(const float *loc, const float *conf, const float *priors,
     if (rc != FDT_OK) return rc;
     return fdt_detect_sort_nms(loc, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1,
                                out, counts, kept_prior, ws, ws_bytes, stream);
+}
+
+// Diagnostics: with FDT_K3_PROFILE=1 in the environment, CTA 0 of k_sort_nms records clock64 deltas per phase:
+// [0] key min/max, [1] histogram+scan(+select), [2] scatter, [3] rank+permute, [4] decode+extent, [5..9] summed over
+// rounds: phase A, compaction, phase B pairs, resolve, insert; [10] rounds, [11] output, [12] kept, [13] k, [14] big list.
+FDT_API int fdt_debug_k3_profile(long long *out32_h)
+{
+    FDT_REQUIRE(out32_h != nullptr, FDT_E_INVALID, "fdt_debug_k3_profile: null output");
+    FDT_REQUIRE(g_prof_dev != nullptr, FDT_E_INVALID, "fdt_debug_k3_profile: run with FDT_K3_PROFILE=1 first");
+    FDT_CUDA(cudaDeviceSynchronize());
+    FDT_CUDA(cudaMemcpy(out32_h, g_prof_dev, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return FDT_OK;
 }
 
 FDT_API size_t fdt_nms_workspace_bytes(int64_t n)

@@ -74,8 +74,8 @@ int fdt_log_sum_exp(const float *x, int64_t R, int C, float *out, void *ws, size
 
 /* ---- N1  nms  (layers/box_utils.py:275-340) ------------------------------------------------------
  * boxes[n,4], scores[n] -> keep[n] int64 zero-padded (indices into the input, descending score),
- * *count (device int64).  Sort ties: higher index first.  Limits: min(n, top_k) <= FDT_MAX_NMS_TOP_K
- * (top_k <= 0 means n, as idx[-0:] does) and min(n, top_k) <= 5000 when run to completion. */
+ * *count (device int64).  Sort ties: higher index first.  top_k <= 0 means n, as idx[-0:] does.
+ * Limit: min(n, top_k) <= ~6000 (28 B of shared memory per candidate; FDT_E_UNSUPPORTED beyond). */
 size_t fdt_nms_workspace_bytes(int64_t n);
 int fdt_nms(const float *boxes, const float *scores, int64_t n, float overlap, int64_t top_k,
             int64_t *keep, int64_t *count, void *ws, size_t ws_bytes, fdt_stream_t stream);
@@ -85,7 +85,8 @@ int fdt_nms(const float *boxes, const float *scores, int64_t n, float overlap, i
  * in keep order, zero padded; class-0 plane zero.  Optional: counts[B,C] int32 rows written;
  * kept_prior[B,C,top_k] int64 prior index per row (-1 padding).  Candidates: score > conf_thresh
  * (strict); exactly one candidate yields no detection (reference quirk, detection.py:66-72).
- * Limits: 1 <= nms_top_k <= FDT_MAX_NMS_TOP_K, 1 <= top_k <= nms_top_k ... see DESIGN.md. */
+ * Limits: nms_top_k <= ~6500 (26 B of shared memory per candidate + 2 B per kept row; the reference uses 5000);
+ * FDT_E_UNSUPPORTED beyond.  See DESIGN.md. */
 size_t fdt_detect_workspace_bytes(int B, int64_t N, int C);
 int fdt_detect(const float *loc, const float *conf, const float *priors,
                int B, int64_t N, int C, int top_k, int nms_top_k,
@@ -105,6 +106,9 @@ int fdt_detect_sort_nms(const float *loc, const float *priors, int B, int64_t N,
                         void *ws, size_t ws_bytes, fdt_stream_t stream);
 /* Number of candidates per (image, class>=1) list after stage 1: copies B*(C-1) int32 to counts_out (device). */
 int fdt_detect_candidate_counts(const void *ws, int B, int C, int32_t *counts_out, fdt_stream_t stream);
+
+/* Diagnostics (FDT_K3_PROFILE=1): per-phase clock64 deltas of CTA 0 of the last fdt_detect_sort_nms / fdt_nms launch. */
+int fdt_debug_k3_profile(long long *out32_h);
 
 /* ---- host-buffer variants (the reference-facing call when tensors live on the CPU) --------------
  * All pointers are HOST pointers (pinned memory makes the copies asynchronous).  The context owns

@@ -202,12 +202,19 @@ def test_detect_all_priors_are_candidates(layers):
 
 @pytest.mark.parametrize("args,nms_top_k", [((2, 0, 750, 0.3, 0.5), None), ((2, 0, 750, 0.2, 0.35), None),
                                             ((2, 0, 10, 0.05, 0.3), None), ((2, 0, 200, 0.05, 0.3), 300),
-                                            ((2, 0, 750, 0.05, 0.3), 8192)])
+                                            ((2, 0, 750, 0.05, 0.3), 6000)])
 def test_detect_production_thresholds(layers, args, nms_top_k):
     pri = synth.priors_numpy(640, 480)
     loc, conf = synth.detect_inputs(3, pri, 79, args[3], "random")
     assert_same(run_detect(layers, loc, conf, pri, args, nms_top_k=nms_top_k),
                 oracle_detect(loc, conf, pri, args, nms_top_k=nms_top_k))
+
+
+def test_detect_nms_top_k_beyond_shared_memory_is_refused(layers):
+    pri = synth.priors_numpy(640, 640)
+    loc, conf = synth.detect_inputs(1, pri, 1, 0.05)
+    with pytest.raises(NotImplementedError, match="shared memory"):
+        run_detect(layers, loc, conf, pri, nms_top_k=8192)
 
 
 def test_detect_three_classes(layers):
@@ -233,3 +240,88 @@ def test_detect_flat_reference_shapes(layers, golden):
     det = layers.Detect(2, 0, 750, 0.3, 0.5)
     out = det(cu(loc.reshape(4, -1)), cu(conf.reshape(-1, 2)), cu(pri))
     np.testing.assert_allclose(npy(out), g["small_out"], rtol=RTOL, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------- adversarial inputs for the
+# bucket sort (score distributions) and the spatial grid (box geometry); the oracle defines the answer
+def _rand_boxes(rng, n, lo=0.0, hi=1.0, smin=0.02, smax=0.15):
+    ctr = rng.uniform(lo, hi, (n, 2)); wh = rng.uniform(smin, smax, (n, 2)) * (hi - lo)
+    return np.concatenate([ctr - wh / 2, ctr + wh / 2], 1).astype(np.float32)
+
+
+def _check_nms(layers, boxes, scores, thr, topk):
+    keep, count = layers.box_utils.nms(cu(boxes), cu(scores), thr, topk)
+    rk, rc = orc.nms(boxes, scores, thr, topk)
+    assert count == rc, (count, rc)
+    assert np.array_equal(npy(keep), rk)
+
+
+@pytest.mark.parametrize("case", ["near_equal", "all_equal", "wide_range", "negative", "two_values", "one_bucket_overflow"])
+def test_nms_score_distributions(layers, case):
+    rng = np.random.Generator(np.random.PCG64(sum(map(ord, case))))
+    n = 6000
+    boxes = _rand_boxes(rng, n)
+    if case == "near_equal":        # distinct scores a few ulps apart: one bucket holds everything -> radix-select fallback
+        scores = (np.float32(0.5) + np.arange(n, dtype=np.float32) * np.float32(6e-8)).astype(np.float32)
+        scores = rng.permutation(scores)
+    elif case == "all_equal":       # ties resolved by index (higher first)
+        scores = np.full(n, 0.7, np.float32)
+    elif case == "wide_range":
+        scores = np.exp(rng.uniform(-60, 60, n)).astype(np.float32)
+    elif case == "negative":
+        scores = rng.standard_normal(n).astype(np.float32) * 100
+    elif case == "two_values":
+        scores = rng.choice(np.array([0.25, 0.75], np.float32), n)
+    else:                           # 5900 keys share one bucket, 100 spread far above
+        scores = np.concatenate([np.float32(0.1) + np.arange(5900, dtype=np.float32) * np.float32(1e-8),
+                                 rng.uniform(1, 1000, 100).astype(np.float32)]).astype(np.float32)
+        scores = rng.permutation(scores)
+    _check_nms(layers, boxes, scores, 0.4, 5000)
+
+
+@pytest.mark.parametrize("case", ["pixels", "identical", "huge_and_tiny", "zero_area_far_apart", "inverted", "nan_inf",
+                                  "thin", "tiny_thr", "thr_above_one", "dense_cells", "negative_coords", "single_point"])
+def test_nms_box_geometry(layers, case):
+    rng = np.random.Generator(np.random.PCG64(sum(map(ord, case))))
+    n, thr, topk = 3000, 0.3, 5000
+    boxes = _rand_boxes(rng, n)
+    if case == "pixels":
+        boxes = _rand_boxes(rng, n, 0, 1920, 0.01, 0.1)
+    elif case == "identical":
+        boxes = np.tile(np.array([[0.2, 0.2, 0.5, 0.6]], np.float32), (n, 1)); boxes[::7] += np.float32(0.31)
+    elif case == "huge_and_tiny":
+        boxes[:300] = _rand_boxes(rng, 300, 0, 1, 0.6, 1.5); boxes[300:900] = _rand_boxes(rng, 600, 0, 1, 1e-4, 1e-3)
+    elif case == "zero_area_far_apart":       # 0/0 IoU = NaN suppresses at any distance (box_utils.py:337-339)
+        pts = rng.uniform(0, 1, (200, 2)).astype(np.float32); boxes[:200] = np.concatenate([pts, pts], 1)
+        boxes[200:260, 2] = boxes[200:260, 0]                                  # zero width, positive height
+    elif case == "inverted":
+        boxes[:100, [0, 2]] = boxes[:100, [2, 0]]
+    elif case == "nan_inf":
+        boxes[5, 1] = np.nan; boxes[77, 2] = np.inf; boxes[300, 0] = -np.inf; boxes[1500] = np.nan
+    elif case == "thin":
+        boxes[:1500, 3] = boxes[:1500, 1] + np.float32(1e-4); boxes[1500:, 2] = boxes[1500:, 0] + np.float32(0.9)
+    elif case == "tiny_thr":
+        thr = 0.004
+    elif case == "thr_above_one":
+        thr = 1.5
+    elif case == "dense_cells":               # thousands of small boxes inside one grid cell
+        boxes = _rand_boxes(rng, n, 0.50, 0.52, 0.01, 0.2); boxes[0] = [0, 0, 1, 1]
+    elif case == "negative_coords":
+        boxes = _rand_boxes(rng, n, -500, -100, 0.01, 0.1)
+    elif case == "single_point":
+        boxes = np.tile(np.array([[3, 3, 3, 3]], np.float32), (n, 1))
+    scores = rng.permutation(np.unique(rng.uniform(0, 1, 3 * n).astype(np.float32)))[:n].copy()
+    _check_nms(layers, boxes, scores, thr, topk)
+
+
+def test_detect_mixed_pyramid_levels_and_scores(layers):
+    """every pyramid level contributes candidates (boxes from 16 px to 512 px interact across grid levels)."""
+    pri = synth.priors_numpy(640, 640)
+    rng = np.random.Generator(np.random.PCG64(4242))
+    N = pri.shape[0]
+    loc = (rng.standard_normal((4, N, 4)) * 1.5).astype(np.float32)          # strong jitter: sizes vary by e^{+-0.3}
+    s1 = rng.uniform(0, 1, (4, N)).astype(np.float32)
+    s1[:, :25600] *= (rng.uniform(0, 1, (4, 25600)) < 0.1)                   # thin out level 0 so coarse levels matter
+    conf = np.stack([1 - s1, s1], -1).astype(np.float32)
+    for args in ((2, 0, 750, 0.05, 0.3), (2, 0, 750, 0.5, 0.7), (2, 0, 300, 0.05, 0.05)):
+        assert_same(run_detect(layers, loc, conf, pri, args), oracle_detect(loc, conf, pri, args))

@@ -1,0 +1,29 @@
+"""Diagnostics: per-phase cycle breakdown of k_sort_nms (CTA 0) on the headline workload.  FDT_K3_PROFILE=1 python tools_k3_profile.py [mode]"""
+import ctypes as C
+import os
+import sys
+os.environ["FDT_K3_PROFILE"] = "1"
+import torch
+import fdt_b200
+from fdt_b200 import _lib, synth
+from fdt_b200.layers import Detect
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "random"
+pri = synth.priors_numpy(640, 640)
+loc, conf = synth.detect_inputs(8, pri, 20262, 0.05, mode)
+det = Detect(2, 0, 750, 0.05, 0.3)
+args = [torch.from_numpy(a).cuda() for a in (loc, conf, pri)]
+for _ in range(3):
+    det(*args)
+torch.cuda.synchronize()
+out = (C.c_longlong * 32)()
+_lib.check(_lib.lib().fdt_debug_k3_profile(out))
+names = ["minmax", "hist+scan", "scatter", "rank+permute", "decode+extent", "A:kept-query", "compact", "B:pairs", "resolve",
+         "insert", "rounds", "output", "kept", "k", "nbig"]
+tot = sum(out[i] for i in list(range(10)) + [11])
+for i, n in enumerate(names):
+    if n in ("rounds", "kept", "k", "nbig"):
+        print(f"{n:14s} {out[i]}")
+    else:
+        print(f"{n:14s} {out[i]:9d} cyc  {100 * out[i] / max(tot, 1):5.1f}%")
+print("total", tot, "cycles =", tot / 1.965e3, "us @1.965GHz")
