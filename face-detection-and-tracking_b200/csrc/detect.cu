@@ -25,15 +25,15 @@ constexpr int K2_PER_THREAD = 8;
 constexpr int K2_TILE = K2_THREADS * K2_PER_THREAD;
 
 constexpr int K3_THREADS = 1024;
-constexpr int NB = 4096;                        // score buckets of the shared-memory bucket sort
-constexpr int SORT_SLACK = 256;                 // room for the bucket that straddles rank nms_top_k
-constexpr int RANK_U = (FDT_MAX_NMS_TOP_K + SORT_SLACK + K3_THREADS - 1) / K3_THREADS;
-constexpr int ROUND = 256;                      // sorted candidates examined per NMS round
-constexpr int TPC = K3_THREADS / ROUND;         // threads cooperating on one candidate in phase A
+constexpr int WIN = K3_THREADS;                 // sorted candidates examined per NMS round: one thread each
+constexpr int NB = 2048;                        // score buckets of the shared-memory bucket sort
+constexpr int BIG_BUCKET = 512;                 // a larger bucket inside the top-k range -> full bitonic sort fallback
 constexpr int NLEV = 5;                         // grid levels: 32, 16, 8, 4, 2 cells per side
 constexpr int NCELLS = 1024 + 256 + 64 + 16 + 4;
 constexpr int CELL_CAP = 12;
 constexpr int MAX_QUERY_CELLS = 64;
+constexpr int DEPS = 8;                         // stored earlier-suppressors per survivor (more -> re-query path)
+constexpr int KEPT_ROW_BYTES = 28;              // box 16 + key 8 + area 4
 
 enum { MODE_DETECT = 0, MODE_NMS = 1 };
 
@@ -98,6 +98,13 @@ __global__ void k_build_keys(const float *__restrict__ scores, int64_t n, uint64
 }
 
 // ------------------------------------------------------------------------------------------- K3
+struct SmemPlan {
+    int key_cap;                                   // entries of the key array (power of two >= kcap + 64)
+    int off_scr, off_kgrid, off_wbox, off_warea, off_wside, off_status, off_rbig, off_kbig;
+    int off_kbox, off_karea, off_kkey;             // < 0: kept arrays live in the global workspace
+    int total;
+};
+
 struct SortNmsParams {
     const uint64_t *keys;       // [lists, key_stride]
     const int32_t *counters;    // [lists] (MODE_DETECT)
@@ -117,9 +124,11 @@ struct SortNmsParams {
     int64_t *keep;              // [n] (MODE_NMS)
     int64_t *count_out;         // [1] (MODE_NMS)
     int64_t n;                  // MODE_NMS list length
-    int key_cap;                // entries in the shared-memory key array (>= nms_top_k + SORT_SLACK)
+    float4 *g_kbox;             // kept arrays in global memory (per list stride max_keep) when sm.off_kbox < 0
+    float *g_karea;
+    uint64_t *g_kkey;
+    SmemPlan sm;
     long long *prof;            // diagnostics: per-phase clock64 of CTA 0 (null unless FDT_K3_PROFILE=1)
-    int off_cbox, off_scr, off_big, off_klist;   // byte offsets into dynamic shared memory
 };
 
 // "i (kept, higher score) suppresses j": box_utils.py:322-339, union = (area_j - inter) + area_i,
@@ -149,11 +158,20 @@ __device__ __forceinline__ bool box_regular(const float4 b)
            fabsf(b.w) < INFINITY && a > 0.0f && a < INFINITY;
 }
 
+// Multi-level uniform grid over the extent of the first window's boxes.  Level l has (32 >> l)^2 cells; a box lives at the
+// smallest level whose cell is at least as long as the box's longer side and is registered in every cell it touches
+// (<= 3x3, else it goes to the "big" list every query scans).  The cell map is monotone in the coordinate (clamped), so
+// two intersecting boxes always share a cell at whatever level one of them is registered.
 struct GridGeom {
-    float x0, y0;          // origin = min corner over all regular candidate boxes
+    float x0, y0;          // origin = min corner
     float inv0;            // cells per unit length at level 0 (32 / extent)
     float c0;              // cell size at level 0
     int ok;                // 0: degenerate extent -> everything is "big"
+};
+struct Grid {              // views into shared memory
+    int *cnt;              // [NCELLS]
+    int *lev;              // [8] boxes registered per level
+    uint16_t *items;       // [NCELLS * CELL_CAP]
 };
 __device__ __forceinline__ int grid_off(int lev) { return lev == 0 ? 0 : lev == 1 ? 1024 : lev == 2 ? 1280 : lev == 3 ? 1344 : 1360; }
 __device__ __forceinline__ int cell_of(float x, float origin, float inv, int G)
@@ -161,7 +179,6 @@ __device__ __forceinline__ int cell_of(float x, float origin, float inv, int G)
     int c = __float2int_rd((x - origin) * inv);
     return max(0, min(G - 1, c));
 }
-// smallest level whose cell size is >= the box's longer side; NLEV if none (box is "big")
 __device__ __forceinline__ int level_of(float side, float c0)
 {
     float c = c0;
@@ -170,35 +187,112 @@ __device__ __forceinline__ int level_of(float side, float c0)
     return NLEV;
 }
 
+// Visits every item stored in a cell that box bj (longer side sj) touches, at every level whose boxes can reach IoU >= thr
+// with it (IoU <= ratio of the longer sides; `prune` = 0.99 * thr leaves a 1 % margin for fp32 rounding of IoU).
+// visit(item) returns true to stop.  Returns 0 = done, 1 = stopped by the visitor, 2 = too many cells: caller brute-forces.
+template <typename F>
+__device__ __forceinline__ int grid_query(const GridGeom &gg, const Grid &g, const float4 bj, const float sj, const float prune, F &&visit)
+{
+    float c = gg.c0, inv = gg.inv0, cprev = 0.0f;
+    int G = 32, base = 0;
+#pragma unroll 1
+    for (int lev = 0; lev < NLEV; ++lev, cprev = c, c *= 2.0f, inv *= 0.5f, base += G * G, G >>= 1) {
+        if (c < prune * sj) continue;                    // every box of this level is too small to reach thr
+        if (cprev * prune > sj) break;                   // this and all coarser levels only hold boxes too large
+        if (g.lev[lev] == 0) continue;
+        const int cx0 = cell_of(bj.x, gg.x0, inv, G), cx1 = cell_of(bj.z, gg.x0, inv, G);
+        const int cy0 = cell_of(bj.y, gg.y0, inv, G), cy1 = cell_of(bj.w, gg.y0, inv, G);
+        if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) > MAX_QUERY_CELLS) return 2;
+        for (int cy = cy0; cy <= cy1; ++cy)
+            for (int cx = cx0; cx <= cx1; ++cx) {
+                const int cell = base + cy * G + cx;
+                const int n = min(g.cnt[cell], CELL_CAP);
+                for (int t = 0; t < n; ++t)
+                    if (visit(g.items[cell * CELL_CAP + t])) return 1;
+            }
+    }
+    return 0;
+}
+// Registers `id`; false -> the caller must (also) put it on the big list (irregular, too large, or a cell was full).
+__device__ __forceinline__ bool grid_insert(const GridGeom &gg, const Grid &g, const float4 bx, const float side, const uint16_t id)
+{
+    if (!gg.ok || !box_regular(bx)) return false;
+    const int lev = level_of(side, gg.c0);
+    if (lev >= NLEV) return false;
+    const int G = 32 >> lev;
+    const float inv = gg.inv0 / (float)(1 << lev);
+    const int cx0 = cell_of(bx.x, gg.x0, inv, G), cx1 = cell_of(bx.z, gg.x0, inv, G);
+    const int cy0 = cell_of(bx.y, gg.y0, inv, G), cy1 = cell_of(bx.w, gg.y0, inv, G);
+    if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) > 9) return false;
+    bool ok = true;
+    const int base = grid_off(lev);
+    for (int cy = cy0; cy <= cy1; ++cy)
+        for (int cx = cx0; cx <= cx1; ++cx) {
+            const int cell = base + cy * G + cx;
+            const int sl = atomicAdd(&g.cnt[cell], 1);
+            if (sl < CELL_CAP) g.items[cell * CELL_CAP + sl] = id;
+            else ok = false;
+        }
+    atomicAdd(&g.lev[lev], 1);
+    return ok;
+}
+
+// exclusive prefix sum of one int per thread over the 1024-thread block; `total` = block sum
+__device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int n = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += n; }
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    return inc - v + s_warp[warp];
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(K3_THREADS, 1)
 k_sort_nms(const SortNmsParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    uint64_t *skeys = reinterpret_cast<uint64_t *>(smem);                    // [key_cap]
-    float4 *cbox = reinterpret_cast<float4 *>(smem + P.off_cbox);             // [kcap] boxes in sorted order
-    int *s_hist = reinterpret_cast<int *>(smem + P.off_scr);                  // sort: fill[NB] | start[NB]
+    uint64_t *skeys = reinterpret_cast<uint64_t *>(smem);                       // [key_cap] bucket-ordered, then sorted per window
+    int *s_hist = reinterpret_cast<int *>(smem + P.sm.off_scr);                  // sort: fill[NB] | start[NB]
     int *s_start = s_hist + NB;
-    int *cell_cnt = reinterpret_cast<int *>(smem + P.off_scr);                // nms:  cnt[NCELLS] | items[NCELLS*CELL_CAP]
-    uint16_t *cell_items = reinterpret_cast<uint16_t *>(cell_cnt + NCELLS);
-    uint16_t *big = reinterpret_cast<uint16_t *>(smem + P.off_big);           // [kcap] kept boxes every candidate tests
-    uint16_t *klist = reinterpret_cast<uint16_t *>(smem + P.off_klist);       // [max_keep] kept positions, in order
+    Grid rgrid, kgrid;                                                           // round grid aliases the sort scratch... see below
+    kgrid.cnt = reinterpret_cast<int *>(smem + P.sm.off_kgrid);
+    kgrid.lev = kgrid.cnt + NCELLS;
+    kgrid.items = reinterpret_cast<uint16_t *>(kgrid.lev + 8);
+    float4 *wbox = reinterpret_cast<float4 *>(smem + P.sm.off_wbox);             // [WIN] boxes of the current window
+    float *warea = reinterpret_cast<float *>(smem + P.sm.off_warea);
+    float *wside = reinterpret_cast<float *>(smem + P.sm.off_wside);
+    unsigned char *status = smem + P.sm.off_status;                              // [WIN] 0 undecided, 1 kept, 2 dead
+    uint16_t *rbig = reinterpret_cast<uint16_t *>(smem + P.sm.off_rbig);         // [WIN]
+    uint16_t *kbig = reinterpret_cast<uint16_t *>(smem + P.sm.off_kbig);         // [max_keep]
+    const int list = blockIdx.x;
+    float4 *kbox = P.sm.off_kbox >= 0 ? reinterpret_cast<float4 *>(smem + P.sm.off_kbox) : P.g_kbox + (int64_t)list * P.max_keep;
+    float *karea = P.sm.off_karea >= 0 ? reinterpret_cast<float *>(smem + P.sm.off_karea) : P.g_karea + (int64_t)list * P.max_keep;
+    uint64_t *kkey = P.sm.off_kkey >= 0 ? reinterpret_cast<uint64_t *>(smem + P.sm.off_kkey) : P.g_kkey + (int64_t)list * P.max_keep;
 
     __shared__ int s_sel[3];
-    __shared__ int s_placed, s_nbig, s_unknown;
+    __shared__ int s_placed, s_maxb, s_nrbig, s_nkbig;
     __shared__ unsigned s_kmin, s_kmax;
     __shared__ int s_hist8[256];
     __shared__ int s_warp[33];
     __shared__ unsigned s_ext[4];          // extent of the regular boxes as order-preserving keys
-    __shared__ unsigned char s_flag[ROUND];
-    __shared__ float4 sv_box[ROUND];
-    __shared__ float sv_area[ROUND], sv_side[ROUND];
-    __shared__ uint16_t sv_pos[ROUND];
-    __shared__ unsigned sv_rows[ROUND][ROUND / 32];
-    __shared__ unsigned s_keptw[ROUND / 32], s_deadw[ROUND / 32];
+    __shared__ int s_rgrid_cnt[NCELLS + 8];
+    __shared__ uint16_t s_rgrid_items[NCELLS * CELL_CAP];
+    rgrid.cnt = s_rgrid_cnt; rgrid.lev = s_rgrid_cnt + NCELLS; rgrid.items = s_rgrid_items;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int list = blockIdx.x;
     const int b = (MODE == MODE_DETECT) ? list / (P.C - 1) : 0;
     const int cl = (MODE == MODE_DETECT) ? 1 + list % (P.C - 1) : 0;
     const uint64_t *gkeys = P.keys + (int64_t)list * P.key_stride;
@@ -211,27 +305,47 @@ k_sort_nms(const SortNmsParams P)
 #define K3_STAMP(slot) do { if (prof) { long long now_ = clock64(); P.prof[slot] = now_ - pt; pt = now_; } } while (0)
 #define K3_ACC(slot) do { if (prof) { long long now_ = clock64(); pacc[slot] += now_ - pt; pt = now_; } } while (0)
 
-    // =========================================================== stage 1: top-k selection + sort (bucket sort)
-    // Monotone score -> bucket map, counting sort by bucket (descending), exact in-bucket ranking with the full
-    // 64-bit key.  Keys stream from global/L2 three times; only buckets that can reach rank < k are materialised.
+    // =========================================================== stage 1: top-k selection by bucket (counting) sort
+    // Monotone score -> bucket map; counting sort by bucket, descending; only buckets that can reach rank < k are
+    // materialised (bucket-contiguous, unordered inside a bucket).  Exact order inside buckets is produced lazily per
+    // NMS window.  Keys stay in registers across the three passes when the list has <= 8192 entries.
+    bool presorted = false;
+    int placed = 0;
+    unsigned kmin = 0;
+    float binv = 0.0f;
+    auto bucket = [&](uint64_t key) -> int { return min(NB - 1, (int)((float)((unsigned)(key >> 32) - kmin) * binv)); };
     if (k > 0) {
-        if (tid == 0) { s_kmin = 0xffffffffu; s_kmax = 0u; }
+        constexpr int KREG = 8;
+        const bool cached = n_c <= KREG * K3_THREADS;
+        uint64_t kreg[KREG];
+        if (cached) {
+#pragma unroll
+            for (int u = 0; u < KREG; ++u) { const int i = tid + u * K3_THREADS; kreg[u] = i < n_c ? gkeys[i] : 0; }
+        }
+        auto for_each_key = [&](auto &&body) {
+            if (cached) {
+#pragma unroll
+                for (int u = 0; u < KREG; ++u) { if (tid + u * K3_THREADS < n_c) body(kreg[u]); }
+            } else {
+                for (int i = tid; i < n_c; i += K3_THREADS) body(gkeys[i]);
+            }
+        };
+        if (tid == 0) { s_kmin = 0xffffffffu; s_kmax = 0u; s_maxb = 0; }
         for (int i = tid; i < 2 * NB; i += K3_THREADS) s_hist[i] = 0;
         __syncthreads();
         {
             unsigned lo = 0xffffffffu, hi = 0u;
-            for (int i = tid; i < n_c; i += K3_THREADS) { unsigned k32 = (unsigned)(gkeys[i] >> 32); lo = min(lo, k32); hi = max(hi, k32); }
+            for_each_key([&](uint64_t key) { unsigned k32 = (unsigned)(key >> 32); lo = min(lo, k32); hi = max(hi, k32); });
             lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
             if (lane == 0) { atomicMin(&s_kmin, lo); atomicMax(&s_kmax, hi); }
         }
         __syncthreads();
         K3_STAMP(0);
-        const unsigned kmin = s_kmin;
-        const float inv = (float)NB / ((float)(s_kmax - kmin) + 1.0f);
-        auto bucket = [&](uint64_t key) -> int { return min(NB - 1, (int)((float)((unsigned)(key >> 32) - kmin) * inv)); };
+        kmin = s_kmin;
+        binv = (float)NB / ((float)(s_kmax - kmin) + 1.0f);
         uint64_t tmin = 0;                                   // after the fallback select: only keys >= tmin take part
         for (int attempt = 0; attempt < 2; ++attempt) {
-            for (int i = tid; i < n_c; i += K3_THREADS) { uint64_t key = gkeys[i]; if (key >= tmin) atomicAdd(&s_hist[bucket(key)], 1); }
+            for_each_key([&](uint64_t key) { if (key >= tmin) atomicAdd(&s_hist[bucket(key)], 1); });
             __syncthreads();
             // descending exclusive scan: start[b] = number of keys in higher buckets
             int c[NB / K3_THREADS], sum = 0;
@@ -241,7 +355,7 @@ k_sort_nms(const SortNmsParams P)
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
             if (lane == 31) s_warp[warp] = inc;
-            if (tid == 0) s_placed = 0;
+            if (tid == 0) { s_placed = 0; s_maxb = 0; }
             __syncthreads();
             if (warp == 0) {
                 int w = s_warp[lane], winc = w;
@@ -250,19 +364,21 @@ k_sort_nms(const SortNmsParams P)
                 s_warp[lane] = winc - w;
             }
             __syncthreads();
-            int run = inc - sum + s_warp[warp];
+            int run = inc - sum + s_warp[warp], mb = 0;
 #pragma unroll
             for (int q = 0; q < NB / K3_THREADS; ++q) {
                 const int bq = NB - 1 - (tid * (NB / K3_THREADS) + q);
                 s_start[bq] = run;
                 s_hist[bq] = 0;                              // becomes the fill counter of the scatter pass
+                if (run < k) mb = max(mb, c[q]);
                 if (run < k && run + c[q] >= k) s_placed = run + c[q];      // exactly one bucket straddles rank k
                 run += c[q];
             }
+            if (mb > BIG_BUCKET) atomicMax(&s_maxb, mb);
             __syncthreads();
-            if (s_placed <= P.key_cap || attempt == 1) break;
-            // Degenerate score distribution (a single bucket larger than the slack): exact MSB radix select of the
-            // k-th largest key, then bucket only the k keys >= that threshold.
+            if (s_placed <= P.sm.key_cap || attempt == 1) break;
+            // Degenerate score distribution (the straddling bucket does not fit): exact MSB radix select of the k-th
+            // largest key, then bucket only the k keys >= that threshold.
             uint64_t prefix = 0, pmask = 0;
             int need = k;
             for (int shift = 56; shift >= 0; shift -= 8) {
@@ -309,247 +425,240 @@ k_sort_nms(const SortNmsParams P)
         }
         K3_STAMP(1);
         // scatter into bucket-contiguous order (arbitrary order inside a bucket)
-        for (int i = tid; i < n_c; i += K3_THREADS) {
-            uint64_t key = gkeys[i];
-            if (key < tmin) continue;
-            const int bq = bucket(key);
-            const int st = s_start[bq];
-            if (st < k) skeys[st + atomicAdd(&s_hist[bq], 1)] = key;
-        }
-        __syncthreads();
-        K3_STAMP(2);
-        // exact rank = bucket start + number of larger keys in the same bucket; permute through registers
-        const int placed = min(s_placed, P.key_cap);
-        uint64_t rk[RANK_U];
-        int rr[RANK_U];
-#pragma unroll
-        for (int u = 0; u < RANK_U; ++u) {
-            const int i = tid + u * K3_THREADS;
-            rr[u] = -1;
-            if (i < placed) {
-                const uint64_t key = skeys[i];
+        for_each_key([&](uint64_t key) {
+            if (key >= tmin) {
                 const int bq = bucket(key);
-                const int lo = s_start[bq], hi = lo + s_hist[bq];
-                int g = 0;
-                for (int t = lo; t < hi; ++t) g += skeys[t] > key;
-                rk[u] = key; rr[u] = lo + g;
+                const int st = s_start[bq];
+                if (st < k) skeys[st + atomicAdd(&s_hist[bq], 1)] = key;
             }
+        });
+        __syncthreads();
+        placed = min(s_placed, P.sm.key_cap);
+        if (s_maxb > BIG_BUCKET) {
+            // A bucket too large for the per-window ranking (e.g. thousands of equal scores): sort everything that was
+            // placed with a bitonic network (descending, padded with the minimum key).  Rare, slow, exact.
+            int P2 = 2;
+            while (P2 < placed) P2 <<= 1;
+            for (int i = placed + tid; i < P2; i += K3_THREADS) skeys[i] = 0;
+            __syncthreads();
+            for (int size = 2; size <= P2; size <<= 1)
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (int t = tid; t < (P2 >> 1); t += K3_THREADS) {
+                        int i = 2 * t - (t & (stride - 1));
+                        int j = i + stride;
+                        uint64_t a = skeys[i], c2 = skeys[j];
+                        bool desc = (i & size) == 0;
+                        if ((a < c2) == desc) { skeys[i] = c2; skeys[j] = a; }
+                    }
+                    __syncthreads();
+                }
+            presorted = true;
         }
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < RANK_U; ++u)
-            if (rr[u] >= 0 && rr[u] < k) skeys[rr[u]] = rk[u];
-        __syncthreads();
-        K3_STAMP(3);
+        K3_STAMP(2);
     }
 
-    // =========================================================== stage 2: boxes of the selected candidates + extent
-    {
-        float x0 = INFINITY, y0 = INFINITY, x1 = -INFINITY, y1 = -INFINITY;
-        for (int j = tid; j < k; j += K3_THREADS) {
-            const uint32_t p = (uint32_t)skeys[j];
-            float4 bx;
+    // =========================================================== stage 2: lazy greedy NMS over windows of sorted candidates
+    const float thr = P.nms_thresh;
+    const float prune = 0.99f * thr;
+    const int max_keep = P.max_keep;
+    int nkept = 0, rounds = 0;
+    GridGeom gg;
+    gg.ok = 0; gg.x0 = gg.y0 = gg.inv0 = gg.c0 = 0.0f;
+    for (int i = tid; i < NCELLS + 8; i += K3_THREADS) kgrid.cnt[i] = 0;        // cnt[] and lev[] are contiguous
+    if (tid == 0) s_nkbig = 0;
+
+    for (int lo = 0; lo < k && nkept < max_keep; ++rounds) {
+        // ---- window [lo, hi): whole buckets, at most WIN candidates
+        int hi;
+        if (presorted) hi = min(lo + WIN, k);
+        else {
+            const int e = min(lo + WIN, placed);
+            if (e == placed) hi = placed;
+            else {
+                const int bq = bucket(skeys[e - 1]);
+                const int bend = s_start[bq] + s_hist[bq];
+                hi = (bend == e) ? e : s_start[bq];          // buckets in range are <= BIG_BUCKET < WIN, so hi > lo
+            }
+        }
+        for (int i = tid; i < NCELLS + 8; i += K3_THREADS) rgrid.cnt[i] = 0;
+        if (tid == 0) { s_nrbig = 0; s_ext[0] = 0xffffffffu; s_ext[1] = 0xffffffffu; s_ext[2] = 0u; s_ext[3] = 0u; }
+        // ---- exact order inside the window: rank = bucket start + number of larger keys in the same bucket
+        const int j = lo + tid;
+        if (!presorted) {
+            uint64_t key = 0;
+            int r = -1;
+            if (j < hi) {
+                key = skeys[j];
+                const int bq = bucket(key);
+                const int blo = s_start[bq], bhi = blo + s_hist[bq];
+                int g = 0;
+                for (int t = blo; t < bhi; ++t) g += skeys[t] > key;
+                r = blo + g;
+            }
+            __syncthreads();
+            if (r >= 0) skeys[r] = key;
+        }
+        __syncthreads();
+        K3_ACC(0);
+        // ---- boxes of the window (decode only what NMS looks at), grid geometry from the first window
+        const bool valid = j < hi && j < k;
+        float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint64_t kj = 0;
+        if (valid) {
+            kj = skeys[j];
+            const uint32_t p = (uint32_t)kj;
             if (MODE == MODE_DETECT) {
                 const float4 l = __ldg(reinterpret_cast<const float4 *>(P.loc) + ((int64_t)b * P.N + p));
                 const float4 pr = __ldg(reinterpret_cast<const float4 *>(P.priors) + p);
-                bx = fdt_decode1(l, pr, P.v0, P.v1);              // detection.py:55, only for rows NMS can reach
+                bj = fdt_decode1(l, pr, P.v0, P.v1);              // detection.py:55
             } else {
-                bx = __ldg(reinterpret_cast<const float4 *>(P.boxes) + p);
+                bj = __ldg(reinterpret_cast<const float4 *>(P.boxes) + p);
             }
-            cbox[j] = bx;
-            if (box_regular(bx)) { x0 = fminf(x0, bx.x); y0 = fminf(y0, bx.y); x1 = fmaxf(x1, bx.z); y1 = fmaxf(y1, bx.w); }
         }
+        const float aj = box_area(bj);
+        const float sj = fmaxf(bj.z - bj.x, bj.w - bj.y);
+        const bool regj = valid && box_regular(bj);
+        wbox[tid] = bj; warea[tid] = aj; wside[tid] = sj;
+        if (rounds == 0) {
+            float x0 = regj ? bj.x : INFINITY, y0 = regj ? bj.y : INFINITY, x1 = regj ? bj.z : -INFINITY, y1 = regj ? bj.w : -INFINITY;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
-            x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
-        }
-        if (tid == 0) { s_ext[0] = 0xffffffffu; s_ext[1] = 0xffffffffu; s_ext[2] = 0u; s_ext[3] = 0u; s_nbig = 0; }
-        for (int i = tid; i < NCELLS; i += K3_THREADS) cell_cnt[i] = 0;      // the sort scratch is dead: it becomes the grid
-        __syncthreads();
-        if (lane == 0) {      // float min/max through the order-preserving integer map
-            atomicMin(&s_ext[0], fdt_float_key(x0)); atomicMin(&s_ext[1], fdt_float_key(y0));
-            atomicMax(&s_ext[2], fdt_float_key(x1)); atomicMax(&s_ext[3], fdt_float_key(y1));
-        }
-        __syncthreads();
-    }
-    K3_STAMP(4);
-    GridGeom gg;
-    {
-        const float ex0 = fdt_key_float(s_ext[0]), ey0 = fdt_key_float(s_ext[1]);
-        const float ex1 = fdt_key_float(s_ext[2]), ey1 = fdt_key_float(s_ext[3]);
-        const float ext = fmaxf(ex1 - ex0, ey1 - ey0);
-        gg.ok = (k > 0) && (ext > 0.0f) && (ext < INFINITY);
-        gg.x0 = ex0; gg.y0 = ey0;
-        gg.inv0 = gg.ok ? 32.0f / ext : 0.0f;
-        gg.c0 = gg.ok ? ext / 32.0f : 0.0f;
-        if (!(gg.inv0 > 0.0f && gg.inv0 < INFINITY && gg.c0 > 0.0f)) gg.ok = 0;
-    }
-
-    // =========================================================== stage 3: lazy greedy NMS in rounds of ROUND candidates
-    const float thr = P.nms_thresh;
-    const float prune = 0.99f * thr;        // IoU <= ratio of the longer sides; 1 % margin covers fp32 rounding of IoU
-    const int max_keep = P.max_keep;
-    int nkept = 0;
-
-    // tests candidate (bj, aj, sj) against every kept box that could suppress it; work split over TPC threads (q)
-    auto suppressed_by_kept = [&](const float4 bj, const float aj, const float sj, const bool regular, const int q) -> bool {
-        bool brute = !regular || !gg.ok;
-        if (!brute) {
-            float c = gg.c0, inv = gg.inv0, cprev = 0.0f;
-            int G = 32;
-#pragma unroll
-            for (int lev = 0; lev < NLEV; ++lev, cprev = c, c *= 2.0f, inv *= 0.5f, G >>= 1) {
-                if (c < prune * sj) continue;                    // every box of this level is too small to reach thr
-                if (cprev * prune > sj) break;                   // this and all coarser levels hold boxes too large
-                const int cx0 = cell_of(bj.x, gg.x0, inv, G), cx1 = cell_of(bj.z, gg.x0, inv, G);
-                const int cy0 = cell_of(bj.y, gg.y0, inv, G), cy1 = cell_of(bj.w, gg.y0, inv, G);
-                const int nx = cx1 - cx0 + 1, nc = nx * (cy1 - cy0 + 1);
-                if (nc > MAX_QUERY_CELLS) { brute = true; break; }
-                const int base = grid_off(lev);
-                for (int ci = q; ci < nc; ci += TPC) {
-                    const int cy = ci / nx, cx = ci - cy * nx;
-                    const int cell = base + (cy0 + cy) * G + cx0 + cx;
-                    const int n = min(cell_cnt[cell], CELL_CAP);
-                    for (int t = 0; t < n; ++t) {
-                        const float4 bi = cbox[cell_items[cell * CELL_CAP + t]];
-                        if (fdt_suppresses(bi, box_area(bi), bj, aj, thr)) return true;
-                    }
-                }
+            for (int o = 16; o > 0; o >>= 1) {
+                x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+                x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
             }
-        }
-        if (!brute) {
-            const int nb = s_nbig;
-            for (int t = q; t < nb; t += TPC) {
-                const float4 bi = cbox[big[t]];
-                if (fdt_suppresses(bi, box_area(bi), bj, aj, thr)) return true;
+            if (lane == 0) {      // float min/max through the order-preserving integer map
+                atomicMin(&s_ext[0], fdt_float_key(x0)); atomicMin(&s_ext[1], fdt_float_key(y0));
+                atomicMax(&s_ext[2], fdt_float_key(x1)); atomicMax(&s_ext[3], fdt_float_key(y1));
             }
-        } else {
-            const int nk = min(nkept, max_keep);
-            for (int t = q; t < nk; t += TPC) {
-                const float4 bi = cbox[klist[t]];
-                if (fdt_suppresses(bi, box_area(bi), bj, aj, thr)) return true;
-            }
-        }
-        return false;
-    };
-
-    for (int pos = 0; pos < k && nkept < max_keep; pos += ROUND) {
-        // ---- phase A: the round's candidates against the kept boxes (spatial grid + always-tested list)
-        {
-            const int cidx = tid / TPC, q = tid % TPC;
-            const int j = pos + cidx;
-            bool alive = false;
-            if (j < k) {
-                const float4 bj = cbox[j];
-                const float sj = fmaxf(bj.z - bj.x, bj.w - bj.y);
-                alive = !suppressed_by_kept(bj, box_area(bj), sj, box_regular(bj), q);
-            }
-            // all TPC threads of a candidate sit in one warp: AND their verdicts
-            const unsigned bal = __ballot_sync(0xffffffffu, alive);
-            const unsigned grp = ((1u << TPC) - 1u) << ((lane / TPC) * TPC);
-            if (q == 0) s_flag[cidx] = (j < k) && ((bal & grp) == grp);
-        }
-        K3_ACC(0);
-        for (int i = tid; i < ROUND * (ROUND / 32); i += K3_THREADS) (&sv_rows[0][0])[i] = 0;
-        if (tid < ROUND / 32) { s_keptw[tid] = 0; s_deadw[tid] = 0; }
-        __syncthreads();
-        // ---- compact the survivors (order preserved) with their boxes
-        int S;
-        {
-            int f = (tid < ROUND) ? s_flag[tid] : 0;
-            unsigned bal = __ballot_sync(0xffffffffu, f);
-            if (tid < ROUND && lane == 0) s_warp[warp] = __popc(bal);
             __syncthreads();
-            int before = 0, tot = 0;
-#pragma unroll
-            for (int w = 0; w < ROUND / 32; ++w) { int c = s_warp[w]; if (w < warp) before += c; tot += c; }
-            S = tot;
-            if (f) {
-                const int r = before + __popc(bal & ((1u << lane) - 1u));
-                const float4 bx = cbox[pos + tid];
-                sv_box[r] = bx; sv_area[r] = box_area(bx); sv_side[r] = fmaxf(bx.z - bx.x, bx.w - bx.y);
-                sv_pos[r] = (uint16_t)(pos + tid);
-            }
+            const float ex0 = fdt_key_float(s_ext[0]), ey0 = fdt_key_float(s_ext[1]);
+            const float ex1 = fdt_key_float(s_ext[2]), ey1 = fdt_key_float(s_ext[3]);
+            const float ext = fmaxf(ex1 - ex0, ey1 - ey0);
+            gg.ok = (ext > 0.0f) && (ext < INFINITY);
+            gg.x0 = ex0; gg.y0 = ey0;
+            gg.inv0 = gg.ok ? 32.0f / ext : 0.0f;
+            gg.c0 = gg.ok ? ext / 32.0f : 0.0f;
+            if (!(gg.inv0 > 0.0f && gg.inv0 < INFINITY && gg.c0 > 0.0f)) gg.ok = 0;
         }
-        __syncthreads();
         K3_ACC(1);
-        // ---- phase B: suppression bits among the survivors (a earlier than b), then dependency resolution
-        for (int p = tid; p < S * S; p += K3_THREADS) {
-            const int a = p / S, bb = p - a * S;
-            if (a >= bb) continue;
-            const float sa = sv_side[a], sb = sv_side[bb];
-            if (sa < prune * sb || sb < prune * sa) continue;            // longer-side ratio bounds IoU (NaN -> test)
-            if (fdt_suppresses(sv_box[a], sv_area[a], sv_box[bb], sv_area[bb], thr)) atomicOr(&sv_rows[bb][a >> 5], 1u << (a & 31));
-        }
-        __syncthreads();
-        K3_ACC(2);
-        // survivor b is kept iff every earlier survivor that suppresses it is dead; dead iff one of them is kept.
-        // The earliest undecided survivor always resolves, so this terminates; statuses never change once set.
-        {
-            int status = (tid < S) ? 0 : 3;          // 0 undecided, 1 kept, 2 dead, 3 not a survivor
-            for (;;) {
-                if (tid == 0) s_unknown = 0;
-                __syncthreads();
-                if (status == 0) {
-                    bool any_kept = false, all_dead = true;
-#pragma unroll
-                    for (int w = 0; w < ROUND / 32; ++w) {
-                        const unsigned row = sv_rows[tid][w];
-                        any_kept |= (row & s_keptw[w]) != 0;
-                        all_dead &= (row & ~s_deadw[w]) == 0;
-                    }
-                    if (any_kept) { status = 2; atomicOr(&s_deadw[tid >> 5], 1u << (tid & 31)); }
-                    else if (all_dead) { status = 1; atomicOr(&s_keptw[tid >> 5], 1u << (tid & 31)); }
-                    else s_unknown = 1;
-                }
-                __syncthreads();
-                const bool again = s_unknown != 0;
-                __syncthreads();
-                if (!again) break;
+        // ---- phase A: against the boxes kept in earlier windows
+        bool alive = valid;
+        if (valid && nkept > 0) {
+            auto hit = [&](uint16_t slot) -> bool { return fdt_suppresses(kbox[slot], karea[slot], bj, aj, thr); };
+            int rc = 2;
+            if (regj && gg.ok) rc = grid_query(gg, kgrid, bj, sj, prune, hit);
+            if (rc == 1) alive = false;
+            else if (rc == 0) {
+                const int nb = s_nkbig;
+                for (int t = 0; t < nb && alive; ++t) if (hit(kbig[t])) alive = false;
+            } else {
+                for (int t = 0; t < nkept && alive; ++t) if (hit((uint16_t)t)) alive = false;
             }
-            K3_ACC(3);
-            // ---- append the newly kept boxes (in order) and register them in the grid
-            int before = 0, tot = 0;
+        }
+        status[tid] = alive ? 0 : 2;
+        K3_ACC(2);
+        __syncthreads();
+        // ---- phase B: survivors of this window among themselves.  Register them in the round grid, then every survivor
+        //      collects the earlier survivors that would suppress it.
+        if (alive && !grid_insert(gg, rgrid, bj, sj, (uint16_t)tid)) rbig[atomicAdd(&s_nrbig, 1)] = (uint16_t)tid;
+        __syncthreads();
+        int nd = 0;
+        bool ovf = false;
+        uint16_t dep[DEPS];
 #pragma unroll
-            for (int w = 0; w < ROUND / 32; ++w) { const int c = __popc(s_keptw[w]); if (w < (tid >> 5)) before += c; tot += c; }
-            if (status == 1) {
-                const int slot = nkept + before + __popc(s_keptw[tid >> 5] & ((1u << (tid & 31)) - 1u));
-                const int ps = sv_pos[tid];
-                if (slot < max_keep) klist[slot] = (uint16_t)ps;
-                const float4 bx = sv_box[tid];
-                bool to_big = true;
-                if (gg.ok && box_regular(bx)) {
-                    const int lev = level_of(sv_side[tid], gg.c0);
-                    if (lev < NLEV) {
-                        const int G = 32 >> lev;
-                        const float inv = gg.inv0 / (float)(1 << lev);
-                        const int cx0 = cell_of(bx.x, gg.x0, inv, G), cx1 = cell_of(bx.z, gg.x0, inv, G);
-                        const int cy0 = cell_of(bx.y, gg.y0, inv, G), cy1 = cell_of(bx.w, gg.y0, inv, G);
-                        if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) <= 9) {
-                            to_big = false;
-                            for (int cy = cy0; cy <= cy1; ++cy)
-                                for (int cx = cx0; cx <= cx1; ++cx) {
-                                    const int cell = grid_off(lev) + cy * G + cx;
-                                    const int sl = atomicAdd(&cell_cnt[cell], 1);
-                                    if (sl < CELL_CAP) cell_items[cell * CELL_CAP + sl] = (uint16_t)ps;
-                                    else to_big = true;          // full cell: also list it where everybody looks
-                                }
+        for (int d = 0; d < DEPS; ++d) dep[d] = 0;
+        bool brute_b = false;
+        if (alive) {
+            // keeps the DEPS earliest (highest-score) suppressors: in crowded scenes one of them is almost always kept, which
+            // settles this survivor without looking at the rest (ovf marks that there are more)
+            auto collect = [&](uint16_t a) -> bool {
+                if ((int)a < tid && fdt_suppresses(wbox[a], warea[a], bj, aj, thr)) {
+                    bool dup = false;
+#pragma unroll
+                    for (int d = 0; d < DEPS; ++d) dup |= (d < nd) && dep[d] == a;
+                    if (!dup) {
+                        if (nd < DEPS) {
+#pragma unroll
+                            for (int d = 0; d < DEPS; ++d) if (d == nd) dep[d] = a;
+                            ++nd;
+                        } else {
+                            ovf = true;
+                            uint16_t mx = dep[0];
+#pragma unroll
+                            for (int d = 1; d < DEPS; ++d) mx = max(mx, dep[d]);
+                            if (a < mx) {
+#pragma unroll
+                                for (int d = 0; d < DEPS; ++d) if (dep[d] == mx) dep[d] = a;
+                            }
                         }
                     }
                 }
-                if (to_big) big[atomicAdd(&s_nbig, 1)] = (uint16_t)ps;
+                return false;
+            };
+            int rc = 2;
+            if (regj && gg.ok) rc = grid_query(gg, rgrid, bj, sj, prune, collect);
+            if (rc == 0) {
+                const int nb = s_nrbig;
+                for (int t = 0; t < nb; ++t) collect(rbig[t]);
+            } else {
+                brute_b = true;
+                for (int a = 0; a < tid; ++a) if (status[a] == 0) collect((uint16_t)a);     // status is still 0/2 = survivor or not
             }
-            nkept += tot;
+        }
+        K3_ACC(3);
+        // ---- resolve: a survivor is dead iff an earlier survivor that suppresses it is kept, kept iff all of them are dead.
+        //      The earliest undecided survivor always resolves, statuses never change once set.
+        {
+            int st = alive ? 0 : 2;
+            for (;;) {
+                if (st == 0) {
+                    bool any_kept = false, pend = false;
+#pragma unroll
+                    for (int d = 0; d < DEPS; ++d)
+                        if (d < nd) { const int s = status[dep[d]]; any_kept |= (s == 1); pend |= (s == 0); }
+                    if (ovf && !any_kept && !pend) {  // the DEPS earliest suppressors are all dead: look at the others
+                        auto look = [&](uint16_t a) -> bool {
+                            if ((int)a < tid && fdt_suppresses(wbox[a], warea[a], bj, aj, thr)) {
+                                const int s = status[a];
+                                if (s == 1) { any_kept = true; return true; }
+                                pend |= (s == 0);
+                            }
+                            return false;
+                        };
+                        if (!brute_b) {
+                            if (grid_query(gg, rgrid, bj, sj, prune, look) == 0) {
+                                const int nb = s_nrbig;
+                                for (int t = 0; t < nb && !any_kept; ++t) look(rbig[t]);
+                            }
+                        } else {
+                            for (int a = 0; a < tid && !any_kept; ++a) look((uint16_t)a);
+                        }
+                    }
+                    if (any_kept) { st = 2; status[tid] = 2; }
+                    else if (!pend) { st = 1; status[tid] = 1; }
+                }
+                if (!__syncthreads_or(st == 0)) break;       // one barrier per sweep; it also publishes the status bytes
+            }
+            K3_ACC(4);
+            // ---- append the newly kept boxes in order; register them for the next windows
+            int tot;
+            const int before = block_excl_scan(st == 1 ? 1 : 0, s_warp, tot);
+            if (st == 1) {
+                const int slot = nkept + before;
+                if (slot < max_keep) {
+                    kbox[slot] = bj; karea[slot] = aj; kkey[slot] = kj;
+                    if (!grid_insert(gg, kgrid, bj, sj, (uint16_t)slot)) kbig[atomicAdd(&s_nkbig, 1)] = (uint16_t)slot;
+                }
+            }
+            nkept = min(nkept + tot, max_keep);
         }
         __syncthreads();
-        K3_ACC(4);
-        if (prof) pacc[5] += 1;
+        K3_ACC(5);
+        lo = hi;
     }
-    nkept = min(nkept, max_keep);
-    if (prof) { for (int q = 0; q < 6; ++q) P.prof[5 + q] = pacc[q]; P.prof[12] = nkept; P.prof[13] = k; P.prof[14] = s_nbig; }
+    if (prof) { for (int q = 0; q < 6; ++q) P.prof[5 + q] = pacc[q]; P.prof[12] = nkept; P.prof[13] = k; P.prof[14] = rounds; P.prof[15] = s_nkbig; }
 
-    // =========================================================== stage 4: outputs
+    // =========================================================== stage 3: outputs
     if (MODE == MODE_DETECT) {
         const int top_k = P.top_k;
         const int cnt = min(nkept, top_k);                                   // detection.py:80
@@ -558,18 +667,17 @@ k_sort_nms(const SortNmsParams P)
             int r = t / 5, col = t - 5 * r;
             float v = 0.0f;
             if (r < cnt) {
-                int ps = klist[r];
-                if (col == 0) v = fdt_key_float((uint32_t)(skeys[ps] >> 32));
+                if (col == 0) v = fdt_key_float((uint32_t)(kkey[r] >> 32));
                 else {
-                    const float *bx = reinterpret_cast<const float *>(cbox + ps);
-                    v = bx[col - 1];
+                    const float4 bx = kbox[r];
+                    v = col == 1 ? bx.x : col == 2 ? bx.y : col == 3 ? bx.z : bx.w;
                 }
             }
             o[t] = v;                                                        // detection.py:82
         }
         if (P.kept_prior) {
             int64_t *kp = P.kept_prior + (int64_t)(b * P.C + cl) * top_k;
-            for (int r = tid; r < top_k; r += K3_THREADS) kp[r] = r < cnt ? (int64_t)(uint32_t)skeys[klist[r]] : -1;
+            for (int r = tid; r < top_k; r += K3_THREADS) kp[r] = r < cnt ? (int64_t)(uint32_t)kkey[r] : -1;
         }
         if (P.counts && tid == 0) P.counts[b * P.C + cl] = cnt;
         if (cl == 1) {                                                       // class-0 plane stays zero (:48, :63)
@@ -583,7 +691,7 @@ k_sort_nms(const SortNmsParams P)
         }
     } else {
         for (int64_t t = tid; t < P.n; t += K3_THREADS)
-            P.keep[t] = t < nkept ? (int64_t)(uint32_t)skeys[klist[t]] : 0;   // box_utils.py:289 zero-initialised
+            P.keep[t] = t < nkept ? (int64_t)(uint32_t)kkey[t] : 0;           // box_utils.py:289 zero-initialised
         if (tid == 0) *P.count_out = nkept;
     }
     K3_STAMP(11);
@@ -591,27 +699,38 @@ k_sort_nms(const SortNmsParams P)
 #undef K3_ACC
 }
 
-struct SmemPlan { int key_cap, off_cbox, off_scr, off_big, off_klist, total; };
-
-SmemPlan plan_smem(int kcap, int max_keep)
+SmemPlan plan_smem(int kcap, int max_keep, bool kept_in_smem)
 {
     auto up16 = [](int x) { return (x + 15) / 16 * 16; };
     SmemPlan s;
-    s.key_cap = kcap + SORT_SLACK;
-    int off = up16(s.key_cap * 8);
-    s.off_cbox = off; off += up16(kcap * 16);
-    const int scr_sort = 2 * NB * 4, scr_grid = NCELLS * 4 + NCELLS * CELL_CAP * 2;
-    s.off_scr = off; off += up16(scr_sort > scr_grid ? scr_sort : scr_grid);
-    s.off_big = off; off += up16(kcap * 2);
-    s.off_klist = off; off += up16(max_keep * 2);
+    s.key_cap = 64;
+    while (s.key_cap < kcap + 64) s.key_cap <<= 1;
+    int off = s.key_cap * 8;
+    s.off_scr = off; off += up16(2 * NB * 4);
+    s.off_kgrid = off; off += up16((NCELLS + 8) * 4 + NCELLS * CELL_CAP * 2);
+    s.off_wbox = off; off += WIN * 16;
+    s.off_warea = off; off += WIN * 4;
+    s.off_wside = off; off += WIN * 4;
+    s.off_status = off; off += WIN;
+    s.off_rbig = off; off += WIN * 2;
+    s.off_kbig = off; off += up16(max_keep * 2);
+    s.off_kbox = s.off_karea = s.off_kkey = -1;
+    if (kept_in_smem) {
+        s.off_kbox = off; off += up16(max_keep * 16);
+        s.off_karea = off; off += up16(max_keep * 4);
+        s.off_kkey = off; off += up16(max_keep * 8);
+    }
     s.total = off;
     return s;
 }
 
+constexpr int K3_STATIC_SMEM = 40 * 1024;        // round grid + small arrays declared __shared__ in k_sort_nms
+
 static long long *g_prof_dev = nullptr;
 
+// kept_ws: global memory for the kept arrays (28 bytes per kept row and list) used when they do not fit in shared memory
 template <int MODE>
-int launch_sort_nms(SortNmsParams &P, int lists, int kcap, cudaStream_t st)
+int launch_sort_nms(SortNmsParams &P, int lists, int kcap, void *kept_ws, size_t kept_ws_bytes, cudaStream_t st)
 {
     const char *env = getenv("FDT_K3_PROFILE");
     if (env && env[0] == '1') {
@@ -619,11 +738,22 @@ int launch_sort_nms(SortNmsParams &P, int lists, int kcap, cudaStream_t st)
         FDT_CUDA(cudaMemsetAsync(g_prof_dev, 0, 32 * sizeof(long long), st));
         P.prof = g_prof_dev;
     }
-    SmemPlan sp = plan_smem(kcap, P.max_keep);
-    const int limit = FDT_SMEM_MAX - 20480;      // static shared memory of k_sort_nms (round buffers)
+    FDT_REQUIRE(kcap <= FDT_MAX_NMS_TOP_K, FDT_E_UNSUPPORTED, "nms_top_k=%d exceeds %d", kcap, FDT_MAX_NMS_TOP_K);
+    const int limit = FDT_SMEM_MAX - K3_STATIC_SMEM;
+    SmemPlan sp = plan_smem(kcap, P.max_keep, true);
+    if (sp.total > limit) {
+        sp = plan_smem(kcap, P.max_keep, false);
+        const size_t need = (size_t)lists * P.max_keep * KEPT_ROW_BYTES;
+        FDT_REQUIRE(kept_ws != nullptr && kept_ws_bytes >= need, FDT_E_WORKSPACE,
+                    "kept rows (%d per list) do not fit in shared memory and the workspace lacks %zu bytes for them", P.max_keep, need);
+        char *p = (char *)kept_ws;
+        P.g_kbox = (float4 *)p; p += (size_t)lists * P.max_keep * 16;
+        P.g_kkey = (uint64_t *)p; p += (size_t)lists * P.max_keep * 8;
+        P.g_karea = (float *)p;
+    }
     FDT_REQUIRE(sp.total <= limit, FDT_E_UNSUPPORTED,
                 "nms_top_k=%d / max_keep=%d need %d bytes of shared memory (limit %d)", kcap, P.max_keep, sp.total, limit);
-    P.key_cap = sp.key_cap; P.off_cbox = sp.off_cbox; P.off_scr = sp.off_scr; P.off_big = sp.off_big; P.off_klist = sp.off_klist;
+    P.sm = sp;
     FDT_CUDA(cudaFuncSetAttribute(k_sort_nms<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
     k_sort_nms<MODE><<<lists, K3_THREADS, sp.total, st>>>(P);
     FDT_LAUNCH_CHECK();
@@ -637,7 +767,9 @@ FDT_API size_t fdt_detect_workspace_bytes(int B, int64_t N, int C)
 {
     if (B <= 0 || N <= 0 || C <= 1) return 256;
     size_t lists = (size_t)B * (size_t)(C - 1);
-    return fdt_align256(lists * sizeof(int32_t)) + fdt_align256(lists * (size_t)N * sizeof(uint64_t));
+    size_t kept_rows = (size_t)(N < FDT_MAX_NMS_TOP_K ? N : FDT_MAX_NMS_TOP_K);       // only used when top_k rows exceed shared memory
+    return fdt_align256(lists * sizeof(int32_t)) + fdt_align256(lists * (size_t)N * sizeof(uint64_t)) +
+           fdt_align256(lists * kept_rows * KEPT_ROW_BYTES);
 }
 
 static int detect_check_common(const char *who, int B, int64_t N, int C, const void *ws, size_t ws_bytes)
@@ -710,7 +842,10 @@ FDT_API int fdt_detect_sort_nms(const float *loc, const float *priors, int B, in
     P.nms_thresh = nms_thresh; P.v0 = var0; P.v1 = var1;
     P.out = out; P.counts = counts; P.kept_prior = kept_prior;
     int kcap = (int)((int64_t)nms_top_k < N ? nms_top_k : N);
-    return launch_sort_nms<MODE_DETECT>(P, lists, kcap, st);
+    if (P.max_keep > kcap) P.max_keep = kcap;
+    char *kept_ws = (char *)keys + fdt_align256((size_t)lists * (size_t)N * sizeof(uint64_t));
+    size_t kept_rows = (size_t)(N < FDT_MAX_NMS_TOP_K ? N : FDT_MAX_NMS_TOP_K);
+    return launch_sort_nms<MODE_DETECT>(P, lists, kcap, kept_ws, fdt_align256((size_t)lists * kept_rows * KEPT_ROW_BYTES), st);
 }
 
 FDT_API int fdt_detect(const float *loc, const float *conf, const float *priors,
@@ -739,7 +874,9 @@ FDT_API int fdt_debug_k3_profile(long long *out32_h)
 
 FDT_API size_t fdt_nms_workspace_bytes(int64_t n)
 {
-    return fdt_align256((size_t)(n > 0 ? n : 1) * sizeof(uint64_t));
+    size_t nn = (size_t)(n > 0 ? n : 1);
+    size_t kept_rows = nn < FDT_MAX_NMS_TOP_K ? nn : FDT_MAX_NMS_TOP_K;
+    return fdt_align256(nn * sizeof(uint64_t)) + fdt_align256(kept_rows * KEPT_ROW_BYTES);
 }
 
 FDT_API int fdt_nms(const float *boxes, const float *scores, int64_t n, float overlap, int64_t top_k,
@@ -761,5 +898,7 @@ FDT_API int fdt_nms(const float *boxes, const float *scores, int64_t n, float ov
     P.keys = keys; P.key_stride = n; P.boxes = boxes; P.n = n; P.N = n; P.C = 2;
     P.nms_top_k = (int)k; P.max_keep = (int)k; P.nms_thresh = overlap;
     P.keep = keep; P.count_out = count;
-    return launch_sort_nms<MODE_NMS>(P, 1, (int)k, st);
+    char *kept_ws = (char *)ws + fdt_align256((size_t)n * sizeof(uint64_t));
+    size_t kept_rows = (size_t)(n < FDT_MAX_NMS_TOP_K ? n : FDT_MAX_NMS_TOP_K);
+    return launch_sort_nms<MODE_NMS>(P, 1, (int)k, kept_ws, fdt_align256(kept_rows * KEPT_ROW_BYTES), st);
 }

@@ -36,7 +36,7 @@ extern "C" {
 #define FDT_E_UNSUPPORTED -4   /* size outside the kernel limits (see each function) */
 #define FDT_E_DEVICE      -5   /* device is not sm_100 (B200) */
 
-#define FDT_MAX_NMS_TOP_K  8192   /* candidates sorted + held in shared memory per image/class */
+#define FDT_MAX_NMS_TOP_K  8000   /* candidates that can enter NMS per image/class (the reference uses 5000) */
 
 typedef void *fdt_stream_t;        /* cudaStream_t */
 typedef struct fdt_ctx fdt_ctx;    /* host-buffer context: owns a stream, device + pinned staging buffers */
@@ -75,7 +75,7 @@ int fdt_log_sum_exp(const float *x, int64_t R, int C, float *out, void *ws, size
 /* ---- N1  nms  (layers/box_utils.py:275-340) ------------------------------------------------------
  * boxes[n,4], scores[n] -> keep[n] int64 zero-padded (indices into the input, descending score),
  * *count (device int64).  Sort ties: higher index first.  top_k <= 0 means n, as idx[-0:] does.
- * Limit: min(n, top_k) <= ~6000 (28 B of shared memory per candidate; FDT_E_UNSUPPORTED beyond). */
+ * Limit: min(n, top_k) <= FDT_MAX_NMS_TOP_K (FDT_E_UNSUPPORTED beyond). */
 size_t fdt_nms_workspace_bytes(int64_t n);
 int fdt_nms(const float *boxes, const float *scores, int64_t n, float overlap, int64_t top_k,
             int64_t *keep, int64_t *count, void *ws, size_t ws_bytes, fdt_stream_t stream);
@@ -85,8 +85,7 @@ int fdt_nms(const float *boxes, const float *scores, int64_t n, float overlap, i
  * in keep order, zero padded; class-0 plane zero.  Optional: counts[B,C] int32 rows written;
  * kept_prior[B,C,top_k] int64 prior index per row (-1 padding).  Candidates: score > conf_thresh
  * (strict); exactly one candidate yields no detection (reference quirk, detection.py:66-72).
- * Limits: nms_top_k <= ~6500 (26 B of shared memory per candidate + 2 B per kept row; the reference uses 5000);
- * FDT_E_UNSUPPORTED beyond.  See DESIGN.md. */
+ * Limit: nms_top_k <= FDT_MAX_NMS_TOP_K (FDT_E_UNSUPPORTED beyond).  See DESIGN.md. */
 size_t fdt_detect_workspace_bytes(int B, int64_t N, int C);
 int fdt_detect(const float *loc, const float *conf, const float *priors,
                int B, int64_t N, int C, int top_k, int nms_top_k,

@@ -210,10 +210,10 @@ def test_detect_production_thresholds(layers, args, nms_top_k):
                 oracle_detect(loc, conf, pri, args, nms_top_k=nms_top_k))
 
 
-def test_detect_nms_top_k_beyond_shared_memory_is_refused(layers):
+def test_detect_nms_top_k_beyond_limit_is_refused(layers):
     pri = synth.priors_numpy(640, 640)
     loc, conf = synth.detect_inputs(1, pri, 1, 0.05)
-    with pytest.raises(NotImplementedError, match="shared memory"):
+    with pytest.raises(NotImplementedError, match="nms_top_k"):
         run_detect(layers, loc, conf, pri, nms_top_k=8192)
 
 

@@ -18,11 +18,11 @@ for _ in range(3):
 torch.cuda.synchronize()
 out = (C.c_longlong * 32)()
 _lib.check(_lib.lib().fdt_debug_k3_profile(out))
-names = ["minmax", "hist+scan", "scatter", "rank+permute", "decode+extent", "A:kept-query", "compact", "B:pairs", "resolve",
-         "insert", "rounds", "output", "kept", "k", "nbig"]
-tot = sum(out[i] for i in list(range(10)) + [11])
+names = ["minmax", "hist+scan(+select)", "scatter(+bitonic)", "-", "-", "win:rank", "win:decode+geom", "win:csr build",
+         "win:A kept-query", "win:B window-query", "win:resolve+append", "output", "kept", "k", "rounds", "-"]
+tot = sum(out[i] for i in list(range(12)))
 for i, n in enumerate(names):
-    if n in ("rounds", "kept", "k", "nbig"):
+    if n in ("rounds", "kept", "k", "-"):
         print(f"{n:14s} {out[i]}")
     else:
         print(f"{n:14s} {out[i]:9d} cyc  {100 * out[i] / max(tot, 1):5.1f}%")
