@@ -26,12 +26,12 @@ constexpr int K2_TILE = K2_THREADS * K2_PER_THREAD;
 
 constexpr int K3_THREADS = 1024;
 constexpr int WIN = K3_THREADS;                 // sorted candidates examined per NMS round: one thread each
-constexpr int NB = 2048;                        // score buckets of the shared-memory bucket sort
+constexpr int NB = 4096;                        // score buckets of the shared-memory bucket sort
 constexpr int BIG_BUCKET = 512;                 // a larger bucket inside the top-k range -> full bitonic sort fallback
-constexpr int NLEV = 5;                         // grid levels: 32, 16, 8, 4, 2 cells per side
-constexpr int NCELLS = 1024 + 256 + 64 + 16 + 4;
-constexpr int CELL_CAP = 12;
-constexpr int MAX_QUERY_CELLS = 64;
+constexpr int NLEV = 6;                         // grid levels: 32, 16, 8, 4, 2, 1 cells per side
+constexpr int NCELLS = 1024 + 256 + 64 + 16 + 4 + 1;
+constexpr int BIGCELL = NCELLS;                 // pseudo-cell: boxes the grid cannot index (see box_regular)
+constexpr int NCELLX = NCELLS + 1;
 constexpr int DEPS = 8;                         // stored earlier-suppressors per survivor (more -> re-query path)
 constexpr int KEPT_ROW_BYTES = 28;              // box 16 + key 8 + area 4
 
@@ -100,7 +100,8 @@ __global__ void k_build_keys(const float *__restrict__ scores, int64_t n, uint64
 // ------------------------------------------------------------------------------------------- K3
 struct SmemPlan {
     int key_cap;                                   // entries of the key array (power of two >= kcap + 64)
-    int off_scr, off_kgrid, off_wbox, off_warea, off_wside, off_status, off_rbig, off_kbig;
+    int off_scr, off_wbox, off_warea, off_wside, off_wcell, off_status, off_witems, off_wstart, off_sbox, off_sarea;
+    int off_kstart, off_kcur, off_kitems, off_kcell;
     int off_kbox, off_karea, off_kkey;             // < 0: kept arrays live in the global workspace
     int total;
 };
@@ -145,12 +146,32 @@ __device__ __forceinline__ bool fdt_suppresses(const float4 bi, const float area
     return !(uni > 0.0f) && !(uni < 0.0f);          // 0/uni is NaN iff uni is 0 or NaN
 }
 
+// Same predicate, division only when the quotient is within 2^-20 of thr: with p = fl(thr * uni) and uni > 0,
+// inter < p (1 - 2^-20) implies fl(inter / uni) < thr and inter > p (1 + 2^-20) implies fl(inter / uni) >= thr (the rounding
+// errors of p and of the scaled bounds are <= 2^-23 each).  NaNs and uni <= 0 fall through to the exact form.
+__device__ __forceinline__ bool fdt_suppresses_fast(const float4 bi, const float area_i, const float4 bj, const float area_j,
+                                                    const float thr)
+{
+    float xx1 = fmaxf(bj.x, bi.x), yy1 = fmaxf(bj.y, bi.y);
+    float xx2 = fminf(bj.z, bi.z), yy2 = fminf(bj.w, bi.w);
+    float w = fmaxf(xx2 - xx1, 0.0f), h = fmaxf(yy2 - yy1, 0.0f);
+    float inter = w * h;
+    float uni = (area_j - inter) + area_i;
+    const float p = thr * uni;
+    if (p > 1e-30f) {                                  // normal range (no underflow in p); false for NaN and uni <= 0
+        if (inter < p * 0.99999905f) return false;
+        if (inter > p * 1.00000095f) return true;
+    }
+    if (inter > 0.0f) return !(inter / uni < thr);
+    return !(uni > 0.0f) && !(uni < 0.0f);
+}
+
 __device__ __forceinline__ float box_area(const float4 b) { return (b.z - b.x) * (b.w - b.y); }   // box_utils.py:296
 // Boxes the spatial grid may index: finite, not inverted, 0 < area < inf.  For two such boxes inter <= min(area_i,
 // area_j) holds exactly in fp32 (rounding is monotone), so union >= area_i > 0 and IoU is a finite number bounded by
 // the ratio of the longer sides; they can only suppress each other if they intersect.  Everything else (NaN/inf
-// coordinates, inverted or zero-area boxes -- 0/0 = NaN suppresses at ANY distance, box_utils.py:337-339) goes to the
-// always-tested list and is itself tested against every kept box.
+// coordinates, inverted or zero-area boxes -- 0/0 = NaN suppresses at ANY distance, box_utils.py:337-339) lives in a
+// pseudo-cell that every query scans and is itself tested against everything.
 __device__ __forceinline__ bool box_regular(const float4 b)
 {
     const float a = (b.z - b.x) * (b.w - b.y);
@@ -158,40 +179,44 @@ __device__ __forceinline__ bool box_regular(const float4 b)
            fabsf(b.w) < INFINITY && a > 0.0f && a < INFINITY;
 }
 
-// Multi-level uniform grid over the extent of the first window's boxes.  Level l has (32 >> l)^2 cells; a box lives at the
-// smallest level whose cell is at least as long as the box's longer side and is registered in every cell it touches
-// (<= 3x3, else it goes to the "big" list every query scans).  The cell map is monotone in the coordinate (clamped), so
-// two intersecting boxes always share a cell at whatever level one of them is registered.
+// Multi-level uniform grid over the extent of the first window's boxes, stored CSR-style (items sorted by cell).
+// Level l has (32 >> l)^2 cells of size c_l = extent / (32 >> l).  A regular box lives at the smallest level whose
+// cell is at least as long as the box's longer side, in the cell of its min corner (clamped: the cell map is monotone
+// in the coordinate, which is all the proof below needs).  A box j can only reach IoU >= thr with boxes whose longer
+// side is within a factor thr of its own (IoU <= side ratio), so a query visits only the levels that can hold such
+// boxes, and at level l' only rows/columns [cell(x1_j - 1.01 c_l'), cell(x2_j)]: an item i there that intersects j has
+// x1_i <= x2_j and x1_i >= x1_j - (x2_i - x1_i) >= x1_j - c_l' (the 1 % pad covers fp32 rounding of the width).
+// Cells of one row are consecutive in the CSR array, so each visited row is ONE contiguous item segment.
 struct GridGeom {
     float x0, y0;          // origin = min corner
     float inv0;            // cells per unit length at level 0 (32 / extent)
     float c0;              // cell size at level 0
-    int ok;                // 0: degenerate extent -> everything is "big"
+    int ok;                // 0: degenerate extent -> every box sits in the pseudo-cell
 };
-struct Grid {              // views into shared memory
-    int *cnt;              // [NCELLS]
-    int *lev;              // [8] boxes registered per level
-    uint16_t *items;       // [NCELLS * CELL_CAP]
-};
-__device__ __forceinline__ int grid_off(int lev) { return lev == 0 ? 0 : lev == 1 ? 1024 : lev == 2 ? 1280 : lev == 3 ? 1344 : 1360; }
+__device__ __forceinline__ int grid_off(int lev) { return lev == 0 ? 0 : lev == 1 ? 1024 : lev == 2 ? 1280 : lev == 3 ? 1344 : lev == 4 ? 1360 : 1364; }
 __device__ __forceinline__ int cell_of(float x, float origin, float inv, int G)
 {
     int c = __float2int_rd((x - origin) * inv);
     return max(0, min(G - 1, c));
 }
-__device__ __forceinline__ int level_of(float side, float c0)
+__device__ __forceinline__ int reg_cell(const GridGeom &gg, const float4 bx, const float side, const bool valid)
 {
-    float c = c0;
+    if (!valid) return -1;
+    if (!gg.ok || !box_regular(bx)) return BIGCELL;
+    float c = gg.c0;
+    int lev = 0;
 #pragma unroll
-    for (int l = 0; l < NLEV; ++l) { if (side <= c) return l; c *= 2.0f; }
-    return NLEV;
+    for (; lev < NLEV; ++lev, c *= 2.0f) if (side <= c) break;
+    if (lev >= NLEV) return BIGCELL;
+    const int G = 32 >> lev;
+    const float inv = gg.inv0 / (float)(1 << lev);
+    return grid_off(lev) + cell_of(bx.y, gg.y0, inv, G) * G + cell_of(bx.x, gg.x0, inv, G);
 }
-
-// Visits every item stored in a cell that box bj (longer side sj) touches, at every level whose boxes can reach IoU >= thr
-// with it (IoU <= ratio of the longer sides; `prune` = 0.99 * thr leaves a 1 % margin for fp32 rounding of IoU).
-// visit(item) returns true to stop.  Returns 0 = done, 1 = stopped by the visitor, 2 = too many cells: caller brute-forces.
+// visit(t) is called with CSR positions t (item = items[t]) and returns true to stop; returns true iff the visitor stopped.
+// `start` has NCELLX + 1 entries.
 template <typename F>
-__device__ __forceinline__ int grid_query(const GridGeom &gg, const Grid &g, const float4 bj, const float sj, const float prune, F &&visit)
+__device__ __forceinline__ bool csr_query(const GridGeom &gg, const int *start, const float4 bj, const float sj,
+                                          const float prune, F &&visit)
 {
     float c = gg.c0, inv = gg.inv0, cprev = 0.0f;
     int G = 32, base = 0;
@@ -199,42 +224,30 @@ __device__ __forceinline__ int grid_query(const GridGeom &gg, const Grid &g, con
     for (int lev = 0; lev < NLEV; ++lev, cprev = c, c *= 2.0f, inv *= 0.5f, base += G * G, G >>= 1) {
         if (c < prune * sj) continue;                    // every box of this level is too small to reach thr
         if (cprev * prune > sj) break;                   // this and all coarser levels only hold boxes too large
-        if (g.lev[lev] == 0) continue;
-        const int cx0 = cell_of(bj.x, gg.x0, inv, G), cx1 = cell_of(bj.z, gg.x0, inv, G);
-        const int cy0 = cell_of(bj.y, gg.y0, inv, G), cy1 = cell_of(bj.w, gg.y0, inv, G);
-        if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) > MAX_QUERY_CELLS) return 2;
-        for (int cy = cy0; cy <= cy1; ++cy)
-            for (int cx = cx0; cx <= cx1; ++cx) {
-                const int cell = base + cy * G + cx;
-                const int n = min(g.cnt[cell], CELL_CAP);
-                for (int t = 0; t < n; ++t)
-                    if (visit(g.items[cell * CELL_CAP + t])) return 1;
-            }
-    }
-    return 0;
-}
-// Registers `id`; false -> the caller must (also) put it on the big list (irregular, too large, or a cell was full).
-__device__ __forceinline__ bool grid_insert(const GridGeom &gg, const Grid &g, const float4 bx, const float side, const uint16_t id)
-{
-    if (!gg.ok || !box_regular(bx)) return false;
-    const int lev = level_of(side, gg.c0);
-    if (lev >= NLEV) return false;
-    const int G = 32 >> lev;
-    const float inv = gg.inv0 / (float)(1 << lev);
-    const int cx0 = cell_of(bx.x, gg.x0, inv, G), cx1 = cell_of(bx.z, gg.x0, inv, G);
-    const int cy0 = cell_of(bx.y, gg.y0, inv, G), cy1 = cell_of(bx.w, gg.y0, inv, G);
-    if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) > 9) return false;
-    bool ok = true;
-    const int base = grid_off(lev);
-    for (int cy = cy0; cy <= cy1; ++cy)
-        for (int cx = cx0; cx <= cx1; ++cx) {
-            const int cell = base + cy * G + cx;
-            const int sl = atomicAdd(&g.cnt[cell], 1);
-            if (sl < CELL_CAP) g.items[cell * CELL_CAP + sl] = id;
-            else ok = false;
+        if (start[base + G * G] == start[base]) continue;
+        const float pad = 1.01f * c;
+        const int cx0 = cell_of(bj.x - pad, gg.x0, inv, G), cx1 = cell_of(bj.z, gg.x0, inv, G);
+        const int cy0 = cell_of(bj.y - pad, gg.y0, inv, G), cy1 = cell_of(bj.w, gg.y0, inv, G);
+        for (int cy = cy0; cy <= cy1; ++cy) {
+            const int t1 = start[base + cy * G + cx1 + 1];
+            for (int t = start[base + cy * G + cx0]; t < t1; ++t)
+                if (visit(t)) return true;
         }
-    atomicAdd(&g.lev[lev], 1);
-    return ok;
+    }
+    const int t1 = start[BIGCELL + 1];
+    for (int t = start[BIGCELL]; t < t1; ++t)
+        if (visit(t)) return true;
+    return false;
+}
+
+// clock64 that cannot be read before a preceding barrier has released: BAR.SYNC is deferred-blocking, the shared-memory
+// load below is the first instruction that really waits for it, and the clock read takes the loaded value as an input.
+__device__ __forceinline__ long long fdt_clock_after(const int *smem_word)
+{
+    int v = *reinterpret_cast<const volatile int *>(smem_word);
+    long long t;
+    asm volatile("{ .reg .b32 z; and.b32 z, %1, 0; mov.u64 %0, %%clock64; }" : "=l"(t) : "r"(v) : "memory");
+    return t;
 }
 
 // exclusive prefix sum of one int per thread over the 1024-thread block; `total` = block sum
@@ -258,6 +271,17 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total)
     total = s_warp[32];
     return inc - v + s_warp[warp];
 }
+// in-place inclusive scan of a[0 .. NCELLX] (a[0] stays 0): counts at a[c + 1] become CSR starts
+__device__ __forceinline__ void csr_scan(int *a, int *s_warp)
+{
+    const int i0 = 2 * threadIdx.x, i1 = i0 + 1;
+    const int v0 = i0 <= NCELLX ? a[i0] : 0, v1 = i1 <= NCELLX ? a[i1] : 0;
+    int tot;
+    const int ex = block_excl_scan(v0 + v1, s_warp, tot);
+    if (i0 <= NCELLX) a[i0] = ex + v0;
+    if (i1 <= NCELLX) a[i1] = ex + v0 + v1;
+    __syncthreads();
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(K3_THREADS, 1)
@@ -267,30 +291,30 @@ k_sort_nms(const SortNmsParams P)
     uint64_t *skeys = reinterpret_cast<uint64_t *>(smem);                       // [key_cap] bucket-ordered, then sorted per window
     int *s_hist = reinterpret_cast<int *>(smem + P.sm.off_scr);                  // sort: fill[NB] | start[NB]
     int *s_start = s_hist + NB;
-    Grid rgrid, kgrid;                                                           // round grid aliases the sort scratch... see below
-    kgrid.cnt = reinterpret_cast<int *>(smem + P.sm.off_kgrid);
-    kgrid.lev = kgrid.cnt + NCELLS;
-    kgrid.items = reinterpret_cast<uint16_t *>(kgrid.lev + 8);
     float4 *wbox = reinterpret_cast<float4 *>(smem + P.sm.off_wbox);             // [WIN] boxes of the current window
     float *warea = reinterpret_cast<float *>(smem + P.sm.off_warea);
     float *wside = reinterpret_cast<float *>(smem + P.sm.off_wside);
+    uint16_t *wcell = reinterpret_cast<uint16_t *>(smem + P.sm.off_wcell);       // [WIN] grid cell of each window candidate
     unsigned char *status = smem + P.sm.off_status;                              // [WIN] 0 undecided, 1 kept, 2 dead
-    uint16_t *rbig = reinterpret_cast<uint16_t *>(smem + P.sm.off_rbig);         // [WIN]
-    uint16_t *kbig = reinterpret_cast<uint16_t *>(smem + P.sm.off_kbig);         // [max_keep]
+    uint16_t *witems = reinterpret_cast<uint16_t *>(smem + P.sm.off_witems);     // [WIN] window candidates sorted by cell
+    int *wstart = reinterpret_cast<int *>(smem + P.sm.off_wstart);               // [NCELLX + 1]
+    float4 *sbox = reinterpret_cast<float4 *>(smem + P.sm.off_sbox);             // [WIN] window boxes in cell (CSR) order
+    float *sarea = reinterpret_cast<float *>(smem + P.sm.off_sarea);
+    int *kstart = reinterpret_cast<int *>(smem + P.sm.off_kstart);               // [NCELLX + 1] CSR over the kept boxes
+    int *kcur = reinterpret_cast<int *>(smem + P.sm.off_kcur);                   // [NCELLX + 1] fill cursors
+    uint16_t *kitems = reinterpret_cast<uint16_t *>(smem + P.sm.off_kitems);     // [max_keep]
+    uint16_t *kcell = reinterpret_cast<uint16_t *>(smem + P.sm.off_kcell);       // [max_keep]
     const int list = blockIdx.x;
     float4 *kbox = P.sm.off_kbox >= 0 ? reinterpret_cast<float4 *>(smem + P.sm.off_kbox) : P.g_kbox + (int64_t)list * P.max_keep;
     float *karea = P.sm.off_karea >= 0 ? reinterpret_cast<float *>(smem + P.sm.off_karea) : P.g_karea + (int64_t)list * P.max_keep;
     uint64_t *kkey = P.sm.off_kkey >= 0 ? reinterpret_cast<uint64_t *>(smem + P.sm.off_kkey) : P.g_kkey + (int64_t)list * P.max_keep;
 
     __shared__ int s_sel[3];
-    __shared__ int s_placed, s_maxb, s_nrbig, s_nkbig;
+    __shared__ int s_placed, s_maxb;
     __shared__ unsigned s_kmin, s_kmax;
     __shared__ int s_hist8[256];
     __shared__ int s_warp[33];
     __shared__ unsigned s_ext[4];          // extent of the regular boxes as order-preserving keys
-    __shared__ int s_rgrid_cnt[NCELLS + 8];
-    __shared__ uint16_t s_rgrid_items[NCELLS * CELL_CAP];
-    rgrid.cnt = s_rgrid_cnt; rgrid.lev = s_rgrid_cnt + NCELLS; rgrid.items = s_rgrid_items;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = (MODE == MODE_DETECT) ? list / (P.C - 1) : 0;
@@ -301,9 +325,9 @@ k_sort_nms(const SortNmsParams P)
     if (MODE == MODE_DETECT && n_c == 1) n_c = 0;            // detection.py:66-72: one candidate -> `continue`
     const int k = min(n_c, P.nms_top_k);                     // box_utils.py:299 idx[-top_k:]
     const bool prof = P.prof != nullptr && blockIdx.x == 0 && tid == 0;
-    long long pt = prof ? clock64() : 0, pacc[6] = {0, 0, 0, 0, 0, 0};
-#define K3_STAMP(slot) do { if (prof) { long long now_ = clock64(); P.prof[slot] = now_ - pt; pt = now_; } } while (0)
-#define K3_ACC(slot) do { if (prof) { long long now_ = clock64(); pacc[slot] += now_ - pt; pt = now_; } } while (0)
+    long long pt = prof ? clock64() : 0, pacc[7] = {0, 0, 0, 0, 0, 0, 0};
+#define K3_STAMP(slot) do { if (P.prof) __syncthreads(); if (prof) { long long now_ = fdt_clock_after(s_warp); P.prof[slot] = now_ - pt; pt = now_; } } while (0)
+#define K3_ACC(slot) do { if (P.prof) __syncthreads(); if (prof) { long long now_ = fdt_clock_after(s_warp); pacc[slot] += now_ - pt; pt = now_; } } while (0)
 
     // =========================================================== stage 1: top-k selection by bucket (counting) sort
     // Monotone score -> bucket map; counting sort by bucket, descending; only buckets that can reach rank < k are
@@ -458,14 +482,19 @@ k_sort_nms(const SortNmsParams P)
     }
 
     // =========================================================== stage 2: lazy greedy NMS over windows of sorted candidates
+    // Each round takes the next <= 1024 candidates (whole score buckets), orders them exactly, decodes their boxes and
+    //   A  drops those suppressed by a box kept in an earlier round            (query of the kept-box grid),
+    //   B  finds, for every survivor, the earlier survivors that suppress it   (query of the window grid),
+    //   C  resolves: dead iff one of those is kept, kept iff all are dead      (parallel sweeps; the earliest undecided
+    //      survivor always resolves, statuses never change once set -> exactly the sequential greedy result),
+    // and stops once top_k boxes are kept: Detect only reads keep[:top_k] (detection.py:80-81).
+    // In phases A-C thread t works on the t-th candidate IN CELL ORDER, so the lanes of a warp walk the same grid rows.
     const float thr = P.nms_thresh;
     const float prune = 0.99f * thr;
     const int max_keep = P.max_keep;
-    int nkept = 0, rounds = 0;
+    int nkept = 0, rounds = 0, sweeps = 0;
     GridGeom gg;
     gg.ok = 0; gg.x0 = gg.y0 = gg.inv0 = gg.c0 = 0.0f;
-    for (int i = tid; i < NCELLS + 8; i += K3_THREADS) kgrid.cnt[i] = 0;        // cnt[] and lev[] are contiguous
-    if (tid == 0) s_nkbig = 0;
 
     for (int lo = 0; lo < k && nkept < max_keep; ++rounds) {
         // ---- window [lo, hi): whole buckets, at most WIN candidates
@@ -480,8 +509,8 @@ k_sort_nms(const SortNmsParams P)
                 hi = (bend == e) ? e : s_start[bq];          // buckets in range are <= BIG_BUCKET < WIN, so hi > lo
             }
         }
-        for (int i = tid; i < NCELLS + 8; i += K3_THREADS) rgrid.cnt[i] = 0;
-        if (tid == 0) { s_nrbig = 0; s_ext[0] = 0xffffffffu; s_ext[1] = 0xffffffffu; s_ext[2] = 0u; s_ext[3] = 0u; }
+        for (int i = tid; i <= NCELLX; i += K3_THREADS) { wstart[i] = 0; kstart[i] = 0; }
+        if (tid == 0) { s_ext[0] = 0xffffffffu; s_ext[1] = 0xffffffffu; s_ext[2] = 0u; s_ext[3] = 0u; }
         // ---- exact order inside the window: rank = bucket start + number of larger keys in the same bucket
         const int j = lo + tid;
         if (!presorted) {
@@ -500,163 +529,175 @@ k_sort_nms(const SortNmsParams P)
         }
         __syncthreads();
         K3_ACC(0);
-        // ---- boxes of the window (decode only what NMS looks at), grid geometry from the first window
+        // ---- boxes of the window (decode only what NMS looks at); grid geometry from the first window
         const bool valid = j < hi && j < k;
-        float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint64_t kj = 0;
-        if (valid) {
-            kj = skeys[j];
-            const uint32_t p = (uint32_t)kj;
-            if (MODE == MODE_DETECT) {
-                const float4 l = __ldg(reinterpret_cast<const float4 *>(P.loc) + ((int64_t)b * P.N + p));
-                const float4 pr = __ldg(reinterpret_cast<const float4 *>(P.priors) + p);
-                bj = fdt_decode1(l, pr, P.v0, P.v1);              // detection.py:55
-            } else {
-                bj = __ldg(reinterpret_cast<const float4 *>(P.boxes) + p);
+        const int nvalid = min(hi, k) - lo;
+        {
+            float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                const uint32_t p = (uint32_t)skeys[j];
+                if (MODE == MODE_DETECT) {
+                    const float4 l = __ldg(reinterpret_cast<const float4 *>(P.loc) + ((int64_t)b * P.N + p));
+                    const float4 pr = __ldg(reinterpret_cast<const float4 *>(P.priors) + p);
+                    bx = fdt_decode1(l, pr, P.v0, P.v1);              // detection.py:55
+                } else {
+                    bx = __ldg(reinterpret_cast<const float4 *>(P.boxes) + p);
+                }
             }
-        }
-        const float aj = box_area(bj);
-        const float sj = fmaxf(bj.z - bj.x, bj.w - bj.y);
-        const bool regj = valid && box_regular(bj);
-        wbox[tid] = bj; warea[tid] = aj; wside[tid] = sj;
-        if (rounds == 0) {
-            float x0 = regj ? bj.x : INFINITY, y0 = regj ? bj.y : INFINITY, x1 = regj ? bj.z : -INFINITY, y1 = regj ? bj.w : -INFINITY;
+            const float side = fmaxf(bx.z - bx.x, bx.w - bx.y);
+            wbox[tid] = bx; warea[tid] = box_area(bx); wside[tid] = side;
+            if (rounds == 0) {
+                const bool reg = valid && box_regular(bx);
+                float x0 = reg ? bx.x : INFINITY, y0 = reg ? bx.y : INFINITY, x1 = reg ? bx.z : -INFINITY, y1 = reg ? bx.w : -INFINITY;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
-                x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+                for (int o = 16; o > 0; o >>= 1) {
+                    x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+                    x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+                }
+                if (lane == 0) {      // float min/max through the order-preserving integer map
+                    atomicMin(&s_ext[0], fdt_float_key(x0)); atomicMin(&s_ext[1], fdt_float_key(y0));
+                    atomicMax(&s_ext[2], fdt_float_key(x1)); atomicMax(&s_ext[3], fdt_float_key(y1));
+                }
+                __syncthreads();
+                const float ex0 = fdt_key_float(s_ext[0]), ey0 = fdt_key_float(s_ext[1]);
+                const float ex1 = fdt_key_float(s_ext[2]), ey1 = fdt_key_float(s_ext[3]);
+                const float ext = fmaxf(ex1 - ex0, ey1 - ey0);
+                gg.ok = (ext > 0.0f) && (ext < INFINITY);
+                gg.x0 = ex0; gg.y0 = ey0;
+                gg.inv0 = gg.ok ? 32.0f / ext : 0.0f;
+                gg.c0 = gg.ok ? ext / 32.0f : 0.0f;
+                if (!(gg.inv0 > 0.0f && gg.inv0 < INFINITY && gg.c0 > 0.0f)) gg.ok = 0;
             }
-            if (lane == 0) {      // float min/max through the order-preserving integer map
-                atomicMin(&s_ext[0], fdt_float_key(x0)); atomicMin(&s_ext[1], fdt_float_key(y0));
-                atomicMax(&s_ext[2], fdt_float_key(x1)); atomicMax(&s_ext[3], fdt_float_key(y1));
-            }
+            K3_ACC(1);
+            // ---- window grid and (from the second round on) kept-box grid, CSR: count per cell, scan, place
+            const int cell = reg_cell(gg, bx, side, valid);
+            wcell[tid] = (uint16_t)(cell < 0 ? BIGCELL : cell);
+            const int slot = cell >= 0 ? atomicAdd(&wstart[cell + 1], 1) : 0;
+            if (rounds > 0)
+                for (int i = tid; i < nkept; i += K3_THREADS) atomicAdd(&kstart[kcell[i] + 1], 1);
             __syncthreads();
-            const float ex0 = fdt_key_float(s_ext[0]), ey0 = fdt_key_float(s_ext[1]);
-            const float ex1 = fdt_key_float(s_ext[2]), ey1 = fdt_key_float(s_ext[3]);
-            const float ext = fmaxf(ex1 - ex0, ey1 - ey0);
-            gg.ok = (ext > 0.0f) && (ext < INFINITY);
-            gg.x0 = ex0; gg.y0 = ey0;
-            gg.inv0 = gg.ok ? 32.0f / ext : 0.0f;
-            gg.c0 = gg.ok ? ext / 32.0f : 0.0f;
-            if (!(gg.inv0 > 0.0f && gg.inv0 < INFINITY && gg.c0 > 0.0f)) gg.ok = 0;
-        }
-        K3_ACC(1);
-        // ---- phase A: against the boxes kept in earlier windows
-        bool alive = valid;
-        if (valid && nkept > 0) {
-            auto hit = [&](uint16_t slot) -> bool { return fdt_suppresses(kbox[slot], karea[slot], bj, aj, thr); };
-            int rc = 2;
-            if (regj && gg.ok) rc = grid_query(gg, kgrid, bj, sj, prune, hit);
-            if (rc == 1) alive = false;
-            else if (rc == 0) {
-                const int nb = s_nkbig;
-                for (int t = 0; t < nb && alive; ++t) if (hit(kbig[t])) alive = false;
-            } else {
-                for (int t = 0; t < nkept && alive; ++t) if (hit((uint16_t)t)) alive = false;
+            csr_scan(wstart, s_warp);
+            if (cell >= 0) { const int ps = wstart[cell] + slot; witems[ps] = (uint16_t)tid; sbox[ps] = bx; sarea[ps] = box_area(bx); }
+            if (rounds > 0) {
+                csr_scan(kstart, s_warp);
+                for (int i = tid; i <= NCELLX; i += K3_THREADS) kcur[i] = kstart[i];
+                __syncthreads();
+                for (int i = tid; i < nkept; i += K3_THREADS) kitems[atomicAdd(&kcur[kcell[i]], 1)] = (uint16_t)i;
             }
         }
-        status[tid] = alive ? 0 : 2;
+        __syncthreads();
         K3_ACC(2);
+
+        // ---- from here on this thread owns candidate `id` = the tid-th window candidate in cell order
+        const bool have = tid < nvalid;
+        const int id = have ? witems[tid] : 0;
+        const float4 bj = sbox[have ? tid : 0];
+        const float aj = sarea[have ? tid : 0], sj = fmaxf(bj.z - bj.x, bj.w - bj.y);
+        const bool chk = nkept > 0;          // only then can a window candidate already be dead (phase A)
+        const bool in_grid = have && wcell[id] != BIGCELL;
+        // ---- phase A: against the boxes kept in earlier rounds
+        bool alive = have;
+        if (have && nkept > 0) {
+            auto hit = [&](int t) -> bool { const int slot = kitems[t]; return fdt_suppresses_fast(kbox[slot], karea[slot], bj, aj, thr); };
+            if (in_grid) alive = !csr_query(gg, kstart, bj, sj, prune, hit);
+            else for (int t = 0; t < nkept && alive; ++t) if (fdt_suppresses(kbox[t], karea[t], bj, aj, thr)) alive = false;
+        }
+        if (have) status[id] = alive ? 0 : 2;
+        K3_ACC(3);
         __syncthreads();
-        // ---- phase B: survivors of this window among themselves.  Register them in the round grid, then every survivor
-        //      collects the earlier survivors that would suppress it.
-        if (alive && !grid_insert(gg, rgrid, bj, sj, (uint16_t)tid)) rbig[atomicAdd(&s_nrbig, 1)] = (uint16_t)tid;
-        __syncthreads();
+        // ---- phase B: the earlier survivors of this window that suppress this one.  Keeps the DEPS earliest (highest-score)
+        //      ones: in crowded scenes one of them is almost always kept, which settles this survivor without the rest.
         int nd = 0;
         bool ovf = false;
         uint16_t dep[DEPS];
 #pragma unroll
         for (int d = 0; d < DEPS; ++d) dep[d] = 0;
-        bool brute_b = false;
         if (alive) {
-            // keeps the DEPS earliest (highest-score) suppressors: in crowded scenes one of them is almost always kept, which
-            // settles this survivor without looking at the rest (ovf marks that there are more)
-            auto collect = [&](uint16_t a) -> bool {
-                if ((int)a < tid && fdt_suppresses(wbox[a], warea[a], bj, aj, thr)) {
-                    bool dup = false;
+            auto add_dep = [&](const uint16_t a) {
+                bool dup = false;
 #pragma unroll
-                    for (int d = 0; d < DEPS; ++d) dup |= (d < nd) && dep[d] == a;
-                    if (!dup) {
-                        if (nd < DEPS) {
+                for (int d = 0; d < DEPS; ++d) dup |= (d < nd) && dep[d] == a;
+                if (dup) return;
+                if (nd < DEPS) {
 #pragma unroll
-                            for (int d = 0; d < DEPS; ++d) if (d == nd) dep[d] = a;
-                            ++nd;
-                        } else {
-                            ovf = true;
-                            uint16_t mx = dep[0];
+                    for (int d = 0; d < DEPS; ++d) if (d == nd) dep[d] = a;
+                    ++nd;
+                } else {
+                    ovf = true;
+                    uint16_t mx = dep[0];
 #pragma unroll
-                            for (int d = 1; d < DEPS; ++d) mx = max(mx, dep[d]);
-                            if (a < mx) {
+                    for (int d = 1; d < DEPS; ++d) mx = max(mx, dep[d]);
+                    if (a < mx) {
 #pragma unroll
-                                for (int d = 0; d < DEPS; ++d) if (dep[d] == mx) dep[d] = a;
-                            }
-                        }
+                        for (int d = 0; d < DEPS; ++d) if (dep[d] == mx) dep[d] = a;
                     }
                 }
-                return false;
             };
-            int rc = 2;
-            if (regj && gg.ok) rc = grid_query(gg, rgrid, bj, sj, prune, collect);
-            if (rc == 0) {
-                const int nb = s_nrbig;
-                for (int t = 0; t < nb; ++t) collect(rbig[t]);
+            if (in_grid) {
+                auto collect = [&](int t) -> bool {
+                    const int a = witems[t];
+                    if (a < id && !(chk && status[a] == 2) && fdt_suppresses_fast(sbox[t], sarea[t], bj, aj, thr)) add_dep((uint16_t)a);
+                    return false;
+                };
+                csr_query(gg, wstart, bj, sj, prune, collect);
             } else {
-                brute_b = true;
-                for (int a = 0; a < tid; ++a) if (status[a] == 0) collect((uint16_t)a);     // status is still 0/2 = survivor or not
+                for (int a = 0; a < id; ++a)
+                    if (status[a] != 2 && fdt_suppresses(wbox[a], warea[a], bj, aj, thr)) add_dep((uint16_t)a);
             }
         }
-        K3_ACC(3);
-        // ---- resolve: a survivor is dead iff an earlier survivor that suppresses it is kept, kept iff all of them are dead.
-        //      The earliest undecided survivor always resolves, statuses never change once set.
+        K3_ACC(4);
+        // ---- phase C: resolve
         {
             int st = alive ? 0 : 2;
             for (;;) {
+                if (prof) ++sweeps;
                 if (st == 0) {
                     bool any_kept = false, pend = false;
 #pragma unroll
                     for (int d = 0; d < DEPS; ++d)
                         if (d < nd) { const int s = status[dep[d]]; any_kept |= (s == 1); pend |= (s == 0); }
                     if (ovf && !any_kept && !pend) {  // the DEPS earliest suppressors are all dead: look at the others
-                        auto look = [&](uint16_t a) -> bool {
-                            if ((int)a < tid && fdt_suppresses(wbox[a], warea[a], bj, aj, thr)) {
-                                const int s = status[a];
-                                if (s == 1) { any_kept = true; return true; }
-                                pend |= (s == 0);
-                            }
-                            return false;
-                        };
-                        if (!brute_b) {
-                            if (grid_query(gg, rgrid, bj, sj, prune, look) == 0) {
-                                const int nb = s_nrbig;
-                                for (int t = 0; t < nb && !any_kept; ++t) look(rbig[t]);
-                            }
+                        if (in_grid) {
+                            auto look = [&](int t) -> bool {
+                                const int a = witems[t];
+                                if (a < id && status[a] != 2 && fdt_suppresses_fast(sbox[t], sarea[t], bj, aj, thr)) {
+                                    if (status[a] == 1) { any_kept = true; return true; }
+                                    pend = true;
+                                }
+                                return false;
+                            };
+                            csr_query(gg, wstart, bj, sj, prune, look);
                         } else {
-                            for (int a = 0; a < tid && !any_kept; ++a) look((uint16_t)a);
+                            for (int a = 0; a < id && !any_kept; ++a)
+                                if (status[a] != 2 && fdt_suppresses(wbox[a], warea[a], bj, aj, thr)) {
+                                    if (status[a] == 1) any_kept = true; else pend = true;
+                                }
                         }
                     }
-                    if (any_kept) { st = 2; status[tid] = 2; }
-                    else if (!pend) { st = 1; status[tid] = 1; }
+                    if (any_kept) { st = 2; status[id] = 2; }
+                    else if (!pend) { st = 1; status[id] = 1; }
                 }
                 if (!__syncthreads_or(st == 0)) break;       // one barrier per sweep; it also publishes the status bytes
+                if (prof && sweeps <= 4) { long long now_ = clock64(); P.prof[20 + sweeps] = now_ - pt; }
             }
-            K3_ACC(4);
-            // ---- append the newly kept boxes in order; register them for the next windows
+        }
+        K3_ACC(5);
+        // ---- append the newly kept boxes in score order (thread <-> window position again)
+        {
+            const int mine = (valid && status[tid] == 1) ? 1 : 0;
             int tot;
-            const int before = block_excl_scan(st == 1 ? 1 : 0, s_warp, tot);
-            if (st == 1) {
-                const int slot = nkept + before;
-                if (slot < max_keep) {
-                    kbox[slot] = bj; karea[slot] = aj; kkey[slot] = kj;
-                    if (!grid_insert(gg, kgrid, bj, sj, (uint16_t)slot)) kbig[atomicAdd(&s_nkbig, 1)] = (uint16_t)slot;
-                }
+            const int before = block_excl_scan(mine, s_warp, tot);
+            const int slot = nkept + before;
+            if (mine && slot < max_keep) {
+                kbox[slot] = wbox[tid]; karea[slot] = warea[tid]; kkey[slot] = skeys[j]; kcell[slot] = wcell[tid];
             }
             nkept = min(nkept + tot, max_keep);
         }
         __syncthreads();
-        K3_ACC(5);
+        K3_ACC(6);
         lo = hi;
     }
-    if (prof) { for (int q = 0; q < 6; ++q) P.prof[5 + q] = pacc[q]; P.prof[12] = nkept; P.prof[13] = k; P.prof[14] = rounds; P.prof[15] = s_nkbig; }
+    if (prof) { for (int q = 0; q < 6; ++q) P.prof[5 + q] = pacc[q]; P.prof[16] = pacc[6]; P.prof[12] = nkept; P.prof[13] = k; P.prof[14] = rounds; P.prof[15] = sweeps; }
 
     // =========================================================== stage 3: outputs
     if (MODE == MODE_DETECT) {
@@ -707,13 +748,19 @@ SmemPlan plan_smem(int kcap, int max_keep, bool kept_in_smem)
     while (s.key_cap < kcap + 64) s.key_cap <<= 1;
     int off = s.key_cap * 8;
     s.off_scr = off; off += up16(2 * NB * 4);
-    s.off_kgrid = off; off += up16((NCELLS + 8) * 4 + NCELLS * CELL_CAP * 2);
     s.off_wbox = off; off += WIN * 16;
     s.off_warea = off; off += WIN * 4;
     s.off_wside = off; off += WIN * 4;
+    s.off_wcell = off; off += WIN * 2;
     s.off_status = off; off += WIN;
-    s.off_rbig = off; off += WIN * 2;
-    s.off_kbig = off; off += up16(max_keep * 2);
+    s.off_witems = off; off += WIN * 2;
+    s.off_wstart = off; off += up16((NCELLX + 1) * 4);
+    s.off_sbox = off; off += WIN * 16;
+    s.off_sarea = off; off += WIN * 4;
+    s.off_kstart = off; off += up16((NCELLX + 1) * 4);
+    s.off_kcur = off; off += up16((NCELLX + 1) * 4);
+    s.off_kitems = off; off += up16(max_keep * 2);
+    s.off_kcell = off; off += up16(max_keep * 2);
     s.off_kbox = s.off_karea = s.off_kkey = -1;
     if (kept_in_smem) {
         s.off_kbox = off; off += up16(max_keep * 16);
@@ -724,7 +771,7 @@ SmemPlan plan_smem(int kcap, int max_keep, bool kept_in_smem)
     return s;
 }
 
-constexpr int K3_STATIC_SMEM = 40 * 1024;        // round grid + small arrays declared __shared__ in k_sort_nms
+constexpr int K3_STATIC_SMEM = 2 * 1024;         // small arrays declared __shared__ in k_sort_nms
 
 static long long *g_prof_dev = nullptr;
 

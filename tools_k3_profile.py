@@ -19,10 +19,11 @@ torch.cuda.synchronize()
 out = (C.c_longlong * 32)()
 _lib.check(_lib.lib().fdt_debug_k3_profile(out))
 names = ["minmax", "hist+scan(+select)", "scatter(+bitonic)", "-", "-", "win:rank", "win:decode+geom", "win:csr build",
-         "win:A kept-query", "win:B window-query", "win:resolve+append", "output", "kept", "k", "rounds", "-"]
-tot = sum(out[i] for i in list(range(12)))
+         "win:A kept-query", "win:B window-query", "win:resolve", "output", "kept", "k", "rounds", "sweeps", "win:append",
+         "look-calls", "sum nd", "ovf threads", "bigcell cands", "t(sweep1)", "t(sweep2)", "t(sweep3)", "t(sweep4)", "max visits", "sum visits", "max tests", "sum tests"]
+tot = sum(out[i] for i in list(range(12)) + [16])
 for i, n in enumerate(names):
-    if n in ("rounds", "kept", "k", "-"):
+    if n in ("rounds", "kept", "k", "-", "sweeps", "look-calls", "sum nd", "ovf threads", "bigcell cands", "max visits", "sum visits", "max tests", "sum tests") or n.startswith("t("):
         print(f"{n:14s} {out[i]}")
     else:
         print(f"{n:14s} {out[i]:9d} cyc  {100 * out[i] / max(tot, 1):5.1f}%")
