@@ -10,9 +10,11 @@
 //                  shared -> one 64-bit atomicMax per block and GT) and a second pass applies
 //                  box_utils.py:150-154.
 //   k_loss_prior   smooth-L1 over positives (:96-101) and the mining input loss_c (:104-110).
-//   k_mine         one CTA per image: radix select of the num_neg-th largest loss (keys cached in shared
-//                  memory when the row fits), neg = rank < num_neg (:112-116), then CE over pos U neg
-//                  (:119-128).
+//   mining         neg = rank < num_neg of the descending sort (:112-116) == the num_neg largest 64-bit composites
+//                  (loss key << 32 | ~prior): unique, so ties resolve to the lower prior index.  k_loss_prior (or
+//                  k_mine_hist) histograms the top 12 bits chip-wide, k_mine_select (one CTA per image) finishes an MSB
+//                  radix select 12 bits per row scan (normally 2 scans) -> one cutoff per image, k_mine_apply (chip-wide)
+//                  writes the mask and accumulates CE over pos U neg (:119-128).
 //   k_loss_final / k_multibox_backward.
 #include "fdt_common.cuh"
 
@@ -22,11 +24,14 @@ constexpr int M_THREADS = 256;
 constexpr int M_WARPS = M_THREADS / 32;
 constexpr int GT_TILE = 256;
 constexpr int MINE_THREADS = 1024;
-constexpr int MINE_SMEM_KEYS = 53248;       // 208 KB of cached keys
+constexpr int MINE_BINS = 4096;             // 12-bit digits
+
+__device__ __forceinline__ unsigned long long mine_comp(float v, unsigned p) { return ((unsigned long long)fdt_float_key(v) << 32) | (unsigned)~p; }
 
 struct GtTile {
     float4 box[GT_TILE];
     float area[GT_TILE];
+    int idx[GT_TILE];          // GT index inside the image (tiles are compacted, order preserved)
 };
 
 __device__ __forceinline__ float iou_match(const float4 a, const float area_a, const float4 pf, const float area_b)
@@ -54,6 +59,13 @@ __device__ __forceinline__ void finalize_prior(const float *__restrict__ gt, int
     if (bto) bto[t] = ov;
 }
 
+// One thread per prior.  GT boxes are staged through shared memory in tiles of 256 and CULLED per block: a GT box whose
+// clamped overlap with the bounding box of the block's 256 priors is empty has IoU exactly 0 with every one of them (fp32
+// subtraction is monotone, so w_bb <= 0 implies w <= 0 for each prior), and a zero can never win `v > best` -- skipping it
+// leaves best_truth_idx / best_truth_overlap bit-identical.  Consecutive priors are spatial neighbours (one or two feature
+// map rows), so at the fine pyramid levels ~90 % of the GT boxes drop out.  GT 0 is never culled (it seeds the argmax,
+// box_utils.py:197 returns index 0 when all overlaps are 0) and in bipartite mode block 0 culls nothing, so the first prior
+// still wins an all-zero row of overlaps.max(1) (:136).
 template <bool BIP>
 __global__ void __launch_bounds__(M_THREADS)
 k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const int64_t *__restrict__ gt_off,
@@ -63,6 +75,8 @@ k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const i
 {
     __shared__ GtTile tile;
     __shared__ unsigned long long s_best[BIP ? GT_TILE : 1][BIP ? M_WARPS : 1];
+    __shared__ unsigned s_bb[4];
+    __shared__ int s_wcnt[M_WARPS];
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t p = (int64_t)blockIdx.x * M_THREADS + tid;
     const bool valid = p < N;
@@ -81,22 +95,49 @@ k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const i
     const float hw = pr.z / 2.0f, hh = pr.w / 2.0f;    // point_form, box_utils.py:15-16
     const float4 pf = make_float4(pr.x - hw, pr.y - hh, pr.x + hw, pr.y + hh);
     const float area_b = (pf.z - pf.x) * (pf.w - pf.y);
+    // bounding box of the block's priors (order-preserving integer keys make float min/max an integer atomic)
+    if (tid < 4) s_bb[tid] = tid < 2 ? 0xffffffffu : 0u;
+    __syncthreads();
+    {
+        unsigned k0 = valid ? fdt_float_key(pf.x) : 0xffffffffu, k1 = valid ? fdt_float_key(pf.y) : 0xffffffffu;
+        unsigned k2 = valid ? fdt_float_key(pf.z) : 0u, k3 = valid ? fdt_float_key(pf.w) : 0u;
+        k0 = __reduce_min_sync(0xffffffffu, k0); k1 = __reduce_min_sync(0xffffffffu, k1);
+        k2 = __reduce_max_sync(0xffffffffu, k2); k3 = __reduce_max_sync(0xffffffffu, k3);
+        if (lane == 0) { atomicMin(&s_bb[0], k0); atomicMin(&s_bb[1], k1); atomicMax(&s_bb[2], k2); atomicMax(&s_bb[3], k3); }
+    }
+    __syncthreads();
+    const float4 bb = make_float4(fdt_key_float(s_bb[0]), fdt_key_float(s_bb[1]), fdt_key_float(s_bb[2]), fdt_key_float(s_bb[3]));
+    const bool cull = !(BIP && blockIdx.x == 0);
     float best = 0.0f;
     int bi = 0;
     for (int t0 = 0; t0 < G; t0 += GT_TILE) {
         const int tn = min(GT_TILE, G - t0);
-        __syncthreads();
+        // ---- stage + cull + compact (order preserved)
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool keep = false;
         if (tid < tn) {
             const float *row = gt + 5 * (g0 + t0 + tid);
-            float4 a = make_float4(row[0], row[1], row[2], row[3]);
-            tile.box[tid] = a;
-            tile.area[tid] = (a.z - a.x) * (a.w - a.y);
+            a = make_float4(row[0], row[1], row[2], row[3]);
+            const float wbb = fminf(a.z, bb.z) - fmaxf(a.x, bb.x), hbb = fminf(a.w, bb.w) - fmaxf(a.y, bb.y);
+            keep = !cull || (t0 + tid == 0) || !(wbb <= 0.0f || hbb <= 0.0f);      // NaN keeps
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        __syncthreads();                               // previous tile fully consumed
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, tc = 0;
+#pragma unroll
+        for (int w = 0; w < M_WARPS; ++w) { const int c = s_wcnt[w]; if (w < warp) before += c; tc += c; }
+        if (keep) {
+            const int ps = before + __popc(bal & ((1u << lane) - 1u));
+            tile.box[ps] = a; tile.area[ps] = (a.z - a.x) * (a.w - a.y); tile.idx[ps] = t0 + tid;
         }
         __syncthreads();
-        for (int g = 0; g < tn; ++g) {
+        for (int g = 0; g < tc; ++g) {
             const float v = iou_match(tile.box[g], tile.area[g], pf, area_b);
-            if (t0 + g == 0) { best = v; bi = 0; }
-            else if (v > best) { best = v; bi = t0 + g; }                      // first index wins ties (:197)
+            const int gi = tile.idx[g];
+            if (gi == 0) { best = v; bi = 0; }
+            else if (v > best) { best = v; bi = gi; }                          // first index wins ties (:197)
             if (BIP) {
                 unsigned key = valid ? fdt_float_key(v) : 0u;
                 unsigned mx = __reduce_max_sync(0xffffffffu, key);
@@ -107,11 +148,11 @@ k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const i
         }
         if (BIP) {
             __syncthreads();
-            if (tid < tn) {
+            if (tid < tc) {
                 unsigned long long m = s_best[tid][0];
 #pragma unroll
                 for (int w = 1; w < M_WARPS; ++w) m = max(m, s_best[tid][w]);
-                atomicMax(&bestprior[g0 + t0 + tid], m);
+                atomicMax(&bestprior[g0 + tile.idx[tid]], m);
             }
         }
     }
@@ -186,7 +227,7 @@ __device__ __forceinline__ T block_sum(T v, T *s_red)
 __global__ void __launch_bounds__(M_THREADS)
 k_loss_prior(const float4 *__restrict__ loc, const float *__restrict__ conf, const float4 *__restrict__ loc_t,
              const int64_t *__restrict__ conf_t, int64_t N, int C, LossAcc *__restrict__ acc,
-             float *__restrict__ loss_c_all, int32_t *__restrict__ num_pos)
+             float *__restrict__ loss_c_all, int32_t *__restrict__ num_pos, int *__restrict__ hist)
 {
     __shared__ double s_red[M_WARPS];
     __shared__ int s_cnt[M_WARPS];
@@ -209,7 +250,9 @@ k_loss_prior(const float4 *__restrict__ loc, const float *__restrict__ conf, con
         float s = 0.0f;
         for (int c = 0; c < C; ++c) s += fdt_expf_cr(row[c] - xmax);                // box_utils.py:269
         const float v = (fdt_logf_cr(s) + xmax) - row[label];                      // :106
-        loss_c_all[t] = is_pos ? 0.0f : v;                                         // :110
+        const float lc = is_pos ? 0.0f : v;                                        // :110
+        loss_c_all[t] = lc;
+        atomicAdd(&hist[(size_t)b * MINE_BINS + (int)(mine_comp(lc, (unsigned)p) >> 52)], 1);
     }
     const double tot = block_sum<double>(sl, s_red);
     const int cnt = block_sum<int>(is_pos, s_cnt);
@@ -219,128 +262,113 @@ k_loss_prior(const float4 *__restrict__ loc, const float *__restrict__ conf, con
     }
 }
 
-// One CTA per image.  MODE 0: standalone mining (pos given as uint8, writes neg).  MODE 1: fused with the
-// final CE over pos U neg (writes sel = pos | neg and accumulates loss_c).
-template <int MODE>
-__global__ void __launch_bounds__(MINE_THREADS, 1)
-k_mine(const float *__restrict__ loss_c, const uint8_t *__restrict__ pos_in, const int64_t *__restrict__ conf_t,
-       const float *__restrict__ conf, const int32_t *__restrict__ num_pos_in, int64_t N, int C, int negpos_ratio,
-       uint8_t *__restrict__ out_mask, LossAcc *__restrict__ acc, int use_smem)
+// standalone mining entry: histogram of the top 12 composite bits + positives per image
+__global__ void __launch_bounds__(M_THREADS)
+k_mine_hist(const float *__restrict__ loss_c, const uint8_t *__restrict__ pos, int64_t N, int *__restrict__ hist, int32_t *__restrict__ num_pos)
 {
-    extern __shared__ unsigned s_keys[];
-    __shared__ int s_hist[256];
+    __shared__ int s_cnt[M_WARPS];
+    const int b = blockIdx.y;
+    const int64_t p = (int64_t)blockIdx.x * M_THREADS + threadIdx.x;
+    int is_pos = 0;
+    if (p < N) {
+        is_pos = pos[(int64_t)b * N + p] != 0;
+        atomicAdd(&hist[(size_t)b * MINE_BINS + (int)(mine_comp(loss_c[(int64_t)b * N + p], (unsigned)p) >> 52)], 1);
+    }
+    const int cnt = block_sum<int>(is_pos, s_cnt);
+    if (threadIdx.x == 0 && cnt) atomicAdd(&num_pos[b], cnt);
+}
+
+// One CTA per image: cutoff[b] = the num_neg-th largest composite (selected <=> comp >= cutoff); ~0 = nothing selected.
+__global__ void __launch_bounds__(MINE_THREADS, 1)
+k_mine_select(const float *__restrict__ loss_c, const int *__restrict__ hist0, const int32_t *__restrict__ num_pos, int64_t N,
+              int negpos_ratio, unsigned long long *__restrict__ cutoff)
+{
+    __shared__ int s_h[MINE_BINS];
+    __shared__ int s_warp[33];
     __shared__ int s_sel[3];
-    __shared__ int s_red_i[32];
-    __shared__ double s_red_d[32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *lrow = loss_c + (int64_t)b * N;
-
-    int64_t num_pos;
-    if (MODE == 0) {
-        int c = 0;
-        for (int64_t p = tid; p < N; p += MINE_THREADS) c += pos_in[(int64_t)b * N + p] != 0;
-        c = block_sum<int>(c, s_red_i);
-        if (tid == 0) s_sel[0] = c;
-        __syncthreads();
-        num_pos = s_sel[0];
-        __syncthreads();
-    } else {
-        num_pos = num_pos_in[b];
-    }
-    int64_t num_neg = (int64_t)negpos_ratio * num_pos;                         // multibox_loss.py:115
+    long long num_neg = (long long)negpos_ratio * num_pos[b];                   // multibox_loss.py:115
     if (num_neg > N - 1) num_neg = N - 1;
-
-    if (use_smem)
-        for (int64_t p = tid; p < N; p += MINE_THREADS) s_keys[p] = fdt_float_key(lrow[p]);
-    __syncthreads();
-    auto key_at = [&](int64_t p) -> unsigned { return use_smem ? s_keys[p] : fdt_float_key(lrow[p]); };
-
-    unsigned T = 0xffffffffu;      // selected: key > T, plus the first r (index order) with key == T
-    int r = 0, n_eq = 0;
-    if (num_neg > 0) {
-        unsigned prefix = 0, pmask = 0;
-        int need = (int)num_neg;
-        for (int shift = 24; shift >= 0; shift -= 8) {
-            if (tid < 256) s_hist[tid] = 0;
+    if (num_neg <= 0) { if (tid == 0) cutoff[b] = ~0ull; return; }
+    int need = (int)num_neg;
+    unsigned long long prefix = 0, pmask = 0;
+    for (int level = 0, shift = 52; ; ++level, shift -= 12) {
+        const int sh = shift < 0 ? 0 : shift;
+        const int nb = shift < 0 ? 16 : MINE_BINS;                            // last level: the 4 lowest bits
+        if (level == 0) {
+            for (int i = tid; i < MINE_BINS; i += MINE_THREADS) s_h[i] = hist0[(size_t)b * MINE_BINS + i];
+        } else {
+            for (int i = tid; i < MINE_BINS; i += MINE_THREADS) s_h[i] = 0;
             __syncthreads();
-            for (int64_t base = 0; base < N; base += MINE_THREADS) {
-                int64_t p = base + tid;
-                int d = 256;
-                if (p < N) {
-                    unsigned k = key_at(p);
-                    if ((k & pmask) == prefix) d = (int)((k >> shift) & 0xff);
-                }
-                unsigned peers = __match_any_sync(0xffffffffu, d);
-                if (d < 256 && lane == __ffs(peers) - 1) atomicAdd(&s_hist[d], __popc(peers));
+            for (int64_t p = tid; p < N; p += MINE_THREADS) {
+                const unsigned long long c = mine_comp(lrow[p], (unsigned)p);
+                if ((c & pmask) == prefix) atomicAdd(&s_h[(int)((c >> sh) & (unsigned long long)(nb - 1))], 1);
             }
-            __syncthreads();
-            if (warp == 0) {
-                int c = 0;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) c += s_hist[255 - 8 * lane - q];
-                int cum = c;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, cum, o); if (lane >= o) cum += v; }
-                unsigned hit = __ballot_sync(0xffffffffu, cum >= need);
-                int first = __ffs(hit) - 1;
-                if (lane == first) {
-                    int rem = need - (cum - c);
-                    for (int q = 0; q < 8; ++q) {
-                        int hc = s_hist[255 - 8 * lane - q];
-                        if (hc >= rem) { s_sel[0] = 255 - 8 * lane - q; s_sel[1] = rem; s_sel[2] = hc; break; }
-                        rem -= hc;
-                    }
-                }
-            }
-            __syncthreads();
-            prefix |= (unsigned)s_sel[0] << shift;
-            pmask |= 0xffu << shift;
-            need = s_sel[1];
-            n_eq = s_sel[2];
-            __syncthreads();
         }
-        T = prefix; r = need;              // n_eq keys equal T; the first r of them (lowest index) are taken
-    }
-
-    // neg mask (+ CE over pos U neg)
-    unsigned char *mrow = out_mask + (int64_t)b * N;
-    double ce = 0.0;
-    const bool tie_slow = (num_neg > 0) && (r < n_eq);
-    for (int64_t p = tid; p < N; p += MINE_THREADS) {
-        const unsigned k = key_at(p);
-        bool neg = (num_neg > 0) && (k > T || (k == T && !tie_slow));
-        bool pos = (MODE == 0) ? false : (conf_t[(int64_t)b * N + p] > 0);
-        mrow[p] = (unsigned char)(neg || pos);
-    }
-    if (tie_slow) {                        // rare: duplicated boundary value -> ordered pick by one warp
+        __syncthreads();
+        // descending scan over the bins: find the digit d with (count above d) < need <= (count above d) + h[d]
+        int c4[MINE_BINS / MINE_THREADS], sum = 0;
+#pragma unroll
+        for (int q = 0; q < MINE_BINS / MINE_THREADS; ++q) { c4[q] = s_h[MINE_BINS - 1 - (tid * (MINE_BINS / MINE_THREADS) + q)]; sum += c4[q]; }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        if (lane == 31) s_warp[warp] = inc;
         __syncthreads();
         if (warp == 0) {
-            int taken = 0;
-            for (int64_t base = 0; base < N && taken < r; base += 32) {
-                int64_t p = base + lane;
-                bool eq = p < N && key_at(p) == T;
-                unsigned bal = __ballot_sync(0xffffffffu, eq);
-                int rank = taken + __popc(bal & ((1u << lane) - 1u));
-                if (eq && rank < r) mrow[p] = 1;
-                taken += __popc(bal);
-            }
+            int w = s_warp[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += v; }
+            s_warp[lane] = winc - w;
         }
         __syncthreads();
-    }
-    if (MODE == 1) {
+        int run = inc - sum + s_warp[warp];
+#pragma unroll
+        for (int q = 0; q < MINE_BINS / MINE_THREADS; ++q) {
+            if (run < need && run + c4[q] >= need) { s_sel[0] = MINE_BINS - 1 - (tid * (MINE_BINS / MINE_THREADS) + q); s_sel[1] = need - run; s_sel[2] = c4[q]; }
+            run += c4[q];
+        }
         __syncthreads();
-        for (int64_t p = tid; p < N; p += MINE_THREADS) {
-            if (!mrow[p]) continue;
-            const int64_t t = (int64_t)b * N + p;
+        prefix |= (unsigned long long)s_sel[0] << sh;
+        pmask |= (unsigned long long)(nb - 1) << sh;
+        need = s_sel[1];
+        const bool done = (s_sel[2] == need) || shift < 0;                     // whole bin taken, or all 64 bits fixed
+        __syncthreads();
+        if (done) break;
+    }
+    if (tid == 0) cutoff[b] = prefix;
+}
+
+// MODE 0: neg mask only.  MODE 1: sel = pos | neg and CE over the selection (F.cross_entropy, sum).
+template <int MODE>
+__global__ void __launch_bounds__(M_THREADS)
+k_mine_apply(const float *__restrict__ loss_c, const unsigned long long *__restrict__ cutoff, const int64_t *__restrict__ conf_t,
+             const float *__restrict__ conf, int64_t N, int C, uint8_t *__restrict__ out_mask, LossAcc *__restrict__ acc)
+{
+    __shared__ double s_red[M_WARPS];
+    const int b = blockIdx.y;
+    const int64_t p = (int64_t)blockIdx.x * M_THREADS + threadIdx.x;
+    double ce = 0.0;
+    if (p < N) {
+        const int64_t t = (int64_t)b * N + p;
+        const unsigned long long cut = cutoff[b];
+        const bool neg = cut != ~0ull && mine_comp(loss_c[t], (unsigned)p) >= cut;          // multibox_loss.py:116
+        const int64_t label = (MODE == 1) ? conf_t[t] : 0;
+        const bool sel = neg || (MODE == 1 && label > 0);
+        out_mask[t] = (uint8_t)sel;
+        if (MODE == 1 && sel) {
             const float *row = conf + t * C;
             float m = row[0];
             for (int c = 1; c < C; ++c) m = fmaxf(m, row[c]);
             double s = 0.0;
             for (int c = 0; c < C; ++c) s += exp((double)(row[c] - m));
-            ce += (log(s) + (double)m) - (double)row[conf_t[t]];                   // :128 F.cross_entropy, sum
+            ce = (log(s) + (double)m) - (double)row[label];                                  // :128
         }
-        ce = block_sum<double>(ce, s_red_d);
-        if (tid == 0 && ce != 0.0) atomicAdd(&acc->loss_c, ce);
+    }
+    if (MODE == 1) {
+        ce = block_sum<double>(ce, s_red);
+        if (threadIdx.x == 0 && ce != 0.0) atomicAdd(&acc->loss_c, ce);
     }
 }
 
@@ -425,14 +453,27 @@ int launch_match(const float *priors, const float *gt, const int64_t *gt_off, in
     return FDT_OK;
 }
 
-template <int MODE>
-int launch_mine(const float *loss_c, const uint8_t *pos, const int64_t *conf_t, const float *conf, const int32_t *num_pos,
-                int B, int64_t N, int C, int ratio, uint8_t *mask, LossAcc *acc, cudaStream_t st)
+struct MineWs { int *hist; unsigned long long *cutoff; int32_t *num_pos; size_t bytes; };
+MineWs plan_mine_ws(void *ws, int B)
 {
-    const int use_smem = N <= MINE_SMEM_KEYS;
-    const size_t smem = use_smem ? (size_t)N * 4 : 0;
-    FDT_CUDA(cudaFuncSetAttribute(k_mine<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, MINE_SMEM_KEYS * 4));
-    k_mine<MODE><<<B, MINE_THREADS, smem, st>>>(loss_c, pos, conf_t, conf, num_pos, N, C, ratio, mask, acc, use_smem);
+    MineWs m;
+    char *p = (char *)ws;
+    size_t o = 0;
+    m.hist = (int *)(p + o); o += fdt_align256((size_t)B * MINE_BINS * 4);
+    m.cutoff = (unsigned long long *)(p + o); o += fdt_align256((size_t)B * 8);
+    m.num_pos = (int32_t *)(p + o); o += fdt_align256((size_t)B * 4);
+    m.bytes = o;
+    return m;
+}
+
+template <int MODE>
+int launch_mine_tail(const float *loss_c, const MineWs &m, const int64_t *conf_t, const float *conf, int B, int64_t N, int C,
+                     int ratio, uint8_t *mask, LossAcc *acc, cudaStream_t st)
+{
+    k_mine_select<<<B, MINE_THREADS, 0, st>>>(loss_c, m.hist, m.num_pos, N, ratio, m.cutoff);
+    FDT_LAUNCH_CHECK();
+    dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
+    k_mine_apply<MODE><<<grid, M_THREADS, 0, st>>>(loss_c, m.cutoff, conf_t, conf, N, C, mask, acc);
     FDT_LAUNCH_CHECK();
     return FDT_OK;
 }
@@ -471,25 +512,32 @@ FDT_API int fdt_match_encode(const float *priors, const float *gt, const int64_t
                         best_truth_idx, best_truth_overlap, ws, (cudaStream_t)stream);
 }
 
-FDT_API size_t fdt_mine_workspace_bytes(int, int64_t) { return 256; }
+FDT_API size_t fdt_mine_workspace_bytes(int B, int64_t) { return plan_mine_ws(nullptr, B > 0 ? B : 1).bytes; }
 
 FDT_API int fdt_hard_negative_mine(const float *loss_c, const uint8_t *pos, int B, int64_t N, int negpos_ratio,
-                                   uint8_t *neg, void *, size_t, fdt_stream_t stream)
+                                   uint8_t *neg, void *ws, size_t ws_bytes, fdt_stream_t stream)
 {
+    cudaStream_t st = (cudaStream_t)stream;
     FDT_REQUIRE(B >= 0 && N >= 0 && negpos_ratio >= 0, FDT_E_INVALID, "fdt_hard_negative_mine: bad sizes");
     if (B == 0 || N == 0) return FDT_OK;
-    FDT_REQUIRE(loss_c && pos && neg, FDT_E_INVALID, "fdt_hard_negative_mine: null pointer argument");
-    return launch_mine<0>(loss_c, pos, nullptr, nullptr, nullptr, B, N, 2, negpos_ratio, neg, nullptr, (cudaStream_t)stream);
+    FDT_REQUIRE(loss_c && pos && neg && ws && fdt_aligned(ws, 256), FDT_E_INVALID, "fdt_hard_negative_mine: null / misaligned pointer");
+    MineWs m = plan_mine_ws(ws, B);
+    FDT_REQUIRE(ws_bytes >= m.bytes, FDT_E_WORKSPACE, "fdt_hard_negative_mine: workspace %zu < %zu bytes", ws_bytes, m.bytes);
+    FDT_CUDA(cudaMemsetAsync(ws, 0, m.bytes, st));
+    dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
+    k_mine_hist<<<grid, M_THREADS, 0, st>>>(loss_c, pos, N, m.hist, m.num_pos);
+    FDT_LAUNCH_CHECK();
+    return launch_mine_tail<0>(loss_c, m, nullptr, nullptr, B, N, 2, negpos_ratio, neg, nullptr, st);
 }
 
-struct LossWs { LossAcc *acc; int32_t *num_pos; float *loss_c_all; void *match; size_t bytes; };
+struct LossWs { LossAcc *acc; MineWs mine; float *loss_c_all; void *match; size_t bytes; };
 static LossWs plan_loss_ws(void *ws, int B, int64_t N, int64_t total_gt)
 {
     LossWs w;
     char *p = (char *)ws;
     size_t o = 0;
     w.acc = (LossAcc *)(p + o); o += 256;
-    w.num_pos = (int32_t *)(p + o); o += fdt_align256((size_t)B * 4);
+    w.mine = plan_mine_ws(p + o, B); o += w.mine.bytes;
     w.loss_c_all = (float *)(p + o); o += fdt_align256((size_t)B * N * 4);
     w.match = (void *)(p + o); o += plan_match_ws(nullptr, B, N, total_gt).bytes;
     w.bytes = o;
@@ -519,7 +567,7 @@ FDT_API int fdt_multibox_loss_forward(const float *loc, const float *conf, const
     FDT_REQUIRE(ws_bytes >= w.bytes, FDT_E_WORKSPACE, "fdt_multibox_loss_forward: workspace %zu < %zu bytes", ws_bytes, w.bytes);
     float *lca = loss_c_all ? loss_c_all : w.loss_c_all;
 
-    FDT_CUDA(cudaMemsetAsync(w.acc, 0, 256 + fdt_align256((size_t)B * 4), st));
+    FDT_CUDA(cudaMemsetAsync(w.acc, 0, 256 + w.mine.bytes, st));
     const int64_t n_conf = (int64_t)B * N * C;
     unsigned blocks = (unsigned)((n_conf + 256 * 8 - 1) / (256 * 8));
     if (blocks > FDT_NUM_SMS * 8) blocks = FDT_NUM_SMS * 8;
@@ -528,11 +576,11 @@ FDT_API int fdt_multibox_loss_forward(const float *loc, const float *conf, const
     rc = launch_match(priors, gt, gt_off, B, N, total_gt, threshold, var0, var1, bipartite, loc_t, conf_t, nullptr, nullptr, w.match, st);
     if (rc != FDT_OK) return rc;
     dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
-    k_loss_prior<<<grid, M_THREADS, 0, st>>>((const float4 *)loc, conf, (const float4 *)loc_t, conf_t, N, C, w.acc, lca, w.num_pos);
+    k_loss_prior<<<grid, M_THREADS, 0, st>>>((const float4 *)loc, conf, (const float4 *)loc_t, conf_t, N, C, w.acc, lca, w.mine.num_pos, w.mine.hist);
     FDT_LAUNCH_CHECK();
-    rc = launch_mine<1>(lca, nullptr, conf_t, conf, w.num_pos, B, N, C, negpos_ratio, sel, w.acc, st);
+    rc = launch_mine_tail<1>(lca, w.mine, conf_t, conf, B, N, C, negpos_ratio, sel, w.acc, st);
     if (rc != FDT_OK) return rc;
-    k_loss_final<<<1, 32, 0, st>>>(w.acc, w.num_pos, B, losses, norm);
+    k_loss_final<<<1, 32, 0, st>>>(w.acc, w.mine.num_pos, B, losses, norm);
     FDT_LAUNCH_CHECK();
     return FDT_OK;
 }

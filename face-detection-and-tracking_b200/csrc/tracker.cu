@@ -83,12 +83,6 @@ k_track_mask(const double *__restrict__ dets, const int64_t *__restrict__ frame_
     if (lane == 0) row_nan[g] = any_nan;
 }
 
-struct TrackState {            // per local detection index, double buffered across frames
-    int32_t *head, *len, *start;
-    double *maxs;
-    double *box;               // [TR_MAX_D][5]
-};
-
 // exclusive scan of one int per thread over the block; returns (exclusive prefix, total)
 __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total)
 {
@@ -100,7 +94,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total)
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        int w = s_warp[lane], winc = w;
+        int w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0, winc = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int n = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += n; }
         s_warp[lane] = winc - w;
@@ -138,7 +132,7 @@ k_track_resolve(const ResolveParams P)
     __shared__ int s_flag;
     __shared__ int s_slow[4];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x;   // NT = cap: one thread per track / detection
     int cur = 0;                       // buffer index of the frame being processed
     int T = 0;                         // active tracks = |order[prev]|
     int64_t n_fin = 0, fin_rows = 0;   // finished tracks so far, and their total length (uniform across threads)
@@ -158,14 +152,14 @@ k_track_resolve(const ResolveParams P)
         // ---- stage this frame: boxes, candidate rows of the active tracks, NaN flag
         if (tid == 0) s_flag = 0;
         __syncthreads();
-        for (int i = tid; i < D * 5; i += TR_THREADS) box[i] = P.dets[5 * g0 + i];
+        for (int i = tid; i < D * 5; i += NT) box[i] = P.dets[5 * g0 + i];
         const int Wd = (D + 31) >> 5;
         int has_nan = 0;
-        for (int i = tid; i < T * Wd; i += TR_THREADS) {
+        for (int i = tid; i < T * Wd; i += NT) {
             const int t = i / Wd, c = i - t * Wd;
             cand[t * W + c] = P.mask[(gp0 + pord[t]) * W + c];
         }
-        for (int t = tid; t < T; t += TR_THREADS) has_nan |= P.row_nan[gp0 + pord[t]];
+        for (int t = tid; t < T; t += NT) has_nan |= P.row_nan[gp0 + pord[t]];
         if (tid < D) owner[tid] = INT_MAX;
         if (tid < CAP) match[tid] = -1;
         if (has_nan || (P.force_slow && T > 0)) s_flag = 1;
@@ -422,7 +416,7 @@ FDT_API int fdt_iou_track(const double *dets, const int64_t *frame_off, int64_t 
                 "fdt_iou_track: %lld detections in one frame need %zu bytes of shared memory (limit %d; 768 per frame always fits)",
                 (long long)max_dets_per_frame, smem, FDT_SMEM_MAX - 1024);
     FDT_CUDA(cudaFuncSetAttribute(k_track_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_track_resolve<<<1, TR_THREADS, smem, st>>>(P);
+    k_track_resolve<<<1, P.cap, smem, st>>>(P);      // cap = multiple of 32 >= max detections per frame, <= 1024
     FDT_LAUNCH_CHECK();
     k_track_scatter<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t.det_head, t.det_pos, t.fin_id, track_off, total, track_dets);
     FDT_LAUNCH_CHECK();

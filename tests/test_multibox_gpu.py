@@ -98,7 +98,9 @@ def gpu_mine(loss_c, pos, ratio):
     B, N = loss_c.shape
     lc = cu(loss_c.astype(np.float32)); ps = cu(pos.astype(np.uint8))
     neg = torch.empty((B, N), dtype=torch.uint8, device=dev)
-    _lib.check(_lib.lib().fdt_hard_negative_mine(lc.data_ptr(), ps.data_ptr(), B, N, ratio, neg.data_ptr(), None, 0, _lib.stream_ptr()))
+    L = _lib.lib()
+    ws = _lib.workspace(L.fdt_mine_workspace_bytes(B, N), dev, "mine")
+    _lib.check(L.fdt_hard_negative_mine(lc.data_ptr(), ps.data_ptr(), B, N, ratio, neg.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
     return npy(neg).astype(bool)
 
 
