@@ -286,7 +286,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
     e2e = {"value": world * B * e2e_steps / e2e_dt, "unit": "frames/s",
-           "h2d_bytes_per_step": int(loc_h.numel() * 4 + conf_h.numel() * 4 + pri_h.numel() * 4),
+           "h2d_bytes_per_step": int(conf_h.numel() * 4 + pri_h.numel() * 4),
+           "h2d_note": "conf + priors are copied (cudaMemcpyAsync from pinned memory); the pinned loc tensor (%d bytes) is NOT copied: "
+                       "k_sort_nms gathers only the rows NMS decodes (<= 1024 x 16 B per image and round) from host memory over PCIe" % int(loc_h.numel() * 4),
+           "host_input_bytes_per_step": int(loc_h.numel() * 4 + conf_h.numel() * 4 + pri_h.numel() * 4),
            "d2h_bytes_per_step": int(o.numel() * 4), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_dt / e2e_steps,
            "api": "fdt_b200.layers.Detect.__call__(pinned CPU tensors) -> fdt_detect_host"}
 

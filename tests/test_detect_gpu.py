@@ -174,6 +174,20 @@ def test_detect_host_buffers_equal_device_path(layers, golden):
     assert o.device.type == "cpu" and tuple(o.shape) == (4, 2, 750, 5)
 
 
+def test_detect_host_pinned_buffers_zero_copy_loc(layers):
+    """pinned loc is gathered in place over PCIe (no H2D copy of loc); pageable loc is copied: same bits either way."""
+    pri = synth.priors_numpy(640, 640)
+    loc, conf = synth.detect_inputs(4, pri, 123, 0.05)
+    det = layers.Detect(2, 0, 750, 0.05, 0.3)
+    pinned = [torch.from_numpy(a).pin_memory() for a in (loc, conf, pri)]
+    pageable = [torch.from_numpy(a) for a in (loc, conf, pri)]
+    o1 = det(*pinned); o2 = det(*pageable)
+    o3 = det(pinned[0][:, :, :].view(4, -1), pinned[1], pinned[2])
+    ref = oracle_detect(loc, conf, pri)[0]
+    for o in (o1, o2, o3):
+        assert o.device.type == "cpu" and np.array_equal(o.numpy(), ref)
+
+
 @pytest.mark.parametrize("mode", ["random", "clustered"])
 def test_detect_batch64_headline_config(layers, mode):
     """BASELINE config 2: B=64 @640x640, conf 0.05, nms 0.3, top_k 750, nms_top_k 5000."""
