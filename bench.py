@@ -61,11 +61,20 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def host_threads():
+    """all hardware threads this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:                                             # noqa: BLE001
+        return os.cpu_count() or 1
+
+
 def cpu_oracle_rate(loc, conf, pri, budget_s, early_exit, threads=0):
     """frames/s of the C oracle port on the host cores; repeats the batch until ~budget_s of wall time."""
     from oracle import oracle as orc
     det = orc.Detect(2, 0, TOP_K, CONF_T, NMS_T)
     det.early_exit = early_exit
+    threads = threads if threads > 0 else host_threads()
     det.n_threads = threads
     det(loc[:2], conf[:2], pri)                                   # page in
     n, t0 = 0, time.perf_counter()
@@ -75,7 +84,7 @@ def cpu_oracle_rate(loc, conf, pri, budget_s, early_exit, threads=0):
         dt = time.perf_counter() - t0
         if dt >= budget_s or n >= 64 * 64:
             break
-    return n / dt, n, dt, orc.max_threads() if threads <= 0 else threads
+    return n / dt, n, dt, threads
 
 
 class ClockSampler(threading.Thread):
@@ -139,7 +148,8 @@ def run_reference(args):
     from oracle import oracle as orc
     det = orc.Detect(2, 0, TOP_K, CONF_T, NMS_T)
     det.early_exit = False
-    cores = orc.max_threads()
+    cores = host_threads()
+    det.n_threads = cores
     for _ in range(max(args.warmup, 1)):
         det(loc, conf, pri)
     t0 = time.perf_counter()
