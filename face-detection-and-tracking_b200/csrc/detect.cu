@@ -100,7 +100,7 @@ __global__ void k_build_keys(const float *__restrict__ scores, int64_t n, uint64
 // ------------------------------------------------------------------------------------------- K3
 struct SmemPlan {
     int key_cap;                                   // entries of the key array (power of two >= kcap + 64)
-    int off_scr, off_wbox, off_warea, off_wside, off_wcell, off_status, off_witems, off_wstart, off_sbox, off_sarea;
+    int off_scr, off_wbox, off_warea, off_wside, off_wcell, off_status, off_witems, off_wstart, off_sbox, off_sarea, off_sdeps, off_sndep;
     int off_kstart, off_kcur, off_kitems, off_kcell;
     int off_kbox, off_karea, off_kkey;             // < 0: kept arrays live in the global workspace
     int total;
@@ -240,6 +240,40 @@ __device__ __forceinline__ bool csr_query(const GridGeom &gg, const int *start, 
     return false;
 }
 
+// Forward half of csr_query for the window grid: visits only CSR positions AFTER `own_t` (own level: the rest of the own
+// row and the rows below; coarser levels: everything in range; finer levels: nothing).  Every pair of window candidates
+// that csr_query would find from either side is found by exactly one of the two forward queries (the one with the lower
+// CSR position), because each side's full query finds the other.
+template <typename F>
+__device__ __forceinline__ void csr_query_forward(const GridGeom &gg, const int *start, const float4 bj, const float sj,
+                                                  const float prune, const int own_cell, const int own_t, F &&visit)
+{
+    float c = gg.c0, inv = gg.inv0, cprev = 0.0f;
+    int G = 32, base = 0;
+#pragma unroll 1
+    for (int lev = 0; lev < NLEV; ++lev, cprev = c, c *= 2.0f, inv *= 0.5f, base += G * G, G >>= 1) {
+        if (own_cell >= base + G * G) continue;          // finer than the own level: those candidates look forward to us
+        if (c < prune * sj) continue;
+        if (cprev * prune > sj) break;
+        if (start[base + G * G] == start[base]) continue;
+        const float pad = 1.01f * c;
+        const int cx0 = cell_of(bj.x - pad, gg.x0, inv, G), cx1 = cell_of(bj.z, gg.x0, inv, G);
+        int cy0 = cell_of(bj.y - pad, gg.y0, inv, G);
+        const int cy1 = cell_of(bj.w, gg.y0, inv, G);
+        const bool own_level = own_cell >= base;         // (own_cell < base + G*G holds here)
+        const int own_cy = own_level ? (own_cell - base) / G : -1;
+        if (own_level) cy0 = max(cy0, own_cy);
+        for (int cy = cy0; cy <= cy1; ++cy) {
+            const int t1 = start[base + cy * G + cx1 + 1];
+            int t = start[base + cy * G + cx0];
+            if (cy == own_cy) t = max(t, own_t + 1);
+            for (; t < t1; ++t) visit(t);
+        }
+    }
+    const int t1 = start[BIGCELL + 1];
+    for (int t = max(start[BIGCELL], own_t + 1); t < t1; ++t) visit(t);
+}
+
 // clock64 that cannot be read before a preceding barrier has released: BAR.SYNC is deferred-blocking, the shared-memory
 // load below is the first instruction that really waits for it, and the clock read takes the loaded value as an input.
 __device__ __forceinline__ long long fdt_clock_after(const int *smem_word)
@@ -300,6 +334,8 @@ k_sort_nms(const SortNmsParams P)
     int *wstart = reinterpret_cast<int *>(smem + P.sm.off_wstart);               // [NCELLX + 1]
     float4 *sbox = reinterpret_cast<float4 *>(smem + P.sm.off_sbox);             // [WIN] window boxes in cell (CSR) order
     float *sarea = reinterpret_cast<float *>(smem + P.sm.off_sarea);
+    uint16_t *sdeps = reinterpret_cast<uint16_t *>(smem + P.sm.off_sdeps);       // [WIN][DEPS] earlier suppressors per window candidate
+    int *sndep = reinterpret_cast<int *>(smem + P.sm.off_sndep);                 // [WIN] how many were found (may exceed DEPS)
     int *kstart = reinterpret_cast<int *>(smem + P.sm.off_kstart);               // [NCELLX + 1] CSR over the kept boxes
     int *kcur = reinterpret_cast<int *>(smem + P.sm.off_kcur);                   // [NCELLX + 1] fill cursors
     uint16_t *kitems = reinterpret_cast<uint16_t *>(smem + P.sm.off_kitems);     // [max_keep]
@@ -510,6 +546,7 @@ k_sort_nms(const SortNmsParams P)
             }
         }
         for (int i = tid; i <= NCELLX; i += K3_THREADS) { wstart[i] = 0; kstart[i] = 0; }
+        sndep[tid] = 0;
         if (tid == 0) { s_ext[0] = 0xffffffffu; s_ext[1] = 0xffffffffu; s_ext[2] = 0u; s_ext[3] = 0u; }
         // ---- exact order inside the window: rank = bucket start + number of larger keys in the same bucket
         const int j = lo + tid;
@@ -605,57 +642,41 @@ k_sort_nms(const SortNmsParams P)
         if (have) status[id] = alive ? 0 : 2;
         K3_ACC(3);
         __syncthreads();
-        // ---- phase B: the earlier survivors of this window that suppress this one.  Keeps the DEPS earliest (highest-score)
-        //      ones: in crowded scenes one of them is almost always kept, which settles this survivor without the rest.
-        int nd = 0;
-        bool ovf = false;
-        uint16_t dep[DEPS];
-#pragma unroll
-        for (int d = 0; d < DEPS; ++d) dep[d] = 0;
+        // ---- phase B: suppression pairs among the survivors of this window, each unordered pair examined once (forward
+        //      queries); "a suppresses b" (a earlier in score order) is recorded in b's list with shared-memory atomics.
         if (alive) {
-            auto add_dep = [&](const uint16_t a) {
-                bool dup = false;
-#pragma unroll
-                for (int d = 0; d < DEPS; ++d) dup |= (d < nd) && dep[d] == a;
-                if (dup) return;
-                if (nd < DEPS) {
-#pragma unroll
-                    for (int d = 0; d < DEPS; ++d) if (d == nd) dep[d] = a;
-                    ++nd;
-                } else {
-                    ovf = true;
-                    uint16_t mx = dep[0];
-#pragma unroll
-                    for (int d = 1; d < DEPS; ++d) mx = max(mx, dep[d]);
-                    if (a < mx) {
-#pragma unroll
-                        for (int d = 0; d < DEPS; ++d) if (dep[d] == mx) dep[d] = a;
-                    }
+            auto pair = [&](int t2) {
+                const int other = witems[t2];
+                if (chk && status[other] == 2) return;
+                const float4 bo = sbox[t2];
+                const float ao = sarea[t2];
+                const bool me_first = id < other;            // window index = score order
+                const bool sup = me_first ? fdt_suppresses_fast(bj, aj, bo, ao, thr) : fdt_suppresses_fast(bo, ao, bj, aj, thr);
+                if (sup) {
+                    const int later = me_first ? other : id, earlier = me_first ? id : other;
+                    const int sl = atomicAdd(&sndep[later], 1);
+                    if (sl < DEPS) sdeps[later * DEPS + sl] = (uint16_t)earlier;
                 }
             };
-            if (in_grid) {
-                auto collect = [&](int t) -> bool {
-                    const int a = witems[t];
-                    if (a < id && !(chk && status[a] == 2) && fdt_suppresses_fast(sbox[t], sarea[t], bj, aj, thr)) add_dep((uint16_t)a);
-                    return false;
-                };
-                csr_query(gg, wstart, bj, sj, prune, collect);
-            } else {
-                for (int a = 0; a < id; ++a)
-                    if (status[a] != 2 && fdt_suppresses(wbox[a], warea[a], bj, aj, thr)) add_dep((uint16_t)a);
+            if (in_grid) csr_query_forward(gg, wstart, bj, sj, prune, (int)wcell[id], tid, pair);
+            else {
+                const int t1 = wstart[BIGCELL + 1];        // irregular boxes sit last in CSR order: every regular candidate's
+                for (int t2 = tid + 1; t2 < t1; ++t2) pair(t2);       // forward query reaches them; they only pair among themselves
             }
         }
+        __syncthreads();                                   // dependency lists complete
         K3_ACC(4);
         // ---- phase C: resolve
         {
             int st = alive ? 0 : 2;
+            const int nfound = have ? sndep[id] : 0;             // published by the barrier of K3_ACC / first sweep below
+            const int nd = min(nfound, DEPS);
+            const bool ovf = nfound > DEPS;
             for (;;) {
                 if (prof) ++sweeps;
                 if (st == 0) {
                     bool any_kept = false, pend = false;
-#pragma unroll
-                    for (int d = 0; d < DEPS; ++d)
-                        if (d < nd) { const int s = status[dep[d]]; any_kept |= (s == 1); pend |= (s == 0); }
+                    for (int d = 0; d < nd; ++d) { const int s2 = status[sdeps[id * DEPS + d]]; any_kept |= (s2 == 1); pend |= (s2 == 0); }
                     if (ovf && !any_kept && !pend) {  // the DEPS earliest suppressors are all dead: look at the others
                         if (in_grid) {
                             auto look = [&](int t) -> bool {
@@ -757,6 +778,8 @@ SmemPlan plan_smem(int kcap, int max_keep, bool kept_in_smem)
     s.off_wstart = off; off += up16((NCELLX + 1) * 4);
     s.off_sbox = off; off += WIN * 16;
     s.off_sarea = off; off += WIN * 4;
+    s.off_sdeps = off; off += WIN * DEPS * 2;
+    s.off_sndep = off; off += WIN * 4;
     s.off_kstart = off; off += up16((NCELLX + 1) * 4);
     s.off_kcur = off; off += up16((NCELLX + 1) * 4);
     s.off_kitems = off; off += up16(max_keep * 2);
