@@ -244,9 +244,10 @@ __device__ __forceinline__ bool csr_query(const GridGeom &gg, const int *start, 
 // row and the rows below; coarser levels: everything in range; finer levels: nothing).  Every pair of window candidates
 // that csr_query would find from either side is found by exactly one of the two forward queries (the one with the lower
 // CSR position), because each side's full query finds the other.
+// `part` of `nparts` (1, 2 or 4 lanes share a candidate): the lanes take grid rows (and pseudo-cell items) round-robin.
 template <typename F>
 __device__ __forceinline__ void csr_query_forward(const GridGeom &gg, const int *start, const float4 bj, const float sj,
-                                                  const float prune, const int own_cell, const int own_t, F &&visit)
+                                                  const float prune, const int own_cell, const int own_t, const int part, const int nparts, F &&visit)
 {
     float c = gg.c0, inv = gg.inv0, cprev = 0.0f;
     int G = 32, base = 0;
@@ -261,9 +262,9 @@ __device__ __forceinline__ void csr_query_forward(const GridGeom &gg, const int 
         int cy0 = cell_of(bj.y - pad, gg.y0, inv, G);
         const int cy1 = cell_of(bj.w, gg.y0, inv, G);
         const bool own_level = own_cell >= base;         // (own_cell < base + G*G holds here)
-        const int own_cy = own_level ? (own_cell - base) / G : -1;
+        const int own_cy = own_level ? (own_cell - base) >> (5 - lev) : -1;      // G = 32 >> lev
         if (own_level) cy0 = max(cy0, own_cy);
-        for (int cy = cy0; cy <= cy1; ++cy) {
+        for (int cy = cy0 + part; cy <= cy1; cy += nparts) {
             const int t1 = start[base + cy * G + cx1 + 1];
             int t = start[base + cy * G + cx0];
             if (cy == own_cy) t = max(t, own_t + 1);
@@ -271,7 +272,7 @@ __device__ __forceinline__ void csr_query_forward(const GridGeom &gg, const int 
         }
     }
     const int t1 = start[BIGCELL + 1];
-    for (int t = max(start[BIGCELL], own_t + 1); t < t1; ++t) visit(t);
+    for (int t = max(start[BIGCELL], own_t + 1) + part; t < t1; t += nparts) visit(t);
 }
 
 // clock64 that cannot be read before a preceding barrier has released: BAR.SYNC is deferred-blocking, the shared-memory
@@ -346,7 +347,7 @@ k_sort_nms(const SortNmsParams P)
     uint64_t *kkey = P.sm.off_kkey >= 0 ? reinterpret_cast<uint64_t *>(smem + P.sm.off_kkey) : P.g_kkey + (int64_t)list * P.max_keep;
 
     __shared__ int s_sel[3];
-    __shared__ int s_placed, s_maxb;
+    __shared__ int s_placed, s_maxb, s_next;
     __shared__ unsigned s_kmin, s_kmax;
     __shared__ int s_hist8[256];
     __shared__ int s_warp[33];
@@ -547,6 +548,7 @@ k_sort_nms(const SortNmsParams P)
         }
         for (int i = tid; i <= NCELLX; i += K3_THREADS) { wstart[i] = 0; kstart[i] = 0; }
         sndep[tid] = 0;
+        if (tid == 0) s_next = 0;
         if (tid == 0) { s_ext[0] = 0xffffffffu; s_ext[1] = 0xffffffffu; s_ext[2] = 0u; s_ext[3] = 0u; }
         // ---- exact order inside the window: rank = bucket start + number of larger keys in the same bucket
         const int j = lo + tid;
@@ -644,24 +646,41 @@ k_sort_nms(const SortNmsParams P)
         __syncthreads();
         // ---- phase B: suppression pairs among the survivors of this window, each unordered pair examined once (forward
         //      queries); "a suppresses b" (a earlier in score order) is recorded in b's list with shared-memory atomics.
-        if (alive) {
-            auto pair = [&](int t2) {
-                const int other = witems[t2];
-                if (chk && status[other] == 2) return;
-                const float4 bo = sbox[t2];
-                const float ao = sarea[t2];
-                const bool me_first = id < other;            // window index = score order
-                const bool sup = me_first ? fdt_suppresses_fast(bj, aj, bo, ao, thr) : fdt_suppresses_fast(bo, ao, bj, aj, thr);
-                if (sup) {
-                    const int later = me_first ? other : id, earlier = me_first ? id : other;
-                    const int sl = atomicAdd(&sndep[later], 1);
-                    if (sl < DEPS) sdeps[later * DEPS + sl] = (uint16_t)earlier;
+        //      1, 2 or 4 lanes share a candidate (small windows leave threads to spare; the lanes take grid rows round-robin);
+        //      warps fetch chunks of candidates dynamically, coarse levels (the longest queries) first.
+        {
+            const int lpc = nvalid > K3_THREADS / 2 ? 1 : nvalid > K3_THREADS / 4 ? 2 : 4;      // lanes per candidate
+            const int per_chunk = 32 / lpc;
+            const int part = lane % lpc, sub = lane / lpc;
+            for (;;) {
+                int chunk = 0;
+                if (lane == 0) chunk = atomicAdd(&s_next, per_chunk);
+                chunk = __shfl_sync(0xffffffffu, chunk, 0);
+                if (chunk >= nvalid) break;
+                const int t = nvalid - 1 - (chunk + sub);          // CSR position, from the end
+                if (t < 0) continue;
+                const int cid = witems[t];
+                if (status[cid] == 2) continue;                     // suppressed in phase A
+                const float4 cb = sbox[t];
+                const float ca = sarea[t], cs = fmaxf(cb.z - cb.x, cb.w - cb.y);
+                auto pair = [&](int t2) {
+                    const int other = witems[t2];
+                    if (chk && status[other] == 2) return;
+                    const float4 bo = sbox[t2];
+                    const float ao = sarea[t2];
+                    const bool me_first = cid < other;           // window index = score order
+                    const bool sup = me_first ? fdt_suppresses_fast(cb, ca, bo, ao, thr) : fdt_suppresses_fast(bo, ao, cb, ca, thr);
+                    if (sup) {
+                        const int later = me_first ? other : cid, earlier = me_first ? cid : other;
+                        const int sl = atomicAdd(&sndep[later], 1);
+                        if (sl < DEPS) sdeps[later * DEPS + sl] = (uint16_t)earlier;
+                    }
+                };
+                if (wcell[cid] != BIGCELL) csr_query_forward(gg, wstart, cb, cs, prune, (int)wcell[cid], t, part, lpc, pair);
+                else {
+                    const int t1 = wstart[BIGCELL + 1];    // irregular boxes sit last in CSR order: every regular candidate's
+                    for (int t2 = t + 1 + part; t2 < t1; t2 += lpc) pair(t2);   // forward query reaches them; they only pair among themselves
                 }
-            };
-            if (in_grid) csr_query_forward(gg, wstart, bj, sj, prune, (int)wcell[id], tid, pair);
-            else {
-                const int t1 = wstart[BIGCELL + 1];        // irregular boxes sit last in CSR order: every regular candidate's
-                for (int t2 = tid + 1; t2 < t1; ++t2) pair(t2);       // forward query reaches them; they only pair among themselves
             }
         }
         __syncthreads();                                   // dependency lists complete
