@@ -52,7 +52,7 @@ __global__ void k_track_frame_of(const int64_t *__restrict__ frame_off, int64_t 
 // one warp per detection g of frame f (f < F-1): bits over the detections of frame f+1
 __global__ void __launch_bounds__(256)
 k_track_mask(const double *__restrict__ dets, const int64_t *__restrict__ frame_off, const int32_t *__restrict__ frame_of,
-             int64_t F, int64_t total, int W, double sigma_iou, uint32_t *__restrict__ mask, uint8_t *__restrict__ row_nan)
+             int64_t F, int64_t total, int W, double sigma_iou, uint32_t *__restrict__ mask)
 {
     const int lane = threadIdx.x & 31;
     const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -78,9 +78,9 @@ k_track_mask(const double *__restrict__ dets, const int64_t *__restrict__ frame_
         }
         const unsigned bits = __ballot_sync(0xffffffffu, over);
         any_nan |= __any_sync(0xffffffffu, isn);
-        if (lane == 0) mask[g * W + c] = bits;
+        if (lane == 0) mask[g * (W + 1) + c] = bits;
     }
-    if (lane == 0) row_nan[g] = any_nan;
+    if (lane == 0) mask[g * (W + 1) + W] = any_nan ? 1u : 0u;        // row word W: some IoU of this row is NaN
 }
 
 // exclusive scan of one int per thread over the block; returns (exclusive prefix, total)
@@ -107,99 +107,154 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total)
 
 struct ResolveParams {
     const double *dets; const int64_t *frame_off; int64_t F; int W; int cap;   // cap = W * 32 >= max detections per frame
-    const uint32_t *mask; const uint8_t *row_nan;
+    const uint32_t *mask;                        // [total][W + 1]: W words of "IoU > sigma" bits + 1 word NaN flag
     double sigma_iou, sigma_h; int64_t t_min;
     int32_t *det_head, *det_pos, *fin_id;        // [total]
     int64_t *n_tracks, *track_off, *track_start; double *track_max;
     int force_slow;
+    int prefetch;                                // 1: stage frame f+1 while frame f is resolved (needs the larger smem layout)
 };
+
+// async global -> shared copies (LDGSTS) used to stage frame f+1 while frame f is being resolved
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __global__ void __launch_bounds__(TR_THREADS, 1)
 k_track_resolve(const ResolveParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    // layout: cand[cap * W] | boxes[2][CAP*5] f64 | maxs[2][CAP] f64 | int arrays
-    const int W = P.W, CAP = P.cap;
-    uint32_t *cand = reinterpret_cast<uint32_t *>(smem);
-    double *boxbuf = reinterpret_cast<double *>(smem + ((size_t)CAP * W * 4 + 15) / 16 * 16);
-    double *maxbuf = boxbuf + 2 * CAP * 5;
+    // layout: rows[NR][cap*(W+1)] u32 | boxes[NBX][cap*5] f64 | maxs[2][cap] f64 | int arrays   (NR, NBX = 2, 3 with prefetch; 1, 2 without)
+    const int W = P.W, W1 = P.W + 1, CAP = P.cap;
+    const int PF = P.prefetch, NR = PF ? 2 : 1, NBX = PF ? 3 : 2;
+    uint32_t *rowbuf = reinterpret_cast<uint32_t *>(smem);
+    double *boxbuf = reinterpret_cast<double *>(smem + ((size_t)NR * CAP * W1 * 4 + 15) / 16 * 16);
+    double *maxbuf = boxbuf + NBX * CAP * 5;
     int32_t *ibase = reinterpret_cast<int32_t *>(maxbuf + 2 * CAP);
     int32_t *headbuf = ibase, *lenbuf = ibase + 2 * CAP, *startbuf = ibase + 4 * CAP;
     int32_t *order = ibase + 6 * CAP;        // [2][CAP] local det index of each active track, in order
     int32_t *owner = ibase + 8 * CAP;        // [CAP]
     int32_t *match = ibase + 9 * CAP;        // [CAP] det matched to track t (or -1)
     __shared__ int s_warp[33];
-    __shared__ int s_flag;
+    __shared__ long long s_warp64[33];
     __shared__ int s_slow[4];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x;   // NT = cap: one thread per track / detection
-    int cur = 0;                       // buffer index of the frame being processed
+    int cur = 0;                       // parity of the frame being processed (rows / per-det state double buffers)
     int T = 0;                         // active tracks = |order[prev]|
     int64_t n_fin = 0, fin_rows = 0;   // finished tracks so far, and their total length (uniform across threads)
+
+    // async staging: boxes of frame fr -> boxbuf[fr % NBX]; candidate rows of the detections of frame g (they belong to the
+    // tracks that are active while frame g+1 is resolved) -> rowbuf[PF ? g & 1 : 0]
+    auto stage_boxes = [&](int64_t fr) {
+        const int64_t a0 = P.frame_off[fr];
+        const int Dn = min((int)(P.frame_off[fr + 1] - a0), CAP);
+        double *bdst = boxbuf + (fr % NBX) * CAP * 5;
+        for (int i = tid; i < Dn * 5; i += NT) cp_async8(bdst + i, P.dets + 5 * a0 + i);
+    };
+    auto stage_rows = [&](int64_t g) {
+        const int64_t a0 = P.frame_off[g];
+        const int Dn = min((int)(P.frame_off[g + 1] - a0), CAP);
+        uint32_t *rdst = rowbuf + (PF ? (g & 1) : 0) * CAP * W1;
+        for (int i = tid; i < Dn * W1; i += NT) cp_async4(rdst + i, P.mask + a0 * W1 + i);
+    };
+    if (PF && P.F > 0) { stage_boxes(0); cp_async_commit(); }
+
+    // exclusive scan of a 64-bit value per thread (two packed counters)
+    auto scan64 = [&](long long v, long long &total) -> long long {
+        long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { long long n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+        __syncthreads();
+        if (lane == 31) s_warp64[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = lane < (NT >> 5) ? s_warp64[lane] : 0, winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { long long n = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += n; }
+            s_warp64[lane] = winc - w;
+            if (lane == 31) s_warp64[32] = winc;
+        }
+        __syncthreads();
+        total = s_warp64[32];
+        return inc - v + s_warp64[warp];
+    };
 
     for (int64_t f = 0; f < P.F; ++f, cur ^= 1) {
         const int prv = cur ^ 1;
         const int64_t g0 = P.frame_off[f];
         const int D = min((int)(P.frame_off[f + 1] - g0), CAP);      // host guarantees D <= cap; clamp keeps memory safe
-        const int64_t gp0 = f > 0 ? P.frame_off[f - 1] : 0;
-        double *box = boxbuf + cur * CAP * 5, *pbox = boxbuf + prv * CAP * 5;
+        double *box = boxbuf + (f % NBX) * CAP * 5, *pbox = boxbuf + ((f + NBX - 1) % NBX) * CAP * 5;
+        uint32_t *rows = rowbuf + (PF ? prv : 0) * CAP * W1;          // rows of frame f-1's detections = of the active tracks
         double *maxs = maxbuf + cur * CAP, *pmaxs = maxbuf + prv * CAP;
         int32_t *head = headbuf + cur * CAP, *phead = headbuf + prv * CAP;
         int32_t *len = lenbuf + cur * CAP, *plen = lenbuf + prv * CAP;
         int32_t *start = startbuf + cur * CAP, *pstart = startbuf + prv * CAP;
         int32_t *ord = order + cur * CAP, *pord = order + prv * CAP;
 
-        // ---- stage this frame: boxes, candidate rows of the active tracks, NaN flag
-        if (tid == 0) s_flag = 0;
-        __syncthreads();
-        for (int i = tid; i < D * 5; i += NT) box[i] = P.dets[5 * g0 + i];
-        const int Wd = (D + 31) >> 5;
-        int has_nan = 0;
-        for (int i = tid; i < T * Wd; i += NT) {
-            const int t = i / Wd, c = i - t * Wd;
-            cand[t * W + c] = P.mask[(gp0 + pord[t]) * W + c];
-        }
-        for (int t = tid; t < T; t += NT) has_nan |= P.row_nan[gp0 + pord[t]];
+        // ---- with prefetch this frame was staged one iteration ago and the next one is staged behind the resolution
+        if (!PF) { stage_boxes(f); if (f > 0) stage_rows(f - 1); cp_async_commit(); }
+        cp_async_wait_all();
         if (tid < D) owner[tid] = INT_MAX;
         if (tid < CAP) match[tid] = -1;
-        if (has_nan || (P.force_slow && T > 0)) s_flag = 1;
         __syncthreads();
-        const bool slow = s_flag != 0;
-        __syncthreads();
+        if (PF && f + 1 < P.F) { stage_boxes(f + 1); stage_rows(f); cp_async_commit(); }
+        const int Wd = (D + 31) >> 5;
+        const int my = tid < T ? pord[tid] : 0;                       // this thread's track = detection `my` of frame f-1
+        uint32_t *row = rows + my * W1;
+        const bool slow = __syncthreads_or((tid < T && row[W] != 0) || (P.force_slow && T > 0));
 
         int n_upd = 0;                 // tracks continued into this frame (uniform after the paths below)
         if (!slow) {
-            // ---- deferred acceptance == serial dictatorship in track order (see header)
-            int prop = -1;
-            for (;;) {
-                if (tid == 0) s_flag = 0;
-                __syncthreads();
-                prop = -1;
-                if (tid < T && D > 0) {
-                    const double *tb = pbox + 5 * pord[tid];
-                    double bv = 0.0;
-                    for (int c = 0; c < Wd; ++c) {
-                        uint32_t bits = cand[tid * W + c];
-                        while (bits) {
-                            const int j = c * 32 + __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            const double v = iou_f64(box + 5 * j, tb);
-                            if (prop < 0 || v > bv) { bv = v; prop = j; }       // argmax: first max (:133)
-                        }
+            // ---- deferred acceptance == serial dictatorship in track order (see header).  Each track ranks its
+            //      candidates once (the 4 best are cached; more are re-ranked only if all 4 get refused).
+            const double *tb = pbox + 5 * my;
+            double cv[4] = {0.0, 0.0, 0.0, 0.0};
+            int cj[4] = {-1, -1, -1, -1};
+            int nc = 0;
+            auto rank_candidates = [&]() {
+                nc = 0;
+                for (int c = 0; c < Wd; ++c) {
+                    uint32_t bits = row[c];
+                    while (bits) {
+                        const int j = c * 32 + __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const double v = iou_f64(box + 5 * j, tb);
+                        int p = nc < 4 ? nc : 4;                       // first slot with a smaller value (ties keep the lower j first)
+#pragma unroll
+                        for (int q = 3; q >= 0; --q) if (q < nc && cv[q] < v) p = q;
+#pragma unroll
+                        for (int q = 3; q >= 1; --q) if (q > p) { cv[q] = cv[q - 1]; cj[q] = cj[q - 1]; }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) if (q == p) { cv[q] = v; cj[q] = j; }
+                        ++nc;
                     }
+                }
+            };
+            const bool active = tid < T && D > 0;
+            if (active) rank_candidates();
+            int ptr = 0, prop = -1;
+            for (;;) {
+                prop = -1;
+                if (active) {
+                    if (ptr >= 4 && nc > 4) { rank_candidates(); ptr = 0; }      // refused bits were cleared from the row
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (q == ptr && q < nc) prop = cj[q];
                     if (prop >= 0) atomicMin(&owner[prop], tid);
                 }
                 __syncthreads();
-                if (prop >= 0 && owner[prop] != tid) {                          // refused by a lower-order track
-                    cand[tid * W + (prop >> 5)] &= ~(1u << (prop & 31));
-                    s_flag = 1;
-                }
-                __syncthreads();
-                const bool again = s_flag != 0;
-                __syncthreads();
-                if (!again) break;
+                const bool refused = prop >= 0 && owner[prop] != tid;           // a lower-order track holds it
+                if (refused) { row[prop >> 5] &= ~(1u << (prop & 31)); ++ptr; }
+                if (!__syncthreads_or(refused)) break;
             }
-            const int matched = (tid < T && prop >= 0) ? 1 : 0;
+            const int matched = (active && prop >= 0) ? 1 : 0;
             if (matched) match[tid] = prop;
             int tot;
             const int before = block_excl_scan(matched, s_warp, tot);
@@ -207,25 +262,18 @@ k_track_resolve(const ResolveParams P)
             // a track whose turn comes after all D detections are taken is dropped, not finished (:130, Q5)
             const bool had_dets = D > 0 && before < D;
             int fin = 0;
-            if (tid < T && !matched && had_dets) {
-                const int i = pord[tid];
-                fin = (pmaxs[i] > P.sigma_h && (int64_t)plen[i] > P.t_min) ? 1 : 0;        // :147 strict >
-            }
+            if (tid < T && !matched && had_dets) fin = (pmaxs[my] > P.sigma_h && (int64_t)plen[my] > P.t_min) ? 1 : 0;   // :147 strict >
             if (matched) ord[before] = prop;
-            int ftot;
-            const int fbefore = block_excl_scan(fin, s_warp, ftot);
-            int ltot;
-            const int lbefore = block_excl_scan(fin ? plen[pord[tid < T ? tid : 0]] : 0, s_warp, ltot);
+            long long ptot;
+            const long long pb = scan64(fin ? ((1ll << 32) | (long long)plen[my]) : 0ll, ptot);   // (count << 32) | rows
             if (fin) {
-                const int i = pord[tid];
-                const int64_t id = n_fin + fbefore;
-                P.fin_id[phead[i]] = (int32_t)id;
-                P.track_off[id] = fin_rows + lbefore;
-                P.track_start[id] = pstart[i];
-                P.track_max[id] = pmaxs[i];
+                const int64_t id = n_fin + (pb >> 32);
+                P.fin_id[phead[my]] = (int32_t)id;
+                P.track_off[id] = fin_rows + (pb & 0xffffffffll);
+                P.track_start[id] = pstart[my];
+                P.track_max[id] = pmaxs[my];
             }
-            n_fin += ftot; fin_rows += ltot;
-            __syncthreads();
+            n_fin += ptot >> 32; fin_rows += ptot & 0xffffffffll;
         } else {
             // ---- exact sequential path (warp 0), mirrors the python loop including NaN argmax
             if (warp == 0) {
@@ -278,14 +326,14 @@ k_track_resolve(const ResolveParams P)
 
         // ---- state of the continued tracks (:141-143) ...
         if (tid < T && match[tid] >= 0) {
-            const int i = pord[tid], j = match[tid];
+            const int j = match[tid];
             const double sc = box[5 * j + 4];
-            head[j] = phead[i];
-            len[j] = plen[i] + 1;
-            start[j] = pstart[i];
-            maxs[j] = sc > pmaxs[i] ? sc : pmaxs[i];                            // python max(a, b)
-            P.det_head[g0 + j] = phead[i];
-            P.det_pos[g0 + j] = plen[i];
+            head[j] = phead[my];
+            len[j] = plen[my] + 1;
+            start[j] = pstart[my];
+            maxs[j] = sc > pmaxs[my] ? sc : pmaxs[my];                          // python max(a, b)
+            P.det_head[g0 + j] = phead[my];
+            P.det_pos[g0 + j] = plen[my];
         }
         // ---- ... and new tracks from the detections left over, in detection order (:150-154)
         {
@@ -315,17 +363,16 @@ k_track_resolve(const ResolveParams P)
         const int32_t *pord = order + prv * CAP;
         int fin = 0, i = 0;
         if (tid < T) { i = pord[tid]; fin = (pmaxs[i] > P.sigma_h && (int64_t)plen[i] >= P.t_min) ? 1 : 0; }
-        int ftot, ltot;
-        const int fbefore = block_excl_scan(fin, s_warp, ftot);
-        const int lbefore = block_excl_scan(fin ? plen[i] : 0, s_warp, ltot);
+        long long ptot;
+        const long long pb = scan64(fin ? ((1ll << 32) | (long long)plen[i]) : 0ll, ptot);
         if (fin) {
-            const int64_t id = n_fin + fbefore;
+            const int64_t id = n_fin + (pb >> 32);
             P.fin_id[phead[i]] = (int32_t)id;
-            P.track_off[id] = fin_rows + lbefore;
+            P.track_off[id] = fin_rows + (pb & 0xffffffffll);
             P.track_start[id] = pstart[i];
             P.track_max[id] = pmaxs[i];
         }
-        n_fin += ftot; fin_rows += ltot;
+        n_fin += ptot >> 32; fin_rows += ptot & 0xffffffffll;
         if (tid == 0) { *P.n_tracks = n_fin; P.track_off[n_fin] = fin_rows; }
     }
 }
@@ -340,15 +387,14 @@ __global__ void k_track_scatter(const int32_t *__restrict__ det_head, const int3
     if (id >= 0) track_dets[track_off[id] + det_pos[g]] = g;
 }
 
-struct TrackWs { uint32_t *mask; uint8_t *row_nan; int32_t *frame_of, *det_head, *det_pos, *fin_id; size_t bytes; };
+struct TrackWs { uint32_t *mask; int32_t *frame_of, *det_head, *det_pos, *fin_id; size_t bytes; };
 TrackWs plan_track_ws(void *ws, int64_t total, int W)
 {
     TrackWs t;
     char *p = (char *)ws;
     size_t o = 0;
     const size_t n = (size_t)(total > 0 ? total : 1);
-    t.mask = (uint32_t *)(p + o); o += fdt_align256(n * W * 4);
-    t.row_nan = (uint8_t *)(p + o); o += fdt_align256(n);
+    t.mask = (uint32_t *)(p + o); o += fdt_align256(n * (W + 1) * 4);
     t.frame_of = (int32_t *)(p + o); o += fdt_align256(n * 4);
     t.det_head = (int32_t *)(p + o); o += fdt_align256(n * 4);
     t.det_pos = (int32_t *)(p + o); o += fdt_align256(n * 4);
@@ -357,11 +403,11 @@ TrackWs plan_track_ws(void *ws, int64_t total, int W)
     return t;
 }
 
-size_t resolve_smem(int W)
+size_t resolve_smem(int W, int prefetch)
 {
     const size_t cap = (size_t)W * 32;
-    size_t s = (cap * W * 4 + 15) / 16 * 16;
-    s += sizeof(double) * (2 * cap * 5 + 2 * cap);
+    size_t s = ((prefetch ? 2 : 1) * cap * (W + 1) * 4 + 15) / 16 * 16;
+    s += sizeof(double) * ((prefetch ? 3 : 2) * cap * 5 + 2 * cap);
     s += sizeof(int32_t) * 10 * cap;
     return s;
 }
@@ -402,18 +448,19 @@ FDT_API int fdt_iou_track(const double *dets, const int64_t *frame_off, int64_t 
     FDT_CUDA(cudaMemsetAsync(t.fin_id, 0xff, (size_t)total * 4, st));
     k_track_frame_of<<<(unsigned)F, 128, 0, st>>>(frame_off, F, t.frame_of);
     FDT_LAUNCH_CHECK();
-    k_track_mask<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(dets, frame_off, t.frame_of, F, total, W, sigma_iou, t.mask, t.row_nan);
+    k_track_mask<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(dets, frame_off, t.frame_of, F, total, W, sigma_iou, t.mask);
     FDT_LAUNCH_CHECK();
     ResolveParams P{};
-    P.dets = dets; P.frame_off = frame_off; P.F = F; P.W = W; P.cap = W * 32; P.mask = t.mask; P.row_nan = t.row_nan;
+    P.dets = dets; P.frame_off = frame_off; P.F = F; P.W = W; P.cap = W * 32; P.mask = t.mask;
     P.sigma_iou = sigma_iou; P.sigma_h = sigma_h; P.t_min = t_min;
     P.det_head = t.det_head; P.det_pos = t.det_pos; P.fin_id = t.fin_id;
     P.n_tracks = n_tracks; P.track_off = track_off; P.track_start = track_start; P.track_max = track_max;
     const char *env = getenv("FDT_TRACK_FORCE_SLOW");
     P.force_slow = (env && env[0] == '1') ? 1 : 0;
-    const size_t smem = resolve_smem(W);
+    P.prefetch = resolve_smem(W, 1) <= (size_t)FDT_SMEM_MAX - 1024;
+    const size_t smem = resolve_smem(W, P.prefetch);
     FDT_REQUIRE(smem <= (size_t)FDT_SMEM_MAX - 1024, FDT_E_UNSUPPORTED,
-                "fdt_iou_track: %lld detections in one frame need %zu bytes of shared memory (limit %d; 768 per frame always fits)",
+                "fdt_iou_track: %lld detections in one frame need %zu bytes of shared memory (limit %d; 800 per frame always fits)",
                 (long long)max_dets_per_frame, smem, FDT_SMEM_MAX - 1024);
     FDT_CUDA(cudaFuncSetAttribute(k_track_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_track_resolve<<<1, P.cap, smem, st>>>(P);      // cap = multiple of 32 >= max detections per frame, <= 1024
