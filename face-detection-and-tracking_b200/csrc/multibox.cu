@@ -25,6 +25,7 @@ constexpr int M_WARPS = M_THREADS / 32;
 constexpr int GT_TILE = 256;
 constexpr int MINE_THREADS = 1024;
 constexpr int MINE_BINS = 4096;             // 12-bit digits
+constexpr int MINE_REPL = 16;               // level-0 histogram copies (by prior index) to spread same-address atomics
 
 __device__ __forceinline__ unsigned long long mine_comp(float v, unsigned p) { return ((unsigned long long)fdt_float_key(v) << 32) | (unsigned)~p; }
 
@@ -252,7 +253,7 @@ k_loss_prior(const float4 *__restrict__ loc, const float *__restrict__ conf, con
         const float v = (fdt_logf_cr(s) + xmax) - row[label];                      // :106
         const float lc = is_pos ? 0.0f : v;                                        // :110
         loss_c_all[t] = lc;
-        atomicAdd(&hist[(size_t)b * MINE_BINS + (int)(mine_comp(lc, (unsigned)p) >> 52)], 1);
+        atomicAdd(&hist[((size_t)b * MINE_REPL + (p & (MINE_REPL - 1))) * MINE_BINS + (int)(mine_comp(lc, (unsigned)p) >> 52)], 1);
     }
     const double tot = block_sum<double>(sl, s_red);
     const int cnt = block_sum<int>(is_pos, s_cnt);
@@ -272,7 +273,7 @@ k_mine_hist(const float *__restrict__ loss_c, const uint8_t *__restrict__ pos, i
     int is_pos = 0;
     if (p < N) {
         is_pos = pos[(int64_t)b * N + p] != 0;
-        atomicAdd(&hist[(size_t)b * MINE_BINS + (int)(mine_comp(loss_c[(int64_t)b * N + p], (unsigned)p) >> 52)], 1);
+        atomicAdd(&hist[((size_t)b * MINE_REPL + (p & (MINE_REPL - 1))) * MINE_BINS + (int)(mine_comp(loss_c[(int64_t)b * N + p], (unsigned)p) >> 52)], 1);
     }
     const int cnt = block_sum<int>(is_pos, s_cnt);
     if (threadIdx.x == 0 && cnt) atomicAdd(&num_pos[b], cnt);
@@ -297,7 +298,12 @@ k_mine_select(const float *__restrict__ loss_c, const int *__restrict__ hist0, c
         const int sh = shift < 0 ? 0 : shift;
         const int nb = shift < 0 ? 16 : MINE_BINS;                            // last level: the 4 lowest bits
         if (level == 0) {
-            for (int i = tid; i < MINE_BINS; i += MINE_THREADS) s_h[i] = hist0[(size_t)b * MINE_BINS + i];
+            for (int i = tid; i < MINE_BINS; i += MINE_THREADS) {
+                int c = 0;
+#pragma unroll
+                for (int r = 0; r < MINE_REPL; ++r) c += hist0[((size_t)b * MINE_REPL + r) * MINE_BINS + i];
+                s_h[i] = c;
+            }
         } else {
             for (int i = tid; i < MINE_BINS; i += MINE_THREADS) s_h[i] = 0;
             __syncthreads();
@@ -459,7 +465,7 @@ MineWs plan_mine_ws(void *ws, int B)
     MineWs m;
     char *p = (char *)ws;
     size_t o = 0;
-    m.hist = (int *)(p + o); o += fdt_align256((size_t)B * MINE_BINS * 4);
+    m.hist = (int *)(p + o); o += fdt_align256((size_t)B * MINE_REPL * MINE_BINS * 4);
     m.cutoff = (unsigned long long *)(p + o); o += fdt_align256((size_t)B * 8);
     m.num_pos = (int32_t *)(p + o); o += fdt_align256((size_t)B * 4);
     m.bytes = o;
