@@ -16,7 +16,10 @@
 // Tie rule (unspecified in the reference, torch.sort is unstable): keys are unique, descending key order =
 // descending score, higher prior index first among equal scores.
 #include <cstdlib>
+#include <cooperative_groups.h>
 #include "fdt_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -318,7 +321,10 @@ __device__ __forceinline__ void csr_scan(int *a, int *s_warp)
     __syncthreads();
 }
 
-template <int MODE>
+// CL = CTAs per list: 1, or 2 as a thread-block cluster when the batch leaves SMs idle.  With CL = 2 both CTAs run every stage
+// redundantly and deterministically (identical shared-memory state) except phase B -- the dominant one -- whose candidates they
+// split; the partial dependency lists are merged through distributed shared memory.
+template <int MODE, int CL>
 __global__ void __launch_bounds__(K3_THREADS, 1)
 k_sort_nms(const SortNmsParams P)
 {
@@ -341,7 +347,8 @@ k_sort_nms(const SortNmsParams P)
     int *kcur = reinterpret_cast<int *>(smem + P.sm.off_kcur);                   // [NCELLX + 1] fill cursors
     uint16_t *kitems = reinterpret_cast<uint16_t *>(smem + P.sm.off_kitems);     // [max_keep]
     uint16_t *kcell = reinterpret_cast<uint16_t *>(smem + P.sm.off_kcell);       // [max_keep]
-    const int list = blockIdx.x;
+    const int list = blockIdx.x / CL;
+    const int crank = CL == 2 ? (int)(blockIdx.x & 1) : 0;     // cluster dims (2,1,1): rank = blockIdx.x % 2
     float4 *kbox = P.sm.off_kbox >= 0 ? reinterpret_cast<float4 *>(smem + P.sm.off_kbox) : P.g_kbox + (int64_t)list * P.max_keep;
     float *karea = P.sm.off_karea >= 0 ? reinterpret_cast<float *>(smem + P.sm.off_karea) : P.g_karea + (int64_t)list * P.max_keep;
     uint64_t *kkey = P.sm.off_kkey >= 0 ? reinterpret_cast<uint64_t *>(smem + P.sm.off_kkey) : P.g_kkey + (int64_t)list * P.max_keep;
@@ -362,6 +369,7 @@ k_sort_nms(const SortNmsParams P)
     if (MODE == MODE_DETECT && n_c == 1) n_c = 0;            // detection.py:66-72: one candidate -> `continue`
     const int k = min(n_c, P.nms_top_k);                     // box_utils.py:299 idx[-top_k:]
     const bool prof = P.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    const bool writer = crank == 0;                              // only one CTA of a cluster writes the results
     long long pt = prof ? clock64() : 0, pacc[7] = {0, 0, 0, 0, 0, 0, 0};
 #define K3_STAMP(slot) do { if (P.prof) __syncthreads(); if (prof) { long long now_ = fdt_clock_after(s_warp); P.prof[slot] = now_ - pt; pt = now_; } } while (0)
 #define K3_ACC(slot) do { if (P.prof) __syncthreads(); if (prof) { long long now_ = fdt_clock_after(s_warp); pacc[slot] += now_ - pt; pt = now_; } } while (0)
@@ -617,6 +625,25 @@ k_sort_nms(const SortNmsParams P)
             __syncthreads();
             csr_scan(wstart, s_warp);
             if (cell >= 0) { const int ps = wstart[cell] + slot; witems[ps] = (uint16_t)tid; sbox[ps] = bx; sarea[ps] = box_area(bx); }
+            if (CL == 2) {
+                // Both CTAs of the cluster must see the SAME CSR array (they split it by position): order every cell by window
+                // position instead of by atomic arrival.
+                __syncthreads();
+                int np = -1;
+                uint16_t it = 0;
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float ar = 0.0f;
+                if (tid < nvalid) {
+                    it = witems[tid]; b4 = sbox[tid]; ar = sarea[tid];
+                    const int c2 = wcell[it];
+                    const int s0 = wstart[c2], s1 = wstart[c2 + 1];
+                    int r = 0;
+                    for (int t2 = s0; t2 < s1; ++t2) r += witems[t2] < it;
+                    np = s0 + r;
+                }
+                __syncthreads();
+                if (np >= 0) { witems[np] = it; sbox[np] = b4; sarea[np] = ar; }
+            }
             if (rounds > 0) {
                 csr_scan(kstart, s_warp);
                 for (int i = tid; i <= NCELLX; i += K3_THREADS) kcur[i] = kstart[i];
@@ -649,13 +676,15 @@ k_sort_nms(const SortNmsParams P)
         //      1, 2 or 4 lanes share a candidate (small windows leave threads to spare; the lanes take grid rows round-robin);
         //      warps fetch chunks of candidates dynamically, coarse levels (the longest queries) first.
         {
-            const int lpc = nvalid > K3_THREADS / 2 ? 1 : nvalid > K3_THREADS / 4 ? 2 : 4;      // lanes per candidate
+            const int share = (nvalid + CL - 1) / CL;                                            // candidates this CTA queries
+            const int lpc = share > K3_THREADS / 2 ? 1 : share > K3_THREADS / 4 ? 2 : 4;        // lanes per candidate
             const int per_chunk = 32 / lpc;
             const int part = lane % lpc, sub = lane / lpc;
             for (;;) {
                 int chunk = 0;
                 if (lane == 0) chunk = atomicAdd(&s_next, per_chunk);
                 chunk = __shfl_sync(0xffffffffu, chunk, 0);
+                if (CL == 2) chunk = 2 * chunk + crank * per_chunk;    // the cluster's CTAs take alternate chunks
                 if (chunk >= nvalid) break;
                 const int t = nvalid - 1 - (chunk + sub);          // CSR position, from the end
                 if (t < 0) continue;
@@ -684,6 +713,25 @@ k_sort_nms(const SortNmsParams P)
             }
         }
         __syncthreads();                                   // dependency lists complete
+        if (CL == 2) {
+            // merge the other CTA's partial lists (distributed shared memory): read them, cluster barrier, then append
+            cg::cluster_group cluster = cg::this_cluster();
+            cluster.sync();
+            const int *r_ndep = cluster.map_shared_rank(sndep, crank ^ 1);
+            const uint16_t *r_deps = cluster.map_shared_rank(sdeps, crank ^ 1);
+            const int nrem = r_ndep[tid];
+            uint16_t rd[DEPS];
+#pragma unroll
+            for (int d = 0; d < DEPS; ++d) rd[d] = (d < nrem) ? r_deps[tid * DEPS + d] : (uint16_t)0;
+            cluster.sync();
+            const int nloc = sndep[tid];
+            int w = min(nloc, DEPS);
+#pragma unroll
+            for (int d = 0; d < DEPS; ++d)
+                if (d < nrem && w < DEPS) sdeps[tid * DEPS + w++] = rd[d];
+            sndep[tid] = nloc + nrem;
+            __syncthreads();
+        }
         K3_ACC(4);
         // ---- phase C: resolve
         {
@@ -740,6 +788,7 @@ k_sort_nms(const SortNmsParams P)
     if (prof) { for (int q = 0; q < 6; ++q) P.prof[5 + q] = pacc[q]; P.prof[16] = pacc[6]; P.prof[12] = nkept; P.prof[13] = k; P.prof[14] = rounds; P.prof[15] = sweeps; }
 
     // =========================================================== stage 3: outputs
+    if (!writer) return;
     if (MODE == MODE_DETECT) {
         const int top_k = P.top_k;
         const int cnt = min(nkept, top_k);                                   // detection.py:80
@@ -843,8 +892,23 @@ int launch_sort_nms(SortNmsParams &P, int lists, int kcap, void *kept_ws, size_t
     FDT_REQUIRE(sp.total <= limit, FDT_E_UNSUPPORTED,
                 "nms_top_k=%d / max_keep=%d need %d bytes of shared memory (limit %d)", kcap, P.max_keep, sp.total, limit);
     P.sm = sp;
-    FDT_CUDA(cudaFuncSetAttribute(k_sort_nms<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
-    k_sort_nms<MODE><<<lists, K3_THREADS, sp.total, st>>>(P);
+    // Few lists (B = 64 leaves 84 of the 148 SMs idle): two CTAs per list as a thread-block cluster.  Kept rows in global
+    // memory (large max_keep) stay on the single-CTA path.
+    const char *env_cl = getenv("FDT_K3_CLUSTER");
+    const bool want_cluster = env_cl ? env_cl[0] == '1' : true;
+    if (want_cluster && lists * 2 <= FDT_NUM_SMS && sp.off_kbox >= 0) {
+        FDT_CUDA(cudaFuncSetAttribute(k_sort_nms<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(lists * 2)); cfg.blockDim = dim3(K3_THREADS); cfg.dynamicSmemBytes = (size_t)sp.total; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        FDT_CUDA(cudaLaunchKernelEx(&cfg, k_sort_nms<MODE, 2>, P));
+    } else {
+        FDT_CUDA(cudaFuncSetAttribute(k_sort_nms<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+        k_sort_nms<MODE, 1><<<lists, K3_THREADS, sp.total, st>>>(P);
+    }
     FDT_LAUNCH_CHECK();
     return FDT_OK;
 }
