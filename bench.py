@@ -43,14 +43,20 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="random", choices=["random", "clustered"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N>1: peer = rows stored into every rank's block by the NMS kernel over NVLink (fused); nccl = all_gather")
     return ap.parse_args()
 
 
-def workload_config(mode, n_gpus):
+GATHER_NOTE = {"peer": ", gather fused into k_sort_nms (NVLink peer stores + symmetric-memory barrier)",
+               "nccl": ", NCCL all-gather of detections"}
+
+
+def workload_config(mode, n_gpus, gather="nccl"):
     return {"workload": f"Detect batch {B_PER_GPU}/GPU @{WIDTH}x{HEIGHT} (34,125 priors), conf_thresh {CONF_T}, "
                         f"top_k {TOP_K}, nms_top_k {NMS_TOP_K}, NMS {NMS_T}; synthetic heads mode={mode} seed={SEED}",
             "global_batch": B_PER_GPU * n_gpus, "priors": 34125, "classes": 2,
-            "parallelism": f"batch-sharded x{n_gpus}" + (", NCCL all-gather of detections" if n_gpus > 1 else "")}
+            "parallelism": f"batch-sharded x{n_gpus}" + (GATHER_NOTE[gather] if n_gpus > 1 else "")}
 
 
 def peaks():
@@ -211,12 +217,33 @@ def main():
         _lib.check(L.fdt_detect_sort_nms(loc.data_ptr(), pri.data_ptr(), B, N, C, TOP_K, NMS_TOP_K, NMS_T, 0.1, 0.2,
                                          out.data_ptr(), None, None, ws.data_ptr(), ws.numel(), st))
 
+    gather = args.gather if world > 1 else "nccl"
+    peer = None
+    if world > 1 and gather == "peer":
+        try:
+            from fdt_b200.sharding import PeerGatherDetect
+            peer = PeerGatherDetect(det, B)
+        except Exception as e:                          # noqa: BLE001  (symmetric memory unavailable: keep the NCCL gather)
+            if rank == 0:
+                print(f"peer gather unavailable ({e!r}); using NCCL all_gather", file=sys.stderr)
+            gather = "nccl"
+
+    def stage2_gather():
+        if peer is not None:
+            hdl = peer.hdls[peer.turn]
+            peer.turn ^= 1
+            _lib.check(L.fdt_detect_sort_nms_peers(loc.data_ptr(), pri.data_ptr(), B, N, C, TOP_K, NMS_TOP_K, NMS_T, 0.1, 0.2,
+                                                   int(hdl.buffer_ptrs_dev), world, rank * B, ws.data_ptr(), ws.numel(), st))
+            hdl.barrier()
+        else:
+            stage2()
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, out)
+
     def step():
         # == fdt_detect (stage 1 then stage 2), split only so the dominant kernel gets its own event pair
         stage1()
-        stage2()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+        stage2_gather()
 
     spin_cycles = 250_000
     for _ in range(max(args.warmup, 3)):
@@ -239,9 +266,7 @@ def main():
         ev[i][0].record()                               # time: the event pairs then see device time, not launch latency
         stage1()
         ev[i][1].record()
-        stage2()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+        stage2_gather()
         ev[i][2].record()
     torch.cuda.synchronize()
     if sampler.ok:
@@ -322,7 +347,7 @@ def main():
     line = {"metric": "frames/sec for Detect (decode+top-k+NMS) @640^2 batch 64; % HBM roofline",
             "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args.mode, world),
+            "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args.mode, world, gather),
                                                                 l2="flushed between steps (256 MiB memset + 0.1 ms spin outside the event pairs)"),
             "clocks": sampler.result(), "e2e": e2e, "gpu_launches": 2 * args.steps,
             "wall_s_timed_region": wall}

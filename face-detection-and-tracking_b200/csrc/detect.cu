@@ -128,6 +128,9 @@ struct SortNmsParams {
     int64_t *keep;              // [n] (MODE_NMS)
     int64_t *count_out;         // [1] (MODE_NMS)
     int64_t n;                  // MODE_NMS list length
+    const unsigned long long *peer_out;   // device array of n_peers output base pointers (this GPU's and its NVLink peers'), or null
+    int n_peers;
+    int64_t img_offset;         // image index of this rank's first image inside the peers' gathered blocks
     float4 *g_kbox;             // kept arrays in global memory (per list stride max_keep) when sm.off_kbox < 0
     float *g_karea;
     uint64_t *g_kkey;
@@ -792,27 +795,34 @@ k_sort_nms(const SortNmsParams P)
     if (MODE == MODE_DETECT) {
         const int top_k = P.top_k;
         const int cnt = min(nkept, top_k);                                   // detection.py:80
-        float *o = P.out + ((int64_t)(b * P.C + cl) * top_k) * 5;
-        for (int t = tid; t < top_k * 5; t += K3_THREADS) {
-            int r = t / 5, col = t - 5 * r;
-            float v = 0.0f;
-            if (r < cnt) {
-                if (col == 0) v = fdt_key_float((uint32_t)(kkey[r] >> 32));
-                else {
-                    const float4 bx = kbox[r];
-                    v = col == 1 ? bx.x : col == 2 ? bx.y : col == 3 ? bx.z : bx.w;
+        // rows go to the local output, or -- fused gather -- straight into every rank's gathered block over NVLink peer memory
+        const int ndst = P.n_peers > 0 ? P.n_peers : 1;
+        for (int pr = 0; pr < ndst; ++pr) {
+            float *base = P.n_peers > 0 ? reinterpret_cast<float *>(P.peer_out[pr]) + (P.img_offset * P.C) * (int64_t)top_k * 5 : P.out;
+            float *o = base + ((int64_t)(b * P.C + cl) * top_k) * 5;
+            for (int t = tid; t < top_k * 5; t += K3_THREADS) {
+                int r = t / 5, col = t - 5 * r;
+                float v = 0.0f;
+                if (r < cnt) {
+                    if (col == 0) v = fdt_key_float((uint32_t)(kkey[r] >> 32));
+                    else {
+                        const float4 bx = kbox[r];
+                        v = col == 1 ? bx.x : col == 2 ? bx.y : col == 3 ? bx.z : bx.w;
+                    }
                 }
+                o[t] = v;                                                    // detection.py:82
             }
-            o[t] = v;                                                        // detection.py:82
+            if (cl == 1) {                                                   // class-0 plane stays zero (:48, :63)
+                float *o0 = base + ((int64_t)(b * P.C) * top_k) * 5;
+                for (int t = tid; t < top_k * 5; t += K3_THREADS) o0[t] = 0.0f;
+            }
         }
         if (P.kept_prior) {
             int64_t *kp = P.kept_prior + (int64_t)(b * P.C + cl) * top_k;
             for (int r = tid; r < top_k; r += K3_THREADS) kp[r] = r < cnt ? (int64_t)(uint32_t)kkey[r] : -1;
         }
         if (P.counts && tid == 0) P.counts[b * P.C + cl] = cnt;
-        if (cl == 1) {                                                       // class-0 plane stays zero (:48, :63)
-            float *o0 = P.out + ((int64_t)(b * P.C) * top_k) * 5;
-            for (int t = tid; t < top_k * 5; t += K3_THREADS) o0[t] = 0.0f;
+        if (cl == 1) {
             if (P.kept_prior) {
                 int64_t *kp = P.kept_prior + (int64_t)(b * P.C) * top_k;
                 for (int r = tid; r < top_k; r += K3_THREADS) kp[r] = -1;
@@ -963,9 +973,10 @@ FDT_API int fdt_detect_candidate_counts(const void *ws, int B, int C, int32_t *c
     return FDT_OK;
 }
 
-FDT_API int fdt_detect_sort_nms(const float *loc, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
+static int detect_sort_nms_impl(const float *loc, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
                                 float nms_thresh, float var0, float var1,
                                 float *out, int32_t *counts, int64_t *kept_prior,
+                                const unsigned long long *peer_out, int n_peers, int64_t img_offset,
                                 void *ws, size_t ws_bytes, fdt_stream_t stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
@@ -976,9 +987,10 @@ FDT_API int fdt_detect_sort_nms(const float *loc, const float *priors, int B, in
                 "fdt_detect: nms_top_k=%d outside [1,%d]", nms_top_k, FDT_MAX_NMS_TOP_K);
     FDT_REQUIRE(nms_thresh > 0.0f, FDT_E_INVALID, "fdt_detect: nms_thresh must be > 0 (detection.py:28-29)");
     if (B == 0) return FDT_OK;
-    FDT_REQUIRE(out != nullptr, FDT_E_INVALID, "fdt_detect: out is null");
+    FDT_REQUIRE(out != nullptr || n_peers > 0, FDT_E_INVALID, "fdt_detect: out is null");
     const int lists = B * (C - 1);
     if (lists == 0 || N == 0) {
+        FDT_REQUIRE(n_peers == 0, FDT_E_UNSUPPORTED, "fdt_detect_sort_nms_peers: needs C >= 2 and N > 0");
         FDT_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * C * top_k * 5, st));
         if (counts) FDT_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)B * C, st));
         if (kept_prior) FDT_CUDA(cudaMemsetAsync(kept_prior, 0xff, sizeof(int64_t) * (size_t)B * C * top_k, st));
@@ -994,11 +1006,31 @@ FDT_API int fdt_detect_sort_nms(const float *loc, const float *priors, int B, in
     P.nms_top_k = nms_top_k; P.max_keep = top_k < nms_top_k ? top_k : nms_top_k; P.top_k = top_k;
     P.nms_thresh = nms_thresh; P.v0 = var0; P.v1 = var1;
     P.out = out; P.counts = counts; P.kept_prior = kept_prior;
+    P.peer_out = peer_out; P.n_peers = n_peers; P.img_offset = img_offset;
     int kcap = (int)((int64_t)nms_top_k < N ? nms_top_k : N);
     if (P.max_keep > kcap) P.max_keep = kcap;
     char *kept_ws = (char *)keys + fdt_align256((size_t)lists * (size_t)N * sizeof(uint64_t));
     size_t kept_rows = (size_t)(N < FDT_MAX_NMS_TOP_K ? N : FDT_MAX_NMS_TOP_K);
     return launch_sort_nms<MODE_DETECT>(P, lists, kcap, kept_ws, fdt_align256((size_t)lists * kept_rows * KEPT_ROW_BYTES), st);
+}
+
+FDT_API int fdt_detect_sort_nms(const float *loc, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
+                                float nms_thresh, float var0, float var1,
+                                float *out, int32_t *counts, int64_t *kept_prior,
+                                void *ws, size_t ws_bytes, fdt_stream_t stream)
+{
+    return detect_sort_nms_impl(loc, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1, out, counts, kept_prior,
+                                nullptr, 0, 0, ws, ws_bytes, stream);
+}
+
+FDT_API int fdt_detect_sort_nms_peers(const float *loc, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
+                                      float nms_thresh, float var0, float var1,
+                                      const uint64_t *peer_out_ptrs, int n_peers, int64_t image_offset,
+                                      void *ws, size_t ws_bytes, fdt_stream_t stream)
+{
+    FDT_REQUIRE(peer_out_ptrs != nullptr && n_peers >= 1 && image_offset >= 0, FDT_E_INVALID, "fdt_detect_sort_nms_peers: bad peer arguments");
+    return detect_sort_nms_impl(loc, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1, nullptr, nullptr, nullptr,
+                                (const unsigned long long *)peer_out_ptrs, n_peers, image_offset, ws, ws_bytes, stream);
 }
 
 FDT_API int fdt_detect(const float *loc, const float *conf, const float *priors,

@@ -101,3 +101,47 @@ def sharded_multibox_loss(criterion, predictions_local, targets_local, group=Non
     others_l = (sums[0] / n_glob).to(loss_l.device) - loss_l.detach() * scale
     others_c = (sums[1] / n_glob).to(loss_c.device) - loss_c.detach() * scale
     return loss_l * scale + others_l, loss_c * scale + others_c
+
+
+class PeerGatherDetect:
+    """Detect with the gather FUSED into the NMS kernel: k_sort_nms stores the detection rows of this rank's images straight
+    into every rank's gathered block [world * B_local, C, top_k, 5] over NVLink peer memory (torch symmetric memory provides
+    the peer pointers and the cross-rank barrier); no NCCL collective is launched.  Two blocks alternate between calls so a
+    rank that runs ahead never overwrites rows a slower peer is still reading.  The returned tensor is this rank's copy of the
+    gathered block and stays valid until the call after next."""
+
+    def __init__(self, detect, b_local, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._lib = _lib
+        self.detect = detect
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.b_local = int(b_local)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        shape = (self.world * self.b_local, detect.num_classes, detect.top_k, 5)
+        self.bufs, self.hdls = [], []
+        for _ in range(2):
+            t = symm_mem.empty(shape, dtype=torch.float32, device=dev)
+            self.hdls.append(symm_mem.rendezvous(t, self.group))
+            self.bufs.append(t)
+        self.turn = 0
+
+    def __call__(self, loc, conf, priors):
+        _lib = self._lib
+        L = _lib.lib()
+        d = self.detect
+        B, N = loc.shape[0], priors.shape[0]
+        assert B == self.b_local, "PeerGatherDetect was built for a fixed per-rank batch"
+        dev = loc.device
+        loc, conf, priors = _lib.dev_f32(loc, dev), _lib.dev_f32(conf, dev), _lib.dev_f32(priors, dev)
+        ws = _lib.workspace(L.fdt_detect_workspace_bytes(B, N, d.num_classes), dev, "detect")
+        st = _lib.stream_ptr()
+        hdl, buf = self.hdls[self.turn], self.bufs[self.turn]
+        self.turn ^= 1
+        _lib.check(L.fdt_detect_threshold_compact(conf.data_ptr(), B, N, d.num_classes, float(d.conf_thresh), ws.data_ptr(), ws.numel(), st))
+        _lib.check(L.fdt_detect_sort_nms_peers(loc.data_ptr(), priors.data_ptr(), B, N, d.num_classes, int(d.top_k), int(d.nms_top_k),
+                                               float(d.nms_thresh), float(d.variance[0]), float(d.variance[1]),
+                                               int(hdl.buffer_ptrs_dev), self.world, self.rank * B, ws.data_ptr(), ws.numel(), st))
+        hdl.barrier()            # all ranks' rows have landed in this rank's block (and ours in theirs)
+        return buf

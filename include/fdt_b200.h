@@ -103,6 +103,14 @@ int fdt_detect_sort_nms(const float *loc, const float *priors, int B, int64_t N,
                         float nms_thresh, float var0, float var1,
                         float *out, int32_t *counts, int64_t *kept_prior,
                         void *ws, size_t ws_bytes, fdt_stream_t stream);
+/* Stage 2 with the multi-GPU gather fused in: instead of a local `out`, the detection rows of this rank's B
+ * images are stored straight into EVERY rank's gathered block [world*B, C, top_k, 5] at image index image_offset + b, over
+ * NVLink peer memory (no separate collective).  peer_out_ptrs: DEVICE array of n_peers base pointers of those blocks (e.g.
+ * torch symmetric memory `buffer_ptrs_dev`); the caller synchronises the ranks afterwards (a symmetric-memory barrier). */
+int fdt_detect_sort_nms_peers(const float *loc, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
+                              float nms_thresh, float var0, float var1,
+                              const uint64_t *peer_out_ptrs, int n_peers, int64_t image_offset,
+                              void *ws, size_t ws_bytes, fdt_stream_t stream);
 /* Number of candidates per (image, class>=1) list after stage 1: copies B*(C-1) int32 to counts_out (device). */
 int fdt_detect_candidate_counts(const void *ws, int B, int C, int32_t *counts_out, fdt_stream_t stream);
 
