@@ -374,6 +374,9 @@ k_sort_nms(const SortNmsParams P)
     const bool prof = P.prof != nullptr && blockIdx.x == 0 && tid == 0;
     const bool writer = crank == 0;                              // only one CTA of a cluster writes the results
     long long pt = prof ? clock64() : 0, pacc[7] = {0, 0, 0, 0, 0, 0, 0};
+    const long long cta_t0 = (P.prof && tid == 0) ? clock64() : 0;
+    unsigned long long gt0 = 0;
+    if (P.prof && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
 #define K3_STAMP(slot) do { if (P.prof) __syncthreads(); if (prof) { long long now_ = fdt_clock_after(s_warp); P.prof[slot] = now_ - pt; pt = now_; } } while (0)
 #define K3_ACC(slot) do { if (P.prof) __syncthreads(); if (prof) { long long now_ = fdt_clock_after(s_warp); pacc[slot] += now_ - pt; pt = now_; } } while (0)
 
@@ -791,6 +794,7 @@ k_sort_nms(const SortNmsParams P)
     if (prof) { for (int q = 0; q < 6; ++q) P.prof[5 + q] = pacc[q]; P.prof[16] = pacc[6]; P.prof[12] = nkept; P.prof[13] = k; P.prof[14] = rounds; P.prof[15] = sweeps; }
 
     // =========================================================== stage 3: outputs
+    if (P.prof && tid == 0 && blockIdx.x < 256) { unsigned long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1)); atomicMin((unsigned long long *)&P.prof[40], gt0); atomicMax((unsigned long long *)&P.prof[41], gt0); atomicMin((unsigned long long *)&P.prof[42], gt1); atomicMax((unsigned long long *)&P.prof[43], gt1); P.prof[64 + blockIdx.x] = clock64() - cta_t0; P.prof[320 + blockIdx.x] = (long long)rounds * 100000 + k; }
     if (!writer) return;
     if (MODE == MODE_DETECT) {
         const int top_k = P.top_k;
@@ -882,8 +886,10 @@ int launch_sort_nms(SortNmsParams &P, int lists, int kcap, void *kept_ws, size_t
 {
     const char *env = getenv("FDT_K3_PROFILE");
     if (env && env[0] == '1') {
-        if (!g_prof_dev) { FDT_CUDA(cudaMalloc(&g_prof_dev, 32 * sizeof(long long))); }
-        FDT_CUDA(cudaMemsetAsync(g_prof_dev, 0, 32 * sizeof(long long), st));
+        if (!g_prof_dev) { FDT_CUDA(cudaMalloc(&g_prof_dev, 640 * sizeof(long long))); }
+        FDT_CUDA(cudaMemsetAsync(g_prof_dev, 0, 640 * sizeof(long long), st));
+        FDT_CUDA(cudaMemsetAsync(g_prof_dev + 40, 0xff, sizeof(long long), st));
+        FDT_CUDA(cudaMemsetAsync(g_prof_dev + 42, 0xff, sizeof(long long), st));
         P.prof = g_prof_dev;
     }
     FDT_REQUIRE(kcap <= FDT_MAX_NMS_TOP_K, FDT_E_UNSUPPORTED, "nms_top_k=%d exceeds %d", kcap, FDT_MAX_NMS_TOP_K);
@@ -959,6 +965,20 @@ FDT_API int fdt_detect_threshold_compact(const float *conf, int B, int64_t N, in
     uint64_t *keys = (uint64_t *)((char *)ws + fdt_align256((size_t)lists * sizeof(int32_t)));
     FDT_CUDA(cudaMemsetAsync(counters, 0, (size_t)lists * sizeof(int32_t), st));
     dim3 g2((unsigned)((N + K2_TILE - 1) / K2_TILE), (unsigned)B);
+    {
+        // K3 needs the maximum shared-memory carveout; asking for the same split here avoids an SM reconfiguration
+        // (a pipeline drain) between the two kernels of every call
+        static bool carveout_set = false;
+        if (!carveout_set) {
+            const char *e = getenv("FDT_K2_CARVEOUT");
+            const int pct = e ? atoi(e) : 100;
+            if (pct >= 0) {
+                FDT_CUDA(cudaFuncSetAttribute(k_threshold_compact<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+                FDT_CUDA(cudaFuncSetAttribute(k_threshold_compact<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            }
+            carveout_set = true;
+        }
+    }
     if (C == 2) k_threshold_compact<true><<<g2, K2_THREADS, 0, st>>>(conf, N, C, conf_thresh, counters, keys);
     else        k_threshold_compact<false><<<g2, K2_THREADS, 0, st>>>(conf, N, C, conf_thresh, counters, keys);
     FDT_LAUNCH_CHECK();
@@ -1048,12 +1068,12 @@ FDT_API int fdt_detect(const float *loc, const float *conf, const float *priors,
 // Diagnostics: with FDT_K3_PROFILE=1 in the environment, CTA 0 of k_sort_nms records clock64 deltas per phase:
 // [0] key min/max, [1] histogram+scan(+select), [2] scatter, [3] rank+permute, [4] decode+extent, [5..9] summed over
 // rounds: phase A, compaction, phase B pairs, resolve, insert; [10] rounds, [11] output, [12] kept, [13] k, [14] big list.
-FDT_API int fdt_debug_k3_profile(long long *out32_h)
+FDT_API int fdt_debug_k3_profile(long long *out640_h)
 {
-    FDT_REQUIRE(out32_h != nullptr, FDT_E_INVALID, "fdt_debug_k3_profile: null output");
+    FDT_REQUIRE(out640_h != nullptr, FDT_E_INVALID, "fdt_debug_k3_profile: null output");
     FDT_REQUIRE(g_prof_dev != nullptr, FDT_E_INVALID, "fdt_debug_k3_profile: run with FDT_K3_PROFILE=1 first");
     FDT_CUDA(cudaDeviceSynchronize());
-    FDT_CUDA(cudaMemcpy(out32_h, g_prof_dev, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+    FDT_CUDA(cudaMemcpy(out640_h, g_prof_dev, 640 * sizeof(long long), cudaMemcpyDeviceToHost));
     return FDT_OK;
 }
 

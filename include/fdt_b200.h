@@ -115,7 +115,7 @@ int fdt_detect_sort_nms_peers(const float *loc, const float *priors, int B, int6
 int fdt_detect_candidate_counts(const void *ws, int B, int C, int32_t *counts_out, fdt_stream_t stream);
 
 /* Diagnostics (FDT_K3_PROFILE=1): per-phase clock64 deltas of CTA 0 of the last fdt_detect_sort_nms / fdt_nms launch. */
-int fdt_debug_k3_profile(long long *out32_h);
+int fdt_debug_k3_profile(long long *out640_h);   /* [0..31] phases of CTA 0, [64..319] cycles per CTA, [320..575] rounds*1e5 + k per CTA */
 
 /* ---- host-buffer variants (the reference-facing call when tensors live on the CPU) --------------
  * All pointers are HOST pointers (pinned memory makes the copies asynchronous).  The context owns

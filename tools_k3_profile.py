@@ -10,13 +10,14 @@ from fdt_b200.layers import Detect
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "random"
 pri = synth.priors_numpy(640, 640)
-loc, conf = synth.detect_inputs(8, pri, 20262, 0.05, mode)
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+loc, conf = synth.detect_inputs(B, pri, 20262, 0.05, mode)
 det = Detect(2, 0, 750, 0.05, 0.3)
 args = [torch.from_numpy(a).cuda() for a in (loc, conf, pri)]
 for _ in range(3):
     det(*args)
 torch.cuda.synchronize()
-out = (C.c_longlong * 32)()
+out = (C.c_longlong * 640)()
 _lib.check(_lib.lib().fdt_debug_k3_profile(out))
 names = ["minmax", "hist+scan(+select)", "scatter(+bitonic)", "-", "-", "win:rank", "win:decode+geom", "win:csr build",
          "win:A kept-query", "win:B window-query", "win:resolve", "output", "kept", "k", "rounds", "sweeps", "win:append",
@@ -28,3 +29,9 @@ for i, n in enumerate(names):
     else:
         print(f"{n:14s} {out[i]:9d} cyc  {100 * out[i] / max(tot, 1):5.1f}%")
 print("total", tot, "cycles =", tot / 1.965e3, "us @1.965GHz")
+
+import numpy as np
+cyc = np.array([out[64 + i] for i in range(256)]); cyc = cyc[cyc > 0]
+meta = np.array([out[320 + i] for i in range(256)])[:len(cyc)]
+print("per-CTA cycles: n=%d min=%d mean=%d max=%d (%.1f us)  rounds max=%d  k min/max=%d/%d" % (len(cyc), cyc.min(), cyc.mean(), cyc.max(), cyc.max() / 1965.0, (meta // 100000).max(), (meta % 100000).min(), (meta % 100000).max()))
+print("globaltimer (ns): first CTA start 0, last CTA start +%d, first CTA end +%d, last CTA end +%d" % (out[41] - out[40], out[42] - out[40], out[43] - out[40]))
