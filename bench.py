@@ -240,10 +240,18 @@ def main():
             if world > 1:
                 dist.all_gather_into_tensor(gathered, out)
 
+    def detect_call():
+        _lib.check(L.fdt_detect(loc.data_ptr(), conf.data_ptr(), pri.data_ptr(), B, N, C, TOP_K, NMS_TOP_K, CONF_T, NMS_T, 0.1, 0.2,
+                                out.data_ptr(), None, None, ws.data_ptr(), ws.numel(), st))
+
     def step():
-        # == fdt_detect (stage 1 then stage 2), split only so the dominant kernel gets its own event pair
-        stage1()
-        stage2_gather()
+        # N=1: the public C-ABI call (K2 + K3 with programmatic dependent launch, nothing in between).
+        # N>1: the same two kernels through the stage entry points so that K3 can store into the peers' blocks.
+        if world == 1:
+            detect_call()
+        else:
+            stage1()
+            stage2_gather()
 
     spin_cycles = 250_000
     for _ in range(max(args.warmup, 3)):
@@ -254,7 +262,7 @@ def main():
 
     sampler = ClockSampler(local)
     sampler.start()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -264,10 +272,8 @@ def main():
         flush.zero_()                                   # L2 flush, outside the event pairs
         torch.cuda._sleep(spin_cycles)                  # GPU spins ~0.1 ms so the host enqueues the whole step ahead of
         ev[i][0].record()                               # time: the event pairs then see device time, not launch latency
-        stage1()
+        step()
         ev[i][1].record()
-        stage2_gather()
-        ev[i][2].record()
     torch.cuda.synchronize()
     if sampler.ok:
         try:
@@ -279,8 +285,21 @@ def main():
         dist.barrier()
     wall = time.perf_counter() - wall0
     sampler.stop_flag.set()
-    step_ms = [e[0].elapsed_time(e[2]) for e in ev]
-    k3_ms = [e[1].elapsed_time(e[2]) for e in ev] if world == 1 else None
+    step_ms = [e[0].elapsed_time(e[1]) for e in ev]
+    k3_ms = None
+    if world == 1:
+        # dominant kernel alone: same launches through the stage entry points with an event pair around stage 2 only
+        k3_ms = []
+        for _ in range(max(10, min(args.steps, 30))):
+            flush.zero_()
+            torch.cuda._sleep(spin_cycles)
+            stage1()
+            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            stage2()
+            b2.record()
+            torch.cuda.synchronize()
+            k3_ms.append(a.elapsed_time(b2))
     total_ms = float(sum(step_ms))
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)

@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(K2_THREADS)
 k_threshold_compact(const float *__restrict__ conf, int64_t N, int C, float thr,
                     int32_t *__restrict__ counters, uint64_t *__restrict__ keys)
 {
+    // programmatic dependent launch: let k_sort_nms be scheduled while this grid drains (it waits for our completion itself)
+    cudaTriggerProgrammaticLaunchCompletion();
     const int b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t base = (int64_t)blockIdx.x * K2_TILE;
@@ -368,6 +370,7 @@ k_sort_nms(const SortNmsParams P)
     const int cl = (MODE == MODE_DETECT) ? 1 + list % (P.C - 1) : 0;
     const uint64_t *gkeys = P.keys + (int64_t)list * P.key_stride;
 
+    cudaGridDependencySynchronize();      // no-op unless launched with programmatic stream serialization (after K2)
     int n_c = (MODE == MODE_DETECT) ? P.counters[list] : (int)P.n;
     if (MODE == MODE_DETECT && n_c == 1) n_c = 0;            // detection.py:66-72: one candidate -> `continue`
     const int k = min(n_c, P.nms_top_k);                     // box_utils.py:299 idx[-top_k:]
@@ -912,18 +915,31 @@ int launch_sort_nms(SortNmsParams &P, int lists, int kcap, void *kept_ws, size_t
     // memory (large max_keep) stay on the single-CTA path.
     const char *env_cl = getenv("FDT_K3_CLUSTER");
     const bool want_cluster = env_cl ? env_cl[0] == '1' : true;
-    if (want_cluster && lists * 2 <= FDT_NUM_SMS && sp.off_kbox >= 0) {
+    const bool cluster = want_cluster && lists * 2 <= FDT_NUM_SMS && sp.off_kbox >= 0;
+    const char *env_pdl = getenv("FDT_K3_PDL");
+    const bool pdl = env_pdl ? env_pdl[0] == '1' : true;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(lists * (cluster ? 2 : 1))); cfg.blockDim = dim3(K3_THREADS);
+    cfg.dynamicSmemBytes = (size_t)sp.total; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cluster) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl) {      // overlap this kernel's launch latency with the tail of the producer (k_threshold_compact / k_build_keys)
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    if (cluster) {
         FDT_CUDA(cudaFuncSetAttribute(k_sort_nms<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(lists * 2)); cfg.blockDim = dim3(K3_THREADS); cfg.dynamicSmemBytes = (size_t)sp.total; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
         FDT_CUDA(cudaLaunchKernelEx(&cfg, k_sort_nms<MODE, 2>, P));
     } else {
         FDT_CUDA(cudaFuncSetAttribute(k_sort_nms<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
-        k_sort_nms<MODE, 1><<<lists, K3_THREADS, sp.total, st>>>(P);
+        FDT_CUDA(cudaLaunchKernelEx(&cfg, k_sort_nms<MODE, 1>, P));
     }
     FDT_LAUNCH_CHECK();
     return FDT_OK;

@@ -36,3 +36,16 @@ a, b, c = run(1), run(2), run(4)
 print(f"K3 x1 {a:.1f} us, x2 {b:.1f} us, x4 {c:.1f} us -> per launch {(c - a) / 3:.1f} us, fixed {a - (c - a) / 3:.1f} us")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda._sleep(400_000); e0.record(); e1.record(); torch.cuda.synchronize(); print("empty event pair", e0.elapsed_time(e1) * 1e3, "us")
+
+def run_full(reps=50):
+    ts = []
+    for _ in range(reps):
+        flush.zero_(); torch.cuda._sleep(400_000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(L.fdt_detect(loc.data_ptr(), conf.data_ptr(), pri.data_ptr(), B, N, C, 750, 5000, 0.05, 0.3, 0.1, 0.2,
+                                out.data_ptr(), None, None, ws.data_ptr(), ws.numel(), st))
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    return np.median(ts)
+print(f"fdt_detect (one call, no event between the stages): {run_full():.1f} us   [FDT_K3_PDL={os.environ.get('FDT_K3_PDL', 'default')}]")
