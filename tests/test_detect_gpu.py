@@ -242,6 +242,27 @@ def test_detect_three_classes(layers):
     assert_same(run_detect(layers, loc, conf, pri, args), oracle_detect(loc, conf, pri, args))
 
 
+def test_detect_stage_entry_points_and_candidate_counts(layers):
+    """stage 1 + stage 2 == fdt_detect; stage 1's candidate counts are exactly (score > conf_thresh).sum()."""
+    from fdt_b200 import _lib
+    pri = synth.priors_numpy(640, 480)
+    loc, conf = synth.detect_inputs(5, pri, 321, 0.05)
+    B, N, C = 5, pri.shape[0], 2
+    dev = torch.device("cuda", torch.cuda.current_device())
+    l, c, p = cu(loc), cu(conf), cu(pri)
+    L = _lib.lib()
+    ws = torch.empty(L.fdt_detect_workspace_bytes(B, N, C), dtype=torch.uint8, device=dev)
+    st = _lib.stream_ptr()
+    _lib.check(L.fdt_detect_threshold_compact(c.data_ptr(), B, N, C, 0.05, ws.data_ptr(), ws.numel(), st))
+    cnt = torch.empty(B, dtype=torch.int32, device=dev)
+    _lib.check(L.fdt_detect_candidate_counts(ws.data_ptr(), B, C, cnt.data_ptr(), st))
+    assert np.array_equal(npy(cnt), (conf[..., 1] > np.float32(0.05)).sum(1).astype(np.int32))
+    out = torch.empty((B, C, 750, 5), dtype=torch.float32, device=dev)
+    _lib.check(L.fdt_detect_sort_nms(l.data_ptr(), p.data_ptr(), B, N, C, 750, 5000, 0.3, 0.1, 0.2, out.data_ptr(), None, None,
+                                     ws.data_ptr(), ws.numel(), st))
+    assert np.array_equal(npy(out), oracle_detect(loc, conf, pri)[0])
+
+
 def test_detect_rejects_nonpositive_nms_thresh(layers):
     with pytest.raises(ValueError):
         layers.Detect(2, 0, 750, 0.05, 0)
