@@ -29,6 +29,10 @@ SIGNATURES = {
     "fdt_intersect": (_i, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "fdt_calculate_iou": (_i, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "fdt_calculate_iou_f64": (_i, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "fdt_intersect_f64": (_i, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "fdt_calculate_distance_f64": (_i, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "fdt_calc_pr": (_i, [_vp, _i64, _i, _vp, _i64, _d, _vp, _vp]),
+    "fdt_detections_to_rows": (_i, [_vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp]),
     "fdt_encode": (_i, [_vp, _vp, _i64, _f, _f, _vp, _vp]),
     "fdt_decode": (_i, [_vp, _vp, _i64, _f, _f, _vp, _vp]),
     "fdt_log_sum_exp": (_i, [_vp, _i64, _i, _vp, _vp, _sz, _vp]),

@@ -85,6 +85,74 @@ __global__ void k_pairwise(const T *__restrict__ a, int64_t A, const T *__restri
     }
 }
 
+// utils/calc_performance.py:34-51 calculate_distance (float64); `dis ** 0.25` is pow(dis, 0.25) like numpy
+__global__ void k_pairwise_distance_f64(const double *__restrict__ a, int64_t A, const double *__restrict__ b, int64_t B, double *__restrict__ out)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t i = blockIdx.y;
+    if (j >= B) return;
+    const double *p = a + 4 * i, *q = b + 4 * j;
+    const double adx = p[2] - p[0], ady = p[3] - p[1], bdx = q[2] - q[0], bdy = q[3] - q[1];
+    const double cax = (p[2] + p[0]) / 2, cay = (p[3] + p[1]) / 2, cbx = (q[2] + q[0]) / 2, cby = (q[3] + q[1]) / 2;
+    const double dx = cbx - cax, dy = cby - cay;
+    const double dz = ((adx - bdx) + (ady - bdy)) / 2;
+    const double dis = __dadd_rn(__dadd_rn(__dmul_rn(dz, dz), __dmul_rn(dx, dx)), __dmul_rn(dy, dy));      // no FMA, numpy operand order
+    out[i * B + j] = pow(dis, 0.25);
+}
+
+// utils/calc_performance.py:77-92 calc_pr: one thread per prediction, max IoU over the truth boxes (given as x, y, w, h)
+__global__ void k_calc_pr(const double *__restrict__ pred, int64_t P, int stride, const double *__restrict__ truth, int64_t T,
+                          double thr, int32_t *__restrict__ tf)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P) return;
+    const double *q = pred + stride * j;
+    double best = -INFINITY;
+    bool any_nan = false;
+    for (int64_t t = 0; t < T; ++t) {
+        const double x1 = truth[4 * t], y1 = truth[4 * t + 1], x2 = truth[4 * t + 2] + x1, y2 = truth[4 * t + 3] + y1;      // :88
+        double w = nmin(x2, q[2]) - nmax(x1, q[0]);
+        double h = nmin(y2, q[3]) - nmax(y1, q[1]);
+        w = nmax(w, 0.0); h = nmax(h, 0.0);
+        const double inter = w * h;
+        const double uni = (x2 - x1) * (y2 - y1) + (q[2] - q[0]) * (q[3] - q[1]) - inter;
+        const double v = inter / uni;
+        if (v != v) any_nan = true;                 // np.max propagates NaN, NaN > thr is False
+        else if (v > best) best = v;
+    }
+    tf[j] = (!any_nan && best > thr) ? 1 : 0;       // :91
+}
+
+// Detect's consumers (My_test.py:43-57, iouTracke_cal.py:55-68): per image and class, the leading rows with score >= thr
+// (the python `while` stops at the first row below thr), boxes scaled to pixels in fp32 (detections[...] * scale).
+// One block per image; rows_out[b][r] = [x1*w, y1*h, x2*w, y2*h, score] in class-major order, n_rows[b] = how many.
+__global__ void k_detections_to_rows(const float *__restrict__ det, int C, int top_k, float thr, float width, float height,
+                                     float *__restrict__ rows_out, int32_t *__restrict__ n_rows)
+{
+    __shared__ int s_len, s_base;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int i = 0; i < C; ++i) {
+        const float *plane = det + ((int64_t)(b * C + i) * top_k) * 5;
+        if (tid == 0) s_len = top_k;
+        __syncthreads();
+        for (int j = tid; j < top_k; j += blockDim.x)
+            if (!(plane[5 * j] >= thr)) atomicMin(&s_len, j);                 // first row that fails `>= thr` (NaN fails)
+        __syncthreads();
+        const int len = s_len, base = s_base;
+        for (int j = tid; j < len; j += blockDim.x) {
+            const float *r = plane + 5 * j;
+            float *o = rows_out + ((int64_t)b * C * top_k + base + j) * 5;
+            o[0] = r[1] * width; o[1] = r[2] * height; o[2] = r[3] * width; o[3] = r[4] * height; o[4] = r[0];
+        }
+        __syncthreads();
+        if (tid == 0) s_base = base + len;
+        __syncthreads();
+    }
+    if (tid == 0) n_rows[b] = s_base;
+}
+
 // box_utils.py:261-269: global max, then log(sum(exp(x - max))) + max per row
 __global__ void k_global_max(const float *__restrict__ x, int64_t n, unsigned *__restrict__ gmax_key)
 {
@@ -183,6 +251,41 @@ static int pairwise(const char *name, const T *a, int64_t A, const T *b, int64_t
 FDT_API int fdt_intersect(const float *a, int64_t A, const float *b, int64_t B, float *out, fdt_stream_t s) { return pairwise<float, false>("fdt_intersect", a, A, b, B, out, s); }
 FDT_API int fdt_calculate_iou(const float *a, int64_t A, const float *b, int64_t B, float *out, fdt_stream_t s) { return pairwise<float, true>("fdt_calculate_iou", a, A, b, B, out, s); }
 FDT_API int fdt_calculate_iou_f64(const double *a, int64_t A, const double *b, int64_t B, double *out, fdt_stream_t s) { return pairwise<double, true>("fdt_calculate_iou_f64", a, A, b, B, out, s); }
+
+FDT_API int fdt_intersect_f64(const double *a, int64_t A, const double *b, int64_t B, double *out, fdt_stream_t s) { return pairwise<double, false>("fdt_intersect_f64", a, A, b, B, out, s); }
+
+FDT_API int fdt_calculate_distance_f64(const double *a, int64_t A, const double *b, int64_t B, double *out, fdt_stream_t stream)
+{
+    FDT_REQUIRE(A >= 0 && B >= 0 && A < 65536, FDT_E_INVALID, "fdt_calculate_distance_f64: bad sizes");
+    if (A == 0 || B == 0) return FDT_OK;
+    FDT_REQUIRE(a && b && out, FDT_E_INVALID, "fdt_calculate_distance_f64: null pointer");
+    dim3 g(ew_blocks(B), (unsigned)A);
+    k_pairwise_distance_f64<<<g, EW_THREADS, 0, (cudaStream_t)stream>>>(a, A, b, B, out);
+    FDT_LAUNCH_CHECK();
+    return FDT_OK;
+}
+
+FDT_API int fdt_calc_pr(const double *predict, int64_t P, int predict_stride, const double *truth, int64_t T, double iou_thresh,
+                        int32_t *tf, fdt_stream_t stream)
+{
+    FDT_REQUIRE(P >= 0 && T >= 0 && predict_stride >= 4, FDT_E_INVALID, "fdt_calc_pr: bad sizes");
+    if (P == 0) return FDT_OK;
+    FDT_REQUIRE(predict && tf && (T == 0 || truth), FDT_E_INVALID, "fdt_calc_pr: null pointer");
+    k_calc_pr<<<ew_blocks(P), EW_THREADS, 0, (cudaStream_t)stream>>>(predict, P, predict_stride, truth, T, iou_thresh, tf);
+    FDT_LAUNCH_CHECK();
+    return FDT_OK;
+}
+
+FDT_API int fdt_detections_to_rows(const float *detections, int B, int C, int top_k, float thresh, float width, float height,
+                                   float *rows_out, int32_t *n_rows, fdt_stream_t stream)
+{
+    FDT_REQUIRE(B >= 0 && C >= 1 && top_k >= 1, FDT_E_INVALID, "fdt_detections_to_rows: bad sizes");
+    if (B == 0) return FDT_OK;
+    FDT_REQUIRE(detections && rows_out && n_rows, FDT_E_INVALID, "fdt_detections_to_rows: null pointer");
+    k_detections_to_rows<<<B, 256, 0, (cudaStream_t)stream>>>(detections, C, top_k, thresh, width, height, rows_out, n_rows);
+    FDT_LAUNCH_CHECK();
+    return FDT_OK;
+}
 
 FDT_API int fdt_log_sum_exp(const float *x, int64_t R, int C, float *out, void *ws, size_t ws_bytes, fdt_stream_t stream)
 {

@@ -64,6 +64,20 @@ int fdt_calculate_iou(const float *box_a, int64_t A, const float *box_b, int64_t
 /* ---- T1  utils.calc_performance.calculate_iou (utils/calc_performance.py:54-74), float64 -------- */
 int fdt_calculate_iou_f64(const double *box_a, int64_t A, const double *box_b, int64_t B, double *out, fdt_stream_t stream);
 
+/* ---- (Detect consumers)  utils.calc_performance.intersect / calculate_distance / calc_pr, float64 -----------------
+ * (utils/calc_performance.py:4-31, 34-51, 77-92).  calculate_distance ends in pow(x, 0.25): compared at 1e-14 relative.
+ * calc_pr: predict[P, predict_stride >= 4] rows [x1,y1,x2,y2,(score..)], truth[T,4] rows [x,y,w,h] -> tf[P] int32 =
+ * (max_t IoU > iou_thresh); NaN IoU makes the max NaN and the comparison false, as numpy does. */
+int fdt_intersect_f64(const double *box_a, int64_t A, const double *box_b, int64_t B, double *out, fdt_stream_t stream);
+int fdt_calculate_distance_f64(const double *box_a, int64_t A, const double *box_b, int64_t B, double *out, fdt_stream_t stream);
+int fdt_calc_pr(const double *predict, int64_t P, int predict_stride, const double *truth, int64_t T, double iou_thresh,
+                int32_t *tf, fdt_stream_t stream);
+
+/* Detect's row read-out (My_test.py:43-57, iouTracke_cal.py:55-68): for every image, and class by class, the leading rows of
+ * detections[B,C,top_k,5] with score >= thresh, scaled to pixels -> rows_out[B, C*top_k, 5] = [x1,y1,x2,y2,score], n_rows[B]. */
+int fdt_detections_to_rows(const float *detections, int B, int C, int top_k, float thresh, float width, float height,
+                           float *rows_out, int32_t *n_rows, fdt_stream_t stream);
+
 /* ---- M6 / D1  encode / decode  (layers/box_utils.py:213-234, 238-258) --------------------------- */
 int fdt_encode(const float *matched, const float *priors, int64_t n, float var0, float var1, float *out, fdt_stream_t stream);
 int fdt_decode(const float *loc, const float *priors, int64_t n, float var0, float var1, float *out, fdt_stream_t stream);

@@ -465,6 +465,51 @@ ORC_API void orc_calculate_iou_f64(const double *a, int64_t A, const double *b, 
         for (int64_t j = 0; j < B; ++j) out[i * B + j] = iou1_f64(a + 4 * i, b + 4 * j);
 }
 
+/* utils.calc_performance.intersect (utils/calc_performance.py:4-31), float64 */
+ORC_API void orc_intersect_f64(const double *a, int64_t A, const double *b, int64_t B, double *out)
+{
+    for (int64_t i = 0; i < A; ++i)
+        for (int64_t j = 0; j < B; ++j) {
+            const double *p = a + 4 * i, *q = b + 4 * j;
+            double w = d_max(d_min(p[2], q[2]) - d_max(p[0], q[0]), 0.0);
+            double h = d_max(d_min(p[3], q[3]) - d_max(p[1], q[1]), 0.0);
+            out[i * B + j] = w * h;
+        }
+}
+
+/* utils.calc_performance.calculate_distance (utils/calc_performance.py:34-51), float64; `dis ** 0.25` is libm pow */
+ORC_API void orc_calculate_distance_f64(const double *a, int64_t A, const double *b, int64_t B, double *out)
+{
+    for (int64_t i = 0; i < A; ++i)
+        for (int64_t j = 0; j < B; ++j) {
+            const double *p = a + 4 * i, *q = b + 4 * j;
+            double adx = p[2] - p[0], ady = p[3] - p[1], bdx = q[2] - q[0], bdy = q[3] - q[1];      /* :41-42 */
+            double cax = (p[2] + p[0]) / 2, cay = (p[3] + p[1]) / 2, cbx = (q[2] + q[0]) / 2, cby = (q[3] + q[1]) / 2;
+            double dx = cbx - cax, dy = cby - cay;                                                    /* :45 */
+            double dz = ((adx - bdx) + (ady - bdy)) / 2;                                              /* :46-47 */
+            double dis = dz * dz + dx * dx + dy * dy;                                                 /* :48 */
+            out[i * B + j] = pow(dis, 0.25);                                                          /* :49 */
+        }
+}
+
+/* utils.calc_performance.calc_pr (utils/calc_performance.py:77-92): truth rows [x, y, w, h] -> tf[P] = max_t IoU > thresh
+ * (np.max propagates NaN, NaN > thresh is False).  Returns truth_num. */
+ORC_API int64_t orc_calc_pr(const double *predict, int64_t P, int predict_stride, const double *truth, int64_t T,
+                            double iou_thresh, int32_t *tf)
+{
+    for (int64_t j = 0; j < P; ++j) {
+        double best = -INFINITY; int any_nan = 0;
+        for (int64_t t = 0; t < T; ++t) {
+            double tb[4] = {truth[4 * t], truth[4 * t + 1], truth[4 * t + 2] + truth[4 * t], truth[4 * t + 3] + truth[4 * t + 1]};   /* :88 */
+            double v = iou1_f64(tb, predict + predict_stride * j);
+            if (v != v) any_nan = 1;
+            else if (v > best) best = v;
+        }
+        tf[j] = (!any_nan && best > iou_thresh) ? 1 : 0;                                              /* :91 */
+    }
+    return T;
+}
+
 /* ------------------------------------------------------------------------------------------
  * IoU tracker loop (iouTracke_cal.py:126-155 per frame, :174-176 flush), use_iou = True.
  * dets[total,5] float64 rows [x1,y1,x2,y2,score]; frame_off[F+1]; frame numbers are 1-based (:118).

@@ -33,6 +33,7 @@ torch.set_num_threads(8)
 from layers import Detect, PriorBoxLayer, MultiBoxLoss                    # noqa: E402  (reference)
 from layers import box_utils as ref_bu                                    # noqa: E402  (reference)
 from utils.calc_performance import calculate_iou as ref_iou_np            # noqa: E402  (reference)
+from utils import calc_performance as ref_cp                              # noqa: E402  (reference)
 
 from fdt_b200 import synth                                                # noqa: E402
 
@@ -90,6 +91,15 @@ def gen_boxutils():
     a64 = rng.uniform(0, 600, (50, 2)); a64 = np.concatenate([a64, a64 + rng.uniform(5, 80, (50, 2))], 1)
     b64 = rng.uniform(0, 600, (40, 2)); b64 = np.concatenate([b64, b64 + rng.uniform(5, 80, (40, 2))], 1)
     iou64 = ref_iou_np(a64, b64)
+    inter64 = ref_cp.intersect(a64, b64)
+    dist64 = ref_cp.calculate_distance(a64, b64)
+    # calc_pr: predictions [x1,y1,x2,y2,score], truth [x,y,w,h] (My_test.py:163)
+    truth_xywh = np.concatenate([b64[:12, :2], b64[:12, 2:] - b64[:12, :2]], 1)
+    pred = np.concatenate([b64[:12] + rng.normal(0, 4, (12, 4)), rng.uniform(0.3, 1, (12, 1))], 1)
+    pred = np.concatenate([pred, np.concatenate([a64[:9], rng.uniform(0.3, 1, (9, 1))], 1)], 0)
+    pr, tnum = ref_cp.calc_pr(pred, truth_xywh)
+    np.savez_compressed(os.path.join(OUT, "calcperf.npz"), a64=a64, b64=b64, inter64=inter64, dist64=dist64, truth=truth_xywh,
+                        pred=pred, pr=pr, truth_num=np.int64(tnum))
     save("boxutils", priors=pri, loc=loc, decode=dec, gt=gt, encode=enc, point_form=pf, center_size=cs,
          a=a, intersect=inter, iou=iou, x=x, lse=lse, a64=a64, b64=b64, iou64=iou64)
 

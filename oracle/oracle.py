@@ -209,6 +209,27 @@ def calculate_iou_f64(box_a, box_b):
     lib().orc_calculate_iou_f64(_p(a), C.c_int64(a.shape[0]), _p(b), C.c_int64(b.shape[0]), _p(out)); return out
 
 
+def intersect_f64(box_a, box_b):
+    a = np.ascontiguousarray(box_a, dtype=np.float64); b = np.ascontiguousarray(box_b, dtype=np.float64)
+    out = np.empty((a.shape[0], b.shape[0]), np.float64)
+    lib().orc_intersect_f64(_p(a), C.c_int64(a.shape[0]), _p(b), C.c_int64(b.shape[0]), _p(out)); return out
+
+
+def calculate_distance_f64(box_a, box_b):
+    a = np.ascontiguousarray(box_a, dtype=np.float64); b = np.ascontiguousarray(box_b, dtype=np.float64)
+    out = np.empty((a.shape[0], b.shape[0]), np.float64)
+    lib().orc_calculate_distance_f64(_p(a), C.c_int64(a.shape[0]), _p(b), C.c_int64(b.shape[0]), _p(out)); return out
+
+
+def calc_pr(predict, truth, iou_thresh=0.5):
+    """-> (ndarray [2, P] = [tf; score], truth_num)   (calc_performance.py:77-92)"""
+    p = np.ascontiguousarray(predict, dtype=np.float64); t = np.ascontiguousarray(truth, dtype=np.float64)
+    tf = np.zeros(p.shape[0], np.int32)
+    lib().orc_calc_pr.restype = C.c_int64
+    n = lib().orc_calc_pr(_p(p), C.c_int64(p.shape[0]), C.c_int(p.shape[1]), _p(t), C.c_int64(t.shape[0]), C.c_double(iou_thresh), _p(tf))
+    return np.vstack((tf, p[:, 4])), int(n)
+
+
 # ---------------------------------------------------------------- tracker (iouTracke_cal.py:126-155,174-176)
 def iou_track_raw(frames, sigma_iou=0.4, sigma_h=0.6, t_min=5):
     """frames: list of [D_f,5] arrays.  -> (dets[total,5] f64, track_off, track_dets, track_start, track_max)"""

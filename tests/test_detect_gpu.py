@@ -360,3 +360,23 @@ def test_detect_mixed_pyramid_levels_and_scores(layers):
     conf = np.stack([1 - s1, s1], -1).astype(np.float32)
     for args in ((2, 0, 750, 0.05, 0.3), (2, 0, 750, 0.5, 0.7), (2, 0, 300, 0.05, 0.05)):
         assert_same(run_detect(layers, loc, conf, pri, args), oracle_detect(loc, conf, pri, args))
+
+
+def test_detections_to_rows_consumer(layers, golden):
+    """Detect's consumer loop (My_test.py:43-57): leading rows with score >= thr, fp32 scaling to pixels, per class."""
+    from fdt_b200.utils.readout import detections_to_rows
+    g = golden("detect")
+    out = g["small_out"].copy()                         # [4, 2, 750, 5], images 1 and 2 empty
+    out[0, 1, 5, 0] = 0.1                               # a row below the threshold stops the loop: later rows are not read
+    for thr, w, h in ((0.3, 640.0, 480.0), (0.0, 640.0, 640.0), (0.9, 100.0, 50.0)):
+        got = detections_to_rows(cu(out), thr, w, h, dummy_if_empty=True)
+        scale = np.array([w, h, w, h], np.float32)
+        for b in range(out.shape[0]):
+            rows = []
+            for i in range(out.shape[1]):
+                j = 0
+                while j < out.shape[2] and out[b, i, j, 0] >= np.float32(thr):      # verbatim loop of the reference
+                    rows.append(np.concatenate([out[b, i, j, 1:] * scale, out[b, i, j, :1]]))
+                    j += 1
+            ref = np.array(rows, np.float32).reshape(-1, 5) if rows else np.array([[0, 0, 0, 0, 0.4]])
+            assert got[b].dtype == ref.dtype and np.array_equal(got[b], ref)

@@ -175,3 +175,12 @@ def test_tracker_bit_exact(golden, tag):
     assert np.array_equal(np.array([t["max_score"] for t in tr]), g[f"{tag}_max"])
     bb = np.array([b for t in tr for b in t["bboxes"]], np.float64).reshape(-1, 4)
     assert np.array_equal(bb, g[f"{tag}_bboxes"])
+
+
+def test_calc_performance_functions(golden):
+    g = golden("calcperf")
+    assert np.array_equal(orc.intersect_f64(g["a64"], g["b64"]), g["inter64"])
+    np.testing.assert_allclose(orc.calculate_distance_f64(g["a64"], g["b64"]), g["dist64"], rtol=1e-14)
+    pr, tnum = orc.calc_pr(g["pred"], g["truth"])
+    assert tnum == int(g["truth_num"]) and np.array_equal(pr, g["pr"])
+    assert pr[0].sum() >= 10                                   # the fixture really has matches and misses

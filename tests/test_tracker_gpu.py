@@ -77,3 +77,14 @@ def test_calc_performance_iou_f64(golden):
     assert out.dtype == np.float64 and np.array_equal(out, g["iou64"])
     track_box = np.array([g["b64"][3]])
     assert np.array_equal(calculate_iou(g["a64"], track_box), g["iou64"][:, 3:4])          # the tracker's [D,1] call shape
+
+
+def test_calc_performance_intersect_distance_calc_pr(golden):
+    from fdt_b200.utils import calc_performance as cp
+    g = golden("calcperf")
+    assert np.array_equal(cp.intersect(g["a64"], g["b64"]), g["inter64"])
+    np.testing.assert_allclose(cp.calculate_distance(g["a64"], g["b64"]), g["dist64"], rtol=1e-14)
+    pr, tnum = cp.calc_pr(g["pred"], g["truth"])
+    assert tnum == int(g["truth_num"]) and np.array_equal(pr, g["pr"])
+    pred = g["pred"].copy(); pred[3, 0] = np.nan                # NaN IoU -> max is NaN -> not matched (numpy semantics)
+    assert np.array_equal(cp.calc_pr(pred, g["truth"])[0], orc.calc_pr(pred, g["truth"])[0])
