@@ -42,7 +42,14 @@ __device__ __forceinline__ float iou_match(const float4 a, const float area_a, c
     w = fmaxf(w, 0.0f); h = fmaxf(h, 0.0f);
     float inter = w * h;
     float uni = area_a + area_b - inter;               // box_utils.py:98
-    if (inter > 0.0f || !(uni > 0.0f)) return inter / uni;
+    // inter / uni, IEEE -- but only where it matters.  Most pairs do not overlap; the compiler would otherwise evaluate the
+    // division speculatively for every pair (and 0 / x takes the slow-path subroutine: FCHK rejects a zero numerator).  The
+    // volatile asm pins it inside the branch.
+    if (inter > 0.0f || !(uni > 0.0f)) {               // overlapping, or 0/0, 0/negative, NaN: exactly what the reference computes
+        float q;
+        asm volatile("div.rn.f32 %0, %1, %2;" : "=f"(q) : "f"(inter), "f"(uni));
+        return q;
+    }
     return 0.0f;                                       // 0 / positive
 }
 
