@@ -24,6 +24,7 @@
 namespace {
 
 constexpr int TR_THREADS = 1024;
+constexpr int OFF_CHUNK = 512;
 constexpr int TR_MAX_D = 1024;             // one thread per track / detection; shared memory caps this near 800
                                            // (Detect emits at most top_k = 750 detections per frame)
 
@@ -49,7 +50,13 @@ __global__ void k_track_frame_of(const int64_t *__restrict__ frame_off, int64_t 
     for (int64_t g = frame_off[f] + threadIdx.x; g < frame_off[f + 1]; g += blockDim.x) frame_of[g] = (int32_t)f;
 }
 
-// one warp per detection g of frame f (f < F-1): bits over the detections of frame f+1
+// Row layout (uint32 words) per previous-frame detection: [0, W) bits "IoU > sigma_iou" over the next frame's detections,
+// [W] NaN flag, [W+1], [W+2] the 4 best candidates as uint16 (best first: IoU descending, lower index first on ties = numpy's
+// argmax order; 0xffff = none), [W+3] number of candidates.  The ranking is done here, for all frame pairs in parallel, so the
+// serial resolve kernel normally never evaluates an IoU.
+constexpr int ROW_EXTRA = 4;
+
+// one warp per detection g of frame f (f < F-1)
 __global__ void __launch_bounds__(256)
 k_track_mask(const double *__restrict__ dets, const int64_t *__restrict__ frame_off, const int32_t *__restrict__ frame_of,
              int64_t F, int64_t total, int W, double sigma_iou, uint32_t *__restrict__ mask)
@@ -59,28 +66,73 @@ k_track_mask(const double *__restrict__ dets, const int64_t *__restrict__ frame_
     if (g >= total) return;
     const int64_t f = frame_of[g];
     if (f + 1 >= F) return;
+    const int WR = W + ROW_EXTRA;
     const int64_t n0 = frame_off[f + 1];
     const int D = (int)(frame_off[f + 2] - n0);
     double tb[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) tb[k] = dets[5 * g + k];
     bool any_nan = false;
+    int count = 0;
+    double cv[4] = {0.0, 0.0, 0.0, 0.0};        // lane-local best candidates (IoU descending, index ascending)
+    int cj[4] = {-1, -1, -1, -1};
+    int nc = 0;
     for (int c = 0; c * 32 < D && c < W; ++c) {
         const int j = c * 32 + lane;
         bool over = false, isn = false;
+        double v = 0.0;
         if (j < D) {
             double db[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) db[k] = dets[5 * (n0 + j) + k];
-            const double v = iou_f64(db, tb);
+            v = iou_f64(db, tb);
             over = v > sigma_iou;                                  // iouTracke_cal.py:134
             isn = v != v;
         }
         const unsigned bits = __ballot_sync(0xffffffffu, over);
         any_nan |= __any_sync(0xffffffffu, isn);
-        if (lane == 0) mask[g * (W + 1) + c] = bits;
+        count += __popc(bits);
+        if (lane == 0) mask[g * WR + c] = bits;
+        if (over) {
+            int p = nc < 4 ? nc : 4;
+#pragma unroll
+            for (int q = 3; q >= 0; --q) if (q < nc && cv[q] < v) p = q;
+#pragma unroll
+            for (int q = 3; q >= 1; --q) if (q > p) { cv[q] = cv[q - 1]; cj[q] = cj[q - 1]; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (q == p) { cv[q] = v; cj[q] = j; }
+            if (nc < 4) ++nc;
+        }
     }
-    if (lane == 0) mask[g * (W + 1) + W] = any_nan ? 1u : 0u;        // row word W: some IoU of this row is NaN
+    // the warp's 4 best: four rounds of "every lane offers its head, the best one is taken"
+    unsigned packed[2] = {0xffffffffu, 0xffffffffu};
+    if (count > 0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            double bv = nc > 0 ? cv[0] : -1.0;                     // IoU > sigma >= ... candidates are positive; -1 = nothing to offer
+            int bj = nc > 0 ? cj[0] : INT_MAX;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+            }
+            if (bj != INT_MAX) {
+                if (nc > 0 && cj[0] == bj) {                       // this lane's head was taken: pop it
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { cv[q] = cv[q + 1]; cj[q] = cj[q + 1]; }
+                    --nc;
+                }
+                packed[r >> 1] = (packed[r >> 1] & ~(0xffffu << (16 * (r & 1)))) | ((unsigned)bj << (16 * (r & 1)));
+            }
+        }
+    }
+    if (lane == 0) {
+        mask[g * WR + W] = any_nan ? 1u : 0u;
+        mask[g * WR + W + 1] = packed[0];
+        mask[g * WR + W + 2] = packed[1];
+        mask[g * WR + W + 3] = (unsigned)count;
+    }
 }
 
 // exclusive scan of one int per thread over the block; returns (exclusive prefix, total)
@@ -107,7 +159,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total)
 
 struct ResolveParams {
     const double *dets; const int64_t *frame_off; int64_t F; int W; int cap;   // cap = W * 32 >= max detections per frame
-    const uint32_t *mask;                        // [total][W + 1]: W words of "IoU > sigma" bits + 1 word NaN flag
+    const uint32_t *mask;                        // [total][W + ROW_EXTRA], see k_track_mask
     double sigma_iou, sigma_h; int64_t t_min;
     int32_t *det_head, *det_pos, *fin_id;        // [total]
     int64_t *n_tracks, *track_off, *track_start; double *track_max;
@@ -132,7 +184,7 @@ k_track_resolve(const ResolveParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     // layout: rows[NR][cap*(W+1)] u32 | boxes[NBX][cap*5] f64 | maxs[2][cap] f64 | int arrays   (NR, NBX = 2, 3 with prefetch; 1, 2 without)
-    const int W = P.W, W1 = P.W + 1, CAP = P.cap;
+    const int W = P.W, W1 = P.W + ROW_EXTRA, CAP = P.cap;      // W1 = words per row
     const int PF = P.prefetch, NR = PF ? 2 : 1, NBX = PF ? 3 : 2;
     uint32_t *rowbuf = reinterpret_cast<uint32_t *>(smem);
     double *boxbuf = reinterpret_cast<double *>(smem + ((size_t)NR * CAP * W1 * 4 + 15) / 16 * 16);
@@ -145,8 +197,17 @@ k_track_resolve(const ResolveParams P)
     __shared__ int s_warp[33];
     __shared__ long long s_warp64[33];
     __shared__ int s_slow[4];
+    __shared__ int64_t s_off[OFF_CHUNK + 3];       // frame_off[c0 .. c0 + OFF_CHUNK + 2]: no global-latency chain at the top of a frame
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x;   // NT = cap: one thread per track / detection
+    int64_t off_c0 = 0;
+    auto load_offsets = [&](int64_t c0) {
+        off_c0 = c0;
+        for (int i = tid; i < OFF_CHUNK + 3; i += NT) s_off[i] = P.frame_off[min(c0 + i, P.F)];
+        __syncthreads();
+    };
+    auto foff = [&](int64_t fr) -> int64_t { return s_off[fr - off_c0]; };
+    load_offsets(0);
     int cur = 0;                       // parity of the frame being processed (rows / per-det state double buffers)
     int T = 0;                         // active tracks = |order[prev]|
     int64_t n_fin = 0, fin_rows = 0;   // finished tracks so far, and their total length (uniform across threads)
@@ -154,14 +215,14 @@ k_track_resolve(const ResolveParams P)
     // async staging: boxes of frame fr -> boxbuf[fr % NBX]; candidate rows of the detections of frame g (they belong to the
     // tracks that are active while frame g+1 is resolved) -> rowbuf[PF ? g & 1 : 0]
     auto stage_boxes = [&](int64_t fr) {
-        const int64_t a0 = P.frame_off[fr];
-        const int Dn = min((int)(P.frame_off[fr + 1] - a0), CAP);
+        const int64_t a0 = foff(fr);
+        const int Dn = min((int)(foff(fr + 1) - a0), CAP);
         double *bdst = boxbuf + (fr % NBX) * CAP * 5;
         for (int i = tid; i < Dn * 5; i += NT) cp_async8(bdst + i, P.dets + 5 * a0 + i);
     };
     auto stage_rows = [&](int64_t g) {
-        const int64_t a0 = P.frame_off[g];
-        const int Dn = min((int)(P.frame_off[g + 1] - a0), CAP);
+        const int64_t a0 = foff(g);
+        const int Dn = min((int)(foff(g + 1) - a0), CAP);
         uint32_t *rdst = rowbuf + (PF ? (g & 1) : 0) * CAP * W1;
         for (int i = tid; i < Dn * W1; i += NT) cp_async4(rdst + i, P.mask + a0 * W1 + i);
     };
@@ -189,8 +250,9 @@ k_track_resolve(const ResolveParams P)
 
     for (int64_t f = 0; f < P.F; ++f, cur ^= 1) {
         const int prv = cur ^ 1;
-        const int64_t g0 = P.frame_off[f];
-        const int D = min((int)(P.frame_off[f + 1] - g0), CAP);      // host guarantees D <= cap; clamp keeps memory safe
+        if (f - off_c0 >= OFF_CHUNK) load_offsets(f - 1);            // keeps f-1 .. f+2 addressable (stage_rows(f-1) without prefetch)
+        const int64_t g0 = foff(f);
+        const int D = min((int)(foff(f + 1) - g0), CAP);            // host guarantees D <= cap; clamp keeps memory safe
         double *box = boxbuf + (f % NBX) * CAP * 5, *pbox = boxbuf + ((f + NBX - 1) % NBX) * CAP * 5;
         uint32_t *rows = rowbuf + (PF ? prv : 0) * CAP * W1;          // rows of frame f-1's detections = of the active tracks
         double *maxs = maxbuf + cur * CAP, *pmaxs = maxbuf + prv * CAP;
@@ -221,6 +283,10 @@ k_track_resolve(const ResolveParams P)
             int nc = 0;
             auto rank_candidates = [&]() {
                 nc = 0;
+                int nbits = 0, only = -1;
+                for (int c = 0; c < Wd; ++c) { const uint32_t bits = row[c]; if (bits) { nbits += __popc(bits); only = c * 32 + __ffs(bits) - 1; } }
+                if (nbits == 1) { cj[0] = only; nc = 1; return; }        // a single detection above sigma_iou: nothing to rank
+                if (nbits == 0) return;
                 for (int c = 0; c < Wd; ++c) {
                     uint32_t bits = row[c];
                     while (bits) {
@@ -239,7 +305,11 @@ k_track_resolve(const ResolveParams P)
                 }
             };
             const bool active = tid < T && D > 0;
-            if (active) rank_candidates();
+            if (active) {                          // preference list precomputed by k_track_mask
+                const uint32_t p0 = row[W + 1], p1 = row[W + 2];
+                cj[0] = (int)(p0 & 0xffffu); cj[1] = (int)(p0 >> 16); cj[2] = (int)(p1 & 0xffffu); cj[3] = (int)(p1 >> 16);
+                nc = (int)row[W + 3];
+            }
             int ptr = 0, prop = -1;
             for (;;) {
                 prop = -1;
@@ -394,7 +464,7 @@ TrackWs plan_track_ws(void *ws, int64_t total, int W)
     char *p = (char *)ws;
     size_t o = 0;
     const size_t n = (size_t)(total > 0 ? total : 1);
-    t.mask = (uint32_t *)(p + o); o += fdt_align256(n * (W + 1) * 4);
+    t.mask = (uint32_t *)(p + o); o += fdt_align256(n * (W + ROW_EXTRA) * 4);
     t.frame_of = (int32_t *)(p + o); o += fdt_align256(n * 4);
     t.det_head = (int32_t *)(p + o); o += fdt_align256(n * 4);
     t.det_pos = (int32_t *)(p + o); o += fdt_align256(n * 4);
@@ -406,7 +476,7 @@ TrackWs plan_track_ws(void *ws, int64_t total, int W)
 size_t resolve_smem(int W, int prefetch)
 {
     const size_t cap = (size_t)W * 32;
-    size_t s = ((prefetch ? 2 : 1) * cap * (W + 1) * 4 + 15) / 16 * 16;
+    size_t s = ((prefetch ? 2 : 1) * cap * (W + ROW_EXTRA) * 4 + 15) / 16 * 16;
     s += sizeof(double) * ((prefetch ? 3 : 2) * cap * 5 + 2 * cap);
     s += sizeof(int32_t) * 10 * cap;
     return s;
