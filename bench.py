@@ -317,7 +317,10 @@ def main():
         step_bytes = B * (24 * N + C * TOP_K * 5 * 4) + 16 * N         # 849,000 B/image + priors
         roofline = {"bound": "hbm", "kernel": "k_sort_nms (select/sort + decode + lazy NMS + output rows)",
                     "achieved": k3_bytes / (k3 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": k3_bytes / (k3 * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": k3_bytes / (k3 * 1e-3) / 1e9 / peak,
+                    "traffic": 12.54e6,      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full of this config
+                    "traffic_source": "profiles/r01_sortnms_v5_cluster_sass_regions.csv (12.54 MB read, 768 B written)",
+                    "peak_source": peak_src,
                     "kernel_ms": k3, "kernel_share_of_step": k3 / ms_per_step,
                     "algorithmic_bytes_per_launch": k3_bytes,
                     "step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,

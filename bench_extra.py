@@ -141,6 +141,26 @@ def detect1024():
                       "candidates_per_image": float((conf[..., 1] > 0.05).sum(1).mean())}))
 
 
+def detect512():
+    """BASELINE config 5 on ONE GPU: B=512 @1024x1024 (N=87,360).  Inputs are generated on the device (1.07 GB)."""
+    from fdt_b200.layers import Detect
+    B = 512
+    pri = synth.priors_numpy(1024, 1024); N = pri.shape[0]
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    loc = torch.randn((B, N, 4), device="cuda", generator=g) * 0.5
+    d = torch.randn((B, N), device="cuda", generator=g) * 2.0 - 4.5
+    s1 = torch.sigmoid(d)
+    conf = torch.stack([1 - s1, s1], -1).contiguous()
+    det = Detect(2, 0, 750, 0.05, 0.3)
+    p = torch.from_numpy(pri).cuda()
+    ms, ms_min = timed(lambda: det(loc, conf, p), reps=10)
+    alg = B * (24 * N + 30000) + 16 * N
+    print(json.dumps({"workload": "Detect B=512 @1024x1024 (N=87,360) on one GPU (config 5 unsharded; device-generated inputs, scores may tie)",
+                      "ms": ms, "ms_min": ms_min, "frames_per_s": B / (ms * 1e-3), "algorithmic_bytes": alg,
+                      "roofline_frac_of_measured_hbm": alg / (ms * 1e-3) / 1e9 / PEAK,
+                      "candidates_per_image": float((conf[..., 1] > 0.05).sum(1).float().mean())}))
+
+
 def priorbox():
     from fdt_b200.layers import PriorBoxLayer
     layer = PriorBoxLayer(640, 640)

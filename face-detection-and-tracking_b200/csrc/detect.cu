@@ -1,20 +1,23 @@
 // Detect (layers/functions/detection.py:34-84) and nms (layers/box_utils.py:275-340) for sm_100a.
 //
-// Two launches per call, no host synchronisation:
-//   K2  k_threshold_compact : streams conf once (HBM-bound), strict `score > conf_thresh`, warp-ballot +
-//                             block-aggregated compaction into 64-bit keys (score_key << 32 | prior).
-//   K3  k_sort_nms          : one CTA per (image, class) list.  Radix-select of the top nms_top_k keys when
-//                             the list exceeds the shared-memory sort capacity, bitonic sort in shared
-//                             memory, decode of the selected priors only (loc/priors gathered through L2),
-//                             then greedy NMS evaluated LAZILY in chunks of 64 sorted candidates:
-//                               phase A: chunk x kept-so-far IoU tests (16 threads per candidate),
-//                               phase B: 64x64 intra-chunk suppression bitmask (warp ballots, boxes staged
-//                                        in shared memory) + warp-serial mask reduction,
-//                             stopping as soon as top_k boxes are kept (Detect reads only keep[:top_k],
-//                             detection.py:80-81, so the output is identical to running to completion).
+// Two launches per call (+ a 256-byte memset), no host synchronisation, CUDA-graph capturable:
+//   K2  k_threshold_compact : streams conf once (HBM-bound), strict `score > conf_thresh`, warp-ballot + block-aggregated
+//                             compaction into unordered 64-bit keys (score_key << 32 | prior).
+//   K3  k_sort_nms          : one 1024-thread CTA -- or a 2-CTA thread-block cluster when the batch leaves SMs idle -- per
+//                             (image, class) list, launched with programmatic stream serialization behind K2:
+//         stage 1  top-nms_top_k selection by a bucket (counting) sort of the keys in shared memory
+//                  (exact radix-select / bitonic fallbacks for degenerate score distributions);
+//         stage 2  lazy greedy NMS over windows of <= 1024 sorted candidates: exact in-bucket order, decode of exactly those
+//                  rows, a multi-level uniform grid (CSR) over the window, then
+//                    A  drop candidates suppressed by boxes kept in earlier windows,
+//                    B  collect, per survivor, the earlier survivors that suppress it (each pair examined once),
+//                    C  resolve by parallel sweeps (dead iff a suppressor is kept, kept iff all are dead),
+//                  stopping as soon as top_k boxes are kept (Detect reads only keep[:top_k], detection.py:80-81, so the
+//                  output equals the reference's run-to-completion loop);
+//         stage 3  output rows -- locally, or straight into every rank's gathered block over NVLink peer memory.
 //
-// Tie rule (unspecified in the reference, torch.sort is unstable): keys are unique, descending key order =
-// descending score, higher prior index first among equal scores.
+// Tie rule (unspecified in the reference, torch.sort is unstable): keys are unique, descending key order = descending score,
+// higher prior index first among equal scores.  DESIGN.md section 4 has the exactness arguments.
 #include <cstdlib>
 #include <cooperative_groups.h>
 #include "fdt_common.cuh"

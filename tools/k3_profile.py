@@ -1,8 +1,10 @@
-"""Diagnostics: per-phase cycle breakdown of k_sort_nms (CTA 0) on the headline workload.  FDT_K3_PROFILE=1 python tools_k3_profile.py [mode]"""
+"""Diagnostics: per-phase cycle breakdown of k_sort_nms (CTA 0) on the headline workload.  FDT_K3_PROFILE=1 python tools/k3_profile.py [mode] [batch]"""
 import ctypes as C
 import os
 import sys
 os.environ["FDT_K3_PROFILE"] = "1"
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import fdt_b200
 from fdt_b200 import _lib, synth

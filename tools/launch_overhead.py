@@ -1,5 +1,7 @@
 """Diagnostics: how much of k_sort_nms's event-measured time is launch overhead?  Times 1x and 2x back-to-back launches."""
 import sys, os
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import fdt_b200
 from fdt_b200 import _lib, synth
