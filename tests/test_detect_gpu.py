@@ -380,3 +380,30 @@ def test_detections_to_rows_consumer(layers, golden):
                     j += 1
             ref = np.array(rows, np.float32).reshape(-1, 5) if rows else np.array([[0, 0, 0, 0, 0.4]])
             assert got[b].dtype == ref.dtype and np.array_equal(got[b], ref)
+
+
+def test_detect_cuda_graph_capture_and_side_stream(layers):
+    """fdt_detect is asynchronous on the caller's stream, allocation-free and CUDA-graph capturable."""
+    pri = synth.priors_numpy(640, 640)
+    loc, conf = synth.detect_inputs(8, pri, 2024, 0.05)
+    l, c, p = cu(loc), cu(conf), cu(pri)
+    det = layers.Detect(2, 0, 750, 0.05, 0.3)
+    ref = oracle_detect(loc, conf, pri)[0]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            out = det(l, c, p)                      # warm-up on the side stream (workspace allocation happens here)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            out = det(l, c, p)
+    torch.cuda.synchronize()
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(npy(out), ref)
+    c2 = c.clone(); c2[:, :, 1] = 0.0                # new inputs in place: the replay must see them
+    c.copy_(c2)
+    g.replay()
+    torch.cuda.synchronize()
+    assert not npy(out).any()
