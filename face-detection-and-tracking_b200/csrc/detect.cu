@@ -40,15 +40,28 @@ constexpr int BIGCELL = NCELLS;                 // pseudo-cell: boxes the grid c
 constexpr int NCELLX = NCELLS + 1;
 constexpr int DEPS = 8;                         // stored earlier-suppressors per survivor (more -> re-query path)
 constexpr int KEPT_ROW_BYTES = 28;              // box 16 + key 8 + area 4
+constexpr int SEG_SLOTS = 8;                    // phase B: row segments a lane can queue (more -> visited in place)
 
 enum { MODE_DETECT = 0, MODE_NMS = 1 };
 
 // ------------------------------------------------------------------------------------------- K2
+// Clears the per-list counters.  A kernel rather than cudaMemsetAsync so that k_threshold_compact can be launched behind it
+// with programmatic stream serialization: its blocks start and stream `conf` while this grid is still in flight (a memset
+// node costs ~3.5 us of serialised front-end latency per call).
+__global__ void k_zero_counters(int32_t *__restrict__ counters, int n)
+{
+    cudaTriggerProgrammaticLaunchCompletion();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) counters[i] = 0;
+}
+
 template <bool C2>
 __global__ void __launch_bounds__(K2_THREADS)
 k_threshold_compact(const float *__restrict__ conf, int64_t N, int C, float thr,
-                    int32_t *__restrict__ counters, uint64_t *__restrict__ keys)
+                    int32_t *__restrict__ counters, uint64_t *__restrict__ keys, long long *prof)
 {
+    unsigned long long gt0 = 0;
+    if (prof && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
     // programmatic dependent launch: let k_sort_nms be scheduled while this grid drains (it waits for our completion itself)
     cudaTriggerProgrammaticLaunchCompletion();
     const int b = blockIdx.y;
@@ -56,12 +69,15 @@ k_threshold_compact(const float *__restrict__ conf, int64_t N, int C, float thr,
     const int64_t base = (int64_t)blockIdx.x * K2_TILE;
     const float *cb = conf + (int64_t)b * N * C;
     __shared__ int s_warp[K2_THREADS / 32];
+    __shared__ unsigned s_wmax[K2_THREADS / 32], s_wminv[K2_THREADS / 32];
     __shared__ int s_base;
+    const int lists = gridDim.y * (C - 1);
 
     for (int cl = 1; cl < C; ++cl) {
         float sc[K2_PER_THREAD];
         unsigned bal[K2_PER_THREAD];
         int wtotal = 0;
+        unsigned kmx = 0u, kmnv = 0u;                    // max key and max ~key (= ~min key) of this thread's candidates
 #pragma unroll
         for (int u = 0; u < K2_PER_THREAD; ++u) {
             int64_t p = base + u * K2_THREADS + tid;
@@ -72,17 +88,31 @@ k_threshold_compact(const float *__restrict__ conf, int64_t N, int C, float thr,
                 else    s = __ldg(cb + p * C + cl);
             }
             sc[u] = s;
-            bal[u] = __ballot_sync(0xffffffffu, in && s > thr);      // detection.py:64 strict gt
+            const bool cand = in && s > thr;                         // detection.py:64 strict gt
+            bal[u] = __ballot_sync(0xffffffffu, cand);
             wtotal += __popc(bal[u]);
+            if (cand) {
+                const unsigned kk = fdt_float_key(s); kmx = max(kmx, kk); kmnv = max(kmnv, ~kk);
+            }
         }
-        if (lane == 0) s_warp[warp] = wtotal;
+        kmx = __reduce_max_sync(0xffffffffu, kmx); kmnv = __reduce_max_sync(0xffffffffu, kmnv);
+        if (lane == 0) { s_warp[warp] = wtotal; s_wmax[warp] = kmx; s_wminv[warp] = kmnv; }
+        if (cl == 1) cudaGridDependencySynchronize();    // k_zero_counters has completed (the conf loads above were issued before the wait)
         __syncthreads();
         const int list = b * (C - 1) + (cl - 1);
         if (tid == 0) {
             int tot = 0;
+            unsigned bmx = 0u, bmnv = 0u;
 #pragma unroll
-            for (int w = 0; w < K2_THREADS / 32; ++w) { int c = s_warp[w]; s_warp[w] = tot; tot += c; }
+            for (int w = 0; w < K2_THREADS / 32; ++w) {
+                int c = s_warp[w]; s_warp[w] = tot; tot += c;
+                bmx = max(bmx, s_wmax[w]); bmnv = max(bmnv, s_wminv[w]);
+            }
             s_base = tot ? atomicAdd(&counters[list], tot) : 0;
+            if (tot) {           // score range of the list for k_sort_nms' bucket map: counters[lists + list] = max key, [2 lists + list] = ~min key
+                atomicMax(reinterpret_cast<unsigned *>(counters) + lists + list, bmx);
+                atomicMax(reinterpret_cast<unsigned *>(counters) + 2 * lists + list, bmnv);
+            }
         }
         __syncthreads();
         int off = s_base + s_warp[warp];
@@ -97,6 +127,11 @@ k_threshold_compact(const float *__restrict__ conf, int64_t N, int C, float thr,
         }
         __syncthreads();
     }
+    if (prof && threadIdx.x == 0) {      // diagnostics (FDT_K3_PROFILE=1): first block start / last block end on the global timer
+        unsigned long long gt1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        atomicMin((unsigned long long *)&prof[44], gt0); atomicMax((unsigned long long *)&prof[45], gt1);
+    }
 }
 
 __global__ void k_build_keys(const float *__restrict__ scores, int64_t n, uint64_t *__restrict__ keys)
@@ -106,17 +141,34 @@ __global__ void k_build_keys(const float *__restrict__ scores, int64_t n, uint64
 }
 
 // ------------------------------------------------------------------------------------------- K3
+// Shared-memory layout of k_sort_nms.  Everything whose size does not depend on the call sits at a COMPILE-TIME offset (the
+// addresses fold into the LDS/STS immediates; with run-time offsets ~15 % of the kernel's instructions were address
+// arithmetic); the key array and the kept-box arrays follow at run-time offsets.
+constexpr int up16c(int x) { return (x + 15) / 16 * 16; }
+constexpr int SM_HIST = 0;                                          // sort: fill[NB] | start[NB]
+constexpr int SM_SEGS = SM_HIST + 2 * NB * 4;                       // [32 warps][SEG_SLOTS * 32] phase-B row segments
+constexpr int SM_SBOX = SM_SEGS + K3_THREADS * SEG_SLOTS * 4;       // [WIN] window boxes in cell (CSR) order
+constexpr int SM_SAREA = SM_SBOX + WIN * 16;
+constexpr int SM_SDEPS = SM_SAREA + WIN * 4;                        // [WIN][DEPS] earlier suppressors per window candidate
+constexpr int SM_SNDEP = SM_SDEPS + WIN * DEPS * 2;                 // [WIN] how many were found (may exceed DEPS)
+constexpr int SM_WSTART = SM_SNDEP + WIN * 4;                       // [NCELLX + 1] CSR over the window
+constexpr int SM_KSTART = SM_WSTART + up16c((NCELLX + 1) * 4);      // [NCELLX + 1] CSR over the kept boxes
+constexpr int SM_KCUR = SM_KSTART + up16c((NCELLX + 1) * 4);        // [NCELLX + 1] fill cursors
+constexpr int SM_WPOS = SM_KCUR + up16c((NCELLX + 1) * 4);          // [WIN] CSR position of each window candidate
+constexpr int SM_WCELL = SM_WPOS + WIN * 2;                         // [WIN] grid cell of each window candidate
+constexpr int SM_WITEMS = SM_WCELL + WIN * 2;                       // [WIN] window candidates sorted by cell
+constexpr int SM_STATUS = SM_WITEMS + WIN * 2;                      // [WIN] 0 undecided, 1 kept, 2 dead
+constexpr int SM_KEYS = SM_STATUS + WIN;                            // [key_cap] bucket-ordered, then sorted per window
 struct SmemPlan {
     int key_cap;                                   // entries of the key array (power of two >= kcap + 64)
-    int off_scr, off_wbox, off_warea, off_wside, off_wcell, off_status, off_witems, off_wstart, off_sbox, off_sarea, off_sdeps, off_sndep;
-    int off_kstart, off_kcur, off_kitems, off_kcell;
+    int off_kitems, off_kcell;
     int off_kbox, off_karea, off_kkey;             // < 0: kept arrays live in the global workspace
     int total;
 };
 
 struct SortNmsParams {
     const uint64_t *keys;       // [lists, key_stride]
-    const int32_t *counters;    // [lists] (MODE_DETECT)
+    const int32_t *counters;    // [3][lists] (MODE_DETECT): candidate count, max key, ~min key
     int64_t key_stride;
     const float *loc;           // [B,N,4]  (MODE_DETECT)
     const float *priors;        // [N,4]    (MODE_DETECT)
@@ -195,8 +247,11 @@ __device__ __forceinline__ bool box_regular(const float4 b)
 // cell is at least as long as the box's longer side, in the cell of its min corner (clamped: the cell map is monotone
 // in the coordinate, which is all the proof below needs).  A box j can only reach IoU >= thr with boxes whose longer
 // side is within a factor thr of its own (IoU <= side ratio), so a query visits only the levels that can hold such
-// boxes, and at level l' only rows/columns [cell(x1_j - 1.01 c_l'), cell(x2_j)]: an item i there that intersects j has
-// x1_i <= x2_j and x1_i >= x1_j - (x2_i - x1_i) >= x1_j - c_l' (the 1 % pad covers fp32 rounding of the width).
+// boxes, and at level l' only rows/columns [cell(x1_j - (1.01 - q) c_l'), cell(x2_j - q w_j)], q = 0.97 min(thr, 1):
+// IoU <= ox / max(w_i, w_j) (ox = overlap along x: inter <= ox min(h) and union >= each area), so reaching thr needs
+// ox >= thr max(w_i, w_j); then x1_i <= x2_j - ox <= x2_j - thr w_j and x1_i >= x1_j - (w_i - ox) >= x1_j - (1 - thr) c_l'.
+// The 3 % margin on thr and 1 % on c cover the fp32 rounding of the IoU, of the widths and of these bounds (plus an
+// absolute slack of a few ulps of the coordinates for boxes that are tiny relative to their position); same along y.
 // Cells of one row are consecutive in the CSR array, so each visited row is ONE contiguous item segment.
 struct GridGeom {
     float x0, y0;          // origin = min corner
@@ -225,20 +280,28 @@ __device__ __forceinline__ int reg_cell(const GridGeom &gg, const float4 bx, con
 }
 // visit(t) is called with CSR positions t (item = items[t]) and returns true to stop; returns true iff the visitor stopped.
 // `start` has NCELLX + 1 entries.
+// query ranges before the per-level pad: (x1_j - slack, y1_j - slack, x2_j - q w_j + slack, y2_j - q h_j + slack)
+__device__ __forceinline__ float4 query_range(const float4 bj, const float tq)
+{
+    const float sx = 2e-6f * fmaxf(fabsf(bj.x), fabsf(bj.z)), sy = 2e-6f * fmaxf(fabsf(bj.y), fabsf(bj.w));
+    return make_float4(bj.x - sx, bj.y - sy, (bj.z - tq * (bj.z - bj.x)) + sx, (bj.w - tq * (bj.w - bj.y)) + sy);
+}
 template <typename F>
 __device__ __forceinline__ bool csr_query(const GridGeom &gg, const int *start, const float4 bj, const float sj,
-                                          const float prune, F &&visit)
+                                          const float prune, const float tq, F &&visit)
 {
     float c = gg.c0, inv = gg.inv0, cprev = 0.0f;
     int G = 32, base = 0;
+    const float4 qr = query_range(bj, tq);
+    const float padf = 1.01f - tq;
 #pragma unroll 1
     for (int lev = 0; lev < NLEV; ++lev, cprev = c, c *= 2.0f, inv *= 0.5f, base += G * G, G >>= 1) {
         if (c < prune * sj) continue;                    // every box of this level is too small to reach thr
         if (cprev * prune > sj) break;                   // this and all coarser levels only hold boxes too large
         if (start[base + G * G] == start[base]) continue;
-        const float pad = 1.01f * c;
-        const int cx0 = cell_of(bj.x - pad, gg.x0, inv, G), cx1 = cell_of(bj.z, gg.x0, inv, G);
-        const int cy0 = cell_of(bj.y - pad, gg.y0, inv, G), cy1 = cell_of(bj.w, gg.y0, inv, G);
+        const float pad = padf * c;
+        const int cx0 = cell_of(qr.x - pad, gg.x0, inv, G), cx1 = cell_of(qr.z, gg.x0, inv, G);
+        const int cy0 = cell_of(qr.y - pad, gg.y0, inv, G), cy1 = cell_of(qr.w, gg.y0, inv, G);
         for (int cy = cy0; cy <= cy1; ++cy) {
             const int t1 = start[base + cy * G + cx1 + 1];
             for (int t = start[base + cy * G + cx0]; t < t1; ++t)
@@ -251,27 +314,29 @@ __device__ __forceinline__ bool csr_query(const GridGeom &gg, const int *start, 
     return false;
 }
 
-// Forward half of csr_query for the window grid: visits only CSR positions AFTER `own_t` (own level: the rest of the own
-// row and the rows below; coarser levels: everything in range; finer levels: nothing).  Every pair of window candidates
-// that csr_query would find from either side is found by exactly one of the two forward queries (the one with the lower
-// CSR position), because each side's full query finds the other.
-// `part` of `nparts` (1, 2 or 4 lanes share a candidate): the lanes take grid rows (and pseudo-cell items) round-robin.
+// Forward half of csr_query for the window grid, as row segments: emits the non-empty CSR ranges [t0, t1) that lie AFTER
+// `own_t` (own level: the rest of the own row and the rows below; coarser levels: everything in range; finer levels:
+// nothing).  Every pair of window candidates that csr_query would find from either side is found by exactly one of the two
+// forward queries (the one with the lower CSR position), because each side's full query finds the other.
+// `part` of `nparts` (1, 2 or 4 lanes share a candidate): the lanes take grid rows round-robin; part 0 takes the pseudo-cell.
 template <typename F>
-__device__ __forceinline__ void csr_query_forward(const GridGeom &gg, const int *start, const float4 bj, const float sj,
-                                                  const float prune, const int own_cell, const int own_t, const int part, const int nparts, F &&visit)
+__device__ __forceinline__ void csr_segments_forward(const GridGeom &gg, const int *start, const float4 bj, const float sj,
+                                                     const float prune, const float tq, const int own_cell, const int own_t, const int part, const int nparts, F &&emit)
 {
     float c = gg.c0, inv = gg.inv0, cprev = 0.0f;
     int G = 32, base = 0;
+    const float4 qr = query_range(bj, tq);
+    const float padf = 1.01f - tq;
 #pragma unroll 1
     for (int lev = 0; lev < NLEV; ++lev, cprev = c, c *= 2.0f, inv *= 0.5f, base += G * G, G >>= 1) {
         if (own_cell >= base + G * G) continue;          // finer than the own level: those candidates look forward to us
         if (c < prune * sj) continue;
         if (cprev * prune > sj) break;
         if (start[base + G * G] == start[base]) continue;
-        const float pad = 1.01f * c;
-        const int cx0 = cell_of(bj.x - pad, gg.x0, inv, G), cx1 = cell_of(bj.z, gg.x0, inv, G);
-        int cy0 = cell_of(bj.y - pad, gg.y0, inv, G);
-        const int cy1 = cell_of(bj.w, gg.y0, inv, G);
+        const float pad = padf * c;
+        const int cx0 = cell_of(qr.x - pad, gg.x0, inv, G), cx1 = cell_of(qr.z, gg.x0, inv, G);
+        int cy0 = cell_of(qr.y - pad, gg.y0, inv, G);
+        const int cy1 = cell_of(qr.w, gg.y0, inv, G);
         const bool own_level = own_cell >= base;         // (own_cell < base + G*G holds here)
         const int own_cy = own_level ? (own_cell - base) >> (5 - lev) : -1;      // G = 32 >> lev
         if (own_level) cy0 = max(cy0, own_cy);
@@ -279,11 +344,14 @@ __device__ __forceinline__ void csr_query_forward(const GridGeom &gg, const int 
             const int t1 = start[base + cy * G + cx1 + 1];
             int t = start[base + cy * G + cx0];
             if (cy == own_cy) t = max(t, own_t + 1);
-            for (; t < t1; ++t) visit(t);
+            if (t < t1) emit(t, t1);
         }
     }
-    const int t1 = start[BIGCELL + 1];
-    for (int t = max(start[BIGCELL], own_t + 1) + part; t < t1; t += nparts) visit(t);
+    if (part == 0) {
+        const int t1 = start[BIGCELL + 1];
+        const int t = max(start[BIGCELL], own_t + 1);
+        if (t < t1) emit(t, t1);
+    }
 }
 
 // clock64 that cannot be read before a preceding barrier has released: BAR.SYNC is deferred-blocking, the shared-memory
@@ -337,22 +405,21 @@ __global__ void __launch_bounds__(K3_THREADS, 1)
 k_sort_nms(const SortNmsParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    uint64_t *skeys = reinterpret_cast<uint64_t *>(smem);                       // [key_cap] bucket-ordered, then sorted per window
-    int *s_hist = reinterpret_cast<int *>(smem + P.sm.off_scr);                  // sort: fill[NB] | start[NB]
+    uint64_t *skeys = reinterpret_cast<uint64_t *>(smem + SM_KEYS);
+    int *s_hist = reinterpret_cast<int *>(smem + SM_HIST);
     int *s_start = s_hist + NB;
-    float4 *wbox = reinterpret_cast<float4 *>(smem + P.sm.off_wbox);             // [WIN] boxes of the current window
-    float *warea = reinterpret_cast<float *>(smem + P.sm.off_warea);
-    float *wside = reinterpret_cast<float *>(smem + P.sm.off_wside);
-    uint16_t *wcell = reinterpret_cast<uint16_t *>(smem + P.sm.off_wcell);       // [WIN] grid cell of each window candidate
-    unsigned char *status = smem + P.sm.off_status;                              // [WIN] 0 undecided, 1 kept, 2 dead
-    uint16_t *witems = reinterpret_cast<uint16_t *>(smem + P.sm.off_witems);     // [WIN] window candidates sorted by cell
-    int *wstart = reinterpret_cast<int *>(smem + P.sm.off_wstart);               // [NCELLX + 1]
-    float4 *sbox = reinterpret_cast<float4 *>(smem + P.sm.off_sbox);             // [WIN] window boxes in cell (CSR) order
-    float *sarea = reinterpret_cast<float *>(smem + P.sm.off_sarea);
-    uint16_t *sdeps = reinterpret_cast<uint16_t *>(smem + P.sm.off_sdeps);       // [WIN][DEPS] earlier suppressors per window candidate
-    int *sndep = reinterpret_cast<int *>(smem + P.sm.off_sndep);                 // [WIN] how many were found (may exceed DEPS)
-    int *kstart = reinterpret_cast<int *>(smem + P.sm.off_kstart);               // [NCELLX + 1] CSR over the kept boxes
-    int *kcur = reinterpret_cast<int *>(smem + P.sm.off_kcur);                   // [NCELLX + 1] fill cursors
+    uint16_t *wpos = reinterpret_cast<uint16_t *>(smem + SM_WPOS);
+    uint32_t *segs = reinterpret_cast<uint32_t *>(smem + SM_SEGS);
+    uint16_t *wcell = reinterpret_cast<uint16_t *>(smem + SM_WCELL);
+    unsigned char *status = smem + SM_STATUS;
+    uint16_t *witems = reinterpret_cast<uint16_t *>(smem + SM_WITEMS);
+    int *wstart = reinterpret_cast<int *>(smem + SM_WSTART);
+    float4 *sbox = reinterpret_cast<float4 *>(smem + SM_SBOX);
+    float *sarea = reinterpret_cast<float *>(smem + SM_SAREA);
+    uint16_t *sdeps = reinterpret_cast<uint16_t *>(smem + SM_SDEPS);
+    int *sndep = reinterpret_cast<int *>(smem + SM_SNDEP);
+    int *kstart = reinterpret_cast<int *>(smem + SM_KSTART);
+    int *kcur = reinterpret_cast<int *>(smem + SM_KCUR);
     uint16_t *kitems = reinterpret_cast<uint16_t *>(smem + P.sm.off_kitems);     // [max_keep]
     uint16_t *kcell = reinterpret_cast<uint16_t *>(smem + P.sm.off_kcell);       // [max_keep]
     const int list = blockIdx.x / CL;
@@ -373,6 +440,24 @@ k_sort_nms(const SortNmsParams P)
     const int cl = (MODE == MODE_DETECT) ? 1 + list % (P.C - 1) : 0;
     const uint64_t *gkeys = P.keys + (int64_t)list * P.key_stride;
 
+    // Output that does not depend on the producer kernel goes first: the all-zero background plane (detection.py:48, :63)
+    // is written while k_threshold_compact still runs (programmatic dependent launch).
+    if (MODE == MODE_DETECT && crank == 0 && cl == 1) {
+        const int ndst = P.n_peers > 0 ? P.n_peers : 1;
+        const int nq = (P.top_k * 5) >> 2;                       // whole float4s; planes are 16-byte aligned iff top_k * 5 % 4 == 0
+        const bool vec = ((P.top_k * 5) & 3) == 0;
+        for (int pr = 0; pr < ndst; ++pr) {
+            float *base = P.n_peers > 0 ? reinterpret_cast<float *>(P.peer_out[pr]) + (P.img_offset * P.C) * (int64_t)P.top_k * 5 : P.out;
+            float *o0 = base + ((int64_t)(b * P.C) * P.top_k) * 5;
+            if (vec && ((uintptr_t)o0 & 15) == 0) for (int t = tid; t < nq; t += K3_THREADS) reinterpret_cast<float4 *>(o0)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            else for (int t = tid; t < P.top_k * 5; t += K3_THREADS) o0[t] = 0.0f;
+        }
+        if (P.kept_prior) {
+            int64_t *kp = P.kept_prior + (int64_t)(b * P.C) * P.top_k;
+            for (int r = tid; r < P.top_k; r += K3_THREADS) kp[r] = -1;
+        }
+        if (P.counts && tid == 0) P.counts[b * P.C] = 0;
+    }
     cudaGridDependencySynchronize();      // no-op unless launched with programmatic stream serialization (after K2)
     int n_c = (MODE == MODE_DETECT) ? P.counters[list] : (int)P.n;
     if (MODE == MODE_DETECT && n_c == 1) n_c = 0;            // detection.py:66-72: one candidate -> `continue`
@@ -414,16 +499,21 @@ k_sort_nms(const SortNmsParams P)
         if (tid == 0) { s_kmin = 0xffffffffu; s_kmax = 0u; s_maxb = 0; }
         for (int i = tid; i < 2 * NB; i += K3_THREADS) s_hist[i] = 0;
         __syncthreads();
-        {
+        unsigned kmax;
+        if (MODE == MODE_DETECT) {          // k_threshold_compact already reduced the score range of the list
+            const int lists = (int)(gridDim.x / CL);
+            kmax = (unsigned)P.counters[lists + list];
+            kmin = ~(unsigned)P.counters[2 * lists + list];
+        } else {
             unsigned lo = 0xffffffffu, hi = 0u;
             for_each_key([&](uint64_t key) { unsigned k32 = (unsigned)(key >> 32); lo = min(lo, k32); hi = max(hi, k32); });
             lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
             if (lane == 0) { atomicMin(&s_kmin, lo); atomicMax(&s_kmax, hi); }
+            __syncthreads();
+            kmin = s_kmin; kmax = s_kmax;
         }
-        __syncthreads();
         K3_STAMP(0);
-        kmin = s_kmin;
-        binv = (float)NB / ((float)(s_kmax - kmin) + 1.0f);
+        binv = (float)NB / ((float)(kmax - kmin) + 1.0f);
         uint64_t tmin = 0;                                   // after the fallback select: only keys >= tmin take part
         for (int attempt = 0; attempt < 2; ++attempt) {
             for_each_key([&](uint64_t key) { if (key >= tmin) atomicAdd(&s_hist[bucket(key)], 1); });
@@ -548,6 +638,7 @@ k_sort_nms(const SortNmsParams P)
     // In phases A-C thread t works on the t-th candidate IN CELL ORDER, so the lanes of a warp walk the same grid rows.
     const float thr = P.nms_thresh;
     const float prune = 0.99f * thr;
+    const float tq = 0.97f * fminf(thr, 1.0f);          // query-range tightening, see the grid comment
     const int max_keep = P.max_keep;
     int nkept = 0, rounds = 0, sweeps = 0;
     GridGeom gg;
@@ -570,41 +661,44 @@ k_sort_nms(const SortNmsParams P)
         sndep[tid] = 0;
         if (tid == 0) s_next = 0;
         if (tid == 0) { s_ext[0] = 0xffffffffu; s_ext[1] = 0xffffffffu; s_ext[2] = 0u; s_ext[3] = 0u; }
-        // ---- exact order inside the window: rank = bucket start + number of larger keys in the same bucket
+        // ---- exact order inside the window: rank = bucket start + number of larger keys in the same bucket.  The thread that
+        //      holds the key at (unsorted) position lo + tid issues the loads of that candidate's loc / prior rows first, ranks
+        //      the key while they are in flight, and then owns window position `wi` = rank - lo up to the CSR build.
         const int j = lo + tid;
-        if (!presorted) {
+        int wi = -1;
+        float4 ld0 = make_float4(0.f, 0.f, 0.f, 0.f), ld1 = ld0;
+        {
             uint64_t key = 0;
             int r = -1;
             if (j < hi) {
                 key = skeys[j];
-                const int bq = bucket(key);
-                const int blo = s_start[bq], bhi = blo + s_hist[bq];
-                int g = 0;
-                for (int t = blo; t < bhi; ++t) g += skeys[t] > key;
-                r = blo + g;
+                const uint32_t p = (uint32_t)key;
+                if (MODE == MODE_DETECT) {
+                    ld0 = __ldg(reinterpret_cast<const float4 *>(P.loc) + ((int64_t)b * P.N + p));
+                    ld1 = __ldg(reinterpret_cast<const float4 *>(P.priors) + p);
+                } else {
+                    ld0 = __ldg(reinterpret_cast<const float4 *>(P.boxes) + p);
+                }
+                if (!presorted) {
+                    const int bq = bucket(key);
+                    const int blo = s_start[bq], bhi = blo + s_hist[bq];
+                    int g = 0;
+                    for (int t = blo; t < bhi; ++t) g += skeys[t] > key;
+                    r = blo + g;
+                } else r = j;
+                wi = r - lo;
             }
-            __syncthreads();
-            if (r >= 0) skeys[r] = key;
+            __syncthreads();                 // every key of the window is read (and the zeroed grid counters are visible)
+            if (!presorted && r >= 0) skeys[r] = key;
         }
-        __syncthreads();
         K3_ACC(0);
         // ---- boxes of the window (decode only what NMS looks at); grid geometry from the first window
-        const bool valid = j < hi && j < k;
+        const bool valid = wi >= 0 && lo + wi < k;
         const int nvalid = min(hi, k) - lo;
         {
             float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) {
-                const uint32_t p = (uint32_t)skeys[j];
-                if (MODE == MODE_DETECT) {
-                    const float4 l = __ldg(reinterpret_cast<const float4 *>(P.loc) + ((int64_t)b * P.N + p));
-                    const float4 pr = __ldg(reinterpret_cast<const float4 *>(P.priors) + p);
-                    bx = fdt_decode1(l, pr, P.v0, P.v1);              // detection.py:55
-                } else {
-                    bx = __ldg(reinterpret_cast<const float4 *>(P.boxes) + p);
-                }
-            }
+            if (valid) bx = (MODE == MODE_DETECT) ? fdt_decode1(ld0, ld1, P.v0, P.v1) : ld0;      // detection.py:55
             const float side = fmaxf(bx.z - bx.x, bx.w - bx.y);
-            wbox[tid] = bx; warea[tid] = box_area(bx); wside[tid] = side;
             if (rounds == 0) {
                 const bool reg = valid && box_regular(bx);
                 float x0 = reg ? bx.x : INFINITY, y0 = reg ? bx.y : INFINITY, x1 = reg ? bx.z : -INFINITY, y1 = reg ? bx.w : -INFINITY;
@@ -630,13 +724,13 @@ k_sort_nms(const SortNmsParams P)
             K3_ACC(1);
             // ---- window grid and (from the second round on) kept-box grid, CSR: count per cell, scan, place
             const int cell = reg_cell(gg, bx, side, valid);
-            wcell[tid] = (uint16_t)(cell < 0 ? BIGCELL : cell);
+            if (wi >= 0) wcell[wi] = (uint16_t)(cell < 0 ? BIGCELL : cell);
             const int slot = cell >= 0 ? atomicAdd(&wstart[cell + 1], 1) : 0;
             if (rounds > 0)
                 for (int i = tid; i < nkept; i += K3_THREADS) atomicAdd(&kstart[kcell[i] + 1], 1);
             __syncthreads();
             csr_scan(wstart, s_warp);
-            if (cell >= 0) { const int ps = wstart[cell] + slot; witems[ps] = (uint16_t)tid; sbox[ps] = bx; sarea[ps] = box_area(bx); }
+            if (cell >= 0) { const int ps = wstart[cell] + slot; witems[ps] = (uint16_t)wi; wpos[wi] = (uint16_t)ps; sbox[ps] = bx; sarea[ps] = box_area(bx); }
             if (CL == 2) {
                 // Both CTAs of the cluster must see the SAME CSR array (they split it by position): order every cell by window
                 // position instead of by atomic arrival.
@@ -654,7 +748,7 @@ k_sort_nms(const SortNmsParams P)
                     np = s0 + r;
                 }
                 __syncthreads();
-                if (np >= 0) { witems[np] = it; sbox[np] = b4; sarea[np] = ar; }
+                if (np >= 0) { witems[np] = it; wpos[it] = (uint16_t)np; sbox[np] = b4; sarea[np] = ar; }
             }
             if (rounds > 0) {
                 csr_scan(kstart, s_warp);
@@ -677,7 +771,7 @@ k_sort_nms(const SortNmsParams P)
         bool alive = have;
         if (have && nkept > 0) {
             auto hit = [&](int t) -> bool { const int slot = kitems[t]; return fdt_suppresses_fast(kbox[slot], karea[slot], bj, aj, thr); };
-            if (in_grid) alive = !csr_query(gg, kstart, bj, sj, prune, hit);
+            if (in_grid) alive = !csr_query(gg, kstart, bj, sj, prune, tq, hit);
             else for (int t = 0; t < nkept && alive; ++t) if (fdt_suppresses(kbox[t], karea[t], bj, aj, thr)) alive = false;
         }
         if (have) status[id] = alive ? 0 : 2;
@@ -685,43 +779,90 @@ k_sort_nms(const SortNmsParams P)
         __syncthreads();
         // ---- phase B: suppression pairs among the survivors of this window, each unordered pair examined once (forward
         //      queries); "a suppresses b" (a earlier in score order) is recorded in b's list with shared-memory atomics.
-        //      1, 2 or 4 lanes share a candidate (small windows leave threads to spare; the lanes take grid rows round-robin);
-        //      warps fetch chunks of candidates dynamically, coarse levels (the longest queries) first.
+        //      B1: 1, 2 or 4 lanes share a candidate and walk its grid rows (round-robin), queueing the non-empty CSR row
+        //          segments in the warp's own shared-memory region (no item is touched yet);
+        //      B2: the warp flattens its segments into (candidate, item) pairs -- 32 pairs per step whatever the segment
+        //          lengths are (prefix sum + ballot/REDUX owner search) -- so the IoU tests run without divergence.
         {
             const int share = (nvalid + CL - 1) / CL;                                            // candidates this CTA queries
             const int lpc = share > K3_THREADS / 2 ? 1 : share > K3_THREADS / 4 ? 2 : 4;        // lanes per candidate
             const int per_chunk = 32 / lpc;
             const int part = lane % lpc, sub = lane / lpc;
-            for (;;) {
-                int chunk = 0;
-                if (lane == 0) chunk = atomicAdd(&s_next, per_chunk);
-                chunk = __shfl_sync(0xffffffffu, chunk, 0);
-                if (CL == 2) chunk = 2 * chunk + crank * per_chunk;    // the cluster's CTAs take alternate chunks
-                if (chunk >= nvalid) break;
-                const int t = nvalid - 1 - (chunk + sub);          // CSR position, from the end
-                if (t < 0) continue;
-                const int cid = witems[t];
-                if (status[cid] == 2) continue;                     // suppressed in phase A
-                const float4 cb = sbox[t];
-                const float ca = sarea[t], cs = fmaxf(cb.z - cb.x, cb.w - cb.y);
-                auto pair = [&](int t2) {
-                    const int other = witems[t2];
-                    if (chk && status[other] == 2) return;
-                    const float4 bo = sbox[t2];
-                    const float ao = sarea[t2];
-                    const bool me_first = cid < other;           // window index = score order
-                    const bool sup = me_first ? fdt_suppresses_fast(cb, ca, bo, ao, thr) : fdt_suppresses_fast(bo, ao, cb, ca, thr);
-                    if (sup) {
-                        const int later = me_first ? other : cid, earlier = me_first ? cid : other;
-                        const int sl = atomicAdd(&sndep[later], 1);
-                        if (sl < DEPS) sdeps[later * DEPS + sl] = (uint16_t)earlier;
-                    }
-                };
-                if (wcell[cid] != BIGCELL) csr_query_forward(gg, wstart, cb, cs, prune, (int)wcell[cid], t, part, lpc, pair);
-                else {
-                    const int t1 = wstart[BIGCELL + 1];    // irregular boxes sit last in CSR order: every regular candidate's
-                    for (int t2 = t + 1 + part; t2 < t1; t2 += lpc) pair(t2);   // forward query reaches them; they only pair among themselves
+            const bool wprof = P.prof != nullptr && blockIdx.x == 0;
+            const long long wb0 = wprof ? clock64() : 0;
+            int nvis = 0;
+            uint32_t *wseg = segs + warp * (SEG_SLOTS * 32);
+            auto pair = [&](const int tc, const int t2) {       // CSR positions: candidate, item (tc < t2)
+                if (wprof) ++nvis;
+                const int cid = witems[tc], other = witems[t2];
+                if (chk && status[other] == 2) return;
+                const float4 cb = sbox[tc], bo = sbox[t2];
+                const float ca = sarea[tc], ao = sarea[t2];
+                const bool me_first = cid < other;           // window index = score order
+                const bool sup = me_first ? fdt_suppresses_fast(cb, ca, bo, ao, thr) : fdt_suppresses_fast(bo, ao, cb, ca, thr);
+                if (sup) {
+                    const int later = me_first ? other : cid, earlier = me_first ? cid : other;
+                    const int sl = atomicAdd(&sndep[later], 1);
+                    if (sl < DEPS) sdeps[later * DEPS + sl] = (uint16_t)earlier;
                 }
+            };
+            // one chunk of 32 / lpc candidates per warp (the cluster's CTAs take alternate chunks), from the end of the CSR
+            // array: 32 * CL chunks cover the window for every lpc
+            const int t = nvalid - 1 - ((CL * warp + crank) * per_chunk + sub);
+            int nseg = 0;
+            if (t >= 0) {
+                const int cid = witems[t];
+                if (status[cid] != 2) {                         // else: suppressed in phase A
+                    auto emit = [&](const int t0, const int t1) {
+                        if (nseg < SEG_SLOTS) { wseg[nseg * 32 + lane] = (uint32_t)t | ((uint32_t)t0 << 10) | ((uint32_t)(t1 - t0) << 20); ++nseg; }
+                        else for (int t2 = t0; t2 < t1; ++t2) pair(t, t2);
+                    };
+                    if (wcell[cid] != BIGCELL) {
+                        const float4 cb = sbox[t];
+                        csr_segments_forward(gg, wstart, cb, fmaxf(cb.z - cb.x, cb.w - cb.y), prune, tq, (int)wcell[cid], t, part, lpc, emit);
+                    } else if (part == 0) {
+                        // irregular boxes sit last in CSR order: every regular candidate's forward query reaches them; they
+                        // only pair among themselves
+                        const int t1 = wstart[BIGCELL + 1];
+                        if (t + 1 < t1) emit(t + 1, t1);
+                    }
+                }
+            }
+            // compact the lanes' segment queues into one list (in place: position excl + k <= own slot k * 32 + lane ... read first)
+            uint32_t mine[SEG_SLOTS];
+#pragma unroll
+            for (int q = 0; q < SEG_SLOTS; ++q) mine[q] = q < nseg ? wseg[q * 32 + lane] : 0u;
+            int inc = nseg;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+            const int S = __shfl_sync(0xffffffffu, inc, 31);
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < SEG_SLOTS; ++q) if (q < nseg) wseg[inc - nseg + q] = mine[q];
+            __syncwarp();
+            for (int b0 = 0; b0 < S; b0 += 32) {
+                const uint32_t sg = b0 + lane < S ? wseg[b0 + lane] : 0u;
+                const int len = (int)(sg >> 20);
+                int e = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, e, o); if (lane >= o) e += v; }
+                const int T = __shfl_sync(0xffffffffu, e, 31);
+                e -= len;                                        // exclusive: strictly increasing over the valid lanes, T beyond
+                for (int ib = 0; ib < T; ib += 32) {
+                    // owner of pair i = ib + lane: the last segment with e <= i
+                    const unsigned below = __ballot_sync(0xffffffffu, e < ib);
+                    const unsigned M = __reduce_or_sync(0xffffffffu, (e >= ib && e < ib + 32) ? 1u << (e - ib) : 0u);
+                    const int owner = min(31, max(0, __popc(below) + __popc(M & (0xffffffffu >> (31 - lane))) - 1));
+                    const uint32_t so = __shfl_sync(0xffffffffu, sg, owner);
+                    const int eo = __shfl_sync(0xffffffffu, e, owner);
+                    const int i = ib + lane;
+                    if (i < T) pair((int)(so & 1023u), (int)((so >> 10) & 1023u) + (i - eo));
+                }
+            }
+            if (wprof) {
+                const long long wb1 = clock64();
+                const int vsum = __reduce_add_sync(0xffffffffu, nvis), vmax = __reduce_max_sync(0xffffffffu, nvis);
+                if (lane == 0) { P.prof[640 + warp] = wb1 - wb0; P.prof[672 + warp] = vsum; P.prof[704 + warp] = vmax; P.prof[736 + warp] = S; }
             }
         }
         __syncthreads();                                   // dependency lists complete
@@ -766,10 +907,10 @@ k_sort_nms(const SortNmsParams P)
                                 }
                                 return false;
                             };
-                            csr_query(gg, wstart, bj, sj, prune, look);
+                            csr_query(gg, wstart, bj, sj, prune, tq, look);
                         } else {
                             for (int a = 0; a < id && !any_kept; ++a)
-                                if (status[a] != 2 && fdt_suppresses(wbox[a], warea[a], bj, aj, thr)) {
+                                if (status[a] != 2 && fdt_suppresses(sbox[wpos[a]], sarea[wpos[a]], bj, aj, thr)) {
                                     if (status[a] == 1) any_kept = true; else pend = true;
                                 }
                         }
@@ -784,12 +925,13 @@ k_sort_nms(const SortNmsParams P)
         K3_ACC(5);
         // ---- append the newly kept boxes in score order (thread <-> window position again)
         {
-            const int mine = (valid && status[tid] == 1) ? 1 : 0;
+            const int mine = (tid < nvalid && status[tid] == 1) ? 1 : 0;     // thread <-> window position
             int tot;
             const int before = block_excl_scan(mine, s_warp, tot);
             const int slot = nkept + before;
             if (mine && slot < max_keep) {
-                kbox[slot] = wbox[tid]; karea[slot] = warea[tid]; kkey[slot] = skeys[j]; kcell[slot] = wcell[tid];
+                const int ps = wpos[tid];
+                kbox[slot] = sbox[ps]; karea[slot] = sarea[ps]; kkey[slot] = skeys[j]; kcell[slot] = wcell[tid];
             }
             nkept = min(nkept + tot, max_keep);
         }
@@ -822,23 +964,12 @@ k_sort_nms(const SortNmsParams P)
                 }
                 o[t] = v;                                                    // detection.py:82
             }
-            if (cl == 1) {                                                   // class-0 plane stays zero (:48, :63)
-                float *o0 = base + ((int64_t)(b * P.C) * top_k) * 5;
-                for (int t = tid; t < top_k * 5; t += K3_THREADS) o0[t] = 0.0f;
-            }
         }
         if (P.kept_prior) {
             int64_t *kp = P.kept_prior + (int64_t)(b * P.C + cl) * top_k;
             for (int r = tid; r < top_k; r += K3_THREADS) kp[r] = r < cnt ? (int64_t)(uint32_t)kkey[r] : -1;
         }
         if (P.counts && tid == 0) P.counts[b * P.C + cl] = cnt;
-        if (cl == 1) {
-            if (P.kept_prior) {
-                int64_t *kp = P.kept_prior + (int64_t)(b * P.C) * top_k;
-                for (int r = tid; r < top_k; r += K3_THREADS) kp[r] = -1;
-            }
-            if (P.counts && tid == 0) P.counts[b * P.C] = 0;
-        }
     } else {
         for (int64_t t = tid; t < P.n; t += K3_THREADS)
             P.keep[t] = t < nkept ? (int64_t)(uint32_t)kkey[t] : 0;           // box_utils.py:289 zero-initialised
@@ -855,21 +986,7 @@ SmemPlan plan_smem(int kcap, int max_keep, bool kept_in_smem)
     SmemPlan s;
     s.key_cap = 64;
     while (s.key_cap < kcap + 64) s.key_cap <<= 1;
-    int off = s.key_cap * 8;
-    s.off_scr = off; off += up16(2 * NB * 4);
-    s.off_wbox = off; off += WIN * 16;
-    s.off_warea = off; off += WIN * 4;
-    s.off_wside = off; off += WIN * 4;
-    s.off_wcell = off; off += WIN * 2;
-    s.off_status = off; off += WIN;
-    s.off_witems = off; off += WIN * 2;
-    s.off_wstart = off; off += up16((NCELLX + 1) * 4);
-    s.off_sbox = off; off += WIN * 16;
-    s.off_sarea = off; off += WIN * 4;
-    s.off_sdeps = off; off += WIN * DEPS * 2;
-    s.off_sndep = off; off += WIN * 4;
-    s.off_kstart = off; off += up16((NCELLX + 1) * 4);
-    s.off_kcur = off; off += up16((NCELLX + 1) * 4);
+    int off = SM_KEYS + s.key_cap * 8;
     s.off_kitems = off; off += up16(max_keep * 2);
     s.off_kcell = off; off += up16(max_keep * 2);
     s.off_kbox = s.off_karea = s.off_kkey = -1;
@@ -885,6 +1002,17 @@ SmemPlan plan_smem(int kcap, int max_keep, bool kept_in_smem)
 constexpr int K3_STATIC_SMEM = 2 * 1024;         // small arrays declared __shared__ in k_sort_nms
 
 static long long *g_prof_dev = nullptr;
+static bool g_prof_armed = false;       // the producer launch already cleared the buffer (keeps K2 -> K3 adjacent in the stream)
+
+static int prof_arm(cudaStream_t st)
+{
+    if (!g_prof_dev) { FDT_CUDA(cudaMalloc(&g_prof_dev, 1024 * sizeof(long long))); }
+    FDT_CUDA(cudaMemsetAsync(g_prof_dev, 0, 1024 * sizeof(long long), st));
+    FDT_CUDA(cudaMemsetAsync(g_prof_dev + 40, 0xff, sizeof(long long), st));
+    FDT_CUDA(cudaMemsetAsync(g_prof_dev + 42, 0xff, sizeof(long long), st));
+    FDT_CUDA(cudaMemsetAsync(g_prof_dev + 44, 0xff, sizeof(long long), st));
+    return FDT_OK;
+}
 
 // kept_ws: global memory for the kept arrays (28 bytes per kept row and list) used when they do not fit in shared memory
 template <int MODE>
@@ -892,10 +1020,8 @@ int launch_sort_nms(SortNmsParams &P, int lists, int kcap, void *kept_ws, size_t
 {
     const char *env = getenv("FDT_K3_PROFILE");
     if (env && env[0] == '1') {
-        if (!g_prof_dev) { FDT_CUDA(cudaMalloc(&g_prof_dev, 640 * sizeof(long long))); }
-        FDT_CUDA(cudaMemsetAsync(g_prof_dev, 0, 640 * sizeof(long long), st));
-        FDT_CUDA(cudaMemsetAsync(g_prof_dev + 40, 0xff, sizeof(long long), st));
-        FDT_CUDA(cudaMemsetAsync(g_prof_dev + 42, 0xff, sizeof(long long), st));
+        if (!g_prof_armed) { int rc = prof_arm(st); if (rc != FDT_OK) return rc; }
+        g_prof_armed = false;
         P.prof = g_prof_dev;
     }
     FDT_REQUIRE(kcap <= FDT_MAX_NMS_TOP_K, FDT_E_UNSUPPORTED, "nms_top_k=%d exceeds %d", kcap, FDT_MAX_NMS_TOP_K);
@@ -956,7 +1082,7 @@ FDT_API size_t fdt_detect_workspace_bytes(int B, int64_t N, int C)
     if (B <= 0 || N <= 0 || C <= 1) return 256;
     size_t lists = (size_t)B * (size_t)(C - 1);
     size_t kept_rows = (size_t)(N < FDT_MAX_NMS_TOP_K ? N : FDT_MAX_NMS_TOP_K);       // only used when top_k rows exceed shared memory
-    return fdt_align256(lists * sizeof(int32_t)) + fdt_align256(lists * (size_t)N * sizeof(uint64_t)) +
+    return fdt_align256(3 * lists * sizeof(int32_t)) + fdt_align256(lists * (size_t)N * sizeof(uint64_t)) +
            fdt_align256(lists * kept_rows * KEPT_ROW_BYTES);
 }
 
@@ -981,8 +1107,14 @@ FDT_API int fdt_detect_threshold_compact(const float *conf, int B, int64_t N, in
     if (lists == 0 || N == 0) return FDT_OK;
     FDT_REQUIRE(conf && fdt_aligned(conf, 8), FDT_E_INVALID, "fdt_detect_threshold_compact: conf null or not 8-byte aligned");
     int32_t *counters = (int32_t *)ws;
-    uint64_t *keys = (uint64_t *)((char *)ws + fdt_align256((size_t)lists * sizeof(int32_t)));
-    FDT_CUDA(cudaMemsetAsync(counters, 0, (size_t)lists * sizeof(int32_t), st));
+    uint64_t *keys = (uint64_t *)((char *)ws + fdt_align256((size_t)3 * lists * sizeof(int32_t)));
+    long long *prof = nullptr;
+    {
+        const char *env = getenv("FDT_K3_PROFILE");
+        if (env && env[0] == '1') { int rc2 = prof_arm(st); if (rc2 != FDT_OK) return rc2; g_prof_armed = true; prof = g_prof_dev; }
+    }
+    k_zero_counters<<<(3 * lists + 255) / 256, 256, 0, st>>>(counters, 3 * lists);
+    FDT_LAUNCH_CHECK();
     dim3 g2((unsigned)((N + K2_TILE - 1) / K2_TILE), (unsigned)B);
     {
         // K3 needs the maximum shared-memory carveout; asking for the same split here avoids an SM reconfiguration
@@ -998,8 +1130,17 @@ FDT_API int fdt_detect_threshold_compact(const float *conf, int B, int64_t N, in
             carveout_set = true;
         }
     }
-    if (C == 2) k_threshold_compact<true><<<g2, K2_THREADS, 0, st>>>(conf, N, C, conf_thresh, counters, keys);
-    else        k_threshold_compact<false><<<g2, K2_THREADS, 0, st>>>(conf, N, C, conf_thresh, counters, keys);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = g2; cfg.blockDim = dim3(K2_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const int64_t N_ = N;
+        if (C == 2) FDT_CUDA(cudaLaunchKernelEx(&cfg, k_threshold_compact<true>, conf, N_, C, conf_thresh, counters, keys, prof));
+        else        FDT_CUDA(cudaLaunchKernelEx(&cfg, k_threshold_compact<false>, conf, N_, C, conf_thresh, counters, keys, prof));
+    }
     FDT_LAUNCH_CHECK();
     return FDT_OK;
 }
@@ -1038,7 +1179,7 @@ static int detect_sort_nms_impl(const float *loc, const float *priors, int B, in
     FDT_REQUIRE(loc && priors && fdt_aligned(loc, 16) && fdt_aligned(priors, 16), FDT_E_INVALID,
                 "fdt_detect: loc/priors null or not 16-byte aligned");
     int32_t *counters = (int32_t *)ws;
-    uint64_t *keys = (uint64_t *)((char *)ws + fdt_align256((size_t)lists * sizeof(int32_t)));
+    uint64_t *keys = (uint64_t *)((char *)ws + fdt_align256((size_t)3 * lists * sizeof(int32_t)));
     SortNmsParams P{};
     P.keys = keys; P.counters = counters; P.key_stride = N;
     P.loc = loc; P.priors = priors; P.N = N; P.C = C;
@@ -1087,12 +1228,12 @@ FDT_API int fdt_detect(const float *loc, const float *conf, const float *priors,
 // Diagnostics: with FDT_K3_PROFILE=1 in the environment, CTA 0 of k_sort_nms records clock64 deltas per phase:
 // [0] key min/max, [1] histogram+scan(+select), [2] scatter, [3] rank+permute, [4] decode+extent, [5..9] summed over
 // rounds: phase A, compaction, phase B pairs, resolve, insert; [10] rounds, [11] output, [12] kept, [13] k, [14] big list.
-FDT_API int fdt_debug_k3_profile(long long *out640_h)
+FDT_API int fdt_debug_k3_profile(long long *out640_h /* 1024 entries */)
 {
     FDT_REQUIRE(out640_h != nullptr, FDT_E_INVALID, "fdt_debug_k3_profile: null output");
     FDT_REQUIRE(g_prof_dev != nullptr, FDT_E_INVALID, "fdt_debug_k3_profile: run with FDT_K3_PROFILE=1 first");
     FDT_CUDA(cudaDeviceSynchronize());
-    FDT_CUDA(cudaMemcpy(out640_h, g_prof_dev, 640 * sizeof(long long), cudaMemcpyDeviceToHost));
+    FDT_CUDA(cudaMemcpy(out640_h, g_prof_dev, 1024 * sizeof(long long), cudaMemcpyDeviceToHost));
     return FDT_OK;
 }
 

@@ -6,7 +6,9 @@
 // Detect only decodes the candidates NMS actually looks at (<= 1024 rows of `loc` per image and round), so when
 // `loc_h` is pinned (page-locked, hence mapped into the unified address space) it is NOT copied: k_sort_nms gathers
 // those 16-byte rows straight from host memory over PCIe -- ~1 MB instead of 35 MB per batch of 64.  `conf` is streamed
-// in full by K2, so it is copied (17.5 MB) and read from HBM.
+// in full by K2, so it is copied (17.5 MB) and read from HBM.  A pinned `out_h` is likewise written in place: the output
+// stage of k_sort_nms stores the rows over PCIe (posted writes) while other images are still in NMS, and the separate
+// device-to-host copy of the [B,C,top_k,5] block disappears.
 #include <cstdlib>
 #include "fdt_common.cuh"
 
@@ -71,6 +73,14 @@ FDT_API int fdt_detect_host(fdt_ctx *c, const float *loc_h, const float *conf_h,
             loc_dev_view = (const float *)attr.devicePointer;
         else if (e != cudaSuccess) (void)cudaGetLastError();          // pageable memory on old drivers reports an error: ignore
     }
+    float *out_dev_view = nullptr;
+    {
+        cudaPointerAttributes attr;
+        cudaError_t e = cudaPointerGetAttributes(&attr, out_h);
+        if (e == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer && fdt_aligned(attr.devicePointer, 16))
+            out_dev_view = (float *)attr.devicePointer;
+        else if (e != cudaSuccess) (void)cudaGetLastError();
+    }
     const size_t sz_loc = loc_dev_view ? 0 : fdt_align256((size_t)B * N * 16), sz_conf = fdt_align256((size_t)B * N * C * 4);
     const size_t sz_pri = fdt_align256((size_t)N * 16), sz_out = fdt_align256((size_t)B * C * top_k * 20);
     const size_t sz_cnt = fdt_align256((size_t)B * C * 4), sz_kept = fdt_align256((size_t)B * C * top_k * 8);
@@ -81,7 +91,7 @@ FDT_API int fdt_detect_host(fdt_ctx *c, const float *loc_h, const float *conf_h,
     const float *d_loc = loc_dev_view ? loc_dev_view : (const float *)p; p += sz_loc;
     float *d_conf = (float *)p; p += sz_conf;
     float *d_pri = (float *)p; p += sz_pri;
-    float *d_out = (float *)p; p += sz_out;
+    float *d_out = out_dev_view ? out_dev_view : (float *)p; p += sz_out;
     int32_t *d_cnt = (int32_t *)p; p += sz_cnt;
     int64_t *d_kept = (int64_t *)p; p += sz_kept;
     void *d_ws = p;
@@ -92,7 +102,7 @@ FDT_API int fdt_detect_host(fdt_ctx *c, const float *loc_h, const float *conf_h,
     rc = fdt_detect(d_loc, d_conf, d_pri, B, N, C, top_k, nms_top_k, conf_thresh, nms_thresh, var0, var1,
                     d_out, counts_h ? d_cnt : nullptr, kept_prior_h ? d_kept : nullptr, d_ws, sz_ws, st);
     if (rc != FDT_OK) return rc;
-    FDT_CUDA(cudaMemcpyAsync(out_h, d_out, (size_t)B * C * top_k * 20, cudaMemcpyDeviceToHost, st));
+    if (!out_dev_view) FDT_CUDA(cudaMemcpyAsync(out_h, d_out, (size_t)B * C * top_k * 20, cudaMemcpyDeviceToHost, st));
     if (counts_h) FDT_CUDA(cudaMemcpyAsync(counts_h, d_cnt, (size_t)B * C * 4, cudaMemcpyDeviceToHost, st));
     if (kept_prior_h) FDT_CUDA(cudaMemcpyAsync(kept_prior_h, d_kept, (size_t)B * C * top_k * 8, cudaMemcpyDeviceToHost, st));
     FDT_CUDA(cudaStreamSynchronize(st));

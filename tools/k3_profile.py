@@ -19,7 +19,7 @@ args = [torch.from_numpy(a).cuda() for a in (loc, conf, pri)]
 for _ in range(3):
     det(*args)
 torch.cuda.synchronize()
-out = (C.c_longlong * 640)()
+out = (C.c_longlong * 1024)()
 _lib.check(_lib.lib().fdt_debug_k3_profile(out))
 names = ["minmax", "hist+scan(+select)", "scatter(+bitonic)", "-", "-", "win:rank", "win:decode+geom", "win:csr build",
          "win:A kept-query", "win:B window-query", "win:resolve", "output", "kept", "k", "rounds", "sweeps", "win:append",
@@ -36,4 +36,10 @@ import numpy as np
 cyc = np.array([out[64 + i] for i in range(256)]); cyc = cyc[cyc > 0]
 meta = np.array([out[320 + i] for i in range(256)])[:len(cyc)]
 print("per-CTA cycles: n=%d min=%d mean=%d max=%d (%.1f us)  rounds max=%d  k min/max=%d/%d" % (len(cyc), cyc.min(), cyc.mean(), cyc.max(), cyc.max() / 1965.0, (meta // 100000).max(), (meta % 100000).min(), (meta % 100000).max()))
+print("K2 on the same clock (ns): first block start %+d, last block end %+d" % (out[44] - out[40], out[45] - out[40]))
 print("globaltimer (ns): first CTA start 0, last CTA start +%d, first CTA end +%d, last CTA end +%d" % (out[41] - out[40], out[42] - out[40], out[43] - out[40]))
+
+print("phase B per warp (CTA 0): cycles", [out[640 + i] for i in range(32)])
+print("   visits sum", [out[672 + i] for i in range(32)])
+print("   visits max-lane", [out[704 + i] for i in range(32)])
+print("   chunks", [out[736 + i] for i in range(32)])
