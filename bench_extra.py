@@ -5,6 +5,7 @@
     python bench_extra.py tracker    # BASELINE config 4: IoU tracker, 10k frames x 1-300 detections
     python bench_extra.py detect1024 # BASELINE config 5 shape on one GPU: Detect B=64 @1024^2 (N=87,360)
     python bench_extra.py priorbox
+    python bench_extra.py heads      # Detect straight from the per-level NCHW head maps, B=64 @640^2
 
 Each prints one JSON line with device time (CUDA events, L2 flushed between repetitions), the algorithmic bytes of
 SURVEY 8(d) and the CPU oracle port timed on the host beside it."""
@@ -171,6 +172,70 @@ def priorbox():
     print(json.dumps({"workload": "PriorBoxLayer(640,640) x 6 levels (34,125 priors)", "ms_6_launches_incl_python": ms, "cpu_port_ms": cpu_s * 1e3}))
 
 
+def heads():
+    """Head maps -> detections, B=64 @640x640 (N=34,125): fused (fdt_detect_heads) vs materialise + Detect vs the reference's
+    torch ops (pyramid.py:291-309, 331-332 on CUDA tensors) + Detect."""
+    from fdt_b200.layers import Detect, heads_to_loc_conf
+    B = 64
+    loc_maps, conf_maps, neg_max = synth.head_maps(B, 640, 640, 6060)
+    pri = torch.from_numpy(synth.priors_numpy(640, 640)).cuda(); N = pri.shape[0]
+    lm, cm = [torch.from_numpy(m).cuda() for m in loc_maps], [torch.from_numpy(m).cuda() for m in conf_maps]
+    det = Detect(2, 0, 750, 0.05, 0.3)
+
+    def torch_heads():
+        loc, conf = [], []
+        for idx, (lx, tmp_conf) in enumerate(zip(lm, cm)):
+            if idx == 0:
+                a, b, c, pos_conf = tmp_conf.chunk(4, 1)
+                max_conf, _ = torch.cat([a, b, c], 1).max(1)
+                conf.append(torch.cat([max_conf.view_as(pos_conf), pos_conf], 1).permute(0, 2, 3, 1).contiguous())
+            else:
+                neg_conf, a, b, c = tmp_conf.chunk(4, 1)
+                max_conf, _ = torch.cat([a, b, c], 1).max(1)
+                conf.append(torch.cat([neg_conf, max_conf.view_as(neg_conf)], 1).permute(0, 2, 3, 1).contiguous())
+            loc.append(lx.permute(0, 2, 3, 1).contiguous())
+        loc = torch.cat([o.view(o.size(0), -1) for o in loc], 1).view(B, -1, 4)
+        conf = torch.softmax(torch.cat([o.view(o.size(0), -1) for o in conf], 1).view(B, -1, 2), -1)
+        return loc, conf
+
+    fused = det.detect_heads(lm, cm, pri)
+    assert torch.equal(fused, det(*heads_to_loc_conf(lm, cm, neg_max), pri))
+    # the timed calls go straight to the C ABI with prebuilt arguments (as bench.py does), so that the event pairs see device time
+    from fdt_b200.layers.functions.heads import _level_args
+    dev, _, _, keep, (lp, cp, fh, fw, nm, nl) = _level_args(lm, cm, neg_max)
+    L = _lib.lib()
+    out = torch.empty((B, 2, 750, 5), device=dev); loc_b = torch.empty((B, N, 4), device=dev); conf_b = torch.empty((B, N, 2), device=dev)
+    ws = _lib.workspace(L.fdt_detect_workspace_bytes(B, N, 2), dev, "hx")
+    st = _lib.stream_ptr()
+
+    def c_fused():
+        _lib.check(L.fdt_detect_heads(lp, cp, fh, fw, nm, nl, pri.data_ptr(), B, 750, 5000, 0.05, 0.3, 0.1, 0.2, out.data_ptr(), None, None,
+                                      ws.data_ptr(), ws.numel(), st))
+
+    def c_heads():
+        _lib.check(L.fdt_heads_to_loc_conf(lp, cp, fh, fw, nm, nl, B, 1, loc_b.data_ptr(), conf_b.data_ptr(), st))
+
+    def c_mat():
+        c_heads()
+        _lib.check(L.fdt_detect(loc_b.data_ptr(), conf_b.data_ptr(), pri.data_ptr(), B, N, 2, 750, 5000, 0.05, 0.3, 0.1, 0.2, out.data_ptr(),
+                                None, None, ws.data_ptr(), ws.numel(), st))
+    c_fused()
+    assert torch.equal(out, fused)
+    ms_f, min_f = timed(c_fused)
+    ms_m, _ = timed(c_mat)
+    ms_h, _ = timed(c_heads)
+    ms_t, _ = timed(lambda: det(*torch_heads(), pri))
+    ms_th, _ = timed(torch_heads)
+    alg = B * (32 * N + 30000) + 16 * N            # conf maps 16 B + loc maps 16 B per prior, output rows, priors once
+    cand = float((fused[:, 1, :, 0] > 0).sum(1).float().mean())
+    print(json.dumps({"workload": "Detect from per-level NCHW head maps (max-in-out + permute/cat + softmax fused), B=64 @640x640, N=34,125",
+                      "fused_ms": ms_f, "fused_ms_min": min_f, "frames_per_s": B / (ms_f * 1e-3),
+                      "materialise_then_detect_ms": ms_m, "heads_to_loc_conf_ms": ms_h,
+                      "torch_head_ops_then_detect_ms": ms_t, "torch_head_ops_ms": ms_th,
+                      "algorithmic_bytes": alg, "roofline_frac_of_measured_hbm": alg / (ms_f * 1e-3) / 1e9 / PEAK,
+                      "rows_kept_per_image": cand}))
+
+
 if __name__ == "__main__":
-    for w in sys.argv[1:] or ["multibox", "tracker", "detect1024", "priorbox"]:
+    for w in sys.argv[1:] or ["multibox", "tracker", "detect1024", "priorbox", "heads"]:
         globals()[w]()

@@ -44,6 +44,77 @@ constexpr int SEG_SLOTS = 8;                    // phase B: row segments a lane 
 
 enum { MODE_DETECT = 0, MODE_NMS = 1 };
 
+// ------------------------------------------------------------------------------------------- head maps
+// The models hand Detect the outputs of their prediction convolutions, per pyramid level and NCHW: loc_l[B,4,H,W] and the
+// 4-channel max-in-out confidence conf_l[B,4,H,W] (pyramid.py:291-306).  The reference turns them into loc[B,N,4] and
+// conf[B,N,2] with chunk / max / cat / permute / contiguous / view / cat and a 2-way softmax (pyramid.py:293-309, 331-332);
+// the kernels below read the maps directly.  Prior n of level l sits at pixel q = n - off[l] (y outer, x inner).
+constexpr int FDT_MAX_LEVELS = 8;
+struct HeadLevels {
+    const float *conf[FDT_MAX_LEVELS];     // [B,4,hw] per level
+    const float *loc[FDT_MAX_LEVELS];      // [B,4,hw] per level
+    int hw[FDT_MAX_LEVELS];
+    int off[FDT_MAX_LEVELS + 1];           // first prior of each level; off[L] = N
+    int neg_max[FDT_MAX_LEVELS];           // 1: neg = max(ch0..2), pos = ch3 (pyramid.py:293-297); 0: neg = ch0, pos = max(ch1..3) (:299-304)
+    int L;
+};
+__device__ __forceinline__ int head_level(const HeadLevels &h, const int p)
+{
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < FDT_MAX_LEVELS; ++q) l += (q < h.L && p >= h.off[q]) ? 1 : 0;
+    return l;
+}
+// torch.max over a dimension propagates NaN
+__device__ __forceinline__ float nanmax(const float a, const float b) { return (a > b || a != a) ? a : b; }
+// (neg, pos) logits of prior p of image b: the max-in-out reduction
+__device__ __forceinline__ float2 head_logits(const HeadLevels &h, const int b, const int p)
+{
+    const int l = head_level(h, p);
+    const int hw = h.hw[l];
+    const float *c = h.conf[l] + (int64_t)b * 4 * hw + (p - h.off[l]);
+    const float c0 = __ldg(c), c1 = __ldg(c + hw), c2 = __ldg(c + 2 * hw), c3 = __ldg(c + 3 * hw);
+    if (h.neg_max[l]) return make_float2(nanmax(nanmax(c0, c1), c2), c3);
+    return make_float2(c0, nanmax(nanmax(c1, c2), c3));
+}
+// nn.Softmax(dim=-1) over (neg, pos): exp(x - max) / sum, exp evaluated in fp64 and rounded once (library convention), fp32
+// sum and IEEE division.  The larger element contributes exp(0) = 1 exactly, so ONE exp is evaluated; if neither argument
+// is zero a NaN or inf - inf is involved and the sum -- hence both outputs -- is NaN whatever the other term is.
+__device__ __forceinline__ float2 softmax2(const float2 x)
+{
+    const float m = nanmax(x.x, x.y);
+    const float a0 = x.x - m, a1 = x.y - m;
+    const bool z0 = a0 == 0.0f, z1 = a1 == 0.0f;
+    if (!z0 && !z1) return make_float2(NAN, NAN);
+    const float e = fdt_expf_cr(z0 ? a1 : a0);
+    const float e0 = z0 ? 1.0f : e, e1 = z0 ? e : 1.0f;
+    const float sum = e0 + e1;
+    return make_float2(e0 / sum, e1 / sum);
+}
+__device__ __forceinline__ float4 head_loc_row(const HeadLevels &h, const int b, const int p)
+{
+    const int l = head_level(h, p);
+    const int hw = h.hw[l];
+    const float *c = h.loc[l] + (int64_t)b * 4 * hw + (p - h.off[l]);
+    return make_float4(__ldg(c), __ldg(c + hw), __ldg(c + 2 * hw), __ldg(c + 3 * hw));
+}
+
+// Materialises the reference's tensors: loc_out[B,N,4] and conf_out[B,N,2] (softmax applied iff `softmax`; the training
+// path keeps raw logits, pyramid.py:339-346).  Either output may be null.
+__global__ void __launch_bounds__(256)
+k_heads_to_loc_conf(const HeadLevels h, const int N, const int softmax, float *__restrict__ loc_out, float *__restrict__ conf_out)
+{
+    const int b = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    if (conf_out) {
+        float2 x = head_logits(h, b, p);
+        if (softmax) x = softmax2(x);
+        reinterpret_cast<float2 *>(conf_out)[(int64_t)b * N + p] = x;
+    }
+    if (loc_out) reinterpret_cast<float4 *>(loc_out)[(int64_t)b * N + p] = head_loc_row(h, b, p);
+}
+
 // ------------------------------------------------------------------------------------------- K2
 // Clears the per-list counters.  A kernel rather than cudaMemsetAsync so that k_threshold_compact can be launched behind it
 // with programmatic stream serialization: its blocks start and stream `conf` while this grid is still in flight (a memset
@@ -55,9 +126,122 @@ __global__ void k_zero_counters(int32_t *__restrict__ counters, int n)
     if (i < n) counters[i] = 0;
 }
 
-template <bool C2>
+// K2 for head maps (fdt_detect_heads): max-in-out + softmax + threshold + compaction.  The exact softmax costs an fp64 exp,
+// so a block first screens its tile with the logit gap alone (pos - neg > logit(thr) - margin: a superset of the
+// candidates, ~1/4 of the priors on the headline workload) while parking the logits in shared memory, lists the survivors
+// densely, and only those get the exact score, the exact `score > thr` test and a key.  One global atomic per block, as in K2.
+// 9 priors per thread: 15 tiles per 640x640 image, so that B = 64 is a single wave at 7 blocks per SM.
+constexpr int K2H_PER_THREAD = 9;
+constexpr int K2H_TILE = K2_THREADS * K2H_PER_THREAD;
+__global__ void __launch_bounds__(K2_THREADS, 7)
+k_heads_threshold_compact(const HeadLevels hl, const int64_t N, const float thr, const float dcut,
+                          int32_t *__restrict__ counters, uint64_t *__restrict__ keys, long long *prof)
+{
+    unsigned long long gt0 = 0;
+    if (prof && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
+    cudaTriggerProgrammaticLaunchCompletion();
+    const int b = blockIdx.y, lists = gridDim.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t base = (int64_t)blockIdx.x * K2H_TILE;
+    __shared__ int s_warp[K2_THREADS / 32];
+    __shared__ unsigned s_wmax[K2_THREADS / 32], s_wminv[K2_THREADS / 32];
+    __shared__ int s_base, s_total;
+    __shared__ uint16_t s_i[K2H_TILE];                   // tile-local indices of the screened priors, dense
+    __shared__ unsigned long long s_x[K2H_TILE];         // (neg, pos) logits per tile slot; then the key of a candidate (0: rejected)
+
+    // ---- screen
+    unsigned bal[K2H_PER_THREAD];
+    int wtotal = 0;
+#pragma unroll
+    for (int u = 0; u < K2H_PER_THREAD; ++u) {
+        const int64_t p = base + u * K2_THREADS + tid;
+        bool maybe = false;
+        if (p < N) {
+            const float2 lg = head_logits(hl, b, (int)p);
+            maybe = (lg.y - lg.x) > dcut;
+            s_x[u * K2_THREADS + tid] = ((unsigned long long)__float_as_uint(lg.y) << 32) | __float_as_uint(lg.x);
+        }
+        bal[u] = __ballot_sync(0xffffffffu, maybe);
+        wtotal += __popc(bal[u]);
+    }
+    if (lane == 0) s_warp[warp] = wtotal;
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < K2_THREADS / 32; ++w) { const int c = s_warp[w]; s_warp[w] = tot; tot += c; }
+        s_total = tot;
+    }
+    __syncthreads();
+    {
+        int off = s_warp[warp];
+#pragma unroll
+        for (int u = 0; u < K2H_PER_THREAD; ++u) {
+            if ((bal[u] >> lane) & 1u) s_i[off + __popc(bal[u] & ((1u << lane) - 1u))] = (uint16_t)(u * K2_THREADS + tid);
+            off += __popc(bal[u]);
+        }
+    }
+    __syncthreads();
+    // ---- exact score of the screened priors (dense lanes); each listed slot belongs to exactly one entry
+    const int M = s_total;
+    int mine = 0;
+    unsigned kmx = 0u, kmnv = 0u;
+    for (int e = tid; e < M; e += K2_THREADS) {
+        const int sl = s_i[e];
+        const unsigned long long x = s_x[sl];
+        const float sc = softmax2(make_float2(__uint_as_float((unsigned)x), __uint_as_float((unsigned)(x >> 32)))).y;
+        unsigned long long key = 0ull;
+        if (sc > thr) {                                              // detection.py:64 strict gt
+            const unsigned kk = fdt_float_key(sc);
+            key = ((unsigned long long)kk << 32) | (unsigned)(base + sl);
+            kmx = max(kmx, kk); kmnv = max(kmnv, ~kk);
+            ++mine;
+        }
+        s_x[sl] = key;                                               // a key is never 0: its score half has the sign bit set
+    }
+    // ---- block-exclusive scan of the per-thread candidate counts, one atomic, scatter
+    int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    kmx = __reduce_max_sync(0xffffffffu, kmx); kmnv = __reduce_max_sync(0xffffffffu, kmnv);
+    __syncthreads();                                                 // s_warp (screen offsets) is free again
+    if (lane == 31) s_warp[warp] = inc;
+    if (lane == 0) { s_wmax[warp] = kmx; s_wminv[warp] = kmnv; }
+    cudaGridDependencySynchronize();                                 // k_zero_counters has completed
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+        unsigned bmx = 0u, bmnv = 0u;
+#pragma unroll
+        for (int w = 0; w < K2_THREADS / 32; ++w) {
+            const int c = s_warp[w]; s_warp[w] = tot; tot += c;
+            bmx = max(bmx, s_wmax[w]); bmnv = max(bmnv, s_wminv[w]);
+        }
+        s_base = tot ? atomicAdd(&counters[b], tot) : 0;
+        if (tot) {
+            atomicMax(reinterpret_cast<unsigned *>(counters) + lists + b, bmx);
+            atomicMax(reinterpret_cast<unsigned *>(counters) + 2 * lists + b, bmnv);
+        }
+    }
+    __syncthreads();
+    {
+        uint64_t *kl = keys + (int64_t)b * N + s_base + s_warp[warp] + (inc - mine);
+        for (int e = tid; e < M; e += K2_THREADS) {
+            const unsigned long long key = s_x[s_i[e]];
+            if (key) *kl++ = key;
+        }
+    }
+    if (prof && threadIdx.x == 0) {
+        unsigned long long gt1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        atomicMin((unsigned long long *)&prof[44], gt0); atomicMax((unsigned long long *)&prof[45], gt1);
+    }
+}
+
+// SRC 0: conf[B,N,C] with C > 2; 1: conf[B,N,2]
+template <int SRC>
 __global__ void __launch_bounds__(K2_THREADS)
-k_threshold_compact(const float *__restrict__ conf, int64_t N, int C, float thr,
+k_threshold_compact(const float *__restrict__ conf, const HeadLevels hl, int64_t N, int C, float thr,
                     int32_t *__restrict__ counters, uint64_t *__restrict__ keys, long long *prof)
 {
     unsigned long long gt0 = 0;
@@ -84,8 +268,8 @@ k_threshold_compact(const float *__restrict__ conf, int64_t N, int C, float thr,
             float s = 0.0f;
             bool in = p < N;
             if (in) {
-                if (C2) s = __ldg(reinterpret_cast<const float2 *>(cb) + p).y;
-                else    s = __ldg(cb + p * C + cl);
+                if (SRC == 1) s = __ldg(reinterpret_cast<const float2 *>(cb) + p).y;
+                else s = __ldg(cb + p * C + cl);
             }
             sc[u] = s;
             const bool cand = in && s > thr;                         // detection.py:64 strict gt
@@ -170,7 +354,7 @@ struct SortNmsParams {
     const uint64_t *keys;       // [lists, key_stride]
     const int32_t *counters;    // [3][lists] (MODE_DETECT): candidate count, max key, ~min key
     int64_t key_stride;
-    const float *loc;           // [B,N,4]  (MODE_DETECT)
+    const float *loc;           // [B,N,4]  (MODE_DETECT); null: gather the rows from the head maps `hl`
     const float *priors;        // [N,4]    (MODE_DETECT)
     const float *boxes;         // [n,4]    (MODE_NMS)
     int64_t N;
@@ -192,6 +376,7 @@ struct SortNmsParams {
     float *g_karea;
     uint64_t *g_kkey;
     SmemPlan sm;
+    HeadLevels hl;              // per-level NCHW loc maps (MODE_DETECT with loc == null)
     long long *prof;            // diagnostics: per-phase clock64 of CTA 0 (null unless FDT_K3_PROFILE=1)
 };
 
@@ -674,7 +859,7 @@ k_sort_nms(const SortNmsParams P)
                 key = skeys[j];
                 const uint32_t p = (uint32_t)key;
                 if (MODE == MODE_DETECT) {
-                    ld0 = __ldg(reinterpret_cast<const float4 *>(P.loc) + ((int64_t)b * P.N + p));
+                    ld0 = P.loc ? __ldg(reinterpret_cast<const float4 *>(P.loc) + ((int64_t)b * P.N + p)) : head_loc_row(P.hl, b, (int)p);
                     ld1 = __ldg(reinterpret_cast<const float4 *>(P.priors) + p);
                 } else {
                     ld0 = __ldg(reinterpret_cast<const float4 *>(P.boxes) + p);
@@ -1097,15 +1282,15 @@ static int detect_check_common(const char *who, int B, int64_t N, int C, const v
     return FDT_OK;
 }
 
-FDT_API int fdt_detect_threshold_compact(const float *conf, int B, int64_t N, int C, float conf_thresh,
-                                         void *ws, size_t ws_bytes, fdt_stream_t stream)
+static int threshold_compact_impl(const float *conf, const HeadLevels *heads, int B, int64_t N, int C, float conf_thresh,
+                                  void *ws, size_t ws_bytes, fdt_stream_t stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = detect_check_common("fdt_detect_threshold_compact", B, N, C, ws, ws_bytes);
     if (rc != FDT_OK) return rc;
     const int lists = B * (C - 1);
     if (lists == 0 || N == 0) return FDT_OK;
-    FDT_REQUIRE(conf && fdt_aligned(conf, 8), FDT_E_INVALID, "fdt_detect_threshold_compact: conf null or not 8-byte aligned");
+    FDT_REQUIRE(heads || (conf && fdt_aligned(conf, 8)), FDT_E_INVALID, "fdt_detect_threshold_compact: conf null or not 8-byte aligned");
     int32_t *counters = (int32_t *)ws;
     uint64_t *keys = (uint64_t *)((char *)ws + fdt_align256((size_t)3 * lists * sizeof(int32_t)));
     long long *prof = nullptr;
@@ -1124,8 +1309,9 @@ FDT_API int fdt_detect_threshold_compact(const float *conf, int B, int64_t N, in
             const char *e = getenv("FDT_K2_CARVEOUT");
             const int pct = e ? atoi(e) : 100;
             if (pct >= 0) {
-                FDT_CUDA(cudaFuncSetAttribute(k_threshold_compact<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-                FDT_CUDA(cudaFuncSetAttribute(k_threshold_compact<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+                FDT_CUDA(cudaFuncSetAttribute(k_threshold_compact<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+                FDT_CUDA(cudaFuncSetAttribute(k_threshold_compact<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+                FDT_CUDA(cudaFuncSetAttribute(k_heads_threshold_compact, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
             }
             carveout_set = true;
         }
@@ -1138,11 +1324,27 @@ FDT_API int fdt_detect_threshold_compact(const float *conf, int B, int64_t N, in
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         const int64_t N_ = N;
-        if (C == 2) FDT_CUDA(cudaLaunchKernelEx(&cfg, k_threshold_compact<true>, conf, N_, C, conf_thresh, counters, keys, prof));
-        else        FDT_CUDA(cudaLaunchKernelEx(&cfg, k_threshold_compact<false>, conf, N_, C, conf_thresh, counters, keys, prof));
+        HeadLevels hl{};
+        if (heads) hl = *heads;
+        if (heads) {
+            // screening cut on the logit gap: sigmoid(gap) > thr needs gap > logit(thr); 1e-3 covers every rounding on either side
+            float dcut = -INFINITY;
+            if (conf_thresh > 1e-4f && conf_thresh < 1.0f - 1e-4f) dcut = logf(conf_thresh / (1.0f - conf_thresh)) - 1e-3f;
+            else if (conf_thresh >= 1.0f - 1e-4f) dcut = 9.0f;          // sigmoid(9) < 1 - 1e-4: nothing at or below can pass
+            cfg.gridDim = dim3((unsigned)((N + K2H_TILE - 1) / K2H_TILE), (unsigned)B);
+            FDT_CUDA(cudaLaunchKernelEx(&cfg, k_heads_threshold_compact, hl, N_, conf_thresh, dcut, counters, keys, prof));
+        }
+        else if (C == 2) FDT_CUDA(cudaLaunchKernelEx(&cfg, k_threshold_compact<1>, conf, hl, N_, C, conf_thresh, counters, keys, prof));
+        else             FDT_CUDA(cudaLaunchKernelEx(&cfg, k_threshold_compact<0>, conf, hl, N_, C, conf_thresh, counters, keys, prof));
     }
     FDT_LAUNCH_CHECK();
     return FDT_OK;
+}
+
+FDT_API int fdt_detect_threshold_compact(const float *conf, int B, int64_t N, int C, float conf_thresh,
+                                         void *ws, size_t ws_bytes, fdt_stream_t stream)
+{
+    return threshold_compact_impl(conf, nullptr, B, N, C, conf_thresh, ws, ws_bytes, stream);
 }
 
 FDT_API int fdt_detect_candidate_counts(const void *ws, int B, int C, int32_t *counts_out, fdt_stream_t stream)
@@ -1153,7 +1355,7 @@ FDT_API int fdt_detect_candidate_counts(const void *ws, int B, int C, int32_t *c
     return FDT_OK;
 }
 
-static int detect_sort_nms_impl(const float *loc, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
+static int detect_sort_nms_impl(const float *loc, const HeadLevels *heads, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
                                 float nms_thresh, float var0, float var1,
                                 float *out, int32_t *counts, int64_t *kept_prior,
                                 const unsigned long long *peer_out, int n_peers, int64_t img_offset,
@@ -1176,13 +1378,14 @@ static int detect_sort_nms_impl(const float *loc, const float *priors, int B, in
         if (kept_prior) FDT_CUDA(cudaMemsetAsync(kept_prior, 0xff, sizeof(int64_t) * (size_t)B * C * top_k, st));
         return FDT_OK;
     }
-    FDT_REQUIRE(loc && priors && fdt_aligned(loc, 16) && fdt_aligned(priors, 16), FDT_E_INVALID,
+    FDT_REQUIRE((heads || (loc && fdt_aligned(loc, 16))) && priors && fdt_aligned(priors, 16), FDT_E_INVALID,
                 "fdt_detect: loc/priors null or not 16-byte aligned");
     int32_t *counters = (int32_t *)ws;
     uint64_t *keys = (uint64_t *)((char *)ws + fdt_align256((size_t)3 * lists * sizeof(int32_t)));
     SortNmsParams P{};
     P.keys = keys; P.counters = counters; P.key_stride = N;
-    P.loc = loc; P.priors = priors; P.N = N; P.C = C;
+    P.loc = heads ? nullptr : loc; P.priors = priors; P.N = N; P.C = C;
+    if (heads) P.hl = *heads;
     P.nms_top_k = nms_top_k; P.max_keep = top_k < nms_top_k ? top_k : nms_top_k; P.top_k = top_k;
     P.nms_thresh = nms_thresh; P.v0 = var0; P.v1 = var1;
     P.out = out; P.counts = counts; P.kept_prior = kept_prior;
@@ -1199,7 +1402,7 @@ FDT_API int fdt_detect_sort_nms(const float *loc, const float *priors, int B, in
                                 float *out, int32_t *counts, int64_t *kept_prior,
                                 void *ws, size_t ws_bytes, fdt_stream_t stream)
 {
-    return detect_sort_nms_impl(loc, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1, out, counts, kept_prior,
+    return detect_sort_nms_impl(loc, nullptr, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1, out, counts, kept_prior,
                                 nullptr, 0, 0, ws, ws_bytes, stream);
 }
 
@@ -1209,7 +1412,7 @@ FDT_API int fdt_detect_sort_nms_peers(const float *loc, const float *priors, int
                                       void *ws, size_t ws_bytes, fdt_stream_t stream)
 {
     FDT_REQUIRE(peer_out_ptrs != nullptr && n_peers >= 1 && image_offset >= 0, FDT_E_INVALID, "fdt_detect_sort_nms_peers: bad peer arguments");
-    return detect_sort_nms_impl(loc, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1, nullptr, nullptr, nullptr,
+    return detect_sort_nms_impl(loc, nullptr, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1, nullptr, nullptr, nullptr,
                                 (const unsigned long long *)peer_out_ptrs, n_peers, image_offset, ws, ws_bytes, stream);
 }
 
@@ -1223,6 +1426,70 @@ FDT_API int fdt_detect(const float *loc, const float *conf, const float *priors,
     if (rc != FDT_OK) return rc;
     return fdt_detect_sort_nms(loc, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1,
                                out, counts, kept_prior, ws, ws_bytes, stream);
+}
+
+// ---- head maps -> Detect (pyramid.py:291-309, 331-338)
+static int heads_fill(HeadLevels &hl, const char *who, const float *const *loc_maps_h, const float *const *conf_maps_h,
+                      const int *f_h, const int *f_w, const int *neg_max_h, int n_levels, int64_t *N_out)
+{
+    FDT_REQUIRE(n_levels >= 1 && n_levels <= FDT_MAX_LEVELS, FDT_E_UNSUPPORTED, "%s: n_levels=%d outside [1,%d]", who, n_levels, FDT_MAX_LEVELS);
+    FDT_REQUIRE(f_h && f_w && neg_max_h, FDT_E_INVALID, "%s: null level description", who);
+    int64_t off = 0;
+    hl = HeadLevels{};
+    hl.L = n_levels;
+    for (int l = 0; l < n_levels; ++l) {
+        FDT_REQUIRE(f_h[l] >= 1 && f_w[l] >= 1, FDT_E_INVALID, "%s: level %d is %dx%d", who, l, f_h[l], f_w[l]);
+        hl.conf[l] = conf_maps_h ? conf_maps_h[l] : nullptr;
+        hl.loc[l] = loc_maps_h ? loc_maps_h[l] : nullptr;
+        hl.hw[l] = f_h[l] * f_w[l];
+        hl.off[l] = (int)off;
+        hl.neg_max[l] = neg_max_h[l] ? 1 : 0;
+        off += (int64_t)f_h[l] * f_w[l];
+        FDT_REQUIRE(off < (1ll << 31), FDT_E_UNSUPPORTED, "%s: more than 2^31-1 priors", who);
+    }
+    for (int l = n_levels; l <= FDT_MAX_LEVELS; ++l) hl.off[l] = (int)off;
+    *N_out = off;
+    return FDT_OK;
+}
+
+FDT_API int fdt_heads_to_loc_conf(const float *const *loc_maps_h, const float *const *conf_maps_h,
+                                  const int *f_h, const int *f_w, const int *neg_max_h, int n_levels, int B, int softmax,
+                                  float *loc_out, float *conf_out, fdt_stream_t stream)
+{
+    HeadLevels hl;
+    int64_t N = 0;
+    int rc = heads_fill(hl, "fdt_heads_to_loc_conf", loc_maps_h, conf_maps_h, f_h, f_w, neg_max_h, n_levels, &N);
+    if (rc != FDT_OK) return rc;
+    FDT_REQUIRE(B >= 0, FDT_E_INVALID, "fdt_heads_to_loc_conf: B=%d", B);
+    if (B == 0 || (!loc_out && !conf_out)) return FDT_OK;
+    for (int l = 0; l < n_levels; ++l) {
+        FDT_REQUIRE(!loc_out || hl.loc[l], FDT_E_INVALID, "fdt_heads_to_loc_conf: loc map %d is null", l);
+        FDT_REQUIRE(!conf_out || hl.conf[l], FDT_E_INVALID, "fdt_heads_to_loc_conf: conf map %d is null", l);
+    }
+    FDT_REQUIRE((!loc_out || fdt_aligned(loc_out, 16)) && (!conf_out || fdt_aligned(conf_out, 8)), FDT_E_INVALID,
+                "fdt_heads_to_loc_conf: outputs need 16 / 8-byte alignment");
+    dim3 g((unsigned)((N + 255) / 256), (unsigned)B);
+    k_heads_to_loc_conf<<<g, 256, 0, (cudaStream_t)stream>>>(hl, (int)N, softmax, loc_out, conf_out);
+    FDT_LAUNCH_CHECK();
+    return FDT_OK;
+}
+
+FDT_API int fdt_detect_heads(const float *const *loc_maps_h, const float *const *conf_maps_h,
+                             const int *f_h, const int *f_w, const int *neg_max_h, int n_levels, const float *priors,
+                             int B, int top_k, int nms_top_k, float conf_thresh, float nms_thresh, float var0, float var1,
+                             float *out, int32_t *counts, int64_t *kept_prior, void *ws, size_t ws_bytes, fdt_stream_t stream)
+{
+    HeadLevels hl;
+    int64_t N = 0;
+    int rc = heads_fill(hl, "fdt_detect_heads", loc_maps_h, conf_maps_h, f_h, f_w, neg_max_h, n_levels, &N);
+    if (rc != FDT_OK) return rc;
+    FDT_REQUIRE(loc_maps_h && conf_maps_h, FDT_E_INVALID, "fdt_detect_heads: null map arrays");
+    for (int l = 0; l < n_levels; ++l)
+        FDT_REQUIRE(hl.loc[l] && hl.conf[l], FDT_E_INVALID, "fdt_detect_heads: map %d is null", l);
+    rc = threshold_compact_impl(nullptr, &hl, B, N, 2, conf_thresh, ws, ws_bytes, stream);
+    if (rc != FDT_OK) return rc;
+    return detect_sort_nms_impl(nullptr, &hl, priors, B, N, 2, top_k, nms_top_k, nms_thresh, var0, var1, out, counts, kept_prior,
+                                nullptr, 0, 0, ws, ws_bytes, stream);
 }
 
 // Diagnostics: with FDT_K3_PROFILE=1 in the environment, CTA 0 of k_sort_nms records clock64 deltas per phase:

@@ -71,6 +71,32 @@ class Detect:
                                     _lib.ptr(counts), _lib.ptr(kept), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
         return (out, counts, kept) if return_aux else out
 
+    def detect_heads(self, loc_maps, conf_maps, prior_data, neg_max=None, return_aux=False):
+        """Detect straight from the models' per-level NCHW prediction maps (loc_l[B,4,H,W], 4-channel max-in-out
+        conf_l[B,4,H,W]): the max-in-out reduction, NHWC permute/concat and the 2-way softmax of
+        pyramid.py:291-309, 331-332 are fused into the threshold kernel, and NMS gathers the loc rows it decodes
+        from the maps -- loc[B,N,4] / conf[B,N,2] are never materialised.  Same output as
+        self(*heads_to_loc_conf(loc_maps, conf_maps), prior_data)."""
+        from .heads import _level_args
+        dev, num, num_priors, keep, (lp, cp, fh, fw, nm, L) = _level_args(loc_maps, conf_maps, neg_max)
+        if self.num_classes != 2:
+            raise NotImplementedError("detect_heads: the max-in-out heads are two-class (background / face)")
+        if prior_data.size(0) != num_priors:
+            raise ValueError(f"detect_heads: {prior_data.size(0)} priors for {num_priors} map positions")
+        with torch.cuda.device(dev):
+            pri = _lib.dev_f32(prior_data, dev).view(num_priors, 4)
+            out = torch.empty((num, 2, self.top_k, 5), dtype=torch.float32, device=dev)
+            counts = torch.empty((num, 2), dtype=torch.int32, device=dev) if return_aux else None
+            kept = torch.empty((num, 2, self.top_k), dtype=torch.int64, device=dev) if return_aux else None
+            Lb = _lib.lib()
+            ws = _lib.workspace(Lb.fdt_detect_workspace_bytes(num, num_priors, 2), dev, "detect")
+            _lib.check(Lb.fdt_detect_heads(lp, cp, fh, fw, nm, L, _lib.ptr(pri), num, int(self.top_k), int(self.nms_top_k),
+                                           float(self.conf_thresh), float(self.nms_thresh), float(self.variance[0]),
+                                           float(self.variance[1]), _lib.ptr(out), _lib.ptr(counts), _lib.ptr(kept),
+                                           _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        del keep
+        return (out, counts, kept) if return_aux else out
+
     def _call_host(self, loc_data, conf_data, prior_data, args, return_aux):
         num, num_priors, C_ = args[0], args[1], args[2]
         loc = loc_data.detach().to(torch.float32).contiguous()

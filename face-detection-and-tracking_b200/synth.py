@@ -130,3 +130,24 @@ def digest(*arrays):
         a = np.ascontiguousarray(a)
         h.update(str(a.dtype).encode()); h.update(str(a.shape).encode()); h.update(a.tobytes())
     return h.hexdigest()
+
+
+def head_maps(B, width, height, seed, strides=STRIDES6):
+    """Synthetic outputs of the models' prediction convolutions (pyramid.py:291-306), per level and NCHW:
+    loc_l[B,4,H,W] ~ 0.5*N(0,1) and the 4-channel max-in-out confidence conf_l[B,4,H,W].  The (neg, pos) logits after
+    the max-in-out reduction have neg ~ N(0,1) and gap pos - neg ~ N(-4.5, 2) like detect_inputs(mode="random");
+    the channels that lose the max sit up to 2 below it.  Returns (loc_maps, conf_maps, neg_max)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    loc_maps, conf_maps, neg_max = [], [], []
+    for lvl, (fw, fh) in enumerate(feature_maps(width, height, strides)):
+        loc_maps.append((rng.standard_normal((B, 4, fh, fw), dtype=np.float32) * np.float32(0.5)).astype(np.float32))
+        neg = rng.standard_normal((B, fh, fw), dtype=np.float32)
+        pos = (neg + rng.standard_normal((B, fh, fw), dtype=np.float32) * np.float32(2.0) - np.float32(4.5)).astype(np.float32)
+        top = neg if lvl == 0 else pos                      # the logit that is a max over three channels
+        three = top[:, None] - rng.uniform(0.0, 2.0, (B, 3, fh, fw)).astype(np.float32)
+        win = rng.integers(0, 3, (B, fh, fw))
+        np.put_along_axis(three, win[:, None], top[:, None], axis=1)
+        conf = np.concatenate([three, pos[:, None]], 1) if lvl == 0 else np.concatenate([neg[:, None], three], 1)
+        conf_maps.append(np.ascontiguousarray(conf, dtype=np.float32))
+        neg_max.append(1 if lvl == 0 else 0)
+    return loc_maps, conf_maps, neg_max

@@ -128,8 +128,29 @@ int fdt_detect_sort_nms_peers(const float *loc, const float *priors, int B, int6
 /* Number of candidates per (image, class>=1) list after stage 1: copies B*(C-1) int32 to counts_out (device). */
 int fdt_detect_candidate_counts(const void *ws, int B, int C, int32_t *counts_out, fdt_stream_t stream);
 
+/* ----  head post-processing that feeds Detect  (pyramid.py:291-309, 331-338; same code in
+ * pyramid_mobile_try1.py:297-327, pyramid_mb2_try3/4/5.py) -------------------------------------------------------------
+ * The models produce, per pyramid level l, NCHW maps loc_l[B,4,H_l,W_l] and the 4-channel max-in-out confidence
+ * conf_l[B,4,H_l,W_l].  The reference reduces the confidence to (neg, pos) with chunk/max/cat -- neg = max(ch0..2),
+ * pos = ch3 where neg_max_h[l] != 0 (level 0, pyramid.py:293-297), else neg = ch0, pos = max(ch1..3) (:299-304; torch.max
+ * propagates NaN) --, permutes both to NHWC, concatenates the levels into loc[B,N,4] / conf[B,N,2] (N = sum H_l*W_l, y
+ * outer, x inner) and applies nn.Softmax(dim=-1) in the test phase (:331-332).
+ *   loc_maps_h / conf_maps_h : HOST arrays of n_levels DEVICE pointers; f_h / f_w / neg_max_h : HOST int arrays.
+ * fdt_heads_to_loc_conf materialises the reference's tensors (either output may be null; softmax != 0 applies the
+ * softmax, the training path keeps raw logits).  fdt_detect_heads == fdt_heads_to_loc_conf(softmax) + fdt_detect with
+ * nothing materialised: the threshold kernel reads the conf maps (max-in-out + softmax fused), NMS gathers the loc rows
+ * it decodes from the loc maps.  Softmax: exp(x - max) in fp64 rounded once, fp32 sum and IEEE division.
+ * Workspace of fdt_detect_heads: fdt_detect_workspace_bytes(B, N, 2).  Limit: n_levels <= 8. */
+int fdt_heads_to_loc_conf(const float *const *loc_maps_h, const float *const *conf_maps_h,
+                          const int *f_h, const int *f_w, const int *neg_max_h, int n_levels, int B, int softmax,
+                          float *loc_out, float *conf_out, fdt_stream_t stream);
+int fdt_detect_heads(const float *const *loc_maps_h, const float *const *conf_maps_h,
+                     const int *f_h, const int *f_w, const int *neg_max_h, int n_levels, const float *priors,
+                     int B, int top_k, int nms_top_k, float conf_thresh, float nms_thresh, float var0, float var1,
+                     float *out, int32_t *counts, int64_t *kept_prior, void *ws, size_t ws_bytes, fdt_stream_t stream);
+
 /* Diagnostics (FDT_K3_PROFILE=1): per-phase clock64 deltas of CTA 0 of the last fdt_detect_sort_nms / fdt_nms launch. */
-int fdt_debug_k3_profile(long long *out640_h);   /* [0..31] phases of CTA 0, [64..319] cycles per CTA, [320..575] rounds*1e5 + k per CTA */
+int fdt_debug_k3_profile(long long *out1024_h);  /* [0..31] phases of CTA 0, [64..319] cycles per CTA, [320..575] rounds*1e5 + k per CTA, [640..767] phase-B per warp */
 
 /* ---- host-buffer variants (the reference-facing call when tensors live on the CPU) --------------
  * All pointers are HOST pointers (pinned memory makes the copies asynchronous).  The context owns

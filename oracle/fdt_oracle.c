@@ -581,3 +581,46 @@ ORC_API int64_t orc_iou_track(const double *dets, const int64_t *frame_off, int6
     (void)total;
     return T;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Head post-processing that feeds Detect / MultiBoxLoss  (pyramid.py:291-309, 331-332; identical
+ * code in pyramid_mobile_try1.py:297-327 and pyramid_mb2_try3/4/5.py).
+ * Per level l: conf map [B,4,H,W] -> (neg, pos): level with neg_max[l] != 0 has neg = max(ch0..2),
+ * pos = ch3 (:293-297), the others neg = ch0, pos = max(ch1..3) (:299-304); torch.max propagates
+ * NaN.  permute(0,2,3,1) + view + cat = prior index n = off[l] + y*W + x.  softmax != 0 applies
+ * nn.Softmax(dim=-1) (:332): exp(x - max) / sum, exp per this file's convention (fp64, one rounding).
+ * ------------------------------------------------------------------------------------------ */
+ORC_API void orc_heads_to_loc_conf(const float *const *loc_maps, const float *const *conf_maps,
+                                   const int *f_h, const int *f_w, const int *neg_max, int n_levels, int B,
+                                   int softmax, float *loc_out, float *conf_out)
+{
+    int64_t N = 0;
+    for (int l = 0; l < n_levels; ++l) N += (int64_t)f_h[l] * f_w[l];
+    int64_t off = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        const int64_t hw = (int64_t)f_h[l] * f_w[l];
+        for (int b = 0; b < B; ++b)
+            for (int64_t q = 0; q < hw; ++q) {
+                const int64_t n = (int64_t)b * N + off + q;
+                if (conf_out) {
+                    const float *c = conf_maps[l] + (int64_t)b * 4 * hw + q;
+                    const float c0 = c[0], c1 = c[hw], c2 = c[2 * hw], c3 = c[3 * hw];
+                    float neg, pos;
+                    if (neg_max[l]) { neg = f_max(f_max(c0, c1), c2); pos = c3; }
+                    else            { neg = c0; pos = f_max(f_max(c1, c2), c3); }
+                    if (softmax) {
+                        const float m = f_max(neg, pos);
+                        const float e0 = f_exp(neg - m), e1 = f_exp(pos - m);
+                        const float sum = e0 + e1;
+                        neg = e0 / sum; pos = e1 / sum;
+                    }
+                    conf_out[2 * n] = neg; conf_out[2 * n + 1] = pos;
+                }
+                if (loc_out) {
+                    const float *c = loc_maps[l] + (int64_t)b * 4 * hw + q;
+                    loc_out[4 * n] = c[0]; loc_out[4 * n + 1] = c[hw]; loc_out[4 * n + 2] = c[2 * hw]; loc_out[4 * n + 3] = c[3 * hw];
+                }
+            }
+        off += hw;
+    }
+}

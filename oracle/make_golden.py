@@ -291,8 +291,60 @@ def gen_tracker():
     save("tracker", **d)
 
 
+# ------------------------------------------------------------------ 7. head post-processing
+def ref_heads(loc_maps, conf_maps, softmax):
+    """pyramid.py:291-309 and :331-332 restated verbatim (the model forward cannot run here: no weights, and it calls
+    time.clock(), gone in Python 3.12); `tmp_conf` / `l(x)` are the prediction-convolution outputs."""
+    loc, conf = [], []
+    for idx, (lx, tmp_conf) in enumerate(zip(loc_maps, conf_maps)):
+        if idx == 0:
+            a, b, c, pos_conf = tmp_conf.chunk(4, 1)
+            neg_conf = torch.cat([a, b, c], 1)
+            max_conf, _ = neg_conf.max(1)
+            max_conf = max_conf.view_as(pos_conf)
+            conf.append(torch.cat([max_conf, pos_conf], 1).permute(0, 2, 3, 1).contiguous())
+        else:
+            neg_conf, a, b, c = tmp_conf.chunk(4, 1)
+            pos_conf = torch.cat([a, b, c], 1)
+            max_conf, _ = pos_conf.max(1)
+            max_conf = max_conf.view_as(neg_conf)
+            conf.append(torch.cat([neg_conf, max_conf], 1).permute(0, 2, 3, 1).contiguous())
+        loc.append(lx.permute(0, 2, 3, 1).contiguous())
+    loc = torch.cat([o.view(o.size(0), -1) for o in loc], 1)
+    conf = torch.cat([o.view(o.size(0), -1) for o in conf], 1)
+    loc = loc.view(loc.size(0), -1, 4)
+    conf = conf.view(conf.size(0), -1, 2)
+    if softmax:
+        conf = torch.nn.Softmax(dim=-1)(conf)
+    return loc, conf
+
+
+def gen_heads():
+    d = {}
+    for tag, (B, w, h, seed, strides, boxes) in {
+        "a": (2, 160, 128, 31, synth.STRIDES6, synth.BOXES6),
+        "b": (2, 256, 256, 32, synth.STRIDES6[:5], synth.BOXES6[:5]),          # 5-level variant (pyramid_mb2_try3.py:144)
+    }.items():
+        loc_maps, conf_maps, neg_max = synth.head_maps(B, w, h, seed, strides)
+        if tag == "a":
+            conf_maps[1][0, 2, 3, 4] = np.nan                                  # torch.max propagates NaN
+            conf_maps[0][1, 0, 5, 6] = np.inf
+        tl, tc = [torch.from_numpy(m) for m in loc_maps], [torch.from_numpy(m) for m in conf_maps]
+        loc, conf = ref_heads(tl, tc, True)
+        _, raw = ref_heads(tl, tc, False)
+        pri = ref_priors(w, h, strides, boxes)
+        det = Detect(2, 0, 200, 0.05, 0.3)
+        out, counts, kept = ref_detect_aux(det, loc, conf, pri)
+        d.update({f"{tag}_cfg": np.array([B, w, h, seed, len(strides)]), f"{tag}_in_sha": np.array(synth.digest(*loc_maps, *conf_maps)),
+                  f"{tag}_loc_sha": np.array(synth.digest(loc.numpy())), f"{tag}_raw_sha": np.array(synth.digest(raw.numpy())),
+                  f"{tag}_conf": conf.numpy(),
+                  f"{tag}_out": out, f"{tag}_counts": counts, f"{tag}_kept": kept.astype(np.int32)})
+        print("  heads", tag, "N", loc.shape[1], "candidates", int((conf[..., 1] > 0.05).sum()))
+    save("heads", **d)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["priorbox", "boxutils", "nms", "detect", "multibox", "tracker"]
+    which = sys.argv[1:] or ["priorbox", "boxutils", "nms", "detect", "multibox", "tracker", "heads"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()

@@ -256,3 +256,23 @@ def iou_track(frames, sigma_iou=0.4, sigma_h=0.6, t_min=5):
         rows = t_dets[t_off[t]:t_off[t + 1]]
         out.append({'bboxes': dets[rows, :4].tolist(), 'max_score': float(t_max[t]), 'start_frame': int(t_start[t])})
     return out
+
+
+# ---------------------------------------------------------------- head post-processing (pyramid.py:291-309, 331-332)
+def heads_to_loc_conf(loc_maps, conf_maps, neg_max=None, softmax=True):
+    """loc_maps / conf_maps: per-level [B,4,H,W] fp32 arrays (NCHW) -> (loc[B,N,4], conf[B,N,2]).
+    neg_max[l] truthy: neg = max(ch0..2), pos = ch3 (level 0 in every model); default = (1, 0, 0, ...)."""
+    L = len(conf_maps)
+    conf_maps = [_f32(m) for m in conf_maps]
+    loc_maps = [_f32(m) for m in loc_maps]
+    B = conf_maps[0].shape[0]
+    fh = (C.c_int * L)(*[m.shape[2] for m in conf_maps])
+    fw = (C.c_int * L)(*[m.shape[3] for m in conf_maps])
+    nm = (C.c_int * L)(*([1] + [0] * (L - 1) if neg_max is None else [int(bool(v)) for v in neg_max]))
+    N = sum(m.shape[2] * m.shape[3] for m in conf_maps)
+    loc = np.empty((B, N, 4), dtype=np.float32)
+    conf = np.empty((B, N, 2), dtype=np.float32)
+    lp = (C.c_void_p * L)(*[m.ctypes.data for m in loc_maps])
+    cp = (C.c_void_p * L)(*[m.ctypes.data for m in conf_maps])
+    lib().orc_heads_to_loc_conf(lp, cp, fh, fw, nm, C.c_int(L), C.c_int(B), C.c_int(1 if softmax else 0), _p(loc), _p(conf))
+    return loc, conf
