@@ -5,6 +5,7 @@
     python bench_extra.py tracker    # BASELINE config 4: IoU tracker, 10k frames x 1-300 detections
     python bench_extra.py detect1024 # BASELINE config 5 shape on one GPU: Detect B=64 @1024^2 (N=87,360)
     python bench_extra.py priorbox
+    python bench_extra.py siblings   # FaceBoxes decode_np (21,824 default boxes) and MTCNN nms variants
     python bench_extra.py heads      # Detect straight from the per-level NCHW head maps, B=64 @640^2
 
 Each prints one JSON line with device time (CUDA events, L2 flushed between repetitions), the algorithmic bytes of
@@ -172,6 +173,50 @@ def priorbox():
     print(json.dumps({"workload": "PriorBoxLayer(640,640) x 6 levels (34,125 priors)", "ms_6_launches_incl_python": ms, "cpu_port_ms": cpu_s * 1e3}))
 
 
+def siblings():
+    """FaceBoxes DataEncoder.decode_np (threshold + decode + nms_np over the 21,824 default boxes) and MTCNN nms on 3,000 boxes:
+    device time through the C ABI vs the C oracle port on one host core (the reference is single-threaded numpy)."""
+    dev = torch.device("cuda")
+    L = _lib.lib(); st = _lib.stream_ptr()
+    db_np = orc.facebox_default_boxes(); N = db_np.shape[0]
+    rng = np.random.Generator(np.random.PCG64(7070))
+    loc_np = (rng.standard_normal((N, 4)) * 0.5).astype(np.float32)
+    s1 = (1.0 / (1.0 + np.exp(-(rng.standard_normal(N) * 2.0 - 2.0)))).astype(np.float32)
+    conf_np = np.stack([1 - s1, s1], 1).astype(np.float32)
+    loc, conf, db = (torch.from_numpy(a).to(dev) for a in (loc_np, conf_np, db_np))
+    boxes = torch.empty((N, 4), device=dev); keep = torch.zeros(N, dtype=torch.int64, device=dev); cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = _lib.workspace(L.fdt_threshold_nms_workspace_bytes(N), dev, "sx")
+    res = {}
+    for thr in (0.35, 0.25):
+        def run():
+            _lib.check(L.fdt_facebox_decode(loc.data_ptr(), db.data_ptr(), N, 0.1, 0.2, boxes.data_ptr(), st))
+            _lib.check(L.fdt_threshold_nms(boxes.data_ptr(), conf.data_ptr(), N, thr, 0.5, _lib.NMS_SUMFIRST, keep.data_ptr(), cnt.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), st))
+        ms, mn = timed(run)
+        cpu_s, _ = cpu_time(lambda: orc.facebox_decode_np(loc_np, conf_np, db_np, conf_thres=thr), budget=3.0)
+        rb, rs = orc.facebox_decode_np(loc_np, conf_np, db_np, conf_thres=thr)
+        same = int(cnt.item()) == rb.shape[0] and np.array_equal(boxes[keep[:int(cnt.item())]].cpu().numpy(), rb)
+        res[f"decode_np_thr{thr}"] = {"candidates": int((s1 > thr).sum()), "kept": int(cnt.item()), "device_ms": ms, "device_ms_min": mn,
+                                      "cpu_port_ms_1_core": cpu_s * 1e3, "identical_to_oracle": bool(same)}
+    rng = np.random.Generator(np.random.PCG64(7071))
+    n = 3000
+    c = rng.uniform(20, 460, (150, 2)); ctr = c[rng.integers(0, 150, n)] + rng.normal(0, 8, (n, 2)); wh = rng.uniform(6, 120, (n, 2))
+    d_np = np.concatenate([ctr - wh / 2, ctr + wh / 2, (rng.permutation(n) / n)[:, None]], 1).astype(np.float32)
+    bx = torch.from_numpy(np.ascontiguousarray(d_np[:, :4])).to(dev); sc = torch.from_numpy(np.ascontiguousarray(d_np[:, 4])).to(dev)
+    keep = torch.zeros(n, dtype=torch.int64, device=dev)
+    ws2 = _lib.workspace(L.fdt_nms_workspace_bytes(n), dev, "sx2")
+    for name, thr, flags in (("mtcnn_nms_union_0.6", 0.6, _lib.NMS_SUMFIRST), ("mtcnn_nms_minimum_0.4", 0.4, _lib.NMS_MINIMUM),
+                             ("mtcnn_torch_nms_union_0.5", 0.5, _lib.NMS_SUMFIRST | _lib.NMS_PLUS1 | _lib.NMS_LE)):
+        def run():
+            _lib.check(L.fdt_nms_variant(bx.data_ptr(), sc.data_ptr(), n, thr, flags, keep.data_ptr(), cnt.data_ptr(), ws2.data_ptr(), ws2.numel(), st))
+        ms, mn = timed(run)
+        cpu_s, _ = cpu_time(lambda: orc.nms_variant(d_np[:, :4], d_np[:, 4], thr, flags), budget=2.0)
+        ref = orc.nms_variant(d_np[:, :4], d_np[:, 4], thr, flags)
+        res[name] = {"boxes": n, "kept": int(cnt.item()), "device_ms": ms, "device_ms_min": mn, "cpu_port_ms_1_core": cpu_s * 1e3,
+                     "identical_to_oracle": bool(np.array_equal(keep[:int(cnt.item())].cpu().numpy(), ref))}
+    print(json.dumps({"workload": "sibling decode+NMS implementations (FaceBoxes DataEncoder.decode_np, MTCNN nms / torch_nms)", "results": res}))
+
+
 def heads():
     """Head maps -> detections, B=64 @640x640 (N=34,125): fused (fdt_detect_heads) vs materialise + Detect vs the reference's
     torch ops (pyramid.py:291-309, 331-332 on CUDA tensors) + Detect."""
@@ -237,5 +282,5 @@ def heads():
 
 
 if __name__ == "__main__":
-    for w in sys.argv[1:] or ["multibox", "tracker", "detect1024", "priorbox", "heads"]:
+    for w in sys.argv[1:] or ["multibox", "tracker", "detect1024", "priorbox", "heads", "siblings"]:
         globals()[w]()

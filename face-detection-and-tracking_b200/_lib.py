@@ -15,6 +15,7 @@ SO_PATH = os.path.join(CSRC, "libfdt_b200.so")
 
 FDT_OK, FDT_E_INVALID, FDT_E_CUDA, FDT_E_WORKSPACE, FDT_E_UNSUPPORTED, FDT_E_DEVICE = 0, -1, -2, -3, -4, -5
 MAX_NMS_TOP_K = 8000
+NMS_SUMFIRST, NMS_MINIMUM, NMS_PLUS1, NMS_LE = 1, 2, 4, 8
 
 _vp, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
 
@@ -38,6 +39,10 @@ SIGNATURES = {
     "fdt_log_sum_exp": (_i, [_vp, _i64, _i, _vp, _vp, _sz, _vp]),
     "fdt_nms_workspace_bytes": (_sz, [_i64]),
     "fdt_nms": (_i, [_vp, _vp, _i64, _f, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "fdt_nms_variant": (_i, [_vp, _vp, _i64, _f, _i, _vp, _vp, _vp, _sz, _vp]),
+    "fdt_facebox_decode": (_i, [_vp, _vp, _i64, _f, _f, _vp, _vp]),
+    "fdt_threshold_nms_workspace_bytes": (_sz, [_i64]),
+    "fdt_threshold_nms": (_i, [_vp, _vp, _i64, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     "fdt_detect_workspace_bytes": (_sz, [_i, _i64, _i]),
     "fdt_detect": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fdt_detect_threshold_compact": (_i, [_vp, _i, _i64, _i, _f, _vp, _sz, _vp]),

@@ -369,6 +369,7 @@ struct SortNmsParams {
     int64_t *keep;              // [n] (MODE_NMS)
     int64_t *count_out;         // [1] (MODE_NMS)
     int64_t n;                  // MODE_NMS list length
+    int variant;                // MODE_NMS: FDT_NMS_* flags (0 = layers/box_utils.nms)
     const unsigned long long *peer_out;   // device array of n_peers output base pointers (this GPU's and its NVLink peers'), or null
     int n_peers;
     int64_t img_offset;         // image index of this rank's first image inside the peers' gathered blocks
@@ -391,7 +392,7 @@ __device__ __forceinline__ bool fdt_suppresses(const float4 bi, const float area
     float inter = w * h;
     float uni = (area_j - inter) + area_i;
     if (inter > 0.0f) return !(inter / uni < thr);
-    return !(uni > 0.0f) && !(uni < 0.0f);          // 0/uni is NaN iff uni is 0 or NaN
+    return (!(uni > 0.0f) && !(uni < 0.0f)) || !(0.0f < thr);      // 0/uni is NaN iff uni is 0 or NaN, else 0 (survives iff 0 < thr)
 }
 
 // Same predicate, division only when the quotient is within 2^-20 of thr: with p = fl(thr * uni) and uni > 0,
@@ -411,10 +412,44 @@ __device__ __forceinline__ bool fdt_suppresses_fast(const float4 bi, const float
         if (inter > p * 1.00000095f) return true;
     }
     if (inter > 0.0f) return !(inter / uni < thr);
-    return !(uni > 0.0f) && !(uni < 0.0f);
+    return (!(uni > 0.0f) && !(uni < 0.0f)) || !(0.0f < thr);
 }
 
-__device__ __forceinline__ float box_area(const float4 b) { return (b.z - b.x) * (b.w - b.y); }   // box_utils.py:296
+
+// ---- sibling NMS implementations of the reference, selected by FDT_NMS_* flags (include/fdt_b200.h):
+//   FACEBOX/encoderl.py:218-266 nms_np and MTCNN/mtcnn/core/utils.py:62-113 nms: union = (area_i + area_j) - inter  [SUMFIRST],
+//     mode "Minimum": inter / min(area_i, area_j)  [MINIMUM], survive iff ovr < thr;
+//   MTCNN/mtcnn/core/nms.py:4-40 torch_nms: widths, heights and areas with "+ 1"  [PLUS1], survive iff ovr <= thr  [LE];
+//   FACEBOX/encoderl.py:268-306 DataEncoder.nms: SUMFIRST | LE.
+// i = the kept (higher-score) box, j = the candidate.  numpy / torch min-max propagate NaN; here a NaN coordinate always
+// makes the box's area NaN, which reaches the quotient through the denominator, so the plain fminf/fmaxf below suffice
+// (MINIMUM takes the NaN-propagating minimum explicitly).
+__device__ __forceinline__ float box_area_v(const float4 b, const int variant)
+{
+    if (variant & FDT_NMS_PLUS1) return ((b.z - b.x) + 1.0f) * ((b.w - b.y) + 1.0f);
+    return (b.z - b.x) * (b.w - b.y);
+}
+__device__ __forceinline__ bool fdt_suppresses_v(const float4 bi, const float area_i, const float4 bj, const float area_j,
+                                                 const float thr, const int variant)
+{
+    const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+    const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+    float dw = xx2 - xx1, dh = yy2 - yy1;
+    if (variant & FDT_NMS_PLUS1) { dw += 1.0f; dh += 1.0f; }
+    const float inter = fmaxf(0.0f, dw) * fmaxf(0.0f, dh);
+    float den;
+    if (variant & FDT_NMS_MINIMUM) den = (area_i != area_i || area_j != area_j) ? NAN : fminf(area_i, area_j);
+    else if (variant & FDT_NMS_SUMFIRST) den = (area_i + area_j) - inter;
+    else den = (area_j - inter) + area_i;
+    const float ovr = inter / den;
+    return (variant & FDT_NMS_LE) ? !(ovr <= thr) : !(ovr < thr);
+}
+// the box the spatial grid sees: PLUS1 measures [x1, x2 + 1] x [y1, y2 + 1]
+__device__ __forceinline__ float4 grid_box(const float4 b, const int variant)
+{
+    if (variant & FDT_NMS_PLUS1) return make_float4(b.x, b.y, b.z + 1.0f, b.w + 1.0f);
+    return b;
+}
 // Boxes the spatial grid may index: finite, not inverted, 0 < area < inf.  For two such boxes inter <= min(area_i,
 // area_j) holds exactly in fp32 (rounding is monotone), so union >= area_i > 0 and IoU is a finite number bounded by
 // the ratio of the longer sides; they can only suppress each other if they intersect.  Everything else (NaN/inf
@@ -644,7 +679,7 @@ k_sort_nms(const SortNmsParams P)
         if (P.counts && tid == 0) P.counts[b * P.C] = 0;
     }
     cudaGridDependencySynchronize();      // no-op unless launched with programmatic stream serialization (after K2)
-    int n_c = (MODE == MODE_DETECT) ? P.counters[list] : (int)P.n;
+    int n_c = (MODE == MODE_DETECT || P.counters) ? P.counters[list] : (int)P.n;
     if (MODE == MODE_DETECT && n_c == 1) n_c = 0;            // detection.py:66-72: one candidate -> `continue`
     const int k = min(n_c, P.nms_top_k);                     // box_utils.py:299 idx[-top_k:]
     const bool prof = P.prof != nullptr && blockIdx.x == 0 && tid == 0;
@@ -822,8 +857,19 @@ k_sort_nms(const SortNmsParams P)
     // and stops once top_k boxes are kept: Detect only reads keep[:top_k] (detection.py:80-81).
     // In phases A-C thread t works on the t-th candidate IN CELL ORDER, so the lanes of a warp walk the same grid rows.
     const float thr = P.nms_thresh;
-    const float prune = 0.99f * thr;
-    const float tq = 0.97f * fminf(thr, 1.0f);          // query-range tightening, see the grid comment
+    const int variant = (MODE == MODE_NMS) ? P.variant : 0;
+    // "Minimum" overlap (inter / smaller area) is not bounded by the side ratio nor by the overlap / width ratio: every
+    // intersecting pair at every coarser level has to be looked at
+    const float prune = (variant & FDT_NMS_MINIMUM) ? 0.0f : 0.99f * thr;
+    const float tq = (variant & FDT_NMS_MINIMUM) ? 0.0f : 0.97f * fminf(thr, 1.0f);          // query-range tightening, see the grid comment
+    auto suppresses = [&](const float4 bi, const float ai, const float4 bj2, const float aj2) -> bool {
+        if (MODE == MODE_NMS && variant != 0) return fdt_suppresses_v(bi, ai, bj2, aj2, thr, variant);
+        return fdt_suppresses_fast(bi, ai, bj2, aj2, thr);
+    };
+    auto suppresses_exact = [&](const float4 bi, const float ai, const float4 bj2, const float aj2) -> bool {
+        if (MODE == MODE_NMS && variant != 0) return fdt_suppresses_v(bi, ai, bj2, aj2, thr, variant);
+        return fdt_suppresses(bi, ai, bj2, aj2, thr);
+    };
     const int max_keep = P.max_keep;
     int nkept = 0, rounds = 0, sweeps = 0;
     GridGeom gg;
@@ -883,10 +929,11 @@ k_sort_nms(const SortNmsParams P)
         {
             float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) bx = (MODE == MODE_DETECT) ? fdt_decode1(ld0, ld1, P.v0, P.v1) : ld0;      // detection.py:55
-            const float side = fmaxf(bx.z - bx.x, bx.w - bx.y);
+            const float4 gb = grid_box(bx, variant);
+            const float side = fmaxf(gb.z - gb.x, gb.w - gb.y);
             if (rounds == 0) {
-                const bool reg = valid && box_regular(bx);
-                float x0 = reg ? bx.x : INFINITY, y0 = reg ? bx.y : INFINITY, x1 = reg ? bx.z : -INFINITY, y1 = reg ? bx.w : -INFINITY;
+                const bool reg = valid && box_regular(gb);
+                float x0 = reg ? gb.x : INFINITY, y0 = reg ? gb.y : INFINITY, x1 = reg ? gb.z : -INFINITY, y1 = reg ? gb.w : -INFINITY;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
@@ -900,7 +947,7 @@ k_sort_nms(const SortNmsParams P)
                 const float ex0 = fdt_key_float(s_ext[0]), ey0 = fdt_key_float(s_ext[1]);
                 const float ex1 = fdt_key_float(s_ext[2]), ey1 = fdt_key_float(s_ext[3]);
                 const float ext = fmaxf(ex1 - ex0, ey1 - ey0);
-                gg.ok = (ext > 0.0f) && (ext < INFINITY);
+                gg.ok = (ext > 0.0f) && (ext < INFINITY) && (thr > 0.0f);     // thr <= 0 (or NaN): every pair suppresses, at any distance
                 gg.x0 = ex0; gg.y0 = ey0;
                 gg.inv0 = gg.ok ? 32.0f / ext : 0.0f;
                 gg.c0 = gg.ok ? ext / 32.0f : 0.0f;
@@ -908,14 +955,14 @@ k_sort_nms(const SortNmsParams P)
             }
             K3_ACC(1);
             // ---- window grid and (from the second round on) kept-box grid, CSR: count per cell, scan, place
-            const int cell = reg_cell(gg, bx, side, valid);
+            const int cell = reg_cell(gg, gb, side, valid);
             if (wi >= 0) wcell[wi] = (uint16_t)(cell < 0 ? BIGCELL : cell);
             const int slot = cell >= 0 ? atomicAdd(&wstart[cell + 1], 1) : 0;
             if (rounds > 0)
                 for (int i = tid; i < nkept; i += K3_THREADS) atomicAdd(&kstart[kcell[i] + 1], 1);
             __syncthreads();
             csr_scan(wstart, s_warp);
-            if (cell >= 0) { const int ps = wstart[cell] + slot; witems[ps] = (uint16_t)wi; wpos[wi] = (uint16_t)ps; sbox[ps] = bx; sarea[ps] = box_area(bx); }
+            if (cell >= 0) { const int ps = wstart[cell] + slot; witems[ps] = (uint16_t)wi; wpos[wi] = (uint16_t)ps; sbox[ps] = bx; sarea[ps] = box_area_v(bx, variant); }
             if (CL == 2) {
                 // Both CTAs of the cluster must see the SAME CSR array (they split it by position): order every cell by window
                 // position instead of by atomic arrival.
@@ -949,15 +996,16 @@ k_sort_nms(const SortNmsParams P)
         const bool have = tid < nvalid;
         const int id = have ? witems[tid] : 0;
         const float4 bj = sbox[have ? tid : 0];
-        const float aj = sarea[have ? tid : 0], sj = fmaxf(bj.z - bj.x, bj.w - bj.y);
+        const float4 gj = grid_box(bj, variant);
+        const float aj = sarea[have ? tid : 0], sj = fmaxf(gj.z - gj.x, gj.w - gj.y);
         const bool chk = nkept > 0;          // only then can a window candidate already be dead (phase A)
         const bool in_grid = have && wcell[id] != BIGCELL;
         // ---- phase A: against the boxes kept in earlier rounds
         bool alive = have;
         if (have && nkept > 0) {
-            auto hit = [&](int t) -> bool { const int slot = kitems[t]; return fdt_suppresses_fast(kbox[slot], karea[slot], bj, aj, thr); };
-            if (in_grid) alive = !csr_query(gg, kstart, bj, sj, prune, tq, hit);
-            else for (int t = 0; t < nkept && alive; ++t) if (fdt_suppresses(kbox[t], karea[t], bj, aj, thr)) alive = false;
+            auto hit = [&](int t) -> bool { const int slot = kitems[t]; return suppresses(kbox[slot], karea[slot], bj, aj); };
+            if (in_grid) alive = !csr_query(gg, kstart, gj, sj, prune, tq, hit);
+            else for (int t = 0; t < nkept && alive; ++t) if (suppresses_exact(kbox[t], karea[t], bj, aj)) alive = false;
         }
         if (have) status[id] = alive ? 0 : 2;
         K3_ACC(3);
@@ -984,7 +1032,7 @@ k_sort_nms(const SortNmsParams P)
                 const float4 cb = sbox[tc], bo = sbox[t2];
                 const float ca = sarea[tc], ao = sarea[t2];
                 const bool me_first = cid < other;           // window index = score order
-                const bool sup = me_first ? fdt_suppresses_fast(cb, ca, bo, ao, thr) : fdt_suppresses_fast(bo, ao, cb, ca, thr);
+                const bool sup = me_first ? suppresses(cb, ca, bo, ao) : suppresses(bo, ao, cb, ca);
                 if (sup) {
                     const int later = me_first ? other : cid, earlier = me_first ? cid : other;
                     const int sl = atomicAdd(&sndep[later], 1);
@@ -1003,7 +1051,7 @@ k_sort_nms(const SortNmsParams P)
                         else for (int t2 = t0; t2 < t1; ++t2) pair(t, t2);
                     };
                     if (wcell[cid] != BIGCELL) {
-                        const float4 cb = sbox[t];
+                        const float4 cb = grid_box(sbox[t], variant);
                         csr_segments_forward(gg, wstart, cb, fmaxf(cb.z - cb.x, cb.w - cb.y), prune, tq, (int)wcell[cid], t, part, lpc, emit);
                     } else if (part == 0) {
                         // irregular boxes sit last in CSR order: every regular candidate's forward query reaches them; they
@@ -1086,16 +1134,16 @@ k_sort_nms(const SortNmsParams P)
                         if (in_grid) {
                             auto look = [&](int t) -> bool {
                                 const int a = witems[t];
-                                if (a < id && status[a] != 2 && fdt_suppresses_fast(sbox[t], sarea[t], bj, aj, thr)) {
+                                if (a < id && status[a] != 2 && suppresses(sbox[t], sarea[t], bj, aj)) {
                                     if (status[a] == 1) { any_kept = true; return true; }
                                     pend = true;
                                 }
                                 return false;
                             };
-                            csr_query(gg, wstart, bj, sj, prune, tq, look);
+                            csr_query(gg, wstart, gj, sj, prune, tq, look);
                         } else {
                             for (int a = 0; a < id && !any_kept; ++a)
-                                if (status[a] != 2 && fdt_suppresses(sbox[wpos[a]], sarea[wpos[a]], bj, aj, thr)) {
+                                if (status[a] != 2 && suppresses_exact(sbox[wpos[a]], sarea[wpos[a]], bj, aj)) {
                                     if (status[a] == 1) any_kept = true; else pend = true;
                                 }
                         }
@@ -1511,7 +1559,7 @@ FDT_API size_t fdt_nms_workspace_bytes(int64_t n)
     return fdt_align256(nn * sizeof(uint64_t)) + fdt_align256(kept_rows * KEPT_ROW_BYTES);
 }
 
-FDT_API int fdt_nms(const float *boxes, const float *scores, int64_t n, float overlap, int64_t top_k,
+static int nms_impl(const float *boxes, const float *scores, int64_t n, float overlap, int64_t top_k, int variant,
                     int64_t *keep, int64_t *count, void *ws, size_t ws_bytes, fdt_stream_t stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
@@ -1528,9 +1576,87 @@ FDT_API int fdt_nms(const float *boxes, const float *scores, int64_t n, float ov
     FDT_LAUNCH_CHECK();
     SortNmsParams P{};
     P.keys = keys; P.key_stride = n; P.boxes = boxes; P.n = n; P.N = n; P.C = 2;
-    P.nms_top_k = (int)k; P.max_keep = (int)k; P.nms_thresh = overlap;
+    P.nms_top_k = (int)k; P.max_keep = (int)k; P.nms_thresh = overlap; P.variant = variant;
     P.keep = keep; P.count_out = count;
     char *kept_ws = (char *)ws + fdt_align256((size_t)n * sizeof(uint64_t));
     size_t kept_rows = (size_t)(n < FDT_MAX_NMS_TOP_K ? n : FDT_MAX_NMS_TOP_K);
     return launch_sort_nms<MODE_NMS>(P, 1, (int)k, kept_ws, fdt_align256(kept_rows * KEPT_ROW_BYTES), st);
+}
+
+FDT_API int fdt_nms(const float *boxes, const float *scores, int64_t n, float overlap, int64_t top_k,
+                    int64_t *keep, int64_t *count, void *ws, size_t ws_bytes, fdt_stream_t stream)
+{
+    return nms_impl(boxes, scores, n, overlap, top_k, 0, keep, count, ws, ws_bytes, stream);
+}
+
+// ---- sibling NMS implementations: every box enters (no top_k), overlap rule per `variant`
+FDT_API int fdt_nms_variant(const float *boxes, const float *scores, int64_t n, float thresh, int variant,
+                            int64_t *keep, int64_t *count, void *ws, size_t ws_bytes, fdt_stream_t stream)
+{
+    FDT_REQUIRE(variant >= 0 && variant < 16, FDT_E_INVALID, "fdt_nms_variant: unknown variant flags %d", variant);
+    return nms_impl(boxes, scores, n, thresh, 0, variant, keep, count, ws, ws_bytes, stream);
+}
+
+// FaceBoxes DataEncoder.decode_np, box part (FACEBOX/encoderl.py:318-320):
+//   cxcy = loc[:, :2] * 0.1 * d[:, 2:] + d[:, :2];  wh = exp(loc[:, 2:] * 0.2) * d[:, 2:];  boxes = [cxcy - wh/2, cxcy + wh/2]
+__global__ void k_facebox_decode(const float4 *__restrict__ loc, const float4 *__restrict__ dbox, int64_t n, float v0, float v1,
+                                 float4 *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 l = __ldg(loc + i), d = __ldg(dbox + i);
+    const float cx = (l.x * v0) * d.z + d.x, cy = (l.y * v0) * d.w + d.y;
+    const float w = fdt_expf_cr(l.z * v1) * d.z, h = fdt_expf_cr(l.w * v1) * d.w;
+    out[i] = make_float4(cx - w / 2.0f, cy - h / 2.0f, cx + w / 2.0f, cy + h / 2.0f);
+}
+
+FDT_API int fdt_facebox_decode(const float *loc, const float *default_boxes, int64_t n, float var0, float var1, float *out,
+                               fdt_stream_t stream)
+{
+    FDT_REQUIRE(n >= 0, FDT_E_INVALID, "fdt_facebox_decode: n=%lld", (long long)n);
+    if (n == 0) return FDT_OK;
+    FDT_REQUIRE(loc && default_boxes && out && fdt_aligned(loc, 16) && fdt_aligned(default_boxes, 16) && fdt_aligned(out, 16),
+                FDT_E_INVALID, "fdt_facebox_decode: null or not 16-byte aligned pointer");
+    k_facebox_decode<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float4 *)loc, (const float4 *)default_boxes, n, var0, var1, (float4 *)out);
+    FDT_LAUNCH_CHECK();
+    return FDT_OK;
+}
+
+// Threshold + NMS over a box table: the boxes p with conf[p, 1] > conf_thresh enter NMS (all of them, at most
+// FDT_MAX_NMS_TOP_K -- more is FDT_E_UNSUPPORTED at run time: then keep is all zero and *count = -1), no host round trip:
+// K2 compacts the candidates, k_sort_nms reads the count on the device.  keep[N] = table indices in keep order.
+FDT_API size_t fdt_threshold_nms_workspace_bytes(int64_t N) { return fdt_detect_workspace_bytes(1, N, 2); }
+
+__global__ void k_threshold_nms_guard(const int32_t *counters, int64_t *keep, int64_t *count, int64_t N, int limit)
+{
+    // more candidates than NMS admits: k_sort_nms would silently keep only the `limit` best (idx[-top_k:] semantics)
+    if (counters[0] <= limit) return;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) keep[i] = 0;
+    if (threadIdx.x == 0) *count = -1;
+}
+
+FDT_API int fdt_threshold_nms(const float *boxes, const float *conf, int64_t N, float conf_thresh, float nms_thresh, int variant,
+                              int64_t *keep, int64_t *count, void *ws, size_t ws_bytes, fdt_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    FDT_REQUIRE(variant >= 0 && variant < 16, FDT_E_INVALID, "fdt_threshold_nms: unknown variant flags %d", variant);
+    FDT_REQUIRE(N >= 0 && N < (1ll << 31) && count != nullptr, FDT_E_INVALID, "fdt_threshold_nms: bad arguments");
+    if (N == 0) { FDT_CUDA(cudaMemsetAsync(count, 0, sizeof(int64_t), st)); return FDT_OK; }
+    FDT_REQUIRE(boxes && conf && keep && fdt_aligned(boxes, 16), FDT_E_INVALID, "fdt_threshold_nms: null or misaligned pointer");
+    int rc = threshold_compact_impl(conf, nullptr, 1, N, 2, conf_thresh, ws, ws_bytes, stream);
+    if (rc != FDT_OK) return rc;
+    int32_t *counters = (int32_t *)ws;
+    uint64_t *keys = (uint64_t *)((char *)ws + fdt_align256((size_t)3 * sizeof(int32_t)));
+    const int kcap = (int)(N < FDT_MAX_NMS_TOP_K ? N : FDT_MAX_NMS_TOP_K);
+    SortNmsParams P{};
+    P.keys = keys; P.counters = counters; P.key_stride = N; P.boxes = boxes; P.n = N; P.N = N; P.C = 2;
+    P.nms_top_k = kcap; P.max_keep = kcap; P.nms_thresh = nms_thresh; P.variant = variant;
+    P.keep = keep; P.count_out = count;
+    char *kept_ws = (char *)keys + fdt_align256((size_t)N * sizeof(uint64_t));
+    rc = launch_sort_nms<MODE_NMS>(P, 1, kcap, kept_ws, fdt_align256((size_t)kcap * KEPT_ROW_BYTES), st);
+    if (rc != FDT_OK) return rc;
+    k_threshold_nms_guard<<<1, 256, 0, st>>>(counters, keep, count, N, kcap);
+    FDT_LAUNCH_CHECK();
+    return FDT_OK;
 }

@@ -36,6 +36,12 @@ extern "C" {
 #define FDT_E_UNSUPPORTED -4   /* size outside the kernel limits (see each function) */
 #define FDT_E_DEVICE      -5   /* device is not sm_100 (B200) */
 
+/* overlap rule of the sibling NMS implementations (fdt_nms_variant); 0 = layers/box_utils.nms */
+#define FDT_NMS_SUMFIRST   1      /* union = (area_i + area_j) - inter   (numpy / FaceBoxes / MTCNN operand order) */
+#define FDT_NMS_MINIMUM    2      /* overlap = inter / min(area_i, area_j)   (mode="Minimum") */
+#define FDT_NMS_PLUS1      4      /* widths, heights and areas measured with "+ 1" (pixel convention) */
+#define FDT_NMS_LE         8      /* a box survives iff overlap <= thresh (default: overlap < thresh) */
+
 #define FDT_MAX_NMS_TOP_K  8000   /* candidates that can enter NMS per image/class (the reference uses 5000) */
 
 typedef void *fdt_stream_t;        /* cudaStream_t */
@@ -93,6 +99,25 @@ int fdt_log_sum_exp(const float *x, int64_t R, int C, float *out, void *ws, size
 size_t fdt_nms_workspace_bytes(int64_t n);
 int fdt_nms(const float *boxes, const float *scores, int64_t n, float overlap, int64_t top_k,
             int64_t *keep, int64_t *count, void *ws, size_t ws_bytes, fdt_stream_t stream);
+
+/* ----  sibling decode + NMS implementations of the reference ---------------------------------------------
+ * fdt_nms_variant: greedy NMS where EVERY box enters (no top_k) and the overlap rule is chosen by FDT_NMS_* flags:
+ *   FACEBOX/encoderl.py:218-266 DataEncoder.nms_np, MTCNN/mtcnn/core/utils.py:62-113 nms   mode "Union":   FDT_NMS_SUMFIRST
+ *                                                                                      mode "Minimum": FDT_NMS_MINIMUM
+ *   MTCNN/mtcnn/core/nms.py:4-40 torch_nms            FDT_NMS_PLUS1 | FDT_NMS_LE | (FDT_NMS_SUMFIRST or FDT_NMS_MINIMUM)
+ *   FACEBOX/encoderl.py:268-306 DataEncoder.nms       FDT_NMS_SUMFIRST | FDT_NMS_LE
+ * keep[n] int64 zero padded = indices in keep order (descending score; ties: higher index first), *count device int64.
+ * Limit n <= FDT_MAX_NMS_TOP_K; workspace fdt_nms_workspace_bytes(n).
+ * fdt_facebox_decode: the box part of DataEncoder.decode_np (encoderl.py:318-320), corner form [x1,y1,x2,y2].
+ * fdt_threshold_nms: rows p of a box table with conf[p,1] > conf_thresh (conf[N,2]) enter fdt_nms_variant's NMS without a
+ * host round trip; keep[N] holds table indices.  More than FDT_MAX_NMS_TOP_K candidates: keep zeroed, *count = -1. */
+int fdt_nms_variant(const float *boxes, const float *scores, int64_t n, float thresh, int variant,
+                    int64_t *keep, int64_t *count, void *ws, size_t ws_bytes, fdt_stream_t stream);
+int fdt_facebox_decode(const float *loc, const float *default_boxes, int64_t n, float var0, float var1, float *out,
+                       fdt_stream_t stream);
+size_t fdt_threshold_nms_workspace_bytes(int64_t N);
+int fdt_threshold_nms(const float *boxes, const float *conf, int64_t N, float conf_thresh, float nms_thresh, int variant,
+                      int64_t *keep, int64_t *count, void *ws, size_t ws_bytes, fdt_stream_t stream);
 
 /* ---- D3  Detect.__call__  (layers/functions/detection.py:34-84) ---------------------------------
  * loc[B,N,4], conf[B,N,C] (post-softmax), priors[N,4] -> out[B,C,top_k,5] rows [score,x1,y1,x2,y2]

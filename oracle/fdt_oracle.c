@@ -624,3 +624,69 @@ ORC_API void orc_heads_to_loc_conf(const float *const *loc_maps, const float *co
         off += hw;
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Sibling NMS implementations.  flags: 1 SUMFIRST, 2 MINIMUM, 4 PLUS1, 8 LE.
+ *   FACEBOX/encoderl.py:218-266 nms_np and MTCNN/mtcnn/core/utils.py:62-113 nms (numpy):
+ *     areas = (x2-x1)*(y2-y1); order = scores.argsort()[::-1]; per kept i: inter = max(0, xx2-xx1)*max(0, yy2-yy1);
+ *     "Union": inter / (areas[i] + areas[rest] - inter); "Minimum": inter / min(areas[i], areas[rest]); keep ovr < thr.
+ *   MTCNN/mtcnn/core/nms.py:4-40 torch_nms: the same with "+ 1" on widths/heights/areas and keep ovr <= thr.
+ *   FACEBOX/encoderl.py:268-306 DataEncoder.nms (torch): Union, keep ovr <= thr.
+ * np.maximum / np.minimum / clamp propagate NaN.  Sort ties (argsort / torch.sort are unstable): defined as
+ * ascending by (score, index) read from the end, i.e. higher index first, like orc_nms.
+ * Every box enters (no top_k); keep[] gets `count` indices.
+ * ------------------------------------------------------------------------------------------ */
+ORC_API int64_t orc_nms_variant(const float *boxes, const float *scores, int64_t n, float thr, int flags, int64_t *keep)
+{
+    memset(keep, 0, sizeof(int64_t) * (size_t)n);
+    if (n == 0) return 0;
+    const float p1 = (flags & 4) ? 1.0f : 0.0f;
+    float *area = (float *)malloc(sizeof(float) * (size_t)n);
+    orc_si *ord = (orc_si *)malloc(sizeof(orc_si) * (size_t)n);
+    int64_t *idx = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        const float *b = boxes + 4 * i;
+        area[i] = (flags & 4) ? ((b[2] - b[0]) + 1.0f) * ((b[3] - b[1]) + 1.0f) : (b[2] - b[0]) * (b[3] - b[1]);
+        ord[i].s = scores[i]; ord[i].i = i;
+    }
+    qsort(ord, (size_t)n, sizeof(orc_si), cmp_si_asc);
+    int64_t m = n, count = 0;
+    for (int64_t t = 0; t < n; ++t) idx[t] = ord[t].i;
+    while (m > 0) {
+        const int64_t i = idx[m - 1];
+        keep[count++] = i;
+        m -= 1;
+        const float *bi = boxes + 4 * i;
+        int64_t w = 0;
+        for (int64_t t = 0; t < m; ++t) {
+            const int64_t j = idx[t];
+            const float *bj = boxes + 4 * j;
+            const float xx1 = f_max(bi[0], bj[0]), yy1 = f_max(bi[1], bj[1]);
+            const float xx2 = f_min(bi[2], bj[2]), yy2 = f_min(bi[3], bj[3]);
+            float dw = xx2 - xx1, dh = yy2 - yy1;
+            if (flags & 4) { dw += p1; dh += p1; }
+            const float inter = f_max(0.0f, dw) * f_max(0.0f, dh);
+            float den;
+            if (flags & 2) den = f_min(area[i], area[j]);
+            else if (flags & 1) den = (area[i] + area[j]) - inter;
+            else den = (area[j] - inter) + area[i];
+            const float ovr = inter / den;
+            const int survive = (flags & 8) ? (ovr <= thr) : (ovr < thr);
+            if (survive) idx[w++] = j;
+        }
+        m = w;
+    }
+    free(idx); free(ord); free(area);
+    return count;
+}
+
+/* FaceBoxes DataEncoder.decode_np, box part (FACEBOX/encoderl.py:318-320) */
+ORC_API void orc_facebox_decode(const float *loc, const float *dbox, int64_t n, float v0, float v1, float *out)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        const float *l = loc + 4 * i, *d = dbox + 4 * i;
+        const float cx = (l[0] * v0) * d[2] + d[0], cy = (l[1] * v0) * d[3] + d[1];
+        const float w = f_exp(l[2] * v1) * d[2], h = f_exp(l[3] * v1) * d[3];
+        out[4 * i] = cx - w / 2.0f; out[4 * i + 1] = cy - h / 2.0f; out[4 * i + 2] = cx + w / 2.0f; out[4 * i + 3] = cy + h / 2.0f;
+    }
+}

@@ -343,8 +343,103 @@ def gen_heads():
     save("heads", **d)
 
 
+# ------------------------------------------------------------------ 8. sibling decode + NMS implementations
+def sibling_dets(n, seed, size=480.0, clusters=25):
+    """n pixel boxes [x1,y1,x2,y2,score] fp32 around `clusters` centres (heavy overlap), unique scores."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    c = rng.uniform(40, size - 40, (clusters, 2))
+    k = rng.integers(0, clusters, n)
+    side = rng.uniform(12, 90, n)
+    ctr = c[k] + rng.normal(0, 6, (n, 2))
+    w = side * rng.uniform(0.8, 1.25, n); h = side * rng.uniform(0.8, 1.25, n)
+    sc = rng.permutation(n).astype(np.float64) / n * 0.6 + 0.4
+    d = np.stack([ctr[:, 0] - w / 2, ctr[:, 1] - h / 2, ctr[:, 0] + w / 2, ctr[:, 1] + h / 2, sc], 1).astype(np.float32)
+    return d
+
+
+def gen_siblings():
+    sys.path.insert(0, os.path.join(REF, "FACEBOX"))
+    sys.path.insert(0, os.path.join(REF, "MTCNN"))
+    from encoderl import DataEncoder                                       # noqa: E402  (reference, FACEBOX/encoderl.py)
+    from mtcnn.core import utils as mt_utils, nms as mt_nms                # noqa: E402  (reference, MTCNN/mtcnn/core)
+    d = {}
+    enc = DataEncoder()
+    db = enc.default_boxes_np
+    d.update(fb_default_sha=np.array(synth.digest(db)), fb_default_head=db[:40].copy(), fb_default_tail=db[-10:].copy())
+    # FaceBoxes decode_np (encoderl.py:308-325): 21,824 default boxes, conf_thres 0.35, nms_np Union 0.5
+    rng = np.random.Generator(np.random.PCG64(51))
+    N = db.shape[0]
+    loc = (rng.standard_normal((N, 4)) * 0.5).astype(np.float32)
+    s1 = 1.0 / (1.0 + np.exp(-(rng.standard_normal(N) * 2.0 - 4.0)))
+    s1 = synth._uniquify_candidates(s1.astype(np.float32)[None], 0.35)[0]
+    conf = np.stack([1 - s1, s1], 1).astype(np.float32)
+    boxes_k, scores_k = enc.decode_np(torch.from_numpy(loc), torch.from_numpy(conf))
+    score = conf[:, 1]; ids = np.where(score > 0.35)[0]                    # :314-315 restated to recover the kept indices
+    cxcy = loc[ids, :2] * 0.1 * db[ids, 2:] + db[ids, :2]
+    wh = np.exp(loc[ids, 2:] * 0.2) * db[ids, 2:]
+    bx = np.hstack([cxcy - wh / 2, cxcy + wh / 2])
+    keep = np.array(enc.nms_np(bx, score[ids]), dtype=np.int64)
+    assert np.array_equal(bx[keep], boxes_k) and np.array_equal(score[ids][keep], scores_k)
+    d.update(fb_in_sha=np.array(synth.digest(loc, conf)), fb_kept=ids[keep].astype(np.int32), fb_boxes=boxes_k.astype(np.float32),
+             fb_scores=scores_k.astype(np.float32), fb_ncand=np.int64(ids.size))
+    print("  faceboxes decode_np: candidates", ids.size, "kept", keep.size)
+    # FaceBoxes encode (encoderl.py:158-215): 6 faces, two of them sharing their best default box
+    gtb = np.array([[0.10, 0.12, 0.22, 0.30], [0.40, 0.40, 0.47, 0.49], [0.401, 0.401, 0.471, 0.491], [0.6, 0.2, 0.95, 0.7],
+                    [0.05, 0.7, 0.09, 0.76], [0.30, 0.05, 0.33, 0.085]], dtype=np.float32)
+    # enc.encode itself always raises here: `if inf_flag.long().sum() is not 0` (:196) compares a tensor with `is`, true for
+    # every input since torch 0.4, and the handler names an undefined `inf_error`.  Lines :171-193 and :203-206 verbatim:
+    def ref_encode(boxes, classes, threshold=0.35):
+        default_boxes = enc.default_boxes
+        num_obj = boxes.size(0)
+        iou = enc.iou(boxes, torch.cat([default_boxes[:, :2] - default_boxes[:, 2:] / 2,
+                                        default_boxes[:, :2] + default_boxes[:, 2:] / 2], 1))
+        max_iou, max_iou_index = iou.max(1)
+        iou, max_index = iou.max(0)
+        max_index.squeeze_(0)
+        iou.squeeze_(0)
+        max_index[max_iou_index] = torch.LongTensor(range(num_obj))
+        boxes = boxes[max_index]
+        variances = [0.1, 0.2]
+        cxcy = (boxes[:, :2] + boxes[:, 2:]) / 2 - default_boxes[:, :2]
+        cxcy /= variances[0] * default_boxes[:, 2:]
+        wh = (boxes[:, 2:] - boxes[:, :2]) / default_boxes[:, 2:]
+        wh = torch.log(wh) / variances[1]
+        loc = torch.cat([cxcy, wh], 1)
+        conf = classes[max_index]
+        conf[iou < threshold] = 0
+        conf[max_iou_index] = 1
+        return loc, conf
+    eloc, econf = ref_encode(torch.from_numpy(gtb), torch.ones(gtb.shape[0], dtype=torch.long))
+    d.update(enc_gt=gtb, enc_loc=eloc.numpy(), enc_conf=econf.numpy().astype(np.int32))
+    print("  faceboxes encode: positives", int((econf > 0).sum()))
+    # NMS variants on the same detections
+    dets = sibling_dets(600, 52)
+    dets[7, :4] = dets[3, :4]                                              # identical boxes: overlap exactly 1
+    dets[11, 2] = dets[11, 0]                                              # zero width
+    d["dets"] = dets
+    for tag, fn in (("mt_union_06", lambda: mt_utils.nms(dets, 0.6, "Union")),              # detect.py:326, :431
+                    ("mt_min_04", lambda: mt_utils.nms(dets, 0.4, "Minimum")),             # detect.py:314
+                    ("mt_min_05", lambda: mt_utils.nms(dets, 0.5, "Minimum")),             # detect.py:579
+                    ("fb_np_union_05", lambda: enc.nms_np(dets[:, :4], dets[:, 4], 0.5)),
+                    ("fb_np_min_03", lambda: enc.nms_np(dets[:, :4], dets[:, 4], 0.3, "Minimum")),
+                    ("mt_plus1_union_05", lambda: mt_nms.torch_nms(dets, 0.5, "Union")),
+                    ("mt_plus1_min_07", lambda: mt_nms.torch_nms(dets, 0.7, "Minimum")),
+                    ("fb_torch_05", lambda: enc.nms(torch.from_numpy(dets[:, :4].copy()), torch.from_numpy(dets[:, 4].copy()), 0.5).numpy()),
+                    ("fb_torch_1", lambda: enc.nms(torch.from_numpy(dets[:, :4].copy()), torch.from_numpy(dets[:, 4].copy()), 1.0).numpy())):
+        k = np.asarray(fn(), dtype=np.int64).reshape(-1)
+        d[tag] = k.astype(np.int32)
+        print("  ", tag, "kept", k.size)
+    # NaN coordinate: numpy / torch min-max propagate it
+    dn = sibling_dets(64, 53); dn[5, 1] = np.nan
+    d["dets_nan"] = dn
+    d["nan_mt_union_05"] = np.asarray(mt_utils.nms(dn, 0.5, "Union"), np.int32)
+    d["nan_mt_min_05"] = np.asarray(mt_utils.nms(dn, 0.5, "Minimum"), np.int32)
+    d["nan_plus1_union_05"] = np.asarray(mt_nms.torch_nms(dn, 0.5, "Union"), np.int32)
+    save("siblings", **d)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["priorbox", "boxutils", "nms", "detect", "multibox", "tracker", "heads"]
+    which = sys.argv[1:] or ["priorbox", "boxutils", "nms", "detect", "multibox", "tracker", "heads", "siblings"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()

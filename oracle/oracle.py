@@ -276,3 +276,57 @@ def heads_to_loc_conf(loc_maps, conf_maps, neg_max=None, softmax=True):
     cp = (C.c_void_p * L)(*[m.ctypes.data for m in conf_maps])
     lib().orc_heads_to_loc_conf(lp, cp, fh, fw, nm, C.c_int(L), C.c_int(B), C.c_int(1 if softmax else 0), _p(loc), _p(conf))
     return loc, conf
+
+
+# ---------------------------------------------------------------- sibling NMS / decode implementations
+NMS_SUMFIRST, NMS_MINIMUM, NMS_PLUS1, NMS_LE = 1, 2, 4, 8
+
+
+def nms_variant(boxes, scores, thresh, flags):
+    """-> kept indices (int64[count]) in keep order; see orc_nms_variant for the flag meaning."""
+    b = _f32(boxes).reshape(-1, 4); s = _f32(scores).reshape(-1)
+    keep = np.zeros(s.shape[0], dtype=np.int64)
+    lib().orc_nms_variant.restype = C.c_int64
+    c = lib().orc_nms_variant(_p(b), _p(s), C.c_int64(s.shape[0]), C.c_float(thresh), C.c_int(flags), _p(keep))
+    return keep[:int(c)]
+
+
+def facebox_default_boxes():
+    """FACEBOX/encoderl.py:21-46: python-float arithmetic, one rounding to fp32 at torch.Tensor(boxes)."""
+    import itertools
+    scale = 1024.
+    steps = [s / scale for s in (32, 64, 128)]
+    sizes = [s / scale for s in (32, 256, 512)]
+    aspect_ratios = ((1, 2, 4), (1,), (1,))
+    feature_map_sizes = (32, 16, 8)
+    density = [[-3, -1, 1, 3], [-1, 1], [0]]
+    boxes = []
+    for i in range(len(feature_map_sizes)):
+        fmsize = feature_map_sizes[i]
+        for h, w in itertools.product(range(fmsize), repeat=2):
+            cx = (w + 0.5) * steps[i]
+            cy = (h + 0.5) * steps[i]
+            s = sizes[i]
+            for j, ar in enumerate(aspect_ratios[i]):
+                if i == 0:
+                    for dx, dy in itertools.product(density[j], repeat=2):
+                        boxes.append((cx + dx / 8. * s * ar, cy + dy / 8. * s * ar, s * ar, s * ar))
+                else:
+                    boxes.append((cx, cy, s * ar, s * ar))
+    return np.array(boxes, dtype=np.float64).astype(np.float32)
+
+
+def facebox_decode(loc, default_boxes):
+    l = _f32(loc).reshape(-1, 4); d = _f32(default_boxes).reshape(-1, 4)
+    out = np.empty_like(l)
+    lib().orc_facebox_decode(_p(l), _p(d), C.c_int64(l.shape[0]), C.c_float(0.1), C.c_float(0.2), _p(out))
+    return out
+
+
+def facebox_decode_np(loc, conf, default_boxes, conf_thres=0.35, nms_thresh=0.5):
+    """DataEncoder.decode_np (encoderl.py:308-325) -> (boxes[keep], scores[keep])."""
+    score = _f32(conf)[:, 1]
+    ids = np.where(score > np.float32(conf_thres))[0]
+    boxes = facebox_decode(_f32(loc)[ids], _f32(default_boxes)[ids])
+    keep = nms_variant(boxes, score[ids], nms_thresh, NMS_SUMFIRST)
+    return boxes[keep], score[ids][keep]
