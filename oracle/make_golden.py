@@ -438,8 +438,40 @@ def gen_siblings():
     save("siblings", **d)
 
 
+# ------------------------------------------------------------------ 9. on-disk formats
+def gen_formats():
+    from data.widerface import AnnotationTransform as RefAT                      # noqa: E402  (reference)
+    lines = ["a/b/img0.jpg 3 10 20 30 40 5 6 0 9 100 120 -20 35",
+             "c.jpg 2 7 8 9 -10 1 2 3 4",
+             "d.jpg 0",
+             open(os.path.join(REF, "image_and_anno/anno/gen_anno_file_val")).readline().strip()]
+    d = {"lines": np.array(lines)}
+    for i, ln in enumerate(lines):
+        f = ln.strip().split()
+        d[f"at_{i}"] = np.array(RefAT()(f[1:], 640, 480), dtype=np.float64).reshape(-1, 5)
+        num = int(f[1]); tgt = list(f[1:]); del tgt[0]                           # utils/data_collector.py:46-51
+        d[f"px_{i}"] = np.array(tgt).astype(np.int32).reshape(num, 4)
+    # PR data: My_test.py:105, :161, :166-171 and draw_pr_roc.py:5-19, :27-34 restated (both are scripts, not importable)
+    rng = np.random.Generator(np.random.PCG64(61))
+    tf_conf = np.array([[], []]); truth_num = 0
+    for _ in range(5):
+        n = int(rng.integers(1, 40))
+        tfi = np.vstack(((rng.uniform(size=n) > 0.4).astype(np.int32), rng.uniform(0.0, 1.0, n)))
+        tf_conf = np.hstack((tf_conf, tfi)); truth_num += int(rng.integers(1, 30))
+    d["pr_tf_conf"] = tf_conf; d["pr_truth_num"] = np.int64(truth_num)
+    srt = tf_conf[:, np.argsort(tf_conf[1, :])[::-1]]
+    data = np.hstack((srt, [[0], [truth_num]]))
+    d["pr_file"] = data
+    _, M = data[:, :-1].shape
+    tp, fp = np.zeros(M), np.zeros(M)
+    for i in range(1, M + 1):
+        tp[i - 1] = np.count_nonzero(data[0, :i]); fp[i - 1] = i - tp[i - 1]
+    d["pr_tp"] = tp; d["pr_fp"] = fp; d["pr_recall"] = tp / data[1, -1]; d["pr_precision"] = tp / (tp + fp)
+    save("formats", **d)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["priorbox", "boxutils", "nms", "detect", "multibox", "tracker", "heads", "siblings"]
+    which = sys.argv[1:] or ["priorbox", "boxutils", "nms", "detect", "multibox", "tracker", "heads", "siblings", "formats"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()
