@@ -55,14 +55,17 @@ __device__ __forceinline__ float iou_match(const float4 a, const float area_a, c
 
 __device__ __forceinline__ void finalize_prior(const float *__restrict__ gt, int64_t g0, int idx, float ov, float thr,
                                                float4 pr, float v0, float v1, float4 *loc_t, int64_t *conf_t,
-                                               int32_t *bti, float *bto, int64_t t)
+                                               int32_t *bti, float *bto, int64_t t, const bool encode_all)
 {
     const float *row = gt + 5 * (g0 + idx);
     float4 m = make_float4(row[0], row[1], row[2], row[3]);
     float c = row[4] + 1.0f;                           // box_utils.py:205
     if (ov < thr) c = 0.0f;                            // :206
-    conf_t[t] = (int64_t)c;                            // :210 (float -> long)
-    loc_t[t] = fdt_encode1(m, pr, v0, v1);             // :208
+    const int64_t label = (int64_t)c;                  // :210 (float -> long)
+    conf_t[t] = label;
+    // :208 encodes every prior; the loss only ever reads the positives (multibox_loss.py:96-101), so the fused forward
+    // (encode_all = false) spares the two fp64 logs and four divisions of the ~99 % background priors and stores zeros
+    loc_t[t] = (encode_all || label > 0) ? fdt_encode1(m, pr, v0, v1) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (bti) bti[t] = idx;
     if (bto) bto[t] = ov;
 }
@@ -74,17 +77,20 @@ __device__ __forceinline__ void finalize_prior(const float *__restrict__ gt, int
 // map rows), so at the fine pyramid levels ~90 % of the GT boxes drop out.  GT 0 is never culled (it seeds the argmax,
 // box_utils.py:197 returns index 0 when all overlaps are 0) and in bipartite mode block 0 culls nothing, so the first prior
 // still wins an all-zero row of overlaps.max(1) (:136).
+// Default (non-bipartite) matching culls a second time per WARP, against the bounding box of the warp's 32 consecutive
+// priors (same argument): at the fine levels a warp spans a 144 x 16 pixel strip and keeps ~1/3 of what the block kept.
 template <bool BIP>
 __global__ void __launch_bounds__(M_THREADS)
 k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const int64_t *__restrict__ gt_off,
         int64_t N, float thr, float v0, float v1,
         float4 *__restrict__ loc_t, int64_t *__restrict__ conf_t, int32_t *__restrict__ bti, float *__restrict__ bto,
-        int32_t *__restrict__ tmp_idx, float *__restrict__ tmp_ov, unsigned long long *__restrict__ bestprior)
+        int32_t *__restrict__ tmp_idx, float *__restrict__ tmp_ov, unsigned long long *__restrict__ bestprior, const bool encode_all)
 {
     __shared__ GtTile tile;
     __shared__ unsigned long long s_best[BIP ? GT_TILE : 1][BIP ? M_WARPS : 1];
     __shared__ unsigned s_bb[4];
     __shared__ int s_wcnt[M_WARPS];
+    __shared__ unsigned char s_wlist[BIP ? 1 : M_WARPS][BIP ? 1 : GT_TILE];     // per warp: tile slots that survive the warp's cull
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t p = (int64_t)blockIdx.x * M_THREADS + tid;
     const bool valid = p < N;
@@ -106,11 +112,13 @@ k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const i
     // bounding box of the block's priors (order-preserving integer keys make float min/max an integer atomic)
     if (tid < 4) s_bb[tid] = tid < 2 ? 0xffffffffu : 0u;
     __syncthreads();
+    float4 wb;                                         // bounding box of the warp's priors
     {
         unsigned k0 = valid ? fdt_float_key(pf.x) : 0xffffffffu, k1 = valid ? fdt_float_key(pf.y) : 0xffffffffu;
         unsigned k2 = valid ? fdt_float_key(pf.z) : 0u, k3 = valid ? fdt_float_key(pf.w) : 0u;
         k0 = __reduce_min_sync(0xffffffffu, k0); k1 = __reduce_min_sync(0xffffffffu, k1);
         k2 = __reduce_max_sync(0xffffffffu, k2); k3 = __reduce_max_sync(0xffffffffu, k3);
+        wb = make_float4(fdt_key_float(k0), fdt_key_float(k1), fdt_key_float(k2), fdt_key_float(k3));
         if (lane == 0) { atomicMin(&s_bb[0], k0); atomicMin(&s_bb[1], k1); atomicMax(&s_bb[2], k2); atomicMax(&s_bb[3], k3); }
     }
     __syncthreads();
@@ -141,7 +149,32 @@ k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const i
             tile.box[ps] = a; tile.area[ps] = (a.z - a.x) * (a.w - a.y); tile.idx[ps] = t0 + tid;
         }
         __syncthreads();
-        for (int g = 0; g < tc; ++g) {
+        if (!BIP) {
+            // ---- second cull, per warp (order preserved), then the IoU loop over what is left
+            int wn = 0;
+            for (int gb = 0; gb < tc; gb += 32) {
+                const int g = gb + lane;
+                bool k2 = false;
+                if (g < tc) {
+                    const float4 a2 = tile.box[g];
+                    const float wbb = fminf(a2.z, wb.z) - fmaxf(a2.x, wb.x), hbb = fminf(a2.w, wb.w) - fmaxf(a2.y, wb.y);
+                    k2 = (tile.idx[g] == 0) || !(wbb <= 0.0f || hbb <= 0.0f);      // NaN keeps
+                }
+                const unsigned bal2 = __ballot_sync(0xffffffffu, k2);
+                if (k2) s_wlist[warp][wn + __popc(bal2 & ((1u << lane) - 1u))] = (unsigned char)g;
+                wn += __popc(bal2);
+            }
+            __syncwarp();
+            for (int q = 0; q < wn; ++q) {
+                const int g = s_wlist[warp][q];
+                const float v = iou_match(tile.box[g], tile.area[g], pf, area_b);
+                const int gi = tile.idx[g];
+                if (gi == 0) { best = v; bi = 0; }
+                else if (v > best) { best = v; bi = gi; }                      // first index wins ties (:197)
+            }
+            __syncwarp();
+        }
+        for (int g = 0; BIP && g < tc; ++g) {
             const float v = iou_match(tile.box[g], tile.area[g], pf, area_b);
             const int gi = tile.idx[g];
             if (gi == 0) { best = v; bi = 0; }
@@ -166,7 +199,7 @@ k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const i
     }
     if (!valid) return;
     if (BIP) { tmp_idx[t] = bi; tmp_ov[t] = best; }
-    else finalize_prior(gt, g0, bi, best, thr, pr, v0, v1, loc_t, conf_t, bti, bto, t);
+    else finalize_prior(gt, g0, bi, best, thr, pr, v0, v1, loc_t, conf_t, bti, bto, t, encode_all);
 }
 
 // box_utils.py:150-154: best_truth_overlap[best_prior_idx[j]] = 2; best_truth_idx[best_prior_idx[j]] = j (last j wins)
@@ -175,7 +208,7 @@ k_match_bipartite_finalize(const float4 *__restrict__ priors, const float *__res
                            int64_t N, float thr, float v0, float v1,
                            float4 *__restrict__ loc_t, int64_t *__restrict__ conf_t, int32_t *__restrict__ bti, float *__restrict__ bto,
                            const int32_t *__restrict__ tmp_idx, const float *__restrict__ tmp_ov,
-                           const unsigned long long *__restrict__ bestprior)
+                           const unsigned long long *__restrict__ bestprior, const bool encode_all)
 {
     __shared__ unsigned s_bp[GT_TILE];
     const int b = blockIdx.y, tid = threadIdx.x;
@@ -195,7 +228,7 @@ k_match_bipartite_finalize(const float4 *__restrict__ priors, const float *__res
         for (int j = 0; j < tn; ++j)
             if (s_bp[j] == (unsigned)p) { idx = t0 + j; ov = 2.0f; }
     }
-    if (valid) finalize_prior(gt, g0, idx, ov, thr, priors[p], v0, v1, loc_t, conf_t, bti, bto, t);
+    if (valid) finalize_prior(gt, g0, idx, ov, thr, priors[p], v0, v1, loc_t, conf_t, bti, bto, t, encode_all);
 }
 
 // ---------------------------------------------------------------------------------------------- loss
@@ -446,21 +479,21 @@ MatchWs plan_match_ws(void *ws, int B, int64_t N, int64_t total_gt)
 
 int launch_match(const float *priors, const float *gt, const int64_t *gt_off, int B, int64_t N, int64_t total_gt,
                  float thr, float v0, float v1, int bipartite, float *loc_t, int64_t *conf_t, int32_t *bti, float *bto,
-                 void *ws, cudaStream_t st)
+                 void *ws, cudaStream_t st, bool encode_all = true)
 {
     dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
     MatchWs m = plan_match_ws(ws, B, N, total_gt);
     if (!bipartite) {
         k_match<false><<<grid, M_THREADS, 0, st>>>((const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t, conf_t,
-                                                   bti, bto, nullptr, nullptr, nullptr);
+                                                   bti, bto, nullptr, nullptr, nullptr, encode_all);
         FDT_LAUNCH_CHECK();
     } else {
         FDT_CUDA(cudaMemsetAsync(m.bestprior, 0, (size_t)(total_gt > 0 ? total_gt : 1) * 8, st));
         k_match<true><<<grid, M_THREADS, 0, st>>>((const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t, conf_t,
-                                                  bti, bto, m.tmp_idx, m.tmp_ov, m.bestprior);
+                                                  bti, bto, m.tmp_idx, m.tmp_ov, m.bestprior, encode_all);
         FDT_LAUNCH_CHECK();
         k_match_bipartite_finalize<<<grid, M_THREADS, 0, st>>>((const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t,
-                                                               conf_t, bti, bto, m.tmp_idx, m.tmp_ov, m.bestprior);
+                                                               conf_t, bti, bto, m.tmp_idx, m.tmp_ov, m.bestprior, encode_all);
         FDT_LAUNCH_CHECK();
     }
     return FDT_OK;
@@ -586,7 +619,7 @@ FDT_API int fdt_multibox_loss_forward(const float *loc, const float *conf, const
     if (blocks > FDT_NUM_SMS * 8) blocks = FDT_NUM_SMS * 8;
     k_conf_global_max<<<blocks, 256, 0, st>>>(conf, n_conf, &w.acc->gmax_key);
     FDT_LAUNCH_CHECK();
-    rc = launch_match(priors, gt, gt_off, B, N, total_gt, threshold, var0, var1, bipartite, loc_t, conf_t, nullptr, nullptr, w.match, st);
+    rc = launch_match(priors, gt, gt_off, B, N, total_gt, threshold, var0, var1, bipartite, loc_t, conf_t, nullptr, nullptr, w.match, st, false);
     if (rc != FDT_OK) return rc;
     dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
     k_loss_prior<<<grid, M_THREADS, 0, st>>>((const float4 *)loc, conf, (const float4 *)loc_t, conf_t, N, C, w.acc, lca, w.mine.num_pos, w.mine.hist);

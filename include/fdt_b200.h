@@ -207,7 +207,9 @@ int fdt_hard_negative_mine(const float *loss_c, const uint8_t *pos, int B, int64
 /* ---- L2  MultiBoxLoss.forward / backward  (layers/modules/multibox_loss.py:48-136) ---------------
  * forward: match+encode, smooth-L1 over positives, per-prior CE, mining, CE over pos U neg.
  * losses[2] (device) = {loss_l/N, loss_c/N}; norm[1] (device) = N.  loc_t/conf_t/sel are outputs the
- * backward pass reuses (sel[B,N] uint8 = pos | neg).
+ * backward pass reuses (sel[B,N] uint8 = pos | neg).  loc_t holds the encoded target at the POSITIVE priors
+ * (conf_t > 0) and zeros elsewhere: the reference encodes every prior (box_utils.py:208) but its loss only reads
+ * the positives (multibox_loss.py:96-101) and never returns the tensor; fdt_match_encode fills all rows.
  * backward: grad_loc[B,N,4], grad_conf[B,N,C] for upstream gradients g_l, g_c (host scalars). */
 size_t fdt_multibox_workspace_bytes(int B, int64_t N, int C, int64_t total_gt);
 int fdt_multibox_loss_forward(const float *loc, const float *conf, const float *priors,
