@@ -318,8 +318,8 @@ def main():
         roofline = {"bound": "hbm", "kernel": "k_sort_nms (select/sort + decode + lazy NMS + output rows)",
                     "achieved": k3_bytes / (k3 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                     "frac": k3_bytes / (k3 * 1e-3) / 1e9 / peak,
-                    "traffic": 12.54e6,      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full of this config
-                    "traffic_source": "profiles/r01_sortnms_v5_cluster_sass_regions.csv (12.54 MB read, 768 B written)",
+                    "traffic": 12.554e6,     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full of this config
+                    "traffic_source": "profiles/r01_sortnms_v6_phases.txt (12.547 MB read, 7.2 KB written)",
                     "peak_source": peak_src,
                     "kernel_ms": k3, "kernel_share_of_step": k3 / ms_per_step,
                     "algorithmic_bytes_per_launch": k3_bytes,
@@ -371,7 +371,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args.mode, world, gather),
                                                                 l2="flushed between steps (256 MiB memset + 0.1 ms spin outside the event pairs)"),
-            "clocks": sampler.result(), "e2e": e2e, "gpu_launches": 2 * args.steps,
+            "clocks": sampler.result(), "e2e": e2e, "gpu_launches": 3 * args.steps,      # k_zero_counters, k_threshold_compact, k_sort_nms
             "wall_s_timed_region": wall}
     if roofline:
         line["roofline"] = roofline
