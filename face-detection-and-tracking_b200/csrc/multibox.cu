@@ -20,11 +20,32 @@
 
 namespace {
 
+// Launch behind the previous kernel of the stream with programmatic stream serialization: the grid is scheduled while its
+// predecessor drains and every kernel below starts with fdt_pdl_enter() (let the successor be scheduled, then wait for the
+// predecessor's results).  The forward is a chain of six short kernels; the hand-overs are a sizeable part of it.
+__device__ __forceinline__ void fdt_pdl_enter()
+{
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 constexpr int M_THREADS = 256;
 constexpr int M_WARPS = M_THREADS / 32;
 constexpr int GT_TILE = 256;
 constexpr int MINE_THREADS = 1024;
 constexpr int MINE_BINS = 4096;             // 12-bit digits
+constexpr int MINE_COLLECT = 2048;          // k_mine_select: largest level-0 bin finished by one collecting scan
 constexpr int MINE_REPL = 16;               // level-0 histogram copies (by prior index) to spread same-address atomics
 
 __device__ __forceinline__ unsigned long long mine_comp(float v, unsigned p) { return ((unsigned long long)fdt_float_key(v) << 32) | (unsigned)~p; }
@@ -86,6 +107,7 @@ k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const i
         float4 *__restrict__ loc_t, int64_t *__restrict__ conf_t, int32_t *__restrict__ bti, float *__restrict__ bto,
         int32_t *__restrict__ tmp_idx, float *__restrict__ tmp_ov, unsigned long long *__restrict__ bestprior, const bool encode_all)
 {
+    fdt_pdl_enter();
     __shared__ GtTile tile;
     __shared__ unsigned long long s_best[BIP ? GT_TILE : 1][BIP ? M_WARPS : 1];
     __shared__ unsigned s_bb[4];
@@ -202,6 +224,99 @@ k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const i
     else finalize_prior(gt, g0, bi, best, thr, pr, v0, v1, loc_t, conf_t, bti, bto, t, encode_all);
 }
 
+// Default (non-bipartite) matcher, the production one (MyTrain_repo.py:113): the same per-warp culling as above but WITHOUT the
+// block-level stage -- the GT boxes of a tile are staged once, then every warp lists the boxes that touch the bounding box of its
+// 32 consecutive priors (ascending index, so the first-index tie rule holds; GT 0 is always listed) and runs the IoU loop over its
+// own list.  Two block barriers per tile instead of six and no compaction bookkeeping: k_match<false> spent more instructions around
+// the IoU loop than in it.  Optionally folds in the global maximum of `conf` that log_sum_exp needs (box_utils.py:268): one block
+// reduction and one atomicMax per block instead of a separate pass over conf.
+__global__ void __launch_bounds__(M_THREADS)
+k_match_default(const float4 *__restrict__ priors, const float *__restrict__ gt, const int64_t *__restrict__ gt_off,
+                int64_t N, float thr, float v0, float v1,
+                float4 *__restrict__ loc_t, int64_t *__restrict__ conf_t, int32_t *__restrict__ bti, float *__restrict__ bto,
+                const bool encode_all, const float *__restrict__ conf, int C, unsigned *__restrict__ gmax_key)
+{
+    fdt_pdl_enter();
+    __shared__ float4 s_box[GT_TILE];
+    __shared__ float s_area[GT_TILE];
+    __shared__ unsigned char s_wl[M_WARPS][GT_TILE];
+    __shared__ unsigned s_cmax[M_WARPS];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t p = (int64_t)blockIdx.x * M_THREADS + tid;
+    const bool valid = p < N;
+    const int64_t g0 = gt_off[b];
+    const int G = (int)(gt_off[b + 1] - g0);
+    const int64_t t = (int64_t)b * N + p;
+    if (conf) {                                        // global max of conf for log_sum_exp (every block, also for images without GT)
+        unsigned k = 0u;
+        if (valid) for (int c = 0; c < C; ++c) k = max(k, fdt_float_key(__ldg(conf + t * C + c)));
+        k = __reduce_max_sync(0xffffffffu, k);
+        if (lane == 0) s_cmax[warp] = k;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned m = s_cmax[0];
+#pragma unroll
+            for (int w = 1; w < M_WARPS; ++w) m = max(m, s_cmax[w]);
+            atomicMax(gmax_key, m);
+        }
+    }
+    const float4 pr = priors[valid ? p : 0];
+    if (G <= 0) {                                      // reference raises (Q3); defined: all background
+        if (valid) {
+            conf_t[t] = 0; loc_t[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bti) bti[t] = 0;
+            if (bto) bto[t] = 0.0f;
+        }
+        return;
+    }
+    const float hw = pr.z / 2.0f, hh = pr.w / 2.0f;    // point_form, box_utils.py:15-16
+    const float4 pf = make_float4(pr.x - hw, pr.y - hh, pr.x + hw, pr.y + hh);
+    const float area_b = (pf.z - pf.x) * (pf.w - pf.y);
+    float4 wb;                                         // bounding box of the warp's priors
+    {
+        unsigned k0 = valid ? fdt_float_key(pf.x) : 0xffffffffu, k1 = valid ? fdt_float_key(pf.y) : 0xffffffffu;
+        unsigned k2 = valid ? fdt_float_key(pf.z) : 0u, k3 = valid ? fdt_float_key(pf.w) : 0u;
+        k0 = __reduce_min_sync(0xffffffffu, k0); k1 = __reduce_min_sync(0xffffffffu, k1);
+        k2 = __reduce_max_sync(0xffffffffu, k2); k3 = __reduce_max_sync(0xffffffffu, k3);
+        wb = make_float4(fdt_key_float(k0), fdt_key_float(k1), fdt_key_float(k2), fdt_key_float(k3));
+    }
+    float best = 0.0f;
+    int bi = 0;
+    for (int t0 = 0; t0 < G; t0 += GT_TILE) {
+        const int tn = min(GT_TILE, G - t0);
+        __syncthreads();                               // previous tile fully consumed
+        if (tid < tn) {
+            const float *row = gt + 5 * (g0 + t0 + tid);
+            const float4 a = make_float4(row[0], row[1], row[2], row[3]);
+            s_box[tid] = a; s_area[tid] = (a.z - a.x) * (a.w - a.y);
+        }
+        __syncthreads();
+        int wn = 0;
+        for (int gb = 0; gb < tn; gb += 32) {
+            const int g = gb + lane;
+            bool k2 = false;
+            if (g < tn) {
+                const float4 a2 = s_box[g];
+                const float wbb = fminf(a2.z, wb.z) - fmaxf(a2.x, wb.x), hbb = fminf(a2.w, wb.w) - fmaxf(a2.y, wb.y);
+                k2 = (t0 + g == 0) || !(wbb <= 0.0f || hbb <= 0.0f);           // NaN keeps
+            }
+            const unsigned bal2 = __ballot_sync(0xffffffffu, k2);
+            if (k2) s_wl[warp][wn + __popc(bal2 & ((1u << lane) - 1u))] = (unsigned char)g;
+            wn += __popc(bal2);
+        }
+        __syncwarp();
+        for (int q = 0; q < wn; ++q) {
+            const int g = s_wl[warp][q];
+            const float v = iou_match(s_box[g], s_area[g], pf, area_b);
+            const int gi = t0 + g;
+            if (gi == 0) { best = v; bi = 0; }
+            else if (v > best) { best = v; bi = gi; }                          // first index wins ties (:197)
+        }
+        __syncwarp();
+    }
+    if (valid) finalize_prior(gt, g0, bi, best, thr, pr, v0, v1, loc_t, conf_t, bti, bto, t, encode_all);
+}
+
 // box_utils.py:150-154: best_truth_overlap[best_prior_idx[j]] = 2; best_truth_idx[best_prior_idx[j]] = j (last j wins)
 __global__ void __launch_bounds__(M_THREADS)
 k_match_bipartite_finalize(const float4 *__restrict__ priors, const float *__restrict__ gt, const int64_t *__restrict__ gt_off,
@@ -210,6 +325,7 @@ k_match_bipartite_finalize(const float4 *__restrict__ priors, const float *__res
                            const int32_t *__restrict__ tmp_idx, const float *__restrict__ tmp_ov,
                            const unsigned long long *__restrict__ bestprior, const bool encode_all)
 {
+    fdt_pdl_enter();
     __shared__ unsigned s_bp[GT_TILE];
     const int b = blockIdx.y, tid = threadIdx.x;
     const int64_t p = (int64_t)blockIdx.x * M_THREADS + tid;
@@ -234,6 +350,7 @@ k_match_bipartite_finalize(const float4 *__restrict__ priors, const float *__res
 // ---------------------------------------------------------------------------------------------- loss
 __global__ void k_conf_global_max(const float *__restrict__ x, int64_t n, unsigned *__restrict__ gmax_key)
 {
+    fdt_pdl_enter();
     unsigned k = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         k = max(k, fdt_float_key(x[i]));
@@ -270,6 +387,7 @@ k_loss_prior(const float4 *__restrict__ loc, const float *__restrict__ conf, con
              const int64_t *__restrict__ conf_t, int64_t N, int C, LossAcc *__restrict__ acc,
              float *__restrict__ loss_c_all, int32_t *__restrict__ num_pos, int *__restrict__ hist)
 {
+    fdt_pdl_enter();
     __shared__ double s_red[M_WARPS];
     __shared__ int s_cnt[M_WARPS];
     const int b = blockIdx.y;
@@ -307,6 +425,7 @@ k_loss_prior(const float4 *__restrict__ loc, const float *__restrict__ conf, con
 __global__ void __launch_bounds__(M_THREADS)
 k_mine_hist(const float *__restrict__ loss_c, const uint8_t *__restrict__ pos, int64_t N, int *__restrict__ hist, int32_t *__restrict__ num_pos)
 {
+    fdt_pdl_enter();
     __shared__ int s_cnt[M_WARPS];
     const int b = blockIdx.y;
     const int64_t p = (int64_t)blockIdx.x * M_THREADS + threadIdx.x;
@@ -324,9 +443,12 @@ __global__ void __launch_bounds__(MINE_THREADS, 1)
 k_mine_select(const float *__restrict__ loss_c, const int *__restrict__ hist0, const int32_t *__restrict__ num_pos, int64_t N,
               int negpos_ratio, unsigned long long *__restrict__ cutoff)
 {
+    fdt_pdl_enter();
     __shared__ int s_h[MINE_BINS];
     __shared__ int s_warp[33];
     __shared__ int s_sel[3];
+    __shared__ unsigned long long s_cand[MINE_COLLECT];      // composites of the straddling level-0 bin
+    __shared__ int s_ncand;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *lrow = loss_c + (int64_t)b * N;
     long long num_neg = (long long)negpos_ratio * num_pos[b];                   // multibox_loss.py:115
@@ -334,6 +456,7 @@ k_mine_select(const float *__restrict__ loss_c, const int *__restrict__ hist0, c
     if (num_neg <= 0) { if (tid == 0) cutoff[b] = ~0ull; return; }
     int need = (int)num_neg;
     unsigned long long prefix = 0, pmask = 0;
+    bool collected = false;
     for (int level = 0, shift = 52; ; ++level, shift -= 12) {
         const int sh = shift < 0 ? 0 : shift;
         const int nb = shift < 0 ? 16 : MINE_BINS;                            // last level: the 4 lowest bits
@@ -347,9 +470,17 @@ k_mine_select(const float *__restrict__ loss_c, const int *__restrict__ hist0, c
         } else {
             for (int i = tid; i < MINE_BINS; i += MINE_THREADS) s_h[i] = 0;
             __syncthreads();
-            for (int64_t p = tid; p < N; p += MINE_THREADS) {
-                const unsigned long long c = mine_comp(lrow[p], (unsigned)p);
-                if ((c & pmask) == prefix) atomicAdd(&s_h[(int)((c >> sh) & (unsigned long long)(nb - 1))], 1);
+            if (collected) {
+                const int nc = s_ncand;
+                for (int e = tid; e < nc; e += MINE_THREADS) {
+                    const unsigned long long c = s_cand[e];
+                    if ((c & pmask) == prefix) atomicAdd(&s_h[(int)((c >> sh) & (unsigned long long)(nb - 1))], 1);
+                }
+            } else {
+                for (int64_t p = tid; p < N; p += MINE_THREADS) {
+                    const unsigned long long c = mine_comp(lrow[p], (unsigned)p);
+                    if ((c & pmask) == prefix) atomicAdd(&s_h[(int)((c >> sh) & (unsigned long long)(nb - 1))], 1);
+                }
             }
         }
         __syncthreads();
@@ -380,25 +511,44 @@ k_mine_select(const float *__restrict__ loss_c, const int *__restrict__ hist0, c
         pmask |= (unsigned long long)(nb - 1) << sh;
         need = s_sel[1];
         const bool done = (s_sel[2] == need) || shift < 0;                     // whole bin taken, or all 64 bits fixed
+        const int bin_count = s_sel[2];
         __syncthreads();
         if (done) break;
+        if (level == 0 && bin_count <= MINE_COLLECT) {
+            // The cutoff lies inside one level-0 bin of at most MINE_COLLECT composites: ONE scan of the row collects them and
+            // the remaining levels histogram that list in shared memory instead of re-reading the row from L2 each time.
+            if (tid == 0) s_ncand = 0;
+            __syncthreads();
+            for (int64_t p = tid; p < N; p += MINE_THREADS) {
+                const unsigned long long c = mine_comp(lrow[p], (unsigned)p);
+                if ((c & pmask) == prefix) s_cand[atomicAdd(&s_ncand, 1)] = c;
+            }
+            __syncthreads();
+            collected = true;
+        }
     }
     if (tid == 0) cutoff[b] = prefix;
 }
 
 // MODE 0: neg mask only.  MODE 1: sel = pos | neg and CE over the selection (F.cross_entropy, sum).
+// A block covers APPLY_TILES consecutive tiles of one image: the fp64 atomicAdd on the single loss accumulator is the serial
+// resource here (one per block), so fewer, longer blocks finish sooner than one block per 256 priors.
+constexpr int APPLY_TILES = 8;
 template <int MODE>
 __global__ void __launch_bounds__(M_THREADS)
 k_mine_apply(const float *__restrict__ loss_c, const unsigned long long *__restrict__ cutoff, const int64_t *__restrict__ conf_t,
              const float *__restrict__ conf, int64_t N, int C, uint8_t *__restrict__ out_mask, LossAcc *__restrict__ acc)
 {
+    fdt_pdl_enter();
     __shared__ double s_red[M_WARPS];
     const int b = blockIdx.y;
-    const int64_t p = (int64_t)blockIdx.x * M_THREADS + threadIdx.x;
+    const unsigned long long cut = cutoff[b];
     double ce = 0.0;
-    if (p < N) {
+#pragma unroll 2
+    for (int u = 0; u < APPLY_TILES; ++u) {
+        const int64_t p = ((int64_t)blockIdx.x * APPLY_TILES + u) * M_THREADS + threadIdx.x;
+        if (p >= N) break;
         const int64_t t = (int64_t)b * N + p;
-        const unsigned long long cut = cutoff[b];
         const bool neg = cut != ~0ull && mine_comp(loss_c[t], (unsigned)p) >= cut;          // multibox_loss.py:116
         const int64_t label = (MODE == 1) ? conf_t[t] : 0;
         const bool sel = neg || (MODE == 1 && label > 0);
@@ -409,7 +559,7 @@ k_mine_apply(const float *__restrict__ loss_c, const unsigned long long *__restr
             for (int c = 1; c < C; ++c) m = fmaxf(m, row[c]);
             double s = 0.0;
             for (int c = 0; c < C; ++c) s += exp((double)(row[c] - m));
-            ce = (log(s) + (double)m) - (double)row[label];                                  // :128
+            ce += (log(s) + (double)m) - (double)row[label];                                 // :128
         }
     }
     if (MODE == 1) {
@@ -421,6 +571,7 @@ k_mine_apply(const float *__restrict__ loss_c, const unsigned long long *__restr
 __global__ void k_loss_final(const LossAcc *__restrict__ acc, const int32_t *__restrict__ num_pos, int B,
                              float *__restrict__ losses, float *__restrict__ norm)
 {
+    fdt_pdl_enter();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     long long n = 0;
     for (int b = 0; b < B; ++b) n += num_pos[b];
@@ -479,21 +630,21 @@ MatchWs plan_match_ws(void *ws, int B, int64_t N, int64_t total_gt)
 
 int launch_match(const float *priors, const float *gt, const int64_t *gt_off, int B, int64_t N, int64_t total_gt,
                  float thr, float v0, float v1, int bipartite, float *loc_t, int64_t *conf_t, int32_t *bti, float *bto,
-                 void *ws, cudaStream_t st, bool encode_all = true)
+                 void *ws, cudaStream_t st, bool encode_all = true, const float *conf = nullptr, int C = 0, unsigned *gmax_key = nullptr)
 {
     dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
     MatchWs m = plan_match_ws(ws, B, N, total_gt);
     if (!bipartite) {
-        k_match<false><<<grid, M_THREADS, 0, st>>>((const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t, conf_t,
-                                                   bti, bto, nullptr, nullptr, nullptr, encode_all);
+        FDT_CUDA(launch_pdl(k_match_default, grid, dim3(M_THREADS), st, (const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t, conf_t,
+                                                    bti, bto, encode_all, conf, C, gmax_key));
         FDT_LAUNCH_CHECK();
     } else {
         FDT_CUDA(cudaMemsetAsync(m.bestprior, 0, (size_t)(total_gt > 0 ? total_gt : 1) * 8, st));
-        k_match<true><<<grid, M_THREADS, 0, st>>>((const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t, conf_t,
-                                                  bti, bto, m.tmp_idx, m.tmp_ov, m.bestprior, encode_all);
+        FDT_CUDA(launch_pdl(k_match<true>, grid, dim3(M_THREADS), st, (const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t, conf_t,
+                                                  bti, bto, m.tmp_idx, m.tmp_ov, m.bestprior, encode_all));
         FDT_LAUNCH_CHECK();
-        k_match_bipartite_finalize<<<grid, M_THREADS, 0, st>>>((const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t,
-                                                               conf_t, bti, bto, m.tmp_idx, m.tmp_ov, m.bestprior, encode_all);
+        FDT_CUDA(launch_pdl(k_match_bipartite_finalize, grid, dim3(M_THREADS), st, (const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t,
+                                                               conf_t, bti, bto, (const int32_t *)m.tmp_idx, (const float *)m.tmp_ov, (const unsigned long long *)m.bestprior, encode_all));
         FDT_LAUNCH_CHECK();
     }
     return FDT_OK;
@@ -516,10 +667,10 @@ template <int MODE>
 int launch_mine_tail(const float *loss_c, const MineWs &m, const int64_t *conf_t, const float *conf, int B, int64_t N, int C,
                      int ratio, uint8_t *mask, LossAcc *acc, cudaStream_t st)
 {
-    k_mine_select<<<B, MINE_THREADS, 0, st>>>(loss_c, m.hist, m.num_pos, N, ratio, m.cutoff);
+    FDT_CUDA(launch_pdl(k_mine_select, dim3(B), dim3(MINE_THREADS), st, loss_c, (const int *)m.hist, (const int32_t *)m.num_pos, N, ratio, m.cutoff));
     FDT_LAUNCH_CHECK();
-    dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
-    k_mine_apply<MODE><<<grid, M_THREADS, 0, st>>>(loss_c, m.cutoff, conf_t, conf, N, C, mask, acc);
+    dim3 grid((unsigned)((N + M_THREADS * APPLY_TILES - 1) / (M_THREADS * APPLY_TILES)), (unsigned)B);
+    FDT_CUDA(launch_pdl(k_mine_apply<MODE>, grid, dim3(M_THREADS), st, loss_c, (const unsigned long long *)m.cutoff, conf_t, conf, N, C, mask, acc));
     FDT_LAUNCH_CHECK();
     return FDT_OK;
 }
@@ -571,7 +722,7 @@ FDT_API int fdt_hard_negative_mine(const float *loss_c, const uint8_t *pos, int 
     FDT_REQUIRE(ws_bytes >= m.bytes, FDT_E_WORKSPACE, "fdt_hard_negative_mine: workspace %zu < %zu bytes", ws_bytes, m.bytes);
     FDT_CUDA(cudaMemsetAsync(ws, 0, m.bytes, st));
     dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
-    k_mine_hist<<<grid, M_THREADS, 0, st>>>(loss_c, pos, N, m.hist, m.num_pos);
+    FDT_CUDA(launch_pdl(k_mine_hist, grid, dim3(M_THREADS), st, loss_c, pos, N, m.hist, m.num_pos));
     FDT_LAUNCH_CHECK();
     return launch_mine_tail<0>(loss_c, m, nullptr, nullptr, B, N, 2, negpos_ratio, neg, nullptr, st);
 }
@@ -614,19 +765,22 @@ FDT_API int fdt_multibox_loss_forward(const float *loc, const float *conf, const
     float *lca = loss_c_all ? loss_c_all : w.loss_c_all;
 
     FDT_CUDA(cudaMemsetAsync(w.acc, 0, 256 + w.mine.bytes, st));
-    const int64_t n_conf = (int64_t)B * N * C;
-    unsigned blocks = (unsigned)((n_conf + 256 * 8 - 1) / (256 * 8));
-    if (blocks > FDT_NUM_SMS * 8) blocks = FDT_NUM_SMS * 8;
-    k_conf_global_max<<<blocks, 256, 0, st>>>(conf, n_conf, &w.acc->gmax_key);
-    FDT_LAUNCH_CHECK();
-    rc = launch_match(priors, gt, gt_off, B, N, total_gt, threshold, var0, var1, bipartite, loc_t, conf_t, nullptr, nullptr, w.match, st, false);
+    if (bipartite) {               // the default matcher folds the global max of conf (box_utils.py:268) into its own pass
+        const int64_t n_conf = (int64_t)B * N * C;
+        unsigned blocks = (unsigned)((n_conf + 256 * 8 - 1) / (256 * 8));
+        if (blocks > FDT_NUM_SMS * 8) blocks = FDT_NUM_SMS * 8;
+        k_conf_global_max<<<blocks, 256, 0, st>>>(conf, n_conf, &w.acc->gmax_key);
+        FDT_LAUNCH_CHECK();
+    }
+    rc = launch_match(priors, gt, gt_off, B, N, total_gt, threshold, var0, var1, bipartite, loc_t, conf_t, nullptr, nullptr, w.match, st, false,
+                      bipartite ? nullptr : conf, C, &w.acc->gmax_key);
     if (rc != FDT_OK) return rc;
     dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
-    k_loss_prior<<<grid, M_THREADS, 0, st>>>((const float4 *)loc, conf, (const float4 *)loc_t, conf_t, N, C, w.acc, lca, w.mine.num_pos, w.mine.hist);
+    FDT_CUDA(launch_pdl(k_loss_prior, grid, dim3(M_THREADS), st, (const float4 *)loc, conf, (const float4 *)loc_t, (const int64_t *)conf_t, N, C, w.acc, lca, w.mine.num_pos, w.mine.hist));
     FDT_LAUNCH_CHECK();
     rc = launch_mine_tail<1>(lca, w.mine, conf_t, conf, B, N, C, negpos_ratio, sel, w.acc, st);
     if (rc != FDT_OK) return rc;
-    k_loss_final<<<1, 32, 0, st>>>(w.acc, w.mine.num_pos, B, losses, norm);
+    FDT_CUDA(launch_pdl(k_loss_final, dim3(1), dim3(32), st, (const LossAcc *)w.acc, (const int32_t *)w.mine.num_pos, B, losses, norm));
     FDT_LAUNCH_CHECK();
     return FDT_OK;
 }
