@@ -32,7 +32,7 @@ constexpr int K2_TILE = K2_THREADS * K2_PER_THREAD;
 
 constexpr int K3_THREADS = 1024;
 constexpr int WIN = K3_THREADS;                 // sorted candidates examined per NMS round: one thread each
-constexpr int NB = 4096;                        // score buckets of the shared-memory bucket sort
+constexpr int NB = 2048;                        // score buckets of the shared-memory bucket sort
 constexpr int BIG_BUCKET = 512;                 // a larger bucket inside the top-k range -> full bitonic sort fallback
 constexpr int NLEV = 6;                         // grid levels: 32, 16, 8, 4, 2, 1 cells per side
 constexpr int NCELLS = 1024 + 256 + 64 + 16 + 4 + 1;

@@ -98,8 +98,8 @@ __device__ __forceinline__ void finalize_prior(const float *__restrict__ gt, int
 // map rows), so at the fine pyramid levels ~90 % of the GT boxes drop out.  GT 0 is never culled (it seeds the argmax,
 // box_utils.py:197 returns index 0 when all overlaps are 0) and in bipartite mode block 0 culls nothing, so the first prior
 // still wins an all-zero row of overlaps.max(1) (:136).
-// Default (non-bipartite) matching culls a second time per WARP, against the bounding box of the warp's 32 consecutive
-// priors (same argument): at the fine levels a warp spans a 144 x 16 pixel strip and keeps ~1/3 of what the block kept.
+// Only the bipartite matcher (BIP = true) is instantiated: it needs the block-level structure for the per-GT best-prior
+// reduction.  The default matcher is k_match_default below.
 template <bool BIP>
 __global__ void __launch_bounds__(M_THREADS)
 k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const int64_t *__restrict__ gt_off,
@@ -112,7 +112,6 @@ k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const i
     __shared__ unsigned long long s_best[BIP ? GT_TILE : 1][BIP ? M_WARPS : 1];
     __shared__ unsigned s_bb[4];
     __shared__ int s_wcnt[M_WARPS];
-    __shared__ unsigned char s_wlist[BIP ? 1 : M_WARPS][BIP ? 1 : GT_TILE];     // per warp: tile slots that survive the warp's cull
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t p = (int64_t)blockIdx.x * M_THREADS + tid;
     const bool valid = p < N;
@@ -134,13 +133,11 @@ k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const i
     // bounding box of the block's priors (order-preserving integer keys make float min/max an integer atomic)
     if (tid < 4) s_bb[tid] = tid < 2 ? 0xffffffffu : 0u;
     __syncthreads();
-    float4 wb;                                         // bounding box of the warp's priors
     {
         unsigned k0 = valid ? fdt_float_key(pf.x) : 0xffffffffu, k1 = valid ? fdt_float_key(pf.y) : 0xffffffffu;
         unsigned k2 = valid ? fdt_float_key(pf.z) : 0u, k3 = valid ? fdt_float_key(pf.w) : 0u;
         k0 = __reduce_min_sync(0xffffffffu, k0); k1 = __reduce_min_sync(0xffffffffu, k1);
         k2 = __reduce_max_sync(0xffffffffu, k2); k3 = __reduce_max_sync(0xffffffffu, k3);
-        wb = make_float4(fdt_key_float(k0), fdt_key_float(k1), fdt_key_float(k2), fdt_key_float(k3));
         if (lane == 0) { atomicMin(&s_bb[0], k0); atomicMin(&s_bb[1], k1); atomicMax(&s_bb[2], k2); atomicMax(&s_bb[3], k3); }
     }
     __syncthreads();
@@ -171,32 +168,7 @@ k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const i
             tile.box[ps] = a; tile.area[ps] = (a.z - a.x) * (a.w - a.y); tile.idx[ps] = t0 + tid;
         }
         __syncthreads();
-        if (!BIP) {
-            // ---- second cull, per warp (order preserved), then the IoU loop over what is left
-            int wn = 0;
-            for (int gb = 0; gb < tc; gb += 32) {
-                const int g = gb + lane;
-                bool k2 = false;
-                if (g < tc) {
-                    const float4 a2 = tile.box[g];
-                    const float wbb = fminf(a2.z, wb.z) - fmaxf(a2.x, wb.x), hbb = fminf(a2.w, wb.w) - fmaxf(a2.y, wb.y);
-                    k2 = (tile.idx[g] == 0) || !(wbb <= 0.0f || hbb <= 0.0f);      // NaN keeps
-                }
-                const unsigned bal2 = __ballot_sync(0xffffffffu, k2);
-                if (k2) s_wlist[warp][wn + __popc(bal2 & ((1u << lane) - 1u))] = (unsigned char)g;
-                wn += __popc(bal2);
-            }
-            __syncwarp();
-            for (int q = 0; q < wn; ++q) {
-                const int g = s_wlist[warp][q];
-                const float v = iou_match(tile.box[g], tile.area[g], pf, area_b);
-                const int gi = tile.idx[g];
-                if (gi == 0) { best = v; bi = 0; }
-                else if (v > best) { best = v; bi = gi; }                      // first index wins ties (:197)
-            }
-            __syncwarp();
-        }
-        for (int g = 0; BIP && g < tc; ++g) {
+        for (int g = 0; g < tc; ++g) {
             const float v = iou_match(tile.box[g], tile.area[g], pf, area_b);
             const int gi = tile.idx[g];
             if (gi == 0) { best = v; bi = 0; }

@@ -106,3 +106,44 @@ def test_gpu_heads_argument_errors():
         Detect(2, 0, 10, 0.05, 0.3).detect_heads(lm, cm, cu(synth.priors_numpy(64, 64))[:-1])
     with pytest.raises(NotImplementedError):
         Detect(3, 0, 10, 0.05, 0.3).detect_heads(lm, cm, cu(synth.priors_numpy(64, 64)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("thr", [0.0, 1e-5, 0.5, 0.9999, 0.99995, 1.0, 1.5])
+def test_gpu_detect_heads_threshold_range(golden, thr):
+    """The logit-gap screening of k_heads_threshold_compact must stay a superset of the exact candidates at every threshold
+    (the tiny / huge ones switch to the pass-all / fixed cut branches)."""
+    from fdt_b200.layers import Detect
+    g = golden("heads")
+    loc_maps, conf_maps, neg_max, pri = case_inputs(g, "b")
+    conf_maps = [m.copy() for m in conf_maps]
+    conf_maps[0][0, 3, :8, :8] += 14.0                       # a block of very confident faces (scores that round to 1.0f)
+    det = Detect(2, 0, 100, thr, 0.3)
+    if thr <= 1e-5:
+        det.nms_top_k = 8000                                 # nearly every prior is a candidate
+    out, counts, kept = det.detect_heads([cu(m) for m in loc_maps], [cu(m) for m in conf_maps], cu(pri), neg_max, return_aux=True)
+    rl, rc = orc.heads_to_loc_conf(loc_maps, conf_maps, neg_max, softmax=True)
+    rdet = orc.Detect(2, 0, 100, thr, 0.3)
+    rdet.nms_top_k = det.nms_top_k
+    ref = rdet(rl, rc, pri)
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.gpu
+def test_gpu_detect_heads_cuda_graph():
+    from fdt_b200.layers import Detect
+    loc_maps, conf_maps, neg_max = synth.head_maps(4, 320, 256, 9)
+    pri = cu(synth.priors_numpy(320, 256))
+    lm, cm = [cu(m) for m in loc_maps], [cu(m) for m in conf_maps]
+    det = Detect(2, 0, 300, 0.05, 0.3)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        eager = det.detect_heads(lm, cm, pri)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            captured = det.detect_heads(lm, cm, pri)
+    captured.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(captured, eager)
