@@ -5,7 +5,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one Detect pass over one batch of B=64 synthetic head outputs per GPU (weak scaling: every
-rank owns its own 64 images; for N>1 the step ends with the NCCL all-gather of the fixed-shape
+rank owns its own 64 images; for N>1 the step ends with the gather of the fixed-shape detections block to rank 0
 detections block, the only exchange the path has).  Prints ONE JSON line (rank 0).
 
   value     frames/s, inputs resident in HBM, device time = sum of per-step CUDA-event durations on the
@@ -43,12 +43,14 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="random", choices=["random", "clustered"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
-                    help="N>1: peer = rows stored into every rank's block by the NMS kernel over NVLink (fused); nccl = all_gather")
+    ap.add_argument("--gather", default="peer", choices=["peer", "peer-all", "nccl"],
+                    help="N>1: peer = rows stored into rank 0's gathered block by the NMS kernel over NVLink (fused gather); "
+                         "peer-all = into every rank's block (fused all-gather); nccl = all_gather after the kernel")
     return ap.parse_args()
 
 
-GATHER_NOTE = {"peer": ", gather fused into k_sort_nms (NVLink peer stores + symmetric-memory barrier)",
+GATHER_NOTE = {"peer": ", gather to rank 0 fused into k_sort_nms (NVLink peer stores + symmetric-memory barrier)",
+               "peer-all": ", all-gather fused into k_sort_nms (NVLink peer stores into every rank's block + symmetric-memory barrier)",
                "nccl": ", NCCL all-gather of detections"}
 
 
@@ -219,10 +221,10 @@ def main():
 
     gather = args.gather if world > 1 else "nccl"
     peer = None
-    if world > 1 and gather == "peer":
+    if world > 1 and gather in ("peer", "peer-all"):
         try:
             from fdt_b200.sharding import PeerGatherDetect
-            peer = PeerGatherDetect(det, B)
+            peer = PeerGatherDetect(det, B, dest=0 if gather == "peer" else "all")
         except Exception as e:                          # noqa: BLE001  (symmetric memory unavailable: keep the NCCL gather)
             if rank == 0:
                 print(f"peer gather unavailable ({e!r}); using NCCL all_gather", file=sys.stderr)
@@ -232,8 +234,9 @@ def main():
         if peer is not None:
             hdl = peer.hdls[peer.turn]
             peer.turn ^= 1
+            ptrs, n_dst = peer.dest_ptrs(hdl)
             _lib.check(L.fdt_detect_sort_nms_peers(loc.data_ptr(), pri.data_ptr(), B, N, C, TOP_K, NMS_TOP_K, NMS_T, 0.1, 0.2,
-                                                   int(hdl.buffer_ptrs_dev), world, rank * B, ws.data_ptr(), ws.numel(), st))
+                                                   ptrs, n_dst, rank * B, ws.data_ptr(), ws.numel(), st))
             hdl.barrier()
         else:
             stage2()

@@ -6,6 +6,8 @@
     python bench_extra.py detect1024 # BASELINE config 5 shape on one GPU: Detect B=64 @1024^2 (N=87,360)
     python bench_extra.py priorbox
     python bench_extra.py siblings   # FaceBoxes decode_np (21,824 default boxes) and MTCNN nms variants
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 bench_extra.py config5
+                                     # BASELINE config 5: Detect B=512 @1024^2 sharded over N GPUs, gather fused / NCCL
     python bench_extra.py heads      # Detect straight from the per-level NCHW head maps, B=64 @640^2
 
 Each prints one JSON line with device time (CUDA events, L2 flushed between repetitions), the algorithmic bytes of
@@ -161,6 +163,59 @@ def detect512():
                       "ms": ms, "ms_min": ms_min, "frames_per_s": B / (ms * 1e-3), "algorithmic_bytes": alg,
                       "roofline_frac_of_measured_hbm": alg / (ms * 1e-3) / 1e9 / PEAK,
                       "candidates_per_image": float((conf[..., 1] > 0.05).sum(1).float().mean())}))
+
+
+def config5():
+    """BASELINE config 5: Detect batch 512 @1024x1024 (N=87,360) sharded over the ranks of a torchrun launch (strong scaling: every
+    rank owns 512 / world images), detections gathered on every rank -- fused into the NMS kernel over NVLink peer memory, and with
+    an NCCL all-gather for comparison.  Device-generated inputs (as detect512)."""
+    import torch.distributed as dist
+    from fdt_b200.layers import Detect
+    from fdt_b200.sharding import PeerGatherDetect, ShardedDetect
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B_total = 512
+    B = B_total // world
+    pri = synth.priors_numpy(1024, 1024); N = pri.shape[0]
+    g = torch.Generator(device=dev); g.manual_seed(5 + rank)
+    loc = torch.randn((B, N, 4), device=dev, generator=g) * 0.5
+    s1 = torch.sigmoid(torch.randn((B, N), device=dev, generator=g) * 2.0 - 4.5)
+    conf = torch.stack([1 - s1, s1], -1).contiguous()
+    p = torch.from_numpy(pri).to(dev)
+    det = Detect(2, 0, 750, 0.05, 0.3)
+    res = {}
+    variants = [("single", det)] if world == 1 else [("peer_gather_to_rank0", PeerGatherDetect(det, B, dest=0)), ("peer_all_gather", PeerGatherDetect(det, B)),
+                                                       ("nccl_all_gather", ShardedDetect(det, gather="block"))]
+    for name, fn in variants:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            fn(loc, conf, p)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(12):
+            flush.zero_()
+            if world > 1:
+                dist.barrier()
+            torch.cuda._sleep(400_000)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); out = fn(loc, conf, p); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = torch.tensor([float(np.mean(ts))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[name] = {"ms_per_step": float(t.item()), "frames_per_s": B_total / (float(t.item()) * 1e-3), "gathered_shape": list(out.shape)}
+    alg = B_total * (24 * N + 30000) + world * 16 * N
+    if rank == 0:
+        best = min(v["ms_per_step"] for v in res.values())
+        print(json.dumps({"workload": "Detect B=512 @1024x1024 (N=87,360) sharded over %d GPU(s), strong scaling (config 5)" % world, "n_gpus": world,
+                          "images_per_gpu": B, "results": res, "algorithmic_bytes": alg,
+                          "aggregate_roofline_frac_of_measured_hbm": alg / (best * 1e-3) / 1e9 / (PEAK * world)}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def priorbox():

@@ -662,7 +662,8 @@ k_sort_nms(const SortNmsParams P)
 
     // Output that does not depend on the producer kernel goes first: the all-zero background plane (detection.py:48, :63)
     // is written while k_threshold_compact still runs (programmatic dependent launch).
-    if (MODE == MODE_DETECT && crank == 0 && cl == 1) {
+    // (Peer-gather launches skip it: the caller zeroes the gathered blocks once and nothing ever writes their background planes.)
+    if (MODE == MODE_DETECT && crank == 0 && cl == 1 && P.n_peers == 0) {
         const int ndst = P.n_peers > 0 ? P.n_peers : 1;
         const int nq = (P.top_k * 5) >> 2;                       // whole float4s; planes are 16-byte aligned iff top_k * 5 % 4 == 0
         const bool vec = ((P.top_k * 5) & 3) == 0;

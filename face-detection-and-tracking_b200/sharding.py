@@ -110,9 +110,13 @@ class PeerGatherDetect:
     rank that runs ahead never overwrites rows a slower peer is still reading.  The returned tensor is this rank's copy of the
     gathered block and stays valid until the call after next."""
 
-    def __init__(self, detect, b_local, group=None):
+    def __init__(self, detect, b_local, group=None, dest="all"):
+        """dest="all": every rank ends up with the whole gathered block (all-gather).  dest=<rank>: only that rank does (gather
+        to a root): each rank's rows cross NVLink once instead of world - 1 times, so the step no longer grows with the number
+        of ranks; only the root's returned block is meaningful."""
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
+        self.dest = dest
         self._lib = _lib
         self.detect = detect
         self.group = group if group is not None else dist.group.WORLD
@@ -123,8 +127,11 @@ class PeerGatherDetect:
         self.bufs, self.hdls = [], []
         for _ in range(2):
             t = symm_mem.empty(shape, dtype=torch.float32, device=dev)
+            t.zero_()                       # the kernel never writes the background planes: zero once, zero forever
             self.hdls.append(symm_mem.rendezvous(t, self.group))
             self.bufs.append(t)
+        torch.cuda.synchronize()
+        dist.barrier(self.group)            # every rank's blocks are zeroed before any peer stores rows into them
         self.turn = 0
 
     def __call__(self, loc, conf, priors):
@@ -140,8 +147,15 @@ class PeerGatherDetect:
         hdl, buf = self.hdls[self.turn], self.bufs[self.turn]
         self.turn ^= 1
         _lib.check(L.fdt_detect_threshold_compact(conf.data_ptr(), B, N, d.num_classes, float(d.conf_thresh), ws.data_ptr(), ws.numel(), st))
+        ptrs, n_dst = self.dest_ptrs(hdl)
         _lib.check(L.fdt_detect_sort_nms_peers(loc.data_ptr(), priors.data_ptr(), B, N, d.num_classes, int(d.top_k), int(d.nms_top_k),
                                                float(d.nms_thresh), float(d.variance[0]), float(d.variance[1]),
-                                               int(hdl.buffer_ptrs_dev), self.world, self.rank * B, ws.data_ptr(), ws.numel(), st))
-        hdl.barrier()            # all ranks' rows have landed in this rank's block (and ours in theirs)
+                                               ptrs, n_dst, self.rank * B, ws.data_ptr(), ws.numel(), st))
+        hdl.barrier()            # all ranks' rows have landed in the destination block(s)
         return buf
+
+    def dest_ptrs(self, hdl):
+        """(device array of destination block pointers, how many) for fdt_detect_sort_nms_peers."""
+        if self.dest == "all":
+            return int(hdl.buffer_ptrs_dev), self.world
+        return int(hdl.buffer_ptrs_dev) + 8 * int(self.dest), 1          # one entry of the symmetric pointer table: the root's block

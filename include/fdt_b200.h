@@ -145,7 +145,9 @@ int fdt_detect_sort_nms(const float *loc, const float *priors, int B, int64_t N,
 /* Stage 2 with the multi-GPU gather fused in: instead of a local `out`, the detection rows of this rank's B
  * images are stored straight into EVERY rank's gathered block [world*B, C, top_k, 5] at image index image_offset + b, over
  * NVLink peer memory (no separate collective).  peer_out_ptrs: DEVICE array of n_peers base pointers of those blocks (e.g.
- * torch symmetric memory `buffer_ptrs_dev`); the caller synchronises the ranks afterwards (a symmetric-memory barrier). */
+ * torch symmetric memory `buffer_ptrs_dev`); the caller synchronises the ranks afterwards (a symmetric-memory barrier).
+ * The background (class 0) planes of the gathered blocks are NOT written: the caller zeroes the blocks once after allocating
+ * them and they stay zero (half of the NVLink traffic of a two-class Detect). */
 int fdt_detect_sort_nms_peers(const float *loc, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
                               float nms_thresh, float var0, float var1,
                               const uint64_t *peer_out_ptrs, int n_peers, int64_t image_offset,

@@ -30,9 +30,20 @@ def main():
     det = Detect(2, 0, 750, 0.05, 0.3)
     nccl = ShardedDetect(det, gather="block")(cu(loc[lo:hi]), cu(conf[lo:hi]), cu(pri)).cpu().numpy()
     packed = ShardedDetect(det, gather="packed")(cu(loc[lo:hi]), cu(conf[lo:hi]), cu(pri)).cpu().numpy()
+    outs = []
     peer = PeerGatherDetect(det, b_local)
-    outs = [peer(cu(loc[lo:hi]), cu(conf[lo:hi]), cu(pri)).cpu().numpy() for _ in range(3)]
+    outs += [peer(cu(loc[lo:hi]), cu(conf[lo:hi]), cu(pri)).cpu().numpy() for _ in range(5)]
+    # different images in the same blocks: stale rows of the previous call must be overwritten everywhere
+    sh = (np.arange(B) + 3) % B
+    o2 = peer(cu(loc[sh][lo:hi]), cu(conf[sh][lo:hi]), cu(pri)).cpu().numpy()
+    outs.append(o2[np.argsort(sh)])
     ok = nccl.tobytes() == packed.tobytes() and all(o.tobytes() == nccl.tobytes() for o in outs)
+    # gather to a root: only the root's block is written
+    for root in (0, world - 1):
+        pr = PeerGatherDetect(det, b_local, dest=root)
+        for _ in range(3):
+            o = pr(cu(loc[lo:hi]), cu(conf[lo:hi]), cu(pri)).cpu().numpy()
+        ok = ok and (rank != root or o.tobytes() == nccl.tobytes())
     if rank == 0:
         from oracle import oracle as orc
         o = orc.Detect(2, 0, 750, 0.05, 0.3); o.early_exit = True
