@@ -8,6 +8,7 @@
     python bench_extra.py siblings   # FaceBoxes decode_np (21,824 default boxes) and MTCNN nms variants
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 bench_extra.py config5
                                      # BASELINE config 5: Detect B=512 @1024^2 sharded over N GPUs, gather fused / NCCL
+    python bench_extra.py torchref   # the reference's python-loop Detect restated in torch, on CUDA tensors and on the CPU
     python bench_extra.py heads      # Detect straight from the per-level NCHW head maps, B=64 @640^2
 
 Each prints one JSON line with device time (CUDA events, L2 flushed between repetitions), the algorithmic bytes of
@@ -216,6 +217,43 @@ def config5():
                           "aggregate_roofline_frac_of_measured_hbm": alg / (best * 1e-3) / 1e9 / (PEAK * world)}))
     if world > 1:
         dist.destroy_process_group()
+
+
+def torchref():
+    """BASELINE config 1 (one 640x640 image, N=34,125, conf 0.05, nms 0.3) through the reference's algorithm as the reference
+    deploys it -- a python loop of small torch ops (oracle/torch_ref.py restates detection.py:34-84 / box_utils.py:275-340; the
+    reference itself cannot travel to the GPU box) -- on CUDA tensors on this B200 and on the host CPU, next to fdt_detect."""
+    from oracle import torch_ref
+    from fdt_b200.layers import Detect
+    pri = synth.priors_numpy(640, 640)
+    loc, conf = synth.detect_inputs(1, pri, 20261, 0.05)
+    ref_det = torch_ref.Detect(2, 0, 750, 0.05, 0.3)
+    res = {}
+    outs = {}
+    for dev in ("cuda", "cpu"):
+        a = [torch.from_numpy(x).to(dev) for x in (loc, conf, pri)]
+        if dev == "cpu":
+            torch.set_num_threads(os.cpu_count() or 1)
+        best = 1e9
+        for _ in range(3):
+            if dev == "cuda":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            o = ref_det(*a)
+            if dev == "cuda":
+                torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        outs[dev] = o.cpu().numpy()
+        res[f"torch_{dev}_s_per_image"] = best
+        res[f"torch_{dev}_frames_per_s"] = 1.0 / best
+    a = [torch.from_numpy(x).cuda() for x in (loc, conf, pri)]
+    det = Detect(2, 0, 750, 0.05, 0.3)
+    ours = det(*a)
+    ms, _ = timed(lambda: det(*a))
+    same = bool(np.array_equal(ours.cpu().numpy()[..., 0], outs["cuda"][..., 0]) and np.array_equal(outs["cuda"][..., 0], outs["cpu"][..., 0]))
+    print(json.dumps({"workload": "Detect, 1 image @640x640 (N=34,125, %d candidates), conf 0.05, nms 0.3 (config 1)" % int((conf[0, :, 1] > 0.05).sum()),
+                      "reference_algorithm_in_torch": res, "host_threads": os.cpu_count(), "fdt_detect_ms": ms, "fdt_detect_frames_per_s": 1e3 / ms,
+                      "same_kept_scores": same}))
 
 
 def priorbox():

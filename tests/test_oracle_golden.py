@@ -184,3 +184,16 @@ def test_calc_performance_functions(golden):
     pr, tnum = orc.calc_pr(g["pred"], g["truth"])
     assert tnum == int(g["truth_num"]) and np.array_equal(pr, g["pr"])
     assert pr[0].sum() >= 10                                   # the fixture really has matches and misses
+
+
+def test_torch_restatement_matches_oracle():
+    """oracle/torch_ref.py (the reference's python loops restated in torch, used only to time the reference's intended
+    torch-CUDA deployment on the GPU box) agrees with the C oracle: same kept rows, coordinates within the exp tolerance."""
+    import torch
+    from oracle import torch_ref
+    pri = synth.priors_numpy(160, 160)
+    loc, conf = synth.detect_inputs(2, pri, 5, 0.05)
+    out = torch_ref.Detect(2, 0, 750, 0.05, 0.3)(torch.from_numpy(loc), torch.from_numpy(conf), torch.from_numpy(pri)).numpy()
+    ref = orc.Detect(2, 0, 750, 0.05, 0.3)(loc, conf, pri)
+    assert np.array_equal(out[..., 0], ref[..., 0])
+    close(out, ref)
