@@ -33,6 +33,7 @@ B_PER_GPU = 64
 WIDTH = HEIGHT = 640
 TOP_K, NMS_TOP_K, CONF_T, NMS_T = 750, 5000, 0.05, 0.3
 SEED = 20262
+METRIC = "frames/sec for Detect (decode+top-k+NMS) @640^2 batch 64; % HBM roofline"      # BASELINE.json metric, both arms
 
 
 def parse():
@@ -165,7 +166,7 @@ def run_reference(args):
         det(loc, conf, pri)
     dt = time.perf_counter() - t0
     fps = args.steps * B_PER_GPU / dt
-    line = {"impl": "reference", "metric": "frames/sec for Detect (decode+top-k+NMS) @640^2 batch 64", "value": fps,
+    line = {"impl": "reference", "metric": METRIC, "value": fps,
             "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args.mode, 1),
@@ -369,7 +370,7 @@ def main():
                "sample": f"{n} images ({n // B} x the B={B} batch) in {dt:.1f} s, C oracle port with OpenMP over images, "
                          f"NMS run to completion as box_utils.nms does (the reference itself is a Python loop, ~1-2 frames/s)"}
 
-    line = {"metric": "frames/sec for Detect (decode+top-k+NMS) @640^2 batch 64; % HBM roofline",
+    line = {"metric": METRIC,
             "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args.mode, world, gather),
