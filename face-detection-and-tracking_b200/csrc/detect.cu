@@ -119,8 +119,13 @@ k_heads_to_loc_conf(const HeadLevels h, const int N, const int softmax, float *_
 // Clears the per-list counters.  A kernel rather than cudaMemsetAsync so that k_threshold_compact can be launched behind it
 // with programmatic stream serialization: its blocks start and stream `conf` while this grid is still in flight (a memset
 // node costs ~3.5 us of serialised front-end latency per call).
+// It is itself launched behind whatever precedes it in the stream with programmatic serialization: when that is the k_sort_nms
+// of the previous Detect call (which triggers at its start), this grid is already resident when that kernel ends.  It waits for
+// its predecessor's COMPLETION before it lets k_threshold_compact be scheduled: K2 loads `conf` ahead of its own dependency wait,
+// which is only safe once everything earlier in the stream (possibly an early-triggering producer of `conf`) has finished.
 __global__ void k_zero_counters(int32_t *__restrict__ counters, int n)
 {
+    cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) counters[i] = 0;
@@ -624,6 +629,9 @@ template <int MODE, int CL>
 __global__ void __launch_bounds__(K3_THREADS, 1)
 k_sort_nms(const SortNmsParams P)
 {
+    // lets the counter clear / K2 of the NEXT Detect call be scheduled behind this grid (see k_zero_counters); they wait for this
+    // grid's completion before touching anything it reads or writes
+    cudaTriggerProgrammaticLaunchCompletion();
     extern __shared__ __align__(16) unsigned char smem[];
     uint64_t *skeys = reinterpret_cast<uint64_t *>(smem + SM_KEYS);
     int *s_hist = reinterpret_cast<int *>(smem + SM_HIST);
@@ -1347,7 +1355,15 @@ static int threshold_compact_impl(const float *conf, const HeadLevels *heads, in
         const char *env = getenv("FDT_K3_PROFILE");
         if (env && env[0] == '1') { int rc2 = prof_arm(st); if (rc2 != FDT_OK) return rc2; g_prof_armed = true; prof = g_prof_dev; }
     }
-    k_zero_counters<<<(3 * lists + 255) / 256, 256, 0, st>>>(counters, 3 * lists);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((3 * lists + 255) / 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        FDT_CUDA(cudaLaunchKernelEx(&cfg, k_zero_counters, counters, 3 * lists));
+    }
     FDT_LAUNCH_CHECK();
     dim3 g2((unsigned)((N + K2_TILE - 1) / K2_TILE), (unsigned)B);
     {
