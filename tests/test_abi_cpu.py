@@ -88,3 +88,16 @@ def test_product_package_never_imports_the_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|libfdt_oracle|orc_[a-z_]+\(", txt, flags=re.M), \
                     f"{f} reaches into oracle/"
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The boundary is a C ABI: include/fdt_b200.h must compile as C (no C++ or torch types in the signatures)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "h.c"
+    src.write_text('#include "fdt_b200.h"\nint main(void) { return fdt_version() > 0 ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-fsyntax-only", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
