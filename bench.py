@@ -48,13 +48,16 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="random", choices=["random", "clustered"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="peer", choices=["peer", "peer-all", "nccl"],
-                    help="N>1: peer = rows stored into rank 0's gathered block by the NMS kernel over NVLink (fused gather); "
-                         "peer-all = into every rank's block (fused all-gather); nccl = all_gather after the kernel")
+    ap.add_argument("--gather", default="peer", choices=["peer", "peer-barrier", "peer-all", "nccl"],
+                    help="N>1: peer = rows stored into rank 0's gathered block by the NMS kernel over NVLink, completion signalled by the "
+                         "kernel itself (fused gather); peer-barrier = the same followed by a symmetric-memory barrier; "
+                         "peer-all = into every rank's block + barrier (fused all-gather); nccl = all_gather after the kernel")
     return ap.parse_args()
 
 
-GATHER_NOTE = {"peer": ", gather to rank 0 fused into k_sort_nms (NVLink peer stores + symmetric-memory barrier)",
+GATHER_NOTE = {"peer": ", gather to rank 0 fused into k_sort_nms (NVLink peer stores; completion signals published / awaited by the kernel "
+                       "over symmetric memory: only rank 0 waits)",
+               "peer-barrier": ", gather to rank 0 fused into k_sort_nms (NVLink peer stores + symmetric-memory barrier)",
                "peer-all": ", all-gather fused into k_sort_nms (NVLink peer stores into every rank's block + symmetric-memory barrier)",
                "nccl": ", NCCL all-gather of detections"}
 
@@ -237,10 +240,10 @@ def main():
 
     gather = args.gather if world > 1 else "nccl"
     peer = None
-    if world > 1 and gather in ("peer", "peer-all"):
+    if world > 1 and gather in ("peer", "peer-barrier", "peer-all"):
         try:
             from fdt_b200.sharding import PeerGatherDetect
-            peer = PeerGatherDetect(det, B, dest=0 if gather == "peer" else "all")
+            peer = PeerGatherDetect(det, B, dest="all" if gather == "peer-all" else 0, signal="kernel" if gather == "peer" else "barrier")
         except Exception as e:                          # noqa: BLE001  (symmetric memory unavailable: keep the NCCL gather)
             if rank == 0:
                 print(f"peer gather unavailable ({e!r}); using NCCL all_gather", file=sys.stderr)
@@ -250,10 +253,16 @@ def main():
         if peer is not None:
             hdl = peer.hdls[peer.turn]
             peer.turn ^= 1
-            ptrs, n_dst = peer.dest_ptrs(hdl)
-            _lib.check(L.fdt_detect_sort_nms_peers(inputs()[0].data_ptr(), pri.data_ptr(), B, N, C, TOP_K, NMS_TOP_K, NMS_T, 0.1, 0.2,
-                                                   ptrs, n_dst, rank * B, ws.data_ptr(), ws.numel(), st))
-            hdl.barrier()
+            if peer.signal == "kernel":
+                peer.epoch += 1
+                _lib.check(L.fdt_detect_sort_nms_gather_signal(inputs()[0].data_ptr(), pri.data_ptr(), B, N, C, TOP_K, NMS_TOP_K, NMS_T, 0.1, 0.2,
+                                                               int(hdl.buffer_ptrs_dev), int(peer.sig_hdl.buffer_ptrs_dev), world, rank, 0,
+                                                               peer.epoch, rank * B, ws.data_ptr(), ws.numel(), st))
+            else:
+                ptrs, n_dst = peer.dest_ptrs(hdl)
+                _lib.check(L.fdt_detect_sort_nms_peers(inputs()[0].data_ptr(), pri.data_ptr(), B, N, C, TOP_K, NMS_TOP_K, NMS_T, 0.1, 0.2,
+                                                       ptrs, n_dst, rank * B, ws.data_ptr(), ws.numel(), st))
+                hdl.barrier()
         else:
             stage2()
             if world > 1:

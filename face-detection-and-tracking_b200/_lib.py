@@ -48,6 +48,7 @@ SIGNATURES = {
     "fdt_detect_threshold_compact": (_i, [_vp, _i, _i64, _i, _f, _vp, _sz, _vp]),
     "fdt_detect_sort_nms": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fdt_detect_sort_nms_peers": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _vp, _i, _i64, _vp, _sz, _vp]),
+    "fdt_detect_sort_nms_gather_signal": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _vp, _vp, _i, _i, _i, C.c_uint32, _i64, _vp, _sz, _vp]),
     "fdt_detect_candidate_counts": (_i, [_vp, _i, _i, _vp, _vp]),
     "fdt_heads_to_loc_conf": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "fdt_detect_heads": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),

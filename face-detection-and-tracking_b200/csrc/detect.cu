@@ -378,6 +378,11 @@ struct SortNmsParams {
     const unsigned long long *peer_out;   // device array of n_peers output base pointers (this GPU's and its NVLink peers'), or null
     int n_peers;
     int64_t img_offset;         // image index of this rank's first image inside the peers' gathered blocks
+    // signalled gather to a root rank (fdt_detect_sort_nms_gather_signal): no barrier launch
+    const unsigned long long *peer_sig;   // device array of `world` pointers to every rank's uint32 signal[world + 1] (or null)
+    int world, my_rank, root;
+    unsigned epoch;             // call counter, the same on every rank, >= 1
+    int *done_ctr;              // completion ticket (workspace)
     float4 *g_kbox;             // kept arrays in global memory (per list stride max_keep) when sm.off_kbox < 0
     float *g_karea;
     uint64_t *g_kkey;
@@ -1186,6 +1191,19 @@ k_sort_nms(const SortNmsParams P)
     // =========================================================== stage 3: outputs
     if (P.prof && tid == 0 && blockIdx.x < 256) { unsigned long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1)); atomicMin((unsigned long long *)&P.prof[40], gt0); atomicMax((unsigned long long *)&P.prof[41], gt0); atomicMin((unsigned long long *)&P.prof[42], gt1); atomicMax((unsigned long long *)&P.prof[43], gt1); P.prof[64 + blockIdx.x] = clock64() - cta_t0; P.prof[320 + blockIdx.x] = (long long)rounds * 100000 + k; }
     if (!writer) return;
+    if (MODE == MODE_DETECT && P.peer_sig && P.my_rank != P.root) {
+        // The rows go into the root's block of parity epoch % 2: the root must be done with what epoch - 2 left there.  Its
+        // k_sort_nms of epoch - 1 ran after that consumer (stream order) and acknowledged in this rank's slot [world].
+        if (tid == 0) {
+            const unsigned *ack = reinterpret_cast<const unsigned *>(P.peer_sig[P.my_rank]) + P.world;
+            const long long t0 = clock64();
+            unsigned v;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ack) : "memory");
+            } while ((int)(v - (P.epoch - 1)) < 0 && clock64() - t0 < (1ll << 32));
+        }
+        __syncthreads();
+    }
     if (MODE == MODE_DETECT) {
         const int top_k = P.top_k;
         const int cnt = min(nkept, top_k);                                   // detection.py:80
@@ -1212,6 +1230,39 @@ k_sort_nms(const SortNmsParams P)
             for (int r = tid; r < top_k; r += K3_THREADS) kp[r] = r < cnt ? (int64_t)(uint32_t)kkey[r] : -1;
         }
         if (P.counts && tid == 0) P.counts[b * P.C + cl] = cnt;
+        if (P.peer_sig) {
+            // Completion signal instead of a cross-rank barrier launch.  The last writer CTA of a non-root rank publishes `epoch`
+            // in slot [rank] of the ROOT's signal array and leaves; the root's last writer CTA waits until every slot shows
+            // `epoch` (all rows have landed in its block), then acknowledges in slot [world] of every rank.  Only the root waits.
+            __threadfence();        // device scope: ordered before this CTA's ticket; the signalling thread's system-scope fence
+            __syncthreads();        // below is cumulative over everything it has observed through the ticket chain
+            if (tid == 0) {
+                const int writers = (int)(gridDim.x / CL);
+                if (atomicAdd(P.done_ctr, 1) == writers - 1) {
+                    *P.done_ctr = 0;
+                    __threadfence_system();
+                    if (P.my_rank != P.root) {
+                        unsigned *dst = reinterpret_cast<unsigned *>(P.peer_sig[P.root]) + P.my_rank;
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(dst), "r"(P.epoch) : "memory");
+                    } else {
+                        const unsigned *mine = reinterpret_cast<const unsigned *>(P.peer_sig[P.root]);
+                        const long long t0 = clock64();
+                        for (int q = 0; q < P.world; ++q) {
+                            if (q == P.root) continue;
+                            unsigned v;
+                            do {
+                                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + q) : "memory");
+                            } while ((int)(v - P.epoch) < 0 && clock64() - t0 < (1ll << 32));      // ~2 s: a dead peer must not hang the GPU
+                        }
+                        for (int q = 0; q < P.world; ++q) {
+                            if (q == P.root) continue;
+                            unsigned *dst = reinterpret_cast<unsigned *>(P.peer_sig[q]) + P.world;
+                            asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(dst), "r"(P.epoch) : "memory");
+                        }
+                    }
+                }
+            }
+        }
     } else {
         for (int64_t t = tid; t < P.n; t += K3_THREADS)
             P.keep[t] = t < nkept ? (int64_t)(uint32_t)kkey[t] : 0;           // box_utils.py:289 zero-initialised
@@ -1318,13 +1369,16 @@ int launch_sort_nms(SortNmsParams &P, int lists, int kcap, void *kept_ws, size_t
 
 }  // namespace
 
+// workspace head: int32 [3][lists] (candidate count, max key, ~min key) + 1 completion ticket (signalled peer-gather launches)
+static inline size_t detect_counter_bytes(size_t lists) { return fdt_align256((3 * lists + 1) * sizeof(int32_t)); }
+
 // =============================================================================================== C ABI
 FDT_API size_t fdt_detect_workspace_bytes(int B, int64_t N, int C)
 {
     if (B <= 0 || N <= 0 || C <= 1) return 256;
     size_t lists = (size_t)B * (size_t)(C - 1);
     size_t kept_rows = (size_t)(N < FDT_MAX_NMS_TOP_K ? N : FDT_MAX_NMS_TOP_K);       // only used when top_k rows exceed shared memory
-    return fdt_align256(3 * lists * sizeof(int32_t)) + fdt_align256(lists * (size_t)N * sizeof(uint64_t)) +
+    return detect_counter_bytes(lists) + fdt_align256(lists * (size_t)N * sizeof(uint64_t)) +
            fdt_align256(lists * kept_rows * KEPT_ROW_BYTES);
 }
 
@@ -1349,7 +1403,7 @@ static int threshold_compact_impl(const float *conf, const HeadLevels *heads, in
     if (lists == 0 || N == 0) return FDT_OK;
     FDT_REQUIRE(heads || (conf && fdt_aligned(conf, 8)), FDT_E_INVALID, "fdt_detect_threshold_compact: conf null or not 8-byte aligned");
     int32_t *counters = (int32_t *)ws;
-    uint64_t *keys = (uint64_t *)((char *)ws + fdt_align256((size_t)3 * lists * sizeof(int32_t)));
+    uint64_t *keys = (uint64_t *)((char *)ws + detect_counter_bytes((size_t)lists));
     long long *prof = nullptr;
     {
         const char *env = getenv("FDT_K3_PROFILE");
@@ -1357,12 +1411,12 @@ static int threshold_compact_impl(const float *conf, const HeadLevels *heads, in
     }
     {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)((3 * lists + 255) / 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cfg.gridDim = dim3((unsigned)((3 * lists + 1 + 255) / 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        FDT_CUDA(cudaLaunchKernelEx(&cfg, k_zero_counters, counters, 3 * lists));
+        FDT_CUDA(cudaLaunchKernelEx(&cfg, k_zero_counters, counters, 3 * lists + 1));
     }
     FDT_LAUNCH_CHECK();
     dim3 g2((unsigned)((N + K2_TILE - 1) / K2_TILE), (unsigned)B);
@@ -1424,7 +1478,8 @@ static int detect_sort_nms_impl(const float *loc, const HeadLevels *heads, const
                                 float nms_thresh, float var0, float var1,
                                 float *out, int32_t *counts, int64_t *kept_prior,
                                 const unsigned long long *peer_out, int n_peers, int64_t img_offset,
-                                void *ws, size_t ws_bytes, fdt_stream_t stream)
+                                void *ws, size_t ws_bytes, fdt_stream_t stream,
+                                const unsigned long long *peer_sig = nullptr, int world = 0, int my_rank = 0, int root = 0, unsigned epoch = 0)
 {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = detect_check_common("fdt_detect_sort_nms", B, N, C, ws, ws_bytes);
@@ -1446,7 +1501,7 @@ static int detect_sort_nms_impl(const float *loc, const HeadLevels *heads, const
     FDT_REQUIRE((heads || (loc && fdt_aligned(loc, 16))) && priors && fdt_aligned(priors, 16), FDT_E_INVALID,
                 "fdt_detect: loc/priors null or not 16-byte aligned");
     int32_t *counters = (int32_t *)ws;
-    uint64_t *keys = (uint64_t *)((char *)ws + fdt_align256((size_t)3 * lists * sizeof(int32_t)));
+    uint64_t *keys = (uint64_t *)((char *)ws + detect_counter_bytes((size_t)lists));
     SortNmsParams P{};
     P.keys = keys; P.counters = counters; P.key_stride = N;
     P.loc = heads ? nullptr : loc; P.priors = priors; P.N = N; P.C = C;
@@ -1455,6 +1510,7 @@ static int detect_sort_nms_impl(const float *loc, const HeadLevels *heads, const
     P.nms_thresh = nms_thresh; P.v0 = var0; P.v1 = var1;
     P.out = out; P.counts = counts; P.kept_prior = kept_prior;
     P.peer_out = peer_out; P.n_peers = n_peers; P.img_offset = img_offset;
+    P.peer_sig = peer_sig; P.world = world; P.my_rank = my_rank; P.root = root; P.epoch = epoch; P.done_ctr = counters + 3 * lists;
     int kcap = (int)((int64_t)nms_top_k < N ? nms_top_k : N);
     if (P.max_keep > kcap) P.max_keep = kcap;
     char *kept_ws = (char *)keys + fdt_align256((size_t)lists * (size_t)N * sizeof(uint64_t));
@@ -1479,6 +1535,18 @@ FDT_API int fdt_detect_sort_nms_peers(const float *loc, const float *priors, int
     FDT_REQUIRE(peer_out_ptrs != nullptr && n_peers >= 1 && image_offset >= 0, FDT_E_INVALID, "fdt_detect_sort_nms_peers: bad peer arguments");
     return detect_sort_nms_impl(loc, nullptr, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1, nullptr, nullptr, nullptr,
                                 (const unsigned long long *)peer_out_ptrs, n_peers, image_offset, ws, ws_bytes, stream);
+}
+
+FDT_API int fdt_detect_sort_nms_gather_signal(const float *loc, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
+                                              float nms_thresh, float var0, float var1,
+                                              const uint64_t *root_out_ptr, const uint64_t *peer_signal_ptrs, int world, int rank, int root,
+                                              uint32_t epoch, int64_t image_offset, void *ws, size_t ws_bytes, fdt_stream_t stream)
+{
+    FDT_REQUIRE(root_out_ptr && peer_signal_ptrs && world >= 1 && rank >= 0 && rank < world && root >= 0 && root < world &&
+                image_offset >= 0 && epoch >= 1, FDT_E_INVALID, "fdt_detect_sort_nms_gather_signal: bad arguments");
+    return detect_sort_nms_impl(loc, nullptr, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1, nullptr, nullptr, nullptr,
+                                (const unsigned long long *)root_out_ptr, 1, image_offset, ws, ws_bytes, stream,
+                                (const unsigned long long *)peer_signal_ptrs, world, rank, root, epoch);
 }
 
 FDT_API int fdt_detect(const float *loc, const float *conf, const float *priors,
@@ -1664,7 +1732,7 @@ FDT_API int fdt_threshold_nms(const float *boxes, const float *conf, int64_t N, 
     int rc = threshold_compact_impl(conf, nullptr, 1, N, 2, conf_thresh, ws, ws_bytes, stream);
     if (rc != FDT_OK) return rc;
     int32_t *counters = (int32_t *)ws;
-    uint64_t *keys = (uint64_t *)((char *)ws + fdt_align256((size_t)3 * sizeof(int32_t)));
+    uint64_t *keys = (uint64_t *)((char *)ws + detect_counter_bytes(1));
     const int kcap = (int)(N < FDT_MAX_NMS_TOP_K ? N : FDT_MAX_NMS_TOP_K);
     SortNmsParams P{};
     P.keys = keys; P.counters = counters; P.key_stride = N; P.boxes = boxes; P.n = N; P.N = N; P.C = 2;

@@ -110,13 +110,17 @@ class PeerGatherDetect:
     rank that runs ahead never overwrites rows a slower peer is still reading.  The returned tensor is this rank's copy of the
     gathered block and stays valid until the call after next."""
 
-    def __init__(self, detect, b_local, group=None, dest="all"):
+    def __init__(self, detect, b_local, group=None, dest="all", signal="barrier"):
         """dest="all": every rank ends up with the whole gathered block (all-gather).  dest=<rank>: only that rank does (gather
         to a root): each rank's rows cross NVLink once instead of world - 1 times, so the step no longer grows with the number
-        of ranks; only the root's returned block is meaningful."""
+        of ranks; only the root's returned block is meaningful.
+        signal="barrier": a symmetric-memory barrier follows the kernel (works for both, CUDA-graph capturable).
+        signal="kernel" (needs dest=<rank>): the NMS kernel publishes / awaits the completion signals itself -- the non-root
+        ranks never wait, the root's kernel ends when all rows have landed (fdt_detect_sort_nms_gather_signal)."""
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
-        self.dest = dest
+        assert signal in ("barrier", "kernel") and (signal == "barrier" or dest != "all")
+        self.dest, self.signal = dest, signal
         self._lib = _lib
         self.detect = detect
         self.group = group if group is not None else dist.group.WORLD
@@ -130,6 +134,12 @@ class PeerGatherDetect:
             t.zero_()                       # the kernel never writes the background planes: zero once, zero forever
             self.hdls.append(symm_mem.rendezvous(t, self.group))
             self.bufs.append(t)
+        self.sig = self.sig_hdl = None
+        self.epoch = 0
+        if signal == "kernel":
+            self.sig = symm_mem.empty((max(self.world + 1, 64),), dtype=torch.int32, device=dev)    # uint32 epoch slots
+            self.sig.zero_()
+            self.sig_hdl = symm_mem.rendezvous(self.sig, self.group)
         torch.cuda.synchronize()
         dist.barrier(self.group)            # every rank's blocks are zeroed before any peer stores rows into them
         self.turn = 0
@@ -147,6 +157,14 @@ class PeerGatherDetect:
         hdl, buf = self.hdls[self.turn], self.bufs[self.turn]
         self.turn ^= 1
         _lib.check(L.fdt_detect_threshold_compact(conf.data_ptr(), B, N, d.num_classes, float(d.conf_thresh), ws.data_ptr(), ws.numel(), st))
+        if self.signal == "kernel":
+            self.epoch += 1
+            _lib.check(L.fdt_detect_sort_nms_gather_signal(loc.data_ptr(), priors.data_ptr(), B, N, d.num_classes, int(d.top_k), int(d.nms_top_k),
+                                                           float(d.nms_thresh), float(d.variance[0]), float(d.variance[1]),
+                                                           int(hdl.buffer_ptrs_dev) + 8 * int(self.dest), int(self.sig_hdl.buffer_ptrs_dev),
+                                                           self.world, self.rank, int(self.dest), self.epoch, self.rank * B,
+                                                           ws.data_ptr(), ws.numel(), st))
+            return buf           # on the root: complete when the kernel ends
         ptrs, n_dst = self.dest_ptrs(hdl)
         _lib.check(L.fdt_detect_sort_nms_peers(loc.data_ptr(), priors.data_ptr(), B, N, d.num_classes, int(d.top_k), int(d.nms_top_k),
                                                float(d.nms_thresh), float(d.variance[0]), float(d.variance[1]),

@@ -152,6 +152,18 @@ int fdt_detect_sort_nms_peers(const float *loc, const float *priors, int B, int6
                               float nms_thresh, float var0, float var1,
                               const uint64_t *peer_out_ptrs, int n_peers, int64_t image_offset,
                               void *ws, size_t ws_bytes, fdt_stream_t stream);
+/* Gather to ONE rank with the completion signal folded into the kernel (no barrier launch).  root_out_ptr: DEVICE pointer to the
+ * entry of the symmetric pointer table that holds the root's gathered block; peer_signal_ptrs: DEVICE array of `world` pointers to
+ * every rank's uint32 signal[world + 1] array (symmetric memory, zeroed once).  `epoch` (>= 1) is the call counter, the same on every
+ * rank and increasing by one per call; two gathered blocks alternate (parity of epoch).  A non-root rank stores its rows into the
+ * root's block, publishes `epoch` in slot [rank] of the root's array and does not wait for anybody -- except, before storing, for the
+ * root's acknowledgement of epoch - 1 in its own slot [world] (the block of that parity is free again; normally long satisfied).
+ * The root's kernel ends only when every rank's rows of this epoch have landed in its block, then acknowledges.  `epoch` is a launch
+ * parameter: do not replay this call from a captured CUDA graph.  Every wait gives up after ~2 s. */
+int fdt_detect_sort_nms_gather_signal(const float *loc, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
+                                      float nms_thresh, float var0, float var1,
+                                      const uint64_t *root_out_ptr, const uint64_t *peer_signal_ptrs, int world, int rank, int root,
+                                      uint32_t epoch, int64_t image_offset, void *ws, size_t ws_bytes, fdt_stream_t stream);
 /* Number of candidates per (image, class>=1) list after stage 1: copies B*(C-1) int32 to counts_out (device). */
 int fdt_detect_candidate_counts(const void *ws, int B, int C, int32_t *counts_out, fdt_stream_t stream);
 

@@ -38,12 +38,15 @@ def main():
     o2 = peer(cu(loc[sh][lo:hi]), cu(conf[sh][lo:hi]), cu(pri)).cpu().numpy()
     outs.append(o2[np.argsort(sh)])
     ok = nccl.tobytes() == packed.tobytes() and all(o.tobytes() == nccl.tobytes() for o in outs)
-    # gather to a root: only the root's block is written
-    for root in (0, world - 1):
-        pr = PeerGatherDetect(det, b_local, dest=root)
-        for _ in range(3):
-            o = pr(cu(loc[lo:hi]), cu(conf[lo:hi]), cu(pri)).cpu().numpy()
-        ok = ok and (rank != root or o.tobytes() == nccl.tobytes())
+    # gather to a root: only the root's block is written; with the barrier after the kernel, or signalled by the kernel itself
+    for root, signal in ((0, "barrier"), (world - 1, "barrier"), (0, "kernel"), (world - 1, "kernel")):
+        pr = PeerGatherDetect(det, b_local, dest=root, signal=signal)
+        for it in range(6):
+            sh = (np.arange(B) + it) % B           # a different batch every call: stale rows must never survive
+            o = pr(cu(loc[sh][lo:hi]), cu(conf[sh][lo:hi]), cu(pri))
+            if rank == root:
+                torch.cuda.synchronize()
+                ok = ok and o.cpu().numpy()[np.argsort(sh)].tobytes() == nccl.tobytes()
     if rank == 0:
         from oracle import oracle as orc
         o = orc.Detect(2, 0, 750, 0.05, 0.3); o.early_exit = True

@@ -51,6 +51,30 @@ def peers(barrier):
     return f
 
 
+peer_sig = PeerGatherDetect(det, B, dest=0, signal="kernel")
+peer_root = PeerGatherDetect(det, B, dest=0)
+
+
+def root_barrier():
+    hdl = peer_root.hdls[peer_root.turn]
+    peer_root.turn ^= 1
+    k2()
+    ptrs, n_dst = peer_root.dest_ptrs(hdl)
+    _lib.check(L.fdt_detect_sort_nms_peers(loc.data_ptr(), pri.data_ptr(), B, N, C, TOP_K, 5000, 0.3, 0.1, 0.2, ptrs, n_dst, rank * B,
+                                           ws.data_ptr(), ws.numel(), st))
+    hdl.barrier()
+
+
+def root_signal():
+    hdl = peer_sig.hdls[peer_sig.turn]
+    peer_sig.turn ^= 1
+    peer_sig.epoch += 1
+    k2()
+    _lib.check(L.fdt_detect_sort_nms_gather_signal(loc.data_ptr(), pri.data_ptr(), B, N, C, TOP_K, 5000, 0.3, 0.1, 0.2,
+                                                   int(hdl.buffer_ptrs_dev), int(peer_sig.sig_hdl.buffer_ptrs_dev), world, rank, 0, peer_sig.epoch,
+                                                   rank * B, ws.data_ptr(), ws.numel(), st))
+
+
 def barrier_only():
     peer.hdls[0].barrier()
 
@@ -72,6 +96,7 @@ def timed(fn, reps=30):
 
 
 for name, fn in (("local output", local_step), ("peer stores, no barrier", peers(False)), ("peer stores + barrier", peers(True)),
+                 ("gather to rank 0 + barrier", root_barrier), ("gather to rank 0, kernel signal", root_signal),
                  ("barrier alone", barrier_only)):
     v = timed(fn)
     if rank == 0:
