@@ -1,8 +1,10 @@
 // Detect (layers/functions/detection.py:34-84) and nms (layers/box_utils.py:275-340) for sm_100a.
 //
-// Two launches per call (+ a 256-byte memset), no host synchronisation, CUDA-graph capturable:
+// Three launches per call chained by programmatic dependent launch, no host synchronisation, CUDA-graph capturable:
+//   --  k_zero_counters     : clears the per-list counters; resident behind the previous call's K3, releases K2 once that ended.
 //   K2  k_threshold_compact : streams conf once (HBM-bound), strict `score > conf_thresh`, warp-ballot + block-aggregated
-//                             compaction into unordered 64-bit keys (score_key << 32 | prior).
+//                             compaction into unordered 64-bit keys (score_key << 32 | prior) + the list's score range.
+//       k_heads_threshold_compact : the same from the models' per-level NCHW head maps (max-in-out + softmax fused).
 //   K3  k_sort_nms          : one 1024-thread CTA -- or a 2-CTA thread-block cluster when the batch leaves SMs idle -- per
 //                             (image, class) list, launched with programmatic stream serialization behind K2:
 //         stage 1  top-nms_top_k selection by a bucket (counting) sort of the keys in shared memory
@@ -14,7 +16,9 @@
 //                    C  resolve by parallel sweeps (dead iff a suppressor is kept, kept iff all are dead),
 //                  stopping as soon as top_k boxes are kept (Detect reads only keep[:top_k], detection.py:80-81, so the
 //                  output equals the reference's run-to-completion loop);
-//         stage 3  output rows -- locally, or straight into every rank's gathered block over NVLink peer memory.
+//         stage 3  output rows -- locally, or straight into the gathered block of a root rank / of every rank over NVLink peer
+//                  memory, optionally publishing / awaiting the cross-rank completion signals itself.
+// MODE_NMS runs the same kernel for layers/box_utils.nms and, with FDT_NMS_* flags, for the FaceBoxes / MTCNN NMS variants.
 //
 // Tie rule (unspecified in the reference, torch.sort is unstable): keys are unique, descending key order = descending score,
 // higher prior index first among equal scores.  DESIGN.md section 4 has the exactness arguments.
