@@ -17,13 +17,11 @@ def pack_frames(frames):
     """list of per-frame [D_f, 5] arrays (what detect_face returns, iouTracke_cal.py:70-84; float32 rows or
     the float64 dummy [[0,0,0,0,0.4]]) -> (dets[total,5] float64, frame_off[F+1] int64).
     The reference widens to python floats with det0.tolist() (:127), i.e. float64, exactly like this."""
-    off = np.zeros(len(frames) + 1, np.int64)
-    for i, f in enumerate(frames):
-        off[i + 1] = off[i] + np.asarray(f).reshape(-1, 5).shape[0]
-    dets = np.zeros((max(int(off[-1]), 1), 5), np.float64)
-    for i, f in enumerate(frames):
-        if off[i + 1] > off[i]:
-            dets[off[i]:off[i + 1]] = np.asarray(f, dtype=np.float64).reshape(-1, 5)
+    arrs = [np.asarray(f, dtype=np.float64).reshape(-1, 5) for f in frames]
+    off = np.zeros(len(arrs) + 1, np.int64)
+    if arrs:
+        np.cumsum([a.shape[0] for a in arrs], out=off[1:])
+    dets = np.concatenate(arrs, 0) if off[-1] > 0 else np.zeros((1, 5), np.float64)
     return dets, off
 
 

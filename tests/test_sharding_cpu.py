@@ -88,3 +88,19 @@ def test_sharded_equals_single_process_world2(B):
         assert got[rank]["block"].tobytes() == single.tobytes()          # byte-identical to the single-process output
         assert got[rank]["packed"].tobytes() == single.tobytes()
         np.testing.assert_allclose(got[rank]["loss"], (float(sl), float(sc)), rtol=1e-6)
+
+
+def test_tracker_pack_frames_host_logic():
+    """pack_frames (host side of the tracker drop-in): float32 rows, the float64 dummy row, empty frames and an empty video."""
+    import numpy as np
+    from fdt_b200 import tracker
+    frames = [np.array([[1, 2, 3, 4, 0.5], [5, 6, 7, 8, 0.9]], np.float32), np.zeros((0, 5), np.float32),
+              np.array([[0, 0, 0, 0, 0.4]]), [[9.5, 1, 2, 3, 0.7]]]
+    dets, off = tracker.pack_frames(frames)
+    assert dets.dtype == np.float64 and off.dtype == np.int64
+    assert off.tolist() == [0, 2, 2, 3, 4]
+    assert np.array_equal(dets, np.array([[1, 2, 3, 4, np.float32(0.5)], [5, 6, 7, 8, np.float32(0.9)], [0, 0, 0, 0, 0.4], [9.5, 1, 2, 3, 0.7]]))
+    dets, off = tracker.pack_frames([])
+    assert off.tolist() == [0] and dets.shape == (1, 5)
+    dets, off = tracker.pack_frames([np.zeros((0, 5))])
+    assert off.tolist() == [0, 0] and dets.shape == (1, 5)
