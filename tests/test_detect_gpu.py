@@ -407,3 +407,23 @@ def test_detect_cuda_graph_capture_and_side_stream(layers):
     g.replay()
     torch.cuda.synchronize()
     assert not npy(out).any()
+
+
+@pytest.mark.parametrize("tag", ["1024", "480"])
+def test_detect_golden_other_shapes(layers, golden, tag):
+    """Reference fixtures at 1024x1024 (BASELINE config 5 shape) and at the tracker's 640x480 prior set (production thresholds)."""
+    g = golden("detect_shapes")
+    w, h, seed = (int(v) for v in g[tag + "_cfg"])
+    a = g[tag + "_args"]
+    args = (int(a[0]), int(a[1]), int(a[2]), float(a[3]), float(a[4]))
+    pri = synth.priors_numpy(w, h)
+    loc, conf = synth.detect_inputs(1, pri, seed, args[3], str(g[tag + "_mode"]))
+    assert synth.digest(loc, conf) == str(g[tag + "_in_sha"])
+    det = layers.Detect(*args)
+    out, counts, kept = det(cu(loc), cu(conf), cu(pri), return_aux=True)
+    out, counts, kept = npy(out), npy(counts), npy(kept)
+    assert np.array_equal(counts, g[tag + "_counts"]) and np.array_equal(kept, g[tag + "_kept"])      # the reference's kept priors
+    assert np.array_equal(out[:, 1, :, 0], g[tag + "_out"][..., 0])
+    np.testing.assert_allclose(out[:, 1, :, 1:], g[tag + "_out"][..., 1:], rtol=RTOL, atol=1e-7)
+    ref = orc.Detect(*args)(loc, conf, pri, return_aux=True)
+    assert_same((out, counts, kept), ref)

@@ -197,3 +197,24 @@ def test_torch_restatement_matches_oracle():
     ref = orc.Detect(2, 0, 750, 0.05, 0.3)(loc, conf, pri)
     assert np.array_equal(out[..., 0], ref[..., 0])
     close(out, ref)
+
+
+def shapes_case(g, tag):
+    w, h, seed = (int(v) for v in g[tag + "_cfg"])
+    a = g[tag + "_args"]
+    args = (int(a[0]), int(a[1]), int(a[2]), float(a[3]), float(a[4]))
+    pri = synth.priors_numpy(w, h)
+    loc, conf = synth.detect_inputs(1, pri, seed, args[3], str(g[tag + "_mode"]))
+    assert synth.digest(loc, conf) == str(g[tag + "_in_sha"]), "synthetic generator drifted"
+    return loc, conf, pri, args
+
+
+@pytest.mark.parametrize("tag", ["1024", "480"])
+def test_detect_other_shapes(golden, tag):
+    """1024x1024 (BASELINE config 5, N = 87,360) and the tracker's 640x480 prior set with production thresholds."""
+    g = golden("detect_shapes")
+    loc, conf, pri, args = shapes_case(g, tag)
+    out, counts, kept = orc.Detect(*args)(loc, conf, pri, return_aux=True)
+    assert np.array_equal(counts, g[tag + "_counts"]) and np.array_equal(kept, g[tag + "_kept"])
+    assert np.array_equal(out[:, 1, :, 0], g[tag + "_out"][..., 0])
+    close(out[:, 1, :, 1:], g[tag + "_out"][..., 1:])
