@@ -4,22 +4,28 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode random|clustered]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one Detect pass over one batch of B=64 synthetic head outputs per GPU (weak scaling: every
-rank owns its own 64 images; for N>1 the step ends with the gather of the fixed-shape detections block to rank 0
-detections block, the only exchange the path has).  Prints ONE JSON line (rank 0).
+One "step" = one Detect pass over one batch of B=64 synthetic head outputs per GPU (weak scaling: every rank owns its own
+64 images; for N>1 the step includes the gather of the fixed-shape detections block to rank 0, the only exchange the path
+has).  Prints ONE JSON line (rank 0).
 
-  value     frames/s, inputs resident in HBM: the K steps are issued back to back over 3 rotating input sets (165 MB per
-            GPU, larger than the 126 MB L2, so no step finds its inputs cached) and timed on the device with ONE CUDA-event
-            pair on the launching stream, bracketed by barrier + synchronize; max over ranks.
-  latency   the same step timed one at a time (own event pair, 256 MiB L2 flush + spin before it): what one isolated
-            call costs; the gap to 1/value is launch latency that back-to-back issue hides.
+  value     frames/s, inputs resident in HBM: K steps issued back to back on ONE stream over 3 rotating input sets (165 MB per
+            GPU > 126 MB of L2) and `depth` rotating output buffers, timed on the device with one CUDA-event pair per block of
+            K steps, barrier + synchronize on both sides; the block is repeated (>= 5 times, >= 10 ms in total) and the MEDIAN
+            block is reported; max over ranks.  Consecutive calls overlap on the device (workspace ring, fdt_detect in
+            include/fdt_b200.h); completion stays in stream order.
+  latency   the same step timed one at a time (own event pair, 256 MiB L2 flush + spin before it).
   e2e       frames/s through the public API with pinned HOST tensors: Detect.__call__ -> fdt_detect_host
-            (H2D copies + kernels + D2H of the detections inside the timed region, wall clock).
-  roofline  dominant kernel (k_sort_nms) timed live with its own event pair via the stage entry points.
+            (H2D copies + kernels + D2H of the detections inside the timed region, wall clock), beside the host's own pinned
+            H2D rate measured in the same run.
+  roofline  dominant kernel (k_sort_nms) timed live through the stage entry points.
   cpu_baseline  the C oracle port (oracle/, the checker) on the host cores, bounded sample.
---impl reference times that CPU port with all host threads as the reference arm.
+  secondary (N=1) BASELINE configs 3, 4, 5 -- MultiBoxLoss B=32, the IoU tracker over 10k frames, Detect B=512 @1024^2 -- each
+            with a parity bit against the oracle, outside the headline timed region.
+  gather_check (N>1) the fused gathered block on rank 0 == NCCL all-gather of every rank's local Detect output, byte for byte.
+--impl reference times the CPU port with all host threads as the reference arm.
 """
 import argparse
+import glob
 import json
 import os
 import statistics
@@ -48,25 +54,28 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="random", choices=["random", "clustered"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--depth", type=int, default=0, help="workspace slots (calls that may overlap on the device); 0 = library default")
     ap.add_argument("--gather", default="peer", choices=["peer", "peer-barrier", "peer-all", "nccl"],
-                    help="N>1: peer = rows stored into rank 0's gathered block by the NMS kernel over NVLink, completion signalled by the "
-                         "kernel itself (fused gather); peer-barrier = the same followed by a symmetric-memory barrier; "
-                         "peer-all = into every rank's block + barrier (fused all-gather); nccl = all_gather after the kernel")
+                    help="N>1: peer = rows stored into rank 0's gathered block by the NMS kernel over NVLink, completion signalled through "
+                         "symmetric memory (fused gather); peer-barrier = the same followed by a symmetric-memory barrier; "
+                         "peer-all = into every rank's block, signalled (fused all-gather); nccl = all_gather after the kernel")
     return ap.parse_args()
 
 
-GATHER_NOTE = {"peer": ", gather to rank 0 fused into k_sort_nms (NVLink peer stores; completion signals published / awaited by the kernel "
-                       "over symmetric memory: only rank 0 waits)",
-               "peer-barrier": ", gather to rank 0 fused into k_sort_nms (NVLink peer stores + symmetric-memory barrier)",
-               "peer-all": ", all-gather fused into k_sort_nms (NVLink peer stores into every rank's block + symmetric-memory barrier)",
-               "nccl": ", NCCL all-gather of detections"}
-
-
-def workload_config(mode, n_gpus, gather="nccl"):
+def workload_config(mode, n_gpus):
+    """identical for both arms (the driver compares the dicts)"""
     return {"workload": f"Detect batch {B_PER_GPU}/GPU @{WIDTH}x{HEIGHT} (34,125 priors), conf_thresh {CONF_T}, "
                         f"top_k {TOP_K}, nms_top_k {NMS_TOP_K}, NMS {NMS_T}; synthetic heads mode={mode} seed={SEED}",
             "global_batch": B_PER_GPU * n_gpus, "priors": 34125, "classes": 2,
-            "parallelism": f"batch-sharded x{n_gpus}" + (GATHER_NOTE[gather] if n_gpus > 1 else "")}
+            "parallelism": f"batch-sharded x{n_gpus}, detections gathered on rank 0" if n_gpus > 1 else "batch-sharded x1"}
+
+
+GATHER_NOTE = {"peer": "gather to rank 0 fused into k_sort_nms (16-byte NVLink peer stores into a ring of 4 gathered blocks; completion "
+                       "signals through symmetric memory, a one-block await kernel on rank 0; no rank waits inside the NMS kernel)",
+               "peer-barrier": "gather to rank 0 fused into k_sort_nms (NVLink peer stores + symmetric-memory barrier)",
+               "peer-all": "all-gather fused into k_sort_nms (NVLink peer stores into every rank's block, signalled)",
+               "nccl": "NCCL all-gather of detections after the kernel"}
 
 
 def peaks():
@@ -75,6 +84,22 @@ def peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_traffic():
+    """dram bytes per k_sort_nms launch from the newest `ncu --set full` summary under profiles/ (written by tools/ncu_summary.py)"""
+    best = None
+    for path in glob.glob(os.path.join(ROOT, "profiles", "r*_sortnms_traffic*.json")):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            if best is None or d.get("order", 0) >= best[1].get("order", 0):
+                best = (path, d)
+        except Exception:                                         # noqa: BLE001
+            pass
+    if best is None:
+        return None, "no ncu --set full summary under profiles/"
+    return float(best[1]["dram_bytes_read"]) + float(best[1]["dram_bytes_write"]), os.path.relpath(best[0], ROOT) + ": " + best[1].get("note", "")
 
 
 def host_threads():
@@ -176,13 +201,134 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps,
             "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args.mode, 1),
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.mode, args.gpus),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": f"{args.steps} x the full B={B_PER_GPU} batch, C oracle (oracle/fdt_oracle.c), "
                                        f"OpenMP over images, NMS run to completion as the reference does"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ secondary workloads (N = 1)
+def _timed_isolated(torch, fn, flush, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        torch.cuda._sleep(250_000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(statistics.median(ts))
+
+
+def secondary_workloads(torch, dev, flush, peak):
+    """BASELINE.json configs 3, 4 and 5 on one GPU, device-timed (isolated calls, L2 flushed), each checked against the oracle."""
+    from fdt_b200 import _lib, synth
+    from fdt_b200 import tracker as T
+    from fdt_b200.layers import Detect
+    from fdt_b200.layers.modules.multibox_loss import pack_targets
+    from oracle import oracle as orc
+    L = _lib.lib()
+    st = _lib.stream_ptr()
+    out = {}
+    # ---- config 3: MultiBoxLoss forward, B=32, N=34,125, G ~ U{0..200}
+    try:
+        B = 32
+        pri = synth.priors_numpy(640, 640); N = pri.shape[0]
+        loc, conf, targets = synth.multibox_inputs(B, pri, 3030, 0, 200)
+        l, c, p = (torch.from_numpy(a).to(dev) for a in (loc, conf, pri))
+        tg = [torch.from_numpy(t).to(dev) for t in targets]
+        gt, off, total = pack_targets(tg, dev)
+        losses = torch.empty(2, device=dev); norm = torch.empty(1, device=dev)
+        loc_t = torch.empty((B, N, 4), device=dev); conf_t = torch.empty((B, N), dtype=torch.int64, device=dev)
+        sel = torch.empty((B, N), dtype=torch.uint8, device=dev)
+        ws = _lib.workspace(L.fdt_multibox_workspace_bytes(B, N, 2, total), dev, "bench-mbl")
+
+        def fwd():
+            _lib.check(L.fdt_multibox_loss_forward(l.data_ptr(), c.data_ptr(), p.data_ptr(), gt.data_ptr(), off.data_ptr(), total,
+                                                   B, N, 2, 0.35, 3, 0, 0.1, 0.2, losses.data_ptr(), norm.data_ptr(),
+                                                   loc_t.data_ptr(), conf_t.data_ptr(), sel.data_ptr(), None, ws.data_ptr(),
+                                                   ws.numel(), st))
+        ms = _timed_isolated(torch, fwd, flush, 15)
+        ref = orc.multibox_loss(loc, conf, pri, targets, 0.35, 3, False)
+        got = losses.cpu().numpy()
+        ok = bool(np.array_equal(conf_t.cpu().numpy(), ref["conf_t"]) and
+                  np.array_equal(sel.cpu().numpy().astype(bool), (ref["conf_t"] > 0) | ref["neg"]) and
+                  abs(got[0] - ref["loss_l"]) <= 1e-5 * abs(ref["loss_l"]) and abs(got[1] - ref["loss_c"]) <= 1e-5 * abs(ref["loss_c"]))
+        G = int(sum(t.shape[0] for t in targets))
+        alg = B * 48 * N + 20 * G
+        out["multibox_loss_b32"] = {"workload": "MultiBoxLoss match/encode + mining + loss forward, B=32, N=34,125, G~U{0..200} (BASELINE config 3)",
+                                    "ms": ms, "value": B / (ms * 1e-3), "unit": "images/s", "algorithmic_bytes": alg,
+                                    "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak, "gt_boxes": G,
+                                    "parity": "ok" if ok else "MISMATCH",
+                                    "parity_how": "whole batch vs the C oracle: match labels and mined mask bit-exact, both losses within 1e-5 relative"}
+        del l, c, loc_t, conf_t, sel
+    except Exception as e:                                        # noqa: BLE001
+        out["multibox_loss_b32"] = {"error": repr(e)}
+    # ---- config 4: IoU tracker, 10,000 frames x U{1..300} detections
+    try:
+        frames = synth.tracker_frames(F=10000, seed=4040, d_lo=1, d_hi=300, n_objects=300, empty_every=1000)
+        dets, off = T.pack_frames(frames)
+        d = torch.from_numpy(dets).to(dev); o = torch.from_numpy(off).to(dev)
+        F = len(frames); total = int(off[-1]); max_d = int(np.diff(off).max())
+        n = torch.zeros(1, dtype=torch.int64, device=dev); t_off = torch.zeros(total + 2, dtype=torch.int64, device=dev)
+        t_dets = torch.zeros(total, dtype=torch.int64, device=dev); t_start = torch.zeros(total + 1, dtype=torch.int64, device=dev)
+        t_max = torch.zeros(total + 1, dtype=torch.float64, device=dev)
+        ws = _lib.workspace(L.fdt_iou_track_workspace_bytes(F, total, max_d), dev, "bench-trk")
+
+        def run():
+            _lib.check(L.fdt_iou_track(d.data_ptr(), o.data_ptr(), F, total, max_d, 0.4, 0.6, 5, n.data_ptr(), t_off.data_ptr(),
+                                       t_dets.data_ptr(), t_start.data_ptr(), t_max.data_ptr(), ws.data_ptr(), ws.numel(), st))
+        ms = _timed_isolated(torch, run, flush, 3, warm=1)
+        tr = T.iou_track(frames)
+        t0 = time.perf_counter(); ref = orc.iou_track(frames); cpu_s = time.perf_counter() - t0
+        same = len(tr) == len(ref) and all(a["bboxes"] == b["bboxes"] and a["start_frame"] == b["start_frame"] and
+                                           a["max_score"] == b["max_score"] for a, b in zip(tr, ref))
+        out["iou_tracker_10k"] = {"workload": "IoU tracker association, 10,000 frames x U{1..300} detections (BASELINE config 4)",
+                                  "ms": ms, "value": F / (ms * 1e-3), "unit": "frames/s", "detections": total, "tracks": len(tr),
+                                  "algorithmic_bytes": 28 * total, "roofline_frac": 28 * total / (ms * 1e-3) / 1e9 / peak,
+                                  "note": "latency-bound serial chain over the frames (SURVEY 8d); replicas only across GPUs",
+                                  "cpu_port_frames_per_s_1_thread": F / cpu_s,
+                                  "parity": "ok" if same else "MISMATCH",
+                                  "parity_how": "all 10,000 frames vs the C oracle: track membership, order, start frames and max scores bit-exact"}
+    except Exception as e:                                        # noqa: BLE001
+        out["iou_tracker_10k"] = {"error": repr(e)}
+    # ---- config 5 on one GPU: Detect B=512 @1024x1024 (N=87,360), device-generated inputs (1.07 GB)
+    try:
+        B = 512
+        pri = synth.priors_numpy(1024, 1024); N = pri.shape[0]
+        g = torch.Generator(device=dev); g.manual_seed(5)
+        loc = torch.randn((B, N, 4), device=dev, generator=g) * 0.5
+        s1 = torch.sigmoid(torch.randn((B, N), device=dev, generator=g) * 2.0 - 4.5)
+        conf = torch.stack([1 - s1, s1], -1).contiguous()
+        del s1
+        det = Detect(2, 0, TOP_K, CONF_T, NMS_T)
+        p = torch.from_numpy(pri).to(dev)
+        res = [None]
+
+        def run5():
+            res[0] = det(loc, conf, p)
+        ms = _timed_isolated(torch, run5, flush, 6)
+        sample = 6
+        ref = orc.Detect(2, 0, TOP_K, CONF_T, NMS_T)
+        ref.early_exit = True
+        want = ref(loc[:sample].cpu().numpy(), conf[:sample].cpu().numpy(), pri)
+        ok = bool(np.array_equal(res[0][:sample].cpu().numpy(), want))
+        alg = B * (24 * N + 30000) + 16 * N
+        out["detect_b512_1024"] = {"workload": "Detect B=512 @1024x1024 (N=87,360) on one GPU (BASELINE config 5 unsharded; device-generated inputs)",
+                                   "ms": ms, "value": B / (ms * 1e-3), "unit": "frames/s", "algorithmic_bytes": alg,
+                                   "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak,
+                                   "parity": "ok" if ok else "MISMATCH",
+                                   "parity_how": f"first {sample} images vs the C oracle, bit-exact (scores may tie: both sides order ties by prior index)"}
+        del loc, conf
+    except Exception as e:                                        # noqa: BLE001
+        out["detect_b512_1024"] = {"error": repr(e)}
+    return out
 
 
 def main():
@@ -217,17 +363,18 @@ def main():
             loc_np, conf_np = l_np, c_np
         sets.append((torch.from_numpy(l_np).to(dev), torch.from_numpy(c_np).to(dev)))
     pri = torch.from_numpy(pri_np).to(dev)
-    cur = [0]                                            # which input set the next step reads
+    cur = [0]                                            # step counter: which input set / output buffer the next step uses
 
     def inputs():
         return sets[cur[0] % ROTATE]
-    loc, conf = sets[0]
     det = Detect(2, 0, TOP_K, CONF_T, NMS_T)
     B, C = B_PER_GPU, 2
     L = _lib.lib()
-    out = torch.empty((B, C, TOP_K, 5), dtype=torch.float32, device=dev)
-    gathered = torch.empty((world * B, C, TOP_K, 5), dtype=torch.float32, device=dev) if world > 1 else None
-    ws = _lib.workspace(L.fdt_detect_workspace_bytes(B, N, C), dev, "bench")
+    depth = args.depth if args.depth > 0 else _lib.DETECT_DEPTH
+    depth = max(1, min(4, depth))
+    ws = torch.empty(L.fdt_detect_workspace_bytes_depth(B, N, C, depth), dtype=torch.uint8, device=dev)
+    n_out = max(depth, 2)
+    outs = [torch.empty((B, C, TOP_K, 5), dtype=torch.float32, device=dev) for _ in range(n_out)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)              # > 126 MB L2
     st = _lib.stream_ptr()
 
@@ -236,51 +383,48 @@ def main():
 
     def stage2():
         _lib.check(L.fdt_detect_sort_nms(inputs()[0].data_ptr(), pri.data_ptr(), B, N, C, TOP_K, NMS_TOP_K, NMS_T, 0.1, 0.2,
-                                         out.data_ptr(), None, None, ws.data_ptr(), ws.numel(), st))
+                                         outs[0].data_ptr(), None, None, ws.data_ptr(), ws.numel(), st))
 
-    gather = args.gather if world > 1 else "nccl"
+    gather = args.gather if world > 1 else None
     peer = None
+    gathered = None
     if world > 1 and gather in ("peer", "peer-barrier", "peer-all"):
         try:
             from fdt_b200.sharding import PeerGatherDetect
-            peer = PeerGatherDetect(det, B, dest="all" if gather == "peer-all" else 0, signal="kernel" if gather == "peer" else "barrier")
+            peer = PeerGatherDetect(det, B, dest="all" if gather == "peer-all" else 0, signal="barrier" if gather == "peer-barrier" else "kernel")
         except Exception as e:                          # noqa: BLE001  (symmetric memory unavailable: keep the NCCL gather)
             if rank == 0:
                 print(f"peer gather unavailable ({e!r}); using NCCL all_gather", file=sys.stderr)
             gather = "nccl"
-
-    def stage2_gather():
-        if peer is not None:
-            hdl = peer.hdls[peer.turn]
-            peer.turn ^= 1
-            if peer.signal == "kernel":
-                peer.epoch += 1
-                _lib.check(L.fdt_detect_sort_nms_gather_signal(inputs()[0].data_ptr(), pri.data_ptr(), B, N, C, TOP_K, NMS_TOP_K, NMS_T, 0.1, 0.2,
-                                                               int(hdl.buffer_ptrs_dev), int(peer.sig_hdl.buffer_ptrs_dev), world, rank, 0,
-                                                               peer.epoch, rank * B, ws.data_ptr(), ws.numel(), st))
-            else:
-                ptrs, n_dst = peer.dest_ptrs(hdl)
-                _lib.check(L.fdt_detect_sort_nms_peers(inputs()[0].data_ptr(), pri.data_ptr(), B, N, C, TOP_K, NMS_TOP_K, NMS_T, 0.1, 0.2,
-                                                       ptrs, n_dst, rank * B, ws.data_ptr(), ws.numel(), st))
-                hdl.barrier()
-        else:
-            stage2()
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, out)
-
-    def detect_call():
-        lc = inputs()
-        _lib.check(L.fdt_detect(lc[0].data_ptr(), lc[1].data_ptr(), pri.data_ptr(), B, N, C, TOP_K, NMS_TOP_K, CONF_T, NMS_T, 0.1, 0.2,
-                                out.data_ptr(), None, None, ws.data_ptr(), ws.numel(), st))
+    if world > 1 and gather == "nccl":
+        gathered = [torch.empty((world * B, C, TOP_K, 5), dtype=torch.float32, device=dev) for _ in range(n_out)]
+    last_block = [None]
 
     def step():
-        # N=1: the public C-ABI call (K2 + K3 with programmatic dependent launch, nothing in between).
-        # N>1: the same two kernels through the stage entry points so that K3 can store into the peers' blocks.
-        if world == 1:
-            detect_call()
+        # N=1: the public C-ABI call.  N>1: the same call with the gather fused into the NMS kernel (or followed by NCCL).
+        lc = inputs()
+        args12 = (lc[0].data_ptr(), lc[1].data_ptr(), pri.data_ptr(), B, N, C, TOP_K, NMS_TOP_K, CONF_T, NMS_T, 0.1, 0.2)
+        if world == 1 or gather == "nccl":
+            o = outs[cur[0] % n_out]
+            _lib.check(L.fdt_detect(*args12, o.data_ptr(), None, None, ws.data_ptr(), ws.numel(), st))
+            if world > 1:
+                dist.all_gather_into_tensor(gathered[cur[0] % n_out], o)
+                last_block[0] = gathered[cur[0] % n_out]
+            else:
+                last_block[0] = o
         else:
-            stage1()
-            stage2_gather()
+            hdl, buf = peer.hdls[peer.turn], peer.bufs[peer.turn]
+            peer.turn = (peer.turn + 1) % peer.RING
+            ptrs, n_dst = peer.dest_ptrs(hdl)
+            if peer.signal == "kernel":
+                peer.epoch += 1
+                _lib.check(L.fdt_detect_gather_signal(*args12, ptrs, n_dst, int(peer.sig_hdl.buffer_ptrs_dev), world, rank,
+                                                      -1 if peer.dest == "all" else 0, peer.epoch, peer.RING, rank * B,
+                                                      ws.data_ptr(), ws.numel(), st))
+            else:
+                _lib.check(L.fdt_detect_peers(*args12, ptrs, n_dst, rank * B, ws.data_ptr(), ws.numel(), st))
+                hdl.barrier()
+            last_block[0] = buf
         cur[0] += 1
 
     spin_cycles = 250_000
@@ -292,23 +436,58 @@ def main():
 
     sampler = ClockSampler(local)
     sampler.start()
-    # ---- throughput: K steps back to back over the rotating input sets, one event pair, barrier + synchronize on both sides
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler.active = True
+    # ---- throughput: blocks of K steps back to back over the rotating input sets, one event pair per block, barrier + synchronize
+    #      on both sides of every block; the median block is reported
+    blocks_ms = []
     wall0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda._sleep(2_000_000)                        # ~1 ms of GPU spin: the host gets ahead, the pair sees device time only
-    e0.record()
-    for i in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    sampler.active = True
+    n_blocks = 0
+    while n_blocks < 5 or (sum(blocks_ms) < 10.0 and n_blocks < 50):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(2_000_000)                    # ~1 ms of GPU spin: the host gets ahead, the pair sees device time only
+        e0.record()
+        for i in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([float(e0.elapsed_time(e1))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)    # every block: max over ranks
+        blocks_ms.append(float(t.item()))
+        n_blocks += 1
     wall = time.perf_counter() - wall0
-    total_ms = float(e0.elapsed_time(e1))
+    total_ms = float(statistics.median(blocks_ms))
+    # ---- N>1: the gathered block the timed path produced must equal the NCCL all-gather of the ranks' local outputs
+    gather_check = None
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        cur[0] = 0
+        step()                                          # one more step on input set 0
+        torch.cuda.synchronize()
+        dist.barrier()
+        fused = last_block[0].clone()
+        local_out = det(sets[0][0], sets[0][1], pri)
+        ref_block = torch.empty((world * B, C, TOP_K, 5), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(ref_block, local_out)
+        torch.cuda.synchronize()
+        same = True
+        if rank == 0 or gather in ("peer-all", "nccl"):
+            same = bool(torch.equal(fused.view(torch.int32), ref_block.view(torch.int32)))
+        if peer is not None:
+            try:
+                peer.check()
+            except RuntimeError as e:
+                same = False
+                print(f"rank {rank}: {e}", file=sys.stderr)
+        t = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        gather_check = "ok" if int(t.item()) == 1 else "MISMATCH"
     # ---- latency: the same step in isolation (own event pair; L2 flushed and the GPU spinning while the host enqueues it)
     n_lat = max(10, min(args.steps, 30))
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(n_lat)]
@@ -327,10 +506,10 @@ def main():
     sampler.active = False
     sampler.stop_flag.set()
     step_ms = [e[0].elapsed_time(e[1]) for e in ev]
-    k3_ms = None
+    k3_iso_ms = k3_b2b_ms = None
     if world == 1:
-        # dominant kernel alone: same launches through the stage entry points with an event pair around stage 2 only
-        k3_ms = []
+        # dominant kernel alone, (a) isolated: stage 1, then an event pair around the stage-2 launch, L2 flushed before the step
+        k3 = []
         for _ in range(max(10, min(args.steps, 30))):
             flush.zero_()
             torch.cuda._sleep(spin_cycles)
@@ -340,31 +519,51 @@ def main():
             stage2()
             b2.record()
             torch.cuda.synchronize()
-            k3_ms.append(a.elapsed_time(b2))
+            k3.append(a.elapsed_time(b2))
+            cur[0] += 1
+        k3_iso_ms = float(statistics.median(k3))
+        # (b) as it runs in the timed region -- launches back to back, overlapping each other like consecutive calls do:
+        #     one event pair around K stage-2 launches on the same prepared workspace slot, average per launch
+        reps = []
+        for _ in range(5):
+            stage1()
+            torch.cuda.synchronize()
+            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(1_000_000)
+            a.record()
+            for _ in range(args.steps):
+                stage2()
+            b2.record()
+            torch.cuda.synchronize()
+            reps.append(a.elapsed_time(b2) / args.steps)
+            cur[0] += 1
+        k3_b2b_ms = float(statistics.median(reps))
     lat_ms = float(np.mean(step_ms))
     if world > 1:
-        t = torch.tensor([total_ms, lat_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([lat_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, lat_ms = float(t[0].item()), float(t[1].item())
+        lat_ms = float(t[0].item())
     ms_per_step = total_ms / args.steps
     value = world * B * args.steps / (total_ms * 1e-3)
 
-    # ---- dominant kernel alone (k_sort_nms), timed live at N=1 with its own event pair
     peak, peak_src = peaks()
     roofline = None
     if world == 1:
-        k3 = float(np.mean(k3_ms))
         k3_bytes = B * (16 * N + C * TOP_K * 5 * 4) + 16 * N           # loc + output rows per image, priors once
         step_bytes = B * (24 * N + C * TOP_K * 5 * 4) + 16 * N         # 849,000 B/image + priors
+        traffic, traffic_src = measured_traffic()
         roofline = {"bound": "hbm", "kernel": "k_sort_nms (select/sort + decode + lazy NMS + output rows)",
-                    "achieved": k3_bytes / (k3 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": k3_bytes / (k3 * 1e-3) / 1e9 / peak,
-                    "traffic": 12.554e6,     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full of this config
-                    "traffic_source": "profiles/r01_sortnms_v6_phases.txt (12.547 MB read, 7.2 KB written)",
+                    "achieved": k3_bytes / (k3_b2b_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": k3_bytes / (k3_b2b_ms * 1e-3) / 1e9 / peak,
+                    "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peak_src,
-                    "kernel_ms": k3, "kernel_share_of_step": k3 / lat_ms,
-                    "kernel_timing": "own event pair around the stage-2 launch of an isolated step, L2 flushed before the step "
-                                     "(share = kernel_ms / latency.ms_per_step, both measured on isolated steps)",
+                    "kernel_ms": k3_b2b_ms, "kernel_ms_isolated": k3_iso_ms,
+                    "frac_isolated": k3_bytes / (k3_iso_ms * 1e-3) / 1e9 / peak,
+                    "kernel_share_of_step": min(1.0, k3_b2b_ms / ms_per_step),
+                    "kernel_timing": "kernel_ms = average launch duration with the launches issued back to back as in the timed region "
+                                     f"(one event pair around {args.steps} stage-2 launches on a prepared workspace; consecutive launches overlap on "
+                                     "the device exactly like consecutive Detect calls, median of 5); kernel_ms_isolated = own event pair around "
+                                     "ONE stage-2 launch, L2 flushed before the step",
                     "algorithmic_bytes_per_launch": k3_bytes,
                     "step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                              "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
@@ -388,18 +587,34 @@ def main():
         t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
+    # the host's pinned H2D rate in this run: what bounds e2e from below
+    h2d_bytes = int(conf_h.numel() * 4 + pri_h.numel() * 4)
+    stage_dev = torch.empty_like(conf_h, device=dev)
+    stage_dev.copy_(conf_h, non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        stage_dev.copy_(conf_h, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_gbs = 10 * conf_h.numel() * 4 / (time.perf_counter() - t0) / 1e9
+    floor_ms = h2d_bytes / (h2d_gbs * 1e9) * 1e3
     e2e = {"value": world * B * e2e_steps / e2e_dt, "unit": "frames/s",
-           "h2d_bytes_per_step": int(conf_h.numel() * 4 + pri_h.numel() * 4),
+           "h2d_bytes_per_step": h2d_bytes,
            "h2d_note": "conf + priors are copied (cudaMemcpyAsync from pinned memory); the pinned loc tensor (%d bytes) is NOT copied: "
                        "k_sort_nms gathers only the rows NMS decodes (<= 1024 x 16 B per image and round) from host memory over PCIe" % int(loc_h.numel() * 4),
            "host_input_bytes_per_step": int(loc_h.numel() * 4 + conf_h.numel() * 4 + pri_h.numel() * 4),
            "d2h_bytes_per_step": int(o.numel() * 4), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_dt / e2e_steps,
            "ms_per_step_median": 1e3 * statistics.median(per), "ms_per_step_max": 1e3 * max(per),
+           "pinned_h2d_gbs_this_host": h2d_gbs, "pcie_floor_ms": floor_ms,
+           "frac_of_pcie_floor": floor_ms / (1e3 * e2e_dt / e2e_steps),
+           "scope": "single-process public API" if world == 1 else "per-rank, no gather (every rank runs Detect on host tensors independently)",
            "api": "fdt_b200.layers.Detect.__call__(pinned CPU tensors) -> fdt_detect_host"}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
+        if gather_check == "MISMATCH":
+            sys.exit(3)
         return
 
     cpu = None
@@ -408,24 +623,41 @@ def main():
         cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": f"{n} images ({n // B} x the B={B} batch) in {dt:.1f} s, C oracle port with OpenMP over images, "
                          f"NMS run to completion as box_utils.nms does (the reference itself is a Python loop, ~1-2 frames/s)"}
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        del sets
+        secondary = secondary_workloads(torch, dev, flush, peak)
 
+    launches_per_step = 3 + (1 if (world > 1 and peer is not None and peer.signal == "kernel") else 0)
     line = {"metric": METRIC,
             "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args.mode, world, gather),
-                                                                l2=f"inputs larger than L2: {ROTATE} rotating input sets per GPU ({ROTATE * 54.9:.0f} MB > 126 MB), steps issued back to back, "
-                                                                   "one CUDA-event pair around the K steps"),
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.mode, world),
+            "l2": f"inputs larger than L2: {ROTATE} rotating input sets per GPU ({ROTATE * 54.9:.0f} MB > 126 MB), steps issued back to back on one stream",
+            "timing": {"blocks": n_blocks, "steps_per_block": args.steps, "block_ms": blocks_ms, "reported": "median block",
+                       "how": "one CUDA-event pair per block of K steps on the launching stream, barrier + synchronize on both sides of every block, "
+                              "max over ranks per block", "workspace_depth": depth,
+                       "overlap": "consecutive calls overlap on the device (workspace ring of `depth` slots; completion in stream order)"},
             "latency": {"ms_per_step": lat_ms, "frames_per_s": world * B / (lat_ms * 1e-3), "steps": n_lat,
                         "how": "each step alone with its own event pair; 256 MiB L2 flush + 0.1 ms GPU spin before it (outside the pair)"},
-            "clocks": sampler.result(), "e2e": e2e, "gpu_launches": 3 * args.steps,      # k_zero_counters, k_threshold_compact, k_sort_nms
+            "clocks": sampler.result(), "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps * n_blocks,      # k_detect_begin, k_threshold_compact, k_sort_nms (+ k_gather_await on rank 0)
+            "gpu_launches_per_step": launches_per_step,
             "wall_s_timed_region": wall}
+    if world > 1:
+        line["gather"] = GATHER_NOTE[gather]
+        line["gather_check"] = gather_check
     if roofline:
         line["roofline"] = roofline
     if cpu:
         line["cpu_baseline"] = cpu
+    if secondary:
+        line["secondary"] = secondary
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if gather_check == "MISMATCH":
+        sys.exit(3)
 
 
 if __name__ == "__main__":

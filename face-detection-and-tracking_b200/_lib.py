@@ -44,12 +44,17 @@ SIGNATURES = {
     "fdt_threshold_nms_workspace_bytes": (_sz, [_i64]),
     "fdt_threshold_nms": (_i, [_vp, _vp, _i64, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     "fdt_detect_workspace_bytes": (_sz, [_i, _i64, _i]),
+    "fdt_detect_workspace_bytes_depth": (_sz, [_i, _i64, _i, _i]),
+    "fdt_detect_status": (_i, [_vp, _vp, _vp]),
+    "fdt_set_option": (_i, [C.c_char_p, _i]),
     "fdt_detect": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fdt_detect_threshold_compact": (_i, [_vp, _i, _i64, _i, _f, _vp, _sz, _vp]),
     "fdt_detect_sort_nms": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "fdt_detect_sort_nms_peers": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _vp, _i, _i64, _vp, _sz, _vp]),
-    "fdt_detect_sort_nms_gather_signal": (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _vp, _vp, _i, _i, _i, C.c_uint32, _i64, _vp, _sz, _vp]),
-    "fdt_detect_candidate_counts": (_i, [_vp, _i, _i, _vp, _vp]),
+    "fdt_detect_peers": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _f, _vp, _i, _i64, _vp, _sz, _vp]),
+    "fdt_detect_gather_signal": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _f, _vp, _i, _vp, _i, _i, _i, C.c_uint32, _i, _i64,
+                                      _vp, _sz, _vp]),
+    "fdt_detect_gather_await": (_i, [_vp, _i, _i, C.c_uint32, _vp, _vp]),
+    "fdt_detect_candidate_counts": (_i, [_vp, _sz, _i, _i64, _i, _vp, _vp]),
     "fdt_heads_to_loc_conf": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "fdt_detect_heads": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fdt_debug_k3_profile": (_i, [_vp]),
@@ -134,14 +139,59 @@ _workspaces = {}
 
 
 def workspace(nbytes: int, device: torch.device, tag: str = "") -> torch.Tensor:
-    """Grow-only scratch buffer per (device, stream, tag); torch's caching allocator returns 512-byte
-    aligned blocks, which satisfies the library's 256-byte requirement."""
+    """Grow-only scratch buffer per (device, stream, tag) for the STATELESS entry points (everything but the Detect family);
+    torch's caching allocator returns 512-byte aligned blocks, which satisfies the library's 256-byte requirement.
+    A buffer is never replaced while its stream is capturing a CUDA graph (the graph would keep the old pointer)."""
     key = (device.index, stream_ptr(), tag)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError(f"fdt_b200: workspace '{tag}' would have to grow ({ws.numel()} -> {nbytes} bytes) during CUDA-graph "
+                               "capture; run the largest shape once before capturing")
         ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
+
+
+DETECT_DEPTH = int(os.environ.get("FDT_DETECT_DEPTH", "3"))          # workspace slots: how many calls may overlap on the device
+DETECT_WS_BUDGET = 2 << 30                                             # do not spend more than this on one Detect workspace
+
+
+class DetectWorkspaces:
+    """Workspaces of the Detect family, owned by the object that makes the calls (a Detect instance).  They are STATEFUL -- the
+    control block at their head sequences consecutive calls so that they overlap on the device -- hence one buffer per
+    (device, stream, B, N, C), kept for the owner's lifetime and never replaced (a captured CUDA graph may hold its pointer)."""
+
+    def __init__(self):
+        self._ws = {}
+
+    def get(self, B: int, N: int, C: int, device: torch.device) -> torch.Tensor:
+        key = (device.index, stream_ptr(), B, N, C)
+        ws = self._ws.get(key)
+        if ws is None:
+            L = lib()
+            slot = L.fdt_detect_workspace_bytes_depth(B, N, C, 2) - L.fdt_detect_workspace_bytes(B, N, C)
+            depth = max(1, min(DETECT_DEPTH, DETECT_WS_BUDGET // max(slot, 1)))
+            ws = torch.empty(int(L.fdt_detect_workspace_bytes_depth(B, N, C, int(depth))), dtype=torch.uint8, device=device)
+            self._ws[key] = ws
+            if len(self._ws) > 64:                     # streams / shapes come and go: drop the oldest entries
+                for k in list(self._ws)[:-32]:
+                    del self._ws[k]
+        return ws
+
+    def status(self, device=None) -> int:
+        """OR of the FDT_STATUS_* bits of every workspace (synchronises)."""
+        bits = 0
+        out = C.c_uint32(0)
+        for (dev_index, st, *_), ws in self._ws.items():
+            with torch.cuda.device(dev_index):
+                check(lib().fdt_detect_status(ws.data_ptr(), st, C.byref(out)))
+            bits |= out.value
+        return bits
+
+
+def set_option(name: str, value: int) -> None:
+    check(lib().fdt_set_option(name.encode(), int(value)))
 
 
 def dev_f32(t: torch.Tensor, device: torch.device) -> torch.Tensor:

@@ -22,7 +22,10 @@
 //
 // Tie rule (unspecified in the reference, torch.sort is unstable): keys are unique, descending key order = descending score,
 // higher prior index first among equal scores.  DESIGN.md section 4 has the exactness arguments.
+#include <atomic>
 #include <cstdlib>
+#include <mutex>
+#include <string>
 #include <cooperative_groups.h>
 #include "fdt_common.cuh"
 
@@ -119,20 +122,162 @@ k_heads_to_loc_conf(const HeadLevels h, const int N, const int softmax, float *_
     if (loc_out) reinterpret_cast<float4 *>(loc_out)[(int64_t)b * N + p] = head_loc_row(h, b, p);
 }
 
-// ------------------------------------------------------------------------------------------- K2
-// Clears the per-list counters.  A kernel rather than cudaMemsetAsync so that k_threshold_compact can be launched behind it
-// with programmatic stream serialization: its blocks start and stream `conf` while this grid is still in flight (a memset
-// node costs ~3.5 us of serialised front-end latency per call).
-// It is itself launched behind whatever precedes it in the stream with programmatic serialization: when that is the k_sort_nms
-// of the previous Detect call (which triggers at its start), this grid is already resident when that kernel ends.  It waits for
-// its predecessor's COMPLETION before it lets k_threshold_compact be scheduled: K2 loads `conf` ahead of its own dependency wait,
-// which is only safe once everything earlier in the stream (possibly an early-triggering producer of `conf`) has finished.
-__global__ void k_zero_counters(int32_t *__restrict__ counters, int n)
+// ------------------------------------------------------------------------------------------- call sequencing
+// The first 256 bytes of a Detect workspace hold a control block that lives across calls; the rest is a ring of R >= 1 slots
+// (per-list counters + candidate keys + spilled kept rows), R = how many the caller's workspace has room for.  Call number s
+// (1, 2, ...) of a workspace uses slot s % R, so with R >= 2 nothing call s + 1 writes before its NMS is read by call s: its
+// counter clear and K2 run UNDER the previous call's k_sort_nms (on the SMs that kernel leaves idle), and its k_sort_nms CTAs take
+// over SMs as the previous call's CTAs retire -- consecutive calls on one stream overlap on the device.  Everything is chained by
+// programmatic dependent launch; the hazards that stream order no longer covers are covered here:
+//   * k_detect_begin(s) runs while k_sort_nms(s - 1) may still be in flight (that kernel triggers at its start).  If NO call of
+//     this workspace is in flight (done == seq) whatever precedes us in the stream may be a foreign kernel, e.g. the producer of
+//     `conf`: full dependency wait.  If one is in flight it IS our predecessor (a foreign kernel launched after it would have
+//     waited for its completion, which publishes done == seq): nothing to wait for, the inputs were complete before it began.
+//   * slot reuse: wait until call s - R has completed (done >= s - R).
+//   * the same `out` / `counts` / `kept_prior` buffer as one of the calls still in flight: wait until done == s - 1.
+//   * completion in order: the last CTA of k_sort_nms(s) publishes done = s only after done == s - 1, so a kernel that waits for
+//     k_sort_nms(s) (normal stream order) also finds every earlier call complete.
+// seq, k3s and done are sequence numbers (wrapping uint32, compared by signed difference).
+//
+// Inside a call the three kernels depend on each other through FLAGS in the slot, not through griddepcontrol.wait: that
+// instruction waits for EVERY earlier grid of the stream (grids retire in order), i.e. also for the previous call's k_sort_nms --
+// measured with tools/pdl_probe.cu: with hardware waits a chain of calls runs strictly one after another, without them the
+// stream runs up to 8 grids ahead of its oldest incomplete one.  So: k_detect_begin publishes begin_seq = s once the slot's counters
+// are cleared, every K2 block waits for that before its first atomic and counts itself in k2_done when its keys are written
+// (fence + atomic), and every k_sort_nms CTA waits until k2_done has reached the number of K2 blocks.  A waiting grid was launched
+// after ALL blocks of the grid it waits for had started (programmatic launch completion), so the producers are resident and the
+// spins cannot deadlock.  Keys and counters written by another grid still in flight are read with ld.global.cg (L2).
+//
+// Slot header: int32 counters[3 * lists] | ticket | k2_done | begin_seq.
+constexpr unsigned long long FDT_CTL_MAGIC = 0x4644543262303031ull;      // "FDT2b001"
+constexpr int FDT_DETECT_MAX_DEPTH = 4;
+struct DetectCtl {
+    unsigned long long magic;          // FDT_CTL_MAGIC ^ geometry hash; anything else: first call on this memory
+    unsigned seq;                      // calls begun
+    unsigned k3s;                      // latest call whose k_sort_nms has started
+    unsigned done;                     // latest call whose k_sort_nms has completed (in order)
+    unsigned error;                    // sticky FDT_STATUS_* bits (a wait timed out)
+    unsigned check;                    // ~seq ^ (unsigned)magic: guards against foreign writes into a recycled buffer
+    unsigned pad;
+    unsigned long long outs[FDT_DETECT_MAX_DEPTH][3];      // out / counts / kept_prior of the last R calls
+};
+static_assert(sizeof(DetectCtl) <= 256, "control block is 256 bytes");
+struct DetectSlots {
+    DetectCtl *ctl;                    // null: no sequencing (fdt_nms), `base` is the only slot
+    char *base;                        // slot 0
+    size_t stride;                     // bytes per slot
+    size_t keys_off, kept_off;         // inside a slot: counters | keys | kept rows
+    int depth;                         // R
+};
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
 {
-    cudaGridDependencySynchronize();
-    cudaTriggerProgrammaticLaunchCompletion();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) counters[i] = 0;
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+constexpr int SLOT_TICKET = 0, SLOT_K2_DONE = 1, SLOT_BEGIN_SEQ = 2, SLOT_EXTRA = 4;     // after counters[3 * lists]
+// spins until (int)(*p - target) >= 0; false after ~4 s (a bug or a dead peer must not hang the GPU for ever)
+__device__ __forceinline__ bool spin_until_reached(const unsigned *p, const unsigned target)
+{
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_u32(p) - target) < 0) {
+        if (clock64() - t0 > (1ll << 33)) return false;
+        __nanosleep(64);
+    }
+    return true;
+}
+
+// First kernel of every call: sequencing (see above) + clears the call's per-list counters.  A kernel rather than
+// cudaMemsetAsync so that K2 can be launched behind it with programmatic stream serialization.
+__global__ void __launch_bounds__(256)
+k_detect_begin(const DetectSlots S, const unsigned long long magic, const int lists, const int serialize,
+               const unsigned long long out0, const unsigned long long out1, const unsigned long long out2)
+{
+    __shared__ unsigned s_slot, s_seqv;
+    DetectCtl *ctl = S.ctl;
+    if (threadIdx.x == 0) {
+        const int R = S.depth;
+        volatile DetectCtl *v = ctl;
+        unsigned seq = v->seq, k3s = v->k3s, done = ld_acquire_u32(&ctl->done);
+        bool fresh = v->magic != magic || v->check != (~seq ^ (unsigned)magic) || (int)(seq - done) < 0 || (int)(seq - done) > R ||
+                     (int)(seq - k3s) < 0 || (int)(k3s - done) < 0;
+        bool waited = false;
+        if (fresh || done == seq || serialize) {              // nothing of ours in flight: the predecessor may be anybody
+            cudaGridDependencySynchronize();
+            waited = true;
+        }
+        if (fresh) {
+            // sequence numbers start from an arbitrary value: a stale begin_seq / k2_done pair left in recycled memory cannot match
+            seq = k3s = done = (unsigned)(clock64() >> 3) * 2654435761u;
+            for (int q = 0; q < FDT_DETECT_MAX_DEPTH; ++q) { v->outs[q][0] = 0; v->outs[q][1] = 0; v->outs[q][2] = 0; }
+            v->error = 0; v->k3s = seq; v->done = seq;
+        } else {
+            if (k3s != seq) {
+                // the previous call never launched its k_sort_nms (stage 1 alone): it is void.  Its K2 is our predecessor.
+                if (!waited) { cudaGridDependencySynchronize(); waited = true; }
+                if (!spin_until_reached(&ctl->done, k3s)) { atomicOr(&ctl->error, FDT_STATUS_TIMEOUT_LOCAL); __trap(); }
+                v->k3s = seq; v->done = seq; done = seq;
+            }
+            // an output buffer of a call that may still be running is about to be written again: take turns
+            bool alias = serialize != 0;
+            for (int q = 1; q < R && !alias; ++q) {
+                if ((int)((seq + 1 - q) - done) <= 0) break;                  // call seq + 1 - q has completed
+                const int sl = (seq + 1 - q) % R;
+                alias = (out0 && v->outs[sl][0] == out0) || (out1 && v->outs[sl][1] == out1) || (out2 && v->outs[sl][2] == out2);
+            }
+            const unsigned need = alias ? seq : seq + 1 - (unsigned)R;        // slot reuse: call s - R has completed
+            if ((int)(done - need) < 0 && !spin_until_reached(&ctl->done, need)) { atomicOr(&ctl->error, FDT_STATUS_TIMEOUT_LOCAL); __trap(); }
+        }
+        seq += 1;
+        const int sl = seq % R;
+        v->outs[sl][0] = out0; v->outs[sl][1] = out1; v->outs[sl][2] = out2;
+        v->magic = magic; v->check = ~seq ^ (unsigned)magic;
+        v->seq = seq;
+        s_slot = (unsigned)sl; s_seqv = seq;
+        __threadfence();
+    }
+    __syncthreads();
+    cudaTriggerProgrammaticLaunchCompletion();           // K2 may be scheduled: its blocks wait for begin_seq below
+    int32_t *counters = reinterpret_cast<int32_t *>(S.base + (size_t)s_slot * S.stride);
+    for (int i = threadIdx.x; i < 3 * lists + SLOT_BEGIN_SEQ; i += blockDim.x) counters[i] = 0;       // counters, ticket, k2_done
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_u32(reinterpret_cast<unsigned *>(counters) + 3 * lists + SLOT_BEGIN_SEQ, s_seqv);
+}
+__device__ __forceinline__ bool spin_until_equal(const unsigned *p, const unsigned target)
+{
+    const long long t0 = clock64();
+    while (ld_acquire_u32(p) != target) {
+        if (clock64() - t0 > (1ll << 33)) return false;
+        __nanosleep(32);
+    }
+    return true;
+}
+// K2 side of the flags: wait until k_detect_begin has cleared this call's slot (thread 0; callers follow with a barrier), and count
+// the block in once its keys and counters are written
+__device__ __forceinline__ void k2_wait_slot_ready(const int32_t *counters, const int lists, const unsigned seq, DetectCtl *ctl)
+{
+    if (threadIdx.x == 0 && !spin_until_equal(reinterpret_cast<const unsigned *>(counters) + 3 * lists + SLOT_BEGIN_SEQ, seq)) {
+        atomicOr(&ctl->error, FDT_STATUS_TIMEOUT_LOCAL); __trap();
+    }
+}
+__device__ __forceinline__ void k2_block_done(int32_t *counters, const int lists)
+{
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(counters + 3 * lists + SLOT_K2_DONE, 1);
+}
+// slot of the call this kernel belongs to, read by every K2 / k_sort_nms CTA BEFORE it lets its dependents be scheduled: the
+// next call's k_detect_begin (which advances seq) cannot start until every CTA of this grid has triggered.
+__device__ __forceinline__ unsigned detect_call_seq(const DetectSlots &S, unsigned *s_seq)
+{
+    if (threadIdx.x == 0) *s_seq = *reinterpret_cast<volatile unsigned *>(&S.ctl->seq);
+    __syncthreads();
+    return *s_seq;
 }
 
 // K2 for head maps (fdt_detect_heads): max-in-out + softmax + threshold + compaction.  The exact softmax costs an fp64 exp,
@@ -144,11 +289,16 @@ constexpr int K2H_PER_THREAD = 9;
 constexpr int K2H_TILE = K2_THREADS * K2H_PER_THREAD;
 __global__ void __launch_bounds__(K2_THREADS, 7)
 k_heads_threshold_compact(const HeadLevels hl, const int64_t N, const float thr, const float dcut,
-                          int32_t *__restrict__ counters, uint64_t *__restrict__ keys, long long *prof)
+                          const DetectSlots S, long long *prof)
 {
     unsigned long long gt0 = 0;
     if (prof && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
+    __shared__ unsigned s_seq;
+    const unsigned my_seq = detect_call_seq(S, &s_seq);
+    char *slot = S.base + (size_t)(my_seq % (unsigned)S.depth) * S.stride;
     cudaTriggerProgrammaticLaunchCompletion();
+    int32_t *__restrict__ counters = reinterpret_cast<int32_t *>(slot);
+    uint64_t *__restrict__ keys = reinterpret_cast<uint64_t *>(slot + S.keys_off);
     const int b = blockIdx.y, lists = gridDim.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t base = (int64_t)blockIdx.x * K2H_TILE;
@@ -216,7 +366,7 @@ k_heads_threshold_compact(const HeadLevels hl, const int64_t N, const float thr,
     __syncthreads();                                                 // s_warp (screen offsets) is free again
     if (lane == 31) s_warp[warp] = inc;
     if (lane == 0) { s_wmax[warp] = kmx; s_wminv[warp] = kmnv; }
-    cudaGridDependencySynchronize();                                 // k_zero_counters has completed
+    k2_wait_slot_ready(counters, lists, my_seq, S.ctl);              // k_detect_begin has cleared the slot
     __syncthreads();
     if (tid == 0) {
         int tot = 0;
@@ -240,6 +390,7 @@ k_heads_threshold_compact(const HeadLevels hl, const int64_t N, const float thr,
             if (key) *kl++ = key;
         }
     }
+    k2_block_done(counters, lists);
     if (prof && threadIdx.x == 0) {
         unsigned long long gt1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
@@ -251,12 +402,10 @@ k_heads_threshold_compact(const HeadLevels hl, const int64_t N, const float thr,
 template <int SRC>
 __global__ void __launch_bounds__(K2_THREADS)
 k_threshold_compact(const float *__restrict__ conf, const HeadLevels hl, int64_t N, int C, float thr,
-                    int32_t *__restrict__ counters, uint64_t *__restrict__ keys, long long *prof)
+                    const DetectSlots S, long long *prof)
 {
     unsigned long long gt0 = 0;
     if (prof && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
-    // programmatic dependent launch: let k_sort_nms be scheduled while this grid drains (it waits for our completion itself)
-    cudaTriggerProgrammaticLaunchCompletion();
     const int b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t base = (int64_t)blockIdx.x * K2_TILE;
@@ -264,7 +413,11 @@ k_threshold_compact(const float *__restrict__ conf, const HeadLevels hl, int64_t
     __shared__ int s_warp[K2_THREADS / 32];
     __shared__ unsigned s_wmax[K2_THREADS / 32], s_wminv[K2_THREADS / 32];
     __shared__ int s_base;
+    __shared__ unsigned s_seq;
     const int lists = gridDim.y * (C - 1);
+    int32_t *__restrict__ counters = nullptr;
+    uint64_t *__restrict__ keys = nullptr;
+    unsigned my_seq = 0;
 
     for (int cl = 1; cl < C; ++cl) {
         float sc[K2_PER_THREAD];
@@ -272,15 +425,28 @@ k_threshold_compact(const float *__restrict__ conf, const HeadLevels hl, int64_t
         int wtotal = 0;
         unsigned kmx = 0u, kmnv = 0u;                    // max key and max ~key (= ~min key) of this thread's candidates
 #pragma unroll
-        for (int u = 0; u < K2_PER_THREAD; ++u) {
-            int64_t p = base + u * K2_THREADS + tid;
+        for (int u = 0; u < K2_PER_THREAD; ++u) {        // the tile's loads are in flight before anything below waits
+            const int64_t p = base + u * K2_THREADS + tid;
             float s = 0.0f;
-            bool in = p < N;
-            if (in) {
+            if (p < N) {
                 if (SRC == 1) s = __ldg(reinterpret_cast<const float2 *>(cb) + p).y;
                 else s = __ldg(cb + p * C + cl);
             }
             sc[u] = s;
+        }
+        if (cl == 1) {
+            my_seq = detect_call_seq(S, &s_seq);
+            char *slot = S.base + (size_t)(my_seq % (unsigned)S.depth) * S.stride;
+            counters = reinterpret_cast<int32_t *>(slot);
+            keys = reinterpret_cast<uint64_t *>(slot + S.keys_off);
+            // programmatic dependent launch: let k_sort_nms be scheduled while this grid drains (it waits for our completion itself)
+            cudaTriggerProgrammaticLaunchCompletion();
+        }
+#pragma unroll
+        for (int u = 0; u < K2_PER_THREAD; ++u) {
+            const int64_t p = base + u * K2_THREADS + tid;
+            const bool in = p < N;
+            const float s = sc[u];
             const bool cand = in && s > thr;                         // detection.py:64 strict gt
             bal[u] = __ballot_sync(0xffffffffu, cand);
             wtotal += __popc(bal[u]);
@@ -290,7 +456,7 @@ k_threshold_compact(const float *__restrict__ conf, const HeadLevels hl, int64_t
         }
         kmx = __reduce_max_sync(0xffffffffu, kmx); kmnv = __reduce_max_sync(0xffffffffu, kmnv);
         if (lane == 0) { s_warp[warp] = wtotal; s_wmax[warp] = kmx; s_wminv[warp] = kmnv; }
-        if (cl == 1) cudaGridDependencySynchronize();    // k_zero_counters has completed (the conf loads above were issued before the wait)
+        if (cl == 1) k2_wait_slot_ready(counters, lists, my_seq, S.ctl);    // k_detect_begin has cleared the slot (the conf loads were issued before the wait)
         __syncthreads();
         const int list = b * (C - 1) + (cl - 1);
         if (tid == 0) {
@@ -320,6 +486,7 @@ k_threshold_compact(const float *__restrict__ conf, const HeadLevels hl, int64_t
         }
         __syncthreads();
     }
+    k2_block_done(counters, lists);
     if (prof && threadIdx.x == 0) {      // diagnostics (FDT_K3_PROFILE=1): first block start / last block end on the global timer
         unsigned long long gt1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
@@ -360,8 +527,11 @@ struct SmemPlan {
 };
 
 struct SortNmsParams {
-    const uint64_t *keys;       // [lists, key_stride]
-    const int32_t *counters;    // [3][lists] (MODE_DETECT): candidate count, max key, ~min key
+    DetectSlots S;              // S.ctl != null: keys / counters / kept rows come from the call's workspace slot (sequenced calls)
+    const uint64_t *keys;       // [lists, key_stride]            (S.ctl == null)
+    const int32_t *counters;    // [3][lists] (MODE_DETECT): candidate count, max key, ~min key; null: P.n candidates   (S.ctl == null)
+    int use_counters;           // S.ctl != null: the slot's counters hold the candidate count
+    int k2_blocks;              // S.ctl != null: blocks of the call's K2 grid (k_sort_nms waits until all have counted themselves in)
     int64_t key_stride;
     const float *loc;           // [B,N,4]  (MODE_DETECT); null: gather the rows from the head maps `hl`
     const float *priors;        // [N,4]    (MODE_DETECT)
@@ -386,8 +556,9 @@ struct SortNmsParams {
     const unsigned long long *peer_sig;   // device array of `world` pointers to every rank's uint32 signal[world + 1] (or null)
     int world, my_rank, root;
     unsigned epoch;             // call counter, the same on every rank, >= 1
-    int *done_ctr;              // completion ticket (workspace)
-    float4 *g_kbox;             // kept arrays in global memory (per list stride max_keep) when sm.off_kbox < 0
+    int ring;                   // gathered blocks that alternate (epoch % ring)
+    int kept_global;            // kept arrays live in global memory (per list stride max_keep): sm.off_kbox < 0
+    float4 *g_kbox;             // (S.ctl == null; else carved from the slot)
     float *g_karea;
     uint64_t *g_kkey;
     SmemPlan sm;
@@ -638,10 +809,33 @@ template <int MODE, int CL>
 __global__ void __launch_bounds__(K3_THREADS, 1)
 k_sort_nms(const SortNmsParams P)
 {
-    // lets the counter clear / K2 of the NEXT Detect call be scheduled behind this grid (see k_zero_counters); they wait for this
-    // grid's completion before touching anything it reads or writes
-    cudaTriggerProgrammaticLaunchCompletion();
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned s_seq;
+    // Sequenced call: which call of the workspace this is (hence its slot) must be read before the trigger below lets the NEXT
+    // call's k_detect_begin be scheduled; block 0 also records that this call's k_sort_nms exists (see k_detect_begin).
+    unsigned my_seq = 0;
+    const uint64_t *keys_base = P.keys;
+    const int32_t *counters = P.counters;
+    int *ticket = nullptr;
+    char *slot_kept = nullptr;
+    if (P.S.ctl) {
+        my_seq = detect_call_seq(P.S, &s_seq);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { *reinterpret_cast<volatile unsigned *>(&P.S.ctl->k3s) = my_seq; __threadfence(); }
+        char *slot = P.S.base + (size_t)(my_seq % (unsigned)P.S.depth) * P.S.stride;
+        keys_base = reinterpret_cast<const uint64_t *>(slot + P.S.keys_off);
+        counters = P.use_counters ? reinterpret_cast<const int32_t *>(slot) : nullptr;
+        ticket = reinterpret_cast<int *>(slot) + 3 * (int)(gridDim.x / CL) + SLOT_TICKET;
+        slot_kept = slot + P.S.kept_off;
+        if (MODE == MODE_DETECT && P.peer_sig && blockIdx.x == 0 && (P.root < 0 || P.root == P.my_rank) &&
+            threadIdx.x < P.world && (int)threadIdx.x != P.my_rank) {
+            // destination of a fused gather: "call `epoch` has begun here" -> the blocks of epochs <= epoch - 1 have been consumed
+            unsigned *dst = reinterpret_cast<unsigned *>(P.peer_sig[threadIdx.x]) + P.world + P.my_rank;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(dst), "r"(P.epoch) : "memory");
+        }
+    }
+    // lets the NEXT Detect call's k_detect_begin / K2 be scheduled behind this grid: with a deep enough workspace ring they run
+    // while this grid is still in NMS (see "call sequencing")
+    cudaTriggerProgrammaticLaunchCompletion();
     uint64_t *skeys = reinterpret_cast<uint64_t *>(smem + SM_KEYS);
     int *s_hist = reinterpret_cast<int *>(smem + SM_HIST);
     int *s_start = s_hist + NB;
@@ -661,9 +855,19 @@ k_sort_nms(const SortNmsParams P)
     uint16_t *kcell = reinterpret_cast<uint16_t *>(smem + P.sm.off_kcell);       // [max_keep]
     const int list = blockIdx.x / CL;
     const int crank = CL == 2 ? (int)(blockIdx.x & 1) : 0;     // cluster dims (2,1,1): rank = blockIdx.x % 2
-    float4 *kbox = P.sm.off_kbox >= 0 ? reinterpret_cast<float4 *>(smem + P.sm.off_kbox) : P.g_kbox + (int64_t)list * P.max_keep;
-    float *karea = P.sm.off_karea >= 0 ? reinterpret_cast<float *>(smem + P.sm.off_karea) : P.g_karea + (int64_t)list * P.max_keep;
-    uint64_t *kkey = P.sm.off_kkey >= 0 ? reinterpret_cast<uint64_t *>(smem + P.sm.off_kkey) : P.g_kkey + (int64_t)list * P.max_keep;
+    float4 *kbox; float *karea; uint64_t *kkey;
+    if (P.sm.off_kbox >= 0) {
+        kbox = reinterpret_cast<float4 *>(smem + P.sm.off_kbox);
+        karea = reinterpret_cast<float *>(smem + P.sm.off_karea);
+        kkey = reinterpret_cast<uint64_t *>(smem + P.sm.off_kkey);
+    } else {
+        // kept rows in global memory: [lists][max_keep] boxes | keys | areas, carved from the slot (or passed by fdt_nms)
+        const size_t nl = gridDim.x / CL;
+        float4 *gb = slot_kept ? reinterpret_cast<float4 *>(slot_kept) : P.g_kbox;
+        uint64_t *gk = slot_kept ? reinterpret_cast<uint64_t *>(slot_kept + nl * (size_t)P.max_keep * 16) : P.g_kkey;
+        float *ga = slot_kept ? reinterpret_cast<float *>(slot_kept + nl * (size_t)P.max_keep * 24) : P.g_karea;
+        kbox = gb + (int64_t)list * P.max_keep; kkey = gk + (int64_t)list * P.max_keep; karea = ga + (int64_t)list * P.max_keep;
+    }
 
     __shared__ int s_sel[3];
     __shared__ int s_placed, s_maxb, s_next;
@@ -675,7 +879,7 @@ k_sort_nms(const SortNmsParams P)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = (MODE == MODE_DETECT) ? list / (P.C - 1) : 0;
     const int cl = (MODE == MODE_DETECT) ? 1 + list % (P.C - 1) : 0;
-    const uint64_t *gkeys = P.keys + (int64_t)list * P.key_stride;
+    const uint64_t *gkeys = keys_base + (int64_t)list * P.key_stride;
 
     // Output that does not depend on the producer kernel goes first: the all-zero background plane (detection.py:48, :63)
     // is written while k_threshold_compact still runs (programmatic dependent launch).
@@ -696,8 +900,20 @@ k_sort_nms(const SortNmsParams P)
         }
         if (P.counts && tid == 0) P.counts[b * P.C] = 0;
     }
-    cudaGridDependencySynchronize();      // no-op unless launched with programmatic stream serialization (after K2)
-    int n_c = (MODE == MODE_DETECT || P.counters) ? P.counters[list] : (int)P.n;
+    if (P.S.ctl) {
+        // K2 of this call has written the slot: every one of its blocks has counted itself in (see "call sequencing")
+        if (tid == 0) {
+            const unsigned *hdr = reinterpret_cast<const unsigned *>(ticket) - SLOT_TICKET;
+            // (begin_seq first: until k_detect_begin has cleared the slot, k2_done still holds what call seq - depth left there)
+            if (!spin_until_equal(hdr + SLOT_BEGIN_SEQ, my_seq) || !spin_until_reached(hdr + SLOT_K2_DONE, (unsigned)P.k2_blocks)) {
+                atomicOr(&P.S.ctl->error, FDT_STATUS_TIMEOUT_LOCAL); __trap();
+            }
+        }
+        __syncthreads();
+    } else {
+        cudaGridDependencySynchronize();  // fdt_nms: behind k_build_keys; a no-op unless launched with programmatic stream serialization
+    }
+    int n_c = counters ? __ldcg(counters + list) : (int)P.n;
     if (MODE == MODE_DETECT && n_c == 1) n_c = 0;            // detection.py:66-72: one candidate -> `continue`
     const int k = min(n_c, P.nms_top_k);                     // box_utils.py:299 idx[-top_k:]
     const bool prof = P.prof != nullptr && blockIdx.x == 0 && tid == 0;
@@ -724,14 +940,14 @@ k_sort_nms(const SortNmsParams P)
         uint64_t kreg[KREG];
         if (cached) {
 #pragma unroll
-            for (int u = 0; u < KREG; ++u) { const int i = tid + u * K3_THREADS; kreg[u] = i < n_c ? gkeys[i] : 0; }
+            for (int u = 0; u < KREG; ++u) { const int i = tid + u * K3_THREADS; kreg[u] = i < n_c ? __ldcg(gkeys + i) : 0; }
         }
         auto for_each_key = [&](auto &&body) {
             if (cached) {
 #pragma unroll
                 for (int u = 0; u < KREG; ++u) { if (tid + u * K3_THREADS < n_c) body(kreg[u]); }
             } else {
-                for (int i = tid; i < n_c; i += K3_THREADS) body(gkeys[i]);
+                for (int i = tid; i < n_c; i += K3_THREADS) body(__ldcg(gkeys + i));
             }
         };
         if (tid == 0) { s_kmin = 0xffffffffu; s_kmax = 0u; s_maxb = 0; }
@@ -740,8 +956,8 @@ k_sort_nms(const SortNmsParams P)
         unsigned kmax;
         if (MODE == MODE_DETECT) {          // k_threshold_compact already reduced the score range of the list
             const int lists = (int)(gridDim.x / CL);
-            kmax = (unsigned)P.counters[lists + list];
-            kmin = ~(unsigned)P.counters[2 * lists + list];
+            kmax = (unsigned)__ldcg(counters + lists + list);
+            kmin = ~(unsigned)__ldcg(counters + 2 * lists + list);
         } else {
             unsigned lo = 0xffffffffu, hi = 0u;
             for_each_key([&](uint64_t key) { unsigned k32 = (unsigned)(key >> 32); lo = min(lo, k32); hi = max(hi, k32); });
@@ -797,7 +1013,7 @@ k_sort_nms(const SortNmsParams P)
                     int i = base + tid;
                     int d = 256;
                     if (i < n_c) {
-                        uint64_t key = gkeys[i];
+                        uint64_t key = __ldcg(gkeys + i);
                         if ((key & pmask) == prefix) d = (int)((key >> shift) & 0xff);
                     }
                     unsigned peers = __match_any_sync(0xffffffffu, d);
@@ -1195,82 +1411,106 @@ k_sort_nms(const SortNmsParams P)
     // =========================================================== stage 3: outputs
     if (P.prof && tid == 0 && blockIdx.x < 256) { unsigned long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1)); atomicMin((unsigned long long *)&P.prof[40], gt0); atomicMax((unsigned long long *)&P.prof[41], gt0); atomicMin((unsigned long long *)&P.prof[42], gt1); atomicMax((unsigned long long *)&P.prof[43], gt1); P.prof[64 + blockIdx.x] = clock64() - cta_t0; P.prof[320 + blockIdx.x] = (long long)rounds * 100000 + k; }
     if (!writer) return;
-    if (MODE == MODE_DETECT && P.peer_sig && P.my_rank != P.root) {
-        // The rows go into the root's block of parity epoch % 2: the root must be done with what epoch - 2 left there.  Its
-        // k_sort_nms of epoch - 1 ran after that consumer (stream order) and acknowledged in this rank's slot [world].
-        if (tid == 0) {
-            const unsigned *ack = reinterpret_cast<const unsigned *>(P.peer_sig[P.my_rank]) + P.world;
+    const bool gather = MODE == MODE_DETECT && P.peer_sig != nullptr;
+    bool peer_ok = true;
+    if (gather) {
+        // Rows of epoch e go into block e % ring of every destination rank: that rank must be done with what epoch e - ring left
+        // there.  A destination acknowledges "call x has begun" (which, in its stream, follows the consumer of call x - 1) in
+        // slot [world + its rank] of every source's signal array at the start of its own k_sort_nms: wait for e - ring + 1.
+        bool bad = false;
+        if (tid < P.world && tid != P.my_rank && (P.root < 0 || tid == P.root)) {
+            const unsigned *ack = reinterpret_cast<const unsigned *>(P.peer_sig[P.my_rank]) + P.world + tid;
+            const unsigned need = P.epoch - (unsigned)P.ring + 1u;
             const long long t0 = clock64();
             unsigned v;
-            do {
+            for (;;) {
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ack) : "memory");
-            } while ((int)(v - (P.epoch - 1)) < 0 && clock64() - t0 < (1ll << 32));
+                if ((int)(v - need) >= 0) break;
+                if (clock64() - t0 > (1ll << 33)) { bad = true; break; }       // ~4 s: a dead peer must not hang the GPU
+                __nanosleep(200);
+            }
         }
-        __syncthreads();
+        peer_ok = !__syncthreads_or(bad);
+        if (!peer_ok && tid == 0) atomicOr(&P.S.ctl->error, FDT_STATUS_TIMEOUT_PEER);
     }
     if (MODE == MODE_DETECT) {
         const int top_k = P.top_k;
         const int cnt = min(nkept, top_k);                                   // detection.py:80
-        // rows go to the local output, or -- fused gather -- straight into every rank's gathered block over NVLink peer memory
+        // The plane [top_k, 5] is composed in shared memory (the phase-B segment queues are dead) and stored with 16-byte
+        // vector stores -- to the local output, a pinned host tensor, or (fused gather) the gathered blocks of the destination
+        // ranks over NVLink peer memory.  The staging buffer starts at the same 16-byte phase as the destination.
+        constexpr int CH = 1600;                                             // rows per chunk: 32,000 bytes
+        float *stage0 = reinterpret_cast<float *>(smem + SM_SEGS);
         const int ndst = P.n_peers > 0 ? P.n_peers : 1;
-        for (int pr = 0; pr < ndst; ++pr) {
-            float *base = P.n_peers > 0 ? reinterpret_cast<float *>(P.peer_out[pr]) + (P.img_offset * P.C) * (int64_t)top_k * 5 : P.out;
-            float *o = base + ((int64_t)(b * P.C + cl) * top_k) * 5;
-            for (int t = tid; t < top_k * 5; t += K3_THREADS) {
-                int r = t / 5, col = t - 5 * r;
-                float v = 0.0f;
-                if (r < cnt) {
-                    if (col == 0) v = fdt_key_float((uint32_t)(kkey[r] >> 32));
-                    else {
-                        const float4 bx = kbox[r];
-                        v = col == 1 ? bx.x : col == 2 ? bx.y : col == 3 ? bx.z : bx.w;
+        for (int r0 = 0; r0 < top_k && peer_ok; r0 += CH) {
+            const int nr = min(CH, top_k - r0), nf = nr * 5;
+            int staged_ph = -1;
+            for (int pr = 0; pr < ndst; ++pr) {
+                float *base = P.n_peers > 0 ? reinterpret_cast<float *>(P.peer_out[pr]) + (P.img_offset * P.C) * (int64_t)top_k * 5 : P.out;
+                float *o = base + ((int64_t)(b * P.C + cl) * top_k + r0) * 5;
+                const int ph = (int)(((uintptr_t)o >> 2) & 3);                // floats past a 16-byte boundary
+                float *stage = stage0 + ph;
+                if (ph != staged_ph) {                                       // (every destination block has the same alignment in practice)
+                    if (staged_ph >= 0) __syncthreads();
+                    staged_ph = ph;
+                    for (int r = tid; r < nr; r += K3_THREADS) {
+                        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f;
+                        if (r0 + r < cnt) {
+                            const float4 bx = kbox[r0 + r];
+                            v0 = fdt_key_float((uint32_t)(kkey[r0 + r] >> 32)); v1 = bx.x; v2 = bx.y; v3 = bx.z; v4 = bx.w;
+                        }
+                        float *d = stage + 5 * r;                            // stride 5 words: conflict-free
+                        d[0] = v0; d[1] = v1; d[2] = v2; d[3] = v3; d[4] = v4;       // detection.py:82
                     }
+                    __syncthreads();
                 }
-                o[t] = v;                                                    // detection.py:82
+                const int lead = min(nf, (4 - ph) & 3);                      // scalar floats up to the first 16-byte boundary
+                const int nq = (nf - lead) >> 2;
+                if (tid < lead) o[tid] = stage[tid];
+                const float4 *s4 = reinterpret_cast<const float4 *>(stage + lead);
+                float4 *o4 = reinterpret_cast<float4 *>(o + lead);
+                for (int t = tid; t < nq; t += K3_THREADS) o4[t] = s4[t];
+                const int tail0 = lead + 4 * nq;
+                if (tid < nf - tail0) o[tail0 + tid] = stage[tail0 + tid];
             }
+            if (r0 + CH < top_k) __syncthreads();
         }
         if (P.kept_prior) {
             int64_t *kp = P.kept_prior + (int64_t)(b * P.C + cl) * top_k;
             for (int r = tid; r < top_k; r += K3_THREADS) kp[r] = r < cnt ? (int64_t)(uint32_t)kkey[r] : -1;
         }
         if (P.counts && tid == 0) P.counts[b * P.C + cl] = cnt;
-        if (P.peer_sig) {
-            // Completion signal instead of a cross-rank barrier launch.  The last writer CTA of a non-root rank publishes `epoch`
-            // in slot [rank] of the ROOT's signal array and leaves; the root's last writer CTA waits until every slot shows
-            // `epoch` (all rows have landed in its block), then acknowledges in slot [world] of every rank.  Only the root waits.
-            __threadfence();        // device scope: ordered before this CTA's ticket; the signalling thread's system-scope fence
-            __syncthreads();        // below is cumulative over everything it has observed through the ticket chain
-            if (tid == 0) {
-                const int writers = (int)(gridDim.x / CL);
-                if (atomicAdd(P.done_ctr, 1) == writers - 1) {
-                    *P.done_ctr = 0;
-                    __threadfence_system();
-                    if (P.my_rank != P.root) {
-                        unsigned *dst = reinterpret_cast<unsigned *>(P.peer_sig[P.root]) + P.my_rank;
-                        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(dst), "r"(P.epoch) : "memory");
-                    } else {
-                        const unsigned *mine = reinterpret_cast<const unsigned *>(P.peer_sig[P.root]);
-                        const long long t0 = clock64();
-                        for (int q = 0; q < P.world; ++q) {
-                            if (q == P.root) continue;
-                            unsigned v;
-                            do {
-                                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + q) : "memory");
-                            } while ((int)(v - P.epoch) < 0 && clock64() - t0 < (1ll << 32));      // ~2 s: a dead peer must not hang the GPU
-                        }
-                        for (int q = 0; q < P.world; ++q) {
-                            if (q == P.root) continue;
-                            unsigned *dst = reinterpret_cast<unsigned *>(P.peer_sig[q]) + P.world;
-                            asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(dst), "r"(P.epoch) : "memory");
-                        }
-                    }
-                }
-            }
-        }
     } else {
         for (int64_t t = tid; t < P.n; t += K3_THREADS)
             P.keep[t] = t < nkept ? (int64_t)(uint32_t)kkey[t] : 0;           // box_utils.py:289 zero-initialised
         if (tid == 0) *P.count_out = nkept;
+    }
+    if (P.S.ctl) {
+        // Completion.  Every writer CTA takes a ticket after a device-scope fence; the last one
+        //   * (fused gather) publishes `epoch` in slot [rank] of every destination's signal array -- its system-scope fence is
+        //     cumulative over all rows it has observed through the ticket chain; nobody waits here, the destination's
+        //     k_gather_await does;
+        //   * publishes done = seq once the previous call has completed (in-order completion, see "call sequencing").
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const int writers = (int)(gridDim.x / CL);
+            if (atomicAdd(ticket, 1) == writers - 1) {
+                *ticket = 0;                                   // (a stage-2 launch may be repeated on the same slot)
+                DetectCtl *ctl = P.S.ctl;
+                if (gather) {
+                    __threadfence_system();
+                    const bool ok = *reinterpret_cast<volatile unsigned *>(&ctl->error) == 0;      // a timed-out wait: never signal
+                    for (int q = 0; q < P.world && ok; ++q) {
+                        if (q == P.my_rank || !(P.root < 0 || q == P.root)) continue;
+                        unsigned *dst = reinterpret_cast<unsigned *>(P.peer_sig[q]) + P.my_rank;
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(dst), "r"(P.epoch) : "memory");
+                    }
+                }
+                if (!spin_until_reached(&ctl->done, my_seq - 1u)) { atomicOr(&ctl->error, FDT_STATUS_TIMEOUT_LOCAL); __trap(); }
+                st_release_u32(&ctl->done, my_seq);
+            }
+        }
     }
     K3_STAMP(11);
 #undef K3_STAMP
@@ -1298,6 +1538,21 @@ SmemPlan plan_smem(int kcap, int max_keep, bool kept_in_smem)
 
 constexpr int K3_STATIC_SMEM = 2 * 1024;         // small arrays declared __shared__ in k_sort_nms
 
+// ---- process-wide options: read from the environment once, overridable through fdt_set_option (tests, tools)
+struct Options {
+    std::atomic<int> k3_profile, k3_cluster, k3_pdl, detect_depth;
+    Options()
+    {
+        auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e && *e ? atoi(e) : dflt; };
+        k3_profile = env_int("FDT_K3_PROFILE", 0);
+        k3_cluster = env_int("FDT_K3_CLUSTER", -1);          // -1: automatic
+        k3_pdl = env_int("FDT_K3_PDL", 1);
+        detect_depth = env_int("FDT_DETECT_DEPTH", FDT_DETECT_MAX_DEPTH);
+    }
+};
+static Options &options() { static Options o; return o; }
+
+static std::mutex g_prof_mutex;
 static long long *g_prof_dev = nullptr;
 static bool g_prof_armed = false;       // the producer launch already cleared the buffer (keeps K2 -> K3 adjacent in the stream)
 
@@ -1311,12 +1566,32 @@ static int prof_arm(cudaStream_t st)
     return FDT_OK;
 }
 
-// kept_ws: global memory for the kept arrays (28 bytes per kept row and list) used when they do not fit in shared memory
+// cudaFuncSetAttribute is per device and not free: remember what was set per (kernel, device)
+struct FuncAttrCache {
+    std::mutex m;
+    int smem[16] = {0};          // largest dynamic shared-memory size set so far, per device
+};
+template <typename K>
+static int ensure_dyn_smem(K kernel, FuncAttrCache &c, int bytes)
+{
+    int dev = 0;
+    FDT_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> g(c.m);
+    if (dev < 0 || dev >= 16 || c.smem[dev] < bytes) {
+        FDT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        if (dev >= 0 && dev < 16) c.smem[dev] = bytes;
+    }
+    return FDT_OK;
+}
+
+// `P.S.ctl == null` (fdt_nms): kept_ws = global memory for the kept arrays (28 bytes per kept row and list) used when they do not
+// fit in shared memory; sequenced calls carve them from the workspace slot (kept_ws_bytes = what a slot reserves for them).
 template <int MODE>
 int launch_sort_nms(SortNmsParams &P, int lists, int kcap, void *kept_ws, size_t kept_ws_bytes, cudaStream_t st)
 {
-    const char *env = getenv("FDT_K3_PROFILE");
-    if (env && env[0] == '1') {
+    Options &opt = options();
+    if (opt.k3_profile.load() == 1) {
+        std::lock_guard<std::mutex> g(g_prof_mutex);
         if (!g_prof_armed) { int rc = prof_arm(st); if (rc != FDT_OK) return rc; }
         g_prof_armed = false;
         P.prof = g_prof_dev;
@@ -1327,23 +1602,26 @@ int launch_sort_nms(SortNmsParams &P, int lists, int kcap, void *kept_ws, size_t
     if (sp.total > limit) {
         sp = plan_smem(kcap, P.max_keep, false);
         const size_t need = (size_t)lists * P.max_keep * KEPT_ROW_BYTES;
-        FDT_REQUIRE(kept_ws != nullptr && kept_ws_bytes >= need, FDT_E_WORKSPACE,
+        FDT_REQUIRE(kept_ws_bytes >= need && (kept_ws != nullptr || P.S.ctl != nullptr), FDT_E_WORKSPACE,
                     "kept rows (%d per list) do not fit in shared memory and the workspace lacks %zu bytes for them", P.max_keep, need);
-        char *p = (char *)kept_ws;
-        P.g_kbox = (float4 *)p; p += (size_t)lists * P.max_keep * 16;
-        P.g_kkey = (uint64_t *)p; p += (size_t)lists * P.max_keep * 8;
-        P.g_karea = (float *)p;
+        if (kept_ws) {
+            char *p = (char *)kept_ws;
+            P.g_kbox = (float4 *)p; p += (size_t)lists * P.max_keep * 16;
+            P.g_kkey = (uint64_t *)p; p += (size_t)lists * P.max_keep * 8;
+            P.g_karea = (float *)p;
+        }
     }
     FDT_REQUIRE(sp.total <= limit, FDT_E_UNSUPPORTED,
                 "nms_top_k=%d / max_keep=%d need %d bytes of shared memory (limit %d)", kcap, P.max_keep, sp.total, limit);
     P.sm = sp;
-    // Few lists (B = 64 leaves 84 of the 148 SMs idle): two CTAs per list as a thread-block cluster.  Kept rows in global
-    // memory (large max_keep) stay on the single-CTA path.
-    const char *env_cl = getenv("FDT_K3_CLUSTER");
-    const bool want_cluster = env_cl ? env_cl[0] == '1' : true;
-    const bool cluster = want_cluster && lists * 2 <= FDT_NUM_SMS && sp.off_kbox >= 0;
-    const char *env_pdl = getenv("FDT_K3_PDL");
-    const bool pdl = env_pdl ? env_pdl[0] == '1' : true;
+    // Two CTAs per list as a thread-block cluster (phase B split, dependency lists merged through DSMEM): shortens an isolated
+    // call when the batch leaves SMs idle.  Back-to-back calls overlap on the device (workspace ring), where total SM time
+    // counts: the cluster repeats every stage but phase B in both CTAs, so it is only used when the workspace has a single slot.
+    // Kept rows in global memory (large max_keep) stay on the single-CTA path.
+    const int want = opt.k3_cluster.load();
+    const bool fits = lists * 2 <= FDT_NUM_SMS && sp.off_kbox >= 0;
+    const bool cluster = fits && (want < 0 ? (P.S.ctl == nullptr || P.S.depth == 1) : want == 1);
+    const bool pdl = opt.k3_pdl.load() == 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(lists * (cluster ? 2 : 1))); cfg.blockDim = dim3(K3_THREADS);
     cfg.dynamicSmemBytes = (size_t)sp.total; cfg.stream = st;
@@ -1360,30 +1638,85 @@ int launch_sort_nms(SortNmsParams &P, int lists, int kcap, void *kept_ws, size_t
         ++na;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
+    static FuncAttrCache cache_cl, cache_1;
     if (cluster) {
-        FDT_CUDA(cudaFuncSetAttribute(k_sort_nms<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+        int rc = ensure_dyn_smem(k_sort_nms<MODE, 2>, cache_cl, sp.total); if (rc != FDT_OK) return rc;
         FDT_CUDA(cudaLaunchKernelEx(&cfg, k_sort_nms<MODE, 2>, P));
     } else {
-        FDT_CUDA(cudaFuncSetAttribute(k_sort_nms<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+        int rc = ensure_dyn_smem(k_sort_nms<MODE, 1>, cache_1, sp.total); if (rc != FDT_OK) return rc;
         FDT_CUDA(cudaLaunchKernelEx(&cfg, k_sort_nms<MODE, 1>, P));
     }
     FDT_LAUNCH_CHECK();
     return FDT_OK;
 }
 
+// Workspace of the Detect family: [control block 256 B][slot 0][slot 1] ... ; slot = int32 [3][lists] (candidate count, max key,
+// ~min key) + 1 completion ticket | uint64 keys[lists][N] | kept rows (only used when top_k rows exceed shared memory).
+struct DetectWsPlan {
+    size_t counters_bytes, keys_bytes, kept_bytes, slot_bytes;
+    int lists;
+};
+static DetectWsPlan detect_ws_plan(int B, int64_t N, int C)
+{
+    DetectWsPlan w;
+    w.lists = B * (C - 1);
+    const size_t lists = (size_t)w.lists;
+    const size_t kept_rows = (size_t)(N < FDT_MAX_NMS_TOP_K ? N : FDT_MAX_NMS_TOP_K);
+    w.counters_bytes = fdt_align256((3 * lists + SLOT_EXTRA) * sizeof(int32_t));
+    w.keys_bytes = fdt_align256(lists * (size_t)N * sizeof(uint64_t));
+    w.kept_bytes = fdt_align256(lists * kept_rows * KEPT_ROW_BYTES);
+    w.slot_bytes = w.counters_bytes + w.keys_bytes + w.kept_bytes;
+    return w;
+}
+static DetectSlots detect_slots(void *ws, size_t ws_bytes, const DetectWsPlan &w)
+{
+    DetectSlots S;
+    S.ctl = (DetectCtl *)ws;
+    S.base = (char *)ws + 256;
+    S.stride = w.slot_bytes;
+    S.keys_off = w.counters_bytes;
+    S.kept_off = w.counters_bytes + w.keys_bytes;
+    size_t fit = (ws_bytes - 256) / w.slot_bytes;
+    int cap = options().detect_depth.load();
+    if (cap < 1) cap = 1;
+    if (cap > FDT_DETECT_MAX_DEPTH) cap = FDT_DETECT_MAX_DEPTH;
+    S.depth = (int)(fit < (size_t)cap ? fit : (size_t)cap);
+    return S;
+}
+static int k2_grid_x(int64_t N, bool heads) { const int tile = heads ? K2H_TILE : K2_TILE; return (int)((N + tile - 1) / tile); }
+static unsigned long long detect_geometry_magic(int B, int64_t N, int C, int depth)
+{
+    unsigned long long h = 0x9e3779b97f4a7c15ull;
+    for (unsigned long long v : {(unsigned long long)B, (unsigned long long)N, (unsigned long long)C, (unsigned long long)depth}) {
+        h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+        h *= 0xff51afd7ed558ccdull;
+    }
+    return FDT_CTL_MAGIC ^ h;
+}
+
 }  // namespace
 
-// workspace head: int32 [3][lists] (candidate count, max key, ~min key) + 1 completion ticket (signalled peer-gather launches)
-static inline size_t detect_counter_bytes(size_t lists) { return fdt_align256((3 * lists + 1) * sizeof(int32_t)); }
-
 // =============================================================================================== C ABI
-FDT_API size_t fdt_detect_workspace_bytes(int B, int64_t N, int C)
+FDT_API size_t fdt_detect_workspace_bytes_depth(int B, int64_t N, int C, int depth)
 {
     if (B <= 0 || N <= 0 || C <= 1) return 256;
-    size_t lists = (size_t)B * (size_t)(C - 1);
-    size_t kept_rows = (size_t)(N < FDT_MAX_NMS_TOP_K ? N : FDT_MAX_NMS_TOP_K);       // only used when top_k rows exceed shared memory
-    return detect_counter_bytes(lists) + fdt_align256(lists * (size_t)N * sizeof(uint64_t)) +
-           fdt_align256(lists * kept_rows * KEPT_ROW_BYTES);
+    if (depth < 1) depth = 1;
+    if (depth > FDT_DETECT_MAX_DEPTH) depth = FDT_DETECT_MAX_DEPTH;
+    return 256 + (size_t)depth * detect_ws_plan(B, N, C).slot_bytes;
+}
+FDT_API size_t fdt_detect_workspace_bytes(int B, int64_t N, int C) { return fdt_detect_workspace_bytes_depth(B, N, C, 1); }
+
+FDT_API int fdt_set_option(const char *name, int value)
+{
+    FDT_REQUIRE(name != nullptr, FDT_E_INVALID, "fdt_set_option: null name");
+    Options &o = options();
+    const std::string n(name);
+    if (n == "k3_profile") o.k3_profile = value;
+    else if (n == "k3_cluster") o.k3_cluster = value;
+    else if (n == "k3_pdl") o.k3_pdl = value;
+    else if (n == "detect_depth") o.detect_depth = value;
+    else { fdt_set_error("fdt_set_option: unknown option '%s'", name); return FDT_E_INVALID; }
+    return FDT_OK;
 }
 
 static int detect_check_common(const char *who, int B, int64_t N, int C, const void *ws, size_t ws_bytes)
@@ -1397,8 +1730,11 @@ static int detect_check_common(const char *who, int B, int64_t N, int C, const v
     return FDT_OK;
 }
 
+// out0..2: the buffers the call's k_sort_nms will write (k_detect_begin serialises a call behind an in-flight one that shares
+// them); the stage entry point does not know them and serialises instead.
 static int threshold_compact_impl(const float *conf, const HeadLevels *heads, int B, int64_t N, int C, float conf_thresh,
-                                  void *ws, size_t ws_bytes, fdt_stream_t stream)
+                                  void *ws, size_t ws_bytes, fdt_stream_t stream,
+                                  const void *out0, const void *out1, const void *out2, int serialize)
 {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = detect_check_common("fdt_detect_threshold_compact", B, N, C, ws, ws_bytes);
@@ -1406,45 +1742,29 @@ static int threshold_compact_impl(const float *conf, const HeadLevels *heads, in
     const int lists = B * (C - 1);
     if (lists == 0 || N == 0) return FDT_OK;
     FDT_REQUIRE(heads || (conf && fdt_aligned(conf, 8)), FDT_E_INVALID, "fdt_detect_threshold_compact: conf null or not 8-byte aligned");
-    int32_t *counters = (int32_t *)ws;
-    uint64_t *keys = (uint64_t *)((char *)ws + detect_counter_bytes((size_t)lists));
+    const DetectWsPlan w = detect_ws_plan(B, N, C);
+    const DetectSlots S = detect_slots(ws, ws_bytes, w);
     long long *prof = nullptr;
-    {
-        const char *env = getenv("FDT_K3_PROFILE");
-        if (env && env[0] == '1') { int rc2 = prof_arm(st); if (rc2 != FDT_OK) return rc2; g_prof_armed = true; prof = g_prof_dev; }
+    if (options().k3_profile.load() == 1) {
+        std::lock_guard<std::mutex> g(g_prof_mutex);
+        int rc2 = prof_arm(st); if (rc2 != FDT_OK) return rc2;
+        g_prof_armed = true; prof = g_prof_dev;
     }
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
     {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)((3 * lists + 1 + 255) / 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.gridDim = dim3(1); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        FDT_CUDA(cudaLaunchKernelEx(&cfg, k_zero_counters, counters, 3 * lists + 1));
+        FDT_CUDA(cudaLaunchKernelEx(&cfg, k_detect_begin, S, detect_geometry_magic(B, N, C, S.depth), lists, serialize,
+                                    (unsigned long long)(uintptr_t)out0, (unsigned long long)(uintptr_t)out1, (unsigned long long)(uintptr_t)out2));
     }
     FDT_LAUNCH_CHECK();
-    dim3 g2((unsigned)((N + K2_TILE - 1) / K2_TILE), (unsigned)B);
-    {
-        // K3 needs the maximum shared-memory carveout; asking for the same split here avoids an SM reconfiguration
-        // (a pipeline drain) between the two kernels of every call
-        static bool carveout_set = false;
-        if (!carveout_set) {
-            const char *e = getenv("FDT_K2_CARVEOUT");
-            const int pct = e ? atoi(e) : 100;
-            if (pct >= 0) {
-                FDT_CUDA(cudaFuncSetAttribute(k_threshold_compact<0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-                FDT_CUDA(cudaFuncSetAttribute(k_threshold_compact<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-                FDT_CUDA(cudaFuncSetAttribute(k_heads_threshold_compact, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-            }
-            carveout_set = true;
-        }
-    }
     {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = g2; cfg.blockDim = dim3(K2_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.gridDim = dim3((unsigned)k2_grid_x(N, heads != nullptr), (unsigned)B);
+        cfg.blockDim = dim3(K2_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
         cfg.attrs = attr; cfg.numAttrs = 1;
         const int64_t N_ = N;
         HeadLevels hl{};
@@ -1454,11 +1774,10 @@ static int threshold_compact_impl(const float *conf, const HeadLevels *heads, in
             float dcut = -INFINITY;
             if (conf_thresh > 1e-4f && conf_thresh < 1.0f - 1e-4f) dcut = logf(conf_thresh / (1.0f - conf_thresh)) - 1e-3f;
             else if (conf_thresh >= 1.0f - 1e-4f) dcut = 9.0f;          // sigmoid(9) < 1 - 1e-4: nothing at or below can pass
-            cfg.gridDim = dim3((unsigned)((N + K2H_TILE - 1) / K2H_TILE), (unsigned)B);
-            FDT_CUDA(cudaLaunchKernelEx(&cfg, k_heads_threshold_compact, hl, N_, conf_thresh, dcut, counters, keys, prof));
+            FDT_CUDA(cudaLaunchKernelEx(&cfg, k_heads_threshold_compact, hl, N_, conf_thresh, dcut, S, prof));
         }
-        else if (C == 2) FDT_CUDA(cudaLaunchKernelEx(&cfg, k_threshold_compact<1>, conf, hl, N_, C, conf_thresh, counters, keys, prof));
-        else             FDT_CUDA(cudaLaunchKernelEx(&cfg, k_threshold_compact<0>, conf, hl, N_, C, conf_thresh, counters, keys, prof));
+        else if (C == 2) FDT_CUDA(cudaLaunchKernelEx(&cfg, k_threshold_compact<1>, conf, hl, N_, C, conf_thresh, S, prof));
+        else             FDT_CUDA(cudaLaunchKernelEx(&cfg, k_threshold_compact<0>, conf, hl, N_, C, conf_thresh, S, prof));
     }
     FDT_LAUNCH_CHECK();
     return FDT_OK;
@@ -1467,23 +1786,49 @@ static int threshold_compact_impl(const float *conf, const HeadLevels *heads, in
 FDT_API int fdt_detect_threshold_compact(const float *conf, int B, int64_t N, int C, float conf_thresh,
                                          void *ws, size_t ws_bytes, fdt_stream_t stream)
 {
-    return threshold_compact_impl(conf, nullptr, B, N, C, conf_thresh, ws, ws_bytes, stream);
+    return threshold_compact_impl(conf, nullptr, B, N, C, conf_thresh, ws, ws_bytes, stream, nullptr, nullptr, nullptr, 1);
 }
 
-FDT_API int fdt_detect_candidate_counts(const void *ws, int B, int C, int32_t *counts_out, fdt_stream_t stream)
+__global__ void k_copy_candidate_counts(const DetectSlots S, const int n, int32_t *__restrict__ out)
 {
-    FDT_REQUIRE(ws && counts_out && B >= 0 && C >= 1, FDT_E_INVALID, "fdt_detect_candidate_counts: bad arguments");
-    if (B * (C - 1) == 0) return FDT_OK;
-    FDT_CUDA(cudaMemcpyAsync(counts_out, ws, (size_t)B * (C - 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    const int32_t *c = reinterpret_cast<const int32_t *>(S.base + (size_t)(S.ctl->seq % (unsigned)S.depth) * S.stride);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = c[i];
+}
+
+FDT_API int fdt_detect_candidate_counts(const void *ws, size_t ws_bytes, int B, int64_t N, int C, int32_t *counts_out, fdt_stream_t stream)
+{
+    FDT_REQUIRE(ws && counts_out && B >= 0 && C >= 1 && N >= 0, FDT_E_INVALID, "fdt_detect_candidate_counts: bad arguments");
+    if (B * (C - 1) == 0 || N == 0) return FDT_OK;
+    int rc = detect_check_common("fdt_detect_candidate_counts", B, N, C, ws, ws_bytes);
+    if (rc != FDT_OK) return rc;
+    const DetectSlots S = detect_slots((void *)ws, ws_bytes, detect_ws_plan(B, N, C));
+    k_copy_candidate_counts<<<1, 256, 0, (cudaStream_t)stream>>>(S, B * (C - 1), counts_out);
+    FDT_LAUNCH_CHECK();
     return FDT_OK;
 }
+
+// Sticky status of a Detect workspace (FDT_STATUS_* bits; 0 = fine): synchronises `stream`.
+FDT_API int fdt_detect_status(const void *ws, fdt_stream_t stream, uint32_t *status_h)
+{
+    FDT_REQUIRE(ws && status_h, FDT_E_INVALID, "fdt_detect_status: null argument");
+    FDT_CUDA(cudaMemcpyAsync(status_h, &((const DetectCtl *)ws)->error, sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    FDT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return FDT_OK;
+}
+
+struct GatherArgs {
+    const unsigned long long *dest_out = nullptr;     // device array of n_dest destination block pointers
+    int n_dest = 0;
+    int64_t img_offset = 0;
+    const unsigned long long *peer_sig = nullptr;
+    int world = 0, rank = 0, root = 0, ring = 2;
+    unsigned epoch = 0;
+};
 
 static int detect_sort_nms_impl(const float *loc, const HeadLevels *heads, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
                                 float nms_thresh, float var0, float var1,
                                 float *out, int32_t *counts, int64_t *kept_prior,
-                                const unsigned long long *peer_out, int n_peers, int64_t img_offset,
-                                void *ws, size_t ws_bytes, fdt_stream_t stream,
-                                const unsigned long long *peer_sig = nullptr, int world = 0, int my_rank = 0, int root = 0, unsigned epoch = 0)
+                                const GatherArgs &G, void *ws, size_t ws_bytes, fdt_stream_t stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = detect_check_common("fdt_detect_sort_nms", B, N, C, ws, ws_bytes);
@@ -1493,6 +1838,7 @@ static int detect_sort_nms_impl(const float *loc, const HeadLevels *heads, const
                 "fdt_detect: nms_top_k=%d outside [1,%d]", nms_top_k, FDT_MAX_NMS_TOP_K);
     FDT_REQUIRE(nms_thresh > 0.0f, FDT_E_INVALID, "fdt_detect: nms_thresh must be > 0 (detection.py:28-29)");
     if (B == 0) return FDT_OK;
+    const int n_peers = G.n_dest;
     FDT_REQUIRE(out != nullptr || n_peers > 0, FDT_E_INVALID, "fdt_detect: out is null");
     const int lists = B * (C - 1);
     if (lists == 0 || N == 0) {
@@ -1504,22 +1850,19 @@ static int detect_sort_nms_impl(const float *loc, const HeadLevels *heads, const
     }
     FDT_REQUIRE((heads || (loc && fdt_aligned(loc, 16))) && priors && fdt_aligned(priors, 16), FDT_E_INVALID,
                 "fdt_detect: loc/priors null or not 16-byte aligned");
-    int32_t *counters = (int32_t *)ws;
-    uint64_t *keys = (uint64_t *)((char *)ws + detect_counter_bytes((size_t)lists));
+    const DetectWsPlan w = detect_ws_plan(B, N, C);
     SortNmsParams P{};
-    P.keys = keys; P.counters = counters; P.key_stride = N;
+    P.S = detect_slots(ws, ws_bytes, w); P.use_counters = 1; P.key_stride = N; P.k2_blocks = k2_grid_x(N, heads != nullptr) * B;
     P.loc = heads ? nullptr : loc; P.priors = priors; P.N = N; P.C = C;
     if (heads) P.hl = *heads;
     P.nms_top_k = nms_top_k; P.max_keep = top_k < nms_top_k ? top_k : nms_top_k; P.top_k = top_k;
     P.nms_thresh = nms_thresh; P.v0 = var0; P.v1 = var1;
     P.out = out; P.counts = counts; P.kept_prior = kept_prior;
-    P.peer_out = peer_out; P.n_peers = n_peers; P.img_offset = img_offset;
-    P.peer_sig = peer_sig; P.world = world; P.my_rank = my_rank; P.root = root; P.epoch = epoch; P.done_ctr = counters + 3 * lists;
+    P.peer_out = G.dest_out; P.n_peers = n_peers; P.img_offset = G.img_offset;
+    P.peer_sig = G.peer_sig; P.world = G.world; P.my_rank = G.rank; P.root = G.root; P.epoch = G.epoch; P.ring = G.ring;
     int kcap = (int)((int64_t)nms_top_k < N ? nms_top_k : N);
     if (P.max_keep > kcap) P.max_keep = kcap;
-    char *kept_ws = (char *)keys + fdt_align256((size_t)lists * (size_t)N * sizeof(uint64_t));
-    size_t kept_rows = (size_t)(N < FDT_MAX_NMS_TOP_K ? N : FDT_MAX_NMS_TOP_K);
-    return launch_sort_nms<MODE_DETECT>(P, lists, kcap, kept_ws, fdt_align256((size_t)lists * kept_rows * KEPT_ROW_BYTES), st);
+    return launch_sort_nms<MODE_DETECT>(P, lists, kcap, nullptr, w.kept_bytes, st);
 }
 
 FDT_API int fdt_detect_sort_nms(const float *loc, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
@@ -1528,29 +1871,80 @@ FDT_API int fdt_detect_sort_nms(const float *loc, const float *priors, int B, in
                                 void *ws, size_t ws_bytes, fdt_stream_t stream)
 {
     return detect_sort_nms_impl(loc, nullptr, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1, out, counts, kept_prior,
-                                nullptr, 0, 0, ws, ws_bytes, stream);
+                                GatherArgs{}, ws, ws_bytes, stream);
 }
 
-FDT_API int fdt_detect_sort_nms_peers(const float *loc, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
-                                      float nms_thresh, float var0, float var1,
-                                      const uint64_t *peer_out_ptrs, int n_peers, int64_t image_offset,
-                                      void *ws, size_t ws_bytes, fdt_stream_t stream)
+// Destination side of the signalled gather: ends when every source rank has published `epoch` (its rows of that call have landed in
+// this rank's block) and this rank's own k_sort_nms of the call has completed.  Launched behind that kernel with programmatic
+// serialization and triggering at once, so the NEXT call is not held back; whatever consumes the gathered block follows it in
+// stream order.  A source that does not show up within ~4 s sets FDT_STATUS_TIMEOUT_PEER in the workspace status.
+__global__ void k_gather_await(const unsigned long long *peer_sig, const int world, const int my_rank, const unsigned epoch, DetectCtl *ctl)
 {
-    FDT_REQUIRE(peer_out_ptrs != nullptr && n_peers >= 1 && image_offset >= 0, FDT_E_INVALID, "fdt_detect_sort_nms_peers: bad peer arguments");
-    return detect_sort_nms_impl(loc, nullptr, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1, nullptr, nullptr, nullptr,
-                                (const unsigned long long *)peer_out_ptrs, n_peers, image_offset, ws, ws_bytes, stream);
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
+    const int q = threadIdx.x;
+    if (q < world && q != my_rank) {
+        const unsigned *mine = reinterpret_cast<const unsigned *>(peer_sig[my_rank]) + q;
+        const long long t0 = clock64();
+        unsigned v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if ((int)(v - epoch) >= 0) break;
+            if (clock64() - t0 > (1ll << 33)) { atomicOr(&ctl->error, FDT_STATUS_TIMEOUT_PEER); break; }
+            __nanosleep(200);
+        }
+    }
 }
 
-FDT_API int fdt_detect_sort_nms_gather_signal(const float *loc, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
-                                              float nms_thresh, float var0, float var1,
-                                              const uint64_t *root_out_ptr, const uint64_t *peer_signal_ptrs, int world, int rank, int root,
-                                              uint32_t epoch, int64_t image_offset, void *ws, size_t ws_bytes, fdt_stream_t stream)
+FDT_API int fdt_detect_gather_await(const uint64_t *peer_signal_ptrs, int world, int rank, uint32_t epoch, void *ws, fdt_stream_t stream)
 {
-    FDT_REQUIRE(root_out_ptr && peer_signal_ptrs && world >= 1 && rank >= 0 && rank < world && root >= 0 && root < world &&
-                image_offset >= 0 && epoch >= 1, FDT_E_INVALID, "fdt_detect_sort_nms_gather_signal: bad arguments");
+    FDT_REQUIRE(peer_signal_ptrs && ws && world >= 1 && world <= 1024 && rank >= 0 && rank < world && epoch >= 1, FDT_E_INVALID,
+                "fdt_detect_gather_await: bad arguments");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3((unsigned)((world + 31) / 32 * 32)); cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    FDT_CUDA(cudaLaunchKernelEx(&cfg, k_gather_await, (const unsigned long long *)peer_signal_ptrs, world, rank, (unsigned)epoch, (DetectCtl *)ws));
+    FDT_LAUNCH_CHECK();
+    return FDT_OK;
+}
+
+FDT_API int fdt_detect_peers(const float *loc, const float *conf, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
+                             float conf_thresh, float nms_thresh, float var0, float var1,
+                             const uint64_t *peer_out_ptrs, int n_peers, int64_t image_offset,
+                             void *ws, size_t ws_bytes, fdt_stream_t stream)
+{
+    FDT_REQUIRE(peer_out_ptrs != nullptr && n_peers >= 1 && image_offset >= 0, FDT_E_INVALID, "fdt_detect_peers: bad peer arguments");
+    GatherArgs G;
+    G.dest_out = (const unsigned long long *)peer_out_ptrs; G.n_dest = n_peers; G.img_offset = image_offset;
+    int rc = threshold_compact_impl(conf, nullptr, B, N, C, conf_thresh, ws, ws_bytes, stream, peer_out_ptrs, nullptr, nullptr, 0);
+    if (rc != FDT_OK) return rc;
     return detect_sort_nms_impl(loc, nullptr, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1, nullptr, nullptr, nullptr,
-                                (const unsigned long long *)root_out_ptr, 1, image_offset, ws, ws_bytes, stream,
-                                (const unsigned long long *)peer_signal_ptrs, world, rank, root, epoch);
+                                G, ws, ws_bytes, stream);
+}
+
+FDT_API int fdt_detect_gather_signal(const float *loc, const float *conf, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
+                                     float conf_thresh, float nms_thresh, float var0, float var1,
+                                     const uint64_t *dest_out_ptrs, int n_dest, const uint64_t *peer_signal_ptrs,
+                                     int world, int rank, int root, uint32_t epoch, int ring, int64_t image_offset,
+                                     void *ws, size_t ws_bytes, fdt_stream_t stream)
+{
+    FDT_REQUIRE(dest_out_ptrs && peer_signal_ptrs && world >= 1 && world <= K3_THREADS && rank >= 0 && rank < world && root >= -1 && root < world &&
+                image_offset >= 0 && epoch >= 1 && ring >= 1 && (root >= 0 ? n_dest == 1 : n_dest == world), FDT_E_INVALID,
+                "fdt_detect_gather_signal: bad arguments");
+    FDT_REQUIRE(B > 0 && N > 0 && C >= 2, FDT_E_UNSUPPORTED, "fdt_detect_gather_signal: needs B > 0, N > 0, C >= 2");
+    GatherArgs G;
+    G.dest_out = (const unsigned long long *)dest_out_ptrs; G.n_dest = n_dest; G.img_offset = image_offset;
+    G.peer_sig = (const unsigned long long *)peer_signal_ptrs; G.world = world; G.rank = rank; G.root = root; G.epoch = epoch; G.ring = ring;
+    int rc = threshold_compact_impl(conf, nullptr, B, N, C, conf_thresh, ws, ws_bytes, stream, dest_out_ptrs, nullptr, nullptr, 0);
+    if (rc != FDT_OK) return rc;
+    rc = detect_sort_nms_impl(loc, nullptr, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1, nullptr, nullptr, nullptr,
+                              G, ws, ws_bytes, stream);
+    if (rc != FDT_OK) return rc;
+    if (root < 0 || root == rank) return fdt_detect_gather_await(peer_signal_ptrs, world, rank, epoch, ws, stream);
+    return FDT_OK;
 }
 
 FDT_API int fdt_detect(const float *loc, const float *conf, const float *priors,
@@ -1559,7 +1953,7 @@ FDT_API int fdt_detect(const float *loc, const float *conf, const float *priors,
                        float *out, int32_t *counts, int64_t *kept_prior,
                        void *ws, size_t ws_bytes, fdt_stream_t stream)
 {
-    int rc = fdt_detect_threshold_compact(conf, B, N, C, conf_thresh, ws, ws_bytes, stream);
+    int rc = threshold_compact_impl(conf, nullptr, B, N, C, conf_thresh, ws, ws_bytes, stream, out, counts, kept_prior, 0);
     if (rc != FDT_OK) return rc;
     return fdt_detect_sort_nms(loc, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1,
                                out, counts, kept_prior, ws, ws_bytes, stream);
@@ -1623,10 +2017,10 @@ FDT_API int fdt_detect_heads(const float *const *loc_maps_h, const float *const 
     FDT_REQUIRE(loc_maps_h && conf_maps_h, FDT_E_INVALID, "fdt_detect_heads: null map arrays");
     for (int l = 0; l < n_levels; ++l)
         FDT_REQUIRE(hl.loc[l] && hl.conf[l], FDT_E_INVALID, "fdt_detect_heads: map %d is null", l);
-    rc = threshold_compact_impl(nullptr, &hl, B, N, 2, conf_thresh, ws, ws_bytes, stream);
+    rc = threshold_compact_impl(nullptr, &hl, B, N, 2, conf_thresh, ws, ws_bytes, stream, out, counts, kept_prior, 0);
     if (rc != FDT_OK) return rc;
     return detect_sort_nms_impl(nullptr, &hl, priors, B, N, 2, top_k, nms_top_k, nms_thresh, var0, var1, out, counts, kept_prior,
-                                nullptr, 0, 0, ws, ws_bytes, stream);
+                                GatherArgs{}, ws, ws_bytes, stream);
 }
 
 // Diagnostics: with FDT_K3_PROFILE=1 in the environment, CTA 0 of k_sort_nms records clock64 deltas per phase:
@@ -1717,9 +2111,10 @@ FDT_API int fdt_facebox_decode(const float *loc, const float *default_boxes, int
 // K2 compacts the candidates, k_sort_nms reads the count on the device.  keep[N] = table indices in keep order.
 FDT_API size_t fdt_threshold_nms_workspace_bytes(int64_t N) { return fdt_detect_workspace_bytes(1, N, 2); }
 
-__global__ void k_threshold_nms_guard(const int32_t *counters, int64_t *keep, int64_t *count, int64_t N, int limit)
+__global__ void k_threshold_nms_guard(const DetectSlots S, int64_t *keep, int64_t *count, int64_t N, int limit)
 {
     // more candidates than NMS admits: k_sort_nms would silently keep only the `limit` best (idx[-top_k:] semantics)
+    const int32_t *counters = reinterpret_cast<const int32_t *>(S.base + (size_t)(S.ctl->seq % (unsigned)S.depth) * S.stride);
     if (counters[0] <= limit) return;
     for (int64_t i = threadIdx.x; i < N; i += blockDim.x) keep[i] = 0;
     if (threadIdx.x == 0) *count = -1;
@@ -1733,19 +2128,17 @@ FDT_API int fdt_threshold_nms(const float *boxes, const float *conf, int64_t N, 
     FDT_REQUIRE(N >= 0 && N < (1ll << 31) && count != nullptr, FDT_E_INVALID, "fdt_threshold_nms: bad arguments");
     if (N == 0) { FDT_CUDA(cudaMemsetAsync(count, 0, sizeof(int64_t), st)); return FDT_OK; }
     FDT_REQUIRE(boxes && conf && keep && fdt_aligned(boxes, 16), FDT_E_INVALID, "fdt_threshold_nms: null or misaligned pointer");
-    int rc = threshold_compact_impl(conf, nullptr, 1, N, 2, conf_thresh, ws, ws_bytes, stream);
+    int rc = threshold_compact_impl(conf, nullptr, 1, N, 2, conf_thresh, ws, ws_bytes, stream, keep, count, nullptr, 0);
     if (rc != FDT_OK) return rc;
-    int32_t *counters = (int32_t *)ws;
-    uint64_t *keys = (uint64_t *)((char *)ws + detect_counter_bytes(1));
+    const DetectWsPlan w = detect_ws_plan(1, N, 2);
     const int kcap = (int)(N < FDT_MAX_NMS_TOP_K ? N : FDT_MAX_NMS_TOP_K);
     SortNmsParams P{};
-    P.keys = keys; P.counters = counters; P.key_stride = N; P.boxes = boxes; P.n = N; P.N = N; P.C = 2;
+    P.S = detect_slots(ws, ws_bytes, w); P.use_counters = 1; P.k2_blocks = k2_grid_x(N, false); P.key_stride = N; P.boxes = boxes; P.n = N; P.N = N; P.C = 2;
     P.nms_top_k = kcap; P.max_keep = kcap; P.nms_thresh = nms_thresh; P.variant = variant;
     P.keep = keep; P.count_out = count;
-    char *kept_ws = (char *)keys + fdt_align256((size_t)N * sizeof(uint64_t));
-    rc = launch_sort_nms<MODE_NMS>(P, 1, kcap, kept_ws, fdt_align256((size_t)kcap * KEPT_ROW_BYTES), st);
+    rc = launch_sort_nms<MODE_NMS>(P, 1, kcap, nullptr, w.kept_bytes, st);
     if (rc != FDT_OK) return rc;
-    k_threshold_nms_guard<<<1, 256, 0, st>>>(counters, keep, count, N, kcap);
+    k_threshold_nms_guard<<<1, 256, 0, st>>>(P.S, keep, count, N, kcap);
     FDT_LAUNCH_CHECK();
     return FDT_OK;
 }

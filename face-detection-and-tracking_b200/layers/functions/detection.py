@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
+import weakref
 
 import torch
 
@@ -21,6 +22,8 @@ def _ctx(device_index: int):
         h = C.c_void_p()
         _lib.check(_lib.lib().fdt_ctx_create(device_index, C.byref(h)))
         d[device_index] = h
+        f = weakref.finalize(threading.current_thread(), _lib.lib().fdt_ctx_destroy, h)  # freed when the owning thread goes away
+        f.atexit = False                                                                 # (not at interpreter exit: CUDA may be gone)
     return d[device_index]
 
 
@@ -29,6 +32,8 @@ class Detect:
 
     Same constructor, attributes and call signature as the reference.  CUDA inputs are processed in
     place on the current stream (asynchronous, CUDA-graph capturable) and the result is a CUDA tensor;
+    consecutive calls on one stream overlap on the device (the instance owns a ring of scratch slots per
+    stream and shape; completion stays in stream order, see fdt_detect in include/fdt_b200.h);
     CPU inputs go through fdt_detect_host (H2D copy, kernels, D2H copy) and the result is a CPU tensor,
     like the reference's torch.zeros(...) output on a CPU default device (detection.py:48).
     """
@@ -43,6 +48,7 @@ class Detect:
         self.conf_thresh = conf_thresh
         self.variance = cfg['variance']
         self.nms_top_k = 5000                                            # detection.py:32
+        self._workspaces = _lib.DetectWorkspaces()                       # stateful scratch, one per (device, stream, shape)
 
     def __call__(self, loc_data, conf_data, prior_data, return_aux=False):
         """loc_data [B,N,4] (or [B,N*4]), conf_data [B,N,C] (or [B*N,C]) post-softmax, prior_data [N,4]
@@ -65,8 +71,7 @@ class Detect:
             counts = torch.empty((num, C_), dtype=torch.int32, device=dev) if return_aux else None
             kept = torch.empty((num, C_, self.top_k), dtype=torch.int64, device=dev) if return_aux else None
             L = _lib.lib()
-            nbytes = L.fdt_detect_workspace_bytes(num, num_priors, C_)
-            ws = _lib.workspace(nbytes, dev, "detect")
+            ws = self._workspaces.get(num, num_priors, C_, dev)
             _lib.check(L.fdt_detect(_lib.ptr(loc), _lib.ptr(conf), _lib.ptr(pri), *args, _lib.ptr(out),
                                     _lib.ptr(counts), _lib.ptr(kept), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
         return (out, counts, kept) if return_aux else out
@@ -89,7 +94,7 @@ class Detect:
             counts = torch.empty((num, 2), dtype=torch.int32, device=dev) if return_aux else None
             kept = torch.empty((num, 2, self.top_k), dtype=torch.int64, device=dev) if return_aux else None
             Lb = _lib.lib()
-            ws = _lib.workspace(Lb.fdt_detect_workspace_bytes(num, num_priors, 2), dev, "detect")
+            ws = self._workspaces.get(num, num_priors, 2, dev)
             _lib.check(Lb.fdt_detect_heads(lp, cp, fh, fw, nm, L, _lib.ptr(pri), num, int(self.top_k), int(self.nms_top_k),
                                            float(self.conf_thresh), float(self.nms_thresh), float(self.variance[0]),
                                            float(self.variance[1]), _lib.ptr(out), _lib.ptr(counts), _lib.ptr(kept),

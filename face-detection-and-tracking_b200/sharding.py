@@ -62,21 +62,25 @@ class ShardedDetect:
         self.detect, self.group, self.gather = detect, group, gather
 
     def __call__(self, loc_local, conf_local, priors):
-        out = self.detect(loc_local, conf_local, priors)
         rank, world = _world(self.group)
-        if world == 1:
-            return out
-        if self.gather == "block":
-            return all_gather_ragged(out, self.group)
+        if world == 1 or self.gather == "block":
+            out = self.detect(loc_local, conf_local, priors)
+            return out if world == 1 else all_gather_ragged(out, self.group)
+        # packed: the kernel's own row counts (rows are contiguous from 0 in every plane) -- no assumption about the sign of the
+        # scores, no extra pass over the block
+        try:
+            out, counts, _ = self.detect(loc_local, conf_local, priors, return_aux=True)
+        except TypeError:                            # a Detect-like callable without aux outputs: count the leading non-zero rows
+            out = self.detect(loc_local, conf_local, priors)
+            counts = (out != 0).any(-1).sum(-1).to(torch.int32)
         B, C, K, _ = out.shape
-        valid = out[..., 0] > 0                      # rows are written in keep order, scores > conf_thresh >= 0
-        counts = valid.sum(-1).to(torch.int32)       # [B, C]
-        rows = out[valid]                            # [sum counts, 5] in (image, class, rank) order
+        idx = torch.arange(K, device=out.device).expand(B, C, K) < counts.unsqueeze(-1)
+        rows = out[idx]                              # [sum counts, 5] in (image, class, rank) order
         counts_all = all_gather_ragged(counts, self.group)
         rows_all = all_gather_ragged(rows, self.group)
         full = torch.zeros((counts_all.shape[0], C, K, 5), dtype=out.dtype, device=out.device)
-        idx = torch.arange(K, device=out.device).expand(counts_all.shape[0], C, K) < counts_all.unsqueeze(-1)
-        full[idx] = rows_all
+        idx_all = torch.arange(K, device=out.device).expand(counts_all.shape[0], C, K) < counts_all.unsqueeze(-1)
+        full[idx_all] = rows_all
         return full
 
 
@@ -105,21 +109,23 @@ def sharded_multibox_loss(criterion, predictions_local, targets_local, group=Non
 
 class PeerGatherDetect:
     """Detect with the gather FUSED into the NMS kernel: k_sort_nms stores the detection rows of this rank's images straight
-    into every rank's gathered block [world * B_local, C, top_k, 5] over NVLink peer memory (torch symmetric memory provides
-    the peer pointers and the cross-rank barrier); no NCCL collective is launched.  Two blocks alternate between calls so a
+    into the destination ranks' gathered block [world * B_local, C, top_k, 5] over NVLink peer memory with 16-byte vector stores
+    (torch symmetric memory provides the peer pointers); no NCCL collective is launched.  RING blocks alternate between calls so a
     rank that runs ahead never overwrites rows a slower peer is still reading.  The returned tensor is this rank's copy of the
-    gathered block and stays valid until the call after next."""
+    gathered block and stays valid until RING - 1 further calls have been made."""
+
+    RING = 4
 
     def __init__(self, detect, b_local, group=None, dest="all", signal="barrier"):
         """dest="all": every rank ends up with the whole gathered block (all-gather).  dest=<rank>: only that rank does (gather
-        to a root): each rank's rows cross NVLink once instead of world - 1 times, so the step no longer grows with the number
-        of ranks; only the root's returned block is meaningful.
-        signal="barrier": a symmetric-memory barrier follows the kernel (works for both, CUDA-graph capturable).
-        signal="kernel" (needs dest=<rank>): the NMS kernel publishes / awaits the completion signals itself -- the non-root
-        ranks never wait, the root's kernel ends when all rows have landed (fdt_detect_sort_nms_gather_signal)."""
+        to a root): each rank's rows cross NVLink once instead of world - 1 times; only the root's returned block is meaningful.
+        signal="barrier": a symmetric-memory barrier follows the kernel (CUDA-graph capturable).
+        signal="kernel": the completion signals travel through symmetric memory inside the call (fdt_detect_gather_signal): a source
+        rank never waits for anybody (except for a destination that is RING calls behind), a destination enqueues a one-block
+        await kernel behind its own NMS kernel -- consumers of the block follow it in stream order, the next call does not."""
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
-        assert signal in ("barrier", "kernel") and (signal == "barrier" or dest != "all")
+        assert signal in ("barrier", "kernel")
         self.dest, self.signal = dest, signal
         self._lib = _lib
         self.detect = detect
@@ -129,7 +135,7 @@ class PeerGatherDetect:
         dev = torch.device("cuda", torch.cuda.current_device())
         shape = (self.world * self.b_local, detect.num_classes, detect.top_k, 5)
         self.bufs, self.hdls = [], []
-        for _ in range(2):
+        for _ in range(self.RING):
             t = symm_mem.empty(shape, dtype=torch.float32, device=dev)
             t.zero_()                       # the kernel never writes the background planes: zero once, zero forever
             self.hdls.append(symm_mem.rendezvous(t, self.group))
@@ -137,9 +143,10 @@ class PeerGatherDetect:
         self.sig = self.sig_hdl = None
         self.epoch = 0
         if signal == "kernel":
-            self.sig = symm_mem.empty((max(self.world + 1, 64),), dtype=torch.int32, device=dev)    # uint32 epoch slots
+            self.sig = symm_mem.empty((max(2 * self.world, 64),), dtype=torch.int32, device=dev)    # uint32 epoch slots
             self.sig.zero_()
             self.sig_hdl = symm_mem.rendezvous(self.sig, self.group)
+        self._workspaces = _lib.DetectWorkspaces()
         torch.cuda.synchronize()
         dist.barrier(self.group)            # every rank's blocks are zeroed before any peer stores rows into them
         self.turn = 0
@@ -152,28 +159,32 @@ class PeerGatherDetect:
         assert B == self.b_local, "PeerGatherDetect was built for a fixed per-rank batch"
         dev = loc.device
         loc, conf, priors = _lib.dev_f32(loc, dev), _lib.dev_f32(conf, dev), _lib.dev_f32(priors, dev)
-        ws = _lib.workspace(L.fdt_detect_workspace_bytes(B, N, d.num_classes), dev, "detect")
+        ws = self._workspaces.get(B, N, d.num_classes, dev)
         st = _lib.stream_ptr()
         hdl, buf = self.hdls[self.turn], self.bufs[self.turn]
-        self.turn ^= 1
-        _lib.check(L.fdt_detect_threshold_compact(conf.data_ptr(), B, N, d.num_classes, float(d.conf_thresh), ws.data_ptr(), ws.numel(), st))
+        self.turn = (self.turn + 1) % self.RING
+        args = (loc.data_ptr(), conf.data_ptr(), priors.data_ptr(), B, N, d.num_classes, int(d.top_k), int(d.nms_top_k),
+                float(d.conf_thresh), float(d.nms_thresh), float(d.variance[0]), float(d.variance[1]))
+        ptrs, n_dst = self.dest_ptrs(hdl)
         if self.signal == "kernel":
             self.epoch += 1
-            _lib.check(L.fdt_detect_sort_nms_gather_signal(loc.data_ptr(), priors.data_ptr(), B, N, d.num_classes, int(d.top_k), int(d.nms_top_k),
-                                                           float(d.nms_thresh), float(d.variance[0]), float(d.variance[1]),
-                                                           int(hdl.buffer_ptrs_dev) + 8 * int(self.dest), int(self.sig_hdl.buffer_ptrs_dev),
-                                                           self.world, self.rank, int(self.dest), self.epoch, self.rank * B,
-                                                           ws.data_ptr(), ws.numel(), st))
-            return buf           # on the root: complete when the kernel ends
-        ptrs, n_dst = self.dest_ptrs(hdl)
-        _lib.check(L.fdt_detect_sort_nms_peers(loc.data_ptr(), priors.data_ptr(), B, N, d.num_classes, int(d.top_k), int(d.nms_top_k),
-                                               float(d.nms_thresh), float(d.variance[0]), float(d.variance[1]),
-                                               ptrs, n_dst, self.rank * B, ws.data_ptr(), ws.numel(), st))
+            _lib.check(L.fdt_detect_gather_signal(*args, ptrs, n_dst, int(self.sig_hdl.buffer_ptrs_dev), self.world, self.rank,
+                                                  -1 if self.dest == "all" else int(self.dest), self.epoch, self.RING, self.rank * B,
+                                                  ws.data_ptr(), ws.numel(), st))
+            return buf           # on a destination: complete in stream order (the await kernel is enqueued by the call)
+        _lib.check(L.fdt_detect_peers(*args, ptrs, n_dst, self.rank * B, ws.data_ptr(), ws.numel(), st))
         hdl.barrier()            # all ranks' rows have landed in the destination block(s)
         return buf
 
     def dest_ptrs(self, hdl):
-        """(device array of destination block pointers, how many) for fdt_detect_sort_nms_peers."""
+        """(device array of destination block pointers, how many)."""
         if self.dest == "all":
             return int(hdl.buffer_ptrs_dev), self.world
         return int(hdl.buffer_ptrs_dev) + 8 * int(self.dest), 1          # one entry of the symmetric pointer table: the root's block
+
+    def check(self):
+        """Raises if a cross-rank wait timed out (a peer died or never made the call); synchronises."""
+        bits = self._workspaces.status()
+        if bits:
+            raise RuntimeError(f"fdt_b200: fused gather timed out (status {bits:#x}: "
+                               f"{'peer never signalled / acknowledged' if bits & 2 else 'local call never completed'})")

@@ -14,6 +14,9 @@
  *     workspace sized by the matching *_workspace_bytes(); 256-byte alignment is required;
  *   - every launch goes to `stream` (a cudaStream_t passed as void*), asynchronously; calls are
  *     reentrant across streams with distinct workspaces and CUDA-graph capturable;
+ *   - a Detect workspace is STATEFUL: its first 256 bytes carry a call sequence between calls (see
+ *     fdt_detect).  Use one workspace per stream, do not write into it, and do not hand the same
+ *     workspace to two streams at a time; memory that never was a workspace (any content) is fine;
  *   - returns FDT_OK or a negative FDT_E_* code; fdt_last_error() gives the thread-local message;
  *     no exceptions, no exit(), no CPU fallback.
  *   - fp32 arithmetic is IEEE in the reference's operand order with FMA contraction off
@@ -43,6 +46,10 @@ extern "C" {
 #define FDT_NMS_LE         8      /* a box survives iff overlap <= thresh (default: overlap < thresh) */
 
 #define FDT_MAX_NMS_TOP_K  8000   /* candidates that can enter NMS per image/class (the reference uses 5000) */
+
+/* sticky status bits of a Detect workspace (fdt_detect_status): a device-side wait gave up after ~4 s */
+#define FDT_STATUS_TIMEOUT_LOCAL 1u   /* a call of the same workspace never completed (the kernel also traps) */
+#define FDT_STATUS_TIMEOUT_PEER  2u   /* fused multi-GPU gather: a peer rank never acknowledged / never delivered its rows */
 
 typedef void *fdt_stream_t;        /* cudaStream_t */
 typedef struct fdt_ctx fdt_ctx;    /* host-buffer context: owns a stream, device + pinned staging buffers */
@@ -131,9 +138,22 @@ int fdt_detect(const float *loc, const float *conf, const float *priors,
                float conf_thresh, float nms_thresh, float var0, float var1,
                float *out, int32_t *counts, int64_t *kept_prior,
                void *ws, size_t ws_bytes, fdt_stream_t stream);
+/* Overlap of consecutive calls.  A workspace of fdt_detect_workspace_bytes_depth(B, N, C, depth) bytes, depth 2..4, holds `depth`
+ * slots of per-call scratch: call s uses slot s % depth, so the threshold pass of call s + 1 runs while the NMS kernel of call s is
+ * still in flight and its NMS CTAs take over SMs as those of call s retire (all on ONE stream, chained by programmatic dependent
+ * launch; a control block at the head of the workspace keeps the calls' completion in order, so anything enqueued after a call
+ * still finds it -- and every earlier call -- complete).  Rules: the inputs of a call must be complete when the call is
+ * enqueued-in-stream-order as usual; a call that writes the same out / counts / kept_prior buffer as a call still in flight waits
+ * for it (use `depth` rotating output buffers to overlap).  depth 1 (fdt_detect_workspace_bytes) runs calls one after another. */
+size_t fdt_detect_workspace_bytes_depth(int B, int64_t N, int C, int depth);
+/* FDT_STATUS_* bits of the workspace (0 = fine); synchronises `stream`. */
+int fdt_detect_status(const void *ws, fdt_stream_t stream, uint32_t *status_h);
+/* Process-wide tuning / diagnostic switches (defaults come from the environment variables FDT_K3_PROFILE, FDT_K3_CLUSTER,
+ * FDT_K3_PDL, FDT_DETECT_DEPTH, read once): "k3_profile" 0/1, "k3_cluster" -1 auto / 0 / 1, "k3_pdl" 0/1, "detect_depth" 1..4. */
+int fdt_set_option(const char *name, int value);
 
 /* Stage entry points (same workspace, same semantics; fdt_detect == stage 1 then stage 2).  They let
- * tests and bench.py check / time the two kernels separately:
+ * tests and bench.py check / time the two kernels separately (a stage-1 call never overlaps an earlier call):
  *   stage 1  K2 threshold + compaction: conf -> per-(image,class) candidate keys + counts in `ws`
  *   stage 2  K3 select/sort + decode + NMS + output rows, consuming `ws` */
 int fdt_detect_threshold_compact(const float *conf, int B, int64_t N, int C, float conf_thresh,
@@ -142,30 +162,39 @@ int fdt_detect_sort_nms(const float *loc, const float *priors, int B, int64_t N,
                         float nms_thresh, float var0, float var1,
                         float *out, int32_t *counts, int64_t *kept_prior,
                         void *ws, size_t ws_bytes, fdt_stream_t stream);
-/* Stage 2 with the multi-GPU gather fused in: instead of a local `out`, the detection rows of this rank's B
- * images are stored straight into EVERY rank's gathered block [world*B, C, top_k, 5] at image index image_offset + b, over
- * NVLink peer memory (no separate collective).  peer_out_ptrs: DEVICE array of n_peers base pointers of those blocks (e.g.
- * torch symmetric memory `buffer_ptrs_dev`); the caller synchronises the ranks afterwards (a symmetric-memory barrier).
- * The background (class 0) planes of the gathered blocks are NOT written: the caller zeroes the blocks once after allocating
- * them and they stay zero (half of the NVLink traffic of a two-class Detect). */
-int fdt_detect_sort_nms_peers(const float *loc, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
-                              float nms_thresh, float var0, float var1,
-                              const uint64_t *peer_out_ptrs, int n_peers, int64_t image_offset,
-                              void *ws, size_t ws_bytes, fdt_stream_t stream);
-/* Gather to ONE rank with the completion signal folded into the kernel (no barrier launch).  root_out_ptr: DEVICE pointer to the
- * entry of the symmetric pointer table that holds the root's gathered block; peer_signal_ptrs: DEVICE array of `world` pointers to
- * every rank's uint32 signal[world + 1] array (symmetric memory, zeroed once).  `epoch` (>= 1) is the call counter, the same on every
- * rank and increasing by one per call; two gathered blocks alternate (parity of epoch).  A non-root rank stores its rows into the
- * root's block, publishes `epoch` in slot [rank] of the root's array and does not wait for anybody -- except, before storing, for the
- * root's acknowledgement of epoch - 1 in its own slot [world] (the block of that parity is free again; normally long satisfied).
- * The root's kernel ends only when every rank's rows of this epoch have landed in its block, then acknowledges.  `epoch` is a launch
- * parameter: do not replay this call from a captured CUDA graph.  Every wait gives up after ~2 s. */
-int fdt_detect_sort_nms_gather_signal(const float *loc, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
-                                      float nms_thresh, float var0, float var1,
-                                      const uint64_t *root_out_ptr, const uint64_t *peer_signal_ptrs, int world, int rank, int root,
-                                      uint32_t epoch, int64_t image_offset, void *ws, size_t ws_bytes, fdt_stream_t stream);
 /* Number of candidates per (image, class>=1) list after stage 1: copies B*(C-1) int32 to counts_out (device). */
-int fdt_detect_candidate_counts(const void *ws, int B, int C, int32_t *counts_out, fdt_stream_t stream);
+int fdt_detect_candidate_counts(const void *ws, size_t ws_bytes, int B, int64_t N, int C, int32_t *counts_out, fdt_stream_t stream);
+
+/* Detect with the multi-GPU gather fused in: instead of a local `out`, the detection rows of this rank's B images are
+ * stored straight into the gathered block [world*B, C, top_k, 5] of n_peers destination ranks at image index image_offset + b, over
+ * NVLink peer memory (16-byte vector stores, no separate collective).  peer_out_ptrs: DEVICE array of n_peers base pointers of those
+ * blocks (e.g. torch symmetric memory `buffer_ptrs_dev`); the caller synchronises the ranks afterwards (a symmetric-memory
+ * barrier).  The background (class 0) planes of the gathered blocks are NOT written: the caller zeroes the blocks once after
+ * allocating them and they stay zero (half of the NVLink traffic of a two-class Detect). */
+int fdt_detect_peers(const float *loc, const float *conf, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
+                     float conf_thresh, float nms_thresh, float var0, float var1,
+                     const uint64_t *peer_out_ptrs, int n_peers, int64_t image_offset,
+                     void *ws, size_t ws_bytes, fdt_stream_t stream);
+/* The same with the completion signalling folded in (no barrier launch, nobody spins inside the NMS kernel).
+ *   dest_out_ptrs     DEVICE array of n_dest block pointers: root >= 0: n_dest = 1, the root's block; root = -1: n_dest = world,
+ *                     every rank's block in rank order (all-gather).  `ring` blocks alternate between calls (the caller passes
+ *                     the pointer table of block epoch % ring).
+ *   peer_signal_ptrs  DEVICE array of `world` pointers to every rank's uint32 signal[2 * world] array (symmetric memory, zeroed
+ *                     once): [q] = last epoch whose rows from rank q have landed here, [world + q] = last call rank q has begun.
+ *   epoch             call counter (>= 1), the same on every rank, increasing by one per call.
+ * A source rank waits (before storing, normally long satisfied) until every destination has begun call epoch - ring + 1 -- in the
+ * destination's stream that follows whatever consumed call epoch - ring, so the block is free --, stores its rows, and its last
+ * CTA publishes `epoch` to the destinations.  A destination rank additionally enqueues fdt_detect_gather_await (done here), a
+ * one-block kernel that ends when all sources have published `epoch`: what consumes the gathered block follows it in stream
+ * order, while the next call is NOT held back by it.  Every rank must make the call for the destinations' streams to advance; a
+ * wait that sees no progress for ~4 s gives up, sets FDT_STATUS_TIMEOUT_PEER (fdt_detect_status) and the rank stops signalling.
+ * `epoch` is a launch parameter: do not replay this call from a captured CUDA graph. */
+int fdt_detect_gather_signal(const float *loc, const float *conf, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
+                             float conf_thresh, float nms_thresh, float var0, float var1,
+                             const uint64_t *dest_out_ptrs, int n_dest, const uint64_t *peer_signal_ptrs,
+                             int world, int rank, int root, uint32_t epoch, int ring, int64_t image_offset,
+                             void *ws, size_t ws_bytes, fdt_stream_t stream);
+int fdt_detect_gather_await(const uint64_t *peer_signal_ptrs, int world, int rank, uint32_t epoch, void *ws, fdt_stream_t stream);
 
 /* ----  head post-processing that feeds Detect  (pyramid.py:291-309, 331-338; same code in
  * pyramid_mobile_try1.py:297-327, pyramid_mb2_try3/4/5.py) -------------------------------------------------------------

@@ -176,17 +176,18 @@ def gen_detect_shapes():
     """Detect at the other shapes of BASELINE.json / the reference scripts: 1024x1024 (config 5, N = 87,360) and the tracker's
     640x480 prior set (iouTracke_cal.py:98, N = 25,600) with production thresholds.  Inputs by seed."""
     d = {}
-    for tag, (w, h, mode, seed, args) in {
-        "1024": (1024, 1024, "random", 20265, (2, 0, 750, 0.05, 0.3)),
-        "480": (640, 480, "clustered", 20266, (2, 0, 750, 0.3, 0.35)),
+    for tag, (w, h, mode, seed, args, B) in {
+        "1024": (1024, 1024, "random", 20265, (2, 0, 750, 0.05, 0.3), 1),
+        "480": (640, 480, "random", 20266, (2, 0, 750, 0.3, 0.35), 1),          # ~820 candidates
+        "480c": (640, 480, "clustered", 20267, (2, 0, 750, 0.3, 0.35), 2),      # a few hundred candidates around face clusters
     }.items():
         pri = ref_priors(w, h)
         assert np.array_equal(pri.numpy(), synth.priors_numpy(w, h))
-        loc, conf = synth.detect_inputs(1, pri.numpy(), seed, args[3], mode)
+        loc, conf = synth.detect_inputs(B, pri.numpy(), seed, args[3], mode)
         det = Detect(*args)
         out, counts, kept = ref_detect_aux(det, torch.from_numpy(loc), torch.from_numpy(conf), pri)
         print("  detect", tag, "N", pri.shape[0], "counts", counts[:, 1], "candidates", (conf[..., 1] > args[3]).sum(1))
-        d.update({f"{tag}_cfg": np.array([w, h, seed]), f"{tag}_mode": np.array(mode), f"{tag}_args": np.array(args, np.float64),
+        d.update({f"{tag}_cfg": np.array([w, h, seed, B]), f"{tag}_mode": np.array(mode), f"{tag}_args": np.array(args, np.float64),
                   f"{tag}_in_sha": np.array(synth.digest(loc, conf)), f"{tag}_out": out[:, 1], f"{tag}_counts": counts,
                   f"{tag}_kept": kept.astype(np.int32)})
     save("detect_shapes", **d)

@@ -1,7 +1,8 @@
 """Multi-GPU check (not collected by pytest; run with torchrun on >= 2 GPUs):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/multigpu_check.py
-Every rank detects its shard; the fused peer-memory gather and the NCCL all-gather must both reproduce, byte for byte, what
-one process computes on the concatenated batch (checked against the CPU oracle on rank 0)."""
+Every rank detects its shard; the fused peer-memory gather (barrier / signalled, to a root / to every rank) and the NCCL
+all-gather must all reproduce, byte for byte, what one process computes on the concatenated batch (checked against the CPU
+oracle on rank 0); the sharded MultiBoxLoss and its gradients must equal the single-process loss on the whole batch."""
 import os
 import sys
 
@@ -15,6 +16,11 @@ import fdt_b200  # noqa: E402
 from fdt_b200 import synth  # noqa: E402
 from fdt_b200.layers import Detect  # noqa: E402
 from fdt_b200.sharding import PeerGatherDetect, ShardedDetect, shard_range  # noqa: E402
+
+
+def orc_loss(loc, conf, pri, targets):
+    from oracle import oracle as orc
+    return orc.multibox_loss(loc, conf, pri, targets, 0.35, 3, False, want_aux=False)
 
 
 def main():
@@ -38,15 +44,39 @@ def main():
     o2 = peer(cu(loc[sh][lo:hi]), cu(conf[sh][lo:hi]), cu(pri)).cpu().numpy()
     outs.append(o2[np.argsort(sh)])
     ok = nccl.tobytes() == packed.tobytes() and all(o.tobytes() == nccl.tobytes() for o in outs)
-    # gather to a root: only the root's block is written; with the barrier after the kernel, or signalled by the kernel itself
-    for root, signal in ((0, "barrier"), (world - 1, "barrier"), (0, "kernel"), (world - 1, "kernel")):
+    # gather to a root: only the root's block is written; with the barrier after the kernel, or signalled through symmetric memory
+    # (10 calls back to back: more than the ring of gathered blocks and than the workspace ring, a different batch every call so
+    # that stale rows can never pass)
+    for root, signal in ((0, "barrier"), (world - 1, "barrier"), (0, "kernel"), (world - 1, "kernel"), ("all", "kernel")):
         pr = PeerGatherDetect(det, b_local, dest=root, signal=signal)
-        for it in range(6):
-            sh = (np.arange(B) + it) % B           # a different batch every call: stale rows must never survive
+        got = []
+        for it in range(10):
+            sh = (np.arange(B) + it) % B
             o = pr(cu(loc[sh][lo:hi]), cu(conf[sh][lo:hi]), cu(pri))
-            if rank == root:
-                torch.cuda.synchronize()
+            got.append((sh, o.clone()))        # an ordinary kernel behind the call: on a destination it must see every rank's rows
+        torch.cuda.synchronize()
+        pr.check()
+        if root == "all" or rank == root:
+            for sh, o in got:
                 ok = ok and o.cpu().numpy()[np.argsort(sh)].tobytes() == nccl.tobytes()
+        dist.barrier()
+    # MultiBoxLoss sharded over the ranks (multibox_loss.py:130-135: one global normalisation) == one process on the whole batch
+    from fdt_b200.layers import MultiBoxLoss
+    from fdt_b200.sharding import sharded_multibox_loss
+    l2, c2, targets = synth.multibox_inputs(B, pri, 98, 0, 40)
+    crit = MultiBoxLoss(2, 0.35, True, 0, True, 3, 0.35, False)
+    la = cu(l2[lo:hi]).requires_grad_(True); ca = cu(c2[lo:hi]).requires_grad_(True)
+    ll, lc = sharded_multibox_loss(crit, (la, ca, cu(pri)), [cu(t) for t in targets[lo:hi]])
+    (ll + lc).backward()
+    lf = cu(l2).requires_grad_(True); cf = cu(c2).requires_grad_(True)
+    fl, fc = MultiBoxLoss(2, 0.35, True, 0, True, 3, 0.35, False)((lf, cf, cu(pri)), [cu(t) for t in targets])
+    (fl + fc).backward()
+    ok = ok and np.allclose([float(ll), float(lc)], [float(fl), float(fc)], rtol=1e-5)
+    ok = ok and np.allclose(la.grad.cpu().numpy(), lf.grad[lo:hi].cpu().numpy(), rtol=1e-4, atol=1e-8)
+    ok = ok and np.allclose(ca.grad.cpu().numpy(), cf.grad[lo:hi].cpu().numpy(), rtol=1e-4, atol=1e-8)
+    if rank == 0:
+        r = orc_loss(l2, c2, pri, targets)
+        ok = ok and np.allclose([float(ll), float(lc)], [r["loss_l"], r["loss_c"]], rtol=1e-5)
     if rank == 0:
         from oracle import oracle as orc
         o = orc.Detect(2, 0, 750, 0.05, 0.3); o.early_exit = True

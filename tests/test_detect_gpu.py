@@ -255,7 +255,7 @@ def test_detect_stage_entry_points_and_candidate_counts(layers):
     st = _lib.stream_ptr()
     _lib.check(L.fdt_detect_threshold_compact(c.data_ptr(), B, N, C, 0.05, ws.data_ptr(), ws.numel(), st))
     cnt = torch.empty(B, dtype=torch.int32, device=dev)
-    _lib.check(L.fdt_detect_candidate_counts(ws.data_ptr(), B, C, cnt.data_ptr(), st))
+    _lib.check(L.fdt_detect_candidate_counts(ws.data_ptr(), ws.numel(), B, N, C, cnt.data_ptr(), st))
     assert np.array_equal(npy(cnt), (conf[..., 1] > np.float32(0.05)).sum(1).astype(np.int32))
     out = torch.empty((B, C, 750, 5), dtype=torch.float32, device=dev)
     _lib.check(L.fdt_detect_sort_nms(l.data_ptr(), p.data_ptr(), B, N, C, 750, 5000, 0.3, 0.1, 0.2, out.data_ptr(), None, None,
@@ -409,15 +409,15 @@ def test_detect_cuda_graph_capture_and_side_stream(layers):
     assert not npy(out).any()
 
 
-@pytest.mark.parametrize("tag", ["1024", "480"])
+@pytest.mark.parametrize("tag", ["1024", "480", "480c"])
 def test_detect_golden_other_shapes(layers, golden, tag):
     """Reference fixtures at 1024x1024 (BASELINE config 5 shape) and at the tracker's 640x480 prior set (production thresholds)."""
     g = golden("detect_shapes")
-    w, h, seed = (int(v) for v in g[tag + "_cfg"])
+    w, h, seed, B = (int(v) for v in g[tag + "_cfg"])
     a = g[tag + "_args"]
     args = (int(a[0]), int(a[1]), int(a[2]), float(a[3]), float(a[4]))
     pri = synth.priors_numpy(w, h)
-    loc, conf = synth.detect_inputs(1, pri, seed, args[3], str(g[tag + "_mode"]))
+    loc, conf = synth.detect_inputs(B, pri, seed, args[3], str(g[tag + "_mode"]))
     assert synth.digest(loc, conf) == str(g[tag + "_in_sha"])
     det = layers.Detect(*args)
     out, counts, kept = det(cu(loc), cu(conf), cu(pri), return_aux=True)

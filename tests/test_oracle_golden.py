@@ -200,16 +200,16 @@ def test_torch_restatement_matches_oracle():
 
 
 def shapes_case(g, tag):
-    w, h, seed = (int(v) for v in g[tag + "_cfg"])
+    w, h, seed, B = (int(v) for v in g[tag + "_cfg"])
     a = g[tag + "_args"]
     args = (int(a[0]), int(a[1]), int(a[2]), float(a[3]), float(a[4]))
     pri = synth.priors_numpy(w, h)
-    loc, conf = synth.detect_inputs(1, pri, seed, args[3], str(g[tag + "_mode"]))
+    loc, conf = synth.detect_inputs(B, pri, seed, args[3], str(g[tag + "_mode"]))
     assert synth.digest(loc, conf) == str(g[tag + "_in_sha"]), "synthetic generator drifted"
     return loc, conf, pri, args
 
 
-@pytest.mark.parametrize("tag", ["1024", "480"])
+@pytest.mark.parametrize("tag", ["1024", "480", "480c"])
 def test_detect_other_shapes(golden, tag):
     """1024x1024 (BASELINE config 5, N = 87,360) and the tracker's 640x480 prior set with production thresholds."""
     g = golden("detect_shapes")

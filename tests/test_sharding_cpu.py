@@ -31,8 +31,11 @@ class OracleDetect:
         self.det = orc.Detect(2, 0, 50, 0.05, 0.3)
         self.det.n_threads = 1
 
-    def __call__(self, loc, conf, pri):
-        return torch.from_numpy(self.det(loc.numpy(), conf.numpy(), pri.numpy()))
+    def __call__(self, loc, conf, pri, return_aux=False):
+        out, counts, kept = self.det(loc.numpy(), conf.numpy(), pri.numpy(), return_aux=True)
+        if return_aux:
+            return torch.from_numpy(out), torch.from_numpy(counts), torch.from_numpy(kept)
+        return torch.from_numpy(out)
 
 
 class OracleLoss:

@@ -41,6 +41,7 @@ def test_tracker_golden(tracker, golden, tag, slow, monkeypatch):
 
 
 @pytest.mark.parametrize("kw", [
+    dict(F=10000, seed=4040, d_lo=1, d_hi=300, n_objects=300, empty_every=1000),        # BASELINE config 4 at full length (bench.py's video)
     dict(F=2000, seed=21, d_lo=1, d_hi=300, n_objects=300, empty_every=333),            # config-4 shape, shorter
     dict(F=500, seed=22, d_lo=100, d_hi=120, n_objects=120, empty_every=0, sigma=6.0),  # crowded, many conflicts
     dict(F=300, seed=23, d_lo=1, d_hi=3, n_objects=3, empty_every=7),

@@ -30,5 +30,5 @@ for name, fn in (("copy + K2", cp), ("zero-copy K2", zc), ("copy + K2", cp), ("z
     for _ in range(20):
         fn(); torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / 20
-    _lib.check(L.fdt_detect_candidate_counts(ws.data_ptr(), B, C, cnt.data_ptr(), st))
+    _lib.check(L.fdt_detect_candidate_counts(ws.data_ptr(), ws.numel(), B, N, C, cnt.data_ptr(), st))
     print(f"{name:14s} {dt * 1e3:.3f} ms  ({conf_h.numel() * 4 / dt / 1e9:.1f} GB/s)  candidates {int(cnt.sum())}")
