@@ -17,7 +17,8 @@ has).  Prints ONE JSON line (rank 0).
   e2e       frames/s through the public API with pinned HOST tensors: Detect.__call__ -> fdt_detect_host
             (H2D copies + kernels + D2H of the detections inside the timed region, wall clock), beside the host's own pinned
             H2D rate measured in the same run.
-  roofline  dominant kernel (k_sort_nms) timed live through the stage entry points.
+  roofline  dominant kernel = the fused k_sort_nms, i.e. the step itself (k_detect_begin is one block); the two-kernel path is
+            timed beside it through the stage entry points.
   cpu_baseline  the C oracle port (oracle/, the checker) on the host cores, bounded sample.
   secondary (N=1) BASELINE configs 3, 4, 5 -- MultiBoxLoss B=32, the IoU tracker over 10k frames, Detect B=512 @1024^2 -- each
             with a parity bit against the oracle, outside the headline timed region.
@@ -86,10 +87,12 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def measured_traffic():
-    """dram bytes per k_sort_nms launch from the newest `ncu --set full` summary under profiles/ (written by tools/ncu_summary.py)"""
+def profile_summary():
+    """What the newest ncu summary under profiles/ (profiles/r*_detect_summary*.json, written by tools/ncu_summary.py from an
+    `ncu --set full` capture and the launch list of this command) says about the dominant kernel: DRAM bytes per launch and its
+    share of the step's kernel time."""
     best = None
-    for path in glob.glob(os.path.join(ROOT, "profiles", "r*_sortnms_traffic*.json")):
+    for path in glob.glob(os.path.join(ROOT, "profiles", "r*_detect_summary*.json")):
         try:
             with open(path) as f:
                 d = json.load(f)
@@ -98,8 +101,10 @@ def measured_traffic():
         except Exception:                                         # noqa: BLE001
             pass
     if best is None:
-        return None, "no ncu --set full summary under profiles/"
-    return float(best[1]["dram_bytes_read"]) + float(best[1]["dram_bytes_write"]), os.path.relpath(best[0], ROOT) + ": " + best[1].get("note", "")
+        return {"traffic": None, "traffic_source": "no ncu summary under profiles/", "kernel_share_of_step": None, "share_source": None}
+    rel, d = os.path.relpath(best[0], ROOT), best[1]
+    return {"traffic": float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), "traffic_source": rel + ": " + d.get("traffic_note", ""),
+            "kernel_share_of_step": d.get("kernel_share_of_step"), "share_source": rel + ": " + d.get("share_note", "")}
 
 
 def host_threads():
@@ -506,9 +511,10 @@ def main():
     sampler.active = False
     sampler.stop_flag.set()
     step_ms = [e[0].elapsed_time(e[1]) for e in ev]
-    k3_iso_ms = k3_b2b_ms = None
+    unfused = None
     if world == 1:
-        # dominant kernel alone, (a) isolated: stage 1, then an event pair around the stage-2 launch, L2 flushed before the step
+        # for reference: the two-kernel path (K2 threshold/compaction grid + k_sort_nms reading its keys), stage entry points.
+        # (a) k_sort_nms isolated: stage 1, then an event pair around the stage-2 launch, L2 flushed before the step
         k3 = []
         for _ in range(max(10, min(args.steps, 30))):
             flush.zero_()
@@ -521,9 +527,7 @@ def main():
             torch.cuda.synchronize()
             k3.append(a.elapsed_time(b2))
             cur[0] += 1
-        k3_iso_ms = float(statistics.median(k3))
-        # (b) as it runs in the timed region -- launches back to back, overlapping each other like consecutive calls do:
-        #     one event pair around K stage-2 launches on the same prepared workspace slot, average per launch
+        # (b) K stage-2 launches back to back on one prepared workspace slot (they overlap on the device), average per launch
         reps = []
         for _ in range(5):
             stage1()
@@ -537,7 +541,9 @@ def main():
             torch.cuda.synchronize()
             reps.append(a.elapsed_time(b2) / args.steps)
             cur[0] += 1
-        k3_b2b_ms = float(statistics.median(reps))
+        unfused = {"k_sort_nms_ms_isolated": float(statistics.median(k3)), "k_sort_nms_ms_back_to_back": float(statistics.median(reps)),
+                   "note": "two-kernel path through fdt_detect_threshold_compact + fdt_detect_sort_nms (head-map input and fdt_set_option('detect_fused', 0) "
+                           "still take it): k_sort_nms alone, isolated and as K overlapping launches on one prepared slot"}
     lat_ms = float(np.mean(step_ms))
     if world > 1:
         t = torch.tensor([lat_ms], dtype=torch.float64, device=dev)
@@ -549,24 +555,21 @@ def main():
     peak, peak_src = peaks()
     roofline = None
     if world == 1:
-        k3_bytes = B * (16 * N + C * TOP_K * 5 * 4) + 16 * N           # loc + output rows per image, priors once
-        step_bytes = B * (24 * N + C * TOP_K * 5 * 4) + 16 * N         # 849,000 B/image + priors
-        traffic, traffic_src = measured_traffic()
-        roofline = {"bound": "hbm", "kernel": "k_sort_nms (select/sort + decode + lazy NMS + output rows)",
-                    "achieved": k3_bytes / (k3_b2b_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": k3_bytes / (k3_b2b_ms * 1e-3) / 1e9 / peak,
-                    "traffic": traffic, "traffic_source": traffic_src,
+        step_bytes = B * (24 * N + C * TOP_K * 5 * 4) + 16 * N         # 849,000 B/image (conf 8 N + loc 16 N + rows) + priors once
+        prof = profile_summary()
+        roofline = {"bound": "hbm", "kernel": "k_sort_nms<DETECT, fused> (threshold + select/sort + decode + lazy NMS + output rows: the whole step but the "
+                                              "one-block sequencing kernel k_detect_begin)",
+                    "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                    "traffic": prof.get("traffic"), "traffic_source": prof.get("traffic_source"),
                     "peak_source": peak_src,
-                    "kernel_ms": k3_b2b_ms, "kernel_ms_isolated": k3_iso_ms,
-                    "frac_isolated": k3_bytes / (k3_iso_ms * 1e-3) / 1e9 / peak,
-                    "kernel_share_of_step": min(1.0, k3_b2b_ms / ms_per_step),
-                    "kernel_timing": "kernel_ms = average launch duration with the launches issued back to back as in the timed region "
-                                     f"(one event pair around {args.steps} stage-2 launches on a prepared workspace; consecutive launches overlap on "
-                                     "the device exactly like consecutive Detect calls, median of 5); kernel_ms_isolated = own event pair around "
-                                     "ONE stage-2 launch, L2 flushed before the step",
-                    "algorithmic_bytes_per_launch": k3_bytes,
-                    "step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
-                             "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
+                    "kernel_ms": ms_per_step, "kernel_ms_isolated": lat_ms,
+                    "frac_isolated": step_bytes / (lat_ms * 1e-3) / 1e9 / peak,
+                    "kernel_share_of_step": prof.get("kernel_share_of_step"), "share_source": prof.get("share_source"),
+                    "kernel_timing": "kernel_ms = average launch duration over the timed region (K launches issued back to back on one stream, "
+                                     "overlapping on the device; median block / K); kernel_ms_isolated = one call alone with its own event pair, L2 flushed",
+                    "algorithmic_bytes_per_launch": step_bytes,
+                    "unfused_path": unfused,
                     "note": "NMS is O(K^2) IoU work on SM ALUs/LSU, not a streaming kernel; frac is bytes/time as the spec asks"}
 
     # ---- end to end through the public API with pinned host tensors
@@ -628,7 +631,7 @@ def main():
         del sets
         secondary = secondary_workloads(torch, dev, flush, peak)
 
-    launches_per_step = 3 + (1 if (world > 1 and peer is not None and peer.signal == "kernel") else 0)
+    launches_per_step = 2 + (1 if (world > 1 and peer is not None and peer.signal == "kernel") else 0)
     line = {"metric": METRIC,
             "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -641,7 +644,7 @@ def main():
             "latency": {"ms_per_step": lat_ms, "frames_per_s": world * B / (lat_ms * 1e-3), "steps": n_lat,
                         "how": "each step alone with its own event pair; 256 MiB L2 flush + 0.1 ms GPU spin before it (outside the pair)"},
             "clocks": sampler.result(), "e2e": e2e,
-            "gpu_launches": launches_per_step * args.steps * n_blocks,      # k_detect_begin, k_threshold_compact, k_sort_nms (+ k_gather_await on rank 0)
+            "gpu_launches": launches_per_step * args.steps * n_blocks,      # k_detect_begin, k_sort_nms<fused> (+ k_gather_await on rank 0)
             "gpu_launches_per_step": launches_per_step,
             "wall_s_timed_region": wall}
     if world > 1:

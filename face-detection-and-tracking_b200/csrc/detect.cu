@@ -148,7 +148,7 @@ k_heads_to_loc_conf(const HeadLevels h, const int N, const int softmax, float *_
 // after ALL blocks of the grid it waits for had started (programmatic launch completion), so the producers are resident and the
 // spins cannot deadlock.  Keys and counters written by another grid still in flight are read with ld.global.cg (L2).
 //
-// Slot header: int32 counters[3 * lists] | ticket | k2_done | begin_seq.
+// Slot header: int32 counters[3 * lists] | k2_done | begin_seq.
 constexpr unsigned long long FDT_CTL_MAGIC = 0x4644543262303031ull;      // "FDT2b001"
 constexpr int FDT_DETECT_MAX_DEPTH = 4;
 struct DetectCtl {
@@ -159,6 +159,7 @@ struct DetectCtl {
     unsigned error;                    // sticky FDT_STATUS_* bits (a wait timed out)
     unsigned check;                    // ~seq ^ (unsigned)magic: guards against foreign writes into a recycled buffer
     unsigned pad;
+    unsigned ticket[FDT_DETECT_MAX_DEPTH];     // completion ticket per slot: writer CTAs of k_sort_nms count themselves out, the last one resets it
     unsigned long long outs[FDT_DETECT_MAX_DEPTH][3];      // out / counts / kept_prior of the last R calls
 };
 static_assert(sizeof(DetectCtl) <= 256, "control block is 256 bytes");
@@ -179,7 +180,7 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
-constexpr int SLOT_TICKET = 0, SLOT_K2_DONE = 1, SLOT_BEGIN_SEQ = 2, SLOT_EXTRA = 4;     // after counters[3 * lists]
+constexpr int SLOT_K2_DONE = 0, SLOT_BEGIN_SEQ = 1, SLOT_EXTRA = 4;     // after counters[3 * lists]
 // spins until (int)(*p - target) >= 0; false after ~4 s (a bug or a dead peer must not hang the GPU for ever)
 __device__ __forceinline__ bool spin_until_reached(const unsigned *p, const unsigned target)
 {
@@ -215,6 +216,7 @@ k_detect_begin(const DetectSlots S, const unsigned long long magic, const int li
             seq = k3s = done = (unsigned)(clock64() >> 3) * 2654435761u;
             for (int q = 0; q < FDT_DETECT_MAX_DEPTH; ++q) { v->outs[q][0] = 0; v->outs[q][1] = 0; v->outs[q][2] = 0; }
             v->error = 0; v->k3s = seq; v->done = seq;
+            for (int q = 0; q < FDT_DETECT_MAX_DEPTH; ++q) v->ticket[q] = 0;
         } else {
             if (k3s != seq) {
                 // the previous call never launched its k_sort_nms (stage 1 alone): it is void.  Its K2 is our predecessor.
@@ -231,6 +233,7 @@ k_detect_begin(const DetectSlots S, const unsigned long long magic, const int li
             }
             const unsigned need = alias ? seq : seq + 1 - (unsigned)R;        // slot reuse: call s - R has completed
             if ((int)(done - need) < 0 && !spin_until_reached(&ctl->done, need)) { atomicOr(&ctl->error, FDT_STATUS_TIMEOUT_LOCAL); __trap(); }
+            if (alias && !waited) { cudaGridDependencySynchronize(); waited = true; }     // and its stores have landed
         }
         seq += 1;
         const int sl = seq % R;
@@ -243,7 +246,7 @@ k_detect_begin(const DetectSlots S, const unsigned long long magic, const int li
     __syncthreads();
     cudaTriggerProgrammaticLaunchCompletion();           // K2 may be scheduled: its blocks wait for begin_seq below
     int32_t *counters = reinterpret_cast<int32_t *>(S.base + (size_t)s_slot * S.stride);
-    for (int i = threadIdx.x; i < 3 * lists + SLOT_BEGIN_SEQ; i += blockDim.x) counters[i] = 0;       // counters, ticket, k2_done
+    for (int i = threadIdx.x; i < 3 * lists + SLOT_BEGIN_SEQ; i += blockDim.x) counters[i] = 0;       // counters, k2_done
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) st_release_u32(reinterpret_cast<unsigned *>(counters) + 3 * lists + SLOT_BEGIN_SEQ, s_seqv);
@@ -533,7 +536,10 @@ struct SortNmsParams {
     int use_counters;           // S.ctl != null: the slot's counters hold the candidate count
     int k2_blocks;              // S.ctl != null: blocks of the call's K2 grid (k_sort_nms waits until all have counted themselves in)
     int64_t key_stride;
+    const float *conf;          // [B,N,C]  (FUSED: the kernel thresholds its own list)
+    float conf_thresh;
     const float *loc;           // [B,N,4]  (MODE_DETECT); null: gather the rows from the head maps `hl`
+    int loc_prefetch;           // loc is device memory: prefetch the rows of the first window into L2 during the scatter
     const float *priors;        // [N,4]    (MODE_DETECT)
     const float *boxes;         // [n,4]    (MODE_NMS)
     int64_t N;
@@ -563,7 +569,8 @@ struct SortNmsParams {
     uint64_t *g_kkey;
     SmemPlan sm;
     HeadLevels hl;              // per-level NCHW loc maps (MODE_DETECT with loc == null)
-    long long *prof;            // diagnostics: per-phase clock64 of CTA 0 (null unless FDT_K3_PROFILE=1)
+    long long *prof;            // diagnostics: per-phase clock64 of CTA 0 (null unless FDT_K3_PROFILE=1 / 2)
+    int prof_all;               // FDT_K3_PROFILE=2: every CTA of every launch ADDS its phase clocks (steady-state averages; [30] counts CTAs)
 };
 
 // "i (kept, higher score) suppresses j": box_utils.py:322-339, union = (area_j - inter) + area_i,
@@ -805,7 +812,11 @@ __device__ __forceinline__ void csr_scan(int *a, int *s_warp)
 // CL = CTAs per list: 1, or 2 as a thread-block cluster when the batch leaves SMs idle.  With CL = 2 both CTAs run every stage
 // redundantly and deterministically (identical shared-memory state) except phase B -- the dominant one -- whose candidates they
 // split; the partial dependency lists are merged through distributed shared memory.
-template <int MODE, int CL>
+// FUSED (MODE_DETECT, CL = 1): no K2, no candidate keys in global memory -- the CTA thresholds its own list of `conf` itself:
+// one pass for the bucket histogram (which also counts the candidates), one for the scatter (served by L2), the rare exact
+// fallbacks re-scan the row.  With consecutive calls overlapping on the device what counts is SM time, not latency: the ~1,350
+// SM-microseconds per B = 64 call that a separate K2 grid and the hand-over to this kernel cost shrink to the two row scans.
+template <int MODE, int CL, bool FUSED>
 __global__ void __launch_bounds__(K3_THREADS, 1)
 k_sort_nms(const SortNmsParams P)
 {
@@ -817,6 +828,7 @@ k_sort_nms(const SortNmsParams P)
     const uint64_t *keys_base = P.keys;
     const int32_t *counters = P.counters;
     int *ticket = nullptr;
+    const int *slot_hdr = nullptr;
     char *slot_kept = nullptr;
     if (P.S.ctl) {
         my_seq = detect_call_seq(P.S, &s_seq);
@@ -824,7 +836,8 @@ k_sort_nms(const SortNmsParams P)
         char *slot = P.S.base + (size_t)(my_seq % (unsigned)P.S.depth) * P.S.stride;
         keys_base = reinterpret_cast<const uint64_t *>(slot + P.S.keys_off);
         counters = P.use_counters ? reinterpret_cast<const int32_t *>(slot) : nullptr;
-        ticket = reinterpret_cast<int *>(slot) + 3 * (int)(gridDim.x / CL) + SLOT_TICKET;
+        ticket = reinterpret_cast<int *>(&P.S.ctl->ticket[my_seq % (unsigned)P.S.depth]);
+        slot_hdr = reinterpret_cast<const int *>(slot) + 3 * (int)(gridDim.x / CL);
         slot_kept = slot + P.S.kept_off;
         if (MODE == MODE_DETECT && P.peer_sig && blockIdx.x == 0 && (P.root < 0 || P.root == P.my_rank) &&
             threadIdx.x < P.world && (int)threadIdx.x != P.my_rank) {
@@ -900,10 +913,13 @@ k_sort_nms(const SortNmsParams P)
         }
         if (P.counts && tid == 0) P.counts[b * P.C] = 0;
     }
-    if (P.S.ctl) {
+    if (FUSED) {
+        // nothing to wait for: k_detect_begin lets this grid be scheduled only after its sequencing (which includes the full
+        // dependency wait when the predecessor may be the producer of conf / loc) is done
+    } else if (P.S.ctl) {
         // K2 of this call has written the slot: every one of its blocks has counted itself in (see "call sequencing")
         if (tid == 0) {
-            const unsigned *hdr = reinterpret_cast<const unsigned *>(ticket) - SLOT_TICKET;
+            const unsigned *hdr = reinterpret_cast<const unsigned *>(slot_hdr);
             // (begin_seq first: until k_detect_begin has cleared the slot, k2_done still holds what call seq - depth left there)
             if (!spin_until_equal(hdr + SLOT_BEGIN_SEQ, my_seq) || !spin_until_reached(hdr + SLOT_K2_DONE, (unsigned)P.k2_blocks)) {
                 atomicOr(&P.S.ctl->error, FDT_STATUS_TIMEOUT_LOCAL); __trap();
@@ -913,16 +929,16 @@ k_sort_nms(const SortNmsParams P)
     } else {
         cudaGridDependencySynchronize();  // fdt_nms: behind k_build_keys; a no-op unless launched with programmatic stream serialization
     }
-    int n_c = counters ? __ldcg(counters + list) : (int)P.n;
+    int n_c = FUSED ? 0 : (counters ? __ldcg(counters + list) : (int)P.n);
     if (MODE == MODE_DETECT && n_c == 1) n_c = 0;            // detection.py:66-72: one candidate -> `continue`
-    const int k = min(n_c, P.nms_top_k);                     // box_utils.py:299 idx[-top_k:]
-    const bool prof = P.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    int k = min(n_c, P.nms_top_k);                           // box_utils.py:299 idx[-top_k:]   (FUSED: known after the first row scan)
+    const bool prof = P.prof != nullptr && (blockIdx.x == 0 || P.prof_all) && tid == 0;
     const bool writer = crank == 0;                              // only one CTA of a cluster writes the results
     long long pt = prof ? clock64() : 0, pacc[7] = {0, 0, 0, 0, 0, 0, 0};
     const long long cta_t0 = (P.prof && tid == 0) ? clock64() : 0;
     unsigned long long gt0 = 0;
     if (P.prof && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
-#define K3_STAMP(slot) do { if (P.prof) __syncthreads(); if (prof) { long long now_ = fdt_clock_after(s_warp); P.prof[slot] = now_ - pt; pt = now_; } } while (0)
+#define K3_STAMP(slot) do { if (P.prof) __syncthreads(); if (prof) { long long now_ = fdt_clock_after(s_warp); atomicAdd((unsigned long long *)&P.prof[slot], (unsigned long long)(now_ - pt)); pt = now_; } } while (0)
 #define K3_ACC(slot) do { if (P.prof) __syncthreads(); if (prof) { long long now_ = fdt_clock_after(s_warp); pacc[slot] += now_ - pt; pt = now_; } } while (0)
 
     // =========================================================== stage 1: top-k selection by bucket (counting) sort
@@ -934,16 +950,72 @@ k_sort_nms(const SortNmsParams P)
     unsigned kmin = 0;
     float binv = 0.0f;
     auto bucket = [&](uint64_t key) -> int { return min(NB - 1, (int)((float)((unsigned)(key >> 32) - kmin) * binv)); };
-    if (k > 0) {
-        constexpr int KREG = 8;
-        const bool cached = n_c <= KREG * K3_THREADS;
+    // FUSED: the candidates of this list are the priors i with conf[b, i, cl] > conf_thresh (detection.py:64, strict), read from the row
+    const float *crow = FUSED ? P.conf + ((int64_t)b * P.N) * P.C + cl : nullptr;
+    const float cthr = P.conf_thresh;
+    const int n_scan = FUSED ? (int)P.N : n_c;               // entries a full pass looks at
+    if (FUSED || k > 0) {
+        constexpr int KREG = FUSED ? 1 : 8;
+        const bool cached = !FUSED && n_c <= KREG * K3_THREADS;
         uint64_t kreg[KREG];
         if (cached) {
 #pragma unroll
             for (int u = 0; u < KREG; ++u) { const int i = tid + u * K3_THREADS; kreg[u] = i < n_c ? __ldcg(gkeys + i) : 0; }
         }
+        // FUSED: the first U x 1024 priors of the row (34 x 1024 covers the 34,125 priors of a 640 x 640 image) are loaded with all
+        // U loads of a thread in flight together, and each warp compacts its candidates (ballot order) into its own queue in the
+        // shared memory that only the NMS windows use later.  The histogram / scatter passes then run over DENSE queue entries:
+        // one shared-memory atomic instruction per 32 candidates instead of one per 32 priors (a candidate density of ~1/5 made the
+        // atomics of the sparse form the most expensive part of the kernel).  What does not fit -- a warp with more than WQ_CAP
+        // candidates, rows longer than U x 1024 -- is visited in place on every pass: the scores of the first round stay in registers,
+        // later rounds are re-read (L2).
+        constexpr int U = FUSED ? 34 : 1;
+        constexpr int WQ_CAP = (SM_WSTART - SM_SEGS) / 8 / (K3_THREADS / 32);          // 288 keys per warp
+        float sv[U];
+        int wq_n = 0, u_split = U;                           // warp-uniform: queue length; first u that did not fit any more
+        bool sv_loaded = false;
+        uint64_t *wq = reinterpret_cast<uint64_t *>(smem + SM_SEGS) + warp * WQ_CAP;
         auto for_each_key = [&](auto &&body) {
-            if (cached) {
+            if (FUSED) {
+                const int Nn = (int)P.N, Cc = P.C;
+                auto key_of = [&](const float sc, const int i) -> uint64_t { return ((uint64_t)fdt_float_key(sc) << 32) | (uint32_t)i; };
+                if (!sv_loaded) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int i = tid + u * K3_THREADS;
+                        sv[u] = i < Nn ? __ldg(crow + (int64_t)i * Cc) : __int_as_float(0x7fc00000);     // NaN: never a candidate
+                    }
+                    int run = 0;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const bool c = sv[u] > cthr;                                         // detection.py:64 strict gt
+                        const unsigned bal = __ballot_sync(0xffffffffu, c);
+                        const int cnt = __popc(bal);
+                        if (u_split == U) {
+                            if (run + cnt <= WQ_CAP) {
+                                if (c) wq[run + __popc(bal & ((1u << lane) - 1u))] = key_of(sv[u], tid + u * K3_THREADS);
+                                run += cnt;
+                            } else u_split = u;
+                        }
+                    }
+                    wq_n = run;
+                    sv_loaded = true;
+                    __syncwarp();
+                }
+                for (int e = lane; e < wq_n; e += 32) body(wq[e]);
+                if (u_split < U) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (u >= u_split && sv[u] > cthr) body(key_of(sv[u], tid + u * K3_THREADS));
+                }
+                for (int base = U * K3_THREADS + tid; base < Nn; base += 8 * K3_THREADS) {
+                    float tv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const int i = base + u * K3_THREADS; tv[u] = i < Nn ? __ldg(crow + (int64_t)i * Cc) : __int_as_float(0x7fc00000); }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) if (tv[u] > cthr) body(key_of(tv[u], base + u * K3_THREADS));
+                }
+            } else if (cached) {
 #pragma unroll
                 for (int u = 0; u < KREG; ++u) { if (tid + u * K3_THREADS < n_c) body(kreg[u]); }
             } else {
@@ -954,7 +1026,12 @@ k_sort_nms(const SortNmsParams P)
         for (int i = tid; i < 2 * NB; i += K3_THREADS) s_hist[i] = 0;
         __syncthreads();
         unsigned kmax;
-        if (MODE == MODE_DETECT) {          // k_threshold_compact already reduced the score range of the list
+        if (FUSED) {
+            // the score range is known beforehand: every candidate is above conf_thresh, softmax outputs end at 1.  Anything beyond
+            // lands in the top bucket (the map clamps) and is handled exactly by the fallbacks below.
+            kmin = fdt_float_key(cthr);
+            kmax = max(fdt_float_key(1.0f), kmin);
+        } else if (MODE == MODE_DETECT) {   // k_threshold_compact already reduced the score range of the list
             const int lists = (int)(gridDim.x / CL);
             kmax = (unsigned)__ldcg(counters + lists + list);
             kmin = ~(unsigned)__ldcg(counters + 2 * lists + list);
@@ -987,8 +1064,15 @@ k_sort_nms(const SortNmsParams P)
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += v; }
                 s_warp[lane] = winc - w;
+                if (lane == 31) s_warp[32] = winc;               // histogram total
             }
             __syncthreads();
+            if (FUSED && attempt == 0) {                         // the first row scan counted the candidates
+                n_c = s_warp[32];
+                if (MODE == MODE_DETECT && n_c == 1) n_c = 0;    // detection.py:66-72: one candidate -> `continue`
+                k = min(n_c, P.nms_top_k);
+                if (k == 0) break;                               // (uniform)
+            }
             int run = inc - sum + s_warp[warp], mb = 0;
 #pragma unroll
             for (int q = 0; q < NB / K3_THREADS; ++q) {
@@ -1009,12 +1093,18 @@ k_sort_nms(const SortNmsParams P)
             for (int shift = 56; shift >= 0; shift -= 8) {
                 if (tid < 256) s_hist8[tid] = 0;
                 __syncthreads();
-                for (int base = 0; base < n_c; base += K3_THREADS) {
+                for (int base = 0; base < n_scan; base += K3_THREADS) {
                     int i = base + tid;
                     int d = 256;
-                    if (i < n_c) {
-                        uint64_t key = __ldcg(gkeys + i);
-                        if ((key & pmask) == prefix) d = (int)((key >> shift) & 0xff);
+                    if (i < n_scan) {
+                        uint64_t key;
+                        bool cand = true;
+                        if (FUSED) {
+                            const float sc = __ldg(crow + (int64_t)i * P.C);
+                            cand = sc > cthr;
+                            key = ((uint64_t)fdt_float_key(sc) << 32) | (uint32_t)i;
+                        } else key = __ldcg(gkeys + i);
+                        if (cand && (key & pmask) == prefix) d = (int)((key >> shift) & 0xff);
                     }
                     unsigned peers = __match_any_sync(0xffffffffu, d);
                     if (d < 256 && lane == __ffs(peers) - 1) atomicAdd(&s_hist8[d], __popc(peers));
@@ -1049,12 +1139,19 @@ k_sort_nms(const SortNmsParams P)
             tmin = prefix;                                   // exactly k keys are >= prefix (keys are unique)
         }
         K3_STAMP(1);
+        if (k > 0) {
         // scatter into bucket-contiguous order (arbitrary order inside a bucket)
         for_each_key([&](uint64_t key) {
             if (key >= tmin) {
                 const int bq = bucket(key);
                 const int st = s_start[bq];
                 if (st < k) skeys[st + atomicAdd(&s_hist[bq], 1)] = key;
+                if (MODE == MODE_DETECT && st < WIN && P.loc_prefetch) {
+                    // will be decoded by the first NMS window: start pulling its loc / prior rows into L2 now
+                    const uint32_t pp = (uint32_t)key;
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const float4 *>(P.loc) + ((int64_t)b * P.N + pp)));
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const float4 *>(P.priors) + pp));
+                }
             }
         });
         __syncthreads();
@@ -1078,6 +1175,7 @@ k_sort_nms(const SortNmsParams P)
                     __syncthreads();
                 }
             presorted = true;
+        }
         }
         K3_STAMP(2);
     }
@@ -1406,7 +1504,14 @@ k_sort_nms(const SortNmsParams P)
         K3_ACC(6);
         lo = hi;
     }
-    if (prof) { for (int q = 0; q < 6; ++q) P.prof[5 + q] = pacc[q]; P.prof[16] = pacc[6]; P.prof[12] = nkept; P.prof[13] = k; P.prof[14] = rounds; P.prof[15] = sweeps; }
+    if (prof) {
+        for (int q = 0; q < 6; ++q) atomicAdd((unsigned long long *)&P.prof[5 + q], (unsigned long long)pacc[q]);
+        atomicAdd((unsigned long long *)&P.prof[16], (unsigned long long)pacc[6]);
+        atomicAdd((unsigned long long *)&P.prof[12], (unsigned long long)nkept); atomicAdd((unsigned long long *)&P.prof[13], (unsigned long long)k);
+        atomicAdd((unsigned long long *)&P.prof[14], (unsigned long long)rounds); atomicAdd((unsigned long long *)&P.prof[15], (unsigned long long)sweeps);
+        atomicAdd((unsigned long long *)&P.prof[30], 1ull);
+        atomicAdd((unsigned long long *)&P.prof[31], (unsigned long long)(clock64() - cta_t0));
+    }
 
     // =========================================================== stage 3: outputs
     if (P.prof && tid == 0 && blockIdx.x < 256) { unsigned long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1)); atomicMin((unsigned long long *)&P.prof[40], gt0); atomicMax((unsigned long long *)&P.prof[41], gt0); atomicMin((unsigned long long *)&P.prof[42], gt1); atomicMax((unsigned long long *)&P.prof[43], gt1); P.prof[64 + blockIdx.x] = clock64() - cta_t0; P.prof[320 + blockIdx.x] = (long long)rounds * 100000 + k; }
@@ -1491,7 +1596,9 @@ k_sort_nms(const SortNmsParams P)
         //     cumulative over all rows it has observed through the ticket chain; nobody waits here, the destination's
         //     k_gather_await does;
         //   * publishes done = seq once the previous call has completed (in-order completion, see "call sequencing").
-        __threadfence();
+        // (fused, local output: `done` only has to say that every CTA has reached its end -- grids retire in stream order, and a
+        // call that writes the same buffers again takes the full dependency wait -- so the stores need not be fenced here)
+        if (!FUSED || gather) __threadfence();
         __syncthreads();
         if (tid == 0) {
             const int writers = (int)(gridDim.x / CL);
@@ -1540,7 +1647,7 @@ constexpr int K3_STATIC_SMEM = 2 * 1024;         // small arrays declared __shar
 
 // ---- process-wide options: read from the environment once, overridable through fdt_set_option (tests, tools)
 struct Options {
-    std::atomic<int> k3_profile, k3_cluster, k3_pdl, detect_depth;
+    std::atomic<int> k3_profile, k3_cluster, k3_pdl, detect_depth, detect_fused;
     Options()
     {
         auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e && *e ? atoi(e) : dflt; };
@@ -1548,6 +1655,7 @@ struct Options {
         k3_cluster = env_int("FDT_K3_CLUSTER", -1);          // -1: automatic
         k3_pdl = env_int("FDT_K3_PDL", 1);
         detect_depth = env_int("FDT_DETECT_DEPTH", FDT_DETECT_MAX_DEPTH);
+        detect_fused = env_int("FDT_DETECT_FUSED", 1);
     }
 };
 static Options &options() { static Options o; return o; }
@@ -1590,7 +1698,11 @@ template <int MODE>
 int launch_sort_nms(SortNmsParams &P, int lists, int kcap, void *kept_ws, size_t kept_ws_bytes, cudaStream_t st)
 {
     Options &opt = options();
-    if (opt.k3_profile.load() == 1) {
+    if (opt.k3_profile.load() == 2) {                    // accumulate over launches; cleared by fdt_debug_k3_profile
+        std::lock_guard<std::mutex> g(g_prof_mutex);
+        if (!g_prof_dev) { int rc = prof_arm(st); if (rc != FDT_OK) return rc; FDT_CUDA(cudaStreamSynchronize(st)); }
+        P.prof = g_prof_dev; P.prof_all = 1;
+    } else if (opt.k3_profile.load() == 1) {
         std::lock_guard<std::mutex> g(g_prof_mutex);
         if (!g_prof_armed) { int rc = prof_arm(st); if (rc != FDT_OK) return rc; }
         g_prof_armed = false;
@@ -1619,8 +1731,9 @@ int launch_sort_nms(SortNmsParams &P, int lists, int kcap, void *kept_ws, size_t
     // counts: the cluster repeats every stage but phase B in both CTAs, so it is only used when the workspace has a single slot.
     // Kept rows in global memory (large max_keep) stay on the single-CTA path.
     const int want = opt.k3_cluster.load();
+    const bool fused = MODE == MODE_DETECT && P.conf != nullptr;
     const bool fits = lists * 2 <= FDT_NUM_SMS && sp.off_kbox >= 0;
-    const bool cluster = fits && (want < 0 ? (P.S.ctl == nullptr || P.S.depth == 1) : want == 1);
+    const bool cluster = !fused && fits && (want < 0 ? (P.S.ctl == nullptr || P.S.depth == 1) : want == 1);
     const bool pdl = opt.k3_pdl.load() == 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(lists * (cluster ? 2 : 1))); cfg.blockDim = dim3(K3_THREADS);
@@ -1638,13 +1751,16 @@ int launch_sort_nms(SortNmsParams &P, int lists, int kcap, void *kept_ws, size_t
         ++na;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
-    static FuncAttrCache cache_cl, cache_1;
-    if (cluster) {
-        int rc = ensure_dyn_smem(k_sort_nms<MODE, 2>, cache_cl, sp.total); if (rc != FDT_OK) return rc;
-        FDT_CUDA(cudaLaunchKernelEx(&cfg, k_sort_nms<MODE, 2>, P));
+    static FuncAttrCache cache_cl, cache_1, cache_f;
+    if (fused) {
+        int rc = ensure_dyn_smem(k_sort_nms<MODE_DETECT, 1, true>, cache_f, sp.total); if (rc != FDT_OK) return rc;
+        FDT_CUDA(cudaLaunchKernelEx(&cfg, k_sort_nms<MODE_DETECT, 1, true>, P));
+    } else if (cluster) {
+        int rc = ensure_dyn_smem(k_sort_nms<MODE, 2, false>, cache_cl, sp.total); if (rc != FDT_OK) return rc;
+        FDT_CUDA(cudaLaunchKernelEx(&cfg, k_sort_nms<MODE, 2, false>, P));
     } else {
-        int rc = ensure_dyn_smem(k_sort_nms<MODE, 1>, cache_1, sp.total); if (rc != FDT_OK) return rc;
-        FDT_CUDA(cudaLaunchKernelEx(&cfg, k_sort_nms<MODE, 1>, P));
+        int rc = ensure_dyn_smem(k_sort_nms<MODE, 1, false>, cache_1, sp.total); if (rc != FDT_OK) return rc;
+        FDT_CUDA(cudaLaunchKernelEx(&cfg, k_sort_nms<MODE, 1, false>, P));
     }
     FDT_LAUNCH_CHECK();
     return FDT_OK;
@@ -1715,6 +1831,7 @@ FDT_API int fdt_set_option(const char *name, int value)
     else if (n == "k3_cluster") o.k3_cluster = value;
     else if (n == "k3_pdl") o.k3_pdl = value;
     else if (n == "detect_depth") o.detect_depth = value;
+    else if (n == "detect_fused") o.detect_fused = value;
     else { fdt_set_error("fdt_set_option: unknown option '%s'", name); return FDT_E_INVALID; }
     return FDT_OK;
 }
@@ -1734,14 +1851,15 @@ static int detect_check_common(const char *who, int B, int64_t N, int C, const v
 // them); the stage entry point does not know them and serialises instead.
 static int threshold_compact_impl(const float *conf, const HeadLevels *heads, int B, int64_t N, int C, float conf_thresh,
                                   void *ws, size_t ws_bytes, fdt_stream_t stream,
-                                  const void *out0, const void *out1, const void *out2, int serialize)
+                                  const void *out0, const void *out1, const void *out2, int serialize, bool begin_only = false)
 {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = detect_check_common("fdt_detect_threshold_compact", B, N, C, ws, ws_bytes);
     if (rc != FDT_OK) return rc;
     const int lists = B * (C - 1);
     if (lists == 0 || N == 0) return FDT_OK;
-    FDT_REQUIRE(heads || (conf && fdt_aligned(conf, 8)), FDT_E_INVALID, "fdt_detect_threshold_compact: conf null or not 8-byte aligned");
+    FDT_REQUIRE(heads || (conf && fdt_aligned(conf, 4)), FDT_E_INVALID, "fdt_detect: conf null or not 4-byte aligned");
+    FDT_REQUIRE(heads || begin_only || C != 2 || fdt_aligned(conf, 8), FDT_E_INVALID, "fdt_detect_threshold_compact: conf not 8-byte aligned");
     const DetectWsPlan w = detect_ws_plan(B, N, C);
     const DetectSlots S = detect_slots(ws, ws_bytes, w);
     long long *prof = nullptr;
@@ -1761,6 +1879,7 @@ static int threshold_compact_impl(const float *conf, const HeadLevels *heads, in
                                     (unsigned long long)(uintptr_t)out0, (unsigned long long)(uintptr_t)out1, (unsigned long long)(uintptr_t)out2));
     }
     FDT_LAUNCH_CHECK();
+    if (begin_only) return FDT_OK;             // fused call: k_sort_nms thresholds its own rows
     {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)k2_grid_x(N, heads != nullptr), (unsigned)B);
@@ -1828,7 +1947,8 @@ struct GatherArgs {
 static int detect_sort_nms_impl(const float *loc, const HeadLevels *heads, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
                                 float nms_thresh, float var0, float var1,
                                 float *out, int32_t *counts, int64_t *kept_prior,
-                                const GatherArgs &G, void *ws, size_t ws_bytes, fdt_stream_t stream)
+                                const GatherArgs &G, void *ws, size_t ws_bytes, fdt_stream_t stream,
+                                const float *fused_conf = nullptr, float conf_thresh = 0.0f, unsigned flags = 0)
 {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = detect_check_common("fdt_detect_sort_nms", B, N, C, ws, ws_bytes);
@@ -1854,6 +1974,8 @@ static int detect_sort_nms_impl(const float *loc, const HeadLevels *heads, const
     SortNmsParams P{};
     P.S = detect_slots(ws, ws_bytes, w); P.use_counters = 1; P.key_stride = N; P.k2_blocks = k2_grid_x(N, heads != nullptr) * B;
     P.loc = heads ? nullptr : loc; P.priors = priors; P.N = N; P.C = C;
+    P.loc_prefetch = (!heads && !(flags & FDT_FLAG_LOC_HOST_MAPPED)) ? 1 : 0;
+    P.conf = fused_conf; P.conf_thresh = conf_thresh;
     if (heads) P.hl = *heads;
     P.nms_top_k = nms_top_k; P.max_keep = top_k < nms_top_k ? top_k : nms_top_k; P.top_k = top_k;
     P.nms_thresh = nms_thresh; P.v0 = var0; P.v1 = var1;
@@ -1872,6 +1994,20 @@ FDT_API int fdt_detect_sort_nms(const float *loc, const float *priors, int B, in
 {
     return detect_sort_nms_impl(loc, nullptr, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1, out, counts, kept_prior,
                                 GatherArgs{}, ws, ws_bytes, stream);
+}
+
+// One whole Detect call: sequencing + (K2 +) k_sort_nms.  Plain `conf` input takes the fused kernel (no K2); head maps and
+// fdt_set_option("detect_fused", 0) take K2 + k_sort_nms.
+static int detect_call(const float *loc, const float *conf, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
+                       float conf_thresh, float nms_thresh, float var0, float var1,
+                       float *out, int32_t *counts, int64_t *kept_prior, const GatherArgs &G, const void *alias0,
+                       void *ws, size_t ws_bytes, fdt_stream_t stream, unsigned flags = 0)
+{
+    const bool fused = options().detect_fused.load() == 1;
+    int rc = threshold_compact_impl(conf, nullptr, B, N, C, conf_thresh, ws, ws_bytes, stream, alias0, counts, kept_prior, 0, fused);
+    if (rc != FDT_OK) return rc;
+    return detect_sort_nms_impl(loc, nullptr, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1, out, counts, kept_prior,
+                                G, ws, ws_bytes, stream, fused ? conf : nullptr, conf_thresh, flags);
 }
 
 // Destination side of the signalled gather: ends when every source rank has published `epoch` (its rows of that call have landed in
@@ -1919,10 +2055,8 @@ FDT_API int fdt_detect_peers(const float *loc, const float *conf, const float *p
     FDT_REQUIRE(peer_out_ptrs != nullptr && n_peers >= 1 && image_offset >= 0, FDT_E_INVALID, "fdt_detect_peers: bad peer arguments");
     GatherArgs G;
     G.dest_out = (const unsigned long long *)peer_out_ptrs; G.n_dest = n_peers; G.img_offset = image_offset;
-    int rc = threshold_compact_impl(conf, nullptr, B, N, C, conf_thresh, ws, ws_bytes, stream, peer_out_ptrs, nullptr, nullptr, 0);
-    if (rc != FDT_OK) return rc;
-    return detect_sort_nms_impl(loc, nullptr, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1, nullptr, nullptr, nullptr,
-                                G, ws, ws_bytes, stream);
+    return detect_call(loc, conf, priors, B, N, C, top_k, nms_top_k, conf_thresh, nms_thresh, var0, var1, nullptr, nullptr, nullptr,
+                       G, peer_out_ptrs, ws, ws_bytes, stream);
 }
 
 FDT_API int fdt_detect_gather_signal(const float *loc, const float *conf, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
@@ -1938,13 +2072,21 @@ FDT_API int fdt_detect_gather_signal(const float *loc, const float *conf, const 
     GatherArgs G;
     G.dest_out = (const unsigned long long *)dest_out_ptrs; G.n_dest = n_dest; G.img_offset = image_offset;
     G.peer_sig = (const unsigned long long *)peer_signal_ptrs; G.world = world; G.rank = rank; G.root = root; G.epoch = epoch; G.ring = ring;
-    int rc = threshold_compact_impl(conf, nullptr, B, N, C, conf_thresh, ws, ws_bytes, stream, dest_out_ptrs, nullptr, nullptr, 0);
-    if (rc != FDT_OK) return rc;
-    rc = detect_sort_nms_impl(loc, nullptr, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1, nullptr, nullptr, nullptr,
-                              G, ws, ws_bytes, stream);
+    int rc = detect_call(loc, conf, priors, B, N, C, top_k, nms_top_k, conf_thresh, nms_thresh, var0, var1, nullptr, nullptr, nullptr,
+                         G, dest_out_ptrs, ws, ws_bytes, stream);
     if (rc != FDT_OK) return rc;
     if (root < 0 || root == rank) return fdt_detect_gather_await(peer_signal_ptrs, world, rank, epoch, ws, stream);
     return FDT_OK;
+}
+
+int fdt_detect_flags(const float *loc, const float *conf, const float *priors,
+                     int B, int64_t N, int C, int top_k, int nms_top_k,
+                     float conf_thresh, float nms_thresh, float var0, float var1,
+                     float *out, int32_t *counts, int64_t *kept_prior,
+                     void *ws, size_t ws_bytes, fdt_stream_t stream, unsigned flags)
+{
+    return detect_call(loc, conf, priors, B, N, C, top_k, nms_top_k, conf_thresh, nms_thresh, var0, var1, out, counts, kept_prior,
+                       GatherArgs{}, out, ws, ws_bytes, stream, flags);
 }
 
 FDT_API int fdt_detect(const float *loc, const float *conf, const float *priors,
@@ -1953,10 +2095,8 @@ FDT_API int fdt_detect(const float *loc, const float *conf, const float *priors,
                        float *out, int32_t *counts, int64_t *kept_prior,
                        void *ws, size_t ws_bytes, fdt_stream_t stream)
 {
-    int rc = threshold_compact_impl(conf, nullptr, B, N, C, conf_thresh, ws, ws_bytes, stream, out, counts, kept_prior, 0);
-    if (rc != FDT_OK) return rc;
-    return fdt_detect_sort_nms(loc, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1,
-                               out, counts, kept_prior, ws, ws_bytes, stream);
+    return fdt_detect_flags(loc, conf, priors, B, N, C, top_k, nms_top_k, conf_thresh, nms_thresh, var0, var1, out, counts, kept_prior,
+                            ws, ws_bytes, stream, 0);
 }
 
 // ---- head maps -> Detect (pyramid.py:291-309, 331-338)
@@ -2032,6 +2172,7 @@ FDT_API int fdt_debug_k3_profile(long long *out640_h /* 1024 entries */)
     FDT_REQUIRE(g_prof_dev != nullptr, FDT_E_INVALID, "fdt_debug_k3_profile: run with FDT_K3_PROFILE=1 first");
     FDT_CUDA(cudaDeviceSynchronize());
     FDT_CUDA(cudaMemcpy(out640_h, g_prof_dev, 1024 * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (options().k3_profile.load() == 2) { int rc = prof_arm(nullptr); if (rc != FDT_OK) return rc; FDT_CUDA(cudaDeviceSynchronize()); }
     return FDT_OK;
 }
 

@@ -9,6 +9,12 @@
 
 void fdt_set_error(const char *fmt, ...);
 
+// library-internal form of fdt_detect (hostctx.cu): `loc` may be a device view of pinned HOST memory that k_sort_nms gathers in place
+constexpr unsigned FDT_FLAG_LOC_HOST_MAPPED = 1u;
+int fdt_detect_flags(const float *loc, const float *conf, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
+                     float conf_thresh, float nms_thresh, float var0, float var1, float *out, int32_t *counts, int64_t *kept_prior,
+                     void *ws, size_t ws_bytes, void *stream, unsigned flags);
+
 #define FDT_CUDA(expr)                                                                            \
     do {                                                                                          \
         cudaError_t e_ = (expr);                                                                  \

@@ -99,8 +99,9 @@ FDT_API int fdt_detect_host(fdt_ctx *c, const float *loc_h, const float *conf_h,
     FDT_CUDA(cudaMemcpyAsync(d_conf, conf_h, (size_t)B * N * C * 4, cudaMemcpyHostToDevice, st));
     FDT_CUDA(cudaMemcpyAsync(d_pri, priors_h, (size_t)N * 16, cudaMemcpyHostToDevice, st));
     if (!loc_dev_view) FDT_CUDA(cudaMemcpyAsync((void *)d_loc, loc_h, (size_t)B * N * 16, cudaMemcpyHostToDevice, st));
-    rc = fdt_detect(d_loc, d_conf, d_pri, B, N, C, top_k, nms_top_k, conf_thresh, nms_thresh, var0, var1,
-                    d_out, counts_h ? d_cnt : nullptr, kept_prior_h ? d_kept : nullptr, d_ws, sz_ws, st);
+    rc = fdt_detect_flags(d_loc, d_conf, d_pri, B, N, C, top_k, nms_top_k, conf_thresh, nms_thresh, var0, var1,
+                          d_out, counts_h ? d_cnt : nullptr, kept_prior_h ? d_kept : nullptr, d_ws, sz_ws, st,
+                          loc_dev_view ? FDT_FLAG_LOC_HOST_MAPPED : 0u);
     if (rc != FDT_OK) return rc;
     if (!out_dev_view) FDT_CUDA(cudaMemcpyAsync(out_h, d_out, (size_t)B * C * top_k * 20, cudaMemcpyDeviceToHost, st));
     if (counts_h) FDT_CUDA(cudaMemcpyAsync(counts_h, d_cnt, (size_t)B * C * 4, cudaMemcpyDeviceToHost, st));

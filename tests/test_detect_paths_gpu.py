@@ -31,6 +31,7 @@ def lib():
     yield _lib
     _lib.set_option("k3_cluster", -1)
     _lib.set_option("detect_depth", 4)
+    _lib.set_option("detect_fused", 1)
 
 
 def c_detect(_lib, l, c, p, ws, out, counts=None, kept=None, top_k=750, nms_top_k=5000, conf_t=0.05, nms_t=0.3):
@@ -50,11 +51,22 @@ def status(_lib, ws):
 
 
 # ------------------------------------------------------------------------------- both instantiations of k_sort_nms<MODE_DETECT>
-@pytest.mark.parametrize("cluster", [0, 1])
-@pytest.mark.parametrize("mode", ["random", "clustered"])
-def test_headline_batch_on_both_kernel_variants(lib, cluster, mode):
-    """B=64 @640x640 (BASELINE config 2) forced onto k_sort_nms<DETECT,1> (one CTA per list) and <DETECT,2> (cluster)."""
+VARIANTS = {"fused": (1, -1), "k2+single": (0, 0), "k2+cluster": (0, 1)}      # (detect_fused, k3_cluster)
+
+
+def set_variant(lib, variant):
+    fused, cluster = VARIANTS[variant]
+    lib.set_option("detect_fused", fused)
     lib.set_option("k3_cluster", cluster)
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("mode", ["random", "clustered"])
+def test_headline_batch_on_every_kernel_variant(lib, variant, mode):
+    """B=64 @640x640 (BASELINE config 2) on the fused kernel (thresholds its own rows, the default), and on K2 followed by
+    k_sort_nms<DETECT,1> (one CTA per list) and <DETECT,2> (2-CTA cluster)."""
+    set_variant(lib, variant)
+    cluster = variant
     pri = synth.priors_numpy(640, 640)
     loc, conf = synth.detect_inputs(64, pri, 20262, 0.05, mode)
     ref = oracle_detect(loc, conf, pri)
@@ -98,11 +110,11 @@ def test_config5_shape_more_images_than_sms(lib):
 
 # ------------------------------------------------------------------------------- overlapped calls (workspace ring)
 @pytest.mark.parametrize("depth", [1, 2, 3, 4])
-@pytest.mark.parametrize("cluster", [-1, 1])
-def test_back_to_back_calls_overlap_and_stay_exact(lib, depth, cluster):
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_back_to_back_calls_overlap_and_stay_exact(lib, depth, variant):
     """16 calls issued back to back on one stream over different batches: with depth >= 2 they overlap on the device; every
     output must equal the oracle's, whether each call has its own output buffer or all share one (then the calls take turns)."""
-    lib.set_option("k3_cluster", cluster)
+    set_variant(lib, variant)
     pri = synth.priors_numpy(640, 640)
     N = pri.shape[0]
     n_sets, B = 4, 8
@@ -134,9 +146,9 @@ def test_back_to_back_calls_overlap_and_stay_exact(lib, depth, cluster):
 
 
 def test_inputs_produced_on_stream_between_overlapped_calls(lib):
-    """Each call's conf / loc are written by ordinary kernels enqueued right before it, into buffers the previous call may still
-    be reading ... no: into fresh buffers; and each output is consumed by an ordinary kernel right after.  The producer must be
-    complete before K2 reads, the consumer must see the finished rows, while the calls themselves overlap where they can."""
+    """Each call's conf / loc are written by ordinary kernels enqueued right before it (into one of four staging buffers) and each
+    output is consumed by an ordinary kernel right after.  The producers must be complete before the call reads its inputs and
+    the consumer must see the finished rows, while the calls themselves overlap where they can."""
     pri = synth.priors_numpy(640, 480)
     N = pri.shape[0]
     B = 6
@@ -231,3 +243,68 @@ def test_output_rows_at_every_alignment(lib, top_k, nms_top_k, shift):
     got = buf.cpu().numpy()
     assert np.array_equal(got[4 + shift: 4 + shift + n].reshape(ref.shape), ref)
     assert np.all(got[:4 + shift] == -7.0) and np.all(got[4 + shift + n:] == -7.0)
+
+
+# ------------------------------------------------------------------------------- fused kernel: score distributions and class counts
+@pytest.mark.parametrize("variant", ["fused", "k2+single"])
+@pytest.mark.parametrize("dist", ["ties", "tiny-range", "above-one", "negative-thresh", "nan-inf"])
+def test_degenerate_score_distributions(lib, variant, dist):
+    """The fused kernel buckets scores over the a-priori range (conf_thresh, 1]; everything that defeats the bucket map (thousands
+    of equal scores, all scores within a few ulps, scores above 1, a negative threshold, NaN / inf scores) must fall back to the
+    exact selection paths and still equal the oracle."""
+    set_variant(lib, variant)
+    pri = synth.priors_numpy(640, 480)
+    N = pri.shape[0]
+    B = 3
+    rng = np.random.Generator(np.random.PCG64(77))
+    loc, conf = synth.detect_inputs(B, pri, 500, 0.05)
+    thr = 0.05
+    s = conf[..., 1].copy()
+    if dist == "ties":
+        s[0, rng.permutation(N)[:9000]] = np.float32(0.7)          # 9,000 equal scores straddle rank nms_top_k
+        s[1, :] = np.float32(0.25)                                 # every prior a candidate, all tied
+    elif dist == "tiny-range":
+        base = np.float32(0.3)
+        s[:] = base + (rng.integers(0, 7, s.shape) * np.spacing(base)).astype(np.float32)
+    elif dist == "above-one":
+        s[0, ::3] = rng.uniform(1.0, 50.0, s[0, ::3].shape).astype(np.float32)
+        s[1, ::5] = np.float32(1.0)
+    elif dist == "negative-thresh":
+        thr = -0.5
+        s[:] = rng.uniform(-1.0, 1.0, s.shape).astype(np.float32)
+    elif dist == "nan-inf":
+        s[0, ::7] = np.nan; s[0, 1::7] = np.inf; s[1, ::9] = -np.inf; s[2, 5] = np.inf
+    conf = np.stack([1 - s, s], -1).astype(np.float32)
+    args = (2, 0, 750, thr, 0.3)
+    ref = oracle_detect(loc, conf, pri, args)
+    ws = new_ws(lib, B, N, 2, 2)
+    out = torch.empty((B, 2, 750, 5), device="cuda")
+    counts = torch.empty((B, 2), dtype=torch.int32, device="cuda")
+    kept = torch.empty((B, 2, 750), dtype=torch.int64, device="cuda")
+    c_detect(lib, cu(loc), cu(conf), cu(pri), ws, out, counts, kept, conf_t=thr)
+    for got, want, name in zip((out, counts, kept), ref, ("out", "counts", "kept_prior")):
+        assert np.array_equal(got.cpu().numpy(), want, equal_nan=True), f"{name} differs ({dist}, {variant})"
+
+
+@pytest.mark.parametrize("variant", ["fused", "k2+single"])
+def test_four_classes_and_quirk_lists(lib, variant):
+    """C = 4: three lists per image read with stride C; lists with zero and with exactly one candidate (detection.py:66-72)."""
+    set_variant(lib, variant)
+    pri = synth.priors_numpy(320, 320)
+    N = pri.shape[0]
+    rng = np.random.Generator(np.random.PCG64(5))
+    loc = (rng.standard_normal((3, N, 4)) * 0.5).astype(np.float32)
+    logits = rng.standard_normal((3, N, 4)) * 2 + np.array([3.0, 0, 0, -1.0])
+    conf = np.exp(logits); conf = (conf / conf.sum(-1, keepdims=True)).astype(np.float32)
+    conf[1, :, 2] = 0.01; conf[1, 123, 2] = 0.8            # exactly one candidate
+    conf[2, :, 3] = 0.0                                     # none
+    args = (4, 0, 100, 0.1, 0.4)
+    ref = oracle_detect(loc, conf, pri, args)
+    ws = new_ws(lib, 3, N, 4, 3)
+    out = torch.empty((3, 4, 100, 5), device="cuda")
+    counts = torch.empty((3, 4), dtype=torch.int32, device="cuda")
+    kept = torch.empty((3, 4, 100), dtype=torch.int64, device="cuda")
+    c_detect(lib, cu(loc), cu(conf), cu(pri), ws, out, counts, kept, top_k=100, conf_t=0.1, nms_t=0.4)
+    for got, want, name in zip((out, counts, kept), ref, ("out", "counts", "kept_prior")):
+        assert np.array_equal(got.cpu().numpy(), want), name
+    assert counts[1, 2].item() == 0 and counts[2, 3].item() == 0
