@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(CSRC, "libfdt_b200.so")
+SO_PATH = os.environ.get("FDT_B200_LIB") or os.path.join(CSRC, "libfdt_b200.so")      # (override: experiments with build variants)
 
 FDT_OK, FDT_E_INVALID, FDT_E_CUDA, FDT_E_WORKSPACE, FDT_E_UNSUPPORTED, FDT_E_DEVICE = 0, -1, -2, -3, -4, -5
 MAX_NMS_TOP_K = 8000
@@ -153,7 +153,7 @@ def workspace(nbytes: int, device: torch.device, tag: str = "") -> torch.Tensor:
     return ws
 
 
-DETECT_DEPTH = int(os.environ.get("FDT_DETECT_DEPTH", "3"))          # workspace slots: how many calls may overlap on the device
+DETECT_DEPTH = int(os.environ.get("FDT_DETECT_DEPTH", "4"))          # workspace slots: how many calls may overlap on the device
 DETECT_WS_BUDGET = 2 << 30                                             # do not spend more than this on one Detect workspace
 
 

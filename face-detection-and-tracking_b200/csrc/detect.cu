@@ -402,8 +402,11 @@ k_heads_threshold_compact(const HeadLevels hl, const int64_t N, const float thr,
 }
 
 // SRC 0: conf[B,N,C] with C > 2; 1: conf[B,N,2]
+#ifndef FDT_K2_MINBLOCKS
+#define FDT_K2_MINBLOCKS 6
+#endif
 template <int SRC>
-__global__ void __launch_bounds__(K2_THREADS)
+__global__ void __launch_bounds__(K2_THREADS, FDT_K2_MINBLOCKS)
 k_threshold_compact(const float *__restrict__ conf, const HeadLevels hl, int64_t N, int C, float thr,
                     const DetectSlots S, long long *prof)
 {
@@ -816,8 +819,16 @@ __device__ __forceinline__ void csr_scan(int *a, int *s_warp)
 // one pass for the bucket histogram (which also counts the candidates), one for the scatter (served by L2), the rare exact
 // fallbacks re-scan the row.  With consecutive calls overlapping on the device what counts is SM time, not latency: the ~1,350
 // SM-microseconds per B = 64 call that a separate K2 grid and the hand-over to this kernel cost shrink to the two row scans.
+#ifndef FDT_K3_MAXREG
+#define FDT_K3_MAXREG 64
+#endif
+#if FDT_K3_MAXREG < 64
+#define K3_BOUNDS __maxnreg__(FDT_K3_MAXREG)
+#else
+#define K3_BOUNDS __launch_bounds__(K3_THREADS, 1)
+#endif
 template <int MODE, int CL, bool FUSED>
-__global__ void __launch_bounds__(K3_THREADS, 1)
+__global__ void K3_BOUNDS
 k_sort_nms(const SortNmsParams P)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -969,51 +980,61 @@ k_sort_nms(const SortNmsParams P)
         // atomics of the sparse form the most expensive part of the kernel).  What does not fit -- a warp with more than WQ_CAP
         // candidates, rows longer than U x 1024 -- is visited in place on every pass: the scores of the first round stay in registers,
         // later rounds are re-read (L2).
-        constexpr int U = FUSED ? 34 : 1;
+        constexpr int U = FUSED ? 34 : 2;
         constexpr int WQ_CAP = (SM_WSTART - SM_SEGS) / 8 / (K3_THREADS / 32);          // 288 keys per warp
-        float sv[U];
-        int wq_n = 0, u_split = U;                           // warp-uniform: queue length; first u that did not fit any more
-        bool sv_loaded = false;
+        int wq_n = 0;                                        // warp-uniform: queue length
+        bool scanned = false, wq_ovf = false;                // wq_ovf: the warp's candidates did not fit, it visits its priors in place
         uint64_t *wq = reinterpret_cast<uint64_t *>(smem + SM_SEGS) + warp * WQ_CAP;
+        const int Nn = (int)P.N, Cc = P.C;
+        auto key_of = [&](const float sc, const int i) -> uint64_t { return ((uint64_t)fdt_float_key(sc) << 32) | (uint32_t)i; };
         auto for_each_key = [&](auto &&body) {
             if (FUSED) {
-                const int Nn = (int)P.N, Cc = P.C;
-                auto key_of = [&](const float sc, const int i) -> uint64_t { return ((uint64_t)fdt_float_key(sc) << 32) | (uint32_t)i; };
-                if (!sv_loaded) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int i = tid + u * K3_THREADS;
-                        sv[u] = i < Nn ? __ldg(crow + (int64_t)i * Cc) : __int_as_float(0x7fc00000);     // NaN: never a candidate
-                    }
+                if (!scanned) {
+                    scanned = true;
+                    // ballot compaction into the warp's queue; positions beyond the queue collapse onto its last entry and the
+                    // warp then visits ALL its priors in place on every pass: no bookkeeping inside the loop.  Two half rounds of
+                    // 17 loads per thread in flight (the registers of 34 would spill).
+                    constexpr int UH = U / 2;
+                    const float qnan = __int_as_float(0x7fc00000);                          // never a candidate
+                    const unsigned lt = (1u << lane) - 1u;
+                    const uint32_t qaddr = (uint32_t)__cvta_generic_to_shared(wq);
                     int run = 0;
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const bool c = sv[u] > cthr;                                         // detection.py:64 strict gt
-                        const unsigned bal = __ballot_sync(0xffffffffu, c);
-                        const int cnt = __popc(bal);
-                        if (u_split == U) {
-                            if (run + cnt <= WQ_CAP) {
-                                if (c) wq[run + __popc(bal & ((1u << lane) - 1u))] = key_of(sv[u], tid + u * K3_THREADS);
-                                run += cnt;
-                            } else u_split = u;
+                    for (int h = 0; h < 2; ++h) {
+                        float sv[UH];
+                        const int i0 = tid + h * UH * K3_THREADS;
+                        if (Cc == 2) {                                                       // (addresses fold into the load immediates)
+                            const float *p0 = crow + 2 * i0;
+#pragma unroll
+                            for (int u = 0; u < UH; ++u) sv[u] = i0 + u * K3_THREADS < Nn ? __ldg(p0 + 2 * u * K3_THREADS) : qnan;
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < UH; ++u) {
+                                const int i = i0 + u * K3_THREADS;
+                                sv[u] = i < Nn ? __ldg(crow + (int64_t)i * Cc) : qnan;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < UH; ++u) {
+                            const bool c = sv[u] > cthr;                                     // detection.py:64 strict gt
+                            const unsigned bal = __ballot_sync(0xffffffffu, c);
+                            if (c) {
+                                const int idx = min(run + __popc(bal & lt), WQ_CAP - 1);
+                                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(qaddr + 8u * (uint32_t)idx), "r"((uint32_t)(i0 + u * K3_THREADS)),
+                                             "r"(fdt_float_key(sv[u])) : "memory");
+                            }
+                            run += __popc(bal);
                         }
                     }
-                    wq_n = run;
-                    sv_loaded = true;
+                    wq_ovf = run > WQ_CAP;
+                    wq_n = wq_ovf ? 0 : run;
                     __syncwarp();
                 }
                 for (int e = lane; e < wq_n; e += 32) body(wq[e]);
-                if (u_split < U) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        if (u >= u_split && sv[u] > cthr) body(key_of(sv[u], tid + u * K3_THREADS));
-                }
-                for (int base = U * K3_THREADS + tid; base < Nn; base += 8 * K3_THREADS) {
-                    float tv[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) { const int i = base + u * K3_THREADS; tv[u] = i < Nn ? __ldg(crow + (int64_t)i * Cc) : __int_as_float(0x7fc00000); }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) if (tv[u] > cthr) body(key_of(tv[u], base + u * K3_THREADS));
+                // in place (re-read, L2): the whole first round of a warp whose queue overflowed, and every prior beyond it
+                for (int i = (wq_ovf ? 0 : U * K3_THREADS) + tid; i < Nn; i += K3_THREADS) {
+                    const float sc = __ldg(crow + (int64_t)i * Cc);
+                    if (sc > cthr) body(key_of(sc, i));
                 }
             } else if (cached) {
 #pragma unroll
@@ -1364,7 +1385,9 @@ k_sort_nms(const SortNmsParams P)
                 const float4 cb = sbox[tc], bo = sbox[t2];
                 const float ca = sarea[tc], ao = sarea[t2];
                 const bool me_first = cid < other;           // window index = score order
-                const bool sup = me_first ? suppresses(cb, ca, bo, ao) : suppresses(bo, ao, cb, ca);
+                // the intersection is symmetric in the two boxes (max / min commute bit for bit); only the union's operand order
+                // depends on which box is the kept one: one evaluation with the areas swapped instead of two divergent ones
+                const bool sup = suppresses(cb, me_first ? ca : ao, bo, me_first ? ao : ca);
                 if (sup) {
                     const int later = me_first ? other : cid, earlier = me_first ? cid : other;
                     const int sl = atomicAdd(&sndep[later], 1);
@@ -1655,7 +1678,7 @@ struct Options {
         k3_cluster = env_int("FDT_K3_CLUSTER", -1);          // -1: automatic
         k3_pdl = env_int("FDT_K3_PDL", 1);
         detect_depth = env_int("FDT_DETECT_DEPTH", FDT_DETECT_MAX_DEPTH);
-        detect_fused = env_int("FDT_DETECT_FUSED", 1);
+        detect_fused = env_int("FDT_DETECT_FUSED", -1);      // -1: automatic
     }
 };
 static Options &options() { static Options o; return o; }
@@ -2003,7 +2026,11 @@ static int detect_call(const float *loc, const float *conf, const float *priors,
                        float *out, int32_t *counts, int64_t *kept_prior, const GatherArgs &G, const void *alias0,
                        void *ws, size_t ws_bytes, fdt_stream_t stream, unsigned flags = 0)
 {
-    const bool fused = options().detect_fused.load() == 1;
+    // Fused pays when one wave of CTAs holds every list (what counts then is SM time per list, and consecutive calls fill the
+    // other SMs); with several waves of lists the chip-wide K2 streams conf at a higher rate than 148 CTAs scanning their own rows,
+    // and rows much longer than the per-warp candidate queues (34 x 1024 priors per round) would mostly be visited in place.
+    const int want = options().detect_fused.load();
+    const bool fused = want < 0 ? ((int64_t)B * (C - 1) <= FDT_NUM_SMS && N <= 40960) : want == 1;
     int rc = threshold_compact_impl(conf, nullptr, B, N, C, conf_thresh, ws, ws_bytes, stream, alias0, counts, kept_prior, 0, fused);
     if (rc != FDT_OK) return rc;
     return detect_sort_nms_impl(loc, nullptr, priors, B, N, C, top_k, nms_top_k, nms_thresh, var0, var1, out, counts, kept_prior,

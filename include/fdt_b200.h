@@ -149,7 +149,8 @@ size_t fdt_detect_workspace_bytes_depth(int B, int64_t N, int C, int depth);
 /* FDT_STATUS_* bits of the workspace (0 = fine); synchronises `stream`. */
 int fdt_detect_status(const void *ws, fdt_stream_t stream, uint32_t *status_h);
 /* Process-wide tuning / diagnostic switches (defaults come from the environment variables FDT_K3_PROFILE, FDT_K3_CLUSTER,
- * FDT_K3_PDL, FDT_DETECT_DEPTH, read once): "k3_profile" 0/1, "k3_cluster" -1 auto / 0 / 1, "k3_pdl" 0/1, "detect_depth" 1..4. */
+ * FDT_K3_PDL, FDT_DETECT_DEPTH, FDT_DETECT_FUSED, read once): "k3_profile" 0/1/2, "k3_cluster" -1 auto / 0 / 1, "k3_pdl" 0/1,
+ * "detect_depth" 1..4, "detect_fused" -1 auto / 0 / 1 (1: k_sort_nms thresholds its own conf rows, no separate threshold grid). */
 int fdt_set_option(const char *name, int value);
 
 /* Stage entry points (same workspace, same semantics; fdt_detect == stage 1 then stage 2).  They let

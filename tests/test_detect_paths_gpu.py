@@ -31,7 +31,7 @@ def lib():
     yield _lib
     _lib.set_option("k3_cluster", -1)
     _lib.set_option("detect_depth", 4)
-    _lib.set_option("detect_fused", 1)
+    _lib.set_option("detect_fused", -1)
 
 
 def c_detect(_lib, l, c, p, ws, out, counts=None, kept=None, top_k=750, nms_top_k=5000, conf_t=0.05, nms_t=0.3):
