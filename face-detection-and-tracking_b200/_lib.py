@@ -34,12 +34,16 @@ SIGNATURES = {
     "fdt_calculate_distance_f64": (_i, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "fdt_calc_pr": (_i, [_vp, _i64, _i, _vp, _i64, _d, _vp, _vp]),
     "fdt_detections_to_rows": (_i, [_vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp]),
+    "fdt_detections_to_frames_count": (_i, [_vp, _i64, _i, _i, _f, _vp, _vp, _vp]),
+    "fdt_detections_to_frames_pack": (_i, [_vp, _i64, _i, _i, _f, _f, _f, _d, _vp, _vp, _vp]),
     "fdt_encode": (_i, [_vp, _vp, _i64, _f, _f, _vp, _vp]),
     "fdt_decode": (_i, [_vp, _vp, _i64, _f, _f, _vp, _vp]),
     "fdt_log_sum_exp": (_i, [_vp, _i64, _i, _vp, _vp, _sz, _vp]),
     "fdt_nms_workspace_bytes": (_sz, [_i64]),
     "fdt_nms": (_i, [_vp, _vp, _i64, _f, _i64, _vp, _vp, _vp, _sz, _vp]),
     "fdt_nms_variant": (_i, [_vp, _vp, _i64, _f, _i, _vp, _vp, _vp, _sz, _vp]),
+    "fdt_nms_f64_workspace_bytes": (_sz, [_i64]),
+    "fdt_nms_variant_f64": (_i, [_vp, _vp, _i64, _d, _i, _vp, _vp, _vp, _sz, _vp]),
     "fdt_facebox_decode": (_i, [_vp, _vp, _i64, _f, _f, _vp, _vp]),
     "fdt_threshold_nms_workspace_bytes": (_sz, [_i64]),
     "fdt_threshold_nms": (_i, [_vp, _vp, _i64, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),
@@ -69,8 +73,10 @@ SIGNATURES = {
     "fdt_multibox_loss_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i64, _i, _f, _i, _i, _f, _f,
                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fdt_multibox_loss_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i64, _i, _vp, _vp, _vp]),
+    "fdt_multibox_loss_backward_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp]),
     "fdt_iou_track_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "fdt_iou_track": (_i, [_vp, _vp, _i64, _i64, _i64, _d, _d, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "fdt_iou_track_metric": (_i, [_vp, _vp, _i64, _i64, _i64, _i, _d, _d, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -153,6 +153,83 @@ __global__ void k_detections_to_rows(const float *__restrict__ det, int C, int t
     if (tid == 0) n_rows[b] = s_base;
 }
 
+// Detect -> tracker without leaving the device (iouTracke_cal.py:55-84 detect_face, one image per frame): the rows of
+// k_detections_to_rows divided by `shrink` (:76-80, float32) and widened to float64, frames packed back to back; a frame without a
+// detection becomes the reference's dummy row [0, 0, 0, 0, 0.4] (:73-74).  Two passes: counts -> offsets, then the rows.
+__device__ __forceinline__ int leading_rows(const float *__restrict__ plane, const int top_k, const float thr, int *s_len)
+{
+    if (threadIdx.x == 0) *s_len = top_k;
+    __syncthreads();
+    for (int j = threadIdx.x; j < top_k; j += blockDim.x)
+        if (!(plane[5 * j] >= thr)) atomicMin(s_len, j);                      // first row that fails `>= thr` (NaN fails)
+    __syncthreads();
+    const int len = *s_len;
+    __syncthreads();
+    return len;
+}
+__global__ void k_frames_count(const float *__restrict__ det, int C, int top_k, float thr, int32_t *__restrict__ n_rows)
+{
+    __shared__ int s_len;
+    const int f = blockIdx.x;
+    int n = 0;
+    for (int i = 0; i < C; ++i) n += leading_rows(det + ((int64_t)(f * C + i) * top_k) * 5, top_k, thr, &s_len);
+    if (threadIdx.x == 0) n_rows[f] = n;
+}
+// frame_off[0] = 0, frame_off[f + 1] = frame_off[f] + max(n_rows[f], 1)   (one block; F in chunks of blockDim)
+__global__ void k_frames_offsets(const int32_t *__restrict__ n_rows, int64_t F, int64_t *__restrict__ frame_off)
+{
+    __shared__ long long s_warp[33];
+    __shared__ long long s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) { s_carry = 0; frame_off[0] = 0; }
+    __syncthreads();
+    for (int64_t base = 0; base < F; base += blockDim.x) {
+        const int64_t f = base + threadIdx.x;
+        long long v = 0;
+        if (f < F) { const int n = n_rows[f]; v = n > 0 ? n : 1; }
+        long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = lane < nw ? s_warp[lane] : 0, winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+            s_warp[lane] = winc - w;
+            if (lane == 31) s_warp[32] = winc;
+        }
+        __syncthreads();
+        if (f < F) frame_off[f + 1] = s_carry + s_warp[warp] + inc;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += s_warp[32];
+        __syncthreads();
+    }
+}
+__global__ void k_frames_pack(const float *__restrict__ det, int C, int top_k, float thr, float width, float height, double shrink,
+                              const int64_t *__restrict__ frame_off, double *__restrict__ dets)
+{
+    __shared__ int s_len;
+    const int f = blockIdx.x;
+    double *out = dets + 5 * frame_off[f];
+    int base = 0;
+    for (int i = 0; i < C; ++i) {
+        const float *plane = det + ((int64_t)(f * C + i) * top_k) * 5;
+        const int len = leading_rows(plane, top_k, thr, &s_len);
+        for (int j = threadIdx.x; j < len; j += blockDim.x) {
+            const float *r = plane + 5 * j;
+            double *o = out + 5 * (base + j);
+            // pt = detections[...] * scale in fp32 (:64); np.array keeps float32 and `/ shrink` divides in float32 (:76-79, a python
+            // scalar does not promote); det0.tolist() then widens exactly (:127).  The score is a float32 too (:70).
+            const float sh = (float)shrink;
+            o[0] = (double)((r[1] * width) / sh); o[1] = (double)((r[2] * height) / sh);
+            o[2] = (double)((r[3] * width) / sh); o[3] = (double)((r[4] * height) / sh); o[4] = (double)r[0];
+        }
+        base += len;
+    }
+    if (base == 0 && threadIdx.x == 0) { out[0] = 0.0; out[1] = 0.0; out[2] = 0.0; out[3] = 0.0; out[4] = 0.4; }     // :73-74
+}
+
 // box_utils.py:261-269: global max, then log(sum(exp(x - max))) + max per row
 __global__ void k_global_max(const float *__restrict__ x, int64_t n, unsigned *__restrict__ gmax_key)
 {
@@ -283,6 +360,31 @@ FDT_API int fdt_detections_to_rows(const float *detections, int B, int C, int to
     if (B == 0) return FDT_OK;
     FDT_REQUIRE(detections && rows_out && n_rows, FDT_E_INVALID, "fdt_detections_to_rows: null pointer");
     k_detections_to_rows<<<B, 256, 0, (cudaStream_t)stream>>>(detections, C, top_k, thresh, width, height, rows_out, n_rows);
+    FDT_LAUNCH_CHECK();
+    return FDT_OK;
+}
+
+FDT_API int fdt_detections_to_frames_count(const float *detections, int64_t F, int C, int top_k, float thresh,
+                                           int32_t *n_rows, int64_t *frame_off, fdt_stream_t stream)
+{
+    FDT_REQUIRE(F >= 0 && F < (1ll << 31) && C >= 1 && top_k >= 1, FDT_E_INVALID, "fdt_detections_to_frames_count: bad sizes");
+    FDT_REQUIRE(frame_off != nullptr, FDT_E_INVALID, "fdt_detections_to_frames_count: frame_off is null");
+    if (F == 0) { FDT_CUDA(cudaMemsetAsync(frame_off, 0, sizeof(int64_t), (cudaStream_t)stream)); return FDT_OK; }
+    FDT_REQUIRE(detections && n_rows, FDT_E_INVALID, "fdt_detections_to_frames_count: null pointer");
+    k_frames_count<<<(unsigned)F, 128, 0, (cudaStream_t)stream>>>(detections, C, top_k, thresh, n_rows);
+    FDT_LAUNCH_CHECK();
+    k_frames_offsets<<<1, 1024, 0, (cudaStream_t)stream>>>(n_rows, F, frame_off);
+    FDT_LAUNCH_CHECK();
+    return FDT_OK;
+}
+
+FDT_API int fdt_detections_to_frames_pack(const float *detections, int64_t F, int C, int top_k, float thresh, float width, float height,
+                                          double shrink, const int64_t *frame_off, double *dets_out, fdt_stream_t stream)
+{
+    FDT_REQUIRE(F >= 0 && F < (1ll << 31) && C >= 1 && top_k >= 1, FDT_E_INVALID, "fdt_detections_to_frames_pack: bad sizes");
+    if (F == 0) return FDT_OK;
+    FDT_REQUIRE(detections && frame_off && dets_out, FDT_E_INVALID, "fdt_detections_to_frames_pack: null pointer");
+    k_frames_pack<<<(unsigned)F, 128, 0, (cudaStream_t)stream>>>(detections, C, top_k, thresh, width, height, shrink, frame_off, dets_out);
     FDT_LAUNCH_CHECK();
     return FDT_OK;
 }

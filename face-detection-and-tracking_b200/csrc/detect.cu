@@ -2207,7 +2207,12 @@ FDT_API size_t fdt_nms_workspace_bytes(int64_t n)
 {
     size_t nn = (size_t)(n > 0 ? n : 1);
     size_t kept_rows = nn < FDT_MAX_NMS_TOP_K ? nn : FDT_MAX_NMS_TOP_K;
-    return fdt_align256(nn * sizeof(uint64_t)) + fdt_align256(kept_rows * KEPT_ROW_BYTES);
+    size_t own = fdt_align256(nn * sizeof(uint64_t)) + fdt_align256(kept_rows * KEPT_ROW_BYTES);
+    if (n > FDT_MAX_NMS_TOP_K) {                  // more candidates than k_sort_nms holds may enter: the mask formulation (nms_generic.cu)
+        const size_t gen = fdt_nms_generic_workspace_bytes(n);
+        if (gen > own) own = gen;
+    }
+    return own;
 }
 
 static int nms_impl(const float *boxes, const float *scores, int64_t n, float overlap, int64_t top_k, int variant,
@@ -2221,7 +2226,8 @@ static int nms_impl(const float *boxes, const float *scores, int64_t n, float ov
     FDT_REQUIRE(fdt_aligned(boxes, 16) && fdt_aligned(ws, 256), FDT_E_INVALID, "fdt_nms: boxes need 16-byte, workspace 256-byte alignment");
     FDT_REQUIRE(ws_bytes >= fdt_nms_workspace_bytes(n), FDT_E_WORKSPACE, "fdt_nms: workspace %zu < %zu bytes", ws_bytes, fdt_nms_workspace_bytes(n));
     int64_t k = (top_k <= 0 || top_k > n) ? n : top_k;         // idx[-top_k:]; idx[-0:] is the whole list
-    FDT_REQUIRE(k <= FDT_MAX_NMS_TOP_K, FDT_E_UNSUPPORTED, "fdt_nms: min(n, top_k)=%lld exceeds %d", (long long)k, FDT_MAX_NMS_TOP_K);
+    if (k > FDT_MAX_NMS_TOP_K)                                 // box_utils.nms has no cap (:296-298): sort + pairwise mask + reduce, any n
+        return fdt_nms_generic<float>(boxes, scores, n, overlap, top_k, variant, keep, count, ws, ws_bytes, st);
     uint64_t *keys = (uint64_t *)ws;
     k_build_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scores, n, keys);
     FDT_LAUNCH_CHECK();

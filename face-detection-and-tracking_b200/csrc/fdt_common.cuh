@@ -15,6 +15,13 @@ int fdt_detect_flags(const float *loc, const float *conf, const float *priors, i
                      float conf_thresh, float nms_thresh, float var0, float var1, float *out, int32_t *counts, int64_t *kept_prior,
                      void *ws, size_t ws_bytes, void *stream, unsigned flags);
 
+// greedy NMS for any n and for float64 (nms_generic.cu): sort + pairwise bit mask + serial reduce
+constexpr int FDT_MAX_NMS_GENERIC = 131072;
+size_t fdt_nms_generic_workspace_bytes(int64_t n);
+template <typename T>
+int fdt_nms_generic(const T *boxes, const T *scores, int64_t n, T thresh, int64_t top_k, int variant,
+                    int64_t *keep, int64_t *count, void *ws, size_t ws_bytes, cudaStream_t st);
+
 #define FDT_CUDA(expr)                                                                            \
     do {                                                                                          \
         cudaError_t e_ = (expr);                                                                  \

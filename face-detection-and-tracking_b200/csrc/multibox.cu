@@ -48,6 +48,11 @@ constexpr int MINE_BINS = 4096;             // 12-bit digits
 constexpr int MINE_COLLECT = 2048;          // k_mine_select: largest level-0 bin finished by one collecting scan
 constexpr int MINE_REPL = 16;               // level-0 histogram copies (by prior index) to spread same-address atomics
 
+// key of a value for the GLOBAL maximum of conf (box_utils.py:268, x.max()): torch's max propagates NaN whatever its sign bit, the
+// order-preserving key alone would rank a sign-bit NaN (x86's default QNaN) lowest and drop it.  Every NaN maps to the top key, which
+// fdt_key_float turns back into a NaN.
+__device__ __forceinline__ unsigned gmax_key_of(float v) { return v != v ? 0xffffffffu : fdt_float_key(v); }
+
 __device__ __forceinline__ unsigned long long mine_comp(float v, unsigned p) { return ((unsigned long long)fdt_float_key(v) << 32) | (unsigned)~p; }
 
 struct GtTile {
@@ -221,7 +226,7 @@ k_match_default(const float4 *__restrict__ priors, const float *__restrict__ gt,
     const int64_t t = (int64_t)b * N + p;
     if (conf) {                                        // global max of conf for log_sum_exp (every block, also for images without GT)
         unsigned k = 0u;
-        if (valid) for (int c = 0; c < C; ++c) k = max(k, fdt_float_key(__ldg(conf + t * C + c)));
+        if (valid) for (int c = 0; c < C; ++c) k = max(k, gmax_key_of(__ldg(conf + t * C + c)));
         k = __reduce_max_sync(0xffffffffu, k);
         if (lane == 0) s_cmax[warp] = k;
         __syncthreads();
@@ -325,9 +330,19 @@ __global__ void k_conf_global_max(const float *__restrict__ x, int64_t n, unsign
     fdt_pdl_enter();
     unsigned k = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        k = max(k, fdt_float_key(x[i]));
+        k = max(k, gmax_key_of(x[i]));
     k = __reduce_max_sync(0xffffffffu, k);
     if ((threadIdx.x & 31) == 0) atomicMax(gmax_key, k);
+}
+
+// Level-0 mining histogram, chip-wide: neighbouring priors have similar losses, so the 32 lanes of a warp hit a handful of bins --
+// one atomic per distinct bin and warp (match_any) instead of one per prior, spread over MINE_REPL copies by warp.
+__device__ __forceinline__ void mine_hist_add(int *__restrict__ hist, const int b, const int bin)
+{
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    const int lane = threadIdx.x & 31;
+    if (bin >= 0 && lane == __ffs(peers) - 1)
+        atomicAdd(&hist[((size_t)b * MINE_REPL + ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (MINE_REPL - 1))) * MINE_BINS + bin], __popc(peers));
 }
 
 struct LossAcc {            // lives in the workspace, zeroed per call
@@ -366,7 +381,7 @@ k_loss_prior(const float4 *__restrict__ loc, const float *__restrict__ conf, con
     const int64_t p = (int64_t)blockIdx.x * M_THREADS + threadIdx.x;
     const float xmax = fdt_key_float(acc->gmax_key);
     double sl = 0.0;
-    int is_pos = 0;
+    int is_pos = 0, bin = -1;
     if (p < N) {
         const int64_t t = (int64_t)b * N + p;
         const int64_t label = conf_t[t];
@@ -383,8 +398,9 @@ k_loss_prior(const float4 *__restrict__ loc, const float *__restrict__ conf, con
         const float v = (fdt_logf_cr(s) + xmax) - row[label];                      // :106
         const float lc = is_pos ? 0.0f : v;                                        // :110
         loss_c_all[t] = lc;
-        atomicAdd(&hist[((size_t)b * MINE_REPL + (p & (MINE_REPL - 1))) * MINE_BINS + (int)(mine_comp(lc, (unsigned)p) >> 52)], 1);
+        bin = (int)(mine_comp(lc, (unsigned)p) >> 52);
     }
+    mine_hist_add(hist, b, bin);
     const double tot = block_sum<double>(sl, s_red);
     const int cnt = block_sum<int>(is_pos, s_cnt);
     if (threadIdx.x == 0) {
@@ -401,11 +417,12 @@ k_mine_hist(const float *__restrict__ loss_c, const uint8_t *__restrict__ pos, i
     __shared__ int s_cnt[M_WARPS];
     const int b = blockIdx.y;
     const int64_t p = (int64_t)blockIdx.x * M_THREADS + threadIdx.x;
-    int is_pos = 0;
+    int is_pos = 0, bin = -1;
     if (p < N) {
         is_pos = pos[(int64_t)b * N + p] != 0;
-        atomicAdd(&hist[((size_t)b * MINE_REPL + (p & (MINE_REPL - 1))) * MINE_BINS + (int)(mine_comp(loss_c[(int64_t)b * N + p], (unsigned)p) >> 52)], 1);
+        bin = (int)(mine_comp(loss_c[(int64_t)b * N + p], (unsigned)p) >> 52);
     }
+    mine_hist_add(hist, b, bin);
     const int cnt = block_sum<int>(is_pos, s_cnt);
     if (threadIdx.x == 0 && cnt) atomicAdd(&num_pos[b], cnt);
 }
@@ -558,10 +575,13 @@ __global__ void k_loss_final(const LossAcc *__restrict__ acc, const int32_t *__r
 __global__ void __launch_bounds__(M_THREADS)
 k_multibox_backward(const float4 *__restrict__ loc, const float *__restrict__ conf, const float4 *__restrict__ loc_t,
                     const int64_t *__restrict__ conf_t, const uint8_t *__restrict__ sel, const float *__restrict__ norm,
-                    float g_l, float g_c, int64_t total, int C, float4 *__restrict__ grad_loc, float *__restrict__ grad_conf)
+                    float g_l, float g_c, const float *__restrict__ g_l_dev, const float *__restrict__ g_c_dev,
+                    int64_t total, int C, float4 *__restrict__ grad_loc, float *__restrict__ grad_conf)
 {
     const int64_t t = (int64_t)blockIdx.x * M_THREADS + threadIdx.x;
     if (t >= total) return;
+    if (g_l_dev) g_l = __ldg(g_l_dev);              // upstream gradients as device scalars: no host synchronisation
+    if (g_c_dev) g_c = __ldg(g_c_dev);
     const float inv = 1.0f / norm[0];
     const int64_t label = conf_t[t];
     float4 gl = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -769,7 +789,24 @@ FDT_API int fdt_multibox_loss_backward(const float *loc, const float *conf, cons
                 "fdt_multibox_loss_backward: loc/loc_t/grad_loc need 16-byte alignment");
     const int64_t total = (int64_t)B * N;
     k_multibox_backward<<<(unsigned)((total + M_THREADS - 1) / M_THREADS), M_THREADS, 0, (cudaStream_t)stream>>>(
-        (const float4 *)loc, conf, (const float4 *)loc_t, conf_t, sel, norm, g_l, g_c, total, C, (float4 *)grad_loc, grad_conf);
+        (const float4 *)loc, conf, (const float4 *)loc_t, conf_t, sel, norm, g_l, g_c, nullptr, nullptr, total, C, (float4 *)grad_loc, grad_conf);
+    FDT_LAUNCH_CHECK();
+    return FDT_OK;
+}
+
+FDT_API int fdt_multibox_loss_backward_dev(const float *loc, const float *conf, const float *loc_t, const int64_t *conf_t,
+                                           const uint8_t *sel, const float *norm, const float *g_l_dev, const float *g_c_dev,
+                                           int B, int64_t N, int C, float *grad_loc, float *grad_conf, fdt_stream_t stream)
+{
+    FDT_REQUIRE(B >= 0 && N >= 0 && C >= 2, FDT_E_INVALID, "fdt_multibox_loss_backward_dev: bad sizes");
+    if (B == 0 || N == 0) return FDT_OK;
+    FDT_REQUIRE(loc && conf && loc_t && conf_t && sel && norm && grad_loc && grad_conf && g_l_dev && g_c_dev, FDT_E_INVALID,
+                "fdt_multibox_loss_backward_dev: null pointer argument");
+    FDT_REQUIRE(fdt_aligned(loc, 16) && fdt_aligned(loc_t, 16) && fdt_aligned(grad_loc, 16), FDT_E_INVALID,
+                "fdt_multibox_loss_backward_dev: loc/loc_t/grad_loc need 16-byte alignment");
+    const int64_t total = (int64_t)B * N;
+    k_multibox_backward<<<(unsigned)((total + M_THREADS - 1) / M_THREADS), M_THREADS, 0, (cudaStream_t)stream>>>(
+        (const float4 *)loc, conf, (const float4 *)loc_t, conf_t, sel, norm, 0.0f, 0.0f, g_l_dev, g_c_dev, total, C, (float4 *)grad_loc, grad_conf);
     FDT_LAUNCH_CHECK();
     return FDT_OK;
 }

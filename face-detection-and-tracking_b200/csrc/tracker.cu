@@ -44,6 +44,24 @@ __device__ __forceinline__ double iou_f64(const double *a, const double *b)
     return inter / uni;
 }
 
+// utils/calc_performance.py:34-51 calculate_distance(box_a = detection, box_b = the track's last box): numpy operand order, no FMA,
+// `dis ** 0.25` = pow (within 2 ulp of numpy's: the association only differs if two candidates' distances agree to ~1e-15)
+__device__ __forceinline__ double distance_f64(const double *a, const double *b)
+{
+    const double adx = a[2] - a[0], ady = a[3] - a[1], bdx = b[2] - b[0], bdy = b[3] - b[1];
+    const double cax = (a[2] + a[0]) / 2, cay = (a[3] + a[1]) / 2, cbx = (b[2] + b[0]) / 2, cby = (b[3] + b[1]) / 2;
+    const double dx = cbx - cax, dy = cby - cay;
+    const double dz = ((adx - bdx) + (ady - bdy)) / 2;
+    const double dis = __dadd_rn(__dadd_rn(__dmul_rn(dz, dz), __dmul_rn(dx, dx)), __dmul_rn(dy, dy));
+    return pow(dis, 0.25);
+}
+// association value, larger = better: the IoU (iouTracke_cal.py:131-134, matched iff > sigma_iou) or minus the distance
+// (:135-138: argmin, matched iff < sigma_dis  <=>  -distance > -sigma_dis).  First index on ties and first NaN wins either way.
+__device__ __forceinline__ double track_value(const double *a, const double *b, const int metric)
+{
+    return metric == 0 ? iou_f64(a, b) : -distance_f64(a, b);
+}
+
 __global__ void k_track_frame_of(const int64_t *__restrict__ frame_off, int64_t F, int32_t *__restrict__ frame_of)
 {
     int64_t f = blockIdx.x;
@@ -59,7 +77,7 @@ constexpr int ROW_EXTRA = 4;
 // one warp per detection g of frame f (f < F-1)
 __global__ void __launch_bounds__(256)
 k_track_mask(const double *__restrict__ dets, const int64_t *__restrict__ frame_off, const int32_t *__restrict__ frame_of,
-             int64_t F, int64_t total, int W, double sigma_iou, uint32_t *__restrict__ mask)
+             int64_t F, int64_t total, int W, int metric, double sigma_iou, uint32_t *__restrict__ mask)
 {
     const int lane = threadIdx.x & 31;
     const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -85,8 +103,8 @@ k_track_mask(const double *__restrict__ dets, const int64_t *__restrict__ frame_
             double db[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) db[k] = dets[5 * (n0 + j) + k];
-            v = iou_f64(db, tb);
-            over = v > sigma_iou;                                  // iouTracke_cal.py:134
+            v = track_value(db, tb, metric);
+            over = v > sigma_iou;                                  // iouTracke_cal.py:134 / :138 (sigma_iou = -sigma_dis there)
             isn = v != v;
         }
         const unsigned bits = __ballot_sync(0xffffffffu, over);
@@ -109,13 +127,13 @@ k_track_mask(const double *__restrict__ dets, const int64_t *__restrict__ frame_
     if (count > 0) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            double bv = nc > 0 ? cv[0] : -1.0;                     // IoU > sigma >= ... candidates are positive; -1 = nothing to offer
+            double bv = nc > 0 ? cv[0] : -INFINITY;                // nothing to offer (bj == INT_MAX decides)
             int bj = nc > 0 ? cj[0] : INT_MAX;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
                 const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-                if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+                if (oj != INT_MAX && (bj == INT_MAX || ov > bv || (ov == bv && oj < bj))) { bv = ov; bj = oj; }
             }
             if (bj != INT_MAX) {
                 if (nc > 0 && cj[0] == bj) {                       // this lane's head was taken: pop it
@@ -160,7 +178,8 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total)
 struct ResolveParams {
     const double *dets; const int64_t *frame_off; int64_t F; int W; int cap;   // cap = W * 32 >= max detections per frame
     const uint32_t *mask;                        // [total][W + ROW_EXTRA], see k_track_mask
-    double sigma_iou, sigma_h; int64_t t_min;
+    double sigma_iou, sigma_h; int64_t t_min;      // sigma_iou: threshold on the association value (-sigma_dis in distance mode)
+    int metric;                                    // 0 IoU, 1 distance
     int32_t *det_head, *det_pos, *fin_id;        // [total]
     int64_t *n_tracks, *track_off, *track_start; double *track_max;
     int force_slow;
@@ -292,7 +311,7 @@ k_track_resolve(const ResolveParams P)
                     while (bits) {
                         const int j = c * 32 + __ffs(bits) - 1;
                         bits &= bits - 1;
-                        const double v = iou_f64(box + 5 * j, tb);
+                        const double v = track_value(box + 5 * j, tb, P.metric);
                         int p = nc < 4 ? nc : 4;                       // first slot with a smaller value (ties keep the lower j first)
 #pragma unroll
                         for (int q = 3; q >= 0; --q) if (q < nc && cv[q] < v) p = q;
@@ -356,7 +375,7 @@ k_track_resolve(const ResolveParams P)
                     double bv = 0.0; int bj = INT_MAX; int bn = 0;               // lane-local: value, index, is-NaN
                     for (int j = lane; j < D; j += 32) {
                         if (owner[j] != INT_MAX) continue;                       // already deleted from dets (:145)
-                        const double v = iou_f64(box + 5 * j, tb);
+                        const double v = track_value(box + 5 * j, tb, P.metric);
                         const int vn = v != v;
                         if (bj == INT_MAX) { bv = v; bj = j; bn = vn; }
                         else if (!bn && (vn || v > bv)) { bv = v; bj = j; bn = vn; }
@@ -497,7 +516,18 @@ FDT_API int fdt_iou_track(const double *dets, const int64_t *frame_off, int64_t 
                           int64_t *n_tracks, int64_t *track_off, int64_t *track_dets, int64_t *track_start, double *track_max,
                           void *ws, size_t ws_bytes, fdt_stream_t stream)
 {
+    return fdt_iou_track_metric(dets, frame_off, F, total, max_dets_per_frame, FDT_TRACK_IOU, sigma_iou, sigma_h, t_min,
+                                n_tracks, track_off, track_dets, track_start, track_max, ws, ws_bytes, stream);
+}
+
+FDT_API int fdt_iou_track_metric(const double *dets, const int64_t *frame_off, int64_t F, int64_t total, int64_t max_dets_per_frame,
+                                 int metric, double sigma, double sigma_h, int64_t t_min,
+                                 int64_t *n_tracks, int64_t *track_off, int64_t *track_dets, int64_t *track_start, double *track_max,
+                                 void *ws, size_t ws_bytes, fdt_stream_t stream)
+{
     cudaStream_t st = (cudaStream_t)stream;
+    FDT_REQUIRE(metric == FDT_TRACK_IOU || metric == FDT_TRACK_DISTANCE, FDT_E_INVALID, "fdt_iou_track: unknown metric %d", metric);
+    const double sigma_iou = metric == FDT_TRACK_IOU ? sigma : -sigma;
     FDT_REQUIRE(F >= 0 && total >= 0 && max_dets_per_frame >= 0, FDT_E_INVALID, "fdt_iou_track: negative size");
     FDT_REQUIRE(n_tracks && track_off, FDT_E_INVALID, "fdt_iou_track: null output pointer");
     FDT_REQUIRE(total < (1ll << 31), FDT_E_UNSUPPORTED, "fdt_iou_track: total=%lld exceeds 2^31-1", (long long)total);
@@ -518,11 +548,11 @@ FDT_API int fdt_iou_track(const double *dets, const int64_t *frame_off, int64_t 
     FDT_CUDA(cudaMemsetAsync(t.fin_id, 0xff, (size_t)total * 4, st));
     k_track_frame_of<<<(unsigned)F, 128, 0, st>>>(frame_off, F, t.frame_of);
     FDT_LAUNCH_CHECK();
-    k_track_mask<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(dets, frame_off, t.frame_of, F, total, W, sigma_iou, t.mask);
+    k_track_mask<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(dets, frame_off, t.frame_of, F, total, W, metric, sigma_iou, t.mask);
     FDT_LAUNCH_CHECK();
     ResolveParams P{};
     P.dets = dets; P.frame_off = frame_off; P.F = F; P.W = W; P.cap = W * 32; P.mask = t.mask;
-    P.sigma_iou = sigma_iou; P.sigma_h = sigma_h; P.t_min = t_min;
+    P.sigma_iou = sigma_iou; P.sigma_h = sigma_h; P.t_min = t_min; P.metric = metric;
     P.det_head = t.det_head; P.det_pos = t.det_pos; P.fin_id = t.fin_id;
     P.n_tracks = n_tracks; P.track_off = track_off; P.track_start = track_start; P.track_max = track_max;
     const char *env = getenv("FDT_TRACK_FORCE_SLOW");

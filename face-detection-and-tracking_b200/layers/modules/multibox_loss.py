@@ -44,7 +44,8 @@ class _MultiBoxLossFn(torch.autograd.Function):
                 _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
         ctx.save_for_backward(loc, conf, loc_t, conf_t, sel, norm)
         ctx.mark_non_differentiable(loc_t, conf_t, sel)
-        return losses[0], losses[1], loc_t, conf_t, sel
+        # two independent 0-dim tensors, as the reference returns (views of one buffer would forbid in-place ops on them)
+        return losses[0].clone(), losses[1].clone(), loc_t, conf_t, sel
 
     @staticmethod
     def backward(ctx, g_l, g_c, *_):
@@ -53,12 +54,21 @@ class _MultiBoxLossFn(torch.autograd.Function):
         C_ = conf.shape[-1]
         grad_loc = torch.empty_like(loc)
         grad_conf = torch.empty_like(conf)
-        gl = float(g_l) if g_l is not None else 0.0
-        gc = float(g_c) if g_c is not None else 0.0
-        with torch.cuda.device(loc.device):
-            _lib.check(_lib.lib().fdt_multibox_loss_backward(
+        # the upstream gradients stay on the device: no float() synchronisation, the loss can be captured in a CUDA graph
+        dev = loc.device
+        zero = None
+        def scalar(g):
+            nonlocal zero
+            if g is None:
+                if zero is None:
+                    zero = torch.zeros((), dtype=torch.float32, device=dev)
+                return zero
+            return g.detach().to(device=dev, dtype=torch.float32).contiguous()
+        gl, gc = scalar(g_l), scalar(g_c)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().fdt_multibox_loss_backward_dev(
                 _lib.ptr(loc), _lib.ptr(conf), _lib.ptr(loc_t), _lib.ptr(conf_t), _lib.ptr(sel), _lib.ptr(norm),
-                gl, gc, B, N, C_, _lib.ptr(grad_loc), _lib.ptr(grad_conf), _lib.stream_ptr()))
+                _lib.ptr(gl), _lib.ptr(gc), B, N, C_, _lib.ptr(grad_loc), _lib.ptr(grad_conf), _lib.stream_ptr()))
         return grad_loc, grad_conf, None, None, None, None, None, None, None, None
 
 

@@ -124,6 +124,31 @@ def tracker_frames(F, seed, d_lo=1, d_hi=300, n_objects=300, width=640.0, height
     return frames
 
 
+def clip_detections(F, top_k, seed):
+    """Detect-shaped output of a clip, [F, 2, top_k, 5]: per frame a few faces that drift from frame to frame, rows in
+    descending score order, then rows below the tracker's read-out threshold (0.4), then zero padding; some frames have no face."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    det = np.zeros((F, 2, top_k, 5), np.float32)
+    n_obj = 9
+    ctr = rng.uniform(0.15, 0.85, (n_obj, 2)); size = rng.uniform(0.04, 0.2, (n_obj, 2))
+    for f in range(F):
+        ctr += rng.normal(0, 0.004, ctr.shape)
+        vis = rng.uniform(size=n_obj) < 0.8
+        if f % 13 == 5:
+            vis[:] = False
+        rows = []
+        for o in np.where(vis)[0]:
+            c = ctr[o] + rng.normal(0, 0.002, 2); s = size[o] * rng.uniform(0.97, 1.03, 2)
+            rows.append([rng.uniform(0.41, 0.999), c[0] - s[0] / 2, c[1] - s[1] / 2, c[0] + s[0] / 2, c[1] + s[1] / 2])
+        for _ in range(int(rng.integers(0, 6))):                       # kept by NMS but below the tracker's 0.4
+            c = rng.uniform(0.1, 0.9, 2); s = rng.uniform(0.03, 0.1, 2)
+            rows.append([rng.uniform(0.05, 0.399), c[0] - s[0] / 2, c[1] - s[1] / 2, c[0] + s[0] / 2, c[1] + s[1] / 2])
+        rows.sort(key=lambda r: -r[0])
+        for j, r in enumerate(rows[:top_k]):
+            det[f, 1, j] = np.array(r, np.float32)
+    return det
+
+
 def digest(*arrays):
     h = hashlib.sha256()
     for a in arrays:

@@ -45,7 +45,7 @@ extern "C" {
 #define FDT_NMS_PLUS1      4      /* widths, heights and areas measured with "+ 1" (pixel convention) */
 #define FDT_NMS_LE         8      /* a box survives iff overlap <= thresh (default: overlap < thresh) */
 
-#define FDT_MAX_NMS_TOP_K  8000   /* candidates that can enter NMS per image/class (the reference uses 5000) */
+#define FDT_MAX_NMS_TOP_K  8000   /* candidates that can enter Detect's NMS per image/class (the reference uses 5000) */
 
 /* sticky status bits of a Detect workspace (fdt_detect_status): a device-side wait gave up after ~4 s */
 #define FDT_STATUS_TIMEOUT_LOCAL 1u   /* a call of the same workspace never completed (the kernel also traps) */
@@ -91,6 +91,15 @@ int fdt_calc_pr(const double *predict, int64_t P, int predict_stride, const doub
 int fdt_detections_to_rows(const float *detections, int B, int C, int top_k, float thresh, float width, float height,
                            float *rows_out, int32_t *n_rows, fdt_stream_t stream);
 
+/* Detect -> tracker on the device (iouTracke_cal.py:55-84 detect_face, one image per frame): the same leading rows, divided by
+ * `shrink` in float32 (:76-80) and widened to float64, packed frame after frame as fdt_iou_track wants them; a frame without a detection gets
+ * the reference's dummy row [0, 0, 0, 0, 0.4] (:73-74).  _count fills n_rows[F] (int32, before the dummy rule) and
+ * frame_off[F+1] (int64, after it); the caller reads frame_off[F] to size dets_out[frame_off[F], 5], then calls _pack. */
+int fdt_detections_to_frames_count(const float *detections, int64_t F, int C, int top_k, float thresh,
+                                   int32_t *n_rows, int64_t *frame_off, fdt_stream_t stream);
+int fdt_detections_to_frames_pack(const float *detections, int64_t F, int C, int top_k, float thresh, float width, float height,
+                                  double shrink, const int64_t *frame_off, double *dets_out, fdt_stream_t stream);
+
 /* ---- M6 / D1  encode / decode  (layers/box_utils.py:213-234, 238-258) --------------------------- */
 int fdt_encode(const float *matched, const float *priors, int64_t n, float var0, float var1, float *out, fdt_stream_t stream);
 int fdt_decode(const float *loc, const float *priors, int64_t n, float var0, float var1, float *out, fdt_stream_t stream);
@@ -102,7 +111,8 @@ int fdt_log_sum_exp(const float *x, int64_t R, int C, float *out, void *ws, size
 /* ---- N1  nms  (layers/box_utils.py:275-340) ------------------------------------------------------
  * boxes[n,4], scores[n] -> keep[n] int64 zero-padded (indices into the input, descending score),
  * *count (device int64).  Sort ties: higher index first.  top_k <= 0 means n, as idx[-0:] does.
- * Limit: min(n, top_k) <= FDT_MAX_NMS_TOP_K (FDT_E_UNSUPPORTED beyond). */
+ * min(n, top_k) <= FDT_MAX_NMS_TOP_K runs in one shared-memory kernel; beyond that (the reference has no cap, :296-298) the call
+ * takes the sort + pairwise-mask + reduce formulation (up to 131,072 boxes; the workspace grows with n * n / 8 bytes). */
 size_t fdt_nms_workspace_bytes(int64_t n);
 int fdt_nms(const float *boxes, const float *scores, int64_t n, float overlap, int64_t top_k,
             int64_t *keep, int64_t *count, void *ws, size_t ws_bytes, fdt_stream_t stream);
@@ -114,12 +124,17 @@ int fdt_nms(const float *boxes, const float *scores, int64_t n, float overlap, i
  *   MTCNN/mtcnn/core/nms.py:4-40 torch_nms            FDT_NMS_PLUS1 | FDT_NMS_LE | (FDT_NMS_SUMFIRST or FDT_NMS_MINIMUM)
  *   FACEBOX/encoderl.py:268-306 DataEncoder.nms       FDT_NMS_SUMFIRST | FDT_NMS_LE
  * keep[n] int64 zero padded = indices in keep order (descending score; ties: higher index first), *count device int64.
- * Limit n <= FDT_MAX_NMS_TOP_K; workspace fdt_nms_workspace_bytes(n).
+ * Workspace fdt_nms_workspace_bytes(n) (n > FDT_MAX_NMS_TOP_K takes the mask formulation, as fdt_nms does).
+ * fdt_nms_variant_f64: the same rules in float64 -- MTCNN's `nms` runs in the dtype of its float64 `dets`
+ * (core/utils.py:62-113, callers core/detect.py:314, 326, 431, 579); workspace fdt_nms_f64_workspace_bytes(n), n <= 131,072.
  * fdt_facebox_decode: the box part of DataEncoder.decode_np (encoderl.py:318-320), corner form [x1,y1,x2,y2].
  * fdt_threshold_nms: rows p of a box table with conf[p,1] > conf_thresh (conf[N,2]) enter fdt_nms_variant's NMS without a
  * host round trip; keep[N] holds table indices.  More than FDT_MAX_NMS_TOP_K candidates: keep zeroed, *count = -1. */
 int fdt_nms_variant(const float *boxes, const float *scores, int64_t n, float thresh, int variant,
                     int64_t *keep, int64_t *count, void *ws, size_t ws_bytes, fdt_stream_t stream);
+size_t fdt_nms_f64_workspace_bytes(int64_t n);
+int fdt_nms_variant_f64(const double *boxes, const double *scores, int64_t n, double thresh, int variant,
+                        int64_t *keep, int64_t *count, void *ws, size_t ws_bytes, fdt_stream_t stream);
 int fdt_facebox_decode(const float *loc, const float *default_boxes, int64_t n, float var0, float var1, float *out,
                        fdt_stream_t stream);
 size_t fdt_threshold_nms_workspace_bytes(int64_t N);
@@ -264,17 +279,29 @@ int fdt_multibox_loss_forward(const float *loc, const float *conf, const float *
 int fdt_multibox_loss_backward(const float *loc, const float *conf, const float *loc_t, const int64_t *conf_t,
                                const uint8_t *sel, const float *norm, float g_l, float g_c,
                                int B, int64_t N, int C, float *grad_loc, float *grad_conf, fdt_stream_t stream);
+/* the same with the upstream gradients as DEVICE scalars (what autograd hands over): no host synchronisation, graph capturable */
+int fdt_multibox_loss_backward_dev(const float *loc, const float *conf, const float *loc_t, const int64_t *conf_t,
+                                   const uint8_t *sel, const float *norm, const float *g_l_dev, const float *g_c_dev,
+                                   int B, int64_t N, int C, float *grad_loc, float *grad_conf, fdt_stream_t stream);
 
 /* ---- T2  IoU tracker association  (iouTracke_cal.py:126-155 loop, :174-176 flush) ----------------
  * dets[total,5] float64 rows [x1,y1,x2,y2,score]; frame_off[F+1] int64 (device); frames are 1-based in
  * the output.  Outputs (device): n_tracks[1] int64; track_off[total+1] int64 CSR offsets into
  * track_dets[total] int64 (global det rows in append order); track_start[total] int64;
  * track_max[total] float64 -- entries [0, n_tracks) are valid, in the reference's finishing order. */
+#define FDT_TRACK_IOU       0   /* use_iou = True:  calculate_iou, argmax, matched iff > sigma_iou   (iouTracke_cal.py:131-134) */
+#define FDT_TRACK_DISTANCE  1   /* use_iou = False: calculate_distance, argmin, matched iff < sigma_dis (iouTracke_cal.py:135-138) */
 size_t fdt_iou_track_workspace_bytes(int64_t F, int64_t total, int64_t max_dets_per_frame);
 int fdt_iou_track(const double *dets, const int64_t *frame_off, int64_t F, int64_t total, int64_t max_dets_per_frame,
                   double sigma_iou, double sigma_h, int64_t t_min,
                   int64_t *n_tracks, int64_t *track_off, int64_t *track_dets, int64_t *track_start, double *track_max,
                   void *ws, size_t ws_bytes, fdt_stream_t stream);
+/* the same with the association rule of the reference's `use_iou` switch: metric FDT_TRACK_IOU (sigma = sigma_iou) or
+ * FDT_TRACK_DISTANCE (sigma = sigma_dis; utils/calc_performance.py:34-51, `** 0.25` evaluated with pow, within 2 ulp of numpy). */
+int fdt_iou_track_metric(const double *dets, const int64_t *frame_off, int64_t F, int64_t total, int64_t max_dets_per_frame,
+                         int metric, double sigma, double sigma_h, int64_t t_min,
+                         int64_t *n_tracks, int64_t *track_off, int64_t *track_dets, int64_t *track_start, double *track_max,
+                         void *ws, size_t ws_bytes, fdt_stream_t stream);
 
 #ifdef __cplusplus
 }

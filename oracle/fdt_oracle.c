@@ -511,7 +511,7 @@ ORC_API int64_t orc_calc_pr(const double *predict, int64_t P, int predict_stride
 }
 
 /* ------------------------------------------------------------------------------------------
- * IoU tracker loop (iouTracke_cal.py:126-155 per frame, :174-176 flush), use_iou = True.
+ * IoU tracker loop (iouTracke_cal.py:126-155 per frame, :174-176 flush), use_iou = True (metric 0) or False (metric 1).
  * dets[total,5] float64 rows [x1,y1,x2,y2,score]; frame_off[F+1]; frame numbers are 1-based (:118).
  * Output (CSR): returns T = number of finished tracks; track_off[T+1] into track_dets (global det
  * row indices, in append order); track_start[T] (1-based), track_max[T].
@@ -523,10 +523,21 @@ static void tr_push(orc_track_t *t, int64_t g)
     if (t->len == t->cap) { t->cap = t->cap ? t->cap * 2 : 8; t->d = (int64_t *)realloc(t->d, sizeof(int64_t) * (size_t)t->cap); }
     t->d[t->len++] = g;
 }
-ORC_API int64_t orc_iou_track(const double *dets, const int64_t *frame_off, int64_t F,
-                              double sigma_iou, double sigma_h, int64_t t_min,
-                              int64_t *track_off, int64_t *track_dets, int64_t *track_start, double *track_max)
+/* association value of detection a against a track's last box b, larger = better:
+ * use_iou (:131-134) the IoU, matched iff > sigma_iou; else (:135-138) minus calculate_distance, matched iff distance < sigma_dis.
+ * argmin of the distance == argmax of its negation, first index on ties, first NaN wins either way (numpy). */
+static double track_value(const double *a, const double *b, int metric)
 {
+    if (metric == 0) return iou1_f64(a, b);
+    double d;
+    orc_calculate_distance_f64(a, 1, b, 1, &d);
+    return -d;
+}
+ORC_API int64_t orc_iou_track_metric(const double *dets, const int64_t *frame_off, int64_t F,
+                                     int metric, double sigma, double sigma_h, int64_t t_min,
+                                     int64_t *track_off, int64_t *track_dets, int64_t *track_start, double *track_max)
+{
+    const double sigma_iou = metric == 0 ? sigma : -sigma;
     int64_t total = frame_off[F];
     orc_track_t *active = NULL, *updated = NULL; int64_t n_active = 0;
     int64_t T = 0, w = 0; track_off[0] = 0;
@@ -545,9 +556,9 @@ ORC_API int64_t orc_iou_track(const double *dets, const int64_t *frame_off, int6
             orc_track_t *tr = &active[t];
             if (n_alive > 0) {                                     /* :130 */
                 const double *last = dets + 5 * tr->d[tr->len - 1];
-                int64_t best = 0; double bv = iou1_f64(dets + 5 * alive[0], last);   /* :132 */
-                for (int64_t a = 1; a < n_alive && !(bv != bv); ++a) {     /* :133 argmax: first max, first NaN wins */
-                    double v = iou1_f64(dets + 5 * alive[a], last);
+                int64_t best = 0; double bv = track_value(dets + 5 * alive[0], last, metric);   /* :132 / :136 */
+                for (int64_t a = 1; a < n_alive && !(bv != bv); ++a) {     /* :133 argmax (:137 argmin): first extremum, first NaN wins */
+                    double v = track_value(dets + 5 * alive[a], last, metric);
                     if (v != v || v > bv) { bv = v; best = a; }
                 }
                 if (bv > sigma_iou) {                              /* :134, :140-145 */
@@ -580,6 +591,12 @@ ORC_API int64_t orc_iou_track(const double *dets, const int64_t *frame_off, int6
     free(active); free(alive);
     (void)total;
     return T;
+}
+ORC_API int64_t orc_iou_track(const double *dets, const int64_t *frame_off, int64_t F,
+                              double sigma_iou, double sigma_h, int64_t t_min,
+                              int64_t *track_off, int64_t *track_dets, int64_t *track_start, double *track_max)
+{
+    return orc_iou_track_metric(dets, frame_off, F, 0, sigma_iou, sigma_h, t_min, track_off, track_dets, track_start, track_max);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -671,6 +688,60 @@ ORC_API int64_t orc_nms_variant(const float *boxes, const float *scores, int64_t
             else if (flags & 1) den = (area[i] + area[j]) - inter;
             else den = (area[j] - inter) + area[i];
             const float ovr = inter / den;
+            const int survive = (flags & 8) ? (ovr <= thr) : (ovr < thr);
+            if (survive) idx[w++] = j;
+        }
+        m = w;
+    }
+    free(idx); free(ord); free(area);
+    return count;
+}
+
+/* The same in float64: MTCNN's `nms` runs in the dtype of its float64 `dets` (MTCNN/mtcnn/core/utils.py:62-113). */
+typedef struct { double s; int64_t i; } orc_di;
+static int cmp_di_asc(const void *pa, const void *pb)
+{
+    const orc_di *a = (const orc_di *)pa, *b = (const orc_di *)pb;
+    int an = a->s != a->s, bn = b->s != b->s;
+    if (an != bn) return an - bn;
+    if (!an) { if (a->s < b->s) return -1; if (a->s > b->s) return 1; }
+    return (a->i > b->i) - (a->i < b->i);
+}
+ORC_API int64_t orc_nms_variant_f64(const double *boxes, const double *scores, int64_t n, double thr, int flags, int64_t *keep)
+{
+    memset(keep, 0, sizeof(int64_t) * (size_t)n);
+    if (n == 0) return 0;
+    const double p1 = (flags & 4) ? 1.0 : 0.0;
+    double *area = (double *)malloc(sizeof(double) * (size_t)n);
+    orc_di *ord = (orc_di *)malloc(sizeof(orc_di) * (size_t)n);
+    int64_t *idx = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        const double *b = boxes + 4 * i;
+        area[i] = (flags & 4) ? ((b[2] - b[0]) + 1.0) * ((b[3] - b[1]) + 1.0) : (b[2] - b[0]) * (b[3] - b[1]);
+        ord[i].s = scores[i]; ord[i].i = i;
+    }
+    qsort(ord, (size_t)n, sizeof(orc_di), cmp_di_asc);
+    int64_t m = n, count = 0;
+    for (int64_t t = 0; t < n; ++t) idx[t] = ord[t].i;
+    while (m > 0) {
+        const int64_t i = idx[m - 1];
+        keep[count++] = i;
+        m -= 1;
+        const double *bi = boxes + 4 * i;
+        int64_t w = 0;
+        for (int64_t t = 0; t < m; ++t) {
+            const int64_t j = idx[t];
+            const double *bj = boxes + 4 * j;
+            const double xx1 = d_max(bi[0], bj[0]), yy1 = d_max(bi[1], bj[1]);
+            const double xx2 = d_min(bi[2], bj[2]), yy2 = d_min(bi[3], bj[3]);
+            double dw = xx2 - xx1, dh = yy2 - yy1;
+            if (flags & 4) { dw += p1; dh += p1; }
+            const double inter = d_max(0.0, dw) * d_max(0.0, dh);
+            double den;
+            if (flags & 2) den = d_min(area[i], area[j]);
+            else if (flags & 1) den = (area[i] + area[j]) - inter;
+            else den = (area[j] - inter) + area[i];
+            const double ovr = inter / den;
             const int survive = (flags & 8) ? (ovr <= thr) : (ovr < thr);
             if (survive) idx[w++] = j;
         }

@@ -265,9 +265,9 @@ def gen_multibox():
 
 
 # ------------------------------------------------------------------ 6. tracker
-def ref_tracker(frames, sigma_iou=0.4, sigma_h=0.6, t_min=5):
-    """VERBATIM restatement of iouTracke_cal.py:126-155 (loop body, use_iou=True) and :174-176 (flush)
-    around the reference's utils.calc_performance.calculate_iou."""
+def ref_tracker(frames, sigma_iou=0.4, sigma_h=0.6, t_min=5, use_iou=True, sigma_dis=8):
+    """VERBATIM restatement of iouTracke_cal.py:126-155 (loop body, both use_iou branches) and :174-176 (flush)
+    around the reference's utils.calc_performance.calculate_iou / calculate_distance."""
     frame_num = 0
     tracks_active = []
     tracks_finished = []
@@ -277,9 +277,14 @@ def ref_tracker(frames, sigma_iou=0.4, sigma_h=0.6, t_min=5):
         updated_tracks = []
         for track in tracks_active:
             if len(dets) > 0:
-                iou = ref_iou_np(np.array(dets)[:, :4], np.array([track['bboxes'][-1]]))
-                best_match = iou.argmax()
-                matched = iou[best_match] > sigma_iou
+                if use_iou:
+                    iou = ref_iou_np(np.array(dets)[:, :4], np.array([track['bboxes'][-1]]))
+                    best_match = iou.argmax()
+                    matched = iou[best_match] > sigma_iou
+                else:
+                    iou = ref_cp.calculate_distance(np.array(dets)[:, :4], np.array([track['bboxes'][-1]]))
+                    best_match = iou.argmin()
+                    matched = iou[best_match] < sigma_dis
                 if matched:
                     track['bboxes'].append(dets[best_match][:4])
                     track['max_score'] = max(track['max_score'], dets[best_match][4])
@@ -298,11 +303,13 @@ def ref_tracker(frames, sigma_iou=0.4, sigma_h=0.6, t_min=5):
 def gen_tracker():
     d = {}
     for tag, kw in (("a", dict(F=400, seed=11, d_lo=1, d_hi=40, n_objects=40, empty_every=57)),
-                    ("b", dict(F=120, seed=12, d_lo=1, d_hi=300, n_objects=300, empty_every=50, sigma=4.0))):
+                    ("b", dict(F=120, seed=12, d_lo=1, d_hi=300, n_objects=300, empty_every=50, sigma=4.0)),
+                    ("c", dict(F=300, seed=13, d_lo=1, d_hi=60, n_objects=60, empty_every=41)),            # use_iou = False
+                    ("d", dict(F=100, seed=14, d_lo=1, d_hi=250, n_objects=250, empty_every=33, sigma=3.0))):  # use_iou = False, crowded
         frames = synth.tracker_frames(**kw)
-        if tag == "a":                      # two consecutive empty frames: dummy-vs-dummy IoU is 0/0 = NaN
+        if tag in ("a", "c"):               # two consecutive empty frames: dummy-vs-dummy IoU is 0/0 = NaN (distance: 0)
             frames[200] = np.array([[0, 0, 0, 0, 0.4]]); frames[201] = np.array([[0, 0, 0, 0, 0.4]])
-        tr = ref_tracker(frames)
+        tr = ref_tracker(frames, use_iou=tag in ("a", "b"))
         bb = np.array([b for t in tr for b in t['bboxes']], np.float64).reshape(-1, 4)
         d.update({f"{tag}_kw": np.array(repr(kw)), f"{tag}_in_sha": np.array(synth.digest(*frames)),
                   f"{tag}_len": np.array([len(t['bboxes']) for t in tr], np.int64),
@@ -310,6 +317,53 @@ def gen_tracker():
                   f"{tag}_max": np.array([t['max_score'] for t in tr], np.float64), f"{tag}_bboxes": bb})
         print("  tracker", tag, "tracks", len(tr), "boxes", bb.shape[0])
     save("tracker", **d)
+
+
+def ref_detect_face_readout(detections, width, height, shrink):
+    """iouTracke_cal.py:55-84 verbatim (detect_face after the network call); `detections` = y.data of ONE image."""
+    scale = torch.Tensor([width, height, width, height])
+    boxes = []
+    scores = []
+    for i in range(detections.size(1)):
+        j = 0
+        while detections[0, i, j, 0] >= 0.4:
+            score_ = detections[0, i, j, 0]
+            pt = (detections[0, i, j, 1:] * scale).cpu().numpy()
+            boxes.append([pt[0], pt[1], pt[2], pt[3]])
+            scores.append(score_)
+            j += 1
+            if j >= detections.size(2):
+                break
+    det_conf = np.array(scores)
+    boxes = np.array(boxes)
+    if boxes.shape[0] == 0:
+        return np.array([[0, 0, 0, 0, 0.4]])
+    det_xmin = boxes[:, 0] / shrink
+    det_ymin = boxes[:, 1] / shrink
+    det_xmax = boxes[:, 2] / shrink
+    det_ymax = boxes[:, 3] / shrink
+    det = np.column_stack((det_xmin, det_ymin, det_xmax, det_ymax, det_conf))
+    keep_index = np.where(det[:, 4] >= 0)[0]
+    det = det[keep_index, :]
+    return det
+
+
+def gen_frames():
+    """Detect -> tracker chain (iouTracke_cal.py:55-84 feeding :126-155): the read-out of every frame and the tracks."""
+    d = {}
+    for tag, (F, top_k, seed, w, h, shrink) in {"a": (90, 24, 71, 640.0, 480.0, 1), "b": (40, 16, 72, 1280.0, 720.0, 0.5)}.items():
+        det = synth.clip_detections(F, top_k, seed)
+        frames = [ref_detect_face_readout(torch.from_numpy(det[f:f + 1]), w, h, shrink) for f in range(F)]
+        # (rows are float32 -- numpy keeps the dtype of the float32 scalars through np.array and `/ shrink` -- the dummy row is float64)
+        tr = ref_tracker(frames)
+        d.update({f"{tag}_cfg": np.array([F, top_k, seed, w, h, shrink], np.float64), f"{tag}_in_sha": np.array(synth.digest(det)),
+                  f"{tag}_n": np.array([fr.shape[0] for fr in frames], np.int64), f"{tag}_dets": np.concatenate(frames, 0),
+                  f"{tag}_len": np.array([len(t['bboxes']) for t in tr], np.int64),
+                  f"{tag}_start": np.array([t['start_frame'] for t in tr], np.int64),
+                  f"{tag}_max": np.array([t['max_score'] for t in tr], np.float64),
+                  f"{tag}_bboxes": np.array([b for t in tr for b in t['bboxes']], np.float64).reshape(-1, 4)})
+        print("  frames", tag, "rows", int(sum(fr.shape[0] for fr in frames)), "dummy frames", int(sum(fr.shape[0] == 1 and fr[0, 4] == 0.4 and fr[0, 2] == 0 for fr in frames)), "tracks", len(tr))
+    save("frames", **d)
 
 
 # ------------------------------------------------------------------ 7. head post-processing (SURVEY 8f rank 1)
@@ -450,6 +504,18 @@ def gen_siblings():
         k = np.asarray(fn(), dtype=np.int64).reshape(-1)
         d[tag] = k.astype(np.int32)
         print("  ", tag, "kept", k.size)
+    # float64 dets, as MTCNN's pipeline passes them (core/detect.py:314, 326): boxes whose overlap sits within fp32 rounding of the
+    # threshold decide differently in fp32 and float64, so these pin the float64 path
+    d64 = sibling_dets(500, 54).astype(np.float64)
+    rng64 = np.random.Generator(np.random.PCG64(55))
+    d64[:, :4] += rng64.uniform(-1e-6, 1e-6, (500, 4))                   # not representable in fp32
+    d64[:, 4] = rng64.permutation(500) / 500.0 * 0.6 + 0.4 + rng64.uniform(0, 1e-9, 500)
+    d["dets64"] = d64
+    d["f64_mt_union_06"] = np.asarray(mt_utils.nms(d64, 0.6, "Union"), np.int32)
+    d["f64_mt_min_04"] = np.asarray(mt_utils.nms(d64, 0.4, "Minimum"), np.int32)
+    d["f64_plus1_union_05"] = np.asarray(mt_nms.torch_nms(d64, 0.5, "Union"), np.int32)
+    d["f64_fb_np_union_05"] = np.asarray(enc.nms_np(d64[:, :4], d64[:, 4], 0.5), np.int32)
+    print("   f64 kept", d["f64_mt_union_06"].size, d["f64_mt_min_04"].size, d["f64_plus1_union_05"].size, d["f64_fb_np_union_05"].size)
     # NaN coordinate: numpy / torch min-max propagate it
     dn = sibling_dets(64, 53); dn[5, 1] = np.nan
     d["dets_nan"] = dn
@@ -492,7 +558,7 @@ def gen_formats():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["priorbox", "boxutils", "nms", "detect", "multibox", "tracker", "heads", "siblings", "formats", "detect_shapes"]
+    which = sys.argv[1:] or ["priorbox", "boxutils", "nms", "detect", "multibox", "tracker", "heads", "siblings", "formats", "detect_shapes", "frames"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()

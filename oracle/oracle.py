@@ -231,8 +231,9 @@ def calc_pr(predict, truth, iou_thresh=0.5):
 
 
 # ---------------------------------------------------------------- tracker (iouTracke_cal.py:126-155,174-176)
-def iou_track_raw(frames, sigma_iou=0.4, sigma_h=0.6, t_min=5):
-    """frames: list of [D_f,5] arrays.  -> (dets[total,5] f64, track_off, track_dets, track_start, track_max)"""
+def iou_track_raw(frames, sigma_iou=0.4, sigma_h=0.6, t_min=5, use_iou=True, sigma_dis=8):
+    """frames: list of [D_f,5] arrays.  -> (dets[total,5] f64, track_off, track_dets, track_start, track_max)
+    use_iou=False: association by calculate_distance / argmin / < sigma_dis (iouTracke_cal.py:135-138)."""
     off = np.zeros(len(frames) + 1, np.int64)
     for i, f in enumerate(frames):
         off[i + 1] = off[i] + np.asarray(f).reshape(-1, 5).shape[0]
@@ -243,18 +244,39 @@ def iou_track_raw(frames, sigma_iou=0.4, sigma_h=0.6, t_min=5):
             dets[off[i]:off[i + 1]] = np.asarray(f, dtype=np.float64).reshape(-1, 5)
     t_off = np.zeros(total + 2, np.int64); t_dets = np.zeros(max(total, 1), np.int64)
     t_start = np.zeros(total + 1, np.int64); t_max = np.zeros(total + 1, np.float64)
-    T = lib().orc_iou_track(_p(dets), _p(off), C.c_int64(len(frames)), C.c_double(sigma_iou), C.c_double(sigma_h),
-                            C.c_int64(t_min), _p(t_off), _p(t_dets), _p(t_start), _p(t_max))
+    lib().orc_iou_track_metric.restype = C.c_int64
+    T = lib().orc_iou_track_metric(_p(dets), _p(off), C.c_int64(len(frames)), C.c_int(0 if use_iou else 1),
+                                   C.c_double(sigma_iou if use_iou else sigma_dis), C.c_double(sigma_h),
+                                   C.c_int64(t_min), _p(t_off), _p(t_dets), _p(t_start), _p(t_max))
     return dets, t_off[:T + 1], t_dets[:int(t_off[T])], t_start[:T], t_max[:T]
 
 
-def iou_track(frames, sigma_iou=0.4, sigma_h=0.6, t_min=5):
+def iou_track(frames, sigma_iou=0.4, sigma_h=0.6, t_min=5, use_iou=True, sigma_dis=8):
     """-> tracks_finished: list of {'bboxes': [[x1,y1,x2,y2],...], 'max_score': float, 'start_frame': int}"""
-    dets, t_off, t_dets, t_start, t_max = iou_track_raw(frames, sigma_iou, sigma_h, t_min)
+    dets, t_off, t_dets, t_start, t_max = iou_track_raw(frames, sigma_iou, sigma_h, t_min, use_iou, sigma_dis)
     out = []
     for t in range(len(t_start)):
         rows = t_dets[t_off[t]:t_off[t + 1]]
         out.append({'bboxes': dets[rows, :4].tolist(), 'max_score': float(t_max[t]), 'start_frame': int(t_start[t])})
+    return out
+
+
+def detections_to_frames(detections, width, height, thresh=0.4, shrink=1.0):
+    """iouTracke_cal.py:55-84 (detect_face after the network call) for a clip: detections [F, C, top_k, 5] float32 -> list of F arrays
+    [n_f, 5]: class by class the leading rows with score >= thresh (:61-68), boxes * (w, h, w, h) in float32 (:64), / shrink in float32
+    (:76-79: numpy keeps float32 against a python scalar), score appended (:80); the float64 dummy [[0,0,0,0,0.4]] if none (:73-74)."""
+    det = np.asarray(detections, dtype=np.float32)
+    scale = np.array([width, height, width, height], np.float32)
+    out = []
+    for f in range(det.shape[0]):
+        rows = []
+        for i in range(det.shape[1]):
+            j = 0
+            while j < det.shape[2] and det[f, i, j, 0] >= np.float32(thresh):
+                pt = det[f, i, j, 1:] * scale
+                rows.append(np.concatenate([pt / np.float32(shrink), det[f, i, j, :1]]))
+                j += 1
+        out.append(np.array(rows, np.float32).reshape(-1, 5) if rows else np.array([[0, 0, 0, 0, 0.4]]))
     return out
 
 
@@ -288,6 +310,15 @@ def nms_variant(boxes, scores, thresh, flags):
     keep = np.zeros(s.shape[0], dtype=np.int64)
     lib().orc_nms_variant.restype = C.c_int64
     c = lib().orc_nms_variant(_p(b), _p(s), C.c_int64(s.shape[0]), C.c_float(thresh), C.c_int(flags), _p(keep))
+    return keep[:int(c)]
+
+
+def nms_variant_f64(boxes, scores, thresh, flags):
+    """float64 form (MTCNN's nms on float64 dets) -> kept indices in keep order."""
+    b = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 4); s = np.ascontiguousarray(scores, dtype=np.float64).reshape(-1)
+    keep = np.zeros(s.shape[0], dtype=np.int64)
+    lib().orc_nms_variant_f64.restype = C.c_int64
+    c = lib().orc_nms_variant_f64(_p(b), _p(s), C.c_int64(s.shape[0]), C.c_double(thresh), C.c_int(flags), _p(keep))
     return keep[:int(c)]
 
 

@@ -43,7 +43,15 @@ def main():
     sh = (np.arange(B) + 3) % B
     o2 = peer(cu(loc[sh][lo:hi]), cu(conf[sh][lo:hi]), cu(pri)).cpu().numpy()
     outs.append(o2[np.argsort(sh)])
-    ok = nccl.tobytes() == packed.tobytes() and all(o.tobytes() == nccl.tobytes() for o in outs)
+    fails = []
+
+    def check(name, cond):
+        if not cond:
+            fails.append(name)
+            print(f"rank {rank}: CHECK FAILED: {name}", flush=True)
+        return cond
+    ok = check("packed == block", nccl.tobytes() == packed.tobytes())
+    ok = check("peer all-gather (barrier) == nccl", all(o.tobytes() == nccl.tobytes() for o in outs)) and ok
     # gather to a root: only the root's block is written; with the barrier after the kernel, or signalled through symmetric memory
     # (10 calls back to back: more than the ring of gathered blocks and than the workspace ring, a different batch every call so
     # that stale rows can never pass)
@@ -57,8 +65,8 @@ def main():
         torch.cuda.synchronize()
         pr.check()
         if root == "all" or rank == root:
-            for sh, o in got:
-                ok = ok and o.cpu().numpy()[np.argsort(sh)].tobytes() == nccl.tobytes()
+            for it, (sh, o) in enumerate(got):
+                ok = check(f"gather dest={root} signal={signal} call {it}", o.cpu().numpy()[np.argsort(sh)].tobytes() == nccl.tobytes()) and ok
         dist.barrier()
     # MultiBoxLoss sharded over the ranks (multibox_loss.py:130-135: one global normalisation) == one process on the whole batch
     from fdt_b200.layers import MultiBoxLoss
@@ -71,16 +79,19 @@ def main():
     lf = cu(l2).requires_grad_(True); cf = cu(c2).requires_grad_(True)
     fl, fc = MultiBoxLoss(2, 0.35, True, 0, True, 3, 0.35, False)((lf, cf, cu(pri)), [cu(t) for t in targets])
     (fl + fc).backward()
-    ok = ok and np.allclose([float(ll), float(lc)], [float(fl), float(fc)], rtol=1e-5)
-    ok = ok and np.allclose(la.grad.cpu().numpy(), lf.grad[lo:hi].cpu().numpy(), rtol=1e-4, atol=1e-8)
-    ok = ok and np.allclose(ca.grad.cpu().numpy(), cf.grad[lo:hi].cpu().numpy(), rtol=1e-4, atol=1e-8)
+    ok = check("sharded loss == single-process loss", np.allclose([float(ll.detach()), float(lc.detach())], [float(fl.detach()), float(fc.detach())], rtol=1e-5)) and ok
+    ok = check("sharded grad_loc", np.allclose(la.grad.cpu().numpy(), lf.grad[lo:hi].cpu().numpy(), rtol=1e-4, atol=1e-7)) and ok
+    ok = check("sharded grad_conf", np.allclose(ca.grad.cpu().numpy(), cf.grad[lo:hi].cpu().numpy(), rtol=1e-4, atol=1e-7)) and ok
     if rank == 0:
         r = orc_loss(l2, c2, pri, targets)
-        ok = ok and np.allclose([float(ll), float(lc)], [r["loss_l"], r["loss_c"]], rtol=1e-5)
+        same = np.allclose([float(ll.detach()), float(lc.detach())], [r["loss_l"], r["loss_c"]], rtol=1e-5)
+        if not same:
+            print("sharded", float(ll.detach()), float(lc.detach()), "single", float(fl.detach()), float(fc.detach()), "oracle", r["loss_l"], r["loss_c"], flush=True)
+        ok = check("sharded loss == oracle", same) and ok
     if rank == 0:
         from oracle import oracle as orc
         o = orc.Detect(2, 0, 750, 0.05, 0.3); o.early_exit = True
-        ok = ok and nccl.tobytes() == o(loc, conf, pri).tobytes()
+        ok = check("nccl block == oracle", nccl.tobytes() == o(loc, conf, pri).tobytes()) and ok
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:

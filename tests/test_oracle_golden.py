@@ -3,6 +3,8 @@
 import numpy as np
 import pytest
 
+from fdt_b200.synth import clip_detections
+
 from fdt_b200 import synth
 from oracle import oracle as orc
 
@@ -161,20 +163,36 @@ def test_multibox_forward_production_size(golden):
         assert np.array_equal(bti, g["big_bti"][b])
 
 
-@pytest.mark.parametrize("tag", ["a", "b"])
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
 def test_tracker_bit_exact(golden, tag):
+    """a, b: use_iou = True; c, d: use_iou = False (calculate_distance, argmin, < sigma_dis; iouTracke_cal.py:135-138)."""
     g = golden("tracker")
     kw = eval(str(g[f"{tag}_kw"]))
     frames = synth.tracker_frames(**kw)
-    if tag == "a":
+    if tag in ("a", "c"):
         frames[200] = np.array([[0, 0, 0, 0, 0.4]]); frames[201] = np.array([[0, 0, 0, 0, 0.4]])
     assert synth.digest(*frames) == str(g[f"{tag}_in_sha"])
-    tr = orc.iou_track(frames)
+    tr = orc.iou_track(frames, use_iou=tag in ("a", "b"))
     assert [len(t["bboxes"]) for t in tr] == g[f"{tag}_len"].tolist()
     assert [t["start_frame"] for t in tr] == g[f"{tag}_start"].tolist()
     assert np.array_equal(np.array([t["max_score"] for t in tr]), g[f"{tag}_max"])
     bb = np.array([b for t in tr for b in t["bboxes"]], np.float64).reshape(-1, 4)
     assert np.array_equal(bb, g[f"{tag}_bboxes"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_detections_to_frames_and_tracks(golden, tag):
+    """Detect -> tracker chain of iouTracke_cal.py:55-84 + :126-155: per-frame read-out (incl. the dummy row) and the tracks."""
+    g = golden("frames")
+    F, top_k, seed, w, h, shrink = g[f"{tag}_cfg"]
+    det = clip_detections(int(F), int(top_k), int(seed))
+    assert synth.digest(det) == str(g[f"{tag}_in_sha"])
+    frames = orc.detections_to_frames(det, float(w), float(h), 0.4, float(shrink))
+    assert [f.shape[0] for f in frames] == g[f"{tag}_n"].tolist()
+    assert np.array_equal(np.concatenate([np.asarray(f, np.float64) for f in frames], 0), g[f"{tag}_dets"])
+    tr = orc.iou_track(frames)
+    assert [len(t["bboxes"]) for t in tr] == g[f"{tag}_len"].tolist() and [t["start_frame"] for t in tr] == g[f"{tag}_start"].tolist()
+    assert np.array_equal(np.array([b for t in tr for b in t["bboxes"]], np.float64).reshape(-1, 4), g[f"{tag}_bboxes"])
 
 
 def test_calc_performance_functions(golden):

@@ -116,6 +116,70 @@ def test_gpu_nms_variants_vs_oracle(flags, n, seed, thr):
     assert np.array_equal(got, ref)
 
 
+F64_CASES = [("f64_mt_union_06", 0.6, S), ("f64_mt_min_04", 0.4, M), ("f64_plus1_union_05", 0.5, S | P1 | LE), ("f64_fb_np_union_05", 0.5, S)]
+
+
+@pytest.mark.parametrize("key,thr,flags", F64_CASES)
+def test_oracle_nms_f64_matches_reference(golden, key, thr, flags):
+    """float64 dets through the reference's own MTCNN / FaceBoxes NMS (the dtype its pipeline uses)."""
+    g = golden("siblings")
+    d = g["dets64"]
+    assert d.dtype == np.float64 and np.array_equal(orc.nms_variant_f64(d[:, :4], d[:, 4], thr, flags), g[key])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key,thr,flags", F64_CASES)
+def test_gpu_nms_f64_fixture(golden, key, thr, flags):
+    from fdt_b200.siblings import mtcnn
+    from fdt_b200.siblings._nms import nms_variant
+    g = golden("siblings")
+    d = g["dets64"]
+    assert np.array_equal(nms_variant(d[:, :4], d[:, 4], thr, flags, keep_dtype=True).cpu().numpy(), g[key])
+    if key == "f64_mt_union_06":
+        assert mtcnn.nms(d, 0.6, "Union") == g[key].tolist()                  # the drop-in keeps float64 dets in float64
+    if key == "f64_plus1_union_05":
+        assert mtcnn.torch_nms(d, 0.5, "Union") == g[key].tolist()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [0, S, M, S | LE, S | P1 | LE, M | P1 | LE])
+@pytest.mark.parametrize("n,seed,thr", [(1, 1, 0.5), (2, 2, 0.5), (65, 3, 0.3), (1000, 4, 0.5), (4100, 5, 0.6)])
+def test_gpu_nms_f64_vs_oracle(flags, n, seed, thr):
+    """float64 overlap rule on boxes that fp32 cannot represent, incl. degenerate boxes and an overlap that differs between the dtypes."""
+    from fdt_b200.siblings._nms import nms_variant
+    rng = np.random.Generator(np.random.PCG64(900 + seed))
+    d = random_dets(n, 300 * seed + flags).astype(np.float64)
+    d[:, :4] += rng.uniform(-1e-7, 1e-7, (n, 4))
+    d[:, 4] += rng.uniform(0, 1e-10, n)
+    if n >= 65:
+        d[5, :4] = d[9, :4]; d[12, 2] = d[12, 0]; d[20, 3] = d[20, 1] - 3.0; d[30, 1] = np.nan
+    ref = orc.nms_variant_f64(d[:, :4], d[:, 4], thr, flags)
+    got = nms_variant(d[:, :4], d[:, 4], thr, flags, keep_dtype=True).cpu().numpy()
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,top_k,thr", [(9000, 0, 0.5), (20000, 12000, 0.3), (8500, 8400, 0.7)])
+def test_gpu_nms_beyond_the_shared_memory_cap(n, top_k, thr):
+    """layers/box_utils.nms has no candidate cap (box_utils.py:296-298): more than FDT_MAX_NMS_TOP_K candidates take the
+    sort + pairwise-mask + reduce formulation; same keep list as the oracle, also for the sibling rules."""
+    import torch
+    from fdt_b200.layers import box_utils as bu
+    from fdt_b200.siblings._nms import nms_variant
+    pri = synth.priors_numpy(640, 640)
+    rng = np.random.Generator(np.random.PCG64(n))
+    sel = np.sort(rng.permutation(pri.shape[0])[:n])
+    loc = (rng.standard_normal((n, 4)) * 0.5).astype(np.float32)
+    boxes = orc.decode(loc, pri[sel], (0.1, 0.2))
+    scores = rng.permutation(np.unique(rng.uniform(0.05, 1, 3 * n).astype(np.float32)))[:n].copy()
+    keep, count = bu.nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), thr, top_k)
+    rk, rc = orc.nms(boxes, scores, thr, top_k)
+    assert int(count) == rc and np.array_equal(keep.cpu().numpy()[:rc], rk[:rc])
+    assert not keep.cpu().numpy()[rc:].any()
+    if n == 9000:
+        assert np.array_equal(nms_variant(boxes, scores, thr, S | LE).cpu().numpy(), orc.nms_variant(boxes, scores, thr, S | LE))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("thr", [0.0, -1.0, 1.5, float("nan")])
 def test_gpu_nms_variant_degenerate_thresholds(thr):

@@ -23,16 +23,17 @@ def same_tracks(a, b):
         assert x["bboxes"] == y["bboxes"]                      # float64 boxes bit-exact, same append order
 
 
-@pytest.mark.parametrize("tag", ["a", "b"])
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
 @pytest.mark.parametrize("slow", ["0", "1"])
 def test_tracker_golden(tracker, golden, tag, slow, monkeypatch):
+    """a, b: use_iou = True; c, d: use_iou = False (calculate_distance / argmin / < sigma_dis, iouTracke_cal.py:135-138)."""
     monkeypatch.setenv("FDT_TRACK_FORCE_SLOW", slow)          # exercise both the parallel and the sequential path
     g = golden("tracker")
     frames = synth.tracker_frames(**eval(str(g[f"{tag}_kw"])))
-    if tag == "a":
+    if tag in ("a", "c"):
         frames[200] = np.array([[0, 0, 0, 0, 0.4]]); frames[201] = np.array([[0, 0, 0, 0, 0.4]])
     assert synth.digest(*frames) == str(g[f"{tag}_in_sha"])
-    tr = tracker.iou_track(frames)
+    tr = tracker.iou_track(frames, use_iou=tag in ("a", "b"))
     assert [len(t["bboxes"]) for t in tr] == g[f"{tag}_len"].tolist()          # track IDs = list order
     assert [t["start_frame"] for t in tr] == g[f"{tag}_start"].tolist()
     assert np.array_equal(np.array([t["max_score"] for t in tr]), g[f"{tag}_max"])
@@ -50,6 +51,45 @@ def test_tracker_golden(tracker, golden, tag, slow, monkeypatch):
 def test_tracker_vs_oracle(tracker, kw):
     frames = synth.tracker_frames(**kw)
     same_tracks(tracker.iou_track(frames), orc.iou_track(frames))
+
+
+@pytest.mark.parametrize("kw,sigma_dis", [
+    (dict(F=1500, seed=51, d_lo=1, d_hi=300, n_objects=300, empty_every=250), 8),
+    (dict(F=400, seed=52, d_lo=80, d_hi=120, n_objects=120, empty_every=0, sigma=6.0), 20),          # loose gate: many conflicts
+    (dict(F=300, seed=53, d_lo=1, d_hi=4, n_objects=4, empty_every=9), 2),
+])
+def test_tracker_distance_mode_vs_oracle(tracker, kw, sigma_dis):
+    frames = synth.tracker_frames(**kw)
+    same_tracks(tracker.iou_track(frames, use_iou=False, sigma_dis=sigma_dis), orc.iou_track(frames, use_iou=False, sigma_dis=sigma_dis))
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_detections_to_frames_chain_on_device(tracker, golden, tag):
+    """Detect output of a clip -> packed float64 frames (+ dummy rows) -> tracks without leaving the device, against the reference's
+    detect_face read-out and tracker loop (iouTracke_cal.py:55-84, :126-155; fixture made by oracle/make_golden.py::gen_frames)."""
+    import torch
+    g = golden("frames")
+    F, top_k, seed, w, h, shrink = g[f"{tag}_cfg"]
+    det = synth.clip_detections(int(F), int(top_k), int(seed))
+    assert synth.digest(det) == str(g[f"{tag}_in_sha"])
+    d = torch.from_numpy(det).cuda()
+    dets, off = tracker.detections_to_frames(d, float(w), float(h), 0.4, float(shrink))
+    assert dets.dtype == torch.float64 and dets.is_cuda and off.is_cuda
+    assert np.array_equal(np.diff(off.cpu().numpy()), g[f"{tag}_n"])
+    assert np.array_equal(dets.cpu().numpy(), g[f"{tag}_dets"])
+    tr = tracker.track_detections(d, float(w), float(h), 0.4, float(shrink))
+    assert [len(t["bboxes"]) for t in tr] == g[f"{tag}_len"].tolist() and [t["start_frame"] for t in tr] == g[f"{tag}_start"].tolist()
+    assert np.array_equal(np.array([t["max_score"] for t in tr]), g[f"{tag}_max"])
+    assert np.array_equal(np.array([b for t in tr for b in t["bboxes"]], np.float64).reshape(-1, 4), g[f"{tag}_bboxes"])
+    # a longer clip (more than one scan chunk of frames) and NaN / all-below-threshold planes against the oracle
+    det2 = synth.clip_detections(2500, 12, 99)
+    det2[7, 1, 0, 0] = np.nan; det2[8, 1, :, 0] = 0.39
+    d2 = torch.from_numpy(det2).cuda()
+    dets2, off2 = tracker.detections_to_frames(d2, 640.0, 480.0, 0.4, 1.0)
+    ref = orc.detections_to_frames(det2, 640.0, 480.0, 0.4, 1.0)
+    assert np.array_equal(np.diff(off2.cpu().numpy()), [f.shape[0] for f in ref])
+    assert np.array_equal(dets2.cpu().numpy(), np.concatenate([np.asarray(f, np.float64) for f in ref], 0))
+    same_tracks(tracker.track_detections(d2, 640.0, 480.0), orc.iou_track(ref))
 
 
 def test_tracker_parameters_and_edge_frames(tracker):
