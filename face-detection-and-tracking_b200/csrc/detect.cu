@@ -980,7 +980,7 @@ k_sort_nms(const SortNmsParams P)
         // atomics of the sparse form the most expensive part of the kernel).  What does not fit -- a warp with more than WQ_CAP
         // candidates, rows longer than U x 1024 -- is visited in place on every pass: the scores of the first round stay in registers,
         // later rounds are re-read (L2).
-        constexpr int U = FUSED ? 34 : 2;
+        constexpr int U = FUSED ? 36 : 3;                    // 36 x 1024 priors per scan (a 640 x 640 image has 34,125)
         constexpr int WQ_CAP = (SM_WSTART - SM_SEGS) / 8 / (K3_THREADS / 32);          // 288 keys per warp
         int wq_n = 0;                                        // warp-uniform: queue length
         bool scanned = false, wq_ovf = false;                // wq_ovf: the warp's candidates did not fit, it visits its priors in place
@@ -992,36 +992,42 @@ k_sort_nms(const SortNmsParams P)
                 if (!scanned) {
                     scanned = true;
                     // ballot compaction into the warp's queue; positions beyond the queue collapse onto its last entry and the
-                    // warp then visits ALL its priors in place on every pass: no bookkeeping inside the loop.  Two half rounds of
-                    // 17 loads per thread in flight (the registers of 34 would spill).
-                    constexpr int UH = U / 2;
+                    // warp then visits ALL its priors in place on every pass: no bookkeeping inside the loop.  The U loads are issued
+                    // in NG groups, group g + 1 before group g is compacted: two groups in flight hide the HBM latency without the
+                    // register spills of all U at once.
+                    constexpr int NG = FUSED ? 4 : 3, UG = U / NG;
                     const float qnan = __int_as_float(0x7fc00000);                          // never a candidate
                     const unsigned lt = (1u << lane) - 1u;
                     const uint32_t qaddr = (uint32_t)__cvta_generic_to_shared(wq);
                     int run = 0;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        float sv[UH];
-                        const int i0 = tid + h * UH * K3_THREADS;
+                    float sv[NG][UG];
+                    auto load_group = [&](const int g) {
+                        const int i0 = tid + g * UG * K3_THREADS;
                         if (Cc == 2) {                                                       // (addresses fold into the load immediates)
                             const float *p0 = crow + 2 * i0;
 #pragma unroll
-                            for (int u = 0; u < UH; ++u) sv[u] = i0 + u * K3_THREADS < Nn ? __ldg(p0 + 2 * u * K3_THREADS) : qnan;
+                            for (int u = 0; u < UG; ++u) sv[g][u] = i0 + u * K3_THREADS < Nn ? __ldg(p0 + 2 * u * K3_THREADS) : qnan;
                         } else {
 #pragma unroll
-                            for (int u = 0; u < UH; ++u) {
+                            for (int u = 0; u < UG; ++u) {
                                 const int i = i0 + u * K3_THREADS;
-                                sv[u] = i < Nn ? __ldg(crow + (int64_t)i * Cc) : qnan;
+                                sv[g][u] = i < Nn ? __ldg(crow + (int64_t)i * Cc) : qnan;
                             }
                         }
+                    };
+                    load_group(0);
 #pragma unroll
-                        for (int u = 0; u < UH; ++u) {
-                            const bool c = sv[u] > cthr;                                     // detection.py:64 strict gt
+                    for (int g = 0; g < NG; ++g) {
+                        if (g + 1 < NG) load_group(g + 1);
+                        const int i0 = tid + g * UG * K3_THREADS;
+#pragma unroll
+                        for (int u = 0; u < UG; ++u) {
+                            const bool c = sv[g][u] > cthr;                                  // detection.py:64 strict gt
                             const unsigned bal = __ballot_sync(0xffffffffu, c);
                             if (c) {
                                 const int idx = min(run + __popc(bal & lt), WQ_CAP - 1);
                                 asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(qaddr + 8u * (uint32_t)idx), "r"((uint32_t)(i0 + u * K3_THREADS)),
-                                             "r"(fdt_float_key(sv[u])) : "memory");
+                                             "r"(fdt_float_key(sv[g][u])) : "memory");
                             }
                             run += __popc(bal);
                         }
@@ -1540,6 +1546,12 @@ k_sort_nms(const SortNmsParams P)
     if (P.prof && tid == 0 && blockIdx.x < 256) { unsigned long long gt1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1)); atomicMin((unsigned long long *)&P.prof[40], gt0); atomicMax((unsigned long long *)&P.prof[41], gt0); atomicMin((unsigned long long *)&P.prof[42], gt1); atomicMax((unsigned long long *)&P.prof[43], gt1); P.prof[64 + blockIdx.x] = clock64() - cta_t0; P.prof[320 + blockIdx.x] = (long long)rounds * 100000 + k; }
     if (!writer) return;
     const bool gather = MODE == MODE_DETECT && P.peer_sig != nullptr;
+    // Completion ticket (see the end of the kernel).  Fused call, local output, kept rows in shared memory: `done` only has to say
+    // that every CTA is past its NMS, so the ticket is taken HERE and its round trip to L2 overlaps the output stores instead of
+    // holding the SM (and its 200 KB of shared memory) at the very end.
+    const bool early_ticket = FUSED && !gather && P.S.ctl != nullptr && P.sm.off_kbox >= 0;
+    int my_ticket = -1;
+    if (early_ticket && tid == 0) my_ticket = atomicAdd(ticket, 1);
     bool peer_ok = true;
     if (gather) {
         // Rows of epoch e go into block e % ring of every destination rank: that rank must be done with what epoch e - ring left
@@ -1621,11 +1633,14 @@ k_sort_nms(const SortNmsParams P)
         //   * publishes done = seq once the previous call has completed (in-order completion, see "call sequencing").
         // (fused, local output: `done` only has to say that every CTA has reached its end -- grids retire in stream order, and a
         // call that writes the same buffers again takes the full dependency wait -- so the stores need not be fenced here)
-        if (!FUSED || gather) __threadfence();
-        __syncthreads();
+        if (!early_ticket) {
+            if (!FUSED || gather) __threadfence();
+            __syncthreads();
+            if (tid == 0) my_ticket = atomicAdd(ticket, 1);
+        }
         if (tid == 0) {
             const int writers = (int)(gridDim.x / CL);
-            if (atomicAdd(ticket, 1) == writers - 1) {
+            if (my_ticket == writers - 1) {
                 *ticket = 0;                                   // (a stage-2 launch may be repeated on the same slot)
                 DetectCtl *ctl = P.S.ctl;
                 if (gather) {

@@ -53,7 +53,8 @@ constexpr int MINE_REPL = 16;               // level-0 histogram copies (by prio
 // fdt_key_float turns back into a NaN.
 __device__ __forceinline__ unsigned gmax_key_of(float v) { return v != v ? 0xffffffffu : fdt_float_key(v); }
 
-__device__ __forceinline__ unsigned long long mine_comp(float v, unsigned p) { return ((unsigned long long)fdt_float_key(v) << 32) | (unsigned)~p; }
+// (a NaN loss ranks highest whatever its sign bit, as torch.sort does)
+__device__ __forceinline__ unsigned long long mine_comp(float v, unsigned p) { return ((unsigned long long)(v != v ? 0xffffffffu : fdt_float_key(v)) << 32) | (unsigned)~p; }
 
 struct GtTile {
     float4 box[GT_TILE];

@@ -204,6 +204,37 @@ def test_multibox_backward_matches_autograd(layers, golden):
     np.testing.assert_allclose([float(ll), float(lc)], [float(rl), float(rc)], rtol=1e-5)
 
 
+@pytest.mark.parametrize("bip", [0, 1])
+def test_multibox_sign_bit_nan_logit_poisons_the_global_max(layers, bip):
+    """x.max() of log_sum_exp (box_utils.py:268) propagates ANY NaN, also x86's default quiet NaN with the sign bit set, which
+    an order-preserving key alone would rank lowest: every row of the mining loss becomes NaN, exactly as in the oracle."""
+    pri = synth.priors_numpy(160, 160)
+    loc, conf, targets = synth.multibox_inputs(3, pri, 66, 1, 12)
+    conf = conf.copy()
+    conf.view(np.uint32)[1, 77, 0] = 0xFFC00000                                  # -NaN
+    assert np.isnan(conf[1, 77, 0]) and np.signbit(conf[1, 77, 0])
+    dev = torch.device("cuda", torch.cuda.current_device())
+    from fdt_b200 import _lib
+    from fdt_b200.layers.modules.multibox_loss import pack_targets
+    l, c, p = cu(loc), cu(conf), cu(pri)
+    gt, off, total = pack_targets([cu(t) for t in targets], dev)
+    B, N = 3, pri.shape[0]
+    losses = torch.empty(2, device=dev); norm = torch.empty(1, device=dev)
+    loc_t = torch.empty((B, N, 4), device=dev); conf_t = torch.empty((B, N), dtype=torch.int64, device=dev)
+    sel = torch.empty((B, N), dtype=torch.uint8, device=dev); lca = torch.empty((B, N), device=dev)
+    L = _lib.lib()
+    ws = _lib.workspace(L.fdt_multibox_workspace_bytes(B, N, 2, total), dev, "t-nan")
+    _lib.check(L.fdt_multibox_loss_forward(l.data_ptr(), c.data_ptr(), p.data_ptr(), gt.data_ptr(), off.data_ptr(), total, B, N, 2,
+                                           0.35, 3, bip, 0.1, 0.2, losses.data_ptr(), norm.data_ptr(), loc_t.data_ptr(), conf_t.data_ptr(),
+                                           sel.data_ptr(), lca.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+    r = orc.multibox_loss(loc, conf, pri, targets, 0.35, 3, bool(bip), VAR)
+    got = npy(lca)
+    pos = r["conf_t"] > 0
+    assert np.isnan(got[~pos]).all() and np.isnan(r["loss_c_all"][~pos]).all()  # every non-positive row is NaN on both sides
+    assert np.array_equal(npy(conf_t), r["conf_t"])
+    assert np.array_equal(npy(sel).astype(bool), r["neg"] | pos)                 # all-NaN ties: lower prior index first on both sides
+
+
 def test_multibox_cpu_tensor_inputs(layers, golden):
     g = golden("multibox")
     pri = g["small_priors"]
