@@ -188,7 +188,7 @@ def config5():
     p = torch.from_numpy(pri).to(dev)
     det = Detect(2, 0, 750, 0.05, 0.3)
     res = {}
-    variants = [("single", det)] if world == 1 else [("peer_gather_to_rank0", PeerGatherDetect(det, B, dest=0)), ("peer_all_gather", PeerGatherDetect(det, B)),
+    variants = [("single", det)] if world == 1 else [("peer_gather_to_rank0", PeerGatherDetect(det, B, dest=0, signal="kernel")), ("peer_all_gather", PeerGatherDetect(det, B, dest="all", signal="kernel")),
                                                        ("nccl_all_gather", ShardedDetect(det, gather="block"))]
     for name, fn in variants:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

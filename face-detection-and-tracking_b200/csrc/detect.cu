@@ -1234,17 +1234,23 @@ k_sort_nms(const SortNmsParams P)
     GridGeom gg;
     gg.ok = 0; gg.x0 = gg.y0 = gg.inv0 = gg.c0 = 0.0f;
 
+    // Window size.  Detect stops at max_keep kept boxes, so a window only needs the candidates that get it there: the first one takes
+    // 1.2 x max_keep (+16) of them, later ones what the keep rate of the previous window predicts (+1/8 + 32) -- at least one whole
+    // bucket more than the largest bucket of the range (BIG_BUCKET), at most WIN.  Windows are consumed in score order whatever their
+    // size, so the result does not depend on it; a short window leaves warps idle in every phase of the round.
+    int win_cap = WIN;
+    if (MODE == MODE_DETECT) win_cap = min(WIN, max(BIG_BUCKET + 64, (max_keep * 6) / 5 + 16));
     for (int lo = 0; lo < k && nkept < max_keep; ++rounds) {
-        // ---- window [lo, hi): whole buckets, at most WIN candidates
+        // ---- window [lo, hi): whole buckets, at most win_cap candidates
         int hi;
-        if (presorted) hi = min(lo + WIN, k);
+        if (presorted) hi = min(lo + win_cap, k);
         else {
-            const int e = min(lo + WIN, placed);
+            const int e = min(lo + win_cap, placed);
             if (e == placed) hi = placed;
             else {
                 const int bq = bucket(skeys[e - 1]);
                 const int bend = s_start[bq] + s_hist[bq];
-                hi = (bend == e) ? e : s_start[bq];          // buckets in range are <= BIG_BUCKET < WIN, so hi > lo
+                hi = (bend == e) ? e : s_start[bq];          // buckets in range are <= BIG_BUCKET < win_cap, so hi > lo
             }
         }
         for (int i = tid; i <= NCELLX; i += K3_THREADS) { wstart[i] = 0; kstart[i] = 0; }
@@ -1528,6 +1534,10 @@ k_sort_nms(const SortNmsParams P)
                 kbox[slot] = sbox[ps]; karea[slot] = sarea[ps]; kkey[slot] = skeys[j]; kcell[slot] = wcell[tid];
             }
             nkept = min(nkept + tot, max_keep);
+            if (MODE == MODE_DETECT) {
+                const int est = (int)(((long long)(max_keep - nkept) * nvalid) / max(tot, 1));
+                win_cap = min(WIN, max(BIG_BUCKET + 64, est + (est >> 3) + 32));
+            }
         }
         __syncthreads();
         K3_ACC(6);

@@ -20,7 +20,7 @@ from fdt_b200.sharding import PeerGatherDetect, ShardedDetect, shard_range  # no
 
 def orc_loss(loc, conf, pri, targets):
     from oracle import oracle as orc
-    return orc.multibox_loss(loc, conf, pri, targets, 0.35, 3, False, want_aux=False)
+    return orc.multibox_loss(loc, conf, pri, targets, 0.35, 3, True, want_aux=False)      # bipartite=True: MultiBoxLoss' default (multibox_loss.py:33)
 
 
 def main():

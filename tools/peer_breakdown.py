@@ -1,104 +1,103 @@
-"""Diagnostics (torchrun, >= 2 GPUs): what the fused multi-GPU gather adds to the Detect step (headline shape, 64 images per rank):
-local output / rows stored into every rank's block / + symmetric-memory barrier."""
+"""Diagnostics (torchrun, >= 2 GPUs): what the multi-GPU gather adds to the Detect step (headline shape, 64 images per rank), as the
+step is timed by bench.py -- K calls back to back per variant, max over ranks -- and per rank, so that the limiter shows:
+
+  local            every rank runs fdt_detect into its own output (no exchange)
+  gather signalled rows stored into rank 0's gathered block by the NMS kernel, completion signals through symmetric memory
+  all-gather sig.  rows stored into every rank's block, signalled
+  gather + barrier rows stored into rank 0's block, symmetric-memory barrier after every call
+  nccl             local output + NCCL all_gather_into_tensor
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/peer_breakdown.py [K]
+"""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import torch
 import torch.distributed as dist
-import fdt_b200
+import fdt_b200  # noqa: F401
 from fdt_b200 import _lib, synth
 from fdt_b200.layers import Detect
 from fdt_b200.sharding import PeerGatherDetect
 
+K = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 B, C, TOP_K = 64, 2, 750
 pri_np = synth.priors_numpy(640, 640)
-loc_np, conf_np = synth.detect_inputs(B, pri_np, 20262 + rank, 0.05, "random")
 N = pri_np.shape[0]
-loc, conf, pri = (torch.from_numpy(a).to(dev) for a in (loc_np, conf_np, pri_np))
+sets = [tuple(torch.from_numpy(a).to(dev) for a in synth.detect_inputs(B, pri_np, 20262 + rank + 1000 * r, 0.05)) for r in range(3)]
+pri = torch.from_numpy(pri_np).to(dev)
 det = Detect(2, 0, TOP_K, 0.05, 0.3)
-peer = PeerGatherDetect(det, B)
 L = _lib.lib()
-out = torch.empty((B, C, TOP_K, 5), device=dev)
-ws = _lib.workspace(L.fdt_detect_workspace_bytes(B, N, C), dev, "diag")
 st = _lib.stream_ptr()
-flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+ws = torch.empty(L.fdt_detect_workspace_bytes_depth(B, N, C, 4), dtype=torch.uint8, device=dev)
+outs = [torch.empty((B, C, TOP_K, 5), device=dev) for _ in range(4)]
+gathered = [torch.empty((world * B, C, TOP_K, 5), device=dev) for _ in range(4)]
+step_no = [0]
 
 
-def k2():
-    _lib.check(L.fdt_detect_threshold_compact(conf.data_ptr(), B, N, C, 0.05, ws.data_ptr(), ws.numel(), st))
+def args12():
+    l, c = sets[step_no[0] % 3]
+    return (l.data_ptr(), c.data_ptr(), pri.data_ptr(), B, N, C, TOP_K, 5000, 0.05, 0.3, 0.1, 0.2)
 
 
 def local_step():
-    k2()
-    _lib.check(L.fdt_detect_sort_nms(loc.data_ptr(), pri.data_ptr(), B, N, C, TOP_K, 5000, 0.3, 0.1, 0.2, out.data_ptr(), None, None,
-                                     ws.data_ptr(), ws.numel(), st))
+    _lib.check(L.fdt_detect(*args12(), outs[step_no[0] % 4].data_ptr(), None, None, ws.data_ptr(), ws.numel(), st))
 
 
-def peers(barrier):
+def make_peer(dest, signal):
+    peer = PeerGatherDetect(det, B, dest=dest, signal=signal)
+
     def f():
         hdl = peer.hdls[peer.turn]
-        peer.turn ^= 1
-        k2()
-        _lib.check(L.fdt_detect_sort_nms_peers(loc.data_ptr(), pri.data_ptr(), B, N, C, TOP_K, 5000, 0.3, 0.1, 0.2,
-                                               int(hdl.buffer_ptrs_dev), world, rank * B, ws.data_ptr(), ws.numel(), st))
-        if barrier:
+        peer.turn = (peer.turn + 1) % peer.RING
+        ptrs, n_dst = peer.dest_ptrs(hdl)
+        if signal == "kernel":
+            peer.epoch += 1
+            _lib.check(L.fdt_detect_gather_signal(*args12(), ptrs, n_dst, int(peer.sig_hdl.buffer_ptrs_dev), world, rank,
+                                                  -1 if dest == "all" else int(dest), peer.epoch, peer.RING, rank * B, ws.data_ptr(), ws.numel(), st))
+        else:
+            _lib.check(L.fdt_detect_peers(*args12(), ptrs, n_dst, rank * B, ws.data_ptr(), ws.numel(), st))
             hdl.barrier()
     return f
 
 
-peer_sig = PeerGatherDetect(det, B, dest=0, signal="kernel")
-peer_root = PeerGatherDetect(det, B, dest=0)
+def nccl_step():
+    o = outs[step_no[0] % 4]
+    _lib.check(L.fdt_detect(*args12(), o.data_ptr(), None, None, ws.data_ptr(), ws.numel(), st))
+    dist.all_gather_into_tensor(gathered[step_no[0] % 4], o)
 
 
-def root_barrier():
-    hdl = peer_root.hdls[peer_root.turn]
-    peer_root.turn ^= 1
-    k2()
-    ptrs, n_dst = peer_root.dest_ptrs(hdl)
-    _lib.check(L.fdt_detect_sort_nms_peers(loc.data_ptr(), pri.data_ptr(), B, N, C, TOP_K, 5000, 0.3, 0.1, 0.2, ptrs, n_dst, rank * B,
-                                           ws.data_ptr(), ws.numel(), st))
-    hdl.barrier()
-
-
-def root_signal():
-    hdl = peer_sig.hdls[peer_sig.turn]
-    peer_sig.turn ^= 1
-    peer_sig.epoch += 1
-    k2()
-    _lib.check(L.fdt_detect_sort_nms_gather_signal(loc.data_ptr(), pri.data_ptr(), B, N, C, TOP_K, 5000, 0.3, 0.1, 0.2,
-                                                   int(hdl.buffer_ptrs_dev), int(peer_sig.sig_hdl.buffer_ptrs_dev), world, rank, 0, peer_sig.epoch,
-                                                   rank * B, ws.data_ptr(), ws.numel(), st))
-
-
-def barrier_only():
-    peer.hdls[0].barrier()
-
-
-def timed(fn, reps=30):
-    ts = []
-    for i in range(reps + 5):
-        flush.zero_()
-        dist.barrier()
-        torch.cuda._sleep(400_000)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record()
+def timed(fn):
+    for _ in range(5):
+        fn(); step_no[0] += 1
+    res = []
+    for _ in range(5):
         torch.cuda.synchronize()
-        if i >= 5:
-            ts.append(a.elapsed_time(b) * 1e3)
-    t = torch.tensor([float(np.mean(ts))], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+        dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(2_000_000)
+        a.record()
+        for _ in range(K):
+            fn(); step_no[0] += 1
+        b.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        res.append(a.elapsed_time(b) * 1e3 / K)
+    mine = sorted(res)[len(res) // 2]
+    t = torch.tensor([mine], dtype=torch.float64, device=dev)
+    allr = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allr, t)
+    return [float(x.item()) for x in allr]
 
 
-for name, fn in (("local output", local_step), ("peer stores, no barrier", peers(False)), ("peer stores + barrier", peers(True)),
-                 ("gather to rank 0 + barrier", root_barrier), ("gather to rank 0, kernel signal", root_signal),
-                 ("barrier alone", barrier_only)):
-    v = timed(fn)
+variants = [("local (no exchange)", local_step), ("gather to rank 0, signalled", make_peer(0, "kernel")),
+            ("all-gather, signalled", make_peer("all", "kernel")), ("gather to rank 0 + barrier", make_peer(0, "barrier")),
+            ("nccl all-gather", nccl_step)]
+for name, fn in variants:
+    per_rank = timed(fn)
     if rank == 0:
-        print(f"{name:28s} {v:7.1f} us (max over {world} ranks)")
+        print(f"{name:30s} max {max(per_rank):6.2f} us/step   per rank: " + " ".join(f"{v:6.2f}" for v in per_rank), flush=True)
 dist.destroy_process_group()
