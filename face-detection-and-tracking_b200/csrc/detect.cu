@@ -163,8 +163,11 @@ struct DetectCtl {
     unsigned long long outs[FDT_DETECT_MAX_DEPTH][3];      // out / counts / kept_prior of the last R calls
 };
 static_assert(sizeof(DetectCtl) <= 256, "control block is 256 bytes");
+constexpr int FDT_GATHER_RING_MAX = 8;
 struct DetectSlots {
     DetectCtl *ctl;                    // null: no sequencing (fdt_nms), `base` is the only slot
+    int32_t *gather_rows;              // [FDT_GATHER_RING_MAX][lists]: rows this rank left in gathered block (epoch % ring) of the destinations
+    int gather_n;                      // FDT_GATHER_RING_MAX * lists
     char *base;                        // slot 0
     size_t stride;                     // bytes per slot
     size_t keys_off, kept_off;         // inside a slot: counters | keys | kept rows
@@ -217,6 +220,7 @@ k_detect_begin(const DetectSlots S, const unsigned long long magic, const int li
             for (int q = 0; q < FDT_DETECT_MAX_DEPTH; ++q) { v->outs[q][0] = 0; v->outs[q][1] = 0; v->outs[q][2] = 0; }
             v->error = 0; v->k3s = seq; v->done = seq;
             for (int q = 0; q < FDT_DETECT_MAX_DEPTH; ++q) v->ticket[q] = 0;
+            for (int q = 0; q < S.gather_n; ++q) S.gather_rows[q] = 0;          // (the destinations' gathered blocks start zeroed)
         } else {
             if (k3s != seq) {
                 // the previous call never launched its k_sort_nms (stage 1 alone): it is void.  Its K2 is our predecessor.
@@ -1024,11 +1028,11 @@ k_sort_nms(const SortNmsParams P)
                         for (int u = 0; u < UG; ++u) {
                             const bool c = sv[g][u] > cthr;                                  // detection.py:64 strict gt
                             const unsigned bal = __ballot_sync(0xffffffffu, c);
-                            if (c) {
-                                const int idx = min(run + __popc(bal & lt), WQ_CAP - 1);
-                                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(qaddr + 8u * (uint32_t)idx), "r"((uint32_t)(i0 + u * K3_THREADS)),
-                                             "r"(fdt_float_key(sv[g][u])) : "memory");
-                            }
+                            const int idx = min(run + __popc(bal & lt), WQ_CAP - 1);
+                            // predicated store, no branch: a divergent `if` costs a BSSY / BRA / BSYNC triple per prior
+                            asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p st.shared.v2.u32 [%0], {%1, %2}; }"
+                                         :: "r"(qaddr + 8u * (uint32_t)idx), "r"((uint32_t)(i0 + u * K3_THREADS)), "r"(fdt_float_key(sv[g][u])),
+                                            "r"((unsigned)c) : "memory");
                             run += __popc(bal);
                         }
                     }
@@ -1592,8 +1596,18 @@ k_sort_nms(const SortNmsParams P)
         constexpr int CH = 1600;                                             // rows per chunk: 32,000 bytes
         float *stage0 = reinterpret_cast<float *>(smem + SM_SEGS);
         const int ndst = P.n_peers > 0 ? P.n_peers : 1;
-        for (int r0 = 0; r0 < top_k && peer_ok; r0 += CH) {
-            const int nr = min(CH, top_k - r0), nf = nr * 5;
+        // Signalled gather: the destination blocks start zeroed and only this protocol writes them, so a plane only needs its `cnt`
+        // rows plus zeros over whatever the epoch that used the same ring block last (epoch - ring) left beyond them -- real images
+        // have a few detections, not top_k: the NVLink traffic follows the detections, not the padding.
+        int rows_w = top_k;
+        if (gather && peer_ok && P.ring <= FDT_GATHER_RING_MAX) {
+            int32_t *left = P.S.gather_rows + (size_t)(P.epoch % (unsigned)P.ring) * (gridDim.x / CL) + list;
+            rows_w = max(cnt, min(top_k, *left));
+            __syncthreads();                                                 // everybody has read the old value
+            if (tid == 0) *left = cnt;
+        }
+        for (int r0 = 0; r0 < rows_w && peer_ok; r0 += CH) {
+            const int nr = min(CH, rows_w - r0), nf = nr * 5;
             int staged_ph = -1;
             for (int pr = 0; pr < ndst; ++pr) {
                 float *base = P.n_peers > 0 ? reinterpret_cast<float *>(P.peer_out[pr]) + (P.img_offset * P.C) * (int64_t)top_k * 5 : P.out;
@@ -1623,7 +1637,7 @@ k_sort_nms(const SortNmsParams P)
                 const int tail0 = lead + 4 * nq;
                 if (tid < nf - tail0) o[tail0 + tid] = stage[tail0 + tid];
             }
-            if (r0 + CH < top_k) __syncthreads();
+            if (r0 + CH < rows_w) __syncthreads();
         }
         if (P.kept_prior) {
             int64_t *kp = P.kept_prior + (int64_t)(b * P.C + cl) * top_k;
@@ -1695,7 +1709,7 @@ constexpr int K3_STATIC_SMEM = 2 * 1024;         // small arrays declared __shar
 
 // ---- process-wide options: read from the environment once, overridable through fdt_set_option (tests, tools)
 struct Options {
-    std::atomic<int> k3_profile, k3_cluster, k3_pdl, detect_depth, detect_fused;
+    std::atomic<int> k3_profile, k3_cluster, k3_pdl, detect_depth, detect_fused, detect_prefetch;
     Options()
     {
         auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e && *e ? atoi(e) : dflt; };
@@ -1704,6 +1718,7 @@ struct Options {
         k3_pdl = env_int("FDT_K3_PDL", 1);
         detect_depth = env_int("FDT_DETECT_DEPTH", FDT_DETECT_MAX_DEPTH);
         detect_fused = env_int("FDT_DETECT_FUSED", -1);      // -1: automatic
+        detect_prefetch = env_int("FDT_DETECT_PREFETCH", 1);
     }
 };
 static Options &options() { static Options o; return o; }
@@ -1817,6 +1832,7 @@ int launch_sort_nms(SortNmsParams &P, int lists, int kcap, void *kept_ws, size_t
 // Workspace of the Detect family: [control block 256 B][slot 0][slot 1] ... ; slot = int32 [3][lists] (candidate count, max key,
 // ~min key) + 1 completion ticket | uint64 keys[lists][N] | kept rows (only used when top_k rows exceed shared memory).
 struct DetectWsPlan {
+    size_t head_bytes;                 // control block + gather_rows
     size_t counters_bytes, keys_bytes, kept_bytes, slot_bytes;
     int lists;
 };
@@ -1830,17 +1846,20 @@ static DetectWsPlan detect_ws_plan(int B, int64_t N, int C)
     w.keys_bytes = fdt_align256(lists * (size_t)N * sizeof(uint64_t));
     w.kept_bytes = fdt_align256(lists * kept_rows * KEPT_ROW_BYTES);
     w.slot_bytes = w.counters_bytes + w.keys_bytes + w.kept_bytes;
+    w.head_bytes = 256 + fdt_align256((size_t)FDT_GATHER_RING_MAX * lists * sizeof(int32_t));
     return w;
 }
 static DetectSlots detect_slots(void *ws, size_t ws_bytes, const DetectWsPlan &w)
 {
     DetectSlots S;
     S.ctl = (DetectCtl *)ws;
-    S.base = (char *)ws + 256;
+    S.gather_rows = (int32_t *)((char *)ws + 256);
+    S.gather_n = FDT_GATHER_RING_MAX * w.lists;
+    S.base = (char *)ws + w.head_bytes;
     S.stride = w.slot_bytes;
     S.keys_off = w.counters_bytes;
     S.kept_off = w.counters_bytes + w.keys_bytes;
-    size_t fit = (ws_bytes - 256) / w.slot_bytes;
+    size_t fit = (ws_bytes - w.head_bytes) / w.slot_bytes;
     int cap = options().detect_depth.load();
     if (cap < 1) cap = 1;
     if (cap > FDT_DETECT_MAX_DEPTH) cap = FDT_DETECT_MAX_DEPTH;
@@ -1866,7 +1885,8 @@ FDT_API size_t fdt_detect_workspace_bytes_depth(int B, int64_t N, int C, int dep
     if (B <= 0 || N <= 0 || C <= 1) return 256;
     if (depth < 1) depth = 1;
     if (depth > FDT_DETECT_MAX_DEPTH) depth = FDT_DETECT_MAX_DEPTH;
-    return 256 + (size_t)depth * detect_ws_plan(B, N, C).slot_bytes;
+    const DetectWsPlan w = detect_ws_plan(B, N, C);
+    return w.head_bytes + (size_t)depth * w.slot_bytes;
 }
 FDT_API size_t fdt_detect_workspace_bytes(int B, int64_t N, int C) { return fdt_detect_workspace_bytes_depth(B, N, C, 1); }
 
@@ -1880,6 +1900,7 @@ FDT_API int fdt_set_option(const char *name, int value)
     else if (n == "k3_pdl") o.k3_pdl = value;
     else if (n == "detect_depth") o.detect_depth = value;
     else if (n == "detect_fused") o.detect_fused = value;
+    else if (n == "detect_prefetch") o.detect_prefetch = value;
     else { fdt_set_error("fdt_set_option: unknown option '%s'", name); return FDT_E_INVALID; }
     return FDT_OK;
 }
@@ -2022,7 +2043,7 @@ static int detect_sort_nms_impl(const float *loc, const HeadLevels *heads, const
     SortNmsParams P{};
     P.S = detect_slots(ws, ws_bytes, w); P.use_counters = 1; P.key_stride = N; P.k2_blocks = k2_grid_x(N, heads != nullptr) * B;
     P.loc = heads ? nullptr : loc; P.priors = priors; P.N = N; P.C = C;
-    P.loc_prefetch = (!heads && !(flags & FDT_FLAG_LOC_HOST_MAPPED)) ? 1 : 0;
+    P.loc_prefetch = (!heads && !(flags & FDT_FLAG_LOC_HOST_MAPPED) && options().detect_prefetch.load() == 1) ? 1 : 0;
     P.conf = fused_conf; P.conf_thresh = conf_thresh;
     if (heads) P.hl = *heads;
     P.nms_top_k = nms_top_k; P.max_keep = top_k < nms_top_k ? top_k : nms_top_k; P.top_k = top_k;

@@ -35,6 +35,10 @@ def main():
     cu = lambda a: torch.from_numpy(a).cuda()
     det = Detect(2, 0, 750, 0.05, 0.3)
     nccl = ShardedDetect(det, gather="block")(cu(loc[lo:hi]), cu(conf[lo:hi]), cu(pri)).cpu().numpy()
+    # a second batch with FEW detections per image (clustered faces): the signalled gather only ships the rows that exist and
+    # clears what an earlier epoch left behind them in the same ring block
+    loc_c, conf_c = synth.detect_inputs(B, pri, 778, 0.05, "clustered")
+    nccl_c = ShardedDetect(det, gather="block")(cu(loc_c[lo:hi]), cu(conf_c[lo:hi]), cu(pri)).cpu().numpy()
     packed = ShardedDetect(det, gather="packed")(cu(loc[lo:hi]), cu(conf[lo:hi]), cu(pri)).cpu().numpy()
     outs = []
     peer = PeerGatherDetect(det, b_local)
@@ -58,15 +62,18 @@ def main():
     for root, signal in ((0, "barrier"), (world - 1, "barrier"), (0, "kernel"), (world - 1, "kernel"), ("all", "kernel")):
         pr = PeerGatherDetect(det, b_local, dest=root, signal=signal)
         got = []
-        for it in range(10):
+        for it in range(12):
             sh = (np.arange(B) + it) % B
-            o = pr(cu(loc[sh][lo:hi]), cu(conf[sh][lo:hi]), cu(pri))
-            got.append((sh, o.clone()))        # an ordinary kernel behind the call: on a destination it must see every rank's rows
+            few = it % 3 == 1 or it in (6, 7, 8)                               # full -> few -> full ... and few three times in a row
+            l_, c_ = (loc_c, conf_c) if few else (loc, conf)
+            o = pr(cu(l_[sh][lo:hi]), cu(c_[sh][lo:hi]), cu(pri))
+            got.append((sh, few, o.clone()))   # an ordinary kernel behind the call: on a destination it must see every rank's rows
         torch.cuda.synchronize()
         pr.check()
         if root == "all" or rank == root:
-            for it, (sh, o) in enumerate(got):
-                ok = check(f"gather dest={root} signal={signal} call {it}", o.cpu().numpy()[np.argsort(sh)].tobytes() == nccl.tobytes()) and ok
+            for it, (sh, few, o) in enumerate(got):
+                want = nccl_c if few else nccl
+                ok = check(f"gather dest={root} signal={signal} call {it}", o.cpu().numpy()[np.argsort(sh)].tobytes() == want.tobytes()) and ok
         dist.barrier()
     # MultiBoxLoss sharded over the ranks (multibox_loss.py:130-135: one global normalisation) == one process on the whole batch
     from fdt_b200.layers import MultiBoxLoss
