@@ -172,6 +172,34 @@ def test_inputs_produced_on_stream_between_overlapped_calls(lib):
         assert np.array_equal(t.cpu().numpy(), refs[i % 3]), f"call {i}"
 
 
+@pytest.mark.parametrize("variant", ["fused", "k2+single"])
+def test_refilled_input_buffers_full_batch(lib, variant):
+    """The same two conf / loc buffers are refilled with new contents before every call, at B = 64 (every SM runs CTAs of several
+    calls that read the same addresses): no call may see what an earlier call read there (read-only / L1 cached loads), while the
+    calls overlap wherever the sequencing allows it."""
+    set_variant(lib, variant)
+    pri = synth.priors_numpy(640, 640)
+    N = pri.shape[0]
+    B = 64
+    data = [synth.detect_inputs(B, pri, 6100 + i, 0.05, "random" if i != 1 else "clustered") for i in range(3)]
+    refs = [oracle_detect(l, c, pri)[0] for l, c in data]
+    src = [(cu(l), cu(c)) for l, c in data]
+    p = cu(pri)
+    ws = new_ws(lib, B, N, 2, 4)
+    stage_l = [torch.zeros_like(src[0][0]) for _ in range(2)]
+    stage_c = [torch.zeros_like(src[0][1]) for _ in range(2)]
+    outs = [torch.empty((B, 2, 750, 5), device="cuda") for _ in range(18)]
+    torch.cuda._sleep(5_000_000)
+    for i in range(18):
+        j = i % 2
+        stage_l[j].copy_(src[i % 3][0]); stage_c[j].copy_(src[i % 3][1])
+        c_detect(lib, stage_l[j], stage_c[j], p, ws, outs[i])
+    torch.cuda.synchronize()
+    for i in range(18):
+        assert np.array_equal(outs[i].cpu().numpy(), refs[i % 3]), f"call {i}"
+    assert status(lib, ws) == 0
+
+
 def test_stage1_alone_then_full_calls_and_geometry_change(lib):
     """A stage-1 call that never gets its stage 2 (tests and tools do that) must not wedge the sequencing; neither must a different
     batch geometry on the same workspace memory, nor memory that holds garbage."""
