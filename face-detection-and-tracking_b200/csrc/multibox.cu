@@ -521,20 +521,23 @@ k_mine_select(const float *__restrict__ loss_c, const int *__restrict__ hist0, c
 }
 
 // MODE 0: neg mask only.  MODE 1: sel = pos | neg and CE over the selection (F.cross_entropy, sum).
-// One prior per thread (the kernel is a latency-bound stream over loss_c / conf_t; 4,267 blocks keep every SM full); the CE partial
-// of a block goes to its own slot of `partials` -- no atomics on the single accumulator -- and k_loss_final adds the slots up.
+// A block covers APPLY_TILES consecutive tiles of one image: the fp64 atomicAdd on the single loss accumulator is the serial
+// resource here (one per block), so fewer, longer blocks finish sooner than one block per 256 priors.
+constexpr int APPLY_TILES = 8;
 template <int MODE>
 __global__ void __launch_bounds__(M_THREADS)
 k_mine_apply(const float *__restrict__ loss_c, const unsigned long long *__restrict__ cutoff, const int64_t *__restrict__ conf_t,
-             const float *__restrict__ conf, int64_t N, int C, uint8_t *__restrict__ out_mask, double *__restrict__ partials)
+             const float *__restrict__ conf, int64_t N, int C, uint8_t *__restrict__ out_mask, LossAcc *__restrict__ acc)
 {
     fdt_pdl_enter();
     __shared__ double s_red[M_WARPS];
     const int b = blockIdx.y;
     const unsigned long long cut = cutoff[b];
     double ce = 0.0;
-    const int64_t p = (int64_t)blockIdx.x * M_THREADS + threadIdx.x;
-    if (p < N) {
+#pragma unroll 2
+    for (int u = 0; u < APPLY_TILES; ++u) {
+        const int64_t p = ((int64_t)blockIdx.x * APPLY_TILES + u) * M_THREADS + threadIdx.x;
+        if (p >= N) break;
         const int64_t t = (int64_t)b * N + p;
         const bool neg = cut != ~0ull && mine_comp(loss_c[t], (unsigned)p) >= cut;          // multibox_loss.py:116
         const int64_t label = (MODE == 1) ? conf_t[t] : 0;
@@ -546,31 +549,26 @@ k_mine_apply(const float *__restrict__ loss_c, const unsigned long long *__restr
             for (int c = 1; c < C; ++c) m = fmaxf(m, row[c]);
             double s = 0.0;
             for (int c = 0; c < C; ++c) s += exp((double)(row[c] - m));
-            ce = (log(s) + (double)m) - (double)row[label];                                  // :128
+            ce += (log(s) + (double)m) - (double)row[label];                                 // :128
         }
     }
     if (MODE == 1) {
         ce = block_sum<double>(ce, s_red);
-        if (threadIdx.x == 0) partials[(size_t)b * gridDim.x + blockIdx.x] = ce;
+        if (threadIdx.x == 0 && ce != 0.0) atomicAdd(&acc->loss_c, ce);
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_loss_final(const LossAcc *__restrict__ acc, const int32_t *__restrict__ num_pos, int B, const double *__restrict__ partials, int n_partials,
-             float *__restrict__ losses, float *__restrict__ norm)
+__global__ void k_loss_final(const LossAcc *__restrict__ acc, const int32_t *__restrict__ num_pos, int B,
+                             float *__restrict__ losses, float *__restrict__ norm)
 {
     fdt_pdl_enter();
-    __shared__ double s_red[8];
-    double ce = 0.0;
-    for (int i = threadIdx.x; i < n_partials; i += blockDim.x) ce += partials[i];       // fixed order per thread: deterministic
-    ce = block_sum<double>(ce, s_red);
-    if (threadIdx.x != 0) return;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     long long n = 0;
     for (int b = 0; b < B; ++b) n += num_pos[b];
     double Nn = (double)n;                         // multibox_loss.py:130
     if (n == 0) Nn = (double)B;                    // :132-133
     losses[0] = (float)(acc->loss_l / Nn);
-    losses[1] = (float)(ce / Nn);
+    losses[1] = (float)(acc->loss_c / Nn);
     norm[0] = (float)Nn;
 }
 
@@ -660,12 +658,12 @@ MineWs plan_mine_ws(void *ws, int B)
 
 template <int MODE>
 int launch_mine_tail(const float *loss_c, const MineWs &m, const int64_t *conf_t, const float *conf, int B, int64_t N, int C,
-                     int ratio, uint8_t *mask, double *partials, cudaStream_t st)
+                     int ratio, uint8_t *mask, LossAcc *acc, cudaStream_t st)
 {
     FDT_CUDA(launch_pdl(k_mine_select, dim3(B), dim3(MINE_THREADS), st, loss_c, (const int *)m.hist, (const int32_t *)m.num_pos, N, ratio, m.cutoff));
     FDT_LAUNCH_CHECK();
-    dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
-    FDT_CUDA(launch_pdl(k_mine_apply<MODE>, grid, dim3(M_THREADS), st, loss_c, (const unsigned long long *)m.cutoff, conf_t, conf, N, C, mask, partials));
+    dim3 grid((unsigned)((N + M_THREADS * APPLY_TILES - 1) / (M_THREADS * APPLY_TILES)), (unsigned)B);
+    FDT_CUDA(launch_pdl(k_mine_apply<MODE>, grid, dim3(M_THREADS), st, loss_c, (const unsigned long long *)m.cutoff, conf_t, conf, N, C, mask, acc));
     FDT_LAUNCH_CHECK();
     return FDT_OK;
 }
@@ -722,7 +720,7 @@ FDT_API int fdt_hard_negative_mine(const float *loss_c, const uint8_t *pos, int 
     return launch_mine_tail<0>(loss_c, m, nullptr, nullptr, B, N, 2, negpos_ratio, neg, nullptr, st);
 }
 
-struct LossWs { LossAcc *acc; MineWs mine; float *loss_c_all; double *partials; int n_partials; void *match; size_t bytes; };
+struct LossWs { LossAcc *acc; MineWs mine; float *loss_c_all; void *match; size_t bytes; };
 static LossWs plan_loss_ws(void *ws, int B, int64_t N, int64_t total_gt)
 {
     LossWs w;
@@ -731,8 +729,6 @@ static LossWs plan_loss_ws(void *ws, int B, int64_t N, int64_t total_gt)
     w.acc = (LossAcc *)(p + o); o += 256;
     w.mine = plan_mine_ws(p + o, B); o += w.mine.bytes;
     w.loss_c_all = (float *)(p + o); o += fdt_align256((size_t)B * N * 4);
-    w.n_partials = B * (int)((N + M_THREADS - 1) / M_THREADS);
-    w.partials = (double *)(p + o); o += fdt_align256((size_t)w.n_partials * 8);
     w.match = (void *)(p + o); o += plan_match_ws(nullptr, B, N, total_gt).bytes;
     w.bytes = o;
     return w;
@@ -775,10 +771,9 @@ FDT_API int fdt_multibox_loss_forward(const float *loc, const float *conf, const
     dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
     FDT_CUDA(launch_pdl(k_loss_prior, grid, dim3(M_THREADS), st, (const float4 *)loc, conf, (const float4 *)loc_t, (const int64_t *)conf_t, N, C, w.acc, lca, w.mine.num_pos, w.mine.hist));
     FDT_LAUNCH_CHECK();
-    rc = launch_mine_tail<1>(lca, w.mine, conf_t, conf, B, N, C, negpos_ratio, sel, w.partials, st);
+    rc = launch_mine_tail<1>(lca, w.mine, conf_t, conf, B, N, C, negpos_ratio, sel, w.acc, st);
     if (rc != FDT_OK) return rc;
-    FDT_CUDA(launch_pdl(k_loss_final, dim3(1), dim3(256), st, (const LossAcc *)w.acc, (const int32_t *)w.mine.num_pos, B,
-                        (const double *)w.partials, w.n_partials, losses, norm));
+    FDT_CUDA(launch_pdl(k_loss_final, dim3(1), dim3(32), st, (const LossAcc *)w.acc, (const int32_t *)w.mine.num_pos, B, losses, norm));
     FDT_LAUNCH_CHECK();
     return FDT_OK;
 }
