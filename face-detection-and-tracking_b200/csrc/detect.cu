@@ -150,7 +150,7 @@ k_heads_to_loc_conf(const HeadLevels h, const int N, const int softmax, float *_
 //
 // Slot header: int32 counters[3 * lists] | k2_done | begin_seq.
 constexpr unsigned long long FDT_CTL_MAGIC = 0x4644543262303031ull;      // "FDT2b001"
-constexpr int FDT_DETECT_MAX_DEPTH = 4;
+constexpr int FDT_DETECT_MAX_DEPTH = 4;                                  // (a power of two: ticket index = seq & 3)
 struct DetectCtl {
     unsigned long long magic;          // FDT_CTL_MAGIC ^ geometry hash; anything else: first call on this memory
     unsigned seq;                      // calls begun
@@ -848,12 +848,15 @@ k_sort_nms(const SortNmsParams P)
     if (P.S.ctl) {
         my_seq = detect_call_seq(P.S, &s_seq);
         if (blockIdx.x == 0 && threadIdx.x == 0) { *reinterpret_cast<volatile unsigned *>(&P.S.ctl->k3s) = my_seq; __threadfence(); }
-        char *slot = P.S.base + (size_t)(my_seq % (unsigned)P.S.depth) * P.S.stride;
-        keys_base = reinterpret_cast<const uint64_t *>(slot + P.S.keys_off);
-        counters = P.use_counters ? reinterpret_cast<const int32_t *>(slot) : nullptr;
-        ticket = reinterpret_cast<int *>(&P.S.ctl->ticket[my_seq % (unsigned)P.S.depth]);
-        slot_hdr = reinterpret_cast<const int *>(slot) + 3 * (int)(gridDim.x / CL);
-        slot_kept = slot + P.S.kept_off;
+        // (tickets are indexed by seq & 3: calls s and s + 4 are never in flight together, k_detect_begin(s + 4) waits for done >= s)
+        ticket = reinterpret_cast<int *>(&P.S.ctl->ticket[my_seq & (FDT_DETECT_MAX_DEPTH - 1)]);
+        if (!FUSED || P.sm.off_kbox < 0) {                     // the fused kernel only needs its slot for spilled kept rows
+            char *slot = P.S.base + (size_t)(my_seq % (unsigned)P.S.depth) * P.S.stride;
+            keys_base = reinterpret_cast<const uint64_t *>(slot + P.S.keys_off);
+            counters = P.use_counters ? reinterpret_cast<const int32_t *>(slot) : nullptr;
+            slot_hdr = reinterpret_cast<const int *>(slot) + 3 * (int)(gridDim.x / CL);
+            slot_kept = slot + P.S.kept_off;
+        }
         if (MODE == MODE_DETECT && P.peer_sig && blockIdx.x == 0 && (P.root < 0 || P.root == P.my_rank) &&
             threadIdx.x < P.world && (int)threadIdx.x != P.my_rank) {
             // destination of a fused gather: "call `epoch` has begun here" -> the blocks of epochs <= epoch - 1 have been consumed
@@ -1078,7 +1081,8 @@ k_sort_nms(const SortNmsParams P)
         binv = (float)NB / ((float)(kmax - kmin) + 1.0f);
         uint64_t tmin = 0;                                   // after the fallback select: only keys >= tmin take part
         for (int attempt = 0; attempt < 2; ++attempt) {
-            for_each_key([&](uint64_t key) { if (key >= tmin) atomicAdd(&s_hist[bucket(key)], 1); });
+            if (tmin == 0) for_each_key([&](uint64_t key) { atomicAdd(&s_hist[bucket(key)], 1); });          // (the common case, no 64-bit compare)
+            else for_each_key([&](uint64_t key) { if (key >= tmin) atomicAdd(&s_hist[bucket(key)], 1); });
             __syncthreads();
             // descending exclusive scan: start[b] = number of keys in higher buckets
             int c[NB / K3_THREADS], sum = 0;
