@@ -64,7 +64,10 @@ SIGNATURES = {
     "fdt_debug_k3_profile": (_i, [_vp]),
     "fdt_ctx_create": (_i, [_i, C.POINTER(_vp)]),
     "fdt_ctx_destroy": (_i, [_vp]),
+    "fdt_ctx_set_priors": (_i, [_vp, _vp, _i64]),
     "fdt_detect_host": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp]),
+    "fdt_detect_host_submit": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, C.POINTER(C.c_uint64)]),
+    "fdt_detect_host_wait": (_i, [_vp, C.c_uint64]),
     "fdt_match_workspace_bytes": (_sz, [_i, _i64, _i64]),
     "fdt_match_encode": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fdt_mine_workspace_bytes": (_sz, [_i, _i64]),

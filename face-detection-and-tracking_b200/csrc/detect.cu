@@ -150,7 +150,7 @@ k_heads_to_loc_conf(const HeadLevels h, const int N, const int softmax, float *_
 //
 // Slot header: int32 counters[3 * lists] | k2_done | begin_seq.
 constexpr unsigned long long FDT_CTL_MAGIC = 0x4644543262303031ull;      // "FDT2b001"
-constexpr int FDT_DETECT_MAX_DEPTH = 4;                                  // (a power of two: ticket index = seq & 3)
+// FDT_DETECT_MAX_DEPTH (fdt_common.cuh) = 4 slots at most                // (a power of two: ticket index = seq & 3)
 struct DetectCtl {
     unsigned long long magic;          // FDT_CTL_MAGIC ^ geometry hash; anything else: first call on this memory
     unsigned seq;                      // calls begun
@@ -1713,7 +1713,7 @@ constexpr int K3_STATIC_SMEM = 2 * 1024;         // small arrays declared __shar
 
 // ---- process-wide options: read from the environment once, overridable through fdt_set_option (tests, tools)
 struct Options {
-    std::atomic<int> k3_profile, k3_cluster, k3_pdl, detect_depth, detect_fused, detect_prefetch;
+    std::atomic<int> k3_profile, k3_cluster, k3_pdl, detect_depth, detect_fused, detect_prefetch, host_chunk;
     Options()
     {
         auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e && *e ? atoi(e) : dflt; };
@@ -1723,6 +1723,7 @@ struct Options {
         detect_depth = env_int("FDT_DETECT_DEPTH", FDT_DETECT_MAX_DEPTH);
         detect_fused = env_int("FDT_DETECT_FUSED", -1);      // -1: automatic
         detect_prefetch = env_int("FDT_DETECT_PREFETCH", 1);
+        host_chunk = env_int("FDT_HOST_CHUNK", 16);          // images per copy/compute chunk of fdt_detect_host (0: no chunking)
     }
 };
 static Options &options() { static Options o; return o; }
@@ -1883,6 +1884,8 @@ static unsigned long long detect_geometry_magic(int B, int64_t N, int C, int dep
 
 }  // namespace
 
+int fdt_option_host_chunk() { return options().host_chunk.load(); }
+
 // =============================================================================================== C ABI
 FDT_API size_t fdt_detect_workspace_bytes_depth(int B, int64_t N, int C, int depth)
 {
@@ -1905,6 +1908,7 @@ FDT_API int fdt_set_option(const char *name, int value)
     else if (n == "detect_depth") o.detect_depth = value;
     else if (n == "detect_fused") o.detect_fused = value;
     else if (n == "detect_prefetch") o.detect_prefetch = value;
+    else if (n == "host_chunk") o.host_chunk = value;
     else { fdt_set_error("fdt_set_option: unknown option '%s'", name); return FDT_E_INVALID; }
     return FDT_OK;
 }

@@ -15,6 +15,9 @@ int fdt_detect_flags(const float *loc, const float *conf, const float *priors, i
                      float conf_thresh, float nms_thresh, float var0, float var1, float *out, int32_t *counts, int64_t *kept_prior,
                      void *ws, size_t ws_bytes, void *stream, unsigned flags);
 
+constexpr int FDT_DETECT_MAX_DEPTH = 4;     // slots of the stateful Detect workspace (calls of one stream in flight)
+int fdt_option_host_chunk();     // images per copy/compute chunk of the host-buffer pipeline (hostctx.cu); option "host_chunk"
+
 // greedy NMS for any n and for float64 (nms_generic.cu): sort + pairwise bit mask + serial reduce
 constexpr int FDT_MAX_NMS_GENERIC = 131072;
 size_t fdt_nms_generic_workspace_bytes(int64_t n);

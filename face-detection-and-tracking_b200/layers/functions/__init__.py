@@ -1,5 +1,5 @@
-from .detection import Detect
+from .detection import Detect, PendingDetections
 from .prior_box import PriorBoxLayer
 from .heads import heads_to_loc_conf
 
-__all__ = ['Detect', 'PriorBoxLayer', 'heads_to_loc_conf']
+__all__ = ['Detect', 'PendingDetections', 'PriorBoxLayer', 'heads_to_loc_conf']

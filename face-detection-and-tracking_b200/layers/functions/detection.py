@@ -103,14 +103,48 @@ class Detect:
         return (out, counts, kept) if return_aux else out
 
     def _call_host(self, loc_data, conf_data, prior_data, args, return_aux):
-        num, num_priors, C_ = args[0], args[1], args[2]
+        return self.submit(loc_data, conf_data, prior_data, return_aux).result()
+
+    def submit(self, loc_data, conf_data, prior_data, return_aux=False):
+        """Asynchronous form of __call__ for HOST tensors (a stream of video batches): enqueues the copies and kernels
+        (fdt_detect_host_submit) and returns a PendingDetections whose .result() blocks until the output landed.  Keeping two
+        batches in flight hides everything but the host-to-device copy of `conf`.  Pinned inputs make the submit non-blocking;
+        the tensors must stay untouched until .result().  A prior tensor that was already uploaded by this thread (same storage,
+        same version counter) is not copied again."""
+        _lib.require_cuda()
+        if loc_data.is_cuda:
+            raise ValueError("Detect.submit is the host-tensor path; CUDA tensors are already asynchronous through __call__")
+        num, num_priors, C_ = loc_data.size(0), prior_data.size(0), self.num_classes
+        args = (num, num_priors, C_, int(self.top_k), int(self.nms_top_k), float(self.conf_thresh),
+                float(self.nms_thresh), float(self.variance[0]), float(self.variance[1]))
         loc = loc_data.detach().to(torch.float32).contiguous()
         conf = conf_data.detach().to(torch.float32).contiguous()
         pri = prior_data.detach().to(torch.float32).contiguous().cpu()
         out = torch.empty((num, C_, self.top_k, 5), dtype=torch.float32, pin_memory=True)
-        counts = torch.empty((num, C_), dtype=torch.int32) if return_aux else None
-        kept = torch.empty((num, C_, self.top_k), dtype=torch.int64) if return_aux else None
-        ctx = _ctx(torch.cuda.current_device())
-        _lib.check(_lib.lib().fdt_detect_host(ctx, _lib.ptr(loc), _lib.ptr(conf), _lib.ptr(pri), *args,
-                                              _lib.ptr(out), _lib.ptr(counts), _lib.ptr(kept)))
-        return (out, counts, kept) if return_aux else out
+        counts = torch.empty((num, C_), dtype=torch.int32, pin_memory=True) if return_aux else None
+        kept = torch.empty((num, C_, self.top_k), dtype=torch.int64, pin_memory=True) if return_aux else None
+        dev_index = torch.cuda.current_device()
+        ctx = _ctx(dev_index)
+        # the prior set is a constant of the model: uploaded once per (thread, device) and tensor.  The cache holds the tensor, so
+        # its storage cannot be recycled under the key; in-place torch writes bump _version (writes through a numpy alias do not).
+        resident = _host_ctx.__dict__.setdefault("priors", {})
+        key = (pri.data_ptr(), pri._version, num_priors)
+        hit = dev_index in resident and resident[dev_index][0] == key
+        ticket = C.c_uint64(0)
+        _lib.check(_lib.lib().fdt_detect_host_submit(ctx, _lib.ptr(loc), _lib.ptr(conf), None if hit else _lib.ptr(pri),
+                                                     *args, _lib.ptr(out), _lib.ptr(counts), _lib.ptr(kept), C.byref(ticket)))
+        resident[dev_index] = (key, pri)
+        return PendingDetections(ctx, ticket.value, (out, counts, kept) if return_aux else out, (loc, conf, pri))
+
+
+class PendingDetections:
+    """Result handle of Detect.submit: .result() waits for the call (fdt_detect_host_wait) and returns what __call__ would."""
+
+    def __init__(self, ctx, ticket, value, keep_alive):
+        self._ctx, self._ticket, self._value, self._keep = ctx, ticket, value, keep_alive
+
+    def result(self):
+        if self._keep is not None:
+            _lib.check(_lib.lib().fdt_detect_host_wait(self._ctx, self._ticket))
+            self._keep = None
+        return self._value

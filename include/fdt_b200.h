@@ -237,14 +237,29 @@ int fdt_detect_heads(const float *const *loc_maps_h, const float *const *conf_ma
 int fdt_debug_k3_profile(long long *out1024_h);  /* [0..31] phases of CTA 0, [64..319] cycles per CTA, [320..575] rounds*1e5 + k per CTA, [640..767] phase-B per warp */
 
 /* ---- host-buffer variants (the reference-facing call when tensors live on the CPU) --------------
- * All pointers are HOST pointers (pinned memory makes the copies asynchronous).  The context owns
- * the stream and grows its device buffers on demand; one context per host thread. */
+ * All pointers are HOST pointers.  The context owns two streams (copies / kernels), device staging slots and the resident prior
+ * set; one context per host thread.  A call is cut into chunks of `host_chunk` images (fdt_set_option, default 16) whose conf
+ * copies overlap the kernels of the chunk before; pinned `loc_h` is gathered in place over PCIe (never copied), pinned `out_h` is
+ * written in place by the kernel.
+ *   fdt_detect_host         submit + wait (returns after the results landed in out_h / counts_h / kept_prior_h)
+ *   fdt_detect_host_submit  enqueues the call and returns a ticket; the host buffers must stay untouched until the wait.  Any
+ *                           number of calls may be in flight; they complete in submission order.  With pageable buffers the
+ *                           copies, hence the submit, block.
+ *   fdt_detect_host_wait    blocks until the call of `ticket` (and every earlier one) has completed
+ *   fdt_ctx_set_priors      uploads a prior set [N,4]; calls that pass priors_h == NULL use the set uploaded last (by this
+ *                           function or by a call that passed priors_h), so a constant set crosses the link once */
 int fdt_ctx_create(int device, fdt_ctx **ctx);
 int fdt_ctx_destroy(fdt_ctx *ctx);
+int fdt_ctx_set_priors(fdt_ctx *ctx, const float *priors_h, int64_t N);
 int fdt_detect_host(fdt_ctx *ctx, const float *loc_h, const float *conf_h, const float *priors_h,
                     int B, int64_t N, int C, int top_k, int nms_top_k,
                     float conf_thresh, float nms_thresh, float var0, float var1,
                     float *out_h, int32_t *counts_h, int64_t *kept_prior_h);
+int fdt_detect_host_submit(fdt_ctx *ctx, const float *loc_h, const float *conf_h, const float *priors_h,
+                           int B, int64_t N, int C, int top_k, int nms_top_k,
+                           float conf_thresh, float nms_thresh, float var0, float var1,
+                           float *out_h, int32_t *counts_h, int64_t *kept_prior_h, uint64_t *ticket);
+int fdt_detect_host_wait(fdt_ctx *ctx, uint64_t ticket);
 
 /* ---- M4/M5  match_default / match_ensure_max_prior (layers/box_utils.py:165-210, 103-162) -------
  * Batched over images: gt[total_gt,5] rows [x1,y1,x2,y2,label], gt_off[B+1] int64 (device).
