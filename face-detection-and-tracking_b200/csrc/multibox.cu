@@ -56,6 +56,20 @@ __device__ __forceinline__ unsigned gmax_key_of(float v) { return v != v ? 0xfff
 // (a NaN loss ranks highest whatever its sign bit, as torch.sort does)
 __device__ __forceinline__ unsigned long long mine_comp(float v, unsigned p) { return ((unsigned long long)(v != v ? 0xffffffffu : fdt_float_key(v)) << 32) | (unsigned)~p; }
 
+// Dispatch order of the matchers: blocks are issued x-fastest, image by image, and the blocks of the coarse pyramid levels (the END of
+// the prior array: a 512-pixel prior overlaps most GT boxes, so its warp walks the whole list) run several times longer than the rest
+// -- in image order the last image's coarse tiles start last and the kernel ends with a dozen SMs finishing them alone (ncu: SMs busy
+// 61 % of the kernel).  Remapped: linear block id -> image = id % B, tile = last - id / B, i.e. every image's last tile first.
+struct MatchBlock { int b; int tile; };
+__device__ __forceinline__ MatchBlock match_block()
+{
+    const int id = blockIdx.y * gridDim.x + blockIdx.x;
+    MatchBlock m;
+    m.b = id % (int)gridDim.y;
+    m.tile = (int)gridDim.x - 1 - id / (int)gridDim.y;
+    return m;
+}
+
 struct GtTile {
     float4 box[GT_TILE];
     float area[GT_TILE];
@@ -78,6 +92,31 @@ __device__ __forceinline__ float iou_match(const float4 a, const float area_a, c
         return q;
     }
     return 0.0f;                                       // 0 / positive
+}
+
+// The default matcher only asks whether a pair's IoU beats the prior's running best (`v > best`, first index wins ties), so the IEEE
+// division is skipped where it cannot: with uni > 0 and best * uni > 0 (hence best > 0, both normal numbers), inter < 0.999999 *
+// RN(best * uni) implies inter / uni < best exactly (RN is within 2^-24 relative of the product), and rounding is monotone, so
+// RN(inter / uni) <= best and the update would not happen.  Returns 0 in that case (0 > best is false as well).  `always` (GT 0, which
+// seeds best with its value whatever it is) and every special case (uni <= 0, NaN, infinities on the wrong side) take the division.
+__device__ __forceinline__ float iou_match_vs_best(const float4 a, const float area_a, const float4 pf, const float area_b,
+                                                   const float best, const bool always)
+{
+    float w = fminf(a.z, pf.z) - fmaxf(a.x, pf.x);
+    float h = fminf(a.w, pf.w) - fmaxf(a.y, pf.y);
+    w = fmaxf(w, 0.0f); h = fmaxf(h, 0.0f);
+    const float inter = w * h;
+    const float uni = area_a + area_b - inter;         // box_utils.py:98
+    if (inter > 0.0f || !(uni > 0.0f)) {
+        const float pth = best * uni;
+        const bool cannot_win = !always && uni > 0.0f && pth > 1e-30f && inter < pth * 0.999999f;
+        if (!cannot_win) {
+            float q;
+            asm volatile("div.rn.f32 %0, %1, %2;" : "=f"(q) : "f"(inter), "f"(uni));
+            return q;
+        }
+    }
+    return 0.0f;
 }
 
 __device__ __forceinline__ void finalize_prior(const float *__restrict__ gt, int64_t g0, int idx, float ov, float thr,
@@ -118,8 +157,9 @@ k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const i
     __shared__ unsigned long long s_best[BIP ? GT_TILE : 1][BIP ? M_WARPS : 1];
     __shared__ unsigned s_bb[4];
     __shared__ int s_wcnt[M_WARPS];
-    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t p = (int64_t)blockIdx.x * M_THREADS + tid;
+    const MatchBlock mb = match_block();
+    const int b = mb.b, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t p = (int64_t)mb.tile * M_THREADS + tid;
     const bool valid = p < N;
     const int64_t g0 = gt_off[b];
     const int G = (int)(gt_off[b + 1] - g0);
@@ -148,7 +188,7 @@ k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const i
     }
     __syncthreads();
     const float4 bb = make_float4(fdt_key_float(s_bb[0]), fdt_key_float(s_bb[1]), fdt_key_float(s_bb[2]), fdt_key_float(s_bb[3]));
-    const bool cull = !(BIP && blockIdx.x == 0);
+    const bool cull = !(BIP && mb.tile == 0);
     float best = 0.0f;
     int bi = 0;
     for (int t0 = 0; t0 < G; t0 += GT_TILE) {
@@ -219,15 +259,24 @@ k_match_default(const float4 *__restrict__ priors, const float *__restrict__ gt,
     __shared__ float s_area[GT_TILE];
     __shared__ unsigned char s_wl[M_WARPS][GT_TILE];
     __shared__ unsigned s_cmax[M_WARPS];
-    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t p = (int64_t)blockIdx.x * M_THREADS + tid;
+    const MatchBlock mb = match_block();
+    const int b = mb.b, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t p = (int64_t)mb.tile * M_THREADS + tid;
     const bool valid = p < N;
     const int64_t g0 = gt_off[b];
     const int G = (int)(gt_off[b + 1] - g0);
     const int64_t t = (int64_t)b * N + p;
-    if (conf) {                                        // global max of conf for log_sum_exp (every block, also for images without GT)
+    // global max of conf for log_sum_exp (every block, also for images without GT): the row is loaded here and reduced at the END of
+    // the kernel, so that nothing waits for it
+    float2 cv = make_float2(0.f, 0.f);
+    if (conf && valid && C == 2) cv = __ldg(reinterpret_cast<const float2 *>(conf + t * 2));
+    auto flush_conf_max = [&]() {
+        if (!conf) return;
         unsigned k = 0u;
-        if (valid) for (int c = 0; c < C; ++c) k = max(k, gmax_key_of(__ldg(conf + t * C + c)));
+        if (valid) {
+            if (C == 2) k = max(gmax_key_of(cv.x), gmax_key_of(cv.y));
+            else for (int c = 0; c < C; ++c) k = max(k, gmax_key_of(__ldg(conf + t * C + c)));
+        }
         k = __reduce_max_sync(0xffffffffu, k);
         if (lane == 0) s_cmax[warp] = k;
         __syncthreads();
@@ -237,7 +286,7 @@ k_match_default(const float4 *__restrict__ priors, const float *__restrict__ gt,
             for (int w = 1; w < M_WARPS; ++w) m = max(m, s_cmax[w]);
             atomicMax(gmax_key, m);
         }
-    }
+    };
     const float4 pr = priors[valid ? p : 0];
     if (G <= 0) {                                      // reference raises (Q3); defined: all background
         if (valid) {
@@ -245,6 +294,7 @@ k_match_default(const float4 *__restrict__ priors, const float *__restrict__ gt,
             if (bti) bti[t] = 0;
             if (bto) bto[t] = 0.0f;
         }
+        flush_conf_max();
         return;
     }
     const float hw = pr.z / 2.0f, hh = pr.w / 2.0f;    // point_form, box_utils.py:15-16
@@ -285,14 +335,15 @@ k_match_default(const float4 *__restrict__ priors, const float *__restrict__ gt,
         __syncwarp();
         for (int q = 0; q < wn; ++q) {
             const int g = s_wl[warp][q];
-            const float v = iou_match(s_box[g], s_area[g], pf, area_b);
             const int gi = t0 + g;
+            const float v = iou_match_vs_best(s_box[g], s_area[g], pf, area_b, best, gi == 0);
             if (gi == 0) { best = v; bi = 0; }
             else if (v > best) { best = v; bi = gi; }                          // first index wins ties (:197)
         }
         __syncwarp();
     }
     if (valid) finalize_prior(gt, g0, bi, best, thr, pr, v0, v1, loc_t, conf_t, bti, bto, t, encode_all);
+    flush_conf_max();
 }
 
 // box_utils.py:150-154: best_truth_overlap[best_prior_idx[j]] = 2; best_truth_idx[best_prior_idx[j]] = j (last j wins)
@@ -376,10 +427,12 @@ k_loss_prior(const float4 *__restrict__ loc, const float *__restrict__ conf, con
              float *__restrict__ loss_c_all, int32_t *__restrict__ num_pos, int *__restrict__ hist)
 {
     fdt_pdl_enter();
-    __shared__ double s_red[M_WARPS];
-    __shared__ int s_cnt[M_WARPS];
+    __shared__ double s_tot;
+    __shared__ int s_cnt;
     const int b = blockIdx.y;
     const int64_t p = (int64_t)blockIdx.x * M_THREADS + threadIdx.x;
+    if (threadIdx.x == 0) { s_tot = 0.0; s_cnt = 0; }
+    __syncthreads();
     const float xmax = fdt_key_float(acc->gmax_key);
     double sl = 0.0;
     int is_pos = 0, bin = -1;
@@ -402,11 +455,17 @@ k_loss_prior(const float4 *__restrict__ loc, const float *__restrict__ conf, con
         bin = (int)(mine_comp(lc, (unsigned)p) >> 52);
     }
     mine_hist_add(hist, b, bin);
-    const double tot = block_sum<double>(sl, s_red);
-    const int cnt = block_sum<int>(is_pos, s_cnt);
-    if (threadIdx.x == 0) {
-        if (tot != 0.0) atomicAdd(&acc->loss_l, tot);
-        if (cnt) atomicAdd(&num_pos[b], cnt);
+    // positives are ~1 % of the priors: only the warps that hold one reduce, into shared memory, and the block flushes once
+    const unsigned posm = __ballot_sync(0xffffffffu, is_pos);
+    if (posm) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, o);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&s_tot, sl); atomicAdd(&s_cnt, __popc(posm)); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) {
+        if (s_tot != 0.0) atomicAdd(&acc->loss_l, s_tot);
+        atomicAdd(&num_pos[b], s_cnt);
     }
 }
 
@@ -531,19 +590,44 @@ k_mine_apply(const float *__restrict__ loss_c, const unsigned long long *__restr
 {
     fdt_pdl_enter();
     __shared__ double s_red[M_WARPS];
-    const int b = blockIdx.y;
+    __shared__ int s_list[APPLY_TILES * M_THREADS];          // selected priors of the block (MODE 1)
+    __shared__ int s_n;
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
     const unsigned long long cut = cutoff[b];
-    double ce = 0.0;
+    if (MODE == 1) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+    }
 #pragma unroll 2
     for (int u = 0; u < APPLY_TILES; ++u) {
         const int64_t p = ((int64_t)blockIdx.x * APPLY_TILES + u) * M_THREADS + threadIdx.x;
-        if (p >= N) break;
-        const int64_t t = (int64_t)b * N + p;
-        const bool neg = cut != ~0ull && mine_comp(loss_c[t], (unsigned)p) >= cut;          // multibox_loss.py:116
-        const int64_t label = (MODE == 1) ? conf_t[t] : 0;
-        const bool sel = neg || (MODE == 1 && label > 0);
-        out_mask[t] = (uint8_t)sel;
-        if (MODE == 1 && sel) {
+        bool sel = false;
+        if (p < N) {
+            const int64_t t = (int64_t)b * N + p;
+            const bool neg = cut != ~0ull && mine_comp(loss_c[t], (unsigned)p) >= cut;      // multibox_loss.py:116
+            const int64_t label = (MODE == 1) ? conf_t[t] : 0;
+            sel = neg || (MODE == 1 && label > 0);
+            out_mask[t] = (uint8_t)sel;
+        }
+        if (MODE == 1) {
+            // a few percent of the priors are selected: list them and evaluate the fp64 cross entropy over the dense list below,
+            // not under a 3-lanes-in-32 branch here
+            const unsigned bal = __ballot_sync(0xffffffffu, sel);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_n, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (sel) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)p;
+            }
+        }
+    }
+    if (MODE == 1) {
+        __syncthreads();
+        const int n = s_n;
+        double ce = 0.0;
+        for (int e = threadIdx.x; e < n; e += M_THREADS) {
+            const int64_t t = (int64_t)b * N + s_list[e];
+            const int64_t label = conf_t[t];
             const float *row = conf + t * C;
             float m = row[0];
             for (int c = 1; c < C; ++c) m = fmaxf(m, row[c]);
@@ -551,10 +635,10 @@ k_mine_apply(const float *__restrict__ loss_c, const unsigned long long *__restr
             for (int c = 0; c < C; ++c) s += exp((double)(row[c] - m));
             ce += (log(s) + (double)m) - (double)row[label];                                 // :128
         }
-    }
-    if (MODE == 1) {
-        ce = block_sum<double>(ce, s_red);
-        if (threadIdx.x == 0 && ce != 0.0) atomicAdd(&acc->loss_c, ce);
+        if (n) {                                                                             // (uniform: s_n is shared)
+            ce = block_sum<double>(ce, s_red);
+            if (threadIdx.x == 0 && ce != 0.0) atomicAdd(&acc->loss_c, ce);
+        }
     }
 }
 
