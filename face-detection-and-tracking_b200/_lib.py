@@ -39,6 +39,7 @@ SIGNATURES = {
     "fdt_encode": (_i, [_vp, _vp, _i64, _f, _f, _vp, _vp]),
     "fdt_decode": (_i, [_vp, _vp, _i64, _f, _f, _vp, _vp]),
     "fdt_log_sum_exp": (_i, [_vp, _i64, _i, _vp, _vp, _sz, _vp]),
+    "fdt_selftest_cr_math": (_i, [_i, C.c_uint32, C.c_uint64, _vp, _vp]),
     "fdt_nms_workspace_bytes": (_sz, [_i64]),
     "fdt_nms": (_i, [_vp, _vp, _i64, _f, _i64, _vp, _vp, _vp, _sz, _vp]),
     "fdt_nms_variant": (_i, [_vp, _vp, _i64, _f, _i, _vp, _vp, _vp, _sz, _vp]),

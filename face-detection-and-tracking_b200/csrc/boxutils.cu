@@ -405,3 +405,32 @@ FDT_API int fdt_log_sum_exp(const float *x, int64_t R, int C, float *out, void *
     FDT_LAUNCH_CHECK();
     return FDT_OK;
 }
+
+// ---- self-test of fdt_expf_cr / fdt_logf_cr against the CUDA math library (fdt_common.cuh) --------------------------------------
+namespace {
+__global__ void k_selftest_cr_math(int which, uint32_t first, uint64_t count, unsigned long long *result)
+{
+    unsigned long long bad = 0, lowest = ~0ull;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t bits = first + (uint32_t)i;
+        const float x = __uint_as_float(bits);
+        const float a = which == 0 ? fdt_expf_cr(x) : fdt_logf_cr(x);
+        const float b = which == 0 ? (float)exp((double)x) : (float)log((double)x);
+        const bool same = __float_as_uint(a) == __float_as_uint(b) || (a != a && b != b);
+        if (!same) { ++bad; if ((unsigned long long)bits + 1 < lowest) lowest = (unsigned long long)bits + 1; }
+    }
+    if (bad) { atomicAdd(&result[0], bad); atomicMin(&result[1], lowest); }
+}
+}  // namespace
+
+FDT_API int fdt_selftest_cr_math(int which, uint32_t first_bits, uint64_t count, uint64_t *result, fdt_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    FDT_REQUIRE((which == 0 || which == 1) && result, FDT_E_INVALID, "fdt_selftest_cr_math: which must be 0 or 1, result non-null");
+    const unsigned long long init[2] = {0ull, ~0ull};
+    FDT_CUDA(cudaMemcpyAsync(result, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    if (count == 0) return FDT_OK;
+    k_selftest_cr_math<<<FDT_NUM_SMS * 8, 256, 0, st>>>(which, first_bits, count, (unsigned long long *)result);
+    FDT_LAUNCH_CHECK();
+    return FDT_OK;
+}

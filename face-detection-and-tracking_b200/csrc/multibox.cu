@@ -242,64 +242,19 @@ k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const i
     else finalize_prior(gt, g0, bi, best, thr, pr, v0, v1, loc_t, conf_t, bti, bto, t, encode_all);
 }
 
-// Default (non-bipartite) matcher, the production one (MyTrain_repo.py:113): the same per-warp culling as above but WITHOUT the
+// Default (non-bipartite) matcher, the production one (MyTrain_repo.py:113): the same culling as above but per WARP and without the
 // block-level stage -- the GT boxes of a tile are staged once, then every warp lists the boxes that touch the bounding box of its
 // 32 consecutive priors (ascending index, so the first-index tie rule holds; GT 0 is always listed) and runs the IoU loop over its
-// own list.  Two block barriers per tile instead of six and no compaction bookkeeping: k_match<false> spent more instructions around
-// the IoU loop than in it.  Optionally folds in the global maximum of `conf` that log_sum_exp needs (box_utils.py:268): one block
-// reduction and one atomicMax per block instead of a separate pass over conf.
-__global__ void __launch_bounds__(M_THREADS)
-k_match_default(const float4 *__restrict__ priors, const float *__restrict__ gt, const int64_t *__restrict__ gt_off,
-                int64_t N, float thr, float v0, float v1,
-                float4 *__restrict__ loc_t, int64_t *__restrict__ conf_t, int32_t *__restrict__ bti, float *__restrict__ bto,
-                const bool encode_all, const float *__restrict__ conf, int C, unsigned *__restrict__ gmax_key)
+// own list.  Two block barriers per tile and no compaction bookkeeping.  The IoU loop is the bulk of the forward's instructions:
+// one 32-byte shared-memory entry per GT box addressed through 32-bit shared addresses (the generic-address form re-derived the
+// shared window base inside the loop), GT 0 peeled (it seeds the arg max unconditionally, box_utils.py:197).
+struct __align__(32) GtEntry { float4 box; float area; float pad[3]; };
+
+__device__ __forceinline__ void match_default_core(const float *__restrict__ gt, const int64_t g0, const int G, const float4 pf,
+                                                   const float area_b, const bool valid, GtEntry *s_gt, unsigned char *s_wl_warp,
+                                                   float &best, int &bi)
 {
-    fdt_pdl_enter();
-    __shared__ float4 s_box[GT_TILE];
-    __shared__ float s_area[GT_TILE];
-    __shared__ unsigned char s_wl[M_WARPS][GT_TILE];
-    __shared__ unsigned s_cmax[M_WARPS];
-    const MatchBlock mb = match_block();
-    const int b = mb.b, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t p = (int64_t)mb.tile * M_THREADS + tid;
-    const bool valid = p < N;
-    const int64_t g0 = gt_off[b];
-    const int G = (int)(gt_off[b + 1] - g0);
-    const int64_t t = (int64_t)b * N + p;
-    // global max of conf for log_sum_exp (every block, also for images without GT): the row is loaded here and reduced at the END of
-    // the kernel, so that nothing waits for it
-    float2 cv = make_float2(0.f, 0.f);
-    if (conf && valid && C == 2) cv = __ldg(reinterpret_cast<const float2 *>(conf + t * 2));
-    auto flush_conf_max = [&]() {
-        if (!conf) return;
-        unsigned k = 0u;
-        if (valid) {
-            if (C == 2) k = max(gmax_key_of(cv.x), gmax_key_of(cv.y));
-            else for (int c = 0; c < C; ++c) k = max(k, gmax_key_of(__ldg(conf + t * C + c)));
-        }
-        k = __reduce_max_sync(0xffffffffu, k);
-        if (lane == 0) s_cmax[warp] = k;
-        __syncthreads();
-        if (tid == 0) {
-            unsigned m = s_cmax[0];
-#pragma unroll
-            for (int w = 1; w < M_WARPS; ++w) m = max(m, s_cmax[w]);
-            atomicMax(gmax_key, m);
-        }
-    };
-    const float4 pr = priors[valid ? p : 0];
-    if (G <= 0) {                                      // reference raises (Q3); defined: all background
-        if (valid) {
-            conf_t[t] = 0; loc_t[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (bti) bti[t] = 0;
-            if (bto) bto[t] = 0.0f;
-        }
-        flush_conf_max();
-        return;
-    }
-    const float hw = pr.z / 2.0f, hh = pr.w / 2.0f;    // point_form, box_utils.py:15-16
-    const float4 pf = make_float4(pr.x - hw, pr.y - hh, pr.x + hw, pr.y + hh);
-    const float area_b = (pf.z - pf.x) * (pf.w - pf.y);
+    const int tid = threadIdx.x, lane = tid & 31;
     float4 wb;                                         // bounding box of the warp's priors
     {
         unsigned k0 = valid ? fdt_float_key(pf.x) : 0xffffffffu, k1 = valid ? fdt_float_key(pf.y) : 0xffffffffu;
@@ -308,15 +263,17 @@ k_match_default(const float4 *__restrict__ priors, const float *__restrict__ gt,
         k2 = __reduce_max_sync(0xffffffffu, k2); k3 = __reduce_max_sync(0xffffffffu, k3);
         wb = make_float4(fdt_key_float(k0), fdt_key_float(k1), fdt_key_float(k2), fdt_key_float(k3));
     }
-    float best = 0.0f;
-    int bi = 0;
+    const unsigned a_gt = (unsigned)__cvta_generic_to_shared(s_gt);
+    const unsigned a_wl = (unsigned)__cvta_generic_to_shared(s_wl_warp);
+    best = 0.0f;
+    bi = 0;
     for (int t0 = 0; t0 < G; t0 += GT_TILE) {
         const int tn = min(GT_TILE, G - t0);
         __syncthreads();                               // previous tile fully consumed
         if (tid < tn) {
             const float *row = gt + 5 * (g0 + t0 + tid);
             const float4 a = make_float4(row[0], row[1], row[2], row[3]);
-            s_box[tid] = a; s_area[tid] = (a.z - a.x) * (a.w - a.y);
+            s_gt[tid].box = a; s_gt[tid].area = (a.z - a.x) * (a.w - a.y);
         }
         __syncthreads();
         int wn = 0;
@@ -324,26 +281,69 @@ k_match_default(const float4 *__restrict__ priors, const float *__restrict__ gt,
             const int g = gb + lane;
             bool k2 = false;
             if (g < tn) {
-                const float4 a2 = s_box[g];
+                const float4 a2 = s_gt[g].box;
                 const float wbb = fminf(a2.z, wb.z) - fmaxf(a2.x, wb.x), hbb = fminf(a2.w, wb.w) - fmaxf(a2.y, wb.y);
                 k2 = (t0 + g == 0) || !(wbb <= 0.0f || hbb <= 0.0f);           // NaN keeps
             }
             const unsigned bal2 = __ballot_sync(0xffffffffu, k2);
-            if (k2) s_wl[warp][wn + __popc(bal2 & ((1u << lane) - 1u))] = (unsigned char)g;
+            if (k2) s_wl_warp[wn + __popc(bal2 & ((1u << lane) - 1u))] = (unsigned char)g;
             wn += __popc(bal2);
         }
         __syncwarp();
-        for (int q = 0; q < wn; ++q) {
-            const int g = s_wl[warp][q];
-            const int gi = t0 + g;
-            const float v = iou_match_vs_best(s_box[g], s_area[g], pf, area_b, best, gi == 0);
-            if (gi == 0) { best = v; bi = 0; }
-            else if (v > best) { best = v; bi = gi; }                          // first index wins ties (:197)
+        int q = 0;
+        if (t0 == 0) {                                 // GT 0 heads the first list: best = its IoU whatever it is
+            best = iou_match(s_gt[0].box, s_gt[0].area, pf, area_b);
+            q = 1;
+        }
+#pragma unroll 2
+        for (; q < wn; ++q) {
+            unsigned g;
+            float4 a;
+            float ar;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(g) : "r"(a_wl + q));
+            const unsigned ad = a_gt + g * 32u;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(ad));
+            asm volatile("ld.shared.f32 %0, [%1+16];" : "=f"(ar) : "r"(ad));
+            const float v = iou_match_vs_best(a, ar, pf, area_b, best, false);
+            if (v > best) { best = v; bi = t0 + (int)g; }                      // first index wins ties (:197)
         }
         __syncwarp();
     }
+}
+
+// standalone matcher (fdt_match_encode, box_utils.match): labels + encode of every prior
+__global__ void __launch_bounds__(M_THREADS)
+k_match_default(const float4 *__restrict__ priors, const float *__restrict__ gt, const int64_t *__restrict__ gt_off,
+                int64_t N, float thr, float v0, float v1,
+                float4 *__restrict__ loc_t, int64_t *__restrict__ conf_t, int32_t *__restrict__ bti, float *__restrict__ bto,
+                const bool encode_all)
+{
+    fdt_pdl_enter();
+    __shared__ GtEntry s_gt[GT_TILE];
+    __shared__ unsigned char s_wl[M_WARPS][GT_TILE];
+    const MatchBlock mb = match_block();
+    const int b = mb.b, tid = threadIdx.x, warp = tid >> 5;
+    const int64_t p = (int64_t)mb.tile * M_THREADS + tid;
+    const bool valid = p < N;
+    const int64_t g0 = gt_off[b];
+    const int G = (int)(gt_off[b + 1] - g0);
+    const int64_t t = (int64_t)b * N + p;
+    const float4 pr = priors[valid ? p : 0];
+    if (G <= 0) {                                      // reference raises (Q3); defined: all background
+        if (valid) {
+            conf_t[t] = 0; loc_t[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bti) bti[t] = 0;
+            if (bto) bto[t] = 0.0f;
+        }
+        return;
+    }
+    const float hw = pr.z / 2.0f, hh = pr.w / 2.0f;    // point_form, box_utils.py:15-16
+    const float4 pf = make_float4(pr.x - hw, pr.y - hh, pr.x + hw, pr.y + hh);
+    const float area_b = (pf.z - pf.x) * (pf.w - pf.y);
+    float best;
+    int bi;
+    match_default_core(gt, g0, G, pf, area_b, valid, s_gt, s_wl[warp], best, bi);
     if (valid) finalize_prior(gt, g0, bi, best, thr, pr, v0, v1, loc_t, conf_t, bti, bto, t, encode_all);
-    flush_conf_max();
 }
 
 // box_utils.py:150-154: best_truth_overlap[best_prior_idx[j]] = 2; best_truth_idx[best_prior_idx[j]] = j (last j wins)
@@ -377,18 +377,8 @@ k_match_bipartite_finalize(const float4 *__restrict__ priors, const float *__res
 }
 
 // ---------------------------------------------------------------------------------------------- loss
-__global__ void k_conf_global_max(const float *__restrict__ x, int64_t n, unsigned *__restrict__ gmax_key)
-{
-    fdt_pdl_enter();
-    unsigned k = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        k = max(k, gmax_key_of(x[i]));
-    k = __reduce_max_sync(0xffffffffu, k);
-    if ((threadIdx.x & 31) == 0) atomicMax(gmax_key, k);
-}
-
-// Level-0 mining histogram, chip-wide: neighbouring priors have similar losses, so the 32 lanes of a warp hit a handful of bins --
-// one atomic per distinct bin and warp (match_any) instead of one per prior, spread over MINE_REPL copies by warp.
+// Level-0 mining histogram of the standalone entry (fdt_hard_negative_mine), chip-wide: neighbouring priors have similar losses, so
+// the 32 lanes of a warp hit a handful of bins -- one atomic per distinct bin and warp (match_any), spread over MINE_REPL copies.
 __device__ __forceinline__ void mine_hist_add(int *__restrict__ hist, const int b, const int bin)
 {
     const unsigned peers = __match_any_sync(0xffffffffu, bin);
@@ -397,9 +387,22 @@ __device__ __forceinline__ void mine_hist_add(int *__restrict__ hist, const int 
         atomicAdd(&hist[((size_t)b * MINE_REPL + ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (MINE_REPL - 1))) * MINE_BINS + bin], __popc(peers));
 }
 
-struct LossAcc {            // lives in the workspace, zeroed per call
+// Mining bins of the fused forward: 4,096 bins, monotone in the composite's loss key -- 256 per octave over [2^-8, 2^8), everything
+// below (the zeros of the positives, tiny and negative losses) in bin 0, everything above (and NaN) in bin 4095.  The cutoff of an
+// image falls into ONE bin; with 8 mantissa bits per octave that bin holds a few dozen of its 34 k priors, so the exact order only
+// has to be settled among those (k_mine_apply2).
+__device__ __forceinline__ int mine_bin2(const float lc)
+{
+    const unsigned key = lc != lc ? 0xffffffffu : fdt_float_key(lc);
+    const unsigned lo = 0x80000000u | 0x3b800000u;                 // key of 2^-8
+    if (key < lo) return 0;
+    const unsigned v = (key - lo) >> 15;
+    return v > (unsigned)(MINE_BINS - 1) ? MINE_BINS - 1 : (int)v;
+}
+
+struct LossAcc {            // lives in the workspace, zeroed per call (k_mbl_prepare)
     double loss_l, loss_c;
-    unsigned gmax_key;
+    unsigned done;          // blocks of k_mine_apply2 that have finished
     unsigned pad;
 };
 
@@ -420,10 +423,92 @@ __device__ __forceinline__ T block_sum(T v, T *s_red)
     return v;     // valid in thread 0
 }
 
-// multibox_loss.py:90-110
+// First kernel of the forward: zeroes the per-call state (accumulators, per-image counters, the mining histogram) and reduces the
+// GLOBAL maximum of conf that log_sum_exp subtracts (box_utils.py:268) to one key per block -- the consumers take the maximum of
+// the PREP_BLOCKS partials, so nothing has to be zeroed before this kernel and no memset node precedes it.  It releases its
+// successor only after its own grid dependency has resolved: when the matcher starts, the previous call on this workspace is over.
+constexpr int PREP_BLOCKS = FDT_NUM_SMS, PREP_THREADS = 1024;
+__global__ void __launch_bounds__(PREP_THREADS)
+k_mbl_prepare(const float *__restrict__ conf, const int64_t n_conf, unsigned *__restrict__ gmax_part, int4 *__restrict__ zero_base,
+              const int64_t zero_int4s)
+{
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+    __shared__ unsigned s_k[PREP_THREADS / 32];
+    const int64_t gtid = (int64_t)blockIdx.x * PREP_THREADS + threadIdx.x, gsz = (int64_t)PREP_BLOCKS * PREP_THREADS;
+    for (int64_t i = gtid; i < zero_int4s; i += gsz) zero_base[i] = make_int4(0, 0, 0, 0);
+    unsigned k = 0u;
+    if (((uintptr_t)conf & 15) == 0) {
+        const float4 *c4 = reinterpret_cast<const float4 *>(conf);
+        const int64_t n4 = n_conf >> 2;
+        for (int64_t i = gtid; i < n4; i += gsz) {
+            const float4 v = __ldg(c4 + i);
+            k = max(max(k, gmax_key_of(v.x)), max(gmax_key_of(v.y), max(gmax_key_of(v.z), gmax_key_of(v.w))));
+        }
+        for (int64_t i = (n4 << 2) + gtid; i < n_conf; i += gsz) k = max(k, gmax_key_of(__ldg(conf + i)));
+    } else {
+        for (int64_t i = gtid; i < n_conf; i += gsz) k = max(k, gmax_key_of(__ldg(conf + i)));
+    }
+    k = __reduce_max_sync(0xffffffffu, k);
+    if ((threadIdx.x & 31) == 0) s_k[threadIdx.x >> 5] = k;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        k = __reduce_max_sync(0xffffffffu, s_k[threadIdx.x]);
+        if (threadIdx.x == 0) gmax_part[blockIdx.x] = k;
+    }
+}
+// the global maximum from the partials of k_mbl_prepare (one warp-wide reduction; every warp of a consumer does its own)
+__device__ __forceinline__ float gmax_from_partials(const unsigned *__restrict__ gmax_part)
+{
+    unsigned k = 0u;
+    for (int i = threadIdx.x & 31; i < PREP_BLOCKS; i += 32) k = max(k, __ldcg(gmax_part + i));
+    return fdt_key_float(__reduce_max_sync(0xffffffffu, k));
+}
+
+// per-prior loss terms shared by k_loss_prior and the fused k_match_loss (multibox_loss.py:96-110): smooth L1 of a positive
+// (beta = 1, sum) in `sl`, the mining input loss_c (0 for positives) returned
+__device__ __forceinline__ float prior_loss_terms(const float4 a, const float4 g, const bool is_pos, const float *__restrict__ row,
+                                                  const int C, const int64_t label, const float xmax, double &sl)
+{
+    if (is_pos) {
+        const float d[4] = {fabsf(a.x - g.x), fabsf(a.y - g.y), fabsf(a.z - g.z), fabsf(a.w - g.w)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sl += (double)(d[k] < 1.0f ? 0.5f * d[k] * d[k] : d[k] - 0.5f);
+    }
+    float s, xl;
+    if (C == 2) {
+        const float2 cv = __ldg(reinterpret_cast<const float2 *>(row));
+        s = fdt_expf_cr(cv.x - xmax) + fdt_expf_cr(cv.y - xmax);                   // box_utils.py:269
+        xl = label ? cv.y : cv.x;
+    } else {
+        s = 0.0f;
+        for (int c = 0; c < C; ++c) s += fdt_expf_cr(row[c] - xmax);
+        xl = row[label];
+    }
+    const float v = (fdt_logf_cr(s) + xmax) - xl;                                  // :106
+    return is_pos ? 0.0f : v;                                                      // :110
+}
+// positives are ~1 % of the priors: only the warps that hold one reduce, into shared memory, and the block flushes once
+__device__ __forceinline__ void flush_positives(double sl, const int is_pos, double *s_tot, int *s_cnt, LossAcc *__restrict__ acc,
+                                                int32_t *__restrict__ num_pos_b)
+{
+    const unsigned posm = __ballot_sync(0xffffffffu, is_pos);
+    if (posm) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, o);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(s_tot, sl); atomicAdd(s_cnt, __popc(posm)); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && *s_cnt) {
+        if (*s_tot != 0.0) atomicAdd(&acc->loss_l, *s_tot);
+        atomicAdd(num_pos_b, *s_cnt);
+    }
+}
+
+// multibox_loss.py:90-110 behind the bipartite matcher (the default matcher computes the same terms inside k_match_loss)
 __global__ void __launch_bounds__(M_THREADS)
 k_loss_prior(const float4 *__restrict__ loc, const float *__restrict__ conf, const float4 *__restrict__ loc_t,
-             const int64_t *__restrict__ conf_t, int64_t N, int C, LossAcc *__restrict__ acc,
+             const int64_t *__restrict__ conf_t, int64_t N, int C, LossAcc *__restrict__ acc, const unsigned *__restrict__ gmax_part,
              float *__restrict__ loss_c_all, int32_t *__restrict__ num_pos, int *__restrict__ hist)
 {
     fdt_pdl_enter();
@@ -433,40 +518,76 @@ k_loss_prior(const float4 *__restrict__ loc, const float *__restrict__ conf, con
     const int64_t p = (int64_t)blockIdx.x * M_THREADS + threadIdx.x;
     if (threadIdx.x == 0) { s_tot = 0.0; s_cnt = 0; }
     __syncthreads();
-    const float xmax = fdt_key_float(acc->gmax_key);
+    const float xmax = gmax_from_partials(gmax_part);
     double sl = 0.0;
-    int is_pos = 0, bin = -1;
+    int is_pos = 0;
     if (p < N) {
         const int64_t t = (int64_t)b * N + p;
         const int64_t label = conf_t[t];
         is_pos = label > 0;
-        if (is_pos) {                                              // :96-101 smooth L1, beta = 1, sum
-            const float4 a = loc[t], g = loc_t[t];
-            const float d[4] = {fabsf(a.x - g.x), fabsf(a.y - g.y), fabsf(a.z - g.z), fabsf(a.w - g.w)};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) sl += (double)(d[k] < 1.0f ? 0.5f * d[k] * d[k] : d[k] - 0.5f);
-        }
-        const float *row = conf + t * C;
-        float s = 0.0f;
-        for (int c = 0; c < C; ++c) s += fdt_expf_cr(row[c] - xmax);                // box_utils.py:269
-        const float v = (fdt_logf_cr(s) + xmax) - row[label];                      // :106
-        const float lc = is_pos ? 0.0f : v;                                        // :110
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
+        if (is_pos) { a = loc[t]; g = loc_t[t]; }
+        const float lc = prior_loss_terms(a, g, is_pos, conf + t * C, C, label, xmax, sl);
         loss_c_all[t] = lc;
-        bin = (int)(mine_comp(lc, (unsigned)p) >> 52);
+        atomicAdd(&hist[(size_t)b * MINE_BINS + mine_bin2(lc)], 1);
     }
-    mine_hist_add(hist, b, bin);
-    // positives are ~1 % of the priors: only the warps that hold one reduce, into shared memory, and the block flushes once
-    const unsigned posm = __ballot_sync(0xffffffffu, is_pos);
-    if (posm) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, o);
-        if ((threadIdx.x & 31) == 0) { atomicAdd(&s_tot, sl); atomicAdd(&s_cnt, __popc(posm)); }
+    flush_positives(sl, is_pos, &s_tot, &s_cnt, acc, &num_pos[b]);
+}
+
+// The forward behind the default matcher in ONE kernel per prior: match (k_match_default's core), label + encode of the positives,
+// and -- once k_mbl_prepare's maximum is there -- the loss terms and the mining histogram of k_loss_prior on the values still in
+// registers.  The matcher is bound by instruction issue and the loss terms by fp64 latency; in one kernel the warps of both phases
+// share every SM, and conf_t / loc_t are not read back.
+__global__ void __launch_bounds__(M_THREADS, 4)
+k_match_loss(const float4 *__restrict__ priors, const float *__restrict__ gt, const int64_t *__restrict__ gt_off,
+             int64_t N, float thr, float v0, float v1, float4 *__restrict__ loc_t, int64_t *__restrict__ conf_t,
+             const float4 *__restrict__ loc, const float *__restrict__ conf, int C, LossAcc *__restrict__ acc,
+             const unsigned *__restrict__ gmax_part, float *__restrict__ loss_c_all, int32_t *__restrict__ num_pos, int *__restrict__ hist)
+{
+    __shared__ GtEntry s_gt[GT_TILE];
+    __shared__ unsigned char s_wl[M_WARPS][GT_TILE];
+    __shared__ double s_tot;
+    __shared__ int s_cnt;
+    const MatchBlock mb = match_block();
+    const int b = mb.b, tid = threadIdx.x, warp = tid >> 5;
+    const int64_t p = (int64_t)mb.tile * M_THREADS + tid;
+    const bool valid = p < N;
+    const int64_t g0 = gt_off[b];
+    const int G = (int)(gt_off[b + 1] - g0);
+    const int64_t t = (int64_t)b * N + p;
+    if (tid == 0) { s_tot = 0.0; s_cnt = 0; }
+    const float4 pr = priors[valid ? p : 0];
+    int64_t label = 0;
+    float4 enc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (G > 0) {                                       // G <= 0: the reference raises (Q3); defined: all background
+        const float hw = pr.z / 2.0f, hh = pr.w / 2.0f;    // point_form, box_utils.py:15-16
+        const float4 pf = make_float4(pr.x - hw, pr.y - hh, pr.x + hw, pr.y + hh);
+        const float area_b = (pf.z - pf.x) * (pf.w - pf.y);
+        float best;
+        int bi;
+        match_default_core(gt, g0, G, pf, area_b, valid, s_gt, s_wl[warp], best, bi);
+        const float *row = gt + 5 * (g0 + bi);
+        float c = row[4] + 1.0f;                       // box_utils.py:205
+        if (best < thr) c = 0.0f;                      // :206
+        label = (int64_t)c;                            // :210 (float -> long)
+        // :208 encodes every prior; the loss only reads the positives (multibox_loss.py:96-101): zeros elsewhere
+        if (label > 0) enc = fdt_encode1(make_float4(row[0], row[1], row[2], row[3]), pr, v0, v1);
     }
+    if (valid) { conf_t[t] = label; loc_t[t] = enc; }
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();                   // k_mbl_prepare: zeroed state + the partial maxima
     __syncthreads();
-    if (threadIdx.x == 0 && s_cnt) {
-        if (s_tot != 0.0) atomicAdd(&acc->loss_l, s_tot);
-        atomicAdd(&num_pos[b], s_cnt);
+    const float xmax = gmax_from_partials(gmax_part);
+    double sl = 0.0;
+    const int is_pos = valid && label > 0;
+    if (valid) {
+        float4 a = enc;
+        if (is_pos) a = loc[t];
+        const float lc = prior_loss_terms(a, enc, is_pos, conf + t * C, C, label, xmax, sl);
+        loss_c_all[t] = lc;
+        atomicAdd(&hist[(size_t)b * MINE_BINS + mine_bin2(lc)], 1);
     }
+    flush_positives(sl, is_pos, &s_tot, &s_cnt, acc, &num_pos[b]);
 }
 
 // standalone mining entry: histogram of the top 12 composite bits + positives per image
@@ -579,81 +700,203 @@ k_mine_select(const float *__restrict__ loss_c, const int *__restrict__ hist0, c
     if (tid == 0) cutoff[b] = prefix;
 }
 
-// MODE 0: neg mask only.  MODE 1: sel = pos | neg and CE over the selection (F.cross_entropy, sum).
-// A block covers APPLY_TILES consecutive tiles of one image: the fp64 atomicAdd on the single loss accumulator is the serial
-// resource here (one per block), so fewer, longer blocks finish sooner than one block per 256 priors.
+// standalone mining entry: the mask of the hard negatives (multibox_loss.py:116)
 constexpr int APPLY_TILES = 8;
-template <int MODE>
 __global__ void __launch_bounds__(M_THREADS)
-k_mine_apply(const float *__restrict__ loss_c, const unsigned long long *__restrict__ cutoff, const int64_t *__restrict__ conf_t,
-             const float *__restrict__ conf, int64_t N, int C, uint8_t *__restrict__ out_mask, LossAcc *__restrict__ acc)
+k_mine_apply(const float *__restrict__ loss_c, const unsigned long long *__restrict__ cutoff, int64_t N, uint8_t *__restrict__ out_mask)
 {
     fdt_pdl_enter();
-    __shared__ double s_red[M_WARPS];
-    __shared__ int s_list[APPLY_TILES * M_THREADS];          // selected priors of the block (MODE 1)
-    __shared__ int s_n;
-    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
     const unsigned long long cut = cutoff[b];
-    if (MODE == 1) {
-        if (threadIdx.x == 0) s_n = 0;
-        __syncthreads();
-    }
 #pragma unroll 2
     for (int u = 0; u < APPLY_TILES; ++u) {
         const int64_t p = ((int64_t)blockIdx.x * APPLY_TILES + u) * M_THREADS + threadIdx.x;
-        bool sel = false;
         if (p < N) {
             const int64_t t = (int64_t)b * N + p;
-            const bool neg = cut != ~0ull && mine_comp(loss_c[t], (unsigned)p) >= cut;      // multibox_loss.py:116
-            const int64_t label = (MODE == 1) ? conf_t[t] : 0;
-            sel = neg || (MODE == 1 && label > 0);
-            out_mask[t] = (uint8_t)sel;
-        }
-        if (MODE == 1) {
-            // a few percent of the priors are selected: list them and evaluate the fp64 cross entropy over the dense list below,
-            // not under a 3-lanes-in-32 branch here
-            const unsigned bal = __ballot_sync(0xffffffffu, sel);
-            if (bal) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_n, __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (sel) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)p;
-            }
-        }
-    }
-    if (MODE == 1) {
-        __syncthreads();
-        const int n = s_n;
-        double ce = 0.0;
-        for (int e = threadIdx.x; e < n; e += M_THREADS) {
-            const int64_t t = (int64_t)b * N + s_list[e];
-            const int64_t label = conf_t[t];
-            const float *row = conf + t * C;
-            float m = row[0];
-            for (int c = 1; c < C; ++c) m = fmaxf(m, row[c]);
-            double s = 0.0;
-            for (int c = 0; c < C; ++c) s += exp((double)(row[c] - m));
-            ce += (log(s) + (double)m) - (double)row[label];                                 // :128
-        }
-        if (n) {                                                                             // (uniform: s_n is shared)
-            ce = block_sum<double>(ce, s_red);
-            if (threadIdx.x == 0 && ce != 0.0) atomicAdd(&acc->loss_c, ce);
+            out_mask[t] = (uint8_t)(cut != ~0ull && mine_comp(loss_c[t], (unsigned)p) >= cut);
         }
     }
 }
 
-__global__ void k_loss_final(const LossAcc *__restrict__ acc, const int32_t *__restrict__ num_pos, int B,
-                             float *__restrict__ losses, float *__restrict__ norm)
+// cross entropy of one prior row, F.cross_entropy (sum) in fp64 (multibox_loss.py:128)
+__device__ __forceinline__ double ce_row(const float *__restrict__ row, const int C, const int64_t label)
+{
+    float m = row[0];
+    for (int c = 1; c < C; ++c) m = fmaxf(m, row[c]);
+    double s = 0.0;
+    for (int c = 0; c < C; ++c) s += exp((double)(row[c] - m));
+    return (log(s) + (double)m) - (double)row[label];
+}
+
+// Mining + selection + cross entropy + the final division of the fused forward, one kernel (multibox_loss.py:112-135).
+//   1. every block finds the cutoff BIN of its image from the 4,096-bin histogram (descending scan; num_neg = min(ratio * num_pos,
+//      N - 1), :115): bins above it are hard negatives, bins below are not;
+//   2. it classifies its 2,048 priors, writes the selection mask (pos | neg, :119-120), lists the selected rows and sums their cross
+//      entropy; priors IN the cutoff bin go to the image's candidate list;
+//   3. the LAST block of an image (a ticket) settles the candidates: the need0 largest composites (loss key, then lower prior index
+//      -- the order of the reference's stable descending sort) among them are negatives too;
+//   4. the last block of the grid divides by N (:130-135).
+// No separate select and final kernels, and the row is read once.
+__global__ void __launch_bounds__(M_THREADS)
+k_mine_apply2(const float *__restrict__ loss_c, const int *__restrict__ hist, const int32_t *__restrict__ num_pos,
+              const int64_t *__restrict__ conf_t, const float *__restrict__ conf, const int64_t N, const int C, const int B,
+              const int negpos_ratio, uint8_t *__restrict__ out_mask, LossAcc *__restrict__ acc, int *__restrict__ img_ticket,
+              int *__restrict__ cand_cnt, int *__restrict__ cand, float *__restrict__ losses, float *__restrict__ norm)
 {
     fdt_pdl_enter();
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    long long n = 0;
-    for (int b = 0; b < B; ++b) n += num_pos[b];
-    double Nn = (double)n;                         // multibox_loss.py:130
-    if (n == 0) Nn = (double)B;                    // :132-133
-    losses[0] = (float)(acc->loss_l / Nn);
-    losses[1] = (float)(acc->loss_c / Nn);
-    norm[0] = (float)Nn;
+    __shared__ double s_red[M_WARPS];
+    __shared__ __align__(8) int s_list[APPLY_TILES * M_THREADS];        // selected priors of the block; composites in step 3
+    __shared__ int s_h[256];
+    __shared__ int s_warp[M_WARPS];
+    __shared__ int s_sel[2];
+    __shared__ int s_n, s_flag;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long num_neg = (long long)negpos_ratio * num_pos[b];                   // multibox_loss.py:115
+    if (num_neg > N - 1) num_neg = N - 1;
+    const bool mining = num_neg > 0;                                            // (block-uniform)
+    if (tid == 0) s_n = 0;
+    // ---- 1. cutoff bin d0 and the number need0 of its members that are selected
+    int d0 = MINE_BINS, need0 = 0;
+    if (mining) {
+        constexpr int PER = MINE_BINS / M_THREADS;                              // 16 bins per thread, thread 0 holds the top ones
+        const int base = MINE_BINS - PER * (tid + 1);
+        const int4 *hp = reinterpret_cast<const int4 *>(hist + (size_t)b * MINE_BINS + base);
+        int c[PER], sum = 0;
+#pragma unroll
+        for (int q = 0; q < PER / 4; ++q) { const int4 v = hp[q]; c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w; }
+#pragma unroll
+        for (int q = 0; q < PER; ++q) sum += c[q];
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        int run = inc - sum;
+#pragma unroll
+        for (int w = 0; w < M_WARPS; ++w) if (w < warp) run += s_warp[w];
+        const int need = (int)num_neg;
+#pragma unroll
+        for (int q = PER - 1; q >= 0; --q) {                                    // descending bins
+            if (run < need && run + c[q] >= need) { s_sel[0] = base + q; s_sel[1] = need - run; }
+            run += c[q];
+        }
+        __syncthreads();
+        d0 = s_sel[0]; need0 = s_sel[1];
+    } else {
+        __syncthreads();
+    }
+    // ---- 2. classify, mask, lists
+#pragma unroll 2
+    for (int u = 0; u < APPLY_TILES; ++u) {
+        const int64_t p = ((int64_t)blockIdx.x * APPLY_TILES + u) * M_THREADS + tid;
+        bool sel = false, cnd = false;
+        if (p < N) {
+            const int64_t t = (int64_t)b * N + p;
+            const int bin = mine_bin2(loss_c[t]);
+            sel = bin > d0 || conf_t[t] > 0;                                    // (d0 = MINE_BINS without mining)
+            cnd = bin == d0;
+            out_mask[t] = (uint8_t)sel;
+        }
+        // a few percent of the priors are selected: list them and evaluate the fp64 cross entropy over the dense list below
+        const unsigned bal = __ballot_sync(0xffffffffu, sel);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_n, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (sel) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)p;
+        }
+        const unsigned cbal = __ballot_sync(0xffffffffu, cnd);
+        if (cbal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&cand_cnt[b], __popc(cbal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (cnd) cand[(size_t)b * N + base + __popc(cbal & ((1u << lane) - 1u))] = (int)p;
+        }
+    }
+    __syncthreads();
+    double ce = 0.0;
+    {
+        const int n = s_n;
+        for (int e = tid; e < n; e += M_THREADS) {
+            const int64_t t = (int64_t)b * N + s_list[e];
+            ce += ce_row(conf + t * C, C, conf_t[t]);
+        }
+    }
+    // ---- 3. the last block of the image settles the cutoff bin
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_flag = atomicAdd(&img_ticket[b], 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (s_flag && mining) {
+        __threadfence();
+        const int n = *(volatile int *)&cand_cnt[b];
+        const int *cl = cand + (size_t)b * N;
+        const float *lrow = loss_c + (size_t)b * N;
+        unsigned long long cutoff = 0ull;                                       // need0 == n: every candidate
+        if (need0 < n && n < APPLY_TILES * M_THREADS / 2) {
+            // rank among the candidates in shared memory: selected <=> fewer than need0 composites are larger
+            unsigned long long *s_comp = reinterpret_cast<unsigned long long *>(s_list);
+            for (int e = tid; e < n; e += M_THREADS) { const int p = __ldcg(cl + e); s_comp[e] = mine_comp(__ldcg(lrow + p), (unsigned)p); }
+            __syncthreads();
+            for (int e = tid; e < n; e += M_THREADS) {
+                const unsigned long long c = s_comp[e];
+                int rank = 0;
+                for (int j = 0; j < n; ++j) rank += s_comp[j] > c;
+                if (rank == need0 - 1) s_comp[n] = c;                           // composites are unique: exactly one writer
+            }
+            __syncthreads();
+            cutoff = s_comp[n];
+        } else if (need0 < n) {
+            // (degenerate rows, e.g. thousands of equal losses) MSB radix select over the list, 8 bits per pass
+            unsigned long long prefix = 0ull, pmask = 0ull;
+            int need = need0;
+            for (int shift = 56; shift >= 0; shift -= 8) {
+                s_h[tid] = 0;
+                __syncthreads();
+                for (int e = tid; e < n; e += M_THREADS) {
+                    const int p = __ldcg(cl + e);
+                    const unsigned long long c = mine_comp(__ldcg(lrow + p), (unsigned)p);
+                    if ((c & pmask) == prefix) atomicAdd(&s_h[(int)((c >> shift) & 255ull)], 1);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int run = 0, d = 255;
+                    for (; d > 0; --d) { if (run + s_h[d] >= need) break; run += s_h[d]; }
+                    s_sel[0] = d; s_sel[1] = need - run;
+                }
+                __syncthreads();
+                prefix |= (unsigned long long)s_sel[0] << shift;
+                pmask |= 255ull << shift;
+                need = s_sel[1];
+                __syncthreads();
+            }
+            cutoff = prefix;
+        }
+        for (int e = tid; e < n; e += M_THREADS) {
+            const int p = __ldcg(cl + e);
+            const int64_t t = (int64_t)b * N + p;
+            if (mine_comp(__ldcg(lrow + p), (unsigned)p) >= cutoff && conf_t[t] <= 0) {     // positives are selected already
+                out_mask[t] = 1;
+                ce += ce_row(conf + t * C, C, 0);
+            }
+        }
+    }
+    ce = block_sum<double>(ce, s_red);
+    // ---- 4. accumulate; the last block of the grid finishes (multibox_loss.py:130-135)
+    if (tid == 0) {
+        if (ce != 0.0) atomicAdd(&acc->loss_c, ce);
+        __threadfence();
+        if (atomicAdd(&acc->done, 1u) == gridDim.x * gridDim.y - 1u) {
+            __threadfence();
+            long long n = 0;
+            for (int i = 0; i < B; ++i) n += num_pos[i];
+            double Nn = (double)n;                         // :130
+            if (n == 0) Nn = (double)B;                    // :132-133
+            losses[0] = (float)(*(volatile double *)&acc->loss_l / Nn);
+            losses[1] = (float)(*(volatile double *)&acc->loss_c / Nn);
+            norm[0] = (float)Nn;
+        }
+    }
 }
 
 // d loss_l / d loc = smooth-L1' at positives / N ; d loss_c / d conf = (softmax - onehot) at pos U neg / N
@@ -707,13 +950,13 @@ MatchWs plan_match_ws(void *ws, int B, int64_t N, int64_t total_gt)
 
 int launch_match(const float *priors, const float *gt, const int64_t *gt_off, int B, int64_t N, int64_t total_gt,
                  float thr, float v0, float v1, int bipartite, float *loc_t, int64_t *conf_t, int32_t *bti, float *bto,
-                 void *ws, cudaStream_t st, bool encode_all = true, const float *conf = nullptr, int C = 0, unsigned *gmax_key = nullptr)
+                 void *ws, cudaStream_t st, bool encode_all = true)
 {
     dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
     MatchWs m = plan_match_ws(ws, B, N, total_gt);
     if (!bipartite) {
         FDT_CUDA(launch_pdl(k_match_default, grid, dim3(M_THREADS), st, (const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t, conf_t,
-                                                    bti, bto, encode_all, conf, C, gmax_key));
+                                                    bti, bto, encode_all));
         FDT_LAUNCH_CHECK();
     } else {
         FDT_CUDA(cudaMemsetAsync(m.bestprior, 0, (size_t)(total_gt > 0 ? total_gt : 1) * 8, st));
@@ -740,14 +983,12 @@ MineWs plan_mine_ws(void *ws, int B)
     return m;
 }
 
-template <int MODE>
-int launch_mine_tail(const float *loss_c, const MineWs &m, const int64_t *conf_t, const float *conf, int B, int64_t N, int C,
-                     int ratio, uint8_t *mask, LossAcc *acc, cudaStream_t st)
+int launch_mine_tail(const float *loss_c, const MineWs &m, int B, int64_t N, int ratio, uint8_t *mask, cudaStream_t st)
 {
     FDT_CUDA(launch_pdl(k_mine_select, dim3(B), dim3(MINE_THREADS), st, loss_c, (const int *)m.hist, (const int32_t *)m.num_pos, N, ratio, m.cutoff));
     FDT_LAUNCH_CHECK();
     dim3 grid((unsigned)((N + M_THREADS * APPLY_TILES - 1) / (M_THREADS * APPLY_TILES)), (unsigned)B);
-    FDT_CUDA(launch_pdl(k_mine_apply<MODE>, grid, dim3(M_THREADS), st, loss_c, (const unsigned long long *)m.cutoff, conf_t, conf, N, C, mask, acc));
+    FDT_CUDA(launch_pdl(k_mine_apply, grid, dim3(M_THREADS), st, loss_c, (const unsigned long long *)m.cutoff, N, mask));
     FDT_LAUNCH_CHECK();
     return FDT_OK;
 }
@@ -801,19 +1042,30 @@ FDT_API int fdt_hard_negative_mine(const float *loss_c, const uint8_t *pos, int 
     dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
     FDT_CUDA(launch_pdl(k_mine_hist, grid, dim3(M_THREADS), st, loss_c, pos, N, m.hist, m.num_pos));
     FDT_LAUNCH_CHECK();
-    return launch_mine_tail<0>(loss_c, m, nullptr, nullptr, B, N, 2, negpos_ratio, neg, nullptr, st);
+    return launch_mine_tail(loss_c, m, B, N, negpos_ratio, neg, st);
 }
 
-struct LossWs { LossAcc *acc; MineWs mine; float *loss_c_all; void *match; size_t bytes; };
-static LossWs plan_loss_ws(void *ws, int B, int64_t N, int64_t total_gt)
+// workspace of the fused forward: [zeroed per call by k_mbl_prepare: accumulators | num_pos, image tickets, candidate counts |
+// mining histogram] [partial maxima] [candidate lists B x N] [loss_c] [matcher scratch]
+struct LossWs {
+    LossAcc *acc; int32_t *num_pos; int *img_ticket; int *cand_cnt; int *hist; size_t zero_bytes;
+    unsigned *gmax_part; int *cand; float *loss_c_all; void *match; size_t bytes;
+};
+static LossWs plan_loss_ws(void *ws, int B, int64_t N, int64_t total_gt, int bipartite)
 {
     LossWs w;
     char *p = (char *)ws;
     size_t o = 0;
     w.acc = (LossAcc *)(p + o); o += 256;
-    w.mine = plan_mine_ws(p + o, B); o += w.mine.bytes;
+    w.num_pos = (int32_t *)(p + o); o += fdt_align256((size_t)B * 4);
+    w.img_ticket = (int *)(p + o); o += fdt_align256((size_t)B * 4);
+    w.cand_cnt = (int *)(p + o); o += fdt_align256((size_t)B * 4);
+    w.hist = (int *)(p + o); o += fdt_align256((size_t)B * MINE_BINS * 4);
+    w.zero_bytes = o;
+    w.gmax_part = (unsigned *)(p + o); o += fdt_align256((size_t)PREP_BLOCKS * 4);
+    w.cand = (int *)(p + o); o += fdt_align256((size_t)B * N * 4);
     w.loss_c_all = (float *)(p + o); o += fdt_align256((size_t)B * N * 4);
-    w.match = (void *)(p + o); o += plan_match_ws(nullptr, B, N, total_gt).bytes;
+    w.match = (void *)(p + o); o += bipartite ? plan_match_ws(nullptr, B, N, total_gt).bytes : 0;
     w.bytes = o;
     return w;
 }
@@ -821,7 +1073,7 @@ static LossWs plan_loss_ws(void *ws, int B, int64_t N, int64_t total_gt)
 FDT_API size_t fdt_multibox_workspace_bytes(int B, int64_t N, int, int64_t total_gt)
 {
     if (B <= 0 || N <= 0) return 256;
-    return plan_loss_ws(nullptr, B, N, total_gt).bytes;
+    return plan_loss_ws(nullptr, B, N, total_gt, 1).bytes;
 }
 
 FDT_API int fdt_multibox_loss_forward(const float *loc, const float *conf, const float *priors,
@@ -836,28 +1088,31 @@ FDT_API int fdt_multibox_loss_forward(const float *loc, const float *conf, const
     FDT_REQUIRE(B > 0 && N > 0 && C >= 2, FDT_E_INVALID, "fdt_multibox_loss_forward: needs B > 0, N > 0, C >= 2");
     FDT_REQUIRE(loc && conf && losses && norm && sel, FDT_E_INVALID, "fdt_multibox_loss_forward: null pointer argument");
     FDT_REQUIRE(fdt_aligned(loc, 16), FDT_E_INVALID, "fdt_multibox_loss_forward: loc needs 16-byte alignment");
-    FDT_REQUIRE(total_gt >= 0, FDT_E_INVALID, "fdt_multibox_loss_forward: negative total_gt");
-    LossWs w = plan_loss_ws(ws, B, N, total_gt);
+    FDT_REQUIRE(C != 2 || fdt_aligned(conf, 8), FDT_E_INVALID, "fdt_multibox_loss_forward: conf needs 8-byte alignment");
+    FDT_REQUIRE(total_gt >= 0 && negpos_ratio >= 0, FDT_E_INVALID, "fdt_multibox_loss_forward: negative total_gt / negpos_ratio");
+    LossWs w = plan_loss_ws(ws, B, N, total_gt, bipartite);
     FDT_REQUIRE(ws_bytes >= w.bytes, FDT_E_WORKSPACE, "fdt_multibox_loss_forward: workspace %zu < %zu bytes", ws_bytes, w.bytes);
     float *lca = loss_c_all ? loss_c_all : w.loss_c_all;
 
-    FDT_CUDA(cudaMemsetAsync(w.acc, 0, 256 + w.mine.bytes, st));
-    if (bipartite) {               // the default matcher folds the global max of conf (box_utils.py:268) into its own pass
-        const int64_t n_conf = (int64_t)B * N * C;
-        unsigned blocks = (unsigned)((n_conf + 256 * 8 - 1) / (256 * 8));
-        if (blocks > FDT_NUM_SMS * 8) blocks = FDT_NUM_SMS * 8;
-        k_conf_global_max<<<blocks, 256, 0, st>>>(conf, n_conf, &w.acc->gmax_key);
+    // three kernels behind the default matcher, chained by programmatic dependent launch: prepare -> match + loss terms -> mining
+    FDT_CUDA(launch_pdl(k_mbl_prepare, dim3(PREP_BLOCKS), dim3(PREP_THREADS), st, conf, (int64_t)B * N * C, w.gmax_part, (int4 *)ws,
+                        (int64_t)(w.zero_bytes / 16)));
+    FDT_LAUNCH_CHECK();
+    dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
+    if (!bipartite) {
+        FDT_CUDA(launch_pdl(k_match_loss, grid, dim3(M_THREADS), st, (const float4 *)priors, gt, gt_off, N, threshold, var0, var1, (float4 *)loc_t,
+                            conf_t, (const float4 *)loc, conf, C, w.acc, (const unsigned *)w.gmax_part, lca, w.num_pos, w.hist));
+        FDT_LAUNCH_CHECK();
+    } else {
+        rc = launch_match(priors, gt, gt_off, B, N, total_gt, threshold, var0, var1, 1, loc_t, conf_t, nullptr, nullptr, w.match, st, false);
+        if (rc != FDT_OK) return rc;
+        FDT_CUDA(launch_pdl(k_loss_prior, grid, dim3(M_THREADS), st, (const float4 *)loc, conf, (const float4 *)loc_t, (const int64_t *)conf_t, N, C,
+                            w.acc, (const unsigned *)w.gmax_part, lca, w.num_pos, w.hist));
         FDT_LAUNCH_CHECK();
     }
-    rc = launch_match(priors, gt, gt_off, B, N, total_gt, threshold, var0, var1, bipartite, loc_t, conf_t, nullptr, nullptr, w.match, st, false,
-                      bipartite ? nullptr : conf, C, &w.acc->gmax_key);
-    if (rc != FDT_OK) return rc;
-    dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
-    FDT_CUDA(launch_pdl(k_loss_prior, grid, dim3(M_THREADS), st, (const float4 *)loc, conf, (const float4 *)loc_t, (const int64_t *)conf_t, N, C, w.acc, lca, w.mine.num_pos, w.mine.hist));
-    FDT_LAUNCH_CHECK();
-    rc = launch_mine_tail<1>(lca, w.mine, conf_t, conf, B, N, C, negpos_ratio, sel, w.acc, st);
-    if (rc != FDT_OK) return rc;
-    FDT_CUDA(launch_pdl(k_loss_final, dim3(1), dim3(32), st, (const LossAcc *)w.acc, (const int32_t *)w.mine.num_pos, B, losses, norm));
+    dim3 agrid((unsigned)((N + M_THREADS * APPLY_TILES - 1) / (M_THREADS * APPLY_TILES)), (unsigned)B);
+    FDT_CUDA(launch_pdl(k_mine_apply2, agrid, dim3(M_THREADS), st, (const float *)lca, (const int *)w.hist, (const int32_t *)w.num_pos,
+                        (const int64_t *)conf_t, conf, N, C, B, negpos_ratio, sel, w.acc, w.img_ticket, w.cand_cnt, w.cand, losses, norm));
     FDT_LAUNCH_CHECK();
     return FDT_OK;
 }

@@ -108,6 +108,12 @@ int fdt_decode(const float *loc, const float *priors, int64_t n, float var0, flo
  * workspace: 256 bytes. */
 int fdt_log_sum_exp(const float *x, int64_t R, int C, float *out, void *ws, size_t ws_bytes, fdt_stream_t stream);
 
+/* Self-test of the library's fp32 exp / log (the convention above: (float)exp((double)x), (float)log((double)x); the common ranges
+ * take a lean fp64 evaluation and hand every value near an fp32 rounding boundary to the CUDA math library): compares both for the
+ * `count` consecutive float bit patterns from `first_bits` on.  which = 0 exp, 1 log.  result (device, 2 x uint64, zeroed by the
+ * call): [0] = mismatching patterns, [1] = the lowest mismatching pattern + 1 (all ones when there is none). */
+int fdt_selftest_cr_math(int which, uint32_t first_bits, uint64_t count, uint64_t *result, fdt_stream_t stream);
+
 /* ---- N1  nms  (layers/box_utils.py:275-340) ------------------------------------------------------
  * boxes[n,4], scores[n] -> keep[n] int64 zero-padded (indices into the input, descending score),
  * *count (device int64).  Sort ties: higher index first.  top_k <= 0 means n, as idx[-0:] does.

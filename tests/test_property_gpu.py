@@ -89,3 +89,20 @@ def test_tracker_random(seed, F, dmax, sigma, s_iou, s_h, t_min, empty_every):
     assert len(a) == len(b)
     for x, y in zip(a, b):
         assert x["start_frame"] == y["start_frame"] and x["max_score"] == y["max_score"] and x["bboxes"] == y["bboxes"]
+
+
+@pytest.mark.parametrize("which", [0, 1], ids=["exp", "log"])
+def test_lean_exp_log_equal_the_math_library_on_every_float(which):
+    """fdt_expf_cr / fdt_logf_cr (csrc/fdt_common.cuh): the lean fp64 evaluation of the common ranges must give the float that
+    (float)exp((double)x) / (float)log((double)x) gives for ALL 2^32 bit patterns (decode, encode, log_sum_exp and the mining
+    order of MultiBoxLoss depend on it bit for bit)."""
+    from fdt_b200 import _lib
+    dev = torch.device("cuda", torch.cuda.current_device())
+    res = torch.zeros(2, dtype=torch.int64, device=dev)
+    total = 0
+    for first in range(0, 1 << 32, 1 << 30):
+        _lib.check(_lib.lib().fdt_selftest_cr_math(which, first, 1 << 30, res.data_ptr(), _lib.stream_ptr()))
+        bad, lowest = (int(v) for v in res.cpu().numpy().view(np.uint64))
+        assert bad == 0, f"{bad} mismatching inputs from pattern {lowest - 1:#010x} on"
+        total += 1 << 30
+    assert total == 1 << 32
