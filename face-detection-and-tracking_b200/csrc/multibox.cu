@@ -248,21 +248,42 @@ k_match(const float4 *__restrict__ priors, const float *__restrict__ gt, const i
 // own list.  Two block barriers per tile and no compaction bookkeeping.  The IoU loop is the bulk of the forward's instructions:
 // one 32-byte shared-memory entry per GT box addressed through 32-bit shared addresses (the generic-address form re-derived the
 // shared window base inside the loop), GT 0 peeled (it seeds the arg max unconditionally, box_utils.py:197).
-struct __align__(32) GtEntry { float4 box; float area; float pad[3]; };
+struct __align__(32) GtEntry { float4 box; float area; float label; float pad[2]; };
 
+//
+// AREA_CULL (the fused forward only, which outputs nothing but the labels and the encoded POSITIVES): IoU <= min(area) / max(area),
+// so a GT box whose area is below thr * (smallest prior area of the warp) or above (largest prior area) / thr cannot reach the
+// positive threshold with any prior of the warp and is not listed.  Every box that does reach thr with some prior is listed, so a
+// positive's best overlap and arg max (first index among ties) are unchanged, and a prior whose true best is below thr still ends
+// below it: conf_t and the encoded rows are bit-identical; only the arg max of BACKGROUND priors (not an output here) may differ.
+// The 0.999 margin covers the few fp32 roundings between the bound and the computed IoU; boxes with a non-positive or NaN area
+// and GT 0 are always listed.  At the production threshold (0.35) the 16-pixel level drops ~85 % of its candidates and the 256- and
+// 512-pixel levels, whose warps used to walk every GT box of the image, usually list none.
+template <bool AREA_CULL>
 __device__ __forceinline__ void match_default_core(const float *__restrict__ gt, const int64_t g0, const int G, const float4 pf,
-                                                   const float area_b, const bool valid, GtEntry *s_gt, unsigned char *s_wl_warp,
-                                                   float &best, int &bi)
+                                                   const float area_b, const bool valid, const float thr, GtEntry *s_gt,
+                                                   unsigned char *s_wl_warp, float &best, int &bi)
 {
     const int tid = threadIdx.x, lane = tid & 31;
     float4 wb;                                         // bounding box of the warp's priors
+    float ap_lo = 0.0f, ap_hi = 0.0f;                  // thr' * smallest prior area, largest prior area / thr' (AREA_CULL)
     {
         unsigned k0 = valid ? fdt_float_key(pf.x) : 0xffffffffu, k1 = valid ? fdt_float_key(pf.y) : 0xffffffffu;
         unsigned k2 = valid ? fdt_float_key(pf.z) : 0u, k3 = valid ? fdt_float_key(pf.w) : 0u;
         k0 = __reduce_min_sync(0xffffffffu, k0); k1 = __reduce_min_sync(0xffffffffu, k1);
         k2 = __reduce_max_sync(0xffffffffu, k2); k3 = __reduce_max_sync(0xffffffffu, k3);
         wb = make_float4(fdt_key_float(k0), fdt_key_float(k1), fdt_key_float(k2), fdt_key_float(k3));
+        if (AREA_CULL) {
+            // any invalid lane, non-positive or NaN prior area switches the area cull off for the warp (amin <= 0)
+            const bool okp = valid && area_b > 0.0f;
+            const unsigned all_ok = __all_sync(0xffffffffu, okp || !valid) && __any_sync(0xffffffffu, okp);
+            const unsigned amin = __reduce_min_sync(0xffffffffu, okp ? __float_as_uint(area_b) : 0xffffffffu);
+            const unsigned amax = __reduce_max_sync(0xffffffffu, okp ? __float_as_uint(area_b) : 0u);
+            const float kk = 0.999f * thr;
+            if (all_ok && kk > 0.0f) { ap_lo = kk * __uint_as_float(amin); ap_hi = __uint_as_float(amax) / kk; }
+        }
     }
+    const bool area_cull = AREA_CULL && ap_lo > 0.0f;
     const unsigned a_gt = (unsigned)__cvta_generic_to_shared(s_gt);
     const unsigned a_wl = (unsigned)__cvta_generic_to_shared(s_wl_warp);
     best = 0.0f;
@@ -273,7 +294,7 @@ __device__ __forceinline__ void match_default_core(const float *__restrict__ gt,
         if (tid < tn) {
             const float *row = gt + 5 * (g0 + t0 + tid);
             const float4 a = make_float4(row[0], row[1], row[2], row[3]);
-            s_gt[tid].box = a; s_gt[tid].area = (a.z - a.x) * (a.w - a.y);
+            s_gt[tid].box = a; s_gt[tid].area = (a.z - a.x) * (a.w - a.y); s_gt[tid].label = row[4];
         }
         __syncthreads();
         int wn = 0;
@@ -283,7 +304,12 @@ __device__ __forceinline__ void match_default_core(const float *__restrict__ gt,
             if (g < tn) {
                 const float4 a2 = s_gt[g].box;
                 const float wbb = fminf(a2.z, wb.z) - fmaxf(a2.x, wb.x), hbb = fminf(a2.w, wb.w) - fmaxf(a2.y, wb.y);
-                k2 = (t0 + g == 0) || !(wbb <= 0.0f || hbb <= 0.0f);           // NaN keeps
+                k2 = !(wbb <= 0.0f || hbb <= 0.0f);                            // NaN keeps
+                if (area_cull) {
+                    const float ag = s_gt[g].area;
+                    if (ag > 0.0f && (ag < ap_lo || ag > ap_hi)) k2 = false;
+                }
+                k2 = k2 || (t0 + g == 0);
             }
             const unsigned bal2 = __ballot_sync(0xffffffffu, k2);
             if (k2) s_wl_warp[wn + __popc(bal2 & ((1u << lane) - 1u))] = (unsigned char)g;
@@ -342,7 +368,7 @@ k_match_default(const float4 *__restrict__ priors, const float *__restrict__ gt,
     const float area_b = (pf.z - pf.x) * (pf.w - pf.y);
     float best;
     int bi;
-    match_default_core(gt, g0, G, pf, area_b, valid, s_gt, s_wl[warp], best, bi);
+    match_default_core<false>(gt, g0, G, pf, area_b, valid, thr, s_gt, s_wl[warp], best, bi);
     if (valid) finalize_prior(gt, g0, bi, best, thr, pr, v0, v1, loc_t, conf_t, bti, bto, t, encode_all);
 }
 
@@ -466,9 +492,10 @@ __device__ __forceinline__ float gmax_from_partials(const unsigned *__restrict__
 }
 
 // per-prior loss terms shared by k_loss_prior and the fused k_match_loss (multibox_loss.py:96-110): smooth L1 of a positive
-// (beta = 1, sum) in `sl`, the mining input loss_c (0 for positives) returned
-__device__ __forceinline__ float prior_loss_terms(const float4 a, const float4 g, const bool is_pos, const float *__restrict__ row,
-                                                  const int C, const int64_t label, const float xmax, double &sl)
+// (beta = 1, sum) in `sl`, the mining input loss_c (0 for positives) returned; cv = the row when C == 2 (loaded by the caller)
+__device__ __forceinline__ float prior_loss_terms(const float4 a, const float4 g, const bool is_pos, const float2 cv,
+                                                  const float *__restrict__ row, const int C, const int64_t label, const float xmax,
+                                                  double &sl)
 {
     if (is_pos) {
         const float d[4] = {fabsf(a.x - g.x), fabsf(a.y - g.y), fabsf(a.z - g.z), fabsf(a.w - g.w)};
@@ -477,9 +504,8 @@ __device__ __forceinline__ float prior_loss_terms(const float4 a, const float4 g
     }
     float s, xl;
     if (C == 2) {
-        const float2 cv = __ldg(reinterpret_cast<const float2 *>(row));
         s = fdt_expf_cr(cv.x - xmax) + fdt_expf_cr(cv.y - xmax);                   // box_utils.py:269
-        xl = label ? cv.y : cv.x;
+        xl = label == 0 ? cv.x : (label == 1 ? cv.y : row[label]);
     } else {
         s = 0.0f;
         for (int c = 0; c < C; ++c) s += fdt_expf_cr(row[c] - xmax);
@@ -527,7 +553,9 @@ k_loss_prior(const float4 *__restrict__ loc, const float *__restrict__ conf, con
         is_pos = label > 0;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
         if (is_pos) { a = loc[t]; g = loc_t[t]; }
-        const float lc = prior_loss_terms(a, g, is_pos, conf + t * C, C, label, xmax, sl);
+        float2 cv = make_float2(0.f, 0.f);
+        if (C == 2) cv = __ldg(reinterpret_cast<const float2 *>(conf + t * 2));
+        const float lc = prior_loss_terms(a, g, is_pos, cv, conf + t * C, C, label, xmax, sl);
         loss_c_all[t] = lc;
         atomicAdd(&hist[(size_t)b * MINE_BINS + mine_bin2(lc)], 1);
     }
@@ -538,7 +566,7 @@ k_loss_prior(const float4 *__restrict__ loc, const float *__restrict__ conf, con
 // and -- once k_mbl_prepare's maximum is there -- the loss terms and the mining histogram of k_loss_prior on the values still in
 // registers.  The matcher is bound by instruction issue and the loss terms by fp64 latency; in one kernel the warps of both phases
 // share every SM, and conf_t / loc_t are not read back.
-__global__ void __launch_bounds__(M_THREADS, 4)
+__global__ void __launch_bounds__(M_THREADS, 5)
 k_match_loss(const float4 *__restrict__ priors, const float *__restrict__ gt, const int64_t *__restrict__ gt_off,
              int64_t N, float thr, float v0, float v1, float4 *__restrict__ loc_t, int64_t *__restrict__ conf_t,
              const float4 *__restrict__ loc, const float *__restrict__ conf, int C, LossAcc *__restrict__ acc,
@@ -548,6 +576,7 @@ k_match_loss(const float4 *__restrict__ priors, const float *__restrict__ gt, co
     __shared__ unsigned char s_wl[M_WARPS][GT_TILE];
     __shared__ double s_tot;
     __shared__ int s_cnt;
+    __shared__ float s_xmax;
     const MatchBlock mb = match_block();
     const int b = mb.b, tid = threadIdx.x, warp = tid >> 5;
     const int64_t p = (int64_t)mb.tile * M_THREADS + tid;
@@ -557,6 +586,8 @@ k_match_loss(const float4 *__restrict__ priors, const float *__restrict__ gt, co
     const int64_t t = (int64_t)b * N + p;
     if (tid == 0) { s_tot = 0.0; s_cnt = 0; }
     const float4 pr = priors[valid ? p : 0];
+    float2 cv = make_float2(0.f, 0.f);                 // the row of the loss phase, in flight during the match
+    if (C == 2 && valid) cv = __ldg(reinterpret_cast<const float2 *>(conf + t * 2));
     int64_t label = 0;
     float4 enc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (G > 0) {                                       // G <= 0: the reference raises (Q3); defined: all background
@@ -565,25 +596,32 @@ k_match_loss(const float4 *__restrict__ priors, const float *__restrict__ gt, co
         const float area_b = (pf.z - pf.x) * (pf.w - pf.y);
         float best;
         int bi;
-        match_default_core(gt, g0, G, pf, area_b, valid, s_gt, s_wl[warp], best, bi);
-        const float *row = gt + 5 * (g0 + bi);
-        float c = row[4] + 1.0f;                       // box_utils.py:205
-        if (best < thr) c = 0.0f;                      // :206
-        label = (int64_t)c;                            // :210 (float -> long)
-        // :208 encodes every prior; the loss only reads the positives (multibox_loss.py:96-101): zeros elsewhere
-        if (label > 0) enc = fdt_encode1(make_float4(row[0], row[1], row[2], row[3]), pr, v0, v1);
+        match_default_core<true>(gt, g0, G, pf, area_b, valid, thr, s_gt, s_wl[warp], best, bi);
+        if (!(best < thr)) {                           // box_utils.py:205-206 (a NaN overlap stays positive, as there)
+            float4 m;
+            float lab;
+            if (G <= GT_TILE) { m = s_gt[bi].box; lab = s_gt[bi].label; }       // the only tile is still staged
+            else { const float *row = gt + 5 * (g0 + bi); m = make_float4(row[0], row[1], row[2], row[3]); lab = row[4]; }
+            label = (int64_t)(lab + 1.0f);             // :205, :210 (float -> long)
+            // :208 encodes every prior; the loss only reads the positives (multibox_loss.py:96-101): zeros elsewhere
+            if (label > 0) enc = fdt_encode1(m, pr, v0, v1);
+        }
     }
+    const int is_pos = valid && label > 0;
+    float4 a = enc;
+    if (is_pos) a = loc[t];
     if (valid) { conf_t[t] = label; loc_t[t] = enc; }
     cudaTriggerProgrammaticLaunchCompletion();
     cudaGridDependencySynchronize();                   // k_mbl_prepare: zeroed state + the partial maxima
+    if (warp == 0) {
+        const float x = gmax_from_partials(gmax_part);
+        if (tid == 0) s_xmax = x;
+    }
     __syncthreads();
-    const float xmax = gmax_from_partials(gmax_part);
+    const float xmax = s_xmax;
     double sl = 0.0;
-    const int is_pos = valid && label > 0;
     if (valid) {
-        float4 a = enc;
-        if (is_pos) a = loc[t];
-        const float lc = prior_loss_terms(a, enc, is_pos, conf + t * C, C, label, xmax, sl);
+        const float lc = prior_loss_terms(a, enc, is_pos, cv, conf + t * C, C, label, xmax, sl);
         loss_c_all[t] = lc;
         atomicAdd(&hist[(size_t)b * MINE_BINS + mine_bin2(lc)], 1);
     }
@@ -718,30 +756,82 @@ k_mine_apply(const float *__restrict__ loss_c, const unsigned long long *__restr
     }
 }
 
+// fp64 exp / log of the cross entropy below: the lean evaluations of fdt_common.cuh without the final rounding to fp32 (a few
+// fp64 ulps of error; the loss is a sum of thousands of such terms compared at 1e-5) -- the library routines are several times
+// longer, and this kernel is a chain of dependent latencies
+__device__ __forceinline__ double lean_exp_d(const float x)
+{
+    if (x <= 0.0f && x >= -87.0f) {
+        const double xd = (double)x;
+        double t = fma(xd, FDT_LN2[0], FDT_LN2[1]);
+        const int k = __double2loint(t);
+        t -= FDT_LN2[1];
+        double r = fma(t, -FDT_LN2[2], xd);
+        r = fma(t, -FDT_LN2[3], r);
+        double p = FDT_EXP_C[13];
+#pragma unroll
+        for (int n = 12; n >= 0; --n) p = fma(p, r, FDT_EXP_C[n]);
+        return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    }
+    return exp((double)x);
+}
+__device__ __forceinline__ double lean_log_d(const double s)
+{
+    const int hi = __double2hiint(s);
+    if ((unsigned)(hi - 0x00100000) < 0x7fe00000u) {         // positive, normal, finite
+        int e = (hi >> 20) - 1023;
+        double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(s));
+        if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+        const double f = m - 1.0, den = m + 1.0;
+        double y;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
+        double er = fma(-den, y, 1.0);
+        y = fma(y, er, y);
+        er = fma(-den, y, 1.0);
+        y = fma(y, er, y);
+        double u = f * y;
+        u = fma(fma(-den, u, f), y, u);
+        const double u2 = u * u;
+        double q = FDT_LOG_C[9];
+#pragma unroll
+        for (int n = 8; n >= 0; --n) q = fma(q, u2, FDT_LOG_C[n]);
+        const double ed = (double)e;
+        double res = fma(u, u2 * q, u + u);
+        res = fma(ed, FDT_LN2[3], res);
+        return fma(ed, FDT_LN2[2], res);
+    }
+    return log(s);
+}
 // cross entropy of one prior row, F.cross_entropy (sum) in fp64 (multibox_loss.py:128)
 __device__ __forceinline__ double ce_row(const float *__restrict__ row, const int C, const int64_t label)
 {
+    if (C == 2) {
+        const float2 v = __ldg(reinterpret_cast<const float2 *>(row));
+        const float m = fmaxf(v.x, v.y);
+        const double s = lean_exp_d(v.x - m) + lean_exp_d(v.y - m);
+        return (lean_log_d(s) + (double)m) - (double)(label == 0 ? v.x : (label == 1 ? v.y : row[label]));
+    }
     float m = row[0];
     for (int c = 1; c < C; ++c) m = fmaxf(m, row[c]);
     double s = 0.0;
-    for (int c = 0; c < C; ++c) s += exp((double)(row[c] - m));
-    return (log(s) + (double)m) - (double)row[label];
+    for (int c = 0; c < C; ++c) s += lean_exp_d(row[c] - m);
+    return (lean_log_d(s) + (double)m) - (double)row[label];
 }
 
 // Mining + selection + cross entropy + the final division of the fused forward, one kernel (multibox_loss.py:112-135).
 //   1. every block finds the cutoff BIN of its image from the 4,096-bin histogram (descending scan; num_neg = min(ratio * num_pos,
 //      N - 1), :115): bins above it are hard negatives, bins below are not;
-//   2. it classifies its 2,048 priors, writes the selection mask (pos | neg, :119-120), lists the selected rows and sums their cross
-//      entropy; priors IN the cutoff bin go to the image's candidate list;
+//   2. it classifies its 2,048 priors (loaded before the scan), writes the selection mask (pos | neg, :119-120), lists the selected
+//      rows and sums their cross entropy; the composites of the priors IN the cutoff bin go to the image's candidate list;
 //   3. the LAST block of an image (a ticket) settles the candidates: the need0 largest composites (loss key, then lower prior index
 //      -- the order of the reference's stable descending sort) among them are negatives too;
-//   4. the last block of the grid divides by N (:130-135).
+//   4. the last of those B blocks divides by N (:130-135).
 // No separate select and final kernels, and the row is read once.
 __global__ void __launch_bounds__(M_THREADS)
 k_mine_apply2(const float *__restrict__ loss_c, const int *__restrict__ hist, const int32_t *__restrict__ num_pos,
               const int64_t *__restrict__ conf_t, const float *__restrict__ conf, const int64_t N, const int C, const int B,
               const int negpos_ratio, uint8_t *__restrict__ out_mask, LossAcc *__restrict__ acc, int *__restrict__ img_ticket,
-              int *__restrict__ cand_cnt, int *__restrict__ cand, float *__restrict__ losses, float *__restrict__ norm)
+              int *__restrict__ cand_cnt, unsigned long long *__restrict__ cand, float *__restrict__ losses, float *__restrict__ norm)
 {
     fdt_pdl_enter();
     __shared__ double s_red[M_WARPS];
@@ -751,6 +841,15 @@ k_mine_apply2(const float *__restrict__ loss_c, const int *__restrict__ hist, co
     __shared__ int s_sel[2];
     __shared__ int s_n, s_flag;
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // the block's rows first: their latency overlaps the histogram scan
+    float lcv[APPLY_TILES];
+    bool posv[APPLY_TILES];
+#pragma unroll
+    for (int u = 0; u < APPLY_TILES; ++u) {
+        const int64_t p = ((int64_t)blockIdx.x * APPLY_TILES + u) * M_THREADS + tid;
+        lcv[u] = 0.0f; posv[u] = false;
+        if (p < N) { lcv[u] = loss_c[(int64_t)b * N + p]; posv[u] = conf_t[(int64_t)b * N + p] > 0; }
+    }
     long long num_neg = (long long)negpos_ratio * num_pos[b];                   // multibox_loss.py:115
     if (num_neg > N - 1) num_neg = N - 1;
     const bool mining = num_neg > 0;                                            // (block-uniform)
@@ -786,16 +885,15 @@ k_mine_apply2(const float *__restrict__ loss_c, const int *__restrict__ hist, co
         __syncthreads();
     }
     // ---- 2. classify, mask, lists
-#pragma unroll 2
+#pragma unroll
     for (int u = 0; u < APPLY_TILES; ++u) {
         const int64_t p = ((int64_t)blockIdx.x * APPLY_TILES + u) * M_THREADS + tid;
         bool sel = false, cnd = false;
         if (p < N) {
-            const int64_t t = (int64_t)b * N + p;
-            const int bin = mine_bin2(loss_c[t]);
-            sel = bin > d0 || conf_t[t] > 0;                                    // (d0 = MINE_BINS without mining)
+            const int bin = mine_bin2(lcv[u]);
+            sel = bin > d0 || posv[u];                                          // (d0 = MINE_BINS without mining)
             cnd = bin == d0;
-            out_mask[t] = (uint8_t)sel;
+            out_mask[(int64_t)b * N + p] = (uint8_t)sel;
         }
         // a few percent of the priors are selected: list them and evaluate the fp64 cross entropy over the dense list below
         const unsigned bal = __ballot_sync(0xffffffffu, sel);
@@ -803,40 +901,46 @@ k_mine_apply2(const float *__restrict__ loss_c, const int *__restrict__ hist, co
             int base = 0;
             if (lane == 0) base = atomicAdd(&s_n, __popc(bal));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (sel) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)p;
+            if (sel) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (int)p | (posv[u] ? (int)0x80000000 : 0);
         }
         const unsigned cbal = __ballot_sync(0xffffffffu, cnd);
         if (cbal) {
             int base = 0;
             if (lane == 0) base = atomicAdd(&cand_cnt[b], __popc(cbal));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (cnd) cand[(size_t)b * N + base + __popc(cbal & ((1u << lane) - 1u))] = (int)p;
+            if (cnd) cand[(size_t)b * N + base + __popc(cbal & ((1u << lane) - 1u))] = mine_comp(lcv[u], (unsigned)p);
         }
     }
+    __threadfence();                                                            // mask + candidates, before the ticket below
     __syncthreads();
     double ce = 0.0;
     {
         const int n = s_n;
         for (int e = tid; e < n; e += M_THREADS) {
-            const int64_t t = (int64_t)b * N + s_list[e];
-            ce += ce_row(conf + t * C, C, conf_t[t]);
+            const int v = s_list[e];
+            const int64_t t = (int64_t)b * N + (v & 0x7fffffff);
+            ce += ce_row(conf + t * C, C, v < 0 ? conf_t[t] : 0);
         }
     }
+    ce = block_sum<double>(ce, s_red);
+    if (tid == 0) {
+        if (ce != 0.0) atomicAdd(&acc->loss_c, ce);
+        __threadfence();
+        s_flag = atomicAdd(&img_ticket[b], 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_flag) return;
     // ---- 3. the last block of the image settles the cutoff bin
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_flag = atomicAdd(&img_ticket[b], 1) == (int)gridDim.x - 1;
-    __syncthreads();
-    if (s_flag && mining) {
+    ce = 0.0;
+    if (mining) {
         __threadfence();
         const int n = *(volatile int *)&cand_cnt[b];
-        const int *cl = cand + (size_t)b * N;
-        const float *lrow = loss_c + (size_t)b * N;
+        const unsigned long long *cl = cand + (size_t)b * N;
         unsigned long long cutoff = 0ull;                                       // need0 == n: every candidate
         if (need0 < n && n < APPLY_TILES * M_THREADS / 2) {
             // rank among the candidates in shared memory: selected <=> fewer than need0 composites are larger
             unsigned long long *s_comp = reinterpret_cast<unsigned long long *>(s_list);
-            for (int e = tid; e < n; e += M_THREADS) { const int p = __ldcg(cl + e); s_comp[e] = mine_comp(__ldcg(lrow + p), (unsigned)p); }
+            for (int e = tid; e < n; e += M_THREADS) s_comp[e] = __ldcg(cl + e);
             __syncthreads();
             for (int e = tid; e < n; e += M_THREADS) {
                 const unsigned long long c = s_comp[e];
@@ -854,8 +958,7 @@ k_mine_apply2(const float *__restrict__ loss_c, const int *__restrict__ hist, co
                 s_h[tid] = 0;
                 __syncthreads();
                 for (int e = tid; e < n; e += M_THREADS) {
-                    const int p = __ldcg(cl + e);
-                    const unsigned long long c = mine_comp(__ldcg(lrow + p), (unsigned)p);
+                    const unsigned long long c = __ldcg(cl + e);
                     if ((c & pmask) == prefix) atomicAdd(&s_h[(int)((c >> shift) & 255ull)], 1);
                 }
                 __syncthreads();
@@ -873,29 +976,35 @@ k_mine_apply2(const float *__restrict__ loss_c, const int *__restrict__ hist, co
             cutoff = prefix;
         }
         for (int e = tid; e < n; e += M_THREADS) {
-            const int p = __ldcg(cl + e);
-            const int64_t t = (int64_t)b * N + p;
-            if (mine_comp(__ldcg(lrow + p), (unsigned)p) >= cutoff && conf_t[t] <= 0) {     // positives are selected already
-                out_mask[t] = 1;
-                ce += ce_row(conf + t * C, C, 0);
-            }
+            const unsigned long long c = __ldcg(cl + e);
+            if (c < cutoff) continue;
+            const int64_t t = (int64_t)b * N + (unsigned)~(unsigned)c;
+            // positives are selected already; their loss is 0, so they can only be candidates when the cutoff bin is bin 0
+            if (d0 == 0 && conf_t[t] > 0) continue;
+            out_mask[t] = 1;
+            ce += ce_row(conf + t * C, C, 0);
         }
     }
     ce = block_sum<double>(ce, s_red);
-    // ---- 4. accumulate; the last block of the grid finishes (multibox_loss.py:130-135)
+    // ---- 4. the last of the B settling blocks finishes (multibox_loss.py:130-135)
     if (tid == 0) {
         if (ce != 0.0) atomicAdd(&acc->loss_c, ce);
         __threadfence();
-        if (atomicAdd(&acc->done, 1u) == gridDim.x * gridDim.y - 1u) {
-            __threadfence();
-            long long n = 0;
-            for (int i = 0; i < B; ++i) n += num_pos[i];
-            double Nn = (double)n;                         // :130
-            if (n == 0) Nn = (double)B;                    // :132-133
-            losses[0] = (float)(*(volatile double *)&acc->loss_l / Nn);
-            losses[1] = (float)(*(volatile double *)&acc->loss_c / Nn);
-            norm[0] = (float)Nn;
-        }
+        s_flag = atomicAdd(&acc->done, 1u) == (unsigned)B - 1u;
+    }
+    __syncthreads();
+    if (!s_flag || warp != 0) return;
+    __threadfence();
+    long long n = 0;
+    for (int i = lane; i < B; i += 32) n += num_pos[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (lane == 0) {
+        double Nn = (double)n;                         // :130
+        if (n == 0) Nn = (double)B;                    // :132-133
+        losses[0] = (float)(*(volatile double *)&acc->loss_l / Nn);
+        losses[1] = (float)(*(volatile double *)&acc->loss_c / Nn);
+        norm[0] = (float)Nn;
     }
 }
 
@@ -1049,7 +1158,7 @@ FDT_API int fdt_hard_negative_mine(const float *loss_c, const uint8_t *pos, int 
 // mining histogram] [partial maxima] [candidate lists B x N] [loss_c] [matcher scratch]
 struct LossWs {
     LossAcc *acc; int32_t *num_pos; int *img_ticket; int *cand_cnt; int *hist; size_t zero_bytes;
-    unsigned *gmax_part; int *cand; float *loss_c_all; void *match; size_t bytes;
+    unsigned *gmax_part; unsigned long long *cand; float *loss_c_all; void *match; size_t bytes;
 };
 static LossWs plan_loss_ws(void *ws, int B, int64_t N, int64_t total_gt, int bipartite)
 {
@@ -1063,7 +1172,7 @@ static LossWs plan_loss_ws(void *ws, int B, int64_t N, int64_t total_gt, int bip
     w.hist = (int *)(p + o); o += fdt_align256((size_t)B * MINE_BINS * 4);
     w.zero_bytes = o;
     w.gmax_part = (unsigned *)(p + o); o += fdt_align256((size_t)PREP_BLOCKS * 4);
-    w.cand = (int *)(p + o); o += fdt_align256((size_t)B * N * 4);
+    w.cand = (unsigned long long *)(p + o); o += fdt_align256((size_t)B * N * 8);
     w.loss_c_all = (float *)(p + o); o += fdt_align256((size_t)B * N * 4);
     w.match = (void *)(p + o); o += bipartite ? plan_match_ws(nullptr, B, N, total_gt).bytes : 0;
     w.bytes = o;

@@ -21,7 +21,7 @@ for ln in open(sass, errors="replace"):
     m = re.search(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', ln)
     if m:
         # with `nvdisasm -gi` an inline chain is printed innermost first; keep the outermost frame (the kernel body)
-        if m.group(3):
+        if m.group(3) and not __import__("os").environ.get("INNER"):
             cur_line = (m.group(3).split("/")[-1], int(m.group(4)), "")
         else:
             cur_line = (m.group(1).split("/")[-1], int(m.group(2)), "")
