@@ -56,19 +56,19 @@ __device__ __forceinline__ unsigned gmax_key_of(float v) { return v != v ? 0xfff
 // (a NaN loss ranks highest whatever its sign bit, as torch.sort does)
 __device__ __forceinline__ unsigned long long mine_comp(float v, unsigned p) { return ((unsigned long long)(v != v ? 0xffffffffu : fdt_float_key(v)) << 32) | (unsigned)~p; }
 
-// Dispatch order of the matchers: blocks are issued x-fastest, image by image, and the blocks of the coarse pyramid levels (the END of
-// the prior array: a 512-pixel prior overlaps most GT boxes, so its warp walks the whole list) run several times longer than the rest
-// -- in image order the last image's coarse tiles start last and the kernel ends with a dozen SMs finishing them alone (ncu: SMs busy
-// 61 % of the kernel).  Remapped: linear block id -> image = id % B, tile = last - id / B, i.e. every image's last tile first.
+// Dispatch order of the matchers: blocks are issued x-fastest, and the blocks of the coarse pyramid levels (the END of the prior
+// array: a 512-pixel prior overlaps most GT boxes) run several times longer than the rest -- in image-major order the last image's
+// coarse tiles start last and the kernel ends with a dozen SMs finishing them alone (ncu: SMs busy 61 % of the kernel).  The grid
+// is (images, tiles): x = image, y counts the tiles from the last one down, i.e. every image's last tile first (and no division).
 struct MatchBlock { int b; int tile; };
 __device__ __forceinline__ MatchBlock match_block()
 {
-    const int id = blockIdx.y * gridDim.x + blockIdx.x;
     MatchBlock m;
-    m.b = id % (int)gridDim.y;
-    m.tile = (int)gridDim.x - 1 - id / (int)gridDim.y;
+    m.b = (int)blockIdx.x;
+    m.tile = (int)gridDim.y - 1 - (int)blockIdx.y;
     return m;
 }
+__host__ inline dim3 match_grid(int B, int64_t N) { return dim3((unsigned)B, (unsigned)((N + M_THREADS - 1) / M_THREADS)); }
 
 struct GtTile {
     float4 box[GT_TILE];
@@ -893,7 +893,8 @@ k_mine_apply2(const float *__restrict__ loss_c, const int *__restrict__ hist, co
             const int bin = mine_bin2(lcv[u]);
             sel = bin > d0 || posv[u];                                          // (d0 = MINE_BINS without mining)
             cnd = bin == d0;
-            out_mask[(int64_t)b * N + p] = (uint8_t)sel;
+            // the mask byte of a candidate is written by the settling block alone (no ordering between two writers needed)
+            if (!cnd || sel) out_mask[(int64_t)b * N + p] = (uint8_t)sel;
         }
         // a few percent of the priors are selected: list them and evaluate the fp64 cross entropy over the dense list below
         const unsigned bal = __ballot_sync(0xffffffffu, sel);
@@ -909,10 +910,12 @@ k_mine_apply2(const float *__restrict__ loss_c, const int *__restrict__ hist, co
             if (lane == 0) base = atomicAdd(&cand_cnt[b], __popc(cbal));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (cnd) cand[(size_t)b * N + base + __popc(cbal & ((1u << lane) - 1u))] = mine_comp(lcv[u], (unsigned)p);
+            __threadfence();                                                    // the list entries, before the ticket below
         }
     }
-    __threadfence();                                                            // mask + candidates, before the ticket below
     __syncthreads();
+    // the image's ticket is taken now: the settling block works while the others still sum their cross entropy
+    if (tid == 0) s_flag = atomicAdd(&img_ticket[b], 1) == (int)gridDim.x - 1;
     double ce = 0.0;
     {
         const int n = s_n;
@@ -922,17 +925,9 @@ k_mine_apply2(const float *__restrict__ loss_c, const int *__restrict__ hist, co
             ce += ce_row(conf + t * C, C, v < 0 ? conf_t[t] : 0);
         }
     }
-    ce = block_sum<double>(ce, s_red);
-    if (tid == 0) {
-        if (ce != 0.0) atomicAdd(&acc->loss_c, ce);
-        __threadfence();
-        s_flag = atomicAdd(&img_ticket[b], 1) == (int)gridDim.x - 1;
-    }
     __syncthreads();
-    if (!s_flag) return;
+    if (s_flag && mining) {
     // ---- 3. the last block of the image settles the cutoff bin
-    ce = 0.0;
-    if (mining) {
         __threadfence();
         const int n = *(volatile int *)&cand_cnt[b];
         const unsigned long long *cl = cand + (size_t)b * N;
@@ -977,20 +972,20 @@ k_mine_apply2(const float *__restrict__ loss_c, const int *__restrict__ hist, co
         }
         for (int e = tid; e < n; e += M_THREADS) {
             const unsigned long long c = __ldcg(cl + e);
-            if (c < cutoff) continue;
             const int64_t t = (int64_t)b * N + (unsigned)~(unsigned)c;
-            // positives are selected already; their loss is 0, so they can only be candidates when the cutoff bin is bin 0
+            // positives are selected (and written) already; their loss is 0, so they can only be candidates when the cutoff bin is 0
             if (d0 == 0 && conf_t[t] > 0) continue;
-            out_mask[t] = 1;
-            ce += ce_row(conf + t * C, C, 0);
+            const bool take = c >= cutoff;
+            out_mask[t] = (uint8_t)take;
+            if (take) ce += ce_row(conf + t * C, C, 0);
         }
     }
     ce = block_sum<double>(ce, s_red);
-    // ---- 4. the last of the B settling blocks finishes (multibox_loss.py:130-135)
+    // ---- 4. the last block of the grid finishes (multibox_loss.py:130-135)
     if (tid == 0) {
         if (ce != 0.0) atomicAdd(&acc->loss_c, ce);
         __threadfence();
-        s_flag = atomicAdd(&acc->done, 1u) == (unsigned)B - 1u;
+        s_flag = atomicAdd(&acc->done, 1u) == gridDim.x * gridDim.y - 1u;
     }
     __syncthreads();
     if (!s_flag || warp != 0) return;
@@ -1064,12 +1059,12 @@ int launch_match(const float *priors, const float *gt, const int64_t *gt_off, in
     dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
     MatchWs m = plan_match_ws(ws, B, N, total_gt);
     if (!bipartite) {
-        FDT_CUDA(launch_pdl(k_match_default, grid, dim3(M_THREADS), st, (const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t, conf_t,
+        FDT_CUDA(launch_pdl(k_match_default, match_grid(B, N), dim3(M_THREADS), st, (const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t, conf_t,
                                                     bti, bto, encode_all));
         FDT_LAUNCH_CHECK();
     } else {
         FDT_CUDA(cudaMemsetAsync(m.bestprior, 0, (size_t)(total_gt > 0 ? total_gt : 1) * 8, st));
-        FDT_CUDA(launch_pdl(k_match<true>, grid, dim3(M_THREADS), st, (const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t, conf_t,
+        FDT_CUDA(launch_pdl(k_match<true>, match_grid(B, N), dim3(M_THREADS), st, (const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t, conf_t,
                                                   bti, bto, m.tmp_idx, m.tmp_ov, m.bestprior, encode_all));
         FDT_LAUNCH_CHECK();
         FDT_CUDA(launch_pdl(k_match_bipartite_finalize, grid, dim3(M_THREADS), st, (const float4 *)priors, gt, gt_off, N, thr, v0, v1, (float4 *)loc_t,
@@ -1114,7 +1109,7 @@ FDT_API size_t fdt_match_workspace_bytes(int B, int64_t N, int64_t total_gt)
 static int match_args_ok(const char *who, const float *priors, const float *gt, const int64_t *gt_off, int B, int64_t N,
                          const float *loc_t, const int64_t *conf_t, const void *ws)
 {
-    FDT_REQUIRE(B >= 0 && N >= 0 && N < (1ll << 31), FDT_E_INVALID, "%s: bad sizes B=%d N=%lld", who, B, (long long)N);
+    FDT_REQUIRE(B >= 0 && N >= 0 && N <= 65535ll * M_THREADS && B <= 65535, FDT_E_INVALID, "%s: bad sizes B=%d N=%lld", who, B, (long long)N);
     if (B == 0 || N == 0) return FDT_OK;
     FDT_REQUIRE(priors && gt && gt_off && loc_t && conf_t && ws, FDT_E_INVALID, "%s: null pointer argument", who);
     FDT_REQUIRE(fdt_aligned(priors, 16) && fdt_aligned(loc_t, 16) && fdt_aligned(ws, 256), FDT_E_INVALID,
@@ -1209,7 +1204,7 @@ FDT_API int fdt_multibox_loss_forward(const float *loc, const float *conf, const
     FDT_LAUNCH_CHECK();
     dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
     if (!bipartite) {
-        FDT_CUDA(launch_pdl(k_match_loss, grid, dim3(M_THREADS), st, (const float4 *)priors, gt, gt_off, N, threshold, var0, var1, (float4 *)loc_t,
+        FDT_CUDA(launch_pdl(k_match_loss, match_grid(B, N), dim3(M_THREADS), st, (const float4 *)priors, gt, gt_off, N, threshold, var0, var1, (float4 *)loc_t,
                             conf_t, (const float4 *)loc, conf, C, w.acc, (const unsigned *)w.gmax_part, lca, w.num_pos, w.hist));
         FDT_LAUNCH_CHECK();
     } else {
