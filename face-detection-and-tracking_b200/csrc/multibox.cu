@@ -2,20 +2,19 @@
 // (layers/box_utils.py:103-210), per-prior confidence loss, hard-negative mining, loss reduction and
 // the backward pass, for sm_100a.
 //
-//   k_match        one thread per (image, prior); GT boxes of the image staged through shared memory in
-//                  tiles; IoU = inter / ((area_a + area_b) - inter) exactly as calculate_iou
-//                  (box_utils.py:94-100), argmax with first-index ties (torch.max(0)), then label +
-//                  encode written straight to loc_t / conf_t -- the [G,N] overlap matrix is never
-//                  materialised.  Bipartite mode also reduces the best prior per GT (warp REDUX ->
-//                  shared -> one 64-bit atomicMax per block and GT) and a second pass applies
-//                  box_utils.py:150-154.
-//   k_loss_prior   smooth-L1 over positives (:96-101) and the mining input loss_c (:104-110).
-//   mining         neg = rank < num_neg of the descending sort (:112-116) == the num_neg largest 64-bit composites
-//                  (loss key << 32 | ~prior): unique, so ties resolve to the lower prior index.  k_loss_prior (or
-//                  k_mine_hist) histograms the top 12 bits chip-wide, k_mine_select (one CTA per image) finishes an MSB
-//                  radix select 12 bits per row scan (normally 2 scans) -> one cutoff per image, k_mine_apply (chip-wide)
-//                  writes the mask and accumulates CE over pos U neg (:119-128).
-//   k_loss_final / k_multibox_backward.
+//   forward, default matcher (three kernels chained by programmatic dependent launch):
+//     k_mbl_prepare   zeroes the per-call state and reduces the global maximum of conf (box_utils.py:268) to per-block partials
+//     k_match_loss    one thread per (image, prior): per-warp culled IoU arg max (first-index ties, torch.max(0)), label +
+//                     encode of the positives, then smooth L1 (:96-101), the mining input loss_c (:104-110) and the image's
+//                     mining histogram -- the [G,N] overlap matrix is never materialised, conf_t / loc_t are not read back
+//     k_mine_apply2   neg = rank < num_neg of the descending sort (:112-116) == the num_neg largest 64-bit composites
+//                     (loss key << 32 | ~prior): unique, so ties resolve to the lower prior index.  Cutoff bin from the
+//                     histogram, mask + cross entropy over pos U neg (:119-128), the candidates of the cutoff bin settled by the
+//                     image's last block, the division by N (:130-135) by the grid's last block
+//   bipartite matcher: k_match<true> (per-GT best prior: warp REDUX -> shared -> one 64-bit atomicMax per block and GT) +
+//                     k_match_bipartite_finalize (box_utils.py:150-154) + k_loss_prior + k_mine_apply2
+//   standalone entries: k_match_default (fdt_match_encode), k_mine_hist / k_mine_select / k_mine_apply (fdt_hard_negative_mine)
+//   k_multibox_backward.
 #include "fdt_common.cuh"
 
 namespace {
