@@ -253,3 +253,103 @@ def test_multibox_no_positive_anywhere(layers, golden):
     targets = [np.array([[0.9, 0.9, 0.9001, 0.9001, 0]], np.float32)] * 2
     crit, l, c, ll, lc = run_loss(layers, loc, conf, pri, targets, 0)
     assert float(ll) == 0.0 and float(lc) == 0.0
+
+
+# ------------------------------------------------------------------ fused forward: shapes and degenerate rows vs the oracle
+def fused_forward(loc, conf, pri, targets, bip=0, thr=0.35, ratio=3):
+    """fdt_multibox_loss_forward through the C ABI -> (losses[2], conf_t, loc_t, sel, loss_c_all) as numpy."""
+    from fdt_b200 import _lib
+    from fdt_b200.layers.modules.multibox_loss import pack_targets
+    dev = torch.device("cuda", torch.cuda.current_device())
+    l, c, p = cu(loc), cu(conf), cu(pri)
+    gt, off, total = pack_targets([cu(t) for t in targets], dev)
+    B, N, Cn = conf.shape
+    losses = torch.empty(2, device=dev); norm = torch.empty(1, device=dev)
+    loc_t = torch.empty((B, N, 4), device=dev); conf_t = torch.empty((B, N), dtype=torch.int64, device=dev)
+    sel = torch.empty((B, N), dtype=torch.uint8, device=dev); lca = torch.empty((B, N), device=dev)
+    L = _lib.lib()
+    ws = _lib.workspace(L.fdt_multibox_workspace_bytes(B, N, Cn, total), dev, "t-fused")
+    for _ in range(2):                     # twice on the same workspace: the per-call state is re-zeroed by the call itself
+        _lib.check(L.fdt_multibox_loss_forward(l.data_ptr(), c.data_ptr(), p.data_ptr(), gt.data_ptr(), off.data_ptr(), total, B, N, Cn,
+                                               thr, ratio, bip, VAR[0], VAR[1], losses.data_ptr(), norm.data_ptr(), loc_t.data_ptr(),
+                                               conf_t.data_ptr(), sel.data_ptr(), lca.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+    return npy(losses), npy(conf_t), npy(loc_t), npy(sel).astype(bool), npy(lca)
+
+
+def check_fused(loc, conf, pri, targets, bip=0, thr=0.35, ratio=3, rtol=1e-5):
+    losses, conf_t, loc_t, sel, lca = fused_forward(loc, conf, pri, targets, bip, thr, ratio)
+    r = orc.multibox_loss(loc, conf, pri, targets, thr, ratio, bool(bip), VAR)
+    assert np.array_equal(conf_t, r["conf_t"])
+    pos = conf_t > 0
+    assert np.array_equal(lca.view(np.uint32), r["loss_c_all"].view(np.uint32))      # the mining input bit for bit
+    assert np.array_equal(sel, r["neg"] | pos)                                       # mined mask bit-exact
+    np.testing.assert_allclose(loc_t[pos], r["loc_t"][pos], rtol=1e-6, atol=1e-7)
+    assert not loc_t[~pos].any()
+    np.testing.assert_allclose(losses, [r["loss_l"], r["loss_c"]], rtol=rtol, atol=1e-7)
+    return sel, pos
+
+
+@pytest.mark.parametrize("bip", [0, 1])
+@pytest.mark.parametrize("kind", ["all_equal", "confident", "quantised"])
+def test_fused_forward_degenerate_losses(kind, bip):
+    """Rows whose mining cutoff cannot be settled by the histogram alone: every loss equal (34 k candidates in the cutoff bin -> the
+    radix path, selection by prior index), near-zero losses (cutoff in bin 0 together with the zeros of the positives), and losses
+    on a coarse grid (a few thousand ties around the cutoff)."""
+    pri = synth.priors_numpy(640, 640)
+    loc, conf, targets = synth.multibox_inputs(3, pri, 515, 20, 60)
+    rng = np.random.Generator(np.random.PCG64(3))
+    if kind == "all_equal":
+        conf = np.zeros_like(conf)
+    elif kind == "confident":
+        conf = np.stack([np.full(conf.shape[:2], 9.0, np.float32), np.full(conf.shape[:2], -9.0, np.float32)], -1)
+        conf += rng.uniform(-1e-3, 1e-3, conf.shape).astype(np.float32)
+    else:
+        conf = (np.round(conf * 2) / 2).astype(np.float32)
+    sel, pos = check_fused(loc, conf, pri, targets, bip)
+    assert (sel & ~pos).sum() > 0
+
+
+@pytest.mark.parametrize("thr", [0.0, 0.01, 0.35, 0.5, 0.9])
+def test_fused_forward_many_gt_tiles_and_thresholds(thr):
+    """G = 600 boxes per image (three staged tiles) at thresholds from 'area bound off' to 'almost nothing matches': the area bound
+    of the fused matcher never changes a label or an encoded row."""
+    pri = synth.priors_numpy(320, 320)
+    loc, conf, targets = synth.multibox_inputs(2, pri, 77, 600, 600)
+    rng = np.random.Generator(np.random.PCG64(5))
+    for t in targets:                                                            # all box sizes from 1 % to 60 % of the image
+        c = rng.uniform(0.1, 0.9, (t.shape[0], 2)); s = rng.uniform(0.01, 0.6, (t.shape[0], 2))
+        t[:, :4] = np.concatenate([c - s / 2, c + s / 2], 1).astype(np.float32)
+    check_fused(loc, conf, pri, targets, 0, thr)
+
+
+@pytest.mark.parametrize("shape", [(1, 100), (2, 257), (1, 2049), (5, 4097)])
+def test_fused_forward_odd_sizes(shape):
+    B, N = shape
+    pri = synth.priors_numpy(320, 320)[-N:].copy()
+    loc, conf, targets = synth.multibox_inputs(B, pri, 1000 + N, 1, 9)
+    check_fused(loc, conf, pri, targets, 0)
+
+
+def test_fused_forward_four_classes():
+    pri = synth.priors_numpy(160, 160)
+    loc, conf, targets = synth.multibox_inputs(3, pri, 31, 3, 30)
+    rng = np.random.Generator(np.random.PCG64(9))
+    conf = rng.standard_normal((3, pri.shape[0], 4)).astype(np.float32)
+    for t in targets:
+        t[:, 4] = rng.integers(0, 3, t.shape[0])
+    check_fused(loc, conf, pri, targets, 0)
+
+
+def test_fused_forward_degenerate_boxes():
+    """zero-area, inverted and NaN GT boxes and a zero-size prior: labels and mask as the oracle (the area bound steps aside)."""
+    pri = synth.priors_numpy(160, 160).copy()
+    loc, conf, targets = synth.multibox_inputs(3, pri, 8, 6, 12)
+    targets[0][1, :4] = [0.3, 0.3, 0.3, 0.5]
+    targets[0][2, :4] = [0.6, 0.6, 0.4, 0.4]
+    targets[1][0, :4] = [0.5, 0.5, 0.2, 0.7]
+    targets[2][3, :4] = [np.nan, 0.2, 0.4, 0.4]
+    pri[1234, 2:] = 0.0
+    losses, conf_t, loc_t, sel, lca = fused_forward(loc, conf, pri, targets, 0)
+    r = orc.multibox_loss(loc, conf, pri, targets, 0.35, 3, False, VAR)
+    assert np.array_equal(conf_t, r["conf_t"])
+    assert np.array_equal(sel, r["neg"] | (conf_t > 0))
