@@ -839,6 +839,7 @@ k_mine_apply2(const float *__restrict__ loss_c, const int *__restrict__ hist, co
     __shared__ int s_warp[M_WARPS];
     __shared__ int s_sel[2];
     __shared__ int s_n, s_flag;
+    __shared__ long long s_ntot;
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // the block's rows first: their latency overlaps the histogram scan
     float lcv[APPLY_TILES];
@@ -853,6 +854,13 @@ k_mine_apply2(const float *__restrict__ loss_c, const int *__restrict__ hist, co
     if (num_neg > N - 1) num_neg = N - 1;
     const bool mining = num_neg > 0;                                            // (block-uniform)
     if (tid == 0) s_n = 0;
+    if (warp == M_WARPS - 1) {                                                  // the batch's positives, for whichever block ends up last
+        long long n = 0;
+        for (int i = lane; i < B; i += 32) n += num_pos[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+        if (lane == 0) s_ntot = n;
+    }
     // ---- 1. cutoff bin d0 and the number need0 of its members that are selected
     int d0 = MINE_BINS, need0 = 0;
     if (mining) {
@@ -986,14 +994,9 @@ k_mine_apply2(const float *__restrict__ loss_c, const int *__restrict__ hist, co
         __threadfence();
         s_flag = atomicAdd(&acc->done, 1u) == gridDim.x * gridDim.y - 1u;
     }
-    __syncthreads();
-    if (!s_flag || warp != 0) return;
-    __threadfence();
-    long long n = 0;
-    for (int i = lane; i < B; i += 32) n += num_pos[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-    if (lane == 0) {
+    if (tid == 0 && s_flag) {                          // (thread 0 set the flag itself)
+        __threadfence();
+        const long long n = s_ntot;
         double Nn = (double)n;                         // :130
         if (n == 0) Nn = (double)B;                    // :132-133
         losses[0] = (float)(*(volatile double *)&acc->loss_l / Nn);

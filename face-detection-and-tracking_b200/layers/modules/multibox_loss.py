@@ -12,12 +12,18 @@ def pack_targets(targets, device):
     """list[B] of [G_i,5] tensors -> (gt[total,5] fp32, gt_off[B+1] int64, total) on `device`.
     One concatenation + one small H2D copy of the offsets; images without GT get an empty range."""
     counts = [int(t.shape[0]) if t is not None and t.numel() else 0 for t in targets]
-    off = torch.zeros(len(targets) + 1, dtype=torch.int64)
-    off[1:] = torch.tensor(counts, dtype=torch.int64).cumsum(0)
-    total = int(off[-1])
-    rows = [t.detach().reshape(-1, 5).to(device=device, dtype=torch.float32) for t, c in zip(targets, counts) if c]
-    gt = torch.cat(rows, 0).contiguous() if rows else torch.zeros((1, 5), dtype=torch.float32, device=device)
-    return gt, off.to(device), total
+    off = [0]
+    for c in counts:
+        off.append(off[-1] + c)
+    total = off[-1]
+    rows = [t for t, c in zip(targets, counts) if c]
+    if not rows:
+        gt = torch.zeros((1, 5), dtype=torch.float32, device=device)
+    elif all(t.device == device and t.dtype == torch.float32 and t.dim() == 2 for t in rows):
+        gt = torch.cat(rows, 0).detach()                  # the training loop's case: one launch for the whole batch
+    else:
+        gt = torch.cat([t.detach().reshape(-1, 5).to(device=device, dtype=torch.float32) for t in rows], 0).contiguous()
+    return gt, torch.tensor(off, dtype=torch.int64).to(device, non_blocking=True), total
 
 
 class _MultiBoxLossFn(torch.autograd.Function):
