@@ -290,6 +290,10 @@ int fdt_hard_negative_mine(const float *loss_c, const uint8_t *pos, int B, int64
  * backward pass reuses (sel[B,N] uint8 = pos | neg).  loc_t holds the encoded target at the POSITIVE priors
  * (conf_t > 0) and zeros elsewhere: the reference encodes every prior (box_utils.py:208) but its loss only reads
  * the positives (multibox_loss.py:96-101) and never returns the tensor; fdt_match_encode fills all rows.
+ * The forward is three kernels on `stream` (prepare -> match + loss terms -> mining + selection + final division) with no memset
+ * node; the workspace content does not matter before a call and is re-initialised by every call.  Limits: B <= 65535,
+ * N <= 65535 * 256; conf needs 8-byte alignment when C == 2.  loss_c_all (optional, [B,N]) receives the mining input
+ * log_sum_exp(conf) - conf[label] with zeros at the positives (multibox_loss.py:104-110).
  * backward: grad_loc[B,N,4], grad_conf[B,N,C] for upstream gradients g_l, g_c (host scalars). */
 size_t fdt_multibox_workspace_bytes(int B, int64_t N, int C, int64_t total_gt);
 int fdt_multibox_loss_forward(const float *loc, const float *conf, const float *priors,
