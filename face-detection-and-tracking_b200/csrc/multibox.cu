@@ -11,9 +11,10 @@
 //                     (loss key << 32 | ~prior): unique, so ties resolve to the lower prior index.  Cutoff bin from the
 //                     histogram, mask + cross entropy over pos U neg (:119-128), the candidates of the cutoff bin settled by the
 //                     image's last block, the division by N (:130-135) by the grid's last block
-//   bipartite matcher: k_match<true> (per-GT best prior: warp REDUX -> shared -> one 64-bit atomicMax per block and GT) +
-//                     k_match_bipartite_finalize (box_utils.py:150-154) + k_loss_prior + k_mine_apply2
-//   standalone entries: k_match_default (fdt_match_encode), k_mine_hist / k_mine_select / k_mine_apply (fdt_hard_negative_mine)
+//   forward, bipartite matcher: k_mbl_prepare (+ the boxes of the 32-prior tiles) -> k_best_prior (one warp per GT box: its best
+//                     prior, box_utils.py:136) -> k_match_loss<BIP> (forces those priors, :150-154) -> k_mine_apply2
+//   standalone entries: k_match_default / k_match<true> + k_match_bipartite_finalize (fdt_match_encode: every row encoded, arg max
+//                     and overlap of every prior returned), k_mine_hist / k_mine_select / k_mine_apply (fdt_hard_negative_mine)
 //   k_multibox_backward.
 #include "fdt_common.cuh"
 
@@ -455,13 +456,61 @@ __device__ __forceinline__ T block_sum(T v, T *s_red)
 constexpr int PREP_BLOCKS = FDT_NUM_SMS, PREP_THREADS = 1024;
 __global__ void __launch_bounds__(PREP_THREADS)
 k_mbl_prepare(const float *__restrict__ conf, const int64_t n_conf, unsigned *__restrict__ gmax_part, int4 *__restrict__ zero_base,
-              const int64_t zero_int4s)
+              const int64_t zero_int4s, const float4 *__restrict__ priors, const int64_t N, float4 *__restrict__ tile_bb, float4 *__restrict__ tile_dim,
+              float4 *__restrict__ super_bb, float4 *__restrict__ super_dim)
 {
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
     __shared__ unsigned s_k[PREP_THREADS / 32];
     const int64_t gtid = (int64_t)blockIdx.x * PREP_THREADS + threadIdx.x, gsz = (int64_t)PREP_BLOCKS * PREP_THREADS;
     for (int64_t i = gtid; i < zero_int4s; i += gsz) zero_base[i] = make_int4(0, 0, 0, 0);
+    if (tile_bb) {
+        // bipartite matcher: the bounding box (point form) and the ranges (min, max) of the widths and heights of every 32
+        // consecutive priors (a tile) and of every 1,024 (a super-tile = one iteration of a block), for k_best_prior's two-level
+        // culling.  Ranges of -1 mark a tile with a prior whose width or height is not positive (NaN included): never pruned by size.
+        __shared__ unsigned s_t[8][PREP_THREADS / 32];
+        __shared__ int s_ok[PREP_THREADS / 32];
+        const int64_t n1024 = (N + 1023) & ~(int64_t)1023;
+        for (int64_t q = gtid; q < n1024; q += gsz) {                           // (uniform trip count within a block)
+            const bool valid = q < N;
+            const float4 pr = priors[valid ? q : 0];
+            const float hw = pr.z / 2.0f, hh = pr.w / 2.0f;
+            const float4 pf = make_float4(pr.x - hw, pr.y - hh, pr.x + hw, pr.y + hh);
+            const float pw = pf.z - pf.x, ph = pf.w - pf.y;
+            const bool okp = !valid || (pw > 0.0f && ph > 0.0f);
+            unsigned k[8];
+            k[0] = valid ? fdt_float_key(pf.x) : 0xffffffffu; k[1] = valid ? fdt_float_key(pf.y) : 0xffffffffu;
+            k[2] = valid ? fdt_float_key(pf.z) : 0u; k[3] = valid ? fdt_float_key(pf.w) : 0u;
+            k[4] = valid && okp ? __float_as_uint(pw) : 0xffffffffu; k[5] = valid && okp ? __float_as_uint(pw) : 0u;      // (positive floats order as integers)
+            k[6] = valid && okp ? __float_as_uint(ph) : 0xffffffffu; k[7] = valid && okp ? __float_as_uint(ph) : 0u;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) k[c] = (c < 2 || c == 4 || c == 6) ? __reduce_min_sync(0xffffffffu, k[c]) : __reduce_max_sync(0xffffffffu, k[c]);
+            const bool all_ok = __all_sync(0xffffffffu, okp);
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            const float4 none = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+            if (lane == 0) {
+                if ((q >> 5) < ((N + 31) >> 5)) {
+                    tile_bb[q >> 5] = make_float4(fdt_key_float(k[0]), fdt_key_float(k[1]), fdt_key_float(k[2]), fdt_key_float(k[3]));
+                    tile_dim[q >> 5] = all_ok ? make_float4(__uint_as_float(k[4]), __uint_as_float(k[5]), __uint_as_float(k[6]), __uint_as_float(k[7])) : none;
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) s_t[c][warp] = k[c];
+                s_ok[warp] = all_ok;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                unsigned r[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) r[c] = (c < 2 || c == 4 || c == 6) ? __reduce_min_sync(0xffffffffu, s_t[c][lane]) : __reduce_max_sync(0xffffffffu, s_t[c][lane]);
+                const bool ok = __all_sync(0xffffffffu, s_ok[lane] != 0);
+                if (lane == 0) {
+                    super_bb[q >> 10] = make_float4(fdt_key_float(r[0]), fdt_key_float(r[1]), fdt_key_float(r[2]), fdt_key_float(r[3]));
+                    super_dim[q >> 10] = ok ? make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7])) : none;
+                }
+            }
+            __syncthreads();
+        }
+    }
     unsigned k = 0u;
     if (((uintptr_t)conf & 15) == 0) {
         const float4 *c4 = reinterpret_cast<const float4 *>(conf);
@@ -490,7 +539,7 @@ __device__ __forceinline__ float gmax_from_partials(const unsigned *__restrict__
     return fdt_key_float(__reduce_max_sync(0xffffffffu, k));
 }
 
-// per-prior loss terms shared by k_loss_prior and the fused k_match_loss (multibox_loss.py:96-110): smooth L1 of a positive
+// per-prior loss terms of the fused k_match_loss (multibox_loss.py:96-110): smooth L1 of a positive
 // (beta = 1, sum) in `sl`, the mining input loss_c (0 for positives) returned; cv = the row when C == 2 (loaded by the caller)
 __device__ __forceinline__ float prior_loss_terms(const float4 a, const float4 g, const bool is_pos, const float2 cv,
                                                   const float *__restrict__ row, const int C, const int64_t label, const float xmax,
@@ -530,52 +579,171 @@ __device__ __forceinline__ void flush_positives(double sl, const int is_pos, dou
     }
 }
 
-// multibox_loss.py:90-110 behind the bipartite matcher (the default matcher computes the same terms inside k_match_loss)
+// Bipartite matcher, per-GT half (box_utils.py:136, overlaps.max(1)): the prior with the largest IoU for every GT box, first prior
+// among ties.  One block per GT box of the whole batch (the priors are the same for every image).  Two-level culling over the
+// boxes k_mbl_prepare made of every 1,024 and every 32 consecutive priors: a tile whose box does not touch the GT box holds exact
+// zeros only, which cannot beat an evaluated pair (tile 0 is always evaluated, so an all-zero row ends at prior 0 as torch.max
+// does).  A best-first order keeps the evaluated tiles to a handful: with the width / height ranges of a tile's priors, IoU <= I /
+// (smallest prior area + GT area - I), I = min(w) * min(h); the tiles with the largest bounds (the pyramid level that fits the box)
+// are evaluated first and the others only while their bound still reaches the best overlap found -- normally none.  A skipped prior is strictly below the maximum, so the arg max and
+// its first-index tie rule are exact.
 __global__ void __launch_bounds__(M_THREADS)
-k_loss_prior(const float4 *__restrict__ loc, const float *__restrict__ conf, const float4 *__restrict__ loc_t,
-             const int64_t *__restrict__ conf_t, int64_t N, int C, LossAcc *__restrict__ acc, const unsigned *__restrict__ gmax_part,
-             float *__restrict__ loss_c_all, int32_t *__restrict__ num_pos, int *__restrict__ hist)
+k_best_prior(const float4 *__restrict__ priors, const int64_t N, const float *__restrict__ gt, const int64_t total_gt,
+             const float4 *__restrict__ tile_bb, const float4 *__restrict__ tile_dim, const float4 *__restrict__ super_bb,
+             const float4 *__restrict__ super_dim, unsigned *__restrict__ bestprior)
 {
-    fdt_pdl_enter();
-    __shared__ double s_tot;
-    __shared__ int s_cnt;
-    const int b = blockIdx.y;
-    const int64_t p = (int64_t)blockIdx.x * M_THREADS + threadIdx.x;
-    if (threadIdx.x == 0) { s_tot = 0.0; s_cnt = 0; }
-    __syncthreads();
-    const float xmax = gmax_from_partials(gmax_part);
-    double sl = 0.0;
-    int is_pos = 0;
-    if (p < N) {
-        const int64_t t = (int64_t)b * N + p;
-        const int64_t label = conf_t[t];
-        is_pos = label > 0;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
-        if (is_pos) { a = loc[t]; g = loc_t[t]; }
-        float2 cv = make_float2(0.f, 0.f);
-        if (C == 2) cv = __ldg(reinterpret_cast<const float2 *>(conf + t * 2));
-        const float lc = prior_loss_terms(a, g, is_pos, cv, conf + t * C, C, label, xmax, sl);
-        loss_c_all[t] = lc;
-        atomicAdd(&hist[(size_t)b * MINE_BINS + mine_bin2(lc)], 1);
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();                   // the tile boxes
+    constexpr int TL_CAP = 1024;                       // hit tiles listed per round (more: further rounds)
+    __shared__ unsigned s_key[M_WARPS], s_p[M_WARPS];
+    __shared__ int s_tl[TL_CAP];
+    __shared__ int s_ntl;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ntile = (N + 31) >> 5, nsuper = (N + 1023) >> 10;
+    // one block per GT box at a time (a single wave of blocks walks the batch's boxes); its warps share the super-tiles round robin
+    for (int64_t g = blockIdx.x; g < total_gt; g += gridDim.x) {
+        const float *row = gt + 5 * g;
+        const float4 a = make_float4(row[0], row[1], row[2], row[3]);
+        const float area_a = (a.z - a.x) * (a.w - a.y);
+        const float wg = a.z - a.x, hg = a.w - a.y;
+        const bool prune = wg > 0.0f && hg > 0.0f;     // (NaN: no)
+        unsigned bestkey = 0u, bestp = 0xffffffffu;
+        auto eval = [&](const int64_t p, const float4 pr) {
+            const float hw = pr.z / 2.0f, hh = pr.w / 2.0f;                    // point_form, box_utils.py:15-16
+            const float4 pf = make_float4(pr.x - hw, pr.y - hh, pr.x + hw, pr.y + hh);
+            const unsigned key = fdt_float_key(iou_match(a, area_a, pf, (pf.z - pf.x) * (pf.w - pf.y)));
+            if (bestp == 0xffffffffu || key > bestkey || (key == bestkey && (unsigned)p < bestp)) { bestkey = key; bestp = (unsigned)p; }   // first prior wins ties
+        };
+        // touches: the clamped overlap with a box is not empty (NaN keeps)
+        auto touches = [&](const float4 bb) {
+            const float wbb = fminf(a.z, bb.z) - fmaxf(a.x, bb.x), hbb = fminf(a.w, bb.w) - fmaxf(a.y, bb.y);
+            return !(wbb <= 0.0f || hbb <= 0.0f);
+        };
+        // d = (wmin, wmax, hmin, hmax) of the priors: inter <= min(wmax, wg) * min(hmax, hg) =: I and union >= wmin * hmin + area - I
+        auto bound_of = [&](const float4 d) {
+            if (!prune || !(d.x > 0.0f)) return 1.0f;
+            const float I = fminf(d.y, wg) * fminf(d.w, hg);
+            const float u = d.x * d.z + area_a - I;
+            return u > I ? I / u : 1.0f;
+        };
+        // best first: the tiles are visited in four classes of their bound, [0.5, inf), [0.25, 0.5), [0.125, 0.25), the rest; a
+        // tile whose bound is below the best overlap found so far (b1) is skipped, and once b1 reaches the upper end of the next
+        // class nothing that is left can beat it
+        float b1 = 0.0f;
+        bool have = false;
+        for (int pass = 0; pass < 4; ++pass) {
+            const float lo = pass == 0 ? 0.5f : pass == 1 ? 0.25f : pass == 2 ? 0.125f : -1.0f;
+            const float hi = pass == 0 ? 3.0e38f : pass == 1 ? 0.5f : pass == 2 ? 0.25f : 0.125f;
+            if (have && hi * 1.00001f < b1) break;                              // (block-uniform)
+            for (int64_t s0 = 0; s0 < nsuper; s0 += 32 * M_WARPS) {
+                // list the hit tiles of this round of super-tiles (warps own super-tiles round robin) ...
+                if (threadIdx.x == 0) s_ntl = 0;
+                __syncthreads();
+                const int64_t sidx = s0 + warp + M_WARPS * lane;
+                bool shit = false;
+                if (sidx < nsuper) {
+                    const float sb = bound_of(__ldg(super_dim + sidx));
+                    shit = (sidx == 0 && pass == 0) || (touches(__ldg(super_bb + sidx)) && sb >= lo && !(have && sb * 1.00001f < b1));
+                }
+                unsigned sm = __ballot_sync(0xffffffffu, shit);
+                while (sm) {
+                    const int64_t t0 = (s0 + warp + M_WARPS * (__ffs(sm) - 1)) << 5;    // the 32 tiles of this super-tile, one per lane
+                    sm &= sm - 1;
+                    const int64_t t = t0 + lane;
+                    bool hit = false;
+                    if (t < ntile) {
+                        const float bound = bound_of(__ldg(tile_dim + t));
+                        if (t == 0) hit = pass == 0;
+                        else hit = touches(__ldg(tile_bb + t)) && bound >= lo && bound < hi && !(have && bound * 1.00001f < b1);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (m) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&s_ntl, __popc(m));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        const int e = base + __popc(m & ((1u << lane) - 1u));
+                        if (hit && e < TL_CAP) s_tl[e] = (int)t;
+                    }
+                }
+                __syncthreads();
+                // ... and evaluate them, all warps together, two tiles in flight per warp.  (Tiles beyond the list's capacity --
+                // more than 1,024 hit tiles in one round -- are evaluated by their owner below.)
+                const int ntl = min(s_ntl, TL_CAP);
+                for (int e = warp; e < ntl; e += 2 * M_WARPS) {
+                    const bool two = e + M_WARPS < ntl;
+                    const int64_t p1 = ((int64_t)s_tl[e] << 5) + lane, p2 = two ? ((int64_t)s_tl[e + M_WARPS] << 5) + lane : p1;
+                    const float4 pr1 = __ldg(priors + min(p1, N - 1)), pr2 = __ldg(priors + min(p2, N - 1));
+                    // (ascending order within a lane is not kept here: ties are settled by the explicit index comparison)
+                    if (p1 < N) eval(p1, pr1);
+                    if (two && p2 < N) eval(p2, pr2);
+                }
+                if (s_ntl > TL_CAP) {                  // (block-uniform) overflow: every warp re-walks its own super-tiles
+                    unsigned sm2 = __ballot_sync(0xffffffffu, shit);
+                    while (sm2) {
+                        const int64_t t0 = (s0 + warp + M_WARPS * (__ffs(sm2) - 1)) << 5;
+                        sm2 &= sm2 - 1;
+                        const int64_t t = t0 + lane;
+                        bool hit = false;
+                        if (t < ntile) {
+                            const float bound = bound_of(__ldg(tile_dim + t));
+                            if (t == 0) hit = pass == 0;
+                            else hit = touches(__ldg(tile_bb + t)) && bound >= lo && bound < hi && !(have && bound * 1.00001f < b1);
+                        }
+                        unsigned m = __ballot_sync(0xffffffffu, hit);
+                        while (m) {
+                            const int64_t p1 = ((t0 + __ffs(m) - 1) << 5) + lane;
+                            m &= m - 1;
+                            if (p1 < N) eval(p1, __ldg(priors + p1));
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            // the block's best so far: its key bounds the next pass, its prior is the result after the last one
+            const unsigned mx = __reduce_max_sync(0xffffffffu, bestp == 0xffffffffu ? 0u : bestkey);
+            const unsigned pm = __reduce_min_sync(0xffffffffu, (bestp != 0xffffffffu && bestkey == mx) ? bestp : 0xffffffffu);
+            __syncthreads();                           // (the previous pass's values have been read)
+            if (lane == 0) { s_key[warp] = mx; s_p[warp] = pm; }
+            __syncthreads();
+            unsigned bk = 0u;
+            have = false;
+#pragma unroll
+            for (int w = 0; w < M_WARPS; ++w) if (s_p[w] != 0xffffffffu) { bk = have ? max(bk, s_key[w]) : s_key[w]; have = true; }
+            b1 = have ? fdt_key_float(bk) : 0.0f;
+        }
+        if (threadIdx.x == 0) {
+            unsigned bk = 0u, bp = 0xffffffffu;
+            for (int w = 0; w < M_WARPS; ++w) {                                 // a lower prior index wins ties
+                const unsigned k = s_key[w], q = s_p[w];
+                if (q != 0xffffffffu && (bp == 0xffffffffu || k > bk || (k == bk && q < bp))) { bk = k; bp = q; }
+            }
+            bestprior[g] = bp;
+        }
+        __syncthreads();                               // s_key / s_p are reused by the next box
     }
-    flush_positives(sl, is_pos, &s_tot, &s_cnt, acc, &num_pos[b]);
 }
 
-// The forward behind the default matcher in ONE kernel per prior: match (k_match_default's core), label + encode of the positives,
-// and -- once k_mbl_prepare's maximum is there -- the loss terms and the mining histogram of k_loss_prior on the values still in
-// registers.  The matcher is bound by instruction issue and the loss terms by fp64 latency; in one kernel the warps of both phases
-// share every SM, and conf_t / loc_t are not read back.
+// The forward in ONE kernel per prior: match (k_match_default's core), label + encode of the positives, and -- once
+// k_mbl_prepare's maximum is there -- the loss terms and the mining histogram of k_loss_prior on the values still in registers.
+// The matcher is bound by instruction issue and the loss terms by fp64 latency; in one kernel the warps of both phases share every
+// SM, and conf_t / loc_t are not read back.  BIP: the bipartite matcher (box_utils.py:103-162) -- the same per-prior arg max (the
+// area bound stays valid: a forced match overrides whatever it found, every other prior is labelled by `best >= thr` alone), then
+// the priors that k_best_prior found for the image's GT boxes are forced to their box with overlap 2 (:150-154, the last GT wins).
+template <bool BIP>
 __global__ void __launch_bounds__(M_THREADS, 5)
 k_match_loss(const float4 *__restrict__ priors, const float *__restrict__ gt, const int64_t *__restrict__ gt_off,
              int64_t N, float thr, float v0, float v1, float4 *__restrict__ loc_t, int64_t *__restrict__ conf_t,
              const float4 *__restrict__ loc, const float *__restrict__ conf, int C, LossAcc *__restrict__ acc,
-             const unsigned *__restrict__ gmax_part, float *__restrict__ loss_c_all, int32_t *__restrict__ num_pos, int *__restrict__ hist)
+             const unsigned *__restrict__ gmax_part, float *__restrict__ loss_c_all, int32_t *__restrict__ num_pos, int *__restrict__ hist,
+             const unsigned *__restrict__ bestprior)
 {
+    constexpr int FORCED_CAP = 64;
     __shared__ GtEntry s_gt[GT_TILE];
     __shared__ unsigned char s_wl[M_WARPS][GT_TILE];
     __shared__ double s_tot;
     __shared__ int s_cnt;
     __shared__ float s_xmax;
+    __shared__ int s_nf, s_fj[BIP ? FORCED_CAP : 1], s_fp[BIP ? FORCED_CAP : 1];
     const MatchBlock mb = match_block();
     const int b = mb.b, tid = threadIdx.x, warp = tid >> 5;
     const int64_t p = (int64_t)mb.tile * M_THREADS + tid;
@@ -583,20 +751,22 @@ k_match_loss(const float4 *__restrict__ priors, const float *__restrict__ gt, co
     const int64_t g0 = gt_off[b];
     const int G = (int)(gt_off[b + 1] - g0);
     const int64_t t = (int64_t)b * N + p;
-    if (tid == 0) { s_tot = 0.0; s_cnt = 0; }
+    if (tid == 0) { s_tot = 0.0; s_cnt = 0; s_nf = 0; }
     const float4 pr = priors[valid ? p : 0];
     float2 cv = make_float2(0.f, 0.f);                 // the row of the loss phase, in flight during the match
     if (C == 2 && valid) cv = __ldg(reinterpret_cast<const float2 *>(conf + t * 2));
     int64_t label = 0;
     float4 enc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float best = 0.0f;
+    int bi = 0;
     if (G > 0) {                                       // G <= 0: the reference raises (Q3); defined: all background
         const float hw = pr.z / 2.0f, hh = pr.w / 2.0f;    // point_form, box_utils.py:15-16
         const float4 pf = make_float4(pr.x - hw, pr.y - hh, pr.x + hw, pr.y + hh);
         const float area_b = (pf.z - pf.x) * (pf.w - pf.y);
-        float best;
-        int bi;
         match_default_core<true>(gt, g0, G, pf, area_b, valid, thr, s_gt, s_wl[warp], best, bi);
-        if (!(best < thr)) {                           // box_utils.py:205-206 (a NaN overlap stays positive, as there)
+    }
+    auto finalize = [&]() {
+        if (G > 0 && !(best < thr)) {                  // box_utils.py:205-206 (a NaN overlap stays positive, as there)
             float4 m;
             float lab;
             if (G <= GT_TILE) { m = s_gt[bi].box; lab = s_gt[bi].label; }       // the only tile is still staged
@@ -605,18 +775,50 @@ k_match_loss(const float4 *__restrict__ priors, const float *__restrict__ gt, co
             // :208 encodes every prior; the loss only reads the positives (multibox_loss.py:96-101): zeros elsewhere
             if (label > 0) enc = fdt_encode1(m, pr, v0, v1);
         }
-    }
-    const int is_pos = valid && label > 0;
+    };
+    int is_pos = 0;
     float4 a = enc;
-    if (is_pos) a = loc[t];
-    if (valid) { conf_t[t] = label; loc_t[t] = enc; }
+    if (!BIP) {
+        finalize();
+        is_pos = valid && label > 0;
+        if (is_pos) a = loc[t];
+        if (valid) { conf_t[t] = label; loc_t[t] = enc; }
+    }
     cudaTriggerProgrammaticLaunchCompletion();
-    cudaGridDependencySynchronize();                   // k_mbl_prepare: zeroed state + the partial maxima
+    cudaGridDependencySynchronize();                   // k_mbl_prepare: zeroed state + the partial maxima (BIP: k_best_prior too)
     if (warp == 0) {
         const float x = gmax_from_partials(gmax_part);
         if (tid == 0) s_xmax = x;
     }
+    if (BIP && G > 0) {
+        // the GT boxes whose best prior lies in this block (usually none, a handful at most)
+        const unsigned p0 = (unsigned)((int64_t)mb.tile * M_THREADS);
+        for (int j = tid; j < G; j += M_THREADS) {
+            const unsigned d = __ldcg(bestprior + g0 + j) - p0;
+            if (d < (unsigned)M_THREADS) {
+                const int e = atomicAdd(&s_nf, 1);
+                if (e < FORCED_CAP) { s_fj[e] = j; s_fp[e] = (int)d; }
+            }
+        }
+    }
     __syncthreads();
+    if (BIP) {
+        if (G > 0) {
+            const int nf = s_nf;
+            int fj = -1;
+            if (nf <= FORCED_CAP) {
+                for (int e = 0; e < nf; ++e) if (s_fp[e] == tid) fj = max(fj, s_fj[e]);
+            } else {
+                for (int j = 0; j < G; ++j) if (__ldcg(bestprior + g0 + j) == (unsigned)p) fj = j;
+            }
+            if (fj >= 0) { best = 2.0f; bi = fj; }     // :150-154
+        }
+        finalize();
+        is_pos = valid && label > 0;
+        a = enc;
+        if (is_pos) a = loc[t];
+        if (valid) { conf_t[t] = label; loc_t[t] = enc; }
+    }
     const float xmax = s_xmax;
     double sl = 0.0;
     if (valid) {
@@ -1155,7 +1357,7 @@ FDT_API int fdt_hard_negative_mine(const float *loss_c, const uint8_t *pos, int 
 // mining histogram] [partial maxima] [candidate lists B x N] [loss_c] [matcher scratch]
 struct LossWs {
     LossAcc *acc; int32_t *num_pos; int *img_ticket; int *cand_cnt; int *hist; size_t zero_bytes;
-    unsigned *gmax_part; unsigned long long *cand; float *loss_c_all; void *match; size_t bytes;
+    unsigned *gmax_part; unsigned long long *cand; float *loss_c_all; float4 *tile_bb, *super_bb, *tile_dim, *super_dim; unsigned *bestprior; size_t bytes;
 };
 static LossWs plan_loss_ws(void *ws, int B, int64_t N, int64_t total_gt, int bipartite)
 {
@@ -1171,7 +1373,11 @@ static LossWs plan_loss_ws(void *ws, int B, int64_t N, int64_t total_gt, int bip
     w.gmax_part = (unsigned *)(p + o); o += fdt_align256((size_t)PREP_BLOCKS * 4);
     w.cand = (unsigned long long *)(p + o); o += fdt_align256((size_t)B * N * 8);
     w.loss_c_all = (float *)(p + o); o += fdt_align256((size_t)B * N * 4);
-    w.match = (void *)(p + o); o += bipartite ? plan_match_ws(nullptr, B, N, total_gt).bytes : 0;
+    w.tile_bb = (float4 *)(p + o); o += bipartite ? fdt_align256((size_t)((N + 31) / 32) * 16) : 0;      // bipartite: 32-prior tile boxes
+    w.tile_dim = (float4 *)(p + o); o += bipartite ? fdt_align256((size_t)((N + 31) / 32) * 16) : 0;
+    w.super_bb = (float4 *)(p + o); o += bipartite ? fdt_align256((size_t)((N + 1023) / 1024) * 16) : 0;
+    w.super_dim = (float4 *)(p + o); o += bipartite ? fdt_align256((size_t)((N + 1023) / 1024) * 16) : 0;
+    w.bestprior = (unsigned *)(p + o); o += bipartite ? fdt_align256((size_t)(total_gt > 0 ? total_gt : 1) * 4) : 0;
     w.bytes = o;
     return w;
 }
@@ -1200,20 +1406,28 @@ FDT_API int fdt_multibox_loss_forward(const float *loc, const float *conf, const
     FDT_REQUIRE(ws_bytes >= w.bytes, FDT_E_WORKSPACE, "fdt_multibox_loss_forward: workspace %zu < %zu bytes", ws_bytes, w.bytes);
     float *lca = loss_c_all ? loss_c_all : w.loss_c_all;
 
-    // three kernels behind the default matcher, chained by programmatic dependent launch: prepare -> match + loss terms -> mining
+    // three kernels (four with the bipartite matcher) chained by programmatic dependent launch:
+    // prepare -> [best prior per GT box ->] match + loss terms -> mining
     FDT_CUDA(launch_pdl(k_mbl_prepare, dim3(PREP_BLOCKS), dim3(PREP_THREADS), st, conf, (int64_t)B * N * C, w.gmax_part, (int4 *)ws,
-                        (int64_t)(w.zero_bytes / 16)));
+                        (int64_t)(w.zero_bytes / 16), (const float4 *)priors, N, bipartite ? w.tile_bb : (float4 *)nullptr, w.tile_dim,
+                        w.super_bb, w.super_dim));
     FDT_LAUNCH_CHECK();
-    dim3 grid((unsigned)((N + M_THREADS - 1) / M_THREADS), (unsigned)B);
     if (!bipartite) {
-        FDT_CUDA(launch_pdl(k_match_loss, match_grid(B, N), dim3(M_THREADS), st, (const float4 *)priors, gt, gt_off, N, threshold, var0, var1, (float4 *)loc_t,
-                            conf_t, (const float4 *)loc, conf, C, w.acc, (const unsigned *)w.gmax_part, lca, w.num_pos, w.hist));
+        FDT_CUDA(launch_pdl(k_match_loss<false>, match_grid(B, N), dim3(M_THREADS), st, (const float4 *)priors, gt, gt_off, N, threshold, var0, var1,
+                            (float4 *)loc_t, conf_t, (const float4 *)loc, conf, C, w.acc, (const unsigned *)w.gmax_part, lca, w.num_pos, w.hist,
+                            (const unsigned *)nullptr));
         FDT_LAUNCH_CHECK();
     } else {
-        rc = launch_match(priors, gt, gt_off, B, N, total_gt, threshold, var0, var1, 1, loc_t, conf_t, nullptr, nullptr, w.match, st, false);
-        if (rc != FDT_OK) return rc;
-        FDT_CUDA(launch_pdl(k_loss_prior, grid, dim3(M_THREADS), st, (const float4 *)loc, conf, (const float4 *)loc_t, (const int64_t *)conf_t, N, C,
-                            w.acc, (const unsigned *)w.gmax_part, lca, w.num_pos, w.hist));
+        if (total_gt > 0) {
+            const unsigned nb = (unsigned)(total_gt < FDT_NUM_SMS * 8 ? total_gt : FDT_NUM_SMS * 8);          // one wave
+            FDT_CUDA(launch_pdl(k_best_prior, dim3(nb), dim3(M_THREADS), st, (const float4 *)priors, N, gt,
+                                total_gt, (const float4 *)w.tile_bb, (const float4 *)w.tile_dim, (const float4 *)w.super_bb,
+                                (const float4 *)w.super_dim, w.bestprior));
+            FDT_LAUNCH_CHECK();
+        }
+        FDT_CUDA(launch_pdl(k_match_loss<true>, match_grid(B, N), dim3(M_THREADS), st, (const float4 *)priors, gt, gt_off, N, threshold, var0, var1,
+                            (float4 *)loc_t, conf_t, (const float4 *)loc, conf, C, w.acc, (const unsigned *)w.gmax_part, lca, w.num_pos, w.hist,
+                            (const unsigned *)w.bestprior));
         FDT_LAUNCH_CHECK();
     }
     dim3 agrid((unsigned)((N + M_THREADS * APPLY_TILES - 1) / (M_THREADS * APPLY_TILES)), (unsigned)B);
