@@ -309,8 +309,9 @@ def test_fused_forward_degenerate_losses(kind, bip):
     assert (sel & ~pos).sum() > 0
 
 
+@pytest.mark.parametrize("bip", [0, 1])
 @pytest.mark.parametrize("thr", [0.0, 0.01, 0.35, 0.5, 0.9])
-def test_fused_forward_many_gt_tiles_and_thresholds(thr):
+def test_fused_forward_many_gt_tiles_and_thresholds(thr, bip):
     """G = 600 boxes per image (three staged tiles) at thresholds from 'area bound off' to 'almost nothing matches': the area bound
     of the fused matcher never changes a label or an encoded row."""
     pri = synth.priors_numpy(320, 320)
@@ -319,15 +320,16 @@ def test_fused_forward_many_gt_tiles_and_thresholds(thr):
     for t in targets:                                                            # all box sizes from 1 % to 60 % of the image
         c = rng.uniform(0.1, 0.9, (t.shape[0], 2)); s = rng.uniform(0.01, 0.6, (t.shape[0], 2))
         t[:, :4] = np.concatenate([c - s / 2, c + s / 2], 1).astype(np.float32)
-    check_fused(loc, conf, pri, targets, 0, thr)
+    check_fused(loc, conf, pri, targets, bip, thr)
 
 
+@pytest.mark.parametrize("bip", [0, 1])
 @pytest.mark.parametrize("shape", [(1, 100), (2, 257), (1, 2049), (5, 4097)])
-def test_fused_forward_odd_sizes(shape):
+def test_fused_forward_odd_sizes(shape, bip):
     B, N = shape
     pri = synth.priors_numpy(320, 320)[-N:].copy()
     loc, conf, targets = synth.multibox_inputs(B, pri, 1000 + N, 1, 9)
-    check_fused(loc, conf, pri, targets, 0)
+    check_fused(loc, conf, pri, targets, bip)
 
 
 def test_fused_forward_four_classes():
@@ -353,3 +355,19 @@ def test_fused_forward_degenerate_boxes():
     r = orc.multibox_loss(loc, conf, pri, targets, 0.35, 3, False, VAR)
     assert np.array_equal(conf_t, r["conf_t"])
     assert np.array_equal(sel, r["neg"] | (conf_t > 0))
+
+
+def test_fused_forward_bipartite_shared_best_priors():
+    """box_utils.py:150-154: many GT boxes with the SAME best prior (100 copies of one box: more forced matches in one block than
+    its list holds), boxes no prior overlaps (best prior = prior 0) and tiny / elongated boxes whose best overlap is far below the
+    threshold: the last GT wins a shared prior, every box still claims one."""
+    pri = synth.priors_numpy(640, 640)
+    loc, conf, targets = synth.multibox_inputs(3, pri, 99, 5, 30)
+    rng = np.random.Generator(np.random.PCG64(11))
+    one = np.array([[0.31, 0.42, 0.37, 0.55, 0]], np.float32)
+    targets[0] = np.concatenate([targets[0], np.repeat(one, 100, 0), targets[0][:3]], 0)
+    targets[1] = np.concatenate([targets[1], np.array([[1.5, 1.5, 1.6, 1.6, 0], [0.2, 0.2, 0.2005, 0.2005, 0], [0.1, 0.5, 0.9, 0.503, 0],
+                                                        [0.5, 0.05, 0.502, 0.95, 0]], np.float32)], 0)
+    sel, pos = check_fused(loc, conf, pri, targets, 1)
+    r = orc.multibox_loss(loc, conf, pri, targets, 0.35, 3, True, VAR)
+    assert pos.sum() > (orc.multibox_loss(loc, conf, pri, targets, 0.35, 3, False, VAR)["conf_t"] > 0).sum()    # forced matches exist
