@@ -1,12 +1,16 @@
 #!/bin/bash
-# 2-GPU box: multigpu_check (Detect gather variants + sharded MultiBoxLoss), then bench.py --gpus 2 as the driver launches it
+# 2-GPU box: multigpu_check (Detect gather variants + sharded MultiBoxLoss), bench.py --gpus 2 as the driver launches it, and the per-variant breakdown
 mkdir -p gpurun_out
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/multigpu_check.py > gpurun_out/r3s_check_2.log 2>&1
 echo "multigpu_check(2) rc $?"; grep -E "CHECK FAILED|MULTIGPU_CHECK|sharded " gpurun_out/r3s_check_2.log | head -20
-timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r3s_bench_2.log 2> gpurun_out/r3s_bench_2.err
-echo "bench 2 rc $?"
-python - gpurun_out/r3s_bench_2.log <<'PY'
+for K in 20 100; do
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $((29630 + K / 10)) bench.py --gpus 2 --steps $K --warmup 5 --no-secondary --no-cpu-baseline > gpurun_out/r3s_bench_2_k$K.log 2> gpurun_out/r3s_bench_2_k$K.err
+echo "bench 2 K=$K rc $?"
+python - gpurun_out/r3s_bench_2_k$K.log <<'PY'
 import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print("  n %d value %.0f ms/step %.4f lat %.4f gather_check %s e2e %.0f" % (d["n_gpus"], d["value"], d["ms_per_step"], d["latency"]["ms_per_step"], d.get("gather_check"), d["e2e"]["value"]))
 PY
+done
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29622 tools/peer_breakdown.py 100 > gpurun_out/r3s_peer_breakdown_2.txt 2>&1
+grep -v Warning gpurun_out/r3s_peer_breakdown_2.txt | tail -6
