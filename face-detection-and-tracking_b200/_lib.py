@@ -159,7 +159,11 @@ def workspace(nbytes: int, device: torch.device, tag: str = "") -> torch.Tensor:
             raise RuntimeError(f"fdt_b200: workspace '{tag}' would have to grow ({ws.numel()} -> {nbytes} bytes) during CUDA-graph "
                                "capture; run the largest shape once before capturing")
         ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
+        _workspaces.pop(key, None)
+        _workspaces[key] = ws                          # (re-inserted: the dict keeps the most recently allocated entries last)
+        if len(_workspaces) > 64 and not torch.cuda.is_current_stream_capturing():
+            for k in list(_workspaces)[:-32]:          # streams come and go: drop the oldest entries (freed in stream order)
+                del _workspaces[k]
     return ws
 
 
