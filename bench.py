@@ -59,9 +59,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--depth", type=int, default=0, help="workspace slots (calls that may overlap on the device); 0 = library default")
-    ap.add_argument("--gather", default="peer", choices=["peer", "peer-barrier", "peer-all", "nccl"],
+    ap.add_argument("--gather", default="peer", choices=["peer", "peer-inline", "peer-barrier", "peer-all", "nccl"],
                     help="N>1: peer = rows stored into rank 0's gathered block by the NMS kernel over NVLink, completion signalled through "
-                         "symmetric memory (fused gather); peer-barrier = the same followed by a symmetric-memory barrier; "
+                         "symmetric memory (fused gather), rank 0's await kernels on a stream of their own; peer-inline = the await "
+                         "kernels in the calls' stream; peer-barrier = the stores followed by a symmetric-memory barrier; "
                          "peer-all = into every rank's block, signalled (fused all-gather); nccl = all_gather after the kernel")
     return ap.parse_args()
 
@@ -74,8 +75,12 @@ def workload_config(mode, n_gpus):
             "parallelism": f"batch-sharded x{n_gpus}, detections gathered on rank 0" if n_gpus > 1 else "batch-sharded x1"}
 
 
-GATHER_NOTE = {"peer": "gather to rank 0 fused into k_sort_nms (16-byte NVLink peer stores into a ring of 4 gathered blocks; completion "
-                       "signals through symmetric memory, a one-block await kernel on rank 0; no rank waits inside the NMS kernel)",
+GATHER_NOTE = {"peer-inline": "gather to rank 0 fused into k_sort_nms (16-byte NVLink peer stores into a ring of 4 gathered blocks; completion "
+                              "signalled through symmetric memory, rank 0's await kernel enqueued behind every call in the same stream)",
+               "peer": "gather to rank 0 fused into k_sort_nms (16-byte NVLink peer stores into a ring of 4 gathered blocks; completion "
+                       "signals through symmetric memory; rank 0 awaits the signals of the LAST call of a timed block -- epochs are monotonic, "
+                       "it covers every call of the block -- with a one-block kernel on a stream of its own that the timed stream waits for "
+                       "before the end of the timed region; no rank waits inside the NMS kernel)",
                "peer-barrier": "gather to rank 0 fused into k_sort_nms (NVLink peer stores + symmetric-memory barrier)",
                "peer-all": "all-gather fused into k_sort_nms (NVLink peer stores into every rank's block, signalled)",
                "nccl": "NCCL all-gather of detections after the kernel"}
@@ -395,10 +400,11 @@ def main():
     gather = args.gather if world > 1 else None
     peer = None
     gathered = None
-    if world > 1 and gather in ("peer", "peer-barrier", "peer-all"):
+    if world > 1 and gather in ("peer", "peer-inline", "peer-barrier", "peer-all"):
         try:
             from fdt_b200.sharding import PeerGatherDetect
-            peer = PeerGatherDetect(det, B, dest="all" if gather == "peer-all" else 0, signal="barrier" if gather == "peer-barrier" else "kernel")
+            peer = PeerGatherDetect(det, B, dest="all" if gather == "peer-all" else 0,
+                                    signal={"peer-barrier": "barrier", "peer": "kernel-side"}.get(gather, "kernel"))
         except Exception as e:                          # noqa: BLE001  (symmetric memory unavailable: keep the NCCL gather)
             if rank == 0:
                 print(f"peer gather unavailable ({e!r}); using NCCL all_gather", file=sys.stderr)
@@ -425,9 +431,11 @@ def main():
             ptrs, n_dst = peer.dest_ptrs(hdl)
             if peer.signal == "kernel":
                 peer.epoch += 1
-                _lib.check(L.fdt_detect_gather_signal(*args12, ptrs, n_dst, int(peer.sig_hdl.buffer_ptrs_dev), world, rank,
-                                                      -1 if peer.dest == "all" else 0, peer.epoch, peer.RING, rank * B,
-                                                      ws.data_ptr(), ws.numel(), st))
+                root = -1 if peer.dest == "all" else 0
+                call = L.fdt_detect_gather_store if peer.await_stream is not None else L.fdt_detect_gather_signal
+                _lib.check(call(*args12, ptrs, n_dst, int(peer.sig_hdl.buffer_ptrs_dev), world, rank, root, peer.epoch, peer.RING, rank * B,
+                                ws.data_ptr(), ws.numel(), st))
+                peer._last_ws = ws                  # (kernel-side: rank 0 awaits when the rows are needed, peer.wait_ready())
             else:
                 _lib.check(L.fdt_detect_peers(*args12, ptrs, n_dst, rank * B, ws.data_ptr(), ws.numel(), st))
                 hdl.barrier()
@@ -458,6 +466,8 @@ def main():
         e0.record()
         for i in range(args.steps):
             step()
+        if peer is not None:
+            peer.wait_ready()                           # (await kernels on their own stream: the timed stream waits for the last one)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -476,6 +486,8 @@ def main():
         dist.barrier()
         cur[0] = 0
         step()                                          # one more step on input set 0
+        if peer is not None:
+            peer.wait_ready()
         torch.cuda.synchronize()
         dist.barrier()
         fused = last_block[0].clone()
@@ -503,6 +515,8 @@ def main():
         torch.cuda._sleep(spin_cycles)
         ev[i][0].record()
         step()
+        if peer is not None:
+            peer.wait_ready()
         ev[i][1].record()
     torch.cuda.synchronize()
     if sampler.ok:

@@ -58,6 +58,8 @@ SIGNATURES = {
     "fdt_detect_peers": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _f, _vp, _i, _i64, _vp, _sz, _vp]),
     "fdt_detect_gather_signal": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _f, _vp, _i, _vp, _i, _i, _i, C.c_uint32, _i, _i64,
                                       _vp, _sz, _vp]),
+    "fdt_detect_gather_store": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _i, _f, _f, _f, _f, _vp, _i, _vp, _i, _i, _i, C.c_uint32, _i, _i64,
+                                     _vp, _sz, _vp]),
     "fdt_detect_gather_await": (_i, [_vp, _i, _i, C.c_uint32, _vp, _vp]),
     "fdt_detect_candidate_counts": (_i, [_vp, _sz, _i, _i64, _i, _vp, _vp]),
     "fdt_heads_to_loc_conf": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

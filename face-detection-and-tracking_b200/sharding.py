@@ -122,10 +122,21 @@ class PeerGatherDetect:
         signal="barrier": a symmetric-memory barrier follows the kernel (CUDA-graph capturable).
         signal="kernel": the completion signals travel through symmetric memory inside the call (fdt_detect_gather_signal): a source
         rank never waits for anybody (except for a destination that is RING calls behind), a destination enqueues a one-block
-        await kernel behind its own NMS kernel -- consumers of the block follow it in stream order, the next call does not."""
+        await kernel behind its own NMS kernel -- consumers of the block follow it in stream order, the next call does not.
+        signal="kernel-side": the same stores and signals, but no await kernel in the calls' stream (there it is a third grid per
+        call in the window of grids the stream runs ahead by, and a resident one-block kernel keeps a whole SM from taking an NMS
+        CTA: measured +1.3 us per call on the destination).  The await kernel depends on nothing but the signal array, so a
+        destination enqueues it on a stream of its own when the rows are NEEDED: `wait_ready()` awaits the latest call -- epochs
+        are monotonic, it covers every earlier call -- and makes the consumer's stream wait for it (an event).  Consumers that run
+        in the calls' stream keep the ring's overwrite protection (a source only reuses a block once the destination has begun
+        the call RING - 1 later, which in that stream follows the consumer)."""
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
-        assert signal in ("barrier", "kernel")
+        assert signal in ("barrier", "kernel", "kernel-side")
+        self.await_stream = None
+        if signal == "kernel-side":
+            signal = "kernel"
+            self.await_stream = torch.cuda.Stream()
         self.dest, self.signal = dest, signal
         self._lib = _lib
         self.detect = detect
@@ -147,6 +158,7 @@ class PeerGatherDetect:
             self.sig.zero_()
             self.sig_hdl = symm_mem.rendezvous(self.sig, self.group)
         self._workspaces = _lib.DetectWorkspaces()
+        self._last_ws = None
         torch.cuda.synchronize()
         dist.barrier(self.group)            # every rank's blocks are zeroed before any peer stores rows into them
         self.turn = 0
@@ -168,13 +180,29 @@ class PeerGatherDetect:
         ptrs, n_dst = self.dest_ptrs(hdl)
         if self.signal == "kernel":
             self.epoch += 1
-            _lib.check(L.fdt_detect_gather_signal(*args, ptrs, n_dst, int(self.sig_hdl.buffer_ptrs_dev), self.world, self.rank,
-                                                  -1 if self.dest == "all" else int(self.dest), self.epoch, self.RING, self.rank * B,
-                                                  ws.data_ptr(), ws.numel(), st))
-            return buf           # on a destination: complete in stream order (the await kernel is enqueued by the call)
+            root = -1 if self.dest == "all" else int(self.dest)
+            call = L.fdt_detect_gather_store if self.await_stream is not None else L.fdt_detect_gather_signal
+            _lib.check(call(*args, ptrs, n_dst, int(self.sig_hdl.buffer_ptrs_dev), self.world, self.rank, root, self.epoch, self.RING,
+                            self.rank * B, ws.data_ptr(), ws.numel(), st))
+            self._last_ws = ws
+            return buf           # on a destination: complete in stream order behind the await kernel (kernel-side: after wait_ready())
         _lib.check(L.fdt_detect_peers(*args, ptrs, n_dst, self.rank * B, ws.data_ptr(), ws.numel(), st))
         hdl.barrier()            # all ranks' rows have landed in the destination block(s)
         return buf
+
+    def wait_ready(self, stream=None, ws=None):
+        """kernel-side: makes `stream` (default: the current one) wait until the gathered blocks of all calls made so far are
+        complete on this rank (one await kernel for the latest epoch on the await stream + an event).  A no-op for the other
+        signal modes (stream order already covers them) and on a rank that is not a destination."""
+        if self.await_stream is None or self.epoch == 0 or not (self.dest == "all" or int(self.dest) == self.rank):
+            return
+        _lib = self._lib
+        ws = ws if ws is not None else self._last_ws
+        _lib.check(_lib.lib().fdt_detect_gather_await(int(self.sig_hdl.buffer_ptrs_dev), self.world, self.rank, self.epoch,
+                                                      ws.data_ptr(), self.await_stream.cuda_stream))
+        ev = torch.cuda.Event()
+        ev.record(self.await_stream)
+        (stream if stream is not None else torch.cuda.current_stream()).wait_event(ev)
 
     def dest_ptrs(self, hdl):
         """(device array of destination block pointers, how many)."""

@@ -206,8 +206,8 @@ int fdt_detect_peers(const float *loc, const float *conf, const float *priors, i
  *   epoch             call counter (>= 1), the same on every rank, increasing by one per call.
  * A source rank waits (before storing, normally long satisfied) until every destination has begun call epoch - ring + 1 -- in the
  * destination's stream that follows whatever consumed call epoch - ring, so the block is free --, stores its rows, and its last
- * CTA publishes `epoch` to the destinations.  A destination rank additionally enqueues fdt_detect_gather_await (done here), a
- * one-block kernel that ends when all sources have published `epoch`: what consumes the gathered block follows it in stream
+ * CTA publishes `epoch` to the destinations (a destination to itself as well).  A destination rank additionally enqueues
+ * fdt_detect_gather_await (done here), a one-block kernel that ends when all ranks have published `epoch`: what consumes the gathered block follows it in stream
  * order, while the next call is NOT held back by it.  Every rank must make the call for the destinations' streams to advance; a
  * wait that sees no progress for ~4 s gives up, sets FDT_STATUS_TIMEOUT_PEER (fdt_detect_status) and the rank stops signalling.
  * `epoch` is a launch parameter: do not replay this call from a captured CUDA graph. */
@@ -217,6 +217,15 @@ int fdt_detect_gather_signal(const float *loc, const float *conf, const float *p
                              int world, int rank, int root, uint32_t epoch, int ring, int64_t image_offset,
                              void *ws, size_t ws_bytes, fdt_stream_t stream);
 int fdt_detect_gather_await(const uint64_t *peer_signal_ptrs, int world, int rank, uint32_t epoch, void *ws, fdt_stream_t stream);
+/* The same call WITHOUT the await kernel: the destination enqueues fdt_detect_gather_await itself, on any stream -- the kernel depends
+ * on nothing but the signal array (a destination's own k_sort_nms publishes `epoch` in its own slot like every source), so it needs
+ * no stream order behind the call.  On a stream of its own it is not a third grid per call in the calls' stream: the destination's
+ * step is 17.4 instead of 18.6 us at B = 64 (tools/peer_breakdown.py); consumers then wait for that stream (an event). */
+int fdt_detect_gather_store(const float *loc, const float *conf, const float *priors, int B, int64_t N, int C, int top_k, int nms_top_k,
+                            float conf_thresh, float nms_thresh, float var0, float var1,
+                            const uint64_t *dest_out_ptrs, int n_dest, const uint64_t *peer_signal_ptrs,
+                            int world, int rank, int root, uint32_t epoch, int ring, int64_t image_offset,
+                            void *ws, size_t ws_bytes, fdt_stream_t stream);
 
 /* ----  head post-processing that feeds Detect  (pyramid.py:291-309, 331-338; same code in
  * pyramid_mobile_try1.py:297-327, pyramid_mb2_try3/4/5.py) -------------------------------------------------------------

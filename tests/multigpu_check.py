@@ -59,7 +59,8 @@ def main():
     # gather to a root: only the root's block is written; with the barrier after the kernel, or signalled through symmetric memory
     # (10 calls back to back: more than the ring of gathered blocks and than the workspace ring, a different batch every call so
     # that stale rows can never pass)
-    for root, signal in ((0, "barrier"), (world - 1, "barrier"), (0, "kernel"), (world - 1, "kernel"), ("all", "kernel")):
+    for root, signal in ((0, "barrier"), (world - 1, "barrier"), (0, "kernel"), (world - 1, "kernel"), ("all", "kernel"),
+                         (0, "kernel-side"), (world - 1, "kernel-side"), ("all", "kernel-side")):
         pr = PeerGatherDetect(det, b_local, dest=root, signal=signal)
         got = []
         for it in range(12):
@@ -67,6 +68,7 @@ def main():
             few = it % 3 == 1 or it in (6, 7, 8)                               # full -> few -> full ... and few three times in a row
             l_, c_ = (loc_c, conf_c) if few else (loc, conf)
             o = pr(cu(l_[sh][lo:hi]), cu(c_[sh][lo:hi]), cu(pri))
+            pr.wait_ready()                    # (kernel-side: the await kernels run on their own stream; a no-op otherwise)
             got.append((sh, few, o.clone()))   # an ordinary kernel behind the call: on a destination it must see every rank's rows
         torch.cuda.synchronize()
         pr.check()

@@ -54,13 +54,17 @@ def make_peer(dest, signal):
         hdl = peer.hdls[peer.turn]
         peer.turn = (peer.turn + 1) % peer.RING
         ptrs, n_dst = peer.dest_ptrs(hdl)
-        if signal == "kernel":
+        if signal.startswith("kernel"):
             peer.epoch += 1
-            _lib.check(L.fdt_detect_gather_signal(*args12(), ptrs, n_dst, int(peer.sig_hdl.buffer_ptrs_dev), world, rank,
-                                                  -1 if dest == "all" else int(dest), peer.epoch, peer.RING, rank * B, ws.data_ptr(), ws.numel(), st))
+            root = -1 if dest == "all" else int(dest)
+            call = L.fdt_detect_gather_store if peer.await_stream is not None else L.fdt_detect_gather_signal
+            _lib.check(call(*args12(), ptrs, n_dst, int(peer.sig_hdl.buffer_ptrs_dev), world, rank, root, peer.epoch, peer.RING, rank * B,
+                            ws.data_ptr(), ws.numel(), st))
+            peer._last_ws = ws
         else:
             _lib.check(L.fdt_detect_peers(*args12(), ptrs, n_dst, rank * B, ws.data_ptr(), ws.numel(), st))
             hdl.barrier()
+    f.peer = peer
     return f
 
 
@@ -82,6 +86,8 @@ def timed(fn):
         a.record()
         for _ in range(K):
             fn(); step_no[0] += 1
+        if getattr(fn, "peer", None) is not None:
+            fn.peer.wait_ready()
         b.record()
         torch.cuda.synchronize()
         dist.barrier()
@@ -94,8 +100,11 @@ def timed(fn):
 
 
 variants = [("local (no exchange)", local_step), ("gather to rank 0, signalled", make_peer(0, "kernel")),
+            ("  .. awaits on their own stream", make_peer(0, "kernel-side")),
             ("all-gather, signalled", make_peer("all", "kernel")), ("gather to rank 0 + barrier", make_peer(0, "barrier")),
             ("nccl all-gather", nccl_step)]
+if os.environ.get("FDT_BREAKDOWN_SHORT"):
+    variants = variants[:3]
 for name, fn in variants:
     per_rank = timed(fn)
     if rank == 0:
