@@ -101,3 +101,28 @@ def test_header_is_plain_c99(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-fsyntax-only", str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_pack_targets_layout():
+    """MultiBoxLoss target packing (layers/modules/multibox_loss.py): list[B] of [G_i,5] -> gt[total,5] fp32 + int64 offsets; images
+    without boxes get an empty range, other dtypes / shapes take the converting path, an all-empty batch a 1-row placeholder."""
+    from fdt_b200.layers.modules.multibox_loss import pack_targets
+    cpu = torch.device("cpu")
+    a = torch.arange(10, dtype=torch.float32).reshape(2, 5)
+    b = torch.zeros((0, 5), dtype=torch.float32)
+    c = torch.arange(15, dtype=torch.float32).reshape(3, 5) + 100
+    gt, off, total = pack_targets([a, b, c], cpu)
+    assert total == 5 and off.dtype == torch.int64 and off.tolist() == [0, 2, 2, 5]
+    assert gt.dtype == torch.float32 and torch.equal(gt, torch.cat([a, c], 0))
+    gt3, off3, total3 = pack_targets([a.double(), None, c.double()], cpu)           # float64 and a missing entry
+    assert total3 == 5 and off3.tolist() == [0, 2, 2, 5] and gt3.dtype == torch.float32 and torch.equal(gt3, torch.cat([a, c], 0))
+    gt4, off4, total4 = pack_targets([b, None], cpu)
+    assert total4 == 0 and off4.tolist() == [0, 0, 0] and tuple(gt4.shape) == (1, 5)
+
+
+def test_multibox_workspace_grows_with_the_batch_and_stays_aligned():
+    L = _lib.lib()
+    w1 = L.fdt_multibox_workspace_bytes(1, 34125, 2, 10)
+    w32 = L.fdt_multibox_workspace_bytes(32, 34125, 2, 3000)
+    assert 0 < w1 < w32 and w1 % 256 == 0 and w32 % 256 == 0
+    assert L.fdt_multibox_workspace_bytes(0, 0, 2, 0) == 256
