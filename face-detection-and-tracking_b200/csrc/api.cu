@@ -13,7 +13,7 @@ void fdt_set_error(const char *fmt, ...)
     va_end(ap);
 }
 
-FDT_API int fdt_version(void) { return 200; }
+FDT_API int fdt_version(void) { return 210; }
 FDT_API const char *fdt_last_error(void) { return g_err; }
 
 FDT_API int fdt_device_check(int device)
