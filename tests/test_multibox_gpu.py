@@ -371,3 +371,45 @@ def test_fused_forward_bipartite_shared_best_priors():
     sel, pos = check_fused(loc, conf, pri, targets, 1)
     r = orc.multibox_loss(loc, conf, pri, targets, 0.35, 3, True, VAR)
     assert pos.sum() > (orc.multibox_loss(loc, conf, pri, targets, 0.35, 3, False, VAR)["conf_t"] > 0).sum()    # forced matches exist
+
+
+@pytest.mark.parametrize("bip", [0, 1])
+def test_fused_forward_under_cuda_graph_capture(bip):
+    """The forward is a chain of programmatically-dependent launches without a memset node or a host read: it can be captured into
+    a CUDA graph and replayed (new logits in the same buffers between replays)."""
+    from fdt_b200 import _lib
+    from fdt_b200.layers.modules.multibox_loss import pack_targets
+    dev = torch.device("cuda", torch.cuda.current_device())
+    pri = synth.priors_numpy(320, 320)
+    loc, conf, targets = synth.multibox_inputs(4, pri, 2024, 2, 40)
+    loc2, conf2, _ = synth.multibox_inputs(4, pri, 2025, 2, 40)
+    B, N, Cn = conf.shape
+    l, c, p = cu(loc), cu(conf), cu(pri)
+    gt, off, total = pack_targets([cu(t) for t in targets], dev)
+    losses = torch.zeros(2, device=dev); norm = torch.zeros(1, device=dev)
+    loc_t = torch.empty((B, N, 4), device=dev); conf_t = torch.empty((B, N), dtype=torch.int64, device=dev)
+    sel = torch.empty((B, N), dtype=torch.uint8, device=dev)
+    L = _lib.lib()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        ws = torch.empty(L.fdt_multibox_workspace_bytes(B, N, Cn, total), dtype=torch.uint8, device=dev)
+
+        def fwd():
+            _lib.check(L.fdt_multibox_loss_forward(l.data_ptr(), c.data_ptr(), p.data_ptr(), gt.data_ptr(), off.data_ptr(), total, B, N, Cn,
+                                                   0.35, 3, bip, VAR[0], VAR[1], losses.data_ptr(), norm.data_ptr(), loc_t.data_ptr(),
+                                                   conf_t.data_ptr(), sel.data_ptr(), None, ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+        fwd()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            fwd()
+    for lo_, co_ in ((loc, conf), (loc2, conf2), (loc, conf)):
+        l.copy_(cu(lo_)); c.copy_(cu(co_))
+        losses.zero_(); sel.zero_()
+        torch.cuda.synchronize()
+        g.replay()
+        torch.cuda.synchronize()
+        r = orc.multibox_loss(lo_, co_, pri, targets, 0.35, 3, bool(bip), VAR)
+        assert np.array_equal(npy(conf_t), r["conf_t"])
+        assert np.array_equal(npy(sel).astype(bool), r["neg"] | (r["conf_t"] > 0))
+        np.testing.assert_allclose(npy(losses), [r["loss_l"], r["loss_c"]], rtol=1e-5)
