@@ -724,7 +724,7 @@ k_best_prior(const float4 *__restrict__ priors, const int64_t N, const float *__
 }
 
 // The forward in ONE kernel per prior: match (k_match_default's core), label + encode of the positives, and -- once
-// k_mbl_prepare's maximum is there -- the loss terms and the mining histogram of k_loss_prior on the values still in registers.
+// k_mbl_prepare's maximum is there -- the loss terms (multibox_loss.py:96-110) and the mining histogram on the values still in registers.
 // The matcher is bound by instruction issue and the loss terms by fp64 latency; in one kernel the warps of both phases share every
 // SM, and conf_t / loc_t are not read back.  BIP: the bipartite matcher (box_utils.py:103-162) -- the same per-prior arg max (the
 // area bound stays valid: a forced match overrides whatever it found, every other prior is labelled by `best >= thr` alone), then
