@@ -590,7 +590,7 @@ def main():
 
     # ---- end to end through the public API with pinned host tensors
     loc_h, conf_h, pri_h = (torch.from_numpy(a).pin_memory() for a in (loc_np, conf_np, pri_np))
-    IN_FLIGHT = 2
+    IN_FLIGHT = int(os.environ.get("FDT_BENCH_IN_FLIGHT", "2"))
 
     def e2e_stream(steps):
         """`steps` batches through Detect.submit with IN_FLIGHT of them in flight; every batch's copies, kernels and results are
