@@ -413,3 +413,12 @@ def test_fused_forward_under_cuda_graph_capture(bip):
         assert np.array_equal(npy(conf_t), r["conf_t"])
         assert np.array_equal(npy(sel).astype(bool), r["neg"] | (r["conf_t"] > 0))
         np.testing.assert_allclose(npy(losses), [r["loss_l"], r["loss_c"]], rtol=1e-5)
+
+
+def test_fused_forward_bipartite_large_prior_set():
+    """196,000 priors (1536 x 1536, 192 super-tiles of 1,024 priors): the two-level search of k_best_prior over more than one round
+    of 32 super-tiles per warp."""
+    pri = synth.priors_numpy(1536, 1536)
+    assert pri.shape[0] > 170_000
+    loc, conf, targets = synth.multibox_inputs(1, pri, 4242, 25, 25)
+    check_fused(loc, conf, pri, targets, 1)
